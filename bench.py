@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 hot path (contract: see DESIGN.md "Measurement").
+
+One "step" = one pass of the RRC matched-filter FIR sweep (BASELINE.json configs[1]):
+real-tap RRC filters of 33, 65, 129 and 257 taps (span 16, sps 2/4/8/16, alpha 0.35) applied as
+streaming ComplexFIRFilter.Filter() over 2^28 synthetic complex samples (uniform(-1,1) from the
+counter RNG, seed 1), i.e. 4 kernel launches per step.  Inputs (2 GiB) and outputs (2 GiB) are far
+larger than the 126 MB L2, so no flush is needed between iterations.
+
+  value   Msamples/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e     the same sweep through the host-pointer C ABI call (qpsk_fir_filter) with pinned host
+          buffers: H2D + kernel + D2H inside the timed region
+  roofline the launch that dominates the step (257 taps: FP32-FMA bound) + one entry per tap count
+  cpu_baseline the oracle's C++ restatement of the C# SIMD FIR on the host cores (bounded sample)
+
+`--impl reference` times that CPU restatement alone (the C# reference cannot run here: no .NET).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TAPS = [(16, 2), (16, 4), (16, 8), (16, 16)]  # (span, sps) -> 33, 65, 129, 257 taps
+ALPHA = 0.35
+LOG2_SAMPLES = 28
+METRIC = "Msamples/s RRC FIR sweep (taps 33-257) on 2^28 cf32 samples"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # under load = the upper half of the samples (idle samples before/after the region are lower)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": (max(mx) if mx else None),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def taps_for(orc_or_q, span, sps):
+    h = orc_or_q.RRCFilter.generateCoefficents(span, ALPHA, sps * 1000, 1000)
+    return orc_or_q.real_taps_to_iq(h)
+
+
+def cpu_baseline(n_each_log2: int = 20):
+    """Oracle port of the C# SIMD FIR (FIRFilter.cs:59-91,144-211) on all host cores: one independent
+    stream per core, each 2^n_each_log2 samples per tap count."""
+    import numpy as np
+    import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    n_each = 1 << n_each_log2
+    x = O.fill_uniform(1, 0, 0, 2 * n_each * cores)
+    y = np.empty_like(x)
+    t_total = 0.0
+    per = {}
+    for span, sps in TAPS:
+        taps = taps_for(O, span, sps)
+        t0 = time.perf_counter()
+        O.fir_filter_mt(taps, x, y, 2 * n_each, cores)
+        dt = time.perf_counter() - t0
+        per[taps.size // 2] = n_each * cores / dt / 1e6
+        t_total += dt
+    # single thread, what the reference library itself uses
+    t1 = 0.0
+    n1 = 1 << max(n_each_log2 - 1, 10)
+    for span, sps in TAPS:
+        taps = taps_for(O, span, sps)
+        t0 = time.perf_counter()
+        O.fir_filter_mt(taps, x, y, 2 * n1, 1)
+        t1 += time.perf_counter() - t0
+    return {
+        "value": len(TAPS) * n_each * cores / t_total / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+        "sample": f"{cores} independent streams x 2^{n_each_log2} samples x taps {{33,65,129,257}}, C++ AVX2 restatement of "
+                  f"the C# SIMD FIR (no .NET in this image)",
+        "single_thread_value": len(TAPS) * n1 / t1 / 1e6,
+        "per_taps": per, "seconds": t_total + t1,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all, vals = [], []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        b = cpu_baseline(19)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            vals.append(b["value"]); t_all.append(dt)
+    v = sum(vals) / len(vals)
+    b["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_all) / len(t_all), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fir_sweep taps{33,65,129,257} (bounded sample per step: cores x 2^19 samples per tap count)"},
+        "cpu_baseline": b,
+        "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-samples", type=int, default=LOG2_SAMPLES)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-chain", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from qpsk_modulator_demodulator_b200 import build as qbuild
+    if rank == 0:
+        qbuild.build()
+    if world > 1:
+        dist.barrier()
+    import qpsk_modulator_demodulator_b200 as Q
+    Q.set_device(local)
+
+    n = 1 << args.log2_samples
+    stream = torch.cuda.current_stream().cuda_stream
+    x = torch.empty(2 * n, dtype=torch.float32, device="cuda")
+    y = torch.empty(2 * n, dtype=torch.float32, device="cuda")
+    Q.fill_uniform_dev(1, rank, 0, 2 * n, x.data_ptr(), stream)
+    filters = []
+    for span, sps in TAPS:
+        t = taps_for(Q, span, sps)
+        filters.append((t.size // 2, Q.ComplexFIRFilter(t)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(ev=None):
+        for i, (nt, f) in enumerate(filters):
+            if ev is not None:
+                ev[i][0].record()
+            f.filter_dev(x.data_ptr(), y.data_ptr(), 2 * n, stream=stream)
+            if ev is not None:
+                ev[i][1].record()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    fma_peak = Q.measure_fma_peak()
+    barrier()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in filters]
+           for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Q.launch_count_reset()
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        step(evs[k])
+    e1.record()
+    barrier()
+    launches = Q.launch_count()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    per_ms = [sum(evs[k][i][0].elapsed_time(evs[k][i][1]) for k in range(args.steps)) / args.steps for i in range(len(filters))]
+
+    hbm_peak, peak_src = peaks()
+    roofs = []
+    for (nt, _), t in zip(filters, per_ms):
+        gbs = 16.0 * n / (t * 1e-3) / 1e9
+        tf = 4.0 * nt * n / (t * 1e-3) / 1e12
+        bound = "hbm" if (16.0 * n / (hbm_peak * 1e9)) >= (4.0 * nt * n / (fma_peak * 1e12)) else "fma"
+        roofs.append({"taps": nt, "ms": t, "msamples_s": n / (t * 1e-3) / 1e6, "bound": bound,
+                      "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "fma_tflops": tf, "fma_frac": tf / fma_peak,
+                      "frac": (gbs / hbm_peak) if bound == "hbm" else (tf / fma_peak)})
+    dom = max(roofs, key=lambda r: r["ms"])
+    roofline = {
+        "kernel": "fir_tma_kernel<R=10,NT=256,real taps>", "taps": dom["taps"], "bound": dom["bound"],
+        "achieved": dom["hbm_gbs"] if dom["bound"] == "hbm" else dom["fma_tflops"],
+        "peak": hbm_peak if dom["bound"] == "hbm" else fma_peak,
+        "unit": "GB/s" if dom["bound"] == "hbm" else "TFLOP/s",
+        "frac": dom["frac"], "traffic": None,
+        "peak_source": (f"HBM {peak_src} (MEASURED_PEAKS.json)" if dom["bound"] == "hbm"
+                        else "FP32 FMA peak measured in this run by qpsk_measure_fma_peak (FFMA2 micro-benchmark)"),
+        "algorithmic": "16 B and 4*taps flop per complex sample (DESIGN.md)",
+    }
+
+    # ---- e2e: host-pointer C ABI with pinned buffers -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hin = Q.PinnedBuffer(2 * n)
+        hout = Q.PinnedBuffer(2 * n)
+        xin = x.cpu().numpy() if False else None
+        torch.cuda.synchronize()
+        # fill the pinned input from the device copy (untimed)
+        import ctypes as C
+        torch.from_numpy(hin.array).copy_(x)
+        for _, f in filters:
+            f.reset()
+        k_e2e = max(1, min(args.steps, 3))
+        for _, f in filters[:1]:
+            f.Filter(hin.array[: 1 << 20], hout.array[: 1 << 20])
+            f.reset()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            for _, f in filters:
+                f.Filter(hin.array, hout.array)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dt = float(t_e.item())
+        e2e = {"value": world * k_e2e * len(filters) * n / dt / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": len(filters) * 8 * n, "d2h_bytes_per_step": len(filters) * 8 * n,
+               "steps": k_e2e, "api": "qpsk_fir_filter (host pointers, pinned, chunked H2D/kernel/D2H pipeline)"}
+        hin.free(); hout.free()
+
+    chain = None
+    if not args.no_chain:
+        try:
+            from bench_chain import run_chain  # optional: config 3 (batched demod chain)
+            chain = run_chain(Q, world, rank, local, dist if world > 1 else None)
+        except ImportError:
+            chain = None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(20)
+
+    if rank == 0:
+        total_samples = world * args.steps * len(filters) * n
+        line = {
+            "metric": METRIC, "value": total_samples / (ms_max * 1e-3) / 1e6, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"fir_sweep: streaming real-tap RRC FIR, taps {{33,65,129,257}}, 2^{args.log2_samples} cf32 samples "
+                                   f"per GPU per tap count (BASELINE.json configs[1])",
+                       "l2": "inputs 2 GiB + outputs 2 GiB per launch >> 126 MB L2; no flush needed",
+                       "parallelism": f"{world} independent streams, one per GPU, no collective"},
+            "roofline": roofline, "roofline_by_taps": roofs, "fma_peak_tflops_measured": fma_peak,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        }
+        if chain is not None:
+            line["chain"] = chain
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,246 @@
+/* qpskcuda.h — C ABI of libqpskcuda.so, the B200 (sm_100a) hot path behind the C# QPSK modem
+ * NustyFrozen/QPSK-Modulator-Demodulator.
+ *
+ * The reference has no FFI of its own: the boundary is its public C# class surface
+ * (SURVEY.md §8b).  Every entry point below names the reference member it stands in for
+ * ("MS/" = Modulation-Simulation/, "TB/" = TestBench/).  INTEGRATION.md shows the
+ * [DllImport("qpskcuda")] stubs a maintainer adds to those classes.
+ *
+ * Conventions
+ *   - samples are interleaved float IQ ([I0,Q0,I1,Q1,...]) exactly like the C# spans; lengths
+ *     named n_floats count floats (2 per complex sample), like Span<float>.Length.
+ *   - every function returns a status (0 ok, <0 error).  The negative codes map 1:1 onto the
+ *     exceptions the reference throws at the same place.
+ *   - handles are opaque, own their device state and CUDA streams, and are not thread-safe
+ *     (the reference objects are not either); different handles may be used concurrently.
+ *   - "host" entry points take host pointers and copy through the device inside the call;
+ *     "_dev" entry points take device pointers (16-byte aligned) and enqueue on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the handle's own stream) without synchronising.
+ *   - there is no CPU fallback: without a CUDA device every compute call returns
+ *     QPSK_ERR_NO_DEVICE / QPSK_ERR_CUDA.
+ */
+#ifndef QPSKCUDA_H_
+#define QPSKCUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define QPSK_API __declspec(dllexport)
+#else
+#define QPSK_API __attribute__((visibility("default")))
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------ */
+#define QPSK_OK 0
+#define QPSK_ERR_NULL (-1)        /* ArgumentNullException                                       */
+#define QPSK_ERR_ARG (-2)         /* ArgumentException (odd IQ length, empty taps, short output) */
+#define QPSK_ERR_RANGE (-3)       /* ArgumentOutOfRangeException (bad design parameter)          */
+#define QPSK_ERR_CUDA (-4)        /* a CUDA runtime call failed; see qpsk_last_cuda_error()      */
+#define QPSK_ERR_NOMEM (-5)       /* host or device allocation failed                            */
+#define QPSK_ERR_CAPACITY (-6)    /* caller buffer too small; the needed size is reported        */
+#define QPSK_ERR_UNSUPPORTED (-7) /* outside the limits stated in DESIGN.md                      */
+#define QPSK_ERR_NO_DEVICE (-8)   /* no CUDA device / wrong architecture                         */
+
+typedef struct qpsk_fir qpsk_fir;
+typedef struct qpsk_fll qpsk_fll;
+typedef struct qpsk_mm qpsk_mm;
+typedef struct qpsk_costas qpsk_costas;
+typedef struct qpsk_mod qpsk_mod;
+typedef struct qpsk_demod qpsk_demod;
+typedef struct qpsk_chan qpsk_chan;
+
+/* ---- library / device -------------------------------------------------------------------- */
+QPSK_API int qpsk_version(void);                       /* 10000*major + 100*minor + patch         */
+QPSK_API const char* qpsk_strerror(int status);
+QPSK_API const char* qpsk_last_cuda_error(void);       /* thread-local text of the last CUDA error */
+QPSK_API int qpsk_device_count(int* n);
+QPSK_API int qpsk_set_device(int ordinal);             /* device used by handles created afterwards */
+QPSK_API int qpsk_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
+/* pinned host memory so host entry points overlap PCIe copies with kernels (optional) */
+QPSK_API int qpsk_host_alloc(void** p, int64_t bytes);
+QPSK_API int qpsk_host_free(void* p);
+/* launches of this library's kernels issued by the calling thread since the last reset */
+QPSK_API int64_t qpsk_launch_count(void);
+QPSK_API void qpsk_launch_count_reset(void);
+
+/* ---- a1  RRCFilter.generateCoefficents  (MS/Models/RRC-filter.cs:16-75) ------------------- */
+/* host-side fp64 design.  out==NULL or cap too small: *n is still set (size query). */
+QPSK_API int qpsk_rrc_taps(double span_symbols, double beta, int sample_rate, int symbol_rate,
+                           double* out, int cap, int* n);
+
+/* ---- a2-a5  ComplexFIRFilter  (MS/Models/FIRFilter.cs:8-232) ------------------------------ */
+#define QPSK_FIR_FAST 0   /* fp32 FMA accumulation (default)                                      */
+#define QPSK_FIR_EXACT 1  /* the reference's summation order: 8 lane partials, no FMA (:165-192) */
+/* ctor :29-53.  taps_iq interleaved complex taps; n_floats even and > 0. */
+QPSK_API int qpsk_fir_create(const float* taps_iq, int n_floats, qpsk_fir** out);
+/* the same filter over `channels` independent streams, one (N-1)-sample history each */
+QPSK_API int qpsk_fir_create_batch(const float* taps_iq, int n_floats, int channels, qpsk_fir** out);
+QPSK_API int qpsk_fir_destroy(qpsk_fir* f);
+QPSK_API int qpsk_fir_reset(qpsk_fir* f);                      /* zero the delay line(s)          */
+QPSK_API int qpsk_fir_set_mode(qpsk_fir* f, int mode);
+QPSK_API int qpsk_fir_num_taps(const qpsk_fir* f, int* n_complex);
+/* Filter(ReadOnlySpan<float>, Span<float>) :80-91 — streaming, same length, history kept.
+ * out_cap_floats < n_floats -> QPSK_ERR_ARG (:83); odd n_floats -> QPSK_ERR_ARG (:82).
+ * Batch handles: in/out are [channels][n_floats] contiguous. */
+QPSK_API int qpsk_fir_filter(qpsk_fir* f, const float* iq_in, float* iq_out, int64_t n_floats,
+                             int64_t out_cap_floats);
+/* fftFilter(float[]) :96-141 — stateless, y[i] = conv(x,h)[i + N-1], i < n. */
+QPSK_API int qpsk_fir_fft_filter(qpsk_fir* f, const float* iq_in, float* iq_out, int64_t n_floats);
+/* device-resident variants; strides are in floats between consecutive channels */
+QPSK_API int qpsk_fir_filter_dev(qpsk_fir* f, const float* d_in, float* d_out, int64_t n_floats,
+                                 int64_t in_stride_floats, int64_t out_stride_floats, void* stream);
+QPSK_API int qpsk_fir_fft_filter_dev(qpsk_fir* f, const float* d_in, float* d_out, int64_t n_floats,
+                                     int64_t in_stride_floats, int64_t out_stride_floats, void* stream);
+/* delay-line checkpoint: the last N-1 inputs per channel, oldest first, [channels][2*(N-1)] */
+QPSK_API int qpsk_fir_get_state(qpsk_fir* f, float* hist_iq, int64_t cap_floats);
+QPSK_API int qpsk_fir_set_state(qpsk_fir* f, const float* hist_iq, int64_t n_floats);
+
+/* ---- a7-a8  FLLBandEdgeFilter  (MS/Models/Band-Edge Filter.cs:14-203) ---------------------- */
+/* DesignFilter :132-183, host-side fp32.  lower/upper: 2*filter_size floats each. */
+QPSK_API int qpsk_fll_design(float sps, float rolloff, int filter_size, float* lower_iq, float* upper_iq);
+QPSK_API int qpsk_fll_create(float sps, float rolloff, int filter_size, float bandwidth, qpsk_fll** out);
+QPSK_API int qpsk_fll_create_batch(float sps, float rolloff, int filter_size, float bandwidth,
+                                   int channels, qpsk_fll** out);
+QPSK_API int qpsk_fll_destroy(qpsk_fll* f);
+/* Process(ReadOnlySpan<float>, Span<float>) :64-87 */
+QPSK_API int qpsk_fll_process(qpsk_fll* f, const float* iq_in, float* iq_out, int64_t n_floats,
+                              int64_t out_cap_floats);
+QPSK_API int qpsk_fll_process_dev(qpsk_fll* f, const float* d_in, float* d_out, int64_t n_floats,
+                                  int64_t in_stride_floats, int64_t out_stride_floats, void* stream);
+/* public fields phase/freq :25-26, per channel */
+QPSK_API int qpsk_fll_get_state(qpsk_fll* f, float* phase, float* freq);
+QPSK_API int qpsk_fll_set_state(qpsk_fll* f, const float* phase, const float* freq);
+
+/* ---- a9  MuellerMuller  (MS/Models/MuellerMuller.cs:17-250) -------------------------------- */
+QPSK_API int qpsk_mm_create(double samples_per_symbol, double kp, double ki, qpsk_mm** out);
+QPSK_API int qpsk_mm_create_batch(double samples_per_symbol, double kp, double ki, int channels, qpsk_mm** out);
+QPSK_API int qpsk_mm_destroy(qpsk_mm* m);
+/* Process(ReadOnlySpan<float>, Span<float>) :52-136.  n_sym: symbols written (per channel for
+ * batch handles: n_sym[channels], out is [channels][cap_floats]). */
+QPSK_API int qpsk_mm_process(qpsk_mm* m, const float* mf_iq_in, int64_t n_floats, float* sym_iq_out,
+                             int64_t cap_floats, int* n_sym);
+QPSK_API int qpsk_mm_process_dev(qpsk_mm* m, const float* d_in, int64_t n_floats, int64_t in_stride_floats,
+                                 float* d_out, int64_t cap_floats, int64_t out_stride_floats,
+                                 int* d_n_sym, void* stream);
+/* per channel: baseIndex, mu, ncoIntegral, queued complex samples */
+QPSK_API int qpsk_mm_get_state(qpsk_mm* m, int* base_index, double* mu, double* integral, int* queued);
+/* setupSymbolSync gains (MS/QPSKDeModulator.cs:39-55) */
+QPSK_API int qpsk_mm_gains_from_bw(double symbol_sync_bw, double* kp, double* ki);
+
+/* ---- a10  CostasLoopQpsk  (MS/Models/CostasLoopQpsk.cs:19-131) ------------------------------ */
+QPSK_API int qpsk_costas_create(double sample_rate, double loop_bw_hz, double damping, qpsk_costas** out);
+QPSK_API int qpsk_costas_create_batch(double sample_rate, double loop_bw_hz, double damping, int channels,
+                                      qpsk_costas** out);
+QPSK_API int qpsk_costas_destroy(qpsk_costas* c);
+/* Process(ReadOnlySpan<float>, Span<float>) :98-114 */
+QPSK_API int qpsk_costas_process(qpsk_costas* c, const float* iq_in, float* iq_out, int64_t n_floats,
+                                 int64_t out_cap_floats);
+/* batch/device: n_sym[channels] valid complex samples per channel (NULL = n_floats/2 for all) */
+QPSK_API int qpsk_costas_process_dev(qpsk_costas* c, const float* d_in, float* d_out, int64_t n_floats,
+                                     int64_t in_stride_floats, int64_t out_stride_floats,
+                                     const int* d_n_sym, void* stream);
+/* GetState() :130, per channel */
+QPSK_API int qpsk_costas_get_state(qpsk_costas* c, double* theta, double* freq);
+
+/* ---- a6  QPSKModulator  (MS/QPSKModulator.cs:18-168) ---------------------------------------- */
+/* tsc_bits: '0'/'1' string or NULL (null/whitespace = no TSC, :27) */
+QPSK_API int qpsk_mod_create(int sample_rate, int symbol_rate, double rrc_alpha, int rrc_span,
+                             int differential, const char* tsc_bits, qpsk_mod** out);
+QPSK_API int qpsk_mod_destroy(qpsk_mod* m);
+QPSK_API int qpsk_mod_taps(const qpsk_mod* m, double* out, int cap, int* n);       /* getCoeef() :32 */
+/* Modulate(string,bool) :104-167.  out==NULL: size query (*n_floats set). */
+QPSK_API int qpsk_mod_modulate_bits(qpsk_mod* m, const char* bits, int64_t n_bits, int pulse_shaping,
+                                    float* iq_out, int64_t cap_floats, int64_t* n_floats);
+/* ModulateBytes :54-72 (ModulateTextUtf8 :74-89 = this over UTF-8 bytes) */
+QPSK_API int qpsk_mod_modulate_bytes(qpsk_mod* m, const uint8_t* payload, int64_t n_payload,
+                                     const uint8_t* start_marker, int64_t n_start,
+                                     const uint8_t* end_marker, int64_t n_end, int pulse_shaping,
+                                     float* iq_out, int64_t cap_floats, int64_t* n_floats);
+/* batch, device-resident: `frames` payloads of n_payload bytes each ([frames][n_payload], device),
+ * each framed START|payload|END (+TSC), differential reference reset per frame (:126); writes
+ * [frames][frame_floats] to d_iq_out.  *frame_floats is set even when d_iq_out==NULL. */
+QPSK_API int qpsk_mod_modulate_frames_dev(qpsk_mod* m, const uint8_t* d_payloads, int64_t n_payload, int frames,
+                                          const uint8_t* start_marker, int64_t n_start,
+                                          const uint8_t* end_marker, int64_t n_end,
+                                          float* d_iq_out, int64_t out_stride_floats, int64_t* frame_floats,
+                                          void* stream);
+
+/* ---- a11-a12  QPSKDeModulator  (MS/QPSKDeModulator.cs:11-456) ------------------------------- */
+/* use_fll: 0 = as shipped (fll.Process commented out, :359/:435); 1 = run the FLL in front.
+ * max_frame_bytes: bound of the framer ring (the reference allocates 300 MB, :58); 0 = 1 MiB. */
+QPSK_API int qpsk_demod_create(int sample_rate, int symbol_rate, float rrc_alpha, int rrc_span,
+                               double symbol_sync_bw, double costas_loop_bw, double cfo_loop_bw,
+                               int differential, const char* tsc_bits, int use_fll,
+                               int64_t max_frame_bytes, qpsk_demod** out);
+QPSK_API int qpsk_demod_create_batch(int sample_rate, int symbol_rate, float rrc_alpha, int rrc_span,
+                                     double symbol_sync_bw, double costas_loop_bw, double cfo_loop_bw,
+                                     int differential, const char* tsc_bits, int use_fll,
+                                     int64_t max_frame_bytes, int channels, qpsk_demod** out);
+QPSK_API int qpsk_demod_destroy(qpsk_demod* d);
+QPSK_API int qpsk_demod_set_fir_mode(qpsk_demod* d, int mode);
+/* DeModulate(ReadOnlySpan<float>) :345-425 -> '0'/'1' chars (not NUL-terminated) */
+QPSK_API int qpsk_demod_bits(qpsk_demod* d, const float* iq_in, int64_t n_floats, char* bits_out,
+                             int64_t cap, int64_t* n_bits);
+/* DeModulateBytes :169-259 (DeModulateTextUtf8 :262-277 = this + UTF-8 decode) */
+QPSK_API int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_floats,
+                              const uint8_t* start_marker, int64_t n_start,
+                              const uint8_t* end_marker, int64_t n_end,
+                              uint8_t* payload_out, int64_t cap, int64_t* n_bytes);
+/* deModulateConstellation :427-455 */
+QPSK_API int qpsk_demod_constellation(qpsk_demod* d, const float* iq_in, int64_t n_floats,
+                                      float* sym_iq_out, int64_t cap_floats, int64_t* n_sym);
+/* batch, device-resident chain: d_in [channels][n_floats] (stride in floats).  Outputs per
+ * channel: bits as bytes 0/1 ([channels][bits_cap], the DeModulate string after TSC strip),
+ * d_n_bits[channels].  Enqueued on `stream`, no synchronisation. */
+QPSK_API int qpsk_demod_bits_dev(qpsk_demod* d, const float* d_in, int64_t n_floats, int64_t in_stride_floats,
+                                 uint8_t* d_bits, int64_t bits_cap, int64_t* d_n_bits, void* stream);
+/* per-channel loop state after the last call */
+QPSK_API int qpsk_demod_loop_state(qpsk_demod* d, double* costas_theta, double* costas_freq, double* mm_mu,
+                                   double* mm_integral, float* fll_phase, float* fll_freq);
+
+/* ---- synthetic channel: NCO pair + AWGN + static multipath ------------------- */
+/* NCO: TB/Simulated/LocalOscilator.cs:5-194; noise: TB/HelperModels.cs:17-45; System.Random is
+ * replaced by the counter RNG of DESIGN.md.  Channel c uses RNG streams 4c (tx NCO), 4c+1 (rx NCO),
+ * 4c+2 (noise), 4c+3 (payload bits). */
+typedef struct qpsk_chan_params {
+  double tx_freq_hz, rx_freq_hz, sample_rate_hz;
+  double tx_ppm, rx_ppm, tx_phase0, rx_phase0;
+  float noise_dbfs;       /* <= -300: no noise                                                    */
+  int mode;               /* 0: x*(tx*conj(rx)) (testAtDataLevel.cs:39-42); 1: ((x+n)*tx)*conj(rx)
+                             (testFullDemodChain.cs:73)                                           */
+  int n_paths;            /* 0 = no multipath; else <= 4 paths                                    */
+  float path_gain_iq[8];
+  int path_delay[4];
+  uint64_t seed;
+} qpsk_chan_params;
+QPSK_API int qpsk_chan_create(const qpsk_chan_params* p, int channels, int first_channel, qpsk_chan** out);
+QPSK_API int qpsk_chan_destroy(qpsk_chan* c);
+/* y[c][n] = channel_c(x[c][n]); state (NCO phase, drift, counters) persists across calls.
+ * x_stride 0 = the same burst for every channel. */
+QPSK_API int qpsk_chan_apply_dev(qpsk_chan* c, const float* d_x, int64_t n_floats, int64_t x_stride_floats,
+                                 float* d_y, int64_t y_stride_floats, void* stream);
+QPSK_API int qpsk_chan_apply(qpsk_chan* c, const float* x, int64_t n_floats, float* y);
+/* uniform(-1,1) fp32 fill from the counter RNG: out[k] = (float)(2*u(seed,stream,first+k)-1) */
+QPSK_API int qpsk_fill_uniform_dev(uint64_t seed, uint64_t stream_id, int64_t first, int64_t n, float* d_out, void* stream);
+/* random payload bytes: out[c][k] = top byte of rng(seed, 4*(first_channel+c)+3, k) */
+QPSK_API int qpsk_fill_bytes_dev(uint64_t seed, int first_channel, int channels, int64_t n_bytes, uint8_t* d_out, void* stream);
+
+/* ---- K6  per-channel BER counters ---------------------------------------------------------- */
+/* bits as bytes 0/1.  errors[c] = Hamming distance over min(n_rx[c], n_ref) bits + |n_rx[c]-n_ref|;
+ * counters[c] = {errors, compared_bits}.  ref_stride 0 = one reference for all channels. */
+QPSK_API int qpsk_ber_count_dev(const uint8_t* d_rx_bits, int64_t rx_stride, const int64_t* d_n_rx,
+                                const uint8_t* d_ref_bits, int64_t ref_stride, int64_t n_ref,
+                                int channels, uint32_t* d_counters, void* stream);
+
+/* ---- measurement helpers ------------------------------------------------------------------- */
+/* FP32 FMA-pipe peak (TFLOP/s) by a register-resident FFMA micro-benchmark, for the roofline */
+QPSK_API int qpsk_measure_fma_peak(double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPSKCUDA_H_ */

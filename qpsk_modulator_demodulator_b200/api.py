@@ -1,0 +1,180 @@
+"""Host-side mirror of the reference's class surface over the C ABI (include/qpskcuda.h).
+
+Same class and method names, argument meaning and error behaviour as the C# classes
+(RRCFilter, ComplexFIRFilter, FLLBandEdgeFilter, MuellerMuller, CostasLoopQpsk, QPSKModulator,
+QPSKDeModulator), so the parity tests read like the reference's own usage.  numpy arrays stand in
+for Span<float>; `*_dev` methods take raw device pointers (e.g. torch.Tensor.data_ptr()).
+Everything computes on the GPU through libqpskcuda.so; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from ._native import (ArgumentException, ArgumentNullException, ArgumentOutOfRangeException, ChanParams,  # noqa: F401
+                      QpskCudaError, check, lib)
+
+FIR_FAST, FIR_EXACT = N.FIR_FAST, N.FIR_EXACT
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _bytes_arr(b) -> np.ndarray:
+    return np.frombuffer(bytes(b), dtype=np.uint8).copy() if len(b) else np.zeros(0, np.uint8)
+
+
+# ---- library / device ---------------------------------------------------------------------
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib().qpsk_device_count(C.byref(n)))
+    return n.value
+
+
+def set_device(ordinal: int):
+    check(lib().qpsk_set_device(ordinal))
+
+
+def device_info() -> dict:
+    sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    check(lib().qpsk_device_info(C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
+    return dict(sm_count=sm.value, cc=(ma.value, mi.value), hbm_bytes=mem.value)
+
+
+def launch_count() -> int:
+    return int(lib().qpsk_launch_count())
+
+
+def launch_count_reset():
+    lib().qpsk_launch_count_reset()
+
+
+def measure_fma_peak() -> float:
+    t = C.c_double(0)
+    check(lib().qpsk_measure_fma_peak(C.byref(t)))
+    return t.value
+
+
+class PinnedBuffer:
+    """qpsk_host_alloc'd float32 buffer exposed as a numpy array (what a C# caller would wrap in a Span)."""
+
+    def __init__(self, n_floats: int):
+        self._p = C.c_void_p()
+        check(lib().qpsk_host_alloc(C.byref(self._p), n_floats * 4))
+        self.array = np.ctypeslib.as_array(C.cast(self._p, N.f32p), shape=(n_floats,))
+
+    def free(self):
+        if self._p:
+            lib().qpsk_host_free(self._p)
+            self._p = None
+            self.array = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def fill_uniform_dev(seed: int, stream_id: int, first: int, n: int, d_out: int, stream: int = 0):
+    check(lib().qpsk_fill_uniform_dev(seed, stream_id, first, n, d_out, stream))
+
+
+# ---- a1 -------------------------------------------------------------------------------------
+class RRCFilter:
+    @staticmethod
+    def generateCoefficents(spanSymbols: float, beta: float, sampleRate: int, SymbolRate: int) -> np.ndarray:
+        n = C.c_int(0)
+        check(lib().qpsk_rrc_taps(spanSymbols, beta, sampleRate, SymbolRate, None, 0, C.byref(n)))
+        out = np.empty(max(n.value, 0), np.float64)
+        check(lib().qpsk_rrc_taps(spanSymbols, beta, sampleRate, SymbolRate, out.ctypes.data_as(N.f64p), n.value, C.byref(n)))
+        return out
+
+
+def real_taps_to_iq(h) -> np.ndarray:
+    """ToInterleavedIQRealTaps (MS/QPSKDeModulator.cs:278-288)."""
+    t = np.zeros(2 * len(h), np.float32)
+    t[0::2] = np.asarray(h, np.float64).astype(np.float32)
+    return t
+
+
+class _Handle:
+    _destroy = None
+
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    def close(self):
+        if self._h and self._destroy:
+            getattr(lib(), self._destroy)(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- a2-a5 ----------------------------------------------------------------------------------
+class ComplexFIRFilter(_Handle):
+    """ComplexFIRFilter (MS/Models/FIRFilter.cs:8-232) on the GPU."""
+    _destroy = "qpsk_fir_destroy"
+
+    def __init__(self, tapsInterleavedIQ, channels: int = 1):
+        super().__init__()
+        if tapsInterleavedIQ is None:
+            raise ArgumentNullException("tapsInterleavedIQ")
+        t = _f32(tapsInterleavedIQ)
+        self.taps = t.copy()
+        self.channels = channels
+        check(lib().qpsk_fir_create_batch(t.ctypes.data_as(N.f32p), t.size, channels, C.byref(self._h)))
+
+    def set_mode(self, mode: int):
+        check(lib().qpsk_fir_set_mode(self._h, mode))
+
+    def reset(self):
+        check(lib().qpsk_fir_reset(self._h))
+
+    def Filter(self, iqIn, iqOut=None, out_len=None) -> np.ndarray:
+        """Filter(ReadOnlySpan<float>, Span<float>) :80-91.  Batch handles: shape [channels, n_floats]."""
+        x = _f32(iqIn)
+        n = x.shape[-1] if x.ndim == 2 else x.size
+        if iqOut is None:
+            iqOut = np.empty(x.shape if out_len is None else out_len, np.float32)
+        cap = iqOut.shape[-1] if iqOut.ndim == 2 else iqOut.size
+        check(lib().qpsk_fir_filter(self._h, _ptr(x), _ptr(iqOut), n, cap))
+        return iqOut
+
+    def fftFilter(self, iqData) -> np.ndarray:
+        """fftFilter(float[]) :96-141."""
+        if iqData is None:
+            raise ArgumentNullException("iqData")
+        x = _f32(iqData)
+        n = x.shape[-1] if x.ndim == 2 else x.size
+        y = np.empty(x.shape if n % 2 == 0 else 0, np.float32)
+        check(lib().qpsk_fir_fft_filter(self._h, _ptr(x), _ptr(y), n))
+        return y
+
+    def filter_dev(self, d_in: int, d_out: int, n_floats: int, in_stride: int = 0, out_stride: int = 0, stream: int = 0):
+        check(lib().qpsk_fir_filter_dev(self._h, d_in, d_out, n_floats, in_stride or n_floats, out_stride or n_floats, stream))
+
+    def fft_filter_dev(self, d_in: int, d_out: int, n_floats: int, in_stride: int = 0, out_stride: int = 0, stream: int = 0):
+        check(lib().qpsk_fir_fft_filter_dev(self._h, d_in, d_out, n_floats, in_stride or n_floats, out_stride or n_floats, stream))
+
+    def get_state(self) -> np.ndarray:
+        keep = self.taps.size // 2 - 1
+        out = np.empty((self.channels, 2 * keep), np.float32)
+        check(lib().qpsk_fir_get_state(self._h, out.ctypes.data_as(N.f32p), out.size))
+        return out
+
+    def set_state(self, hist):
+        h = _f32(hist)
+        check(lib().qpsk_fir_set_state(self._h, h.ctypes.data_as(N.f32p), h.size))

@@ -1,0 +1,250 @@
+// core.cu — library/device plumbing and the host-side filter designers (a1, a7).
+#include <math.h>
+
+#include "common.cuh"
+#include "design.h"
+
+namespace qpsk {
+
+static thread_local std::string tl_cuda_error;
+static thread_local int64_t tl_launches = 0;
+static int g_device = 0;
+
+void set_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s: %s (%s) at %s:%d", what, cudaGetErrorString(e), cudaGetErrorName(e), file, line);
+  tl_cuda_error = buf;
+  (void)cudaGetLastError();  // clear the sticky-less error state
+}
+void count_launch(int n) { tl_launches += n; }
+int current_device() { return g_device; }
+
+int ensure_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    if (e != cudaSuccess) set_cuda_error(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    return QPSK_ERR_NO_DEVICE;
+  }
+  if (g_device >= n) return QPSK_ERR_NO_DEVICE;
+  QPSK_CUDA_TRY(cudaSetDevice(g_device));
+  static thread_local int checked_dev = -1;
+  if (checked_dev != g_device) {
+    int major = 0;
+    QPSK_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, g_device));
+    if (major != 10) {  // the fatbin holds sm_100a SASS only
+      tl_cuda_error = "libqpskcuda is built for sm_100a (B200) only";
+      return QPSK_ERR_NO_DEVICE;
+    }
+    checked_dev = g_device;
+  }
+  return QPSK_OK;
+}
+
+int device_sm_count() {
+  static int cached[64] = {0};
+  int d = g_device;
+  if (d < 64 && cached[d]) return cached[d];
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+  if (d < 64) cached[d] = n;
+  return n;
+}
+
+// ---- a1: root-raised-cosine taps (MS/Models/RRC-filter.cs:16-75) ----------------------------
+// Same three-branch closed form and unit-energy normalisation; tap count from banker's rounding
+// of fs/Rs and of the span (Math.Round).  Compiled without FP contraction so the fp64 results are
+// operation-for-operation those of the C# expression tree.
+std::vector<double> design_rrc(double span_symbols, double beta, int sample_rate, int symbol_rate) {
+  const int sps = (int)nearbyint((double)sample_rate / symbol_rate);
+  const int span = (int)nearbyint(span_symbols);
+  const int count = span * sps + 1;
+  std::vector<double> h((size_t)(count > 0 ? count : 0));
+  const int centre = (count - 1) / 2;
+  const double tiny = 1e-8;
+  for (int n = 0; n < count; ++n) {
+    const double t = (n - centre) / (double)sps;  // time in symbols
+    double v;
+    if (fabs(t) < tiny) {
+      v = 1.0 + beta * (4.0 / M_PI - 1.0);
+    } else if (fabs(fabs(t) - 1.0 / (4.0 * beta)) < tiny) {
+      v = (beta / sqrt(2.0)) * ((1.0 + 2.0 / M_PI) * sin(M_PI / (4.0 * beta)) + (1.0 - 2.0 / M_PI) * cos(M_PI / (4.0 * beta)));
+    } else {
+      const double numer = sin(M_PI * t * (1.0 - beta)) + 4.0 * beta * t * cos(M_PI * t * (1.0 + beta));
+      const double denom = M_PI * t * (1.0 - pow(4.0 * beta * t, 2.0));
+      v = numer / denom;
+    }
+    h[(size_t)n] = v;
+  }
+  double e = 0.0;
+  for (double v : h) e += v * v;
+  const double scale = sqrt(e);
+  for (double& v : h) v /= scale;
+  return h;
+}
+
+std::vector<float> real_taps_as_iq(const std::vector<double>& h) {
+  std::vector<float> t(h.size() * 2, 0.0f);
+  for (size_t i = 0; i < h.size(); ++i) t[2 * i] = (float)h[i];
+  return t;
+}
+
+// ---- a7: band-edge filter pair (MS/Models/Band-Edge Filter.cs:132-183) -----------------------
+static inline float sinc_pi(float x) {
+  if (x == 0.0f) return 1.0f;
+  const float a = kPiF * x;
+  return sinf(a) / a;
+}
+void design_band_edge(float sps, float rolloff, int size, std::vector<float>& lower, std::vector<float>& upper) {
+  const int centre = (size - 1) / 2;
+  std::vector<float> base((size_t)size);
+  float total = 0.0f;
+  for (int i = 0; i < size; ++i) {
+    const float k = (float)(i - centre) / (2.0f * sps);
+    const float pos = rolloff * k;
+    const float v = sinc_pi(pos - 0.5f) + sinc_pi(pos + 0.5f);
+    total += v;
+    base[(size_t)i] = v;
+  }
+  for (float& v : base) v /= total;
+  lower.assign((size_t)size * 2, 0.0f);
+  upper.assign((size_t)size * 2, 0.0f);
+  for (int i = 0; i < size; ++i) {
+    const float k = (float)(i - centre) / (2.0f * sps);
+    const float ang = -kTwoPiF * (1.0f + rolloff) * k;
+    const float re = base[(size_t)i] * cosf(ang);
+    const float im = base[(size_t)i] * sinf(ang);
+    lower[2 * (size_t)i] = re;
+    lower[2 * (size_t)i + 1] = im;
+    upper[2 * (size_t)i] = re;
+    upper[2 * (size_t)i + 1] = -im;
+  }
+}
+
+// setupSymbolSync (MS/QPSKDeModulator.cs:39-55)
+void mm_gains(double bn, double* kp, double* ki) {
+  const double zeta = 1.0 / sqrt(2.0);
+  const double wn = ((2.0 * M_PI * bn) / (zeta + 0.25) / zeta);
+  const double den = 1.0 + 2.0 * zeta * wn + wn * wn;
+  *kp = (4.0 * zeta * wn) / den;
+  *ki = (4.0 * wn * wn) / den;
+}
+
+// CostasLoopQpsk ctor gains (MS/Models/CostasLoopQpsk.cs:38-44)
+void costas_gains(double fs, double bw_hz, double damping, double* alpha, double* beta) {
+  const double bw = 2.0 * M_PI * bw_hz / fs;
+  const double d = 1.0 + 2.0 * damping * bw + bw * bw;
+  *alpha = (4.0 * damping * bw) / d;
+  *beta = (4.0 * bw * bw) / d;
+}
+
+bool blank_or_null(const char* s) {
+  if (!s) return true;
+  for (; *s; ++s)
+    if (!(*s == ' ' || (*s >= '\t' && *s <= '\r'))) return false;
+  return true;
+}
+
+}  // namespace qpsk
+
+using namespace qpsk;
+
+extern "C" {
+
+int qpsk_version(void) { return 100; }
+
+const char* qpsk_strerror(int s) {
+  switch (s) {
+    case QPSK_OK: return "ok";
+    case QPSK_ERR_NULL: return "null argument (ArgumentNullException)";
+    case QPSK_ERR_ARG: return "invalid argument (ArgumentException)";
+    case QPSK_ERR_RANGE: return "argument out of range (ArgumentOutOfRangeException)";
+    case QPSK_ERR_CUDA: return "CUDA failure";
+    case QPSK_ERR_NOMEM: return "out of memory";
+    case QPSK_ERR_CAPACITY: return "output buffer too small";
+    case QPSK_ERR_UNSUPPORTED: return "unsupported configuration";
+    case QPSK_ERR_NO_DEVICE: return "no usable CUDA device (sm_100a required)";
+    default: return "unknown status";
+  }
+}
+
+const char* qpsk_last_cuda_error(void) { return tl_cuda_error.c_str(); }
+
+int qpsk_device_count(int* n) {
+  if (!n) return QPSK_ERR_NULL;
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    c = 0;
+  }
+  *n = c;
+  return QPSK_OK;
+}
+
+int qpsk_set_device(int ordinal) {
+  if (ordinal < 0) return QPSK_ERR_RANGE;
+  int prev = g_device;
+  g_device = ordinal;
+  int st = ensure_device();
+  if (st != QPSK_OK) g_device = prev;
+  return st;
+}
+
+int qpsk_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes) {
+  QPSK_TRY(ensure_device());
+  cudaDeviceProp p;
+  QPSK_CUDA_TRY(cudaGetDeviceProperties(&p, g_device));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (hbm_bytes) *hbm_bytes = (int64_t)p.totalGlobalMem;
+  return QPSK_OK;
+}
+
+int qpsk_host_alloc(void** p, int64_t bytes) {
+  if (!p) return QPSK_ERR_NULL;
+  if (bytes < 0) return QPSK_ERR_RANGE;
+  QPSK_TRY(ensure_device());
+  QPSK_CUDA_TRY(cudaHostAlloc(p, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocPortable));
+  return QPSK_OK;
+}
+int qpsk_host_free(void* p) {
+  if (!p) return QPSK_OK;
+  QPSK_CUDA_TRY(cudaFreeHost(p));
+  return QPSK_OK;
+}
+
+int64_t qpsk_launch_count(void) { return tl_launches; }
+void qpsk_launch_count_reset(void) { tl_launches = 0; }
+
+int qpsk_rrc_taps(double span_symbols, double beta, int sample_rate, int symbol_rate, double* out, int cap, int* n) {
+  if (!n) return QPSK_ERR_NULL;
+  if (symbol_rate == 0) return QPSK_ERR_RANGE;
+  std::vector<double> h = design_rrc(span_symbols, beta, sample_rate, symbol_rate);
+  *n = (int)h.size();
+  if (!out) return QPSK_OK;
+  if (cap < (int)h.size()) return QPSK_ERR_CAPACITY;
+  if (!h.empty()) memcpy(out, h.data(), h.size() * sizeof(double));
+  return QPSK_OK;
+}
+
+int qpsk_fll_design(float sps, float rolloff, int filter_size, float* lower_iq, float* upper_iq) {
+  if (!lower_iq || !upper_iq) return QPSK_ERR_NULL;
+  if (!(sps > 0.0f)) return QPSK_ERR_RANGE;
+  if (rolloff < 0 || rolloff > 1.0f) return QPSK_ERR_RANGE;
+  if (filter_size <= 0) return QPSK_ERR_RANGE;
+  std::vector<float> lo, up;
+  design_band_edge(sps, rolloff, filter_size, lo, up);
+  memcpy(lower_iq, lo.data(), lo.size() * sizeof(float));
+  memcpy(upper_iq, up.data(), up.size() * sizeof(float));
+  return QPSK_OK;
+}
+
+int qpsk_mm_gains_from_bw(double bw, double* kp, double* ki) {
+  if (!kp || !ki) return QPSK_ERR_NULL;
+  mm_gains(bw, kp, ki);
+  return QPSK_OK;
+}
+
+}  // extern "C"

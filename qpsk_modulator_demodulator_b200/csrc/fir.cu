@@ -1,0 +1,796 @@
+// fir.cu — K1/K2: complex-sample FIR kernels for sm_100a and the qpsk_fir_* entry points.
+//
+// Stands in for ComplexFIRFilter (MS/Models/FIRFilter.cs): streaming Filter(span,span) :80-91 with
+// the (N-1)-sample delay line carried across calls, and the stateless fftFilter :96-141 alignment
+// y[i] = conv(x,h)[i+N-1].  Both are the same correlation  y[n0+q] = sum_i g[i] * xs[q+i]  over a
+// shared-memory tile xs (tile + halo), with g[i] = h[HL-i]; only the tile origin differs.
+//
+// fir_tma_kernel (the hot kernel)
+//   * persistent CTAs (2 per SM), each walking tiles  blockIdx.x + k*gridDim.x  of T = NT*R samples;
+//   * input tile + halo staged by TMA bulk copies (cp.async.bulk -> SASS UBLKCP) into a 2-4 deep
+//     mbarrier ring, so loads for the next tiles are in flight while the current one is computed;
+//   * each thread owns R consecutive outputs and slides a register window over the tile: one
+//     LDS.128 (two new samples) feeds 2*R packed FFMA2 (fma.rn.f32x2: I and Q of one sample in one
+//     issue slot, the real tap broadcast from a uniform register);
+//   * R = 10 -> thread stride 80 B = 5 x 16 B chunks, odd, so the LDS.128/STS.128 of a quarter-warp
+//     hit 8 distinct 16-byte bank groups: conflict-free on a dense (TMA-compatible) layout;
+//   * results staged in shared memory and written back with one TMA bulk store per tile.
+//   Algorithmic traffic: 8 B read + 8 B written per complex sample; 4*N flop (real taps) or
+//   8*N flop (complex taps) per sample.
+//
+// fir_generic_kernel: one thread per output straight from global memory.  Serves QPSK_FIR_EXACT
+// (the reference's 8-lane summation order, no FMA: FIRFilter.cs:165-192), unaligned device
+// pointers, and tap counts beyond the parameter-space table.
+#include "fir.cuh"
+
+namespace qpsk {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk copy, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk store (bulk-group completion)
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxG = 1040;  // correlation taps held in kernel-parameter (constant-bank) space
+
+struct FirArgs {
+  const float2* x;
+  float2* y;
+  long long ldx, ldy, L;
+  const float2* hist_in;  // [C][HL] or null (stateless: zeros)
+  float2* hist_out;       // [C][HL] or null
+  long long total_tiles;
+  int tiles_per_ch;
+  int HL, G, advance;
+  int E_load;       // samples staged per tile (even)
+  int stage_elems;  // float2 slots per stage (even)
+  int stages;
+};
+struct TapsReal {
+  float g[kMaxG];
+};
+struct TapsCplx {
+  float gi[kMaxG];
+  float gq[kMaxG];
+};
+
+template <bool CPLX>
+struct TapsOf {
+  using type = TapsReal;
+};
+template <>
+struct TapsOf<true> {
+  using type = TapsCplx;
+};
+
+// ---------------------------------------------------------------------------------------------
+// the hot kernel
+// ---------------------------------------------------------------------------------------------
+template <int R, int NT, bool CPLX>
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1))
+    fir_tma_kernel(const __grid_constant__ FirArgs a, const __grid_constant__ typename TapsOf<CPLX>::type taps) {
+  static_assert(R % 2 == 0, "R must be even (LDS.128 moves two samples)");
+  constexpr int T = R * NT;
+  constexpr int W = 2 * R;  // circular register window
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* xs_base = reinterpret_cast<float2*>(smem_raw);
+  float2* ys_base = xs_base + (size_t)a.stages * a.stage_elems;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ys_base + 2 * T);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // warp 0 stages tile `tile` into ring slot `stage`: TMA bulk copies for the in-range part,
+  // plain zero stores for what lies before the stream start (stateless) or past its end.
+  auto issue = [&](long long tile, int stage) {
+    const int ch = (int)(tile / a.tiles_per_ch);
+    const int k = (int)(tile - (long long)ch * a.tiles_per_ch);
+    const long long n0 = (long long)k * T;
+    const long long s0 = n0 + a.advance - a.HL;  // stream index of xs[0] (even)
+    float2* dst = xs_base + (size_t)stage * a.stage_elems;
+    const float2* xch = a.x + (long long)ch * a.ldx;
+    uint64_t* bar = &full[stage];
+    const int E = a.E_load;
+    uint32_t tx = 0;
+    int nA = 0;
+    if (s0 < 0) {
+      nA = (int)((-s0) < (long long)E ? (-s0) : (long long)E);
+      if (a.hist_in) {
+        if (lane == 0) bulk_g2s(dst, a.hist_in + (long long)ch * a.HL + (a.HL + s0), (uint32_t)nA * 8u, bar);
+        tx += (uint32_t)nA * 8u;
+      } else {
+        for (int i = lane; i < nA; i += 32) dst[i] = make_float2(0.f, 0.f);
+      }
+    }
+    const long long m0 = s0 + nA;
+    long long avail = a.L - m0;
+    if (avail < 0) avail = 0;
+    const int nB = (int)(avail < (long long)(E - nA) ? avail : (long long)(E - nA));
+    const int nB2 = nB & ~1;
+    if (nB2 > 0) {
+      if (lane == 0) bulk_g2s(dst + nA, xch + m0, (uint32_t)nB2 * 8u, bar);
+      tx += (uint32_t)nB2 * 8u;
+    }
+    if ((nB & 1) && lane == 0) dst[nA + nB2] = xch[m0 + nB2];
+    for (int i = nA + nB + lane; i < E; i += 32) dst[i] = make_float2(0.f, 0.f);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_expect_tx(bar, tx);
+  };
+
+  if (warp == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      const long long tile = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (tile < a.total_tiles) issue(tile, s);
+    }
+  }
+
+  const int base = tid * R;
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int it = 0;; ++it) {
+    const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+    if (tile >= a.total_tiles) break;
+    mbar_wait(&full[stage], parity);
+    const float2* xs = xs_base + (size_t)stage * a.stage_elems;
+
+    const int ch = (int)(tile / a.tiles_per_ch);
+    const int k = (int)(tile - (long long)ch * a.tiles_per_ch);
+    const long long n0 = (long long)k * T;
+    const long long left = a.L - n0;
+    const int valid = (int)(left < (long long)T ? left : (long long)T);
+
+    // delay-line carry: the last tile of a channel holds the stream's final HL samples
+    if (a.hist_out && k == a.tiles_per_ch - 1) {
+      const int off = (int)(a.L - n0);
+      float2* ho = a.hist_out + (long long)ch * a.HL;
+      for (int i = tid; i < a.HL; i += NT) ho[i] = xs[off + i];
+    }
+
+    // ---- register-tiled correlation ----
+    float2 w[W];
+    float2 acc[R];
+    float2 accq[CPLX ? R : 1];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+    if (CPLX) {
+#pragma unroll
+      for (int r = 0; r < (CPLX ? R : 1); ++r) accq[r] = make_float2(0.f, 0.f);
+    }
+    const float4* xv = reinterpret_cast<const float4*>(xs + base);
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+      const float4 v = xv[r >> 1];
+      w[r] = make_float2(v.x, v.y);
+      w[r + 1] = make_float2(v.z, v.w);
+    }
+    int i0 = 0;
+    for (; i0 + W <= a.G; i0 += W) {
+      const float4* xn = reinterpret_cast<const float4*>(xs + base + i0 + R);
+#pragma unroll
+      for (int ii = 0; ii < W; ii += 2) {
+        const float4 v = xn[ii >> 1];
+        w[(R + ii) % W] = make_float2(v.x, v.y);
+        w[(R + ii + 1) % W] = make_float2(v.z, v.w);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if constexpr (!CPLX) {
+            const float g = taps.g[i0 + ii + u];
+            const float2 gg = make_float2(g, g);
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(ii + u + r) % W], gg, acc[r]);
+          } else {
+            const float gi = taps.gi[i0 + ii + u];
+            const float gq = taps.gq[i0 + ii + u];
+            const float2 ggi = make_float2(gi, gi), ggq = make_float2(gq, gq);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              acc[r] = ffma2(w[(ii + u + r) % W], ggi, acc[r]);
+              accq[CPLX ? r : 0] = ffma2(w[(ii + u + r) % W], ggq, accq[CPLX ? r : 0]);
+            }
+          }
+        }
+      }
+    }
+    // remainder: two taps per step, window slid explicitly
+    for (; i0 < a.G; i0 += 2) {
+      const float4 v = *reinterpret_cast<const float4*>(xs + base + i0 + R);
+      w[R] = make_float2(v.x, v.y);
+      w[R + 1] = make_float2(v.z, v.w);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if constexpr (!CPLX) {
+          const float g = taps.g[i0 + u];
+          const float2 gg = make_float2(g, g);
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = ffma2(w[u + r], gg, acc[r]);
+        } else {
+          const float gi = taps.gi[i0 + u];
+          const float gq = taps.gq[i0 + u];
+          const float2 ggi = make_float2(gi, gi), ggq = make_float2(gq, gq);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            acc[r] = ffma2(w[u + r], ggi, acc[r]);
+            accq[CPLX ? r : 0] = ffma2(w[u + r], ggq, accq[CPLX ? r : 0]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) w[r] = w[r + 2];
+    }
+
+    // ---- epilogue: registers -> smem -> TMA bulk store ----
+    if (tid == 0) bulk_wait_read<1>();  // the store issued two tiles ago has drained this ys buffer
+    __syncthreads();                    // all reads of xs[stage] done; ys[it&1] reusable
+    if (warp == 0) {
+      const long long next = tile + (long long)a.stages * gridDim.x;
+      if (next < a.total_tiles) issue(next, stage);
+    }
+    float2* ys = ys_base + (size_t)(it & 1) * T;
+    float4* yv = reinterpret_cast<float4*>(ys + base);
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+      float2 o0, o1;
+      if constexpr (!CPLX) {
+        o0 = acc[r];
+        o1 = acc[r + 1];
+      } else {
+        // A = sum gI*(xI,xQ), B = sum gQ*(xI,xQ):  y = (A.x - B.y, A.y + B.x)
+        o0 = make_float2(acc[r].x - accq[CPLX ? r : 0].y, acc[r].y + accq[CPLX ? r : 0].x);
+        o1 = make_float2(acc[r + 1].x - accq[CPLX ? r + 1 : 0].y, acc[r + 1].y + accq[CPLX ? r + 1 : 0].x);
+      }
+      yv[r >> 1] = make_float4(o0.x, o0.y, o1.x, o1.y);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    float2* yg = a.y + (long long)ch * a.ldy + n0;
+    if ((valid & 1) == 0) {
+      if (tid == 0) {
+        bulk_s2g(yg, ys, (uint32_t)valid * 8u);
+        bulk_commit();
+      }
+    } else {
+      for (int i = tid; i < valid; i += NT) yg[i] = ys[i];
+      if (tid == 0) bulk_commit();
+    }
+    if (++stage == a.stages) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  if (tid == 0) bulk_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic kernel: exact reference order / unaligned / very long filters
+// ---------------------------------------------------------------------------------------------
+struct GenArgs {
+  const float2* x;
+  float2* y;
+  long long ldx, ldy, L;
+  const float2* hist_in;
+  const float* hI;  // h[j] real parts, j = 0..N-1
+  const float* hQ;
+  int C, N, HL, advance;
+};
+
+__device__ __forceinline__ float2 gen_in(const GenArgs& a, int ch, long long m) {
+  if (m < 0) {
+    if (!a.hist_in || m < -(long long)a.HL) return make_float2(0.f, 0.f);
+    return a.hist_in[(long long)ch * a.HL + a.HL + m];
+  }
+  if (m >= a.L) return make_float2(0.f, 0.f);
+  return a.x[(long long)ch * a.ldx + m];
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(256) fir_generic_kernel(const GenArgs a) {
+  const long long total = (long long)a.C * a.L;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx / a.L);
+    const long long n = idx - (long long)ch * a.L;
+    float outI, outQ;
+    if (EXACT) {
+      // ComplexDotWindow (FIRFilter.cs:144-211) with Vector<float>.Count == 8: window element i
+      // is x[n-(N-1)+i] against reversed tap h[N-1-i]; 8 lane partials, lanes summed 0..7, scalar
+      // tail; every product and sum rounded separately (no FMA).
+      const int N = a.N;
+      const int nVec = N - (N & 7);
+      float lI[8], lQ[8];
+#pragma unroll
+      for (int l = 0; l < 8; ++l) lI[l] = lQ[l] = 0.f;
+      const long long first = n + a.advance - (N - 1);
+      for (int i = 0; i < nVec; i += 8) {
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          const float2 xv = gen_in(a, ch, first + i + l);
+          const float hi = a.hI[N - 1 - (i + l)], hq = a.hQ[N - 1 - (i + l)];
+          const float tI = __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y));
+          const float tQ = __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x));
+          lI[l] = __fadd_rn(lI[l], tI);
+          lQ[l] = __fadd_rn(lQ[l], tQ);
+        }
+      }
+      float accI = 0.f, accQ = 0.f;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        accI = __fadd_rn(accI, lI[l]);
+        accQ = __fadd_rn(accQ, lQ[l]);
+      }
+      for (int i = nVec; i < N; ++i) {
+        const float2 xv = gen_in(a, ch, first + i);
+        const float hi = a.hI[N - 1 - i], hq = a.hQ[N - 1 - i];
+        const float tI = __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y));
+        const float tQ = __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x));
+        accI = __fadd_rn(accI, tI);
+        accQ = __fadd_rn(accQ, tQ);
+      }
+      outI = accI;
+      outQ = accQ;
+    } else {
+      float aI = 0.f, aQ = 0.f;
+      const long long top = n + a.advance;
+      for (int j = 0; j < a.N; ++j) {
+        const float2 xv = gen_in(a, ch, top - j);
+        const float hi = a.hI[j], hq = a.hQ[j];
+        aI = fmaf(hi, xv.x, aI);
+        aI = fmaf(-hq, xv.y, aI);
+        aQ = fmaf(hi, xv.y, aQ);
+        aQ = fmaf(hq, xv.x, aQ);
+      }
+      outI = aI;
+      outQ = aQ;
+    }
+    a.y[(long long)ch * a.ldy + n] = make_float2(outI, outQ);
+  }
+}
+
+// hist_out[c][i] = element (L - HL + i) of the stream (hist_in ++ x)
+__global__ void fir_hist_update_kernel(const float2* x, long long ldx, long long L, const float2* hist_in,
+                                       float2* hist_out, int C, int HL) {
+  const int total = C * HL;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int ch = idx / HL, i = idx - ch * HL;
+    const long long m = L - HL + i;
+    hist_out[idx] = (m < 0) ? hist_in[(long long)ch * HL + HL + m] : x[(long long)ch * ldx + m];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FirEngine
+// ---------------------------------------------------------------------------------------------
+FirEngine::~FirEngine() {
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int FirEngine::init(const float* taps_in, int n_floats, int channels_in) {
+  if (!taps_in) return QPSK_ERR_NULL;
+  if ((n_floats & 1) != 0 || n_floats == 0) return QPSK_ERR_ARG;  // FIRFilter.cs:32-33
+  if (channels_in <= 0) return QPSK_ERR_RANGE;
+  QPSK_TRY(ensure_device());
+  n_taps = n_floats >> 1;
+  channels = channels_in;
+  taps_iq.assign(taps_in, taps_in + n_floats);
+  real_taps = true;
+  for (int j = 0; j < n_taps; ++j)
+    if (taps_iq[2 * j + 1] != 0.0f) real_taps = false;
+  HL = (n_taps - 1) + ((n_taps - 1) & 1);
+  if (HL == 0) HL = 2;  // keep a non-empty, 16-byte sized history even for a 1-tap filter
+  QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  QPSK_TRY(hist[0].alloc((size_t)channels * HL));
+  QPSK_TRY(hist[1].alloc((size_t)channels * HL));
+  QPSK_TRY(d_taps.alloc((size_t)2 * n_taps));
+  std::vector<float> planar((size_t)2 * n_taps);
+  for (int j = 0; j < n_taps; ++j) {
+    planar[j] = taps_iq[2 * j];
+    planar[n_taps + j] = taps_iq[2 * j + 1];
+  }
+  QPSK_CUDA_TRY(cudaMemcpyAsync(d_taps.p, planar.data(), planar.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+  QPSK_TRY(reset(stream));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(stream));
+  return QPSK_OK;
+}
+
+int FirEngine::reset(cudaStream_t s) {
+  QPSK_TRY(hist[0].zero(s));
+  QPSK_TRY(hist[1].zero(s));
+  cur = 0;
+  return QPSK_OK;
+}
+
+int FirEngine::get_state(float* out, int64_t cap_floats) {
+  if (!out) return QPSK_ERR_NULL;
+  const int keep = n_taps - 1;
+  if (cap_floats < (int64_t)channels * keep * 2) return QPSK_ERR_CAPACITY;
+  if (keep == 0) return QPSK_OK;
+  QPSK_CUDA_TRY(cudaStreamSynchronize(stream));
+  // the newest N-1 of the HL kept samples
+  QPSK_CUDA_TRY(cudaMemcpy2D(out, (size_t)keep * 8, hist[cur].p + (HL - keep), (size_t)HL * 8, (size_t)keep * 8,
+                             (size_t)channels, cudaMemcpyDeviceToHost));
+  return QPSK_OK;
+}
+
+int FirEngine::set_state(const float* in, int64_t n_floats) {
+  if (!in) return QPSK_ERR_NULL;
+  const int keep = n_taps - 1;
+  if (n_floats != (int64_t)channels * keep * 2) return QPSK_ERR_ARG;
+  QPSK_CUDA_TRY(cudaStreamSynchronize(stream));
+  QPSK_CUDA_TRY(cudaMemset(hist[cur].p, 0, hist[cur].n * sizeof(float2)));
+  if (keep == 0) return QPSK_OK;
+  QPSK_CUDA_TRY(cudaMemcpy2D(hist[cur].p + (HL - keep), (size_t)HL * 8, in, (size_t)keep * 8, (size_t)keep * 8,
+                             (size_t)channels, cudaMemcpyHostToDevice));
+  return QPSK_OK;
+}
+
+namespace {
+
+constexpr int kR = 10;
+constexpr int kNT = 256;
+constexpr int kT = kR * kNT;
+constexpr int kSmemBudget = 112 * 1024;  // per CTA, two CTAs per SM
+
+template <bool CPLX>
+int launch_tma(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, size_t smem, int grid, cudaStream_t s) {
+  auto kern = fir_tma_kernel<kR, kNT, CPLX>;
+  QPSK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kNT, smem, s>>>(a, taps);
+  QPSK_LAUNCH_CHECK();
+  return QPSK_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t ldy, bool stateless, cudaStream_t s) {
+  if (L == 0) return QPSK_OK;
+  if (!x || !y) return QPSK_ERR_NULL;
+  QPSK_TRY(ensure_device());
+  if (!s) s = stream;
+  const int N = n_taps;
+  // geometry: y[n0+q] = sum_i g[i]*xs[q+i], xs[0] = stream index n0 + advance - hl, g[i] = h[hl-i]
+  const int advance = stateless ? (N - 1) : 0;
+  const int hl = stateless ? (N - 1) : HL;
+  const int G = (hl + 1 + 1) & ~1;
+
+  bool use_tma = (mode == QPSK_FIR_FAST || stateless) && G <= kMaxG && hl <= kT;
+  if (use_tma) {
+    if (!aligned16(x) || !aligned16(y)) use_tma = false;
+    if (channels > 1 && ((ldx & 1) || (ldy & 1))) use_tma = false;
+  }
+  if (!stateless) {
+    // the kernels read hist[cur] and leave the updated delay line in hist[cur^1]
+  }
+  const float2* hin = stateless ? nullptr : hist[cur].p;
+  float2* hout = stateless ? nullptr : hist[cur ^ 1].p;
+
+  if (use_tma) {
+    FirArgs a;
+    a.x = x; a.y = y; a.ldx = ldx; a.ldy = ldy; a.L = L;
+    a.hist_in = hin; a.hist_out = hout;
+    a.tiles_per_ch = (int)((L + kT - 1) / kT);
+    a.total_tiles = (long long)a.tiles_per_ch * channels;
+    a.HL = hl; a.G = G; a.advance = advance;
+    a.E_load = kT + G;
+    a.stage_elems = a.E_load + 2;
+    const size_t stage_bytes = (size_t)a.stage_elems * 8;
+    const size_t out_bytes = (size_t)2 * kT * 8;
+    int stages = (int)((kSmemBudget - out_bytes - 64) / stage_bytes);
+    if (stages > 4) stages = 4;
+    if (stages >= 2) {
+      a.stages = stages;
+      const size_t smem = (size_t)stages * stage_bytes + out_bytes + (size_t)stages * 8;
+      long long grid = 2LL * device_sm_count();
+      if (grid > a.total_tiles) grid = a.total_tiles;
+      if (real_taps) {
+        TapsReal t;
+        memset(&t, 0, sizeof t);
+        for (int i = 0; i <= hl; ++i) {
+          const int j = hl - i;
+          t.g[i] = (j < N) ? taps_iq[2 * j] : 0.0f;
+        }
+        QPSK_TRY(launch_tma<false>(a, t, smem, (int)grid, s));
+      } else {
+        TapsCplx t;
+        memset(&t, 0, sizeof t);
+        for (int i = 0; i <= hl; ++i) {
+          const int j = hl - i;
+          t.gi[i] = (j < N) ? taps_iq[2 * j] : 0.0f;
+          t.gq[i] = (j < N) ? taps_iq[2 * j + 1] : 0.0f;
+        }
+        QPSK_TRY(launch_tma<true>(a, t, smem, (int)grid, s));
+      }
+      if (!stateless) cur ^= 1;
+      return QPSK_OK;
+    }
+  }
+
+  GenArgs g;
+  g.x = x; g.y = y; g.ldx = ldx; g.ldy = ldy; g.L = L;
+  g.hist_in = hin; g.hI = d_taps.p; g.hQ = d_taps.p + N;
+  g.C = channels; g.N = N; g.HL = HL; g.advance = advance;
+  const long long total = (long long)channels * L;
+  long long blocks = (total + 255) / 256;
+  const long long cap = 32LL * device_sm_count();
+  if (blocks > cap) blocks = cap;
+  if (mode == QPSK_FIR_EXACT && !stateless)
+    fir_generic_kernel<true><<<(int)blocks, 256, 0, s>>>(g);
+  else
+    fir_generic_kernel<false><<<(int)blocks, 256, 0, s>>>(g);
+  QPSK_LAUNCH_CHECK();
+  if (!stateless) {
+    const int tot = channels * HL;
+    fir_hist_update_kernel<<<(tot + 255) / 256, 256, 0, s>>>(x, ldx, L, hin, hout, channels, HL);
+    QPSK_LAUNCH_CHECK();
+    cur ^= 1;
+  }
+  return QPSK_OK;
+}
+
+int FirEngine::filter_dev(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t ldy, cudaStream_t s) {
+  return run(x, y, L, ldx, ldy, false, s);
+}
+int FirEngine::fft_filter_dev(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t ldy, cudaStream_t s) {
+  return run(x, y, L, ldx, ldy, true, s);
+}
+
+}  // namespace qpsk
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace qpsk;
+
+struct qpsk_fir {
+  FirEngine eng;
+  // host-pointer pipeline: H2D / kernel / D2H on three streams over two device slots
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  DevBuf<float2> d_in[2], d_out[2];
+  ~qpsk_fir() {
+    for (int i = 0; i < 2; ++i) {
+      if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
+      if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+      if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+  }
+};
+
+namespace {
+
+constexpr int64_t kChunk = 8LL << 20;  // complex samples per pipelined chunk (64 MiB each way)
+
+int fir_pipeline_init(qpsk_fir* f) {
+  if (f->s_in) return QPSK_OK;
+  QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&f->s_in, cudaStreamNonBlocking));
+  QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    QPSK_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_h2d[i], cudaEventDisableTiming));
+    QPSK_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_k[i], cudaEventDisableTiming));
+    QPSK_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_d2h[i], cudaEventDisableTiming));
+  }
+  return QPSK_OK;
+}
+
+// one stream of L complex samples, host to host, chunked so copies overlap the kernels
+int fir_host_stream(qpsk_fir* f, const float* in, float* out, int64_t L, bool stateless) {
+  FirEngine& e = f->eng;
+  QPSK_TRY(fir_pipeline_init(f));
+  if (stateless || L <= kChunk) {
+    QPSK_TRY(f->d_in[0].ensure((size_t)L));
+    QPSK_TRY(f->d_out[0].ensure((size_t)L));
+    QPSK_CUDA_TRY(cudaMemcpyAsync(f->d_in[0].p, in, (size_t)L * 8, cudaMemcpyHostToDevice, e.stream));
+    QPSK_TRY(stateless ? e.fft_filter_dev(f->d_in[0].p, f->d_out[0].p, L, L, L, e.stream)
+                       : e.filter_dev(f->d_in[0].p, f->d_out[0].p, L, L, L, e.stream));
+    QPSK_CUDA_TRY(cudaMemcpyAsync(out, f->d_out[0].p, (size_t)L * 8, cudaMemcpyDeviceToHost, e.stream));
+    QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
+    return QPSK_OK;
+  }
+  for (int b = 0; b < 2; ++b) {
+    QPSK_TRY(f->d_in[b].ensure((size_t)kChunk));
+    QPSK_TRY(f->d_out[b].ensure((size_t)kChunk));
+  }
+  const int64_t chunks = (L + kChunk - 1) / kChunk;
+  for (int64_t c = 0; c < chunks; ++c) {
+    const int b = (int)(c & 1);
+    const int64_t off = c * kChunk;
+    const int64_t len = (L - off < kChunk) ? (L - off) : kChunk;
+    if (c >= 2) QPSK_CUDA_TRY(cudaStreamWaitEvent(f->s_in, f->ev_k[b], 0));  // slot's previous kernel done
+    QPSK_CUDA_TRY(cudaMemcpyAsync(f->d_in[b].p, in + 2 * off, (size_t)len * 8, cudaMemcpyHostToDevice, f->s_in));
+    QPSK_CUDA_TRY(cudaEventRecord(f->ev_h2d[b], f->s_in));
+    QPSK_CUDA_TRY(cudaStreamWaitEvent(e.stream, f->ev_h2d[b], 0));
+    if (c >= 2) QPSK_CUDA_TRY(cudaStreamWaitEvent(e.stream, f->ev_d2h[b], 0));  // slot's previous D2H done
+    QPSK_TRY(e.filter_dev(f->d_in[b].p, f->d_out[b].p, len, len, len, e.stream));
+    QPSK_CUDA_TRY(cudaEventRecord(f->ev_k[b], e.stream));
+    QPSK_CUDA_TRY(cudaStreamWaitEvent(f->s_out, f->ev_k[b], 0));
+    QPSK_CUDA_TRY(cudaMemcpyAsync(out + 2 * off, f->d_out[b].p, (size_t)len * 8, cudaMemcpyDeviceToHost, f->s_out));
+    QPSK_CUDA_TRY(cudaEventRecord(f->ev_d2h[b], f->s_out));
+  }
+  QPSK_CUDA_TRY(cudaStreamSynchronize(f->s_out));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return QPSK_OK;
+}
+
+int fir_host_batch(qpsk_fir* f, const float* in, float* out, int64_t L, bool stateless) {
+  FirEngine& e = f->eng;
+  const size_t tot = (size_t)L * e.channels;
+  QPSK_TRY(f->d_in[0].ensure(tot));
+  QPSK_TRY(f->d_out[0].ensure(tot));
+  QPSK_CUDA_TRY(cudaMemcpyAsync(f->d_in[0].p, in, tot * 8, cudaMemcpyHostToDevice, e.stream));
+  QPSK_TRY(stateless ? e.fft_filter_dev(f->d_in[0].p, f->d_out[0].p, L, L, L, e.stream)
+                     : e.filter_dev(f->d_in[0].p, f->d_out[0].p, L, L, L, e.stream));
+  QPSK_CUDA_TRY(cudaMemcpyAsync(out, f->d_out[0].p, tot * 8, cudaMemcpyDeviceToHost, e.stream));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return QPSK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qpsk_fir_create_batch(const float* taps_iq, int n_floats, int channels, qpsk_fir** out) {
+  if (!taps_iq || !out) return QPSK_ERR_NULL;
+  *out = nullptr;
+  if ((n_floats & 1) != 0 || n_floats <= 0) return QPSK_ERR_ARG;
+  qpsk_fir* f = new (std::nothrow) qpsk_fir();
+  if (!f) return QPSK_ERR_NOMEM;
+  int st = f->eng.init(taps_iq, n_floats, channels);
+  if (st != QPSK_OK) {
+    delete f;
+    return st;
+  }
+  *out = f;
+  return QPSK_OK;
+}
+int qpsk_fir_create(const float* taps_iq, int n_floats, qpsk_fir** out) {
+  return qpsk_fir_create_batch(taps_iq, n_floats, 1, out);
+}
+int qpsk_fir_destroy(qpsk_fir* f) {
+  if (f) {
+    cudaSetDevice(current_device());
+    if (f->eng.stream) cudaStreamSynchronize(f->eng.stream);
+    delete f;
+  }
+  return QPSK_OK;
+}
+int qpsk_fir_reset(qpsk_fir* f) {
+  if (!f) return QPSK_ERR_NULL;
+  QPSK_TRY(ensure_device());
+  QPSK_TRY(f->eng.reset(f->eng.stream));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(f->eng.stream));
+  return QPSK_OK;
+}
+int qpsk_fir_set_mode(qpsk_fir* f, int mode) {
+  if (!f) return QPSK_ERR_NULL;
+  if (mode != QPSK_FIR_FAST && mode != QPSK_FIR_EXACT) return QPSK_ERR_RANGE;
+  f->eng.mode = mode;
+  return QPSK_OK;
+}
+int qpsk_fir_num_taps(const qpsk_fir* f, int* n) {
+  if (!f || !n) return QPSK_ERR_NULL;
+  *n = f->eng.n_taps;
+  return QPSK_OK;
+}
+
+int qpsk_fir_filter(qpsk_fir* f, const float* in, float* out, int64_t n_floats, int64_t out_cap_floats) {
+  if (!f) return QPSK_ERR_NULL;
+  if (n_floats < 0) return QPSK_ERR_RANGE;
+  if ((n_floats & 1) != 0) return QPSK_ERR_ARG;            // FIRFilter.cs:82
+  if (out_cap_floats < n_floats) return QPSK_ERR_ARG;      // FIRFilter.cs:83
+  if (n_floats == 0) return QPSK_OK;
+  if (!in || !out) return QPSK_ERR_NULL;
+  QPSK_TRY(ensure_device());
+  const int64_t L = n_floats >> 1;
+  return (f->eng.channels == 1) ? fir_host_stream(f, in, out, L, false) : fir_host_batch(f, in, out, L, false);
+}
+
+int qpsk_fir_fft_filter(qpsk_fir* f, const float* in, float* out, int64_t n_floats) {
+  if (!f || !in) return QPSK_ERR_NULL;                     // FIRFilter.cs:98
+  if (n_floats < 0) return QPSK_ERR_RANGE;
+  if ((n_floats & 1) != 0) return QPSK_ERR_ARG;            // :99
+  if (n_floats == 0) return QPSK_OK;                       // :100
+  if (!out) return QPSK_ERR_NULL;
+  QPSK_TRY(ensure_device());
+  const int64_t L = n_floats >> 1;
+  return (f->eng.channels == 1) ? fir_host_stream(f, in, out, L, true) : fir_host_batch(f, in, out, L, true);
+}
+
+static int fir_dev_common(qpsk_fir* f, const float* d_in, float* d_out, int64_t n_floats, int64_t is, int64_t os,
+                          void* stream, bool stateless) {
+  if (!f) return QPSK_ERR_NULL;
+  if (n_floats < 0) return QPSK_ERR_RANGE;
+  if ((n_floats & 1) != 0) return QPSK_ERR_ARG;
+  if (n_floats == 0) return QPSK_OK;
+  if (!d_in || !d_out) return QPSK_ERR_NULL;
+  if ((is & 1) || (os & 1)) return QPSK_ERR_ARG;
+  if (f->eng.channels > 1 && (is < n_floats || os < n_floats)) return QPSK_ERR_ARG;
+  {  // in-place or overlapping buffers would let one tile overwrite another tile's halo
+    const char* a0 = (const char*)d_in;
+    const char* a1 = a0 + ((size_t)(f->eng.channels - 1) * is + n_floats) * 4;
+    const char* b0 = (const char*)d_out;
+    const char* b1 = b0 + ((size_t)(f->eng.channels - 1) * os + n_floats) * 4;
+    if (a0 < b1 && b0 < a1) return QPSK_ERR_ARG;
+  }
+  const int64_t L = n_floats >> 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  return stateless ? f->eng.fft_filter_dev((const float2*)d_in, (float2*)d_out, L, is >> 1, os >> 1, s)
+                   : f->eng.filter_dev((const float2*)d_in, (float2*)d_out, L, is >> 1, os >> 1, s);
+}
+int qpsk_fir_filter_dev(qpsk_fir* f, const float* d_in, float* d_out, int64_t n_floats, int64_t is, int64_t os, void* stream) {
+  return fir_dev_common(f, d_in, d_out, n_floats, is, os, stream, false);
+}
+int qpsk_fir_fft_filter_dev(qpsk_fir* f, const float* d_in, float* d_out, int64_t n_floats, int64_t is, int64_t os, void* stream) {
+  return fir_dev_common(f, d_in, d_out, n_floats, is, os, stream, true);
+}
+
+int qpsk_fir_get_state(qpsk_fir* f, float* hist_iq, int64_t cap_floats) {
+  if (!f) return QPSK_ERR_NULL;
+  QPSK_TRY(ensure_device());
+  return f->eng.get_state(hist_iq, cap_floats);
+}
+int qpsk_fir_set_state(qpsk_fir* f, const float* hist_iq, int64_t n_floats) {
+  if (!f) return QPSK_ERR_NULL;
+  QPSK_TRY(ensure_device());
+  return f->eng.set_state(hist_iq, n_floats);
+}
+
+}  // extern "C"

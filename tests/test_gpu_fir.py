@@ -1,0 +1,178 @@
+"""GPU parity: ComplexFIRFilter (K1/K2) through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+# fp32 tolerance for filter outputs (north_star): max |err| <= 1e-5 * max|y| against the
+# reference's fp64 Complex path; the FAST kernel differs from the oracle's fp32 path only by
+# summation order / FMA contraction.
+REL_TOL = 1e-5
+
+
+def _rand_iq(orc, n_complex, seed=1, stream=0):
+    return orc.fill_uniform(seed, stream, 0, 2 * n_complex)
+
+
+def _rrc_iq(orc, span, sps, alpha=0.35):
+    h = orc.RRCFilter.generateCoefficents(span, alpha, sps * 1000, 1000)
+    return orc.real_taps_to_iq(h)
+
+
+@pytest.mark.parametrize("span,sps", [(16, 2), (8, 4), (4, 8), (10, 2), (32, 8), (16, 16), (5, 3), (1, 1)])
+@pytest.mark.parametrize("L", [1, 7, 620, 2560, 2561, 40000])
+def test_streaming_real_taps_matches_oracle(gpu, orc, span, sps, L):
+    taps = _rrc_iq(orc, span, sps)
+    x = _rand_iq(orc, L)
+    want = orc.ComplexFIRFilter(taps).Filter(x)
+    got = gpu.ComplexFIRFilter(taps).Filter(x)
+    scale = max(np.abs(want).max(), 1e-30)
+    assert np.abs(got - want).max() <= REL_TOL * scale
+    ref64 = orc.fir_filter_f64(taps, x)
+    assert np.abs(got - ref64).max() <= REL_TOL * scale
+
+
+@pytest.mark.parametrize("ntaps", [1, 2, 3, 8, 10, 33, 40, 64, 257])
+def test_streaming_complex_taps_matches_oracle(gpu, orc, ntaps):
+    rng = np.random.default_rng(ntaps)
+    taps = (rng.standard_normal(2 * ntaps) / np.sqrt(ntaps)).astype(np.float32)
+    x = _rand_iq(orc, 9000, seed=3)
+    want = orc.ComplexFIRFilter(taps).Filter(x)
+    got = gpu.ComplexFIRFilter(taps).Filter(x)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= REL_TOL * scale
+
+
+@pytest.mark.parametrize("ntaps,cplx", [(21, False), (33, False), (40, True), (7, True), (257, False)])
+def test_exact_mode_is_bit_identical_to_reference_order(gpu, orc, ntaps, cplx):
+    """QPSK_FIR_EXACT reproduces ComplexDotWindow's 8-lane summation order (FIRFilter.cs:165-192)."""
+    rng = np.random.default_rng(100 + ntaps)
+    taps = (rng.standard_normal(2 * ntaps) / np.sqrt(ntaps)).astype(np.float32)
+    if not cplx:
+        taps[1::2] = 0
+    x = _rand_iq(orc, 5000, seed=5)
+    want = orc.ComplexFIRFilter(taps).Filter(x)
+    f = gpu.ComplexFIRFilter(taps)
+    f.set_mode(gpu.FIR_EXACT)
+    got = f.Filter(x)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", ["fast", "exact"])
+def test_chunked_equals_one_shot(gpu, orc, mode):
+    """State carried across calls: arbitrary chunking gives the same stream."""
+    taps = _rrc_iq(orc, 10, 4)
+    x = _rand_iq(orc, 20000, seed=9)
+    f1 = gpu.ComplexFIRFilter(taps)
+    f2 = gpu.ComplexFIRFilter(taps)
+    if mode == "exact":
+        f1.set_mode(gpu.FIR_EXACT)
+        f2.set_mode(gpu.FIR_EXACT)
+    one = f1.Filter(x)
+    cuts = [0, 2, 4, 38, 40, 1000, 1002, 6122, 16000, 40000]
+    parts = [f2.Filter(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    many = np.concatenate(parts)
+    if mode == "exact":
+        assert np.array_equal(one.view(np.uint32), many.view(np.uint32))
+    else:
+        # tile boundaries move with the chunking, the per-output arithmetic does not
+        assert np.array_equal(one.view(np.uint32), many.view(np.uint32))
+    want = orc.ComplexFIRFilter(taps).Filter(x)
+    assert np.abs(one - want).max() <= REL_TOL * np.abs(want).max()
+
+
+def test_state_roundtrip_and_reset(gpu, orc):
+    taps = _rrc_iq(orc, 8, 4)
+    x = _rand_iq(orc, 3000, seed=11)
+    f = gpu.ComplexFIRFilter(taps)
+    f.Filter(x[:2000])
+    st = f.get_state()
+    assert st.shape == (1, 2 * (taps.size // 2 - 1))
+    assert np.array_equal(st[0], x[2000 - st.shape[1]:2000])
+    g = gpu.ComplexFIRFilter(taps)
+    g.set_state(st)
+    assert np.array_equal(f.Filter(x[2000:]), g.Filter(x[2000:]))
+    f.reset()
+    fresh = gpu.ComplexFIRFilter(taps)
+    assert np.array_equal(f.Filter(x[:100]), fresh.Filter(x[:100]))
+
+
+@pytest.mark.parametrize("span,sps,L", [(10, 2, 620), (6, 4, 1), (6, 4, 5), (10, 30, 9000), (16, 2, 2560), (8, 4, 5121)])
+def test_fft_filter_alignment_and_values(gpu, orc, span, sps, L):
+    """fftFilter: stateless, same length, offset N-1 (FIRFilter.cs:130-138)."""
+    taps = _rrc_iq(orc, span, sps, 0.9)
+    x = _rand_iq(orc, L, seed=13)
+    want = orc.ComplexFIRFilter(taps).fftFilter(x)
+    f = gpu.ComplexFIRFilter(taps)
+    got = f.fftFilter(x)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= REL_TOL * max(np.abs(want).max(), 1e-30)
+    # stateless: a second call gives the same answer and does not disturb the streaming state
+    assert np.array_equal(f.fftFilter(x), got)
+
+
+def test_fft_filter_complex_taps(gpu, orc):
+    rng = np.random.default_rng(5)
+    taps = rng.standard_normal(2 * 19).astype(np.float32)
+    x = _rand_iq(orc, 3001, seed=17)
+    want = orc.ComplexFIRFilter(taps).fftFilter(x)
+    got = gpu.ComplexFIRFilter(taps).fftFilter(x)
+    assert np.abs(got - want).max() <= REL_TOL * np.abs(want).max()
+
+
+def test_batch_channels_are_independent(gpu, orc):
+    taps = _rrc_iq(orc, 10, 4)
+    C, L = 7, 6000
+    x = np.stack([_rand_iq(orc, L, seed=21, stream=c) for c in range(C)])
+    f = gpu.ComplexFIRFilter(taps, channels=C)
+    got1 = f.Filter(x[:, :5000])
+    got2 = f.Filter(x[:, 5000:])
+    got = np.concatenate([got1, got2], axis=1)
+    for c in range(C):
+        want = orc.ComplexFIRFilter(taps).Filter(x[c])
+        assert np.abs(got[c] - want).max() <= REL_TOL * np.abs(want).max()
+
+
+def test_error_behaviour_matches_reference(gpu, orc):
+    Q, O = gpu, orc
+    for mod in (Q, O):
+        with pytest.raises(mod.ArgumentNullException):
+            mod.ComplexFIRFilter(None)
+        with pytest.raises(mod.ArgumentException):
+            mod.ComplexFIRFilter(np.zeros(3, np.float32))     # odd length (FIRFilter.cs:32)
+        with pytest.raises(mod.ArgumentException):
+            mod.ComplexFIRFilter(np.zeros(0, np.float32))     # empty (FIRFilter.cs:33)
+        f = mod.ComplexFIRFilter(np.ones(4, np.float32))
+        with pytest.raises(mod.ArgumentException):
+            f.Filter(np.zeros(3, np.float32))                 # odd input (:82)
+        with pytest.raises(mod.ArgumentException):
+            f.Filter(np.zeros(4, np.float32), out_len=2)      # short output (:83)
+        with pytest.raises(mod.ArgumentException):
+            f.fftFilter(np.zeros(5, np.float32))              # odd (:99)
+        assert f.fftFilter(np.zeros(0, np.float32)).size == 0  # empty -> empty (:100)
+        assert f.Filter(np.zeros(0, np.float32)).size == 0
+
+
+def test_device_resident_large_stream_linearity(gpu, orc):
+    """Full-size property check (no oracle at this size): FIR is linear and shift-invariant."""
+    import torch
+    taps = _rrc_iq(orc, 16, 2)
+    n = 1 << 22
+    x = torch.empty(2 * n, dtype=torch.float32, device="cuda")
+    gpu.fill_uniform_dev(1, 0, 0, 2 * n, x.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    y = torch.empty_like(x)
+    s = torch.cuda.current_stream().cuda_stream
+    f = gpu.ComplexFIRFilter(taps)
+    f.filter_dev(x.data_ptr(), y.data_ptr(), 2 * n, stream=s)
+    x2 = (2.0 * x).contiguous()
+    y2 = torch.empty_like(x)
+    g = gpu.ComplexFIRFilter(taps)
+    g.filter_dev(x2.data_ptr(), y2.data_ptr(), 2 * n, stream=s)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, 2.0 * y)          # scaling by 2 is exact in binary fp
+    # spot-check a window deep inside the stream against the oracle
+    lo = (n // 2) * 2
+    seg = x[lo - 2 * 64: lo + 2 * 1000].cpu().numpy()
+    want = orc.ComplexFIRFilter(taps).Filter(seg)[2 * 64:]
+    got = y[lo: lo + 2 * 1000].cpu().numpy()
+    assert np.abs(got - want).max() <= REL_TOL * np.abs(want).max()
