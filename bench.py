@@ -189,7 +189,12 @@ def main():
     Q.set_device(local)
 
     n = 1 << args.log2_samples
-    stream = torch.cuda.current_stream().cuda_stream
+    # an explicit (non-default) stream: a NULL stream handle means "the handle's own stream" in the C ABI,
+    # and CUDA events must be recorded on the stream the kernels are launched on
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     x = torch.empty(2 * n, dtype=torch.float32, device="cuda")
     y = torch.empty(2 * n, dtype=torch.float32, device="cuda")
     Q.fill_uniform_dev(1, rank, 0, 2 * n, x.data_ptr(), stream)
@@ -266,11 +271,9 @@ def main():
     if not args.no_e2e:
         hin = Q.PinnedBuffer(2 * n)
         hout = Q.PinnedBuffer(2 * n)
-        xin = x.cpu().numpy() if False else None
         torch.cuda.synchronize()
-        # fill the pinned input from the device copy (untimed)
-        import ctypes as C
-        torch.from_numpy(hin.array).copy_(x)
+        torch.from_numpy(hin.array).copy_(x)  # fill the pinned input from the device copy (untimed)
+        torch.cuda.synchronize()
         for _, f in filters:
             f.reset()
         k_e2e = max(1, min(args.steps, 3))

@@ -178,3 +178,116 @@ class ComplexFIRFilter(_Handle):
     def set_state(self, hist):
         h = _f32(hist)
         check(lib().qpsk_fir_set_state(self._h, h.ctypes.data_as(N.f32p), h.size))
+
+
+# ---- a7-a8 ----------------------------------------------------------------------------------
+def fll_design(sps: float, rolloff: float, filterSize: int):
+    """DesignFilter (MS/Models/Band-Edge Filter.cs:132-183): (lower_iq, upper_iq)."""
+    lo = np.empty(2 * max(filterSize, 0), np.float32)
+    up = np.empty(2 * max(filterSize, 0), np.float32)
+    check(lib().qpsk_fll_design(sps, rolloff, filterSize, lo.ctypes.data_as(N.f32p), up.ctypes.data_as(N.f32p)))
+    return lo, up
+
+
+class FLLBandEdgeFilter(_Handle):
+    """FLLBandEdgeFilter (MS/Models/Band-Edge Filter.cs:14-203) on the GPU, one thread per stream."""
+    _destroy = "qpsk_fll_destroy"
+
+    def __init__(self, sps, rolloff, filterSize, bandwidth, channels: int = 1):
+        super().__init__()
+        self.filterSize = filterSize
+        self.channels = channels
+        self._design = (sps, rolloff, filterSize)
+        check(lib().qpsk_fll_create_batch(sps, rolloff, filterSize, bandwidth, channels, C.byref(self._h)))
+
+    def taps(self):
+        return fll_design(*self._design)
+
+    def Process(self, inputIQ, out_len=None) -> np.ndarray:
+        x = _f32(inputIQ)
+        n = x.shape[-1] if x.ndim == 2 else x.size
+        y = np.empty(x.shape if out_len is None else out_len, np.float32)
+        cap = y.shape[-1] if y.ndim == 2 else y.size
+        check(lib().qpsk_fll_process(self._h, _ptr(x), _ptr(y), n, cap))
+        return y
+
+    def process_dev(self, d_in, d_out, n_floats, in_stride=0, out_stride=0, stream=0):
+        check(lib().qpsk_fll_process_dev(self._h, d_in, d_out, n_floats, in_stride or n_floats, out_stride or n_floats, stream))
+
+    @property
+    def state(self):
+        p = np.empty(self.channels, np.float32)
+        f = np.empty(self.channels, np.float32)
+        check(lib().qpsk_fll_get_state(self._h, p.ctypes.data_as(N.f32p), f.ctypes.data_as(N.f32p)))
+        return (float(p[0]), float(f[0])) if self.channels == 1 else (p, f)
+
+    @state.setter
+    def state(self, pf):
+        p = _f32(np.broadcast_to(np.asarray(pf[0], np.float32), (self.channels,)))
+        f = _f32(np.broadcast_to(np.asarray(pf[1], np.float32), (self.channels,)))
+        check(lib().qpsk_fll_set_state(self._h, p.ctypes.data_as(N.f32p), f.ctypes.data_as(N.f32p)))
+
+
+# ---- a9 ---------------------------------------------------------------------------------------
+class MuellerMuller(_Handle):
+    """MuellerMuller (MS/Models/MuellerMuller.cs:17-250) on the GPU."""
+    _destroy = "qpsk_mm_destroy"
+
+    def __init__(self, samplesPerSymbol, kp, ki, channels: int = 1):
+        super().__init__()
+        self.channels = channels
+        check(lib().qpsk_mm_create_batch(samplesPerSymbol, kp, ki, channels, C.byref(self._h)))
+
+    def Process(self, incomingMfSamplesIQ, cap_floats=None):
+        """Returns the symbols (interleaved IQ).  Batch handles: list of per-channel arrays."""
+        x = _f32(incomingMfSamplesIQ)
+        n = x.shape[-1] if x.ndim == 2 else x.size
+        cap = n if cap_floats is None else cap_floats
+        y = np.zeros((self.channels, max(cap, 0)), np.float32)
+        ns = np.zeros(self.channels, np.int32)
+        check(lib().qpsk_mm_process(self._h, _ptr(x), n, _ptr(y), cap, ns.ctypes.data_as(N.i32p)))
+        outs = [y[c, : 2 * ns[c]].copy() for c in range(self.channels)]
+        return outs[0] if self.channels == 1 else outs
+
+    @property
+    def state(self):
+        b = np.empty(self.channels, np.int32)
+        q = np.empty(self.channels, np.int32)
+        mu = np.empty(self.channels, np.float64)
+        it = np.empty(self.channels, np.float64)
+        check(lib().qpsk_mm_get_state(self._h, b.ctypes.data_as(N.i32p), mu.ctypes.data_as(N.f64p),
+                                      it.ctypes.data_as(N.f64p), q.ctypes.data_as(N.i32p)))
+        if self.channels == 1:
+            return dict(baseIndex=int(b[0]), mu=float(mu[0]), ncoIntegral=float(it[0]), queued=int(q[0]))
+        return dict(baseIndex=b, mu=mu, ncoIntegral=it, queued=q)
+
+
+def mm_gains_from_bw(sym_bw: float):
+    kp, ki = C.c_double(), C.c_double()
+    check(lib().qpsk_mm_gains_from_bw(sym_bw, C.byref(kp), C.byref(ki)))
+    return kp.value, ki.value
+
+
+# ---- a10 --------------------------------------------------------------------------------------
+class CostasLoopQpsk(_Handle):
+    """CostasLoopQpsk (MS/Models/CostasLoopQpsk.cs:19-131) on the GPU."""
+    _destroy = "qpsk_costas_destroy"
+
+    def __init__(self, sampleRate, loopBandwidthHz, damping=0.707, channels: int = 1):
+        super().__init__()
+        self.channels = channels
+        check(lib().qpsk_costas_create_batch(sampleRate, loopBandwidthHz, damping, channels, C.byref(self._h)))
+
+    def Process(self, iqIn, out_len=None) -> np.ndarray:
+        x = _f32(iqIn)
+        n = x.shape[-1] if x.ndim == 2 else x.size
+        y = np.empty(x.shape if out_len is None else out_len, np.float32)
+        cap = y.shape[-1] if y.ndim == 2 else y.size
+        check(lib().qpsk_costas_process(self._h, _ptr(x), _ptr(y), n, cap))
+        return y
+
+    def GetState(self):
+        t = np.empty(self.channels, np.float64)
+        f = np.empty(self.channels, np.float64)
+        check(lib().qpsk_costas_get_state(self._h, t.ctypes.data_as(N.f64p), f.ctypes.data_as(N.f64p)))
+        return (float(t[0]), float(f[0])) if self.channels == 1 else (t, f)

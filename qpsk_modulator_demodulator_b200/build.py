@@ -16,6 +16,9 @@ LIB = os.path.join(LIBDIR, "libqpskcuda.so")
 
 SOURCES = ["core.cu", "fir.cu", "util.cu", "loops.cu", "modem.cu", "channel.cu", "stubs.cu"]
 
+# serial-loop kernels restate C# arithmetic in which RyuJIT never fuses a*b+c: no FMA contraction there
+PER_FILE_FLAGS = {"loops.cu": ["--fmad=false"], "modem.cu": ["--fmad=false"], "channel.cu": ["--fmad=false"]}
+
 NVCC_FLAGS = [
     "-std=c++17", "-O3",
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -50,7 +53,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJDIR, s.replace(".cu", ".o"))
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + PER_FILE_FLAGS.get(s, []) + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", src, "-o", obj]
             jobs.append((s, cmd))
 
     def run(job):

@@ -1,0 +1,219 @@
+// loops.cuh — the serial feedback loops, one thread per independent stream, recurrences kept exactly
+// sequential and in the reference's precisions.  This translation unit family is compiled with
+// --fmad=false: RyuJIT never fuses a*b+c, so every product and sum below rounds separately.
+//
+//   FllState/fll_step      FLLBandEdgeFilter.Process   MS/Models/Band-Edge Filter.cs:102-129,185-195
+//   MmState/mm_*           MuellerMuller.Process       MS/Models/MuellerMuller.cs:52-136,160-198
+//   CostasState/costas_step CostasLoopQpsk.Process     MS/Models/CostasLoopQpsk.cs:63-92
+#pragma once
+#include "common.cuh"
+#include "design.h"
+
+namespace qpsk {
+
+// ---------------------------------------------------------------------------------------------
+// FLL
+// ---------------------------------------------------------------------------------------------
+struct FllParams {
+  float beta, alpha, max_freq, min_freq;
+  int n_taps;
+};
+
+// The two band-edge filters see the same input and upper = conj(lower) (Band-Edge Filter.cs:176-178),
+// so one ring of past outputs and the four products a*xI, b*xQ, a*xQ, b*xI serve both; sums keep
+// ComplexDotWindow's order (8 lane partials over the chronological window, lanes 0..7, scalar
+// tail: FIRFilter.cs:165-192).  (-b)*x == -(b*x) and p - (-q) == p + q exactly, so sharing the
+// products is bit-neutral.
+//   ring:  float2 ring[n_taps] of this stream, element i at ring[i*ring_stride]
+//   tapI/tapQ: lower-filter taps reversed (rev[i] = lower[N-1-i]), shared memory
+__device__ __forceinline__ void fll_step(const FllParams& P, const float* __restrict__ tapI,
+                                         const float* __restrict__ tapQ, float2* ring, int ring_stride, int& head,
+                                         float& phase, float& freq, float inI, float inQ, float& outI, float& outQ) {
+  float s, c;
+  sincos_f32_exact(phase, &s, &c);                 // MathF.Cos/Sin(phase) :108-109
+  outI = inI * c - inQ * s;                        // :111
+  outQ = inI * s + inQ * c;                        // :112
+  const int N = P.n_taps;
+  // write the newest sample over the oldest, then the window starts at the next slot
+  ring[head * ring_stride] = make_float2(outI, outQ);
+  head = (head + 1 == N) ? 0 : head + 1;           // head = oldest element = window start
+  float loI[8], loQ[8], upI[8], upQ[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) loI[l] = loQ[l] = upI[l] = upQ[l] = 0.f;
+  const int nVec = N - (N & 7);
+  int idx = head;
+  for (int i = 0; i < nVec; i += 8) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const float2 x = ring[idx * ring_stride];
+      idx = (idx + 1 == N) ? 0 : idx + 1;
+      const float a = tapI[i + l], b = tapQ[i + l];
+      const float p1 = a * x.x, p2 = b * x.y, p3 = a * x.y, p4 = b * x.x;
+      loI[l] = loI[l] + (p1 - p2);
+      loQ[l] = loQ[l] + (p3 + p4);
+      upI[l] = upI[l] + (p1 + p2);
+      upQ[l] = upQ[l] + (p3 - p4);
+    }
+  }
+  float aLoI = 0.f, aLoQ = 0.f, aUpI = 0.f, aUpQ = 0.f;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) {
+    aLoI += loI[l]; aLoQ += loQ[l]; aUpI += upI[l]; aUpQ += upQ[l];
+  }
+  for (int i = nVec; i < N; ++i) {
+    const float2 x = ring[idx * ring_stride];
+    idx = (idx + 1 == N) ? 0 : idx + 1;
+    const float a = tapI[i], b = tapQ[i];
+    const float p1 = a * x.x, p2 = b * x.y, p3 = a * x.y, p4 = b * x.x;
+    aLoI += (p1 - p2); aLoQ += (p3 + p4); aUpI += (p1 + p2); aUpQ += (p3 - p4);
+  }
+  const float powUpper = aUpI * aUpI + aUpQ * aUpQ;  // :118
+  const float powLower = aLoI * aLoI + aLoQ * aLoQ;  // :119
+  const float error = powLower - powUpper;           // :121
+  freq += P.beta * error;                            // :124
+  phase += freq + P.alpha * error;                   // :125
+  if (phase > kTwoPiF || phase < -kTwoPiF) phase = remainderf(phase, kTwoPiF);  // :185-189
+  if (freq > P.max_freq) freq = P.max_freq;          // :191-195
+  else if (freq < P.min_freq) freq = P.min_freq;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mueller-Muller
+// ---------------------------------------------------------------------------------------------
+struct MmState {
+  double mu, integral;
+  float prevSI, prevSQ, prevDI, prevDQ;
+  int base_index;
+  int has_prev;
+  int queued;  // complex samples carried in the queue
+  int pad;
+};
+
+struct MmParams {
+  double sps, kp, ki;
+};
+
+// logical buffer = [queue(0..queued) | incoming]
+struct MmView {
+  const float2* queue;
+  const float2* in;
+  int queued;
+  __device__ __forceinline__ float2 at(int k) const { return (k < queued) ? queue[k] : in[k - queued]; }
+};
+
+// CubicLagrange4 (MuellerMuller.cs:160-190): fp32, mu cast to float, products/sums left to right
+__device__ __forceinline__ void mm_interp(const MmView& v, int n, double mu, float& oI, float& oQ) {
+  const float2 xm1 = v.at(n - 1), x0 = v.at(n), x1 = v.at(n + 1), x2 = v.at(n + 2);
+  const float t = (float)mu;
+  const float tm1 = t - 1.f, tm2 = t - 2.f, tp1 = t + 1.f;
+  const float sixth = 1.f / 6.f, half = 1.f / 2.f;
+  const float c_m1 = -(t * tm1 * tm2) * sixth;
+  const float c_0 = (tp1 * tm1 * tm2) * half;
+  const float c_1 = -(tp1 * t * tm2) * half;
+  const float c_2 = (tp1 * t * tm1) * sixth;
+  oI = c_m1 * xm1.x + c_0 * x0.x + c_1 * x1.x + c_2 * x2.x;
+  oQ = c_m1 * xm1.y + c_0 * x0.y + c_1 * x1.y + c_2 * x2.y;
+}
+
+// One pass of the `while` body (:62-120).  Returns false when the loop must stop *before* emitting
+// (output full, :101-102).  `stop_after` is set when the post-advance break (:118-119) fires.
+__device__ __forceinline__ bool mm_symbol(const MmParams& P, MmState& S, const MmView& v, int buf_count, bool room,
+                                          float& currI, float& currQ, bool& stop_after) {
+  mm_interp(v, S.base_index, S.mu, currI, currQ);
+  const float decI = (currI >= 0.f) ? 1.f : -1.f;   // GetSignQpsk :194-198
+  const float decQ = (currQ >= 0.f) ? 1.f : -1.f;
+  double advance;
+  if (S.has_prev) {
+    const double term1 = (double)S.prevDI * currI + (double)S.prevDQ * currQ;   // :78
+    const double term2 = (double)decI * S.prevSI + (double)decQ * S.prevSQ;     // :79
+    const double e = term1 - term2;
+    S.integral += P.ki * e;                          // :83
+    double corr = P.kp * e + S.integral;             // :84
+    if (corr > 0.1) corr = 0.1;                      // :87-89
+    if (corr < -0.1) corr = -0.1;
+    advance = P.sps + corr;
+  } else {
+    S.has_prev = 1;
+    advance = P.sps;
+  }
+  if (!room) return false;                           // :101-102 (loop state already touched)
+  S.prevSI = currI; S.prevSQ = currQ; S.prevDI = decI; S.prevDQ = decQ;
+  const double newTime = S.base_index + S.mu + advance;   // :113
+  S.base_index = (int)floor(newTime);
+  S.mu = newTime - S.base_index;
+  stop_after = (S.base_index + 1 >= buf_count);      // :118-119
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Costas
+// ---------------------------------------------------------------------------------------------
+struct CostasState {
+  double theta, freq;
+};
+struct CostasParams {
+  double alpha, beta;
+};
+
+__device__ __forceinline__ void costas_step(const CostasParams& P, CostasState& S, float inI, float inQ, float& outI,
+                                            float& outQ) {
+  double s, c;
+  sincos(S.theta, &s, &c);
+  const double mi = (double)inI * c + (double)inQ * s;   // :72
+  const double mq = (double)inQ * c - (double)inI * s;   // :73
+  outI = (float)mi;
+  outQ = (float)mq;
+  const float estI = (outI >= 0.f) ? 1.f : -1.f;
+  const float estQ = (outQ >= 0.f) ? 1.f : -1.f;
+  const double pe = (double)estI * mq - (double)estQ * mi;   // :82
+  S.freq += P.beta * pe;
+  S.theta += S.freq + P.alpha * pe;
+  const double kPi = 3.14159265358979323846, kTwoPi = 2.0 * kPi;
+  if (S.theta > kPi) S.theta -= kTwoPi;
+  else if (S.theta < -kPi) S.theta += kTwoPi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// engines (host side)
+// ---------------------------------------------------------------------------------------------
+struct FllEngine {
+  int channels = 1, n_taps = 0;
+  FllParams P{};
+  std::vector<float> lower, upper;
+  DevBuf<float> d_taps;      // [2][N] reversed lower taps, planar
+  DevBuf<float2> d_ring;     // [N][C] ring of past outputs
+  DevBuf<int> d_head;        // [C]
+  DevBuf<float2> d_pf;       // [C] (phase, freq)
+  cudaStream_t stream = nullptr;
+  ~FllEngine();
+  int init(float sps, float rolloff, int size, float bw, int channels_in);
+  int process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t ldy, cudaStream_t s);
+};
+
+struct MmEngine {
+  int channels = 1;
+  MmParams P{};
+  DevBuf<MmState> d_state;
+  DevBuf<float2> d_queue[2];  // [C][qcap], ping-pong
+  int qcur = 0;
+  int64_t qcap = 0;
+  int64_t q_bound = 0;        // host-side upper bound of queued samples
+  cudaStream_t stream = nullptr;
+  ~MmEngine();
+  int init(double sps, double kp, double ki, int channels_in);
+  int ensure_queue(int64_t need, cudaStream_t s);
+  int process_dev(const float2* x, int64_t L, int64_t ldx, float2* y, int64_t cap_sym, int64_t ldy, int* d_nsym,
+                  cudaStream_t s);
+};
+
+struct CostasEngine {
+  int channels = 1;
+  CostasParams P{};
+  DevBuf<CostasState> d_state;
+  cudaStream_t stream = nullptr;
+  ~CostasEngine();
+  int init(double fs, double bw, double damping, int channels_in);
+  int process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t ldy, const int* d_nsym, cudaStream_t s);
+};
+
+}  // namespace qpsk

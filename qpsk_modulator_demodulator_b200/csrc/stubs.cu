@@ -2,25 +2,6 @@
 #include "common.cuh"
 #define S(...) { return QPSK_ERR_UNSUPPORTED; }
 extern "C" {
-int qpsk_fll_create(float, float, int, float, qpsk_fll**) S()
-int qpsk_fll_create_batch(float, float, int, float, int, qpsk_fll**) S()
-int qpsk_fll_destroy(qpsk_fll*) S()
-int qpsk_fll_process(qpsk_fll*, const float*, float*, int64_t, int64_t) S()
-int qpsk_fll_process_dev(qpsk_fll*, const float*, float*, int64_t, int64_t, int64_t, void*) S()
-int qpsk_fll_get_state(qpsk_fll*, float*, float*) S()
-int qpsk_fll_set_state(qpsk_fll*, const float*, const float*) S()
-int qpsk_mm_create(double, double, double, qpsk_mm**) S()
-int qpsk_mm_create_batch(double, double, double, int, qpsk_mm**) S()
-int qpsk_mm_destroy(qpsk_mm*) S()
-int qpsk_mm_process(qpsk_mm*, const float*, int64_t, float*, int64_t, int*) S()
-int qpsk_mm_process_dev(qpsk_mm*, const float*, int64_t, int64_t, float*, int64_t, int64_t, int*, void*) S()
-int qpsk_mm_get_state(qpsk_mm*, int*, double*, double*, int*) S()
-int qpsk_costas_create(double, double, double, qpsk_costas**) S()
-int qpsk_costas_create_batch(double, double, double, int, qpsk_costas**) S()
-int qpsk_costas_destroy(qpsk_costas*) S()
-int qpsk_costas_process(qpsk_costas*, const float*, float*, int64_t, int64_t) S()
-int qpsk_costas_process_dev(qpsk_costas*, const float*, float*, int64_t, int64_t, int64_t, const int*, void*) S()
-int qpsk_costas_get_state(qpsk_costas*, double*, double*) S()
 int qpsk_mod_create(int, int, double, int, int, const char*, qpsk_mod**) S()
 int qpsk_mod_destroy(qpsk_mod*) S()
 int qpsk_mod_taps(const qpsk_mod*, double*, int, int*) S()

@@ -158,10 +158,12 @@ def test_device_resident_large_stream_linearity(gpu, orc):
     import torch
     taps = _rrc_iq(orc, 16, 2)
     n = 1 << 22
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    s = ts.cuda_stream     # non-zero: a NULL stream means "the handle's own stream" in the C ABI
     x = torch.empty(2 * n, dtype=torch.float32, device="cuda")
-    gpu.fill_uniform_dev(1, 0, 0, 2 * n, x.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    gpu.fill_uniform_dev(1, 0, 0, 2 * n, x.data_ptr(), s)
     y = torch.empty_like(x)
-    s = torch.cuda.current_stream().cuda_stream
     f = gpu.ComplexFIRFilter(taps)
     f.filter_dev(x.data_ptr(), y.data_ptr(), 2 * n, stream=s)
     x2 = (2.0 * x).contiguous()
