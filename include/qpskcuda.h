@@ -182,7 +182,9 @@ QPSK_API int qpsk_demod_create_batch(int sample_rate, int symbol_rate, float rrc
                                      int64_t max_frame_bytes, int channels, qpsk_demod** out);
 QPSK_API int qpsk_demod_destroy(qpsk_demod* d);
 QPSK_API int qpsk_demod_set_fir_mode(qpsk_demod* d, int mode);
-/* DeModulate(ReadOnlySpan<float>) :345-425 -> '0'/'1' chars (not NUL-terminated) */
+/* DeModulate(ReadOnlySpan<float>) :345-425 -> '0'/'1' chars (not NUL-terminated).  Batch handles:
+ * iq_in [channels][n_floats], bits_out [channels][cap], n_bits[channels] (same layout rule for the
+ * other host entry points below). */
 QPSK_API int qpsk_demod_bits(qpsk_demod* d, const float* iq_in, int64_t n_floats, char* bits_out,
                              int64_t cap, int64_t* n_bits);
 /* DeModulateBytes :169-259 (DeModulateTextUtf8 :262-277 = this + UTF-8 decode) */
@@ -195,12 +197,25 @@ QPSK_API int qpsk_demod_constellation(qpsk_demod* d, const float* iq_in, int64_t
                                       float* sym_iq_out, int64_t cap_floats, int64_t* n_sym);
 /* batch, device-resident chain: d_in [channels][n_floats] (stride in floats).  Outputs per
  * channel: bits as bytes 0/1 ([channels][bits_cap], the DeModulate string after TSC strip),
- * d_n_bits[channels].  Enqueued on `stream`, no synchronisation. */
+ * d_n_bits[channels].  bits_cap must be even and >= qpsk_demod_bits_bound(n_floats).
+ * Enqueued on `stream`, no synchronisation. */
 QPSK_API int qpsk_demod_bits_dev(qpsk_demod* d, const float* d_in, int64_t n_floats, int64_t in_stride_floats,
                                  uint8_t* d_bits, int64_t bits_cap, int64_t* d_n_bits, void* stream);
+/* most bits one call over n_floats can return per channel (every symbol advances >= sps-0.1 samples) */
+QPSK_API int qpsk_demod_bits_bound(qpsk_demod* d, int64_t n_floats, int64_t* bits_cap);
+/* DeModulateBytes, batch/device: payloads to d_payload [channels][payload_cap]; d_n_bytes[c] = payload
+ * length (0 = no complete frame in this call; > payload_cap = truncated copy) */
+QPSK_API int qpsk_demod_bytes_dev(qpsk_demod* d, const float* d_in, int64_t n_floats, int64_t in_stride_floats,
+                                  const uint8_t* start_marker, int64_t n_start, const uint8_t* end_marker, int64_t n_end,
+                                  uint8_t* d_payload, int64_t payload_cap, int64_t* d_n_bytes, void* stream);
+/* deModulateConstellation, batch/device: d_sym [channels][sym_stride_floats], d_n_sym[channels] */
+QPSK_API int qpsk_demod_constellation_dev(qpsk_demod* d, const float* d_in, int64_t n_floats, int64_t in_stride_floats,
+                                          float* d_sym, int64_t sym_stride_floats, int* d_n_sym, void* stream);
 /* per-channel loop state after the last call */
 QPSK_API int qpsk_demod_loop_state(qpsk_demod* d, double* costas_theta, double* costas_freq, double* mm_mu,
                                    double* mm_integral, float* fll_phase, float* fll_freq);
+/* _inFrame (:62) per channel */
+QPSK_API int qpsk_demod_in_frame(qpsk_demod* d, int* in_frame);
 
 /* ---- synthetic channel: NCO pair + AWGN + static multipath ------------------- */
 /* NCO: TB/Simulated/LocalOscilator.cs:5-194; noise: TB/HelperModels.cs:17-45; System.Random is
@@ -229,9 +244,14 @@ QPSK_API int qpsk_fill_uniform_dev(uint64_t seed, uint64_t stream_id, int64_t fi
 /* random payload bytes: out[c][k] = top byte of rng(seed, 4*(first_channel+c)+3, k) */
 QPSK_API int qpsk_fill_bytes_dev(uint64_t seed, int first_channel, int channels, int64_t n_bytes, uint8_t* d_out, void* stream);
 
+/* bits[c][8k+j] = bit (7-j) of bytes[c][k] as bytes 0/1 (BitPacker.BytesToBitString, HelperFunctions.cs:14-29) */
+QPSK_API int qpsk_unpack_bits_dev(const uint8_t* d_bytes, int64_t n_bytes, int64_t bytes_stride, int channels,
+                                  uint8_t* d_bits, int64_t bits_stride, void* stream);
+
 /* ---- K6  per-channel BER counters ---------------------------------------------------------- */
-/* bits as bytes 0/1.  errors[c] = Hamming distance over min(n_rx[c], n_ref) bits + |n_rx[c]-n_ref|;
- * counters[c] = {errors, compared_bits}.  ref_stride 0 = one reference for all channels. */
+/* bits as bytes 0/1.  errors[c] = Hamming distance over min(n_rx[c], n_ref) bits + max(0, n_ref-n_rx[c])
+ * (bits that never arrived count as errors, extra trailing bits are ignored);
+ * counters[c] = {errors, n_ref}.  ref_stride 0 = one reference for all channels. */
 QPSK_API int qpsk_ber_count_dev(const uint8_t* d_rx_bits, int64_t rx_stride, const int64_t* d_n_rx,
                                 const uint8_t* d_ref_bits, int64_t ref_stride, int64_t n_ref,
                                 int channels, uint32_t* d_counters, void* stream);

@@ -67,6 +67,7 @@ def _declare(L):
         "orc_rng_u64": (u64, [u64, u64, u64]),
         "orc_rng_double": (d, [u64, u64, u64]),
         "orc_fill_uniform": (None, [u64, u64, i64, i64, _f32p]),
+        "orc_fill_bytes": (None, [u64, u64, i64, i64, _u8p]),
         "orc_rrc_taps": (i, [d, d, i, i, _f64p, i, ip]),
         "orc_fir_create": (i, [_f32p, i, _vpp]),
         "orc_fir_destroy": (None, [vp]),
@@ -161,6 +162,12 @@ def fill_uniform(seed: int, stream: int, first: int, n: int) -> np.ndarray:
     out = np.empty(n, np.float32)
     lib().orc_fill_uniform(seed, stream, first, n, _fp(out))
     return out
+
+
+def fill_bytes(seed: int, stream: int, first: int, n: int) -> bytes:
+    out = np.empty(n, np.uint8)
+    lib().orc_fill_bytes(seed, stream, first, n, _up(out))
+    return out.tobytes()
 
 
 class RRCFilter:

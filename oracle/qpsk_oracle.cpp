@@ -230,10 +230,17 @@ struct Fir {
 constexpr float kPiF = 3.14159274101257324f;     // MathF.PI
 constexpr float kTwoPiF = 2.0f * kPiF;           // :16
 
+// MathF.Sin / MathF.Cos model: the correctly rounded fp32 result, obtained by evaluating in fp64 and
+// rounding once.  (glibc's sinf/cosf are NOT correctly rounded — about 1.3 % of arguments differ by
+// one ulp — and neither the Windows CRT behind .NET's MathF nor CUDA's sinf is bit-specified, so the
+// oracle and the CUDA path both use this definition; DESIGN.md "transcendentals".)
+inline float cr_sinf(float x) { return (float)std::sin((double)x); }
+inline float cr_cosf(float x) { return (float)std::cos((double)x); }
+
 inline float sincf_(float x) {                   // :197-202
   if (x == 0.0f) return 1.0f;
   float arg = kPiF * x;
-  return sinf(arg) / arg;
+  return cr_sinf(arg) / arg;
 }
 
 struct Fll {
@@ -273,7 +280,7 @@ struct Fll {
     for (int i = 0; i < numTaps; i++) {
       float k = (float)(i - mid) / (2.0f * sps);
       float angle = -kTwoPiF * (1.0f + rolloff) * k;
-      float wc = cosf(angle), ws = sinf(angle);
+      float wc = cr_cosf(angle), ws = cr_sinf(angle);
       float li = bb[i] * wc, lq = bb[i] * ws;
       int t = i << 1;
       tapsLowerIQ[t] = li; tapsLowerIQ[t + 1] = lq;
@@ -284,7 +291,7 @@ struct Fll {
   }
 
   inline void process1(float inI, float inQ, float& outI, float& outQ) {  // :102-129
-    float c = cosf(phase), s = sinf(phase);
+    float c = cr_cosf(phase), s = cr_sinf(phase);
     float a = inI * c, b = inQ * s; outI = a - b;
     float d = inI * s, e = inQ * c; outQ = d + e;
     float upI, upQ, loI, loQ;
@@ -755,6 +762,11 @@ ORC_API void orc_fill_uniform(uint64_t seed, uint64_t stream, int64_t first, int
   for (int64_t k = 0; k < n; k++) out[k] = (float)(rng_double(seed, stream, (uint64_t)(first + k)) * 2.0 - 1.0);
 }
 
+// payload generator: byte k of stream s = top byte of rng(seed, s, k)
+ORC_API void orc_fill_bytes(uint64_t seed, uint64_t stream, int64_t first, int64_t n, uint8_t* out) {
+  for (int64_t k = 0; k < n; k++) out[k] = (uint8_t)(rng_u64(seed, stream, (uint64_t)(first + k)) >> 56);
+}
+
 ORC_API int orc_rrc_taps(double span, double beta, int fs, int rs, double* out, int cap, int* n) {
   if (!n) return ORC_ERR_NULL;
   auto h = rrc_taps(span, beta, fs, rs);
@@ -962,6 +974,11 @@ ORC_API int orc_demod_create(int fs, int rs, float alpha, int span, double sym_b
                              int diff, const char* tsc, int use_fll, int64_t ring_capacity, void** out) {
   if (!out) return ORC_ERR_NULL;
   if (ring_capacity <= 0) ring_capacity = 300000000;          // QPSKDeModulator.cs:58
+  if (rs == 0) return ORC_ERR_RANGE;                          // DivideByZeroException in the field initialisers
+  {  // the FLLBandEdgeFilter field initialiser (:35) throws for bad parameters (Band-Edge Filter.cs:42-45)
+    float fsps = (float)(fs / rs), fbw = (float)cfo_bw;
+    if (!(fsps > 0.0f) || alpha < 0 || alpha > 1.0f || !(fbw > 0.0f)) return ORC_ERR_RANGE;
+  }
   *out = new Demod(fs, rs, alpha, span, sym_bw, costas_bw, cfo_bw, diff != 0, tsc, use_fll != 0, ring_capacity);
   return ORC_OK;
 }

@@ -104,11 +104,16 @@ def _signatures():
         "qpsk_demod_create_batch": (i, [i, i, f, i, d, d, d, i, cp, i, i64, i, vpp]),
         "qpsk_demod_destroy": (i, [vp]),
         "qpsk_demod_set_fir_mode": (i, [vp, i]),
-        "qpsk_demod_bits": (i, [vp, vp, i64, vp, i64, i64p]),
-        "qpsk_demod_bytes": (i, [vp, vp, i64, vp, i64, vp, i64, vp, i64, i64p]),
-        "qpsk_demod_constellation": (i, [vp, vp, i64, vp, i64, i64p]),
+        "qpsk_demod_bits": (i, [vp, vp, i64, vp, i64, vp]),
+        "qpsk_demod_bytes": (i, [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
+        "qpsk_demod_constellation": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bits_dev": (i, [vp, vp, i64, i64, vp, i64, vp, vp]),
+        "qpsk_demod_bits_bound": (i, [vp, i64, i64p]),
+        "qpsk_demod_bytes_dev": (i, [vp, vp, i64, i64, vp, i64, vp, i64, vp, i64, vp, vp]),
+        "qpsk_demod_constellation_dev": (i, [vp, vp, i64, i64, vp, i64, vp, vp]),
         "qpsk_demod_loop_state": (i, [vp, f64p, f64p, f64p, f64p, f32p, f32p]),
+        "qpsk_demod_in_frame": (i, [vp, i32p]),
+        "qpsk_unpack_bits_dev": (i, [vp, i64, i64, i, vp, i64, vp]),
         "qpsk_chan_create": (i, [C.POINTER(ChanParams), i, i, vpp]),
         "qpsk_chan_destroy": (i, [vp]),
         "qpsk_chan_apply_dev": (i, [vp, vp, i64, i64, vp, i64, vp]),

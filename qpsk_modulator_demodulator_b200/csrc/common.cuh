@@ -96,8 +96,9 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
         "l"(reinterpret_cast<unsigned long long&>(c)));
   return d;
 }
-// Correctly-rounded-in-practice fp32 sin/cos: evaluate in fp64 and round once.  glibc's sinf/cosf
-// (what the oracle runs) are computed the same way, so results agree except at fp64-level ties.
+// MathF.Sin/Cos model: the correctly rounded fp32 value, i.e. fp64 evaluation rounded once.  The
+// oracle uses the same definition (cr_sinf/cr_cosf), so results agree except where the fp64 value
+// lies within an fp64 ulp of an fp32 rounding boundary (probability ~2^-28 per call).
 __device__ __forceinline__ void sincos_f32_exact(float x, float* s, float* c) {
   double sd, cd;
   sincos((double)x, &sd, &cd);

@@ -90,10 +90,14 @@ std::vector<float> real_taps_as_iq(const std::vector<double>& h) {
 }
 
 // ---- a7: band-edge filter pair (MS/Models/Band-Edge Filter.cs:132-183) -----------------------
+// MathF.Sin/Cos are modelled as the correctly rounded fp32 value (fp64 evaluation rounded once), the
+// same definition the device code uses (sincos_f32_exact) — see DESIGN.md "transcendentals".
+static inline float cr_sinf(float x) { return (float)sin((double)x); }
+static inline float cr_cosf(float x) { return (float)cos((double)x); }
 static inline float sinc_pi(float x) {
   if (x == 0.0f) return 1.0f;
   const float a = kPiF * x;
-  return sinf(a) / a;
+  return cr_sinf(a) / a;
 }
 void design_band_edge(float sps, float rolloff, int size, std::vector<float>& lower, std::vector<float>& upper) {
   const int centre = (size - 1) / 2;
@@ -112,8 +116,8 @@ void design_band_edge(float sps, float rolloff, int size, std::vector<float>& lo
   for (int i = 0; i < size; ++i) {
     const float k = (float)(i - centre) / (2.0f * sps);
     const float ang = -kTwoPiF * (1.0f + rolloff) * k;
-    const float re = base[(size_t)i] * cosf(ang);
-    const float im = base[(size_t)i] * sinf(ang);
+    const float re = base[(size_t)i] * cr_cosf(ang);
+    const float im = base[(size_t)i] * cr_sinf(ang);
     lower[2 * (size_t)i] = re;
     lower[2 * (size_t)i + 1] = im;
     upper[2 * (size_t)i] = re;

@@ -1,0 +1,699 @@
+// demod.cu — K5: QPSKDeModulator on the GPU (MS/QPSKDeModulator.cs:11-456), batched over independent
+// channels.  Compiled with --fmad=false (see loops.cuh).
+//
+// Chain per call (DeModulate :345-425):  [FLL (opt-in; the call at :359 is commented out upstream)] ->
+// RRC matched filter (FirEngine, fir.cu) -> Mueller-Muller (loops.cu) -> decode kernel: Costas +
+// decision + differential decode -> bits -> TSC exact-match strip (:413-422).
+// DeModulateBytes (:169-259): the bits then feed the per-channel framer kernel (8 bit-offset marker
+// hunt, MSB-first packing into a bounded ring, end-marker search).
+// All loop / framer state lives in device memory per channel and persists across calls, so arbitrary
+// chunking of a stream gives the same output as the reference object would.
+#include <string>
+
+#include "fir.cuh"
+#include "loops.cuh"
+
+namespace qpsk {
+
+struct DiffState {
+  int have_prev;
+  float prevI, prevQ;
+  int pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// decode: Costas -> sign decision -> (differential) bits, one thread per channel (:374-408)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+    decode_kernel(const CostasParams P, CostasState* cst_g, DiffState* dst_g, int C, const float2* __restrict__ sym,
+                  long long ld_sym, const int* __restrict__ n_sym, int diff, uint8_t* __restrict__ bits, long long ld_bits,
+                  long long* n_bits) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  CostasState S = cst_g[c];
+  DiffState D = dst_g[c];
+  const float2* sc = sym + (long long)c * ld_sym;
+  uchar2* bc = reinterpret_cast<uchar2*>(bits + (long long)c * ld_bits);
+  const int n = n_sym[c];
+  long long nb = 0;
+  for (int k = 0; k < n; ++k) {
+    const float2 in = sc[k];
+    float rI, rQ;
+    costas_step(P, S, in.x, in.y, rI, rQ);                 // :378
+    const float dI = (rI >= 0.f) ? 1.f : -1.f;             // GetSign (CostasLoopQpsk.cs:52-56)
+    const float dQ = (rQ >= 0.f) ? 1.f : -1.f;
+    unsigned char b0, b1;
+    if (diff) {
+      if (!D.have_prev) {                                  // :390-395 first symbol ever: reference only
+        D.prevI = dI; D.prevQ = dQ; D.have_prev = 1;
+        continue;
+      }
+      const float deltaI = dI * D.prevI + dQ * D.prevQ;    // :397
+      const float deltaQ = dQ * D.prevI - dI * D.prevQ;    // :398
+      D.prevI = dI; D.prevQ = dQ;
+      if (fabsf(deltaI) >= fabsf(deltaQ)) {                // AppendDeltaBits :320-337
+        if (deltaI >= 0.f) { b0 = 0; b1 = 0; } else { b0 = 1; b1 = 1; }
+      } else {
+        if (deltaQ >= 0.f) { b0 = 0; b1 = 1; } else { b0 = 1; b1 = 0; }
+      }
+    } else {                                               // AppendDecisionBits :304-318
+      if (dI < 0.f) { b0 = 0; b1 = (dQ < 0.f) ? 0 : 1; }
+      else { b0 = 1; b1 = (dQ >= 0.f) ? 1 : 0; }
+    }
+    bc[nb >> 1] = make_uchar2(b0, b1);
+    nb += 2;
+  }
+  cst_g[c] = S;
+  dst_g[c] = D;
+  n_bits[c] = nb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TSC strip: rx.IndexOf(tsc) then Substring (:413-422), one warp per channel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    tsc_strip_kernel(const uint8_t* __restrict__ raw, long long ld_raw, const long long* __restrict__ n_raw,
+                     const uint8_t* __restrict__ tsc, int T, uint8_t* __restrict__ out, long long ld_out, long long* n_out,
+                     int C) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const int lane = threadIdx.x & 31;
+  const uint8_t* r = raw + (long long)c * ld_raw;
+  const long long n = n_raw[c];
+  long long first = -1;
+  for (long long base = 0; base + T <= n; base += 32) {
+    const long long idx = base + lane;
+    bool ok = idx + T <= n;
+    for (int j = 0; ok && j < T; ++j) ok = (r[idx + j] == tsc[j]);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m) {
+      first = base + (__ffs(m) - 1);
+      break;
+    }
+  }
+  uint8_t* o = out + (long long)c * ld_out;
+  long long len = 0;
+  if (first >= 0) {
+    const long long start = first + T;
+    len = n - start;
+    for (long long i = lane; i < len; i += 32) o[i] = r[start + i];
+  }
+  if (lane == 0) n_out[c] = len;
+}
+
+// ---------------------------------------------------------------------------------------------
+// framer (DeModulateBytes :169-259), one thread per channel
+// ---------------------------------------------------------------------------------------------
+struct FramerState {
+  int in_frame;
+  int pack_byte;
+  int pack_bits;
+  int carry_len;
+  long long ring_count;
+};
+
+struct FramerArgs {
+  FramerState* st;
+  uint8_t* carry;       // [C][carry_cap] bits 0/1
+  int carry_cap;
+  uint8_t* ring;        // [C][ring_cap] payload bytes of the current frame
+  long long ring_cap;
+  uint8_t* pk;          // [C][pk_ld] scratch: candidate bits packed MSB-first at offset 0
+  long long pk_ld;
+  const uint8_t* rx;    // [C][ld_rx] bits 0/1 of this call
+  long long ld_rx;
+  const long long* n_rx;
+  const uint8_t* markers;  // start | end
+  int ns, ne;
+  uint8_t* payload;     // [C][payload_cap]
+  long long payload_cap;
+  long long* n_payload; // [C] full payload length (may exceed payload_cap: truncated copy)
+  int C;
+};
+
+struct FramerCtx {
+  FramerState S;
+  uint8_t* ring;
+  long long ring_cap;
+};
+
+__device__ __forceinline__ void framer_reset(FramerState& S) {   // ResetFramer :159-167
+  S.in_frame = 0; S.pack_byte = 0; S.pack_bits = 0; S.carry_len = 0; S.ring_count = 0;
+}
+
+// AppendBitsToRing :108-129 over bits[from, to) of a bit accessor.  Returns bytes produced or -1.
+template <typename BitAt>
+__device__ __forceinline__ long long framer_append(FramerCtx& X, BitAt bit_at, long long from, long long to) {
+  long long produced = 0;
+  int pb = X.S.pack_byte, nb = X.S.pack_bits;
+  for (long long k = from; k < to; ++k) {
+    pb = ((pb << 1) | (bit_at(k) ? 1 : 0)) & 0xFF;
+    if (++nb == 8) {
+      if (X.S.ring_count >= X.ring_cap) {          // RingTryWriteByte :96-104
+        X.S.pack_byte = pb; X.S.pack_bits = nb;
+        return -1;
+      }
+      X.ring[X.S.ring_count++] = (uint8_t)pb;
+      ++produced;
+      nb = 0; pb = 0;
+    }
+  }
+  X.S.pack_byte = pb; X.S.pack_bits = nb;
+  return produced;
+}
+
+// RingIndexOf :133-149
+__device__ __forceinline__ long long framer_ring_index_of(const FramerCtx& X, const uint8_t* pat, int np, long long from) {
+  if (np == 0) return 0;
+  if (X.S.ring_count < np) return -1;
+  const long long last = X.S.ring_count - np;
+  for (long long i = (from > 0 ? from : 0); i <= last; ++i) {
+    bool ok = true;
+    for (int j = 0; j < np; ++j)
+      if (X.ring[i + j] != pat[j]) { ok = false; break; }
+    if (ok) return i;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ void framer_emit(const FramerArgs& a, int c, const FramerCtx& X, long long end_at) {
+  uint8_t* out = a.payload + (long long)c * a.payload_cap;
+  const long long ncopy = end_at < a.payload_cap ? end_at : a.payload_cap;
+  for (long long i = 0; i < ncopy; ++i) out[i] = X.ring[i];     // RingCopyOut :151-157
+  a.n_payload[c] = end_at;
+}
+
+__global__ void __launch_bounds__(32) framer_kernel(const FramerArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const long long n_rx = a.n_rx[c];
+  a.n_payload[c] = 0;
+  if (n_rx == 0) return;                                         // :179-180
+  FramerCtx X;
+  X.S = a.st[c];
+  X.ring = a.ring + (long long)c * a.ring_cap;
+  X.ring_cap = a.ring_cap;
+  const uint8_t* rx = a.rx + (long long)c * a.ld_rx;
+  const uint8_t* sm = a.markers;
+  const uint8_t* em = a.markers + a.ns;
+  if (!X.S.in_frame) {
+    uint8_t* carry = a.carry + (long long)c * a.carry_cap;
+    const int cl = X.S.carry_len;
+    const long long cand_len = cl + n_rx;                        // :185
+    auto cand = [&](long long k) -> int { return (k < cl) ? carry[k] : rx[k - cl]; };
+    // pack the candidate bits once (offset 0); byte i at bit offset o is a shift of two neighbours
+    uint8_t* pk = a.pk + (long long)c * a.pk_ld;
+    const long long nb0 = (cand_len + 7) >> 3;
+    for (long long i = 0; i < nb0; ++i) {
+      int v = 0;
+      for (int j = 0; j < 8; ++j) {
+        const long long k = 8 * i + j;
+        v = (v << 1) | ((k < cand_len) ? cand(k) : 0);
+      }
+      pk[i] = (uint8_t)v;
+    }
+    pk[nb0] = 0;
+    for (int o = 0; o < 8; ++o) {                                // :187
+      const long long usable = cand_len - o;
+      if (usable < 8) continue;                                  // BitsToBytes -> empty (:190)
+      const long long nB = usable >> 3;
+      if (a.ns > nB) continue;                                   // IndexOf -> -1
+      long long s = -1;
+      for (long long i = 0; i + a.ns <= nB && s < 0; ++i) {
+        bool ok = true;
+        for (int j = 0; j < a.ns; ++j) {
+          const int hi = pk[i + j], lo = pk[i + j + 1];
+          const int b = o ? (((hi << o) | (lo >> (8 - o))) & 0xFF) : hi;
+          if (b != sm[j]) { ok = false; break; }
+        }
+        if (ok) s = i;
+      }
+      if (s < 0) continue;
+      const long long marker_end = o + 8 * (s + a.ns);           // :198
+      if (marker_end > cand_len) continue;
+      X.S.in_frame = 1;                                          // :202-207
+      X.S.ring_count = 0; X.S.pack_byte = 0; X.S.pack_bits = 0;
+      const long long appended = framer_append(X, cand, marker_end, cand_len);   // :210-211
+      if (appended < 0) {                                        // :212-217
+        framer_reset(X.S);
+        a.st[c] = X.S;
+        return;
+      }
+      const long long end_at = framer_ring_index_of(X, em, a.ne, X.S.ring_count - (appended + a.ne));   // :220
+      if (end_at >= 0) {
+        framer_emit(a, c, X, end_at);
+        framer_reset(X.S);
+      }
+      a.st[c] = X.S;
+      return;                                                    // :226 / :229
+    }
+    // no start marker: keep a tail so it can span calls (:233-235)
+    const long long keep = cand_len < (long long)(a.ns * 8 + 7) ? cand_len : (long long)(a.ns * 8 + 7);
+    const long long src0 = cand_len - keep;
+    for (long long i = 0; i < keep; ++i) carry[i] = (uint8_t)cand(src0 + i);   // src index >= i: in-order copy is safe
+    X.S.carry_len = (int)keep;
+    a.st[c] = X.S;
+    return;
+  }
+  // already inside a frame (:238-258)
+  auto rxbit = [&](long long k) -> int { return rx[k]; };
+  const long long appended = framer_append(X, rxbit, 0, n_rx);
+  if (appended < 0) {
+    framer_reset(X.S);
+    a.st[c] = X.S;
+    return;
+  }
+  const long long end_at = framer_ring_index_of(X, em, a.ne, X.S.ring_count - (appended + a.ne));
+  if (end_at >= 0) {
+    framer_emit(a, c, X, end_at);
+    framer_reset(X.S);
+  }
+  a.st[c] = X.S;
+}
+
+__global__ void bits_to_chars_kernel(const uint8_t* in, char* out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = in[i] ? '1' : '0';
+}
+
+// ---------------------------------------------------------------------------------------------
+// DemodEngine
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxMarkerBytes = 256;
+
+struct DemodEngine {
+  int channels = 1;
+  bool diff = true, has_tsc = false, use_fll = false;
+  std::string tsc;
+  double sps = 0.0;
+  FirEngine mf;
+  FllEngine fll;
+  MmEngine mm;
+  CostasEngine costas;
+  DevBuf<float2> t_fll, t_rrc, t_sym;
+  DevBuf<int> d_nsym;
+  DevBuf<uint8_t> d_raw, d_tsc, d_bits, d_markers, d_carry, d_ring, d_pk, d_payload;
+  DevBuf<long long> d_nraw, d_nbits, d_npayload;
+  DevBuf<DiffState> d_diff;
+  DevBuf<FramerState> d_framer;
+  DevBuf<float2> h_in, h_out;       // device staging for the host entry points
+  std::vector<uint8_t> markers_host;
+  long long ring_cap = 0;
+  long long sym_ld = 0;
+  cudaStream_t stream = nullptr;
+
+  ~DemodEngine() {
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  int init(int fs, int rs, float alpha, int span, double sym_bw, double costas_bw, double cfo_bw, int diff_in,
+           const char* tsc_in, int use_fll_in, int64_t max_frame_bytes, int channels_in) {
+    if (channels_in <= 0) return QPSK_ERR_RANGE;
+    if (rs == 0) return QPSK_ERR_RANGE;                        // DivideByZeroException upstream
+    QPSK_TRY(ensure_device());
+    channels = channels_in;
+    diff = diff_in != 0;
+    use_fll = use_fll_in != 0;
+    has_tsc = !blank_or_null(tsc_in);                          // :21
+    if (has_tsc) tsc = tsc_in;
+    sps = (double)fs / (double)rs;
+    QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    const std::vector<double> h = design_rrc((double)span, (double)alpha, fs, rs);   // :28-32
+    const std::vector<float> iq = real_taps_as_iq(h);
+    QPSK_TRY(mf.init(iq.data(), (int)iq.size(), channels));
+    QPSK_TRY(fll.init((float)(fs / rs), alpha, 40, (float)cfo_bw, channels));        // :35 (integer division)
+    double kp, ki;
+    mm_gains(sym_bw, &kp, &ki);                                // :39-55
+    QPSK_TRY(mm.init(sps, kp, ki, channels));
+    QPSK_TRY(costas.init((double)rs, (double)rs / costas_bw, 0.707, channels));      // :56
+    QPSK_TRY(d_nsym.alloc((size_t)channels));
+    QPSK_TRY(d_nraw.alloc((size_t)channels));
+    QPSK_TRY(d_nbits.alloc((size_t)channels));
+    QPSK_TRY(d_npayload.alloc((size_t)channels));
+    QPSK_TRY(d_diff.alloc((size_t)channels));
+    QPSK_TRY(d_framer.alloc((size_t)channels));
+    QPSK_TRY(d_diff.zero(stream));
+    QPSK_TRY(d_framer.zero(stream));
+    if (has_tsc) {
+      std::vector<uint8_t> t;
+      for (char ch : tsc) t.push_back((uint8_t)(ch == '0' ? 0 : (ch == '1' ? 1 : 2)));
+      QPSK_TRY(d_tsc.alloc(t.size()));
+      QPSK_CUDA_TRY(cudaMemcpyAsync(d_tsc.p, t.data(), t.size(), cudaMemcpyHostToDevice, stream));
+      QPSK_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    ring_cap = max_frame_bytes > 0 ? max_frame_bytes : (1LL << 20);
+    QPSK_CUDA_TRY(cudaStreamSynchronize(stream));
+    return QPSK_OK;
+  }
+
+  // most symbols one call can emit: every symbol advances time by >= sps - 0.1 (MuellerMuller.cs:87-89)
+  long long symbols_bound(int64_t L) const {
+    if (sps - 0.1 <= 1.0) return L;
+    long long b = (long long)((double)(L + 4) / (sps - 0.1)) + 2;
+    return b < L ? b : L;
+  }
+  long long bits_bound(int64_t L) const { return 2 * symbols_bound(L); }
+
+  // FLL? -> MF -> MM.  Symbols in t_sym [C][sym_ld], counts in d_nsym.
+  int front(const float2* x, int64_t L, int64_t ldx, cudaStream_t s) {
+    const int64_t ld = L + (L & 1);
+    QPSK_TRY(t_rrc.ensure((size_t)ld * channels));
+    sym_ld = symbols_bound(L);
+    if (sym_ld < 1) sym_ld = 1;
+    QPSK_TRY(t_sym.ensure((size_t)sym_ld * channels));
+    const float2* src = x;
+    int64_t lds = ldx;
+    if (use_fll) {
+      QPSK_TRY(t_fll.ensure((size_t)ld * channels));
+      QPSK_TRY(fll.process_dev(x, t_fll.p, L, ldx, ld, s));    // the call at :359
+      src = t_fll.p;
+      lds = ld;
+    }
+    QPSK_TRY(mf.filter_dev(src, t_rrc.p, L, lds, ld, s));      // :360
+    QPSK_TRY(mm.process_dev(t_rrc.p, L, ld, t_sym.p, 2 * L, sym_ld, d_nsym.p, s));   // :364-367
+    return QPSK_OK;
+  }
+
+  // DeModulate: bits (bytes 0/1) to out [C][ld_out], counts to n_out[C]
+  int bits_dev(const float2* x, int64_t L, int64_t ldx, uint8_t* out, int64_t ld_out, long long* n_out, cudaStream_t s) {
+    if (L == 0) {
+      QPSK_CUDA_TRY(cudaMemsetAsync(n_out, 0, sizeof(long long) * channels, s));   // :350-351
+      return QPSK_OK;
+    }
+    QPSK_TRY(front(x, L, ldx, s));
+    const long long need = 2 * sym_ld;
+    if (ld_out < need) return QPSK_ERR_CAPACITY;
+    uint8_t* raw = out;
+    long long ld_raw = ld_out;
+    long long* n_raw = n_out;
+    if (has_tsc) {
+      const long long ldr = need + (need & 1);
+      QPSK_TRY(d_raw.ensure((size_t)ldr * channels));
+      raw = d_raw.p; ld_raw = ldr; n_raw = d_nraw.p;
+    }
+    if ((reinterpret_cast<uintptr_t>(raw) & 1) || (ld_raw & 1)) return QPSK_ERR_ARG;   // uchar2 stores
+    decode_kernel<<<(channels + 31) / 32, 32, 0, s>>>(costas.P, costas.d_state.p, d_diff.p, channels, t_sym.p, sym_ld,
+                                                      d_nsym.p, diff ? 1 : 0, raw, ld_raw, n_raw);
+    QPSK_LAUNCH_CHECK();
+    if (has_tsc) {
+      tsc_strip_kernel<<<(channels + 3) / 4, 128, 0, s>>>(raw, ld_raw, n_raw, d_tsc.p, (int)tsc.size(), out, ld_out, n_out,
+                                                          channels);
+      QPSK_LAUNCH_CHECK();
+    }
+    return QPSK_OK;
+  }
+
+  int constellation_dev(const float2* x, int64_t L, int64_t ldx, float2* out, int64_t ld_out, int* n_out, cudaStream_t s) {
+    if (L == 0) {
+      QPSK_CUDA_TRY(cudaMemsetAsync(n_out, 0, sizeof(int) * channels, s));
+      return QPSK_OK;
+    }
+    QPSK_TRY(front(x, L, ldx, s));
+    if (ld_out < sym_ld) return QPSK_ERR_CAPACITY;
+    QPSK_TRY(costas.process_dev(t_sym.p, out, sym_ld, sym_ld, ld_out, d_nsym.p, s));   // :447-452
+    QPSK_CUDA_TRY(cudaMemcpyAsync(n_out, d_nsym.p, sizeof(int) * channels, cudaMemcpyDeviceToDevice, s));
+    return QPSK_OK;
+  }
+
+  int upload_markers(const uint8_t* sm, int64_t ns, const uint8_t* em, int64_t ne, cudaStream_t s) {
+    std::vector<uint8_t> m(sm, sm + ns);
+    m.insert(m.end(), em, em + ne);
+    if (m != markers_host || !d_markers.p) {
+      QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+      QPSK_TRY(d_markers.ensure(m.size()));
+      markers_host = m;
+      QPSK_CUDA_TRY(cudaMemcpyAsync(d_markers.p, markers_host.data(), markers_host.size(), cudaMemcpyHostToDevice, s));
+    }
+    return QPSK_OK;
+  }
+
+  // DeModulateBytes: payload bytes to payload [C][cap], full lengths to n_payload[C]
+  int bytes_dev(const float2* x, int64_t L, int64_t ldx, const uint8_t* sm, int64_t ns, const uint8_t* em, int64_t ne,
+                uint8_t* payload, int64_t cap, long long* n_payload, cudaStream_t s) {
+    if (ns == 0 || ne == 0) return QPSK_ERR_ARG;               // :174-175
+    if (!sm || !em) return QPSK_ERR_NULL;
+    if (ns > kMaxMarkerBytes || ne > kMaxMarkerBytes) return QPSK_ERR_UNSUPPORTED;
+    const long long ldb = bits_bound(L) + 2;
+    QPSK_TRY(d_bits.ensure((size_t)ldb * channels));
+    QPSK_TRY(bits_dev(x, L, ldx, d_bits.p, ldb, d_nbits.p, s));
+    QPSK_TRY(upload_markers(sm, ns, em, ne, s));
+    const int carry_cap = kMaxMarkerBytes * 8 + 8;
+    if (!d_carry.p) {
+      QPSK_TRY(d_carry.alloc((size_t)carry_cap * channels));
+      QPSK_TRY(d_ring.alloc((size_t)ring_cap * channels));
+    }
+    const long long pk_ld = ((carry_cap + ldb) >> 3) + 4;
+    QPSK_TRY(d_pk.ensure((size_t)pk_ld * channels));
+    FramerArgs a;
+    a.st = d_framer.p; a.carry = d_carry.p; a.carry_cap = carry_cap; a.ring = d_ring.p; a.ring_cap = ring_cap;
+    a.pk = d_pk.p; a.pk_ld = pk_ld; a.rx = d_bits.p; a.ld_rx = ldb; a.n_rx = d_nbits.p; a.markers = d_markers.p;
+    a.ns = (int)ns; a.ne = (int)ne; a.payload = payload; a.payload_cap = cap; a.n_payload = n_payload; a.C = channels;
+    framer_kernel<<<(channels + 31) / 32, 32, 0, s>>>(a);
+    QPSK_LAUNCH_CHECK();
+    return QPSK_OK;
+  }
+};
+
+}  // namespace qpsk
+
+using namespace qpsk;
+
+struct qpsk_demod {
+  DemodEngine eng;
+};
+
+extern "C" {
+
+int qpsk_demod_create_batch(int sample_rate, int symbol_rate, float rrc_alpha, int rrc_span, double symbol_sync_bw,
+                            double costas_loop_bw, double cfo_loop_bw, int differential, const char* tsc_bits, int use_fll,
+                            int64_t max_frame_bytes, int channels, qpsk_demod** out) {
+  if (!out) return QPSK_ERR_NULL;
+  *out = nullptr;
+  qpsk_demod* d = new (std::nothrow) qpsk_demod();
+  if (!d) return QPSK_ERR_NOMEM;
+  int st = d->eng.init(sample_rate, symbol_rate, rrc_alpha, rrc_span, symbol_sync_bw, costas_loop_bw, cfo_loop_bw, differential,
+                       tsc_bits, use_fll, max_frame_bytes, channels);
+  if (st != QPSK_OK) { delete d; return st; }
+  *out = d;
+  return QPSK_OK;
+}
+int qpsk_demod_create(int sample_rate, int symbol_rate, float rrc_alpha, int rrc_span, double symbol_sync_bw,
+                      double costas_loop_bw, double cfo_loop_bw, int differential, const char* tsc_bits, int use_fll,
+                      int64_t max_frame_bytes, qpsk_demod** out) {
+  return qpsk_demod_create_batch(sample_rate, symbol_rate, rrc_alpha, rrc_span, symbol_sync_bw, costas_loop_bw, cfo_loop_bw,
+                                 differential, tsc_bits, use_fll, max_frame_bytes, 1, out);
+}
+int qpsk_demod_destroy(qpsk_demod* d) {
+  if (d) {
+    if (d->eng.stream) cudaStreamSynchronize(d->eng.stream);
+    delete d;
+  }
+  return QPSK_OK;
+}
+int qpsk_demod_set_fir_mode(qpsk_demod* d, int mode) {
+  if (!d) return QPSK_ERR_NULL;
+  if (mode != QPSK_FIR_FAST && mode != QPSK_FIR_EXACT) return QPSK_ERR_RANGE;
+  d->eng.mf.mode = mode;
+  return QPSK_OK;
+}
+
+static int demod_check_in(qpsk_demod* d, const void* in, int64_t n_floats) {
+  if (!d) return QPSK_ERR_NULL;
+  if (n_floats < 0) return QPSK_ERR_RANGE;
+  if ((n_floats & 1) != 0) return QPSK_ERR_ARG;              // :347-348
+  if (n_floats > 0 && !in) return QPSK_ERR_NULL;
+  return QPSK_OK;
+}
+
+// host staging: [C][n_floats] -> device
+static int demod_stage_in(DemodEngine& e, const float* iq_in, int64_t L, cudaStream_t s) {
+  const int64_t ld = L + (L & 1);
+  QPSK_TRY(e.h_in.ensure((size_t)(ld > 0 ? ld : 2) * e.channels));
+  if (L > 0)
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(e.h_in.p, (size_t)ld * 8, iq_in, (size_t)L * 8, (size_t)L * 8, (size_t)e.channels,
+                                    cudaMemcpyHostToDevice, s));
+  return QPSK_OK;
+}
+
+int qpsk_demod_bits(qpsk_demod* d, const float* iq_in, int64_t n_floats, char* bits_out, int64_t cap, int64_t* n_bits) {
+  QPSK_TRY(demod_check_in(d, iq_in, n_floats));
+  if (!n_bits) return QPSK_ERR_NULL;
+  DemodEngine& e = d->eng;
+  for (int c = 0; c < e.channels; ++c) n_bits[c] = 0;
+  if (n_floats == 0) return QPSK_OK;                         // :350-351
+  QPSK_TRY(ensure_device());
+  cudaStream_t s = e.stream;
+  const int64_t L = n_floats >> 1, ld = L + (L & 1);
+  QPSK_TRY(demod_stage_in(e, iq_in, L, s));
+  const long long ldb = e.bits_bound(L) + 2;
+  QPSK_TRY(e.d_bits.ensure((size_t)ldb * e.channels));
+  QPSK_TRY(e.bits_dev(e.h_in.p, L, ld, e.d_bits.p, ldb, e.d_nbits.p, s));
+  std::vector<long long> nb((size_t)e.channels);
+  QPSK_CUDA_TRY(cudaMemcpyAsync(nb.data(), e.d_nbits.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  int st = QPSK_OK;
+  std::vector<uint8_t> tmp;
+  for (int c = 0; c < e.channels; ++c) {
+    n_bits[c] = nb[(size_t)c];
+    if (nb[(size_t)c] > cap) { st = QPSK_ERR_CAPACITY; continue; }
+    if (nb[(size_t)c] == 0) continue;
+    if (!bits_out) return QPSK_ERR_NULL;
+    tmp.resize((size_t)nb[(size_t)c]);
+    QPSK_CUDA_TRY(cudaMemcpy(tmp.data(), e.d_bits.p + (size_t)c * ldb, tmp.size(), cudaMemcpyDeviceToHost));
+    char* o = bits_out + (size_t)c * cap;
+    for (size_t i = 0; i < tmp.size(); ++i) o[i] = tmp[i] ? '1' : '0';
+  }
+  return st;
+}
+
+int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_floats, const uint8_t* start_marker, int64_t n_start,
+                     const uint8_t* end_marker, int64_t n_end, uint8_t* payload_out, int64_t cap, int64_t* n_bytes) {
+  if (!d || !n_bytes) return QPSK_ERR_NULL;
+  if (n_start == 0 || n_end == 0) return QPSK_ERR_ARG;       // :174-175 (checked before the samples)
+  QPSK_TRY(demod_check_in(d, iq_in, n_floats));
+  DemodEngine& e = d->eng;
+  for (int c = 0; c < e.channels; ++c) n_bytes[c] = 0;
+  if (n_floats == 0) return QPSK_OK;
+  if (cap < 0) return QPSK_ERR_RANGE;
+  QPSK_TRY(ensure_device());
+  cudaStream_t s = e.stream;
+  const int64_t L = n_floats >> 1, ld = L + (L & 1);
+  QPSK_TRY(demod_stage_in(e, iq_in, L, s));
+  const int64_t pcap = cap > 0 ? cap : 1;
+  QPSK_TRY(e.d_payload.ensure((size_t)pcap * e.channels));
+  QPSK_TRY(e.bytes_dev(e.h_in.p, L, ld, start_marker, n_start, end_marker, n_end, e.d_payload.p, pcap, e.d_npayload.p, s));
+  std::vector<long long> np((size_t)e.channels);
+  QPSK_CUDA_TRY(cudaMemcpyAsync(np.data(), e.d_npayload.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  int st = QPSK_OK;
+  for (int c = 0; c < e.channels; ++c) {
+    n_bytes[c] = np[(size_t)c];
+    if (np[(size_t)c] > cap) { st = QPSK_ERR_CAPACITY; continue; }
+    if (np[(size_t)c] == 0) continue;
+    if (!payload_out) return QPSK_ERR_NULL;
+    QPSK_CUDA_TRY(cudaMemcpy(payload_out + (size_t)c * cap, e.d_payload.p + (size_t)c * pcap, (size_t)np[(size_t)c],
+                             cudaMemcpyDeviceToHost));
+  }
+  return st;
+}
+
+int qpsk_demod_constellation(qpsk_demod* d, const float* iq_in, int64_t n_floats, float* sym_iq_out, int64_t cap_floats,
+                             int64_t* n_sym) {
+  QPSK_TRY(demod_check_in(d, iq_in, n_floats));
+  if (!n_sym) return QPSK_ERR_NULL;
+  DemodEngine& e = d->eng;
+  for (int c = 0; c < e.channels; ++c) n_sym[c] = 0;
+  if (n_floats == 0) return QPSK_OK;
+  QPSK_TRY(ensure_device());
+  cudaStream_t s = e.stream;
+  const int64_t L = n_floats >> 1, ld = L + (L & 1);
+  QPSK_TRY(demod_stage_in(e, iq_in, L, s));
+  const long long lds = e.symbols_bound(L) > 0 ? e.symbols_bound(L) : 1;
+  QPSK_TRY(e.h_out.ensure((size_t)lds * e.channels));
+  DevBuf<int> dn;
+  QPSK_TRY(dn.alloc((size_t)e.channels));
+  QPSK_TRY(e.constellation_dev(e.h_in.p, L, ld, e.h_out.p, lds, dn.p, s));
+  std::vector<int> ns((size_t)e.channels);
+  QPSK_CUDA_TRY(cudaMemcpyAsync(ns.data(), dn.p, sizeof(int) * e.channels, cudaMemcpyDeviceToHost, s));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  int st = QPSK_OK;
+  for (int c = 0; c < e.channels; ++c) {
+    n_sym[c] = ns[(size_t)c];
+    if (2LL * ns[(size_t)c] > cap_floats) { st = QPSK_ERR_CAPACITY; continue; }
+    if (ns[(size_t)c] == 0) continue;
+    if (!sym_iq_out) return QPSK_ERR_NULL;
+    QPSK_CUDA_TRY(cudaMemcpy(sym_iq_out + (size_t)c * cap_floats, e.h_out.p + (size_t)c * lds, (size_t)ns[(size_t)c] * 8,
+                             cudaMemcpyDeviceToHost));
+  }
+  return st;
+}
+
+int qpsk_demod_bits_dev(qpsk_demod* d, const float* d_in, int64_t n_floats, int64_t in_stride_floats, uint8_t* d_bits,
+                        int64_t bits_cap, int64_t* d_n_bits, void* stream) {
+  QPSK_TRY(demod_check_in(d, d_in, n_floats));
+  if (!d_bits || !d_n_bits) return QPSK_ERR_NULL;
+  if (in_stride_floats & 1) return QPSK_ERR_ARG;
+  QPSK_TRY(ensure_device());
+  DemodEngine& e = d->eng;
+  cudaStream_t s = stream ? (cudaStream_t)stream : e.stream;
+  return e.bits_dev((const float2*)d_in, n_floats >> 1, in_stride_floats >> 1, d_bits, bits_cap, (long long*)d_n_bits, s);
+}
+
+int qpsk_demod_bits_bound(qpsk_demod* d, int64_t n_floats, int64_t* bits_cap) {
+  if (!d || !bits_cap) return QPSK_ERR_NULL;
+  if (n_floats < 0) return QPSK_ERR_RANGE;
+  long long b = d->eng.bits_bound(n_floats >> 1);
+  if (b < 2) b = 2;
+  *bits_cap = b + (b & 1);
+  return QPSK_OK;
+}
+
+int qpsk_demod_bytes_dev(qpsk_demod* d, const float* d_in, int64_t n_floats, int64_t in_stride_floats,
+                         const uint8_t* start_marker, int64_t n_start, const uint8_t* end_marker, int64_t n_end,
+                         uint8_t* d_payload, int64_t payload_cap, int64_t* d_n_bytes, void* stream) {
+  if (!d) return QPSK_ERR_NULL;
+  if (n_start == 0 || n_end == 0) return QPSK_ERR_ARG;
+  QPSK_TRY(demod_check_in(d, d_in, n_floats));
+  if (!d_payload || !d_n_bytes) return QPSK_ERR_NULL;
+  if (in_stride_floats & 1) return QPSK_ERR_ARG;
+  if (payload_cap <= 0) return QPSK_ERR_RANGE;
+  QPSK_TRY(ensure_device());
+  DemodEngine& e = d->eng;
+  cudaStream_t s = stream ? (cudaStream_t)stream : e.stream;
+  if (n_floats == 0) {
+    QPSK_CUDA_TRY(cudaMemsetAsync(d_n_bytes, 0, sizeof(int64_t) * e.channels, s));
+    return QPSK_OK;
+  }
+  return e.bytes_dev((const float2*)d_in, n_floats >> 1, in_stride_floats >> 1, start_marker, n_start, end_marker, n_end,
+                     d_payload, payload_cap, (long long*)d_n_bytes, s);
+}
+
+int qpsk_demod_constellation_dev(qpsk_demod* d, const float* d_in, int64_t n_floats, int64_t in_stride_floats, float* d_sym,
+                                 int64_t sym_stride_floats, int* d_n_sym, void* stream) {
+  QPSK_TRY(demod_check_in(d, d_in, n_floats));
+  if (!d_sym || !d_n_sym) return QPSK_ERR_NULL;
+  if ((in_stride_floats & 1) || (sym_stride_floats & 1)) return QPSK_ERR_ARG;
+  QPSK_TRY(ensure_device());
+  DemodEngine& e = d->eng;
+  cudaStream_t s = stream ? (cudaStream_t)stream : e.stream;
+  return e.constellation_dev((const float2*)d_in, n_floats >> 1, in_stride_floats >> 1, (float2*)d_sym, sym_stride_floats >> 1,
+                             d_n_sym, s);
+}
+
+int qpsk_demod_loop_state(qpsk_demod* d, double* costas_theta, double* costas_freq, double* mm_mu, double* mm_integral,
+                          float* fll_phase, float* fll_freq) {
+  if (!d) return QPSK_ERR_NULL;
+  QPSK_TRY(ensure_device());
+  DemodEngine& e = d->eng;
+  QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
+  QPSK_CUDA_TRY(cudaDeviceSynchronize());
+  const size_t C = (size_t)e.channels;
+  std::vector<CostasState> cs(C);
+  std::vector<MmState> ms(C);
+  std::vector<float2> pf(C);
+  QPSK_CUDA_TRY(cudaMemcpy(cs.data(), e.costas.d_state.p, C * sizeof(CostasState), cudaMemcpyDeviceToHost));
+  QPSK_CUDA_TRY(cudaMemcpy(ms.data(), e.mm.d_state.p, C * sizeof(MmState), cudaMemcpyDeviceToHost));
+  QPSK_CUDA_TRY(cudaMemcpy(pf.data(), e.fll.d_pf.p, C * sizeof(float2), cudaMemcpyDeviceToHost));
+  for (size_t c = 0; c < C; ++c) {
+    if (costas_theta) costas_theta[c] = cs[c].theta;
+    if (costas_freq) costas_freq[c] = cs[c].freq;
+    if (mm_mu) mm_mu[c] = ms[c].mu;
+    if (mm_integral) mm_integral[c] = ms[c].integral;
+    if (fll_phase) fll_phase[c] = pf[c].x;
+    if (fll_freq) fll_freq[c] = pf[c].y;
+  }
+  return QPSK_OK;
+}
+
+int qpsk_demod_in_frame(qpsk_demod* d, int* in_frame) {
+  if (!d || !in_frame) return QPSK_ERR_NULL;
+  QPSK_TRY(ensure_device());
+  DemodEngine& e = d->eng;
+  QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
+  std::vector<FramerState> fs((size_t)e.channels);
+  QPSK_CUDA_TRY(cudaMemcpy(fs.data(), e.d_framer.p, fs.size() * sizeof(FramerState), cudaMemcpyDeviceToHost));
+  for (int c = 0; c < e.channels; ++c) in_frame[c] = fs[(size_t)c].in_frame;
+  return QPSK_OK;
+}
+
+}  // extern "C"

@@ -193,7 +193,10 @@ int MmEngine::process_dev(const float2* x, int64_t L, int64_t ldx, float2* y, in
   // queue bound: with room for every symbol the loop leaves <= 3 samples (+ tolerance); without,
   // the unconsumed tail stays queued like the reference's growing buffer (:200-241)
   const int64_t total = q_bound + L;
-  const bool roomy = (cap_floats >> 1) >= total;
+  // every emitted symbol advances time by >= sps - 0.1 (:87-89), so `total` samples yield at most this many
+  const double min_adv = P.sps - 0.1;
+  const int64_t max_sym = (min_adv > 1.0) ? (int64_t)((double)total / min_adv) + 2 : total;
+  const bool roomy = (cap_floats >> 1) >= max_sym;
   const int64_t next_bound = roomy ? 4 : total;
   QPSK_TRY(ensure_queue(next_bound > 8 ? next_bound : 8, s));
   const int threads = kLoopThreads;

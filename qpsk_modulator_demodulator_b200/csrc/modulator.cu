@@ -1,0 +1,488 @@
+// modulator.cu — K3: QPSKModulator on the GPU (MS/QPSKModulator.cs:18-168).
+//
+// The reference builds a zero-stuffed symbol train `up` (one symbol every sps samples, `delay` zeros
+// in front and behind, :120-159) and pushes it through fftFilter (:166, FIRFilter.cs:96-141), i.e.
+//     y[i] = sum_d sym[d] * h[i + (N-1-delay) - d*sps],   0 <= i < 2*delay + nDibits*sps
+// (N-1-delay == delay for the usual odd N).
+// Here that is computed directly as a polyphase interpolator: no zero-stuffed buffer, no FFT.
+//
+//   mod_tile_rot_kernel   per tile of kTD dibits: sum of the differential rotations mod 4
+//   mod_tile_scan_kernel  one warp per frame: exclusive scan of the tile sums (the differential
+//                         encoder sym[d] = sym[d-1]*delta[d] (:137-146) is a prefix sum of quadrants)
+//   mod_shape_kernel      per (frame, tile): unpack dibits -> block scan -> symbols in shared memory
+//                         -> polyphase FIR.  One work item = (R consecutive symbols, one phase p): a
+//                         sliding register window of symbols, one shared-memory tap per step shared
+//                         by R packed FFMA2.  Lanes run over consecutive phases, so every store
+//                         instruction writes runs of sps consecutive samples.
+//   Algorithmic traffic: 8 B written per output sample, 0.25/sps B read.
+//
+// Symbols are exactly (+-1/sqrt2, +-1/sqrt2) in fp32 (prev*delta with delta on the axes is exact), so
+// the quadrant index carries all the information: q = 0:(+,+) 1:(-,+) 2:(-,-) 3:(+,-), and the
+// rotations are 00->+0, 01->+1, 11->+2, 10->+3 quadrants (DibitToDelta :92-102).
+#include <string>
+
+#include "common.cuh"
+#include "design.h"
+
+namespace qpsk {
+
+constexpr int kTD = 2048;        // dibits (symbols) per tile
+constexpr int kModThreads = 256;
+constexpr int kModR = 8;         // symbols per work item
+constexpr float kInvSqrt2 = 0.7071067811865475f;  // QPSKModulator.cs:36
+
+struct ModArgs {
+  // source: mode 0 = framed bytes (tsc | start | payload[f] | end), mode 1 = one code byte per dibit
+  const uint8_t* payload;   // mode 0: [frames][n_payload]; mode 1: codes [n_dibits]
+  const uint8_t* meta;      // tsc values (0,1,2=other) | start bytes | end bytes
+  long long n_payload;
+  int n_tsc, n_start, n_end;
+  int mode, diff;
+  long long n_dibits;       // per frame
+  long long n_virtual;      // symbols incl. the zero tail that still produces output
+  long long total;          // complex output samples per frame
+  int tiles;                // per frame
+  int frames;
+  int sps, M, Mp, delay;    // M taps per phase (multiple of kModR), Mp = padded row pitch (odd)
+  const float* poly;        // [sps][Mp]: poly[p*Mp + m] = h[p + m*sps]
+  uint8_t* tile_sum;        // [frames][tiles]
+  uint8_t* tile_pre;        // [frames][tiles]
+  float2* out;
+  long long out_stride;     // complex samples between frames
+};
+
+__device__ __forceinline__ int code_from(int b0, int b1, int diff) {
+  if (diff) {                                   // DibitToDelta :92-102 (anything else -> -j)
+    if (b0 == 0 && b1 == 0) return 0;
+    if (b0 == 0 && b1 == 1) return 1;
+    if (b0 == 1 && b1 == 1) return 2;
+    return 3;
+  }
+  return ((b0 != 0) << 1) | (b1 != 0);          // :150-151  (bit==0 ? -1/sqrt2 : +1/sqrt2)
+}
+
+__device__ __forceinline__ int frame_bit(const ModArgs& a, int f, long long k) {
+  if (k < a.n_tsc) return a.meta[k];
+  k -= a.n_tsc;
+  const long long b = k >> 3;
+  int v;
+  if (b < a.n_start) v = a.meta[a.n_tsc + b];
+  else if (b < a.n_start + a.n_payload) v = a.payload[(long long)f * a.n_payload + (b - a.n_start)];
+  else v = a.meta[a.n_tsc + a.n_start + (b - a.n_start - a.n_payload)];
+  return (v >> (7 - (int)(k & 7))) & 1;         // MSB first (HelperFunctions.cs:14-29)
+}
+
+__device__ __forceinline__ int dibit_code(const ModArgs& a, int f, long long d) {
+  if (d < 0 || d >= a.n_dibits) return 0;
+  if (a.mode == 1) return a.payload[d];
+  // fast path: both bits in the same payload/marker byte and no TSC char involved
+  return code_from(frame_bit(a, f, 2 * d), frame_bit(a, f, 2 * d + 1), a.diff);
+}
+
+__global__ void __launch_bounds__(kModThreads) mod_tile_rot_kernel(const ModArgs a) {
+  const int f = blockIdx.y, t = blockIdx.x;
+  const long long d0 = (long long)t * kTD;
+  int s = 0;
+  for (int i = threadIdx.x; i < kTD; i += kModThreads) s += dibit_code(a, f, d0 + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ int ws[kModThreads / 32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < kModThreads / 32; ++w) tot += ws[w];
+    a.tile_sum[(long long)f * a.tiles + t] = (uint8_t)(tot & 3);
+  }
+}
+
+__global__ void mod_tile_scan_kernel(const ModArgs a) {
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= a.frames) return;
+  const int lane = threadIdx.x & 31;
+  const uint8_t* ts = a.tile_sum + (long long)f * a.tiles;
+  uint8_t* tp = a.tile_pre + (long long)f * a.tiles;
+  int carry = 0;
+  for (int t0 = 0; t0 < a.tiles; t0 += 32) {
+    const int t = t0 + lane;
+    const int v = (t < a.tiles) ? ts[t] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (t < a.tiles) tp[t] = (uint8_t)((carry + inc - v) & 3);
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+}
+
+__device__ __forceinline__ float2 quadrant_symbol(int q) {
+  const float i = (q == 0 || q == 3) ? kInvSqrt2 : -kInvSqrt2;
+  const float v = (q == 0 || q == 1) ? kInvSqrt2 : -kInvSqrt2;
+  return make_float2(i, v);
+}
+
+__global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int H = a.M;                              // halo symbols in front of the tile
+  const int nsym = kTD + H;
+  float2* sym = reinterpret_cast<float2*>(smem_raw);           // sym[k] = symbol D0 - H + k
+  float* poly = reinterpret_cast<float*>(sym + nsym);          // [sps][Mp]
+  __shared__ int warp_tot[kModThreads / 32];
+  __shared__ int halo_sum_s;
+
+  const int f = blockIdx.y, t = blockIdx.x;
+  const long long D0 = (long long)t * kTD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < a.sps * a.Mp; i += kModThreads) poly[i] = a.poly[i];
+
+  // ---- dibit codes -> quadrants (block-wide inclusive scan) -> symbols ----
+  const int per = (nsym + kModThreads - 1) / kModThreads;
+  const int k0 = tid * per;
+  int local = 0;
+  if (a.diff) {
+    for (int j = 0; j < per; ++j) {
+      const int k = k0 + j;
+      if (k < nsym) local += dibit_code(a, f, D0 - H + k);
+    }
+    int inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    int run = base + inc - local;                 // exclusive prefix of this thread's chunk
+    // the tile prefix refers to symbol D0: subtract the halo's own sum (written by whoever crosses H)
+    // -> first pass stores the running sums, second pass rebases; do it in one pass through smem int
+    for (int j = 0; j < per; ++j) {
+      const int k = k0 + j;
+      if (k < nsym) {
+        run += dibit_code(a, f, D0 - H + k);
+        reinterpret_cast<int*>(sym)[2 * k] = run; // temporarily: inclusive sum S[k]
+        if (k == H - 1) halo_sum_s = run;
+      }
+    }
+    __syncthreads();
+    const int pre = (int)a.tile_pre[(long long)f * a.tiles + t] - halo_sum_s;
+    for (int k = tid; k < nsym; k += kModThreads) {
+      const long long d = D0 - H + k;
+      const int S = reinterpret_cast<int*>(sym)[2 * k];
+      float2 v = make_float2(0.f, 0.f);
+      if (d >= 0 && d < a.n_dibits) v = quadrant_symbol((pre + S) & 3);
+      sym[k] = v;   // same thread reads S[k] and overwrites slot k: no hazard
+    }
+  } else {
+    for (int k = tid; k < nsym; k += kModThreads) {
+      const long long d = D0 - H + k;
+      float2 v = make_float2(0.f, 0.f);
+      if (d >= 0 && d < a.n_dibits) {
+        const int c = dibit_code(a, f, d);
+        v = make_float2((c & 2) ? kInvSqrt2 : -kInvSqrt2, (c & 1) ? kInvSqrt2 : -kInvSqrt2);
+      }
+      sym[k] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- polyphase FIR: item = (group of R symbols, phase) ----
+  constexpr int R = kModR;
+  const int items = (kTD / R) * a.sps;
+  float2* outf = a.out + (long long)f * a.out_stride;
+  for (int item = tid; item < items; item += kModThreads) {
+    const int g = item / a.sps;
+    const int p = item - g * a.sps;
+    const int s_loc = H + g * R;                  // smem index of the group's first symbol
+    const float* hp = poly + p * a.Mp;
+    float2 w[R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      w[r] = sym[s_loc + r];
+      acc[r] = make_float2(0.f, 0.f);
+    }
+    for (int m0 = 0; m0 < a.M; m0 += R) {
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const float tap = hp[m0 + u];
+        const float2 tt = make_float2(tap, tap);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(r - u + R) % R], tt, acc[r]);   // sym[s0 + r - m]
+        w[(R - 1 - u) % R] = sym[s_loc - (m0 + u) - 1];                              // slide back by one
+      }
+    }
+    const long long i0 = (D0 + (long long)g * R) * a.sps + p - a.delay;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long i = i0 + (long long)r * a.sps;
+      if (i >= 0 && i < a.total) outf[i] = acc[r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct ModEngine {
+  int fs = 0, rs = 0;
+  bool diff = true, has_tsc = false;
+  std::string tsc;
+  std::vector<double> taps_d;
+  std::vector<float> taps_f;
+  int sps = 0, delay = 0;
+  // two polyphase banks: [0] pulse shaping with the RRC taps, [1] the "no pulse shaping" delta
+  DevBuf<float> d_poly[2];
+  int M[2] = {0, 0}, Mp[2] = {0, 0}, bank_delay[2] = {0, 0};
+  DevBuf<uint8_t> d_meta, d_tile_sum, d_tile_pre, d_src;
+  DevBuf<float2> d_out;
+  std::vector<uint8_t> meta_host;
+  cudaStream_t stream = nullptr;
+
+  ~ModEngine() {
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  int make_bank(int which, const std::vector<float>& h, int bank_delay_in) {
+    const int n = (int)h.size();
+    int m = (n + sps - 1) / sps;
+    m = ((m + kModR - 1) / kModR) * kModR;
+    const int mp = m | 1;
+    std::vector<float> poly((size_t)sps * mp, 0.0f);
+    for (int p = 0; p < sps; ++p)
+      for (int k = 0; k < m; ++k) {
+        const long long j = p + (long long)k * sps;
+        if (j < n) poly[(size_t)p * mp + k] = h[(size_t)j];
+      }
+    M[which] = m; Mp[which] = mp; bank_delay[which] = bank_delay_in;
+    QPSK_TRY(d_poly[which].alloc(poly.size()));
+    QPSK_CUDA_TRY(cudaMemcpyAsync(d_poly[which].p, poly.data(), poly.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    QPSK_CUDA_TRY(cudaStreamSynchronize(stream));
+    return QPSK_OK;
+  }
+
+  int init(int fs_in, int rs_in, double alpha, int span, int diff_in, const char* tsc_in) {
+    if (rs_in == 0) return QPSK_ERR_RANGE;
+    QPSK_TRY(ensure_device());
+    fs = fs_in; rs = rs_in; diff = diff_in != 0;
+    has_tsc = !blank_or_null(tsc_in);              // :27
+    if (has_tsc) tsc = tsc_in;
+    taps_d = design_rrc((double)span, alpha, fs, rs);   // :29-30
+    taps_f.resize(taps_d.size());
+    for (size_t i = 0; i < taps_d.size(); ++i) taps_f[i] = (float)taps_d[i];   // :43-53
+    sps = fs / rs;                                  // :115 integer division
+    delay = ((int)taps_d.size() - 1) / 2;           // :119
+    QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (sps > 0 && !taps_f.empty()) {
+      // fftFilter advances by N-1 (FIRFilter.cs:130-138) while the symbols sit at delay + d*sps (:128,154):
+      // tap index = i + (N-1-delay) - d*sps.  N-1-delay == delay only for odd N.
+      QPSK_TRY(make_bank(0, taps_f, (int)taps_f.size() - 1 - delay));
+      // up[delay + d*sps] = sym[d]  ==  polyphase with h = delta[j - delay] and zero filter delay
+      std::vector<float> delta((size_t)delay + 1, 0.0f);
+      delta[(size_t)delay] = 1.0f;
+      QPSK_TRY(make_bank(1, delta, 0));
+    }
+    return QPSK_OK;
+  }
+
+  // sizes (:112-121): returns complex samples per frame for n_bits data bits (TSC added here)
+  int64_t frame_complex(int64_t n_bits, bool pulse, int64_t* n_dibits) const {
+    const int64_t all = n_bits + (has_tsc ? (int64_t)tsc.size() : 0);
+    const int64_t nd = all >> 1;
+    if (n_dibits) *n_dibits = nd;
+    if (nd == 0) return 0;
+    const int64_t base = delay + nd * sps;
+    return pulse ? base + delay : base;
+  }
+
+  int upload_meta(const uint8_t* sm, int64_t ns, const uint8_t* em, int64_t ne, cudaStream_t s) {
+    std::vector<uint8_t> m;
+    if (has_tsc)
+      for (char c : tsc) m.push_back((uint8_t)(c == '0' ? 0 : (c == '1' ? 1 : 2)));
+    m.insert(m.end(), sm, sm + ns);
+    m.insert(m.end(), em, em + ne);
+    if (m.empty()) m.push_back(0);
+    if (m != meta_host || !d_meta.p) {
+      QPSK_CUDA_TRY(cudaStreamSynchronize(s));      // the previous launch may still read the old meta
+      QPSK_TRY(d_meta.ensure(m.size()));
+      meta_host = m;
+      QPSK_CUDA_TRY(cudaMemcpyAsync(d_meta.p, meta_host.data(), meta_host.size(), cudaMemcpyHostToDevice, s));
+    }
+    return QPSK_OK;
+  }
+
+  // launches the kernels; `a` has source fields filled in
+  int run(ModArgs a, bool pulse, int64_t n_dibits, int frames, float2* out, int64_t out_stride, cudaStream_t s) {
+    const int bank = pulse ? 0 : 1;
+    a.diff = diff ? 1 : 0;
+    a.n_dibits = n_dibits;
+    a.frames = frames;
+    a.sps = sps; a.M = M[bank]; a.Mp = Mp[bank]; a.delay = bank_delay[bank];
+    a.poly = d_poly[bank].p;
+    a.total = pulse ? (2LL * delay + n_dibits * sps) : ((long long)delay + n_dibits * sps);
+    // last output index + filter delay, in symbols (+1): symbols past n_dibits are zero
+    a.n_virtual = (a.total - 1 + a.delay) / sps + 1;
+    const long long tiles = (a.n_virtual + kTD - 1) / kTD;
+    if (tiles > 0x7fffffffLL || frames > 65535) return QPSK_ERR_UNSUPPORTED;
+    a.tiles = (int)tiles;
+    a.out = out; a.out_stride = out_stride;
+    QPSK_TRY(d_tile_sum.ensure((size_t)tiles * frames));
+    QPSK_TRY(d_tile_pre.ensure((size_t)tiles * frames));
+    a.tile_sum = d_tile_sum.p; a.tile_pre = d_tile_pre.p;
+    const dim3 grid((unsigned)tiles, (unsigned)frames);
+    if (diff) {
+      mod_tile_rot_kernel<<<grid, kModThreads, 0, s>>>(a);
+      QPSK_LAUNCH_CHECK();
+      mod_tile_scan_kernel<<<(frames + 3) / 4, 128, 0, s>>>(a);
+      QPSK_LAUNCH_CHECK();
+    }
+    const size_t smem = (size_t)(kTD + a.M) * sizeof(float2) + (size_t)sps * a.Mp * sizeof(float);
+    if (smem > 200 * 1024) return QPSK_ERR_UNSUPPORTED;
+    QPSK_CUDA_TRY(cudaFuncSetAttribute(mod_shape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mod_shape_kernel<<<grid, kModThreads, smem, s>>>(a);
+    QPSK_LAUNCH_CHECK();
+    return QPSK_OK;
+  }
+};
+
+}  // namespace qpsk
+
+using namespace qpsk;
+
+struct qpsk_mod {
+  ModEngine eng;
+};
+
+extern "C" {
+
+int qpsk_mod_create(int sample_rate, int symbol_rate, double rrc_alpha, int rrc_span, int differential,
+                    const char* tsc_bits, qpsk_mod** out) {
+  if (!out) return QPSK_ERR_NULL;
+  *out = nullptr;
+  qpsk_mod* m = new (std::nothrow) qpsk_mod();
+  if (!m) return QPSK_ERR_NOMEM;
+  int st = m->eng.init(sample_rate, symbol_rate, rrc_alpha, rrc_span, differential, tsc_bits);
+  if (st != QPSK_OK) { delete m; return st; }
+  *out = m;
+  return QPSK_OK;
+}
+
+int qpsk_mod_destroy(qpsk_mod* m) {
+  if (m) {
+    if (m->eng.stream) cudaStreamSynchronize(m->eng.stream);
+    delete m;
+  }
+  return QPSK_OK;
+}
+
+int qpsk_mod_taps(const qpsk_mod* m, double* out, int cap, int* n) {
+  if (!m || !n) return QPSK_ERR_NULL;
+  *n = (int)m->eng.taps_d.size();
+  if (!out) return QPSK_OK;
+  if (cap < *n) return QPSK_ERR_CAPACITY;
+  if (*n) memcpy(out, m->eng.taps_d.data(), sizeof(double) * (size_t)*n);
+  return QPSK_OK;
+}
+
+int qpsk_mod_modulate_bits(qpsk_mod* m, const char* bits, int64_t n_bits, int pulse_shaping, float* iq_out,
+                           int64_t cap_floats, int64_t* n_floats) {
+  if (!m || !n_floats) return QPSK_ERR_NULL;
+  if (!bits && n_bits > 0) return QPSK_ERR_NULL;            // :106
+  if (n_bits < 0) return QPSK_ERR_RANGE;
+  ModEngine& e = m->eng;
+  int64_t nd = 0;
+  const bool pulse = pulse_shaping != 0;
+  const int64_t total = e.frame_complex(n_bits, pulse, &nd);
+  *n_floats = 2 * total;
+  if (nd == 0) return QPSK_OK;                              // :113
+  if (e.sps <= 0) return QPSK_ERR_RANGE;                    // :116-117
+  if (!iq_out) return QPSK_OK;                              // size query
+  if (cap_floats < 2 * total) return QPSK_ERR_CAPACITY;
+  QPSK_TRY(ensure_device());
+  // chars -> one code per dibit, with the reference's `c - '0'` semantics for any character
+  std::vector<uint8_t> codes((size_t)nd);
+  const int64_t nt = e.has_tsc ? (int64_t)e.tsc.size() : 0;
+  auto val = [&](int64_t k) -> int {
+    const char c = (k < nt) ? e.tsc[(size_t)k] : bits[k - nt];
+    return c == '0' ? 0 : (c == '1' ? 1 : 2);
+  };
+  for (int64_t d = 0; d < nd; ++d) {
+    const int b0 = val(2 * d), b1 = val(2 * d + 1);
+    int code;
+    if (e.diff) code = (b0 == 0 && b1 == 0) ? 0 : (b0 == 0 && b1 == 1) ? 1 : (b0 == 1 && b1 == 1) ? 2 : 3;
+    else code = ((b0 != 0) << 1) | (b1 != 0);
+    codes[(size_t)d] = (uint8_t)code;
+  }
+  QPSK_TRY(e.d_src.ensure((size_t)nd));
+  QPSK_TRY(e.d_out.ensure((size_t)total));
+  cudaStream_t s = e.stream;
+  QPSK_CUDA_TRY(cudaMemcpyAsync(e.d_src.p, codes.data(), (size_t)nd, cudaMemcpyHostToDevice, s));
+  ModArgs a{};
+  a.mode = 1; a.payload = e.d_src.p; a.meta = nullptr; a.n_payload = 0; a.n_tsc = a.n_start = a.n_end = 0;
+  QPSK_TRY(e.run(a, pulse, nd, 1, e.d_out.p, total, s));
+  QPSK_CUDA_TRY(cudaMemcpyAsync(iq_out, e.d_out.p, (size_t)total * 8, cudaMemcpyDeviceToHost, s));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  return QPSK_OK;
+}
+
+static int mod_frames_common(qpsk_mod* m, const uint8_t* d_payloads, int64_t n_payload, int frames,
+                             const uint8_t* sm, int64_t ns, const uint8_t* em, int64_t ne, int pulse_shaping,
+                             float2* d_out, int64_t out_stride_c, int64_t* frame_floats, cudaStream_t s) {
+  ModEngine& e = m->eng;
+  if (ns == 0 || ne == 0) return QPSK_ERR_ARG;               // :60-61
+  if (!sm || !em) return QPSK_ERR_NULL;
+  if (n_payload < 0 || ns < 0 || ne < 0 || frames < 0) return QPSK_ERR_RANGE;
+  int64_t nd = 0;
+  const bool pulse = pulse_shaping != 0;
+  const int64_t total = e.frame_complex(8 * (ns + n_payload + ne), pulse, &nd);
+  if (frame_floats) *frame_floats = 2 * total;
+  if (nd == 0 || frames == 0) return QPSK_OK;
+  if (e.sps <= 0) return QPSK_ERR_RANGE;
+  if (!d_out) return QPSK_OK;                                // size query
+  if (n_payload > 0 && !d_payloads) return QPSK_ERR_NULL;
+  if (frames > 1 && out_stride_c < total) return QPSK_ERR_ARG;
+  QPSK_TRY(ensure_device());
+  QPSK_TRY(e.upload_meta(sm, ns, em, ne, s));
+  ModArgs a{};
+  a.mode = 0; a.payload = d_payloads; a.meta = e.d_meta.p; a.n_payload = n_payload;
+  a.n_tsc = e.has_tsc ? (int)e.tsc.size() : 0; a.n_start = (int)ns; a.n_end = (int)ne;
+  return e.run(a, pulse, nd, frames, d_out, out_stride_c, s);
+}
+
+int qpsk_mod_modulate_bytes(qpsk_mod* m, const uint8_t* payload, int64_t n_payload, const uint8_t* start_marker,
+                            int64_t n_start, const uint8_t* end_marker, int64_t n_end, int pulse_shaping,
+                            float* iq_out, int64_t cap_floats, int64_t* n_floats) {
+  if (!m || !n_floats) return QPSK_ERR_NULL;
+  if (n_start == 0 || n_end == 0) return QPSK_ERR_ARG;       // :60-61
+  if (n_payload > 0 && !payload) return QPSK_ERR_NULL;
+  ModEngine& e = m->eng;
+  int64_t ff = 0;
+  QPSK_TRY(mod_frames_common(m, nullptr, n_payload, 1, start_marker, n_start, end_marker, n_end, pulse_shaping, nullptr, 0, &ff,
+                             nullptr));
+  *n_floats = ff;
+  if (ff == 0 || !iq_out) return QPSK_OK;
+  if (cap_floats < ff) return QPSK_ERR_CAPACITY;
+  QPSK_TRY(ensure_device());
+  cudaStream_t s = e.stream;
+  QPSK_TRY(e.d_src.ensure((size_t)(n_payload > 0 ? n_payload : 1)));
+  QPSK_TRY(e.d_out.ensure((size_t)(ff >> 1)));
+  if (n_payload > 0) QPSK_CUDA_TRY(cudaMemcpyAsync(e.d_src.p, payload, (size_t)n_payload, cudaMemcpyHostToDevice, s));
+  QPSK_TRY(mod_frames_common(m, e.d_src.p, n_payload, 1, start_marker, n_start, end_marker, n_end, pulse_shaping, e.d_out.p,
+                             ff >> 1, &ff, s));
+  QPSK_CUDA_TRY(cudaMemcpyAsync(iq_out, e.d_out.p, (size_t)ff * 4, cudaMemcpyDeviceToHost, s));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  return QPSK_OK;
+}
+
+int qpsk_mod_modulate_frames_dev(qpsk_mod* m, const uint8_t* d_payloads, int64_t n_payload, int frames,
+                                 const uint8_t* start_marker, int64_t n_start, const uint8_t* end_marker, int64_t n_end,
+                                 float* d_iq_out, int64_t out_stride_floats, int64_t* frame_floats, void* stream) {
+  if (!m) return QPSK_ERR_NULL;
+  if (out_stride_floats & 1) return QPSK_ERR_ARG;
+  cudaStream_t s = stream ? (cudaStream_t)stream : m->eng.stream;
+  return mod_frames_common(m, d_payloads, n_payload, frames, start_marker, n_start, end_marker, n_end, 1, (float2*)d_iq_out,
+                           out_stride_floats >> 1, frame_floats, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+"""Host-side mirror of QPSKModulator / QPSKDeModulator and the synthetic channel over the C ABI.
+
+Same names, argument meaning and error behaviour as the C# classes (MS/QPSKModulator.cs,
+MS/QPSKDeModulator.cs); the batch (`channels=`) and `*_dev` forms are the device-resident variants
+the benchmarks time.  Everything computes on the GPU through libqpskcuda.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from ._native import ArgumentNullException, ChanParams, check, lib
+from .api import _Handle, _bytes_arr, _f32, _ptr
+
+
+# ---- a6 ---------------------------------------------------------------------------------------
+class QPSKModulator(_Handle):
+    """QPSKModulator (MS/QPSKModulator.cs:18-168) on the GPU: polyphase RRC pulse shaping."""
+    _destroy = "qpsk_mod_destroy"
+
+    def __init__(self, SampleRate, SymbolRate, RrcAlpha=0.9, rrcSpan=6, differentialEncoding=True, tsc=None):
+        super().__init__()
+        t = None if tsc is None else tsc.encode("ascii")
+        check(lib().qpsk_mod_create(SampleRate, SymbolRate, RrcAlpha, rrcSpan, int(differentialEncoding), t, C.byref(self._h)))
+
+    def getCoeef(self) -> np.ndarray:
+        n = C.c_int(0)
+        check(lib().qpsk_mod_taps(self._h, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.float64)
+        check(lib().qpsk_mod_taps(self._h, out.ctypes.data_as(N.f64p), n.value, C.byref(n)))
+        return out
+
+    def Modulate(self, data: str, pulseShaping: bool = True) -> np.ndarray:
+        if data is None:
+            raise ArgumentNullException("data")
+        b = data.encode("latin-1")
+        n = C.c_int64(0)
+        check(lib().qpsk_mod_modulate_bits(self._h, b, len(b), int(pulseShaping), None, 0, C.byref(n)))
+        out = np.empty(n.value, np.float32)
+        if n.value:
+            check(lib().qpsk_mod_modulate_bits(self._h, b, len(b), int(pulseShaping), _ptr(out), out.size, C.byref(n)))
+        return out
+
+    def ModulateBytes(self, payload: bytes, startMarker: bytes, endMarker: bytes, pulseShaping: bool = True) -> np.ndarray:
+        p, s, e = _bytes_arr(payload), _bytes_arr(startMarker), _bytes_arr(endMarker)
+        n = C.c_int64(0)
+        args = (self._h, _ptr(p), p.size, _ptr(s), s.size, _ptr(e), e.size, int(pulseShaping))
+        check(lib().qpsk_mod_modulate_bytes(*args, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.float32)
+        if n.value:
+            check(lib().qpsk_mod_modulate_bytes(*args, _ptr(out), out.size, C.byref(n)))
+        return out
+
+    def ModulateTextUtf8(self, text: str, startMarker="", endMarker="", pulseShaping=True) -> np.ndarray:
+        if text is None:
+            raise ArgumentNullException("text")
+        return self.ModulateBytes(text.encode("utf-8"), startMarker.encode("utf-8"), endMarker.encode("utf-8"), pulseShaping)
+
+    def frame_floats(self, n_payload: int, startMarker: bytes, endMarker: bytes) -> int:
+        """Floats per frame for `n_payload` payload bytes (size query of the batch entry point)."""
+        s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
+        n = C.c_int64(0)
+        check(lib().qpsk_mod_modulate_frames_dev(self._h, None, n_payload, 1, _ptr(s), s.size, _ptr(e), e.size, None, 0,
+                                                 C.byref(n), None))
+        return n.value
+
+    def modulate_frames_dev(self, d_payloads: int, n_payload: int, frames: int, startMarker: bytes, endMarker: bytes,
+                            d_out: int, out_stride_floats: int, stream: int = 0) -> int:
+        """[frames][n_payload] device bytes -> [frames][out_stride_floats] device cf32; returns floats per frame."""
+        s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
+        n = C.c_int64(0)
+        check(lib().qpsk_mod_modulate_frames_dev(self._h, d_payloads, n_payload, frames, _ptr(s), s.size, _ptr(e), e.size,
+                                                 d_out, out_stride_floats, C.byref(n), stream))
+        return n.value
+
+
+# ---- a11-a12 ------------------------------------------------------------------------------------
+def _decode_utf8(b: bytes) -> str:
+    return b.decode("utf-8", errors="replace") if b else ""
+
+
+class QPSKDeModulator(_Handle):
+    """QPSKDeModulator (MS/QPSKDeModulator.cs:11-456) on the GPU, `channels` independent streams."""
+    _destroy = "qpsk_demod_destroy"
+
+    def __init__(self, SampleRate, SymbolRate, RrcAlpha=0.9, rrcSpan=6, SymbolSyncBandwith=0.0001,
+                 CostasLoopBandwith=120.0, CFOLoopBandwith=float(np.float32(0.0001)), differentialEncoding=True,
+                 tsc=None, use_fll=False, max_frame_bytes=0, channels: int = 1):
+        super().__init__()
+        self.channels = channels
+        t = None if tsc is None else tsc.encode("ascii")
+        check(lib().qpsk_demod_create_batch(SampleRate, SymbolRate, RrcAlpha, rrcSpan, SymbolSyncBandwith, CostasLoopBandwith,
+                                            CFOLoopBandwith, int(differentialEncoding), t, int(use_fll), max_frame_bytes,
+                                            channels, C.byref(self._h)))
+
+    def set_fir_mode(self, mode: int):
+        check(lib().qpsk_demod_set_fir_mode(self._h, mode))
+
+    def _in(self, SamplesIQ):
+        if SamplesIQ is None:
+            raise ArgumentNullException("SamplesIQ")
+        x = _f32(SamplesIQ)
+        n = x.shape[-1] if x.ndim == 2 else x.size
+        return x, n
+
+    def DeModulate(self, SamplesIQ):
+        """-> '0'/'1' string (list of strings for batch handles)."""
+        x, n = self._in(SamplesIQ)
+        cap = max(n, 16)
+        buf = np.zeros((self.channels, cap), np.uint8)
+        nb = np.zeros(self.channels, np.int64)
+        check(lib().qpsk_demod_bits(self._h, _ptr(x), n, _ptr(buf), cap, _ptr(nb)))
+        outs = [buf[c, : nb[c]].tobytes().decode("ascii") for c in range(self.channels)]
+        return outs[0] if self.channels == 1 else outs
+
+    def DeModulateBytes(self, samplesIQ, startMarker: bytes, endMarker: bytes, cap: int = 0):
+        x, n = self._in(samplesIQ)
+        s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
+        cap = cap or max(n // 8 + 64, 64)
+        out = np.zeros((self.channels, cap), np.uint8)
+        nb = np.zeros(self.channels, np.int64)
+        check(lib().qpsk_demod_bytes(self._h, _ptr(x), n, _ptr(s), s.size, _ptr(e), e.size, _ptr(out), cap, _ptr(nb)))
+        outs = [out[c, : nb[c]].tobytes() for c in range(self.channels)]
+        return outs[0] if self.channels == 1 else outs
+
+    def DeModulateTextUtf8(self, samplesIQ, startMarker="", endMarker=""):
+        p = self.DeModulateBytes(samplesIQ, startMarker.encode("utf-8"), endMarker.encode("utf-8"))
+        return _decode_utf8(p) if self.channels == 1 else [_decode_utf8(b) for b in p]
+
+    def deModulateConstellation(self, SamplesIQ):
+        x, n = self._in(SamplesIQ)
+        cap = max(n, 2)
+        y = np.zeros((self.channels, cap), np.float32)
+        ns = np.zeros(self.channels, np.int64)
+        check(lib().qpsk_demod_constellation(self._h, _ptr(x), n, _ptr(y), cap, _ptr(ns)))
+        outs = [y[c, : 2 * ns[c]].copy() for c in range(self.channels)]
+        return outs[0] if self.channels == 1 else outs
+
+    def bits_bound(self, n_floats: int) -> int:
+        b = C.c_int64(0)
+        check(lib().qpsk_demod_bits_bound(self._h, n_floats, C.byref(b)))
+        return b.value
+
+    def demod_bits_dev(self, d_in: int, n_floats: int, in_stride: int, d_bits: int, bits_cap: int, d_n_bits: int, stream: int = 0):
+        check(lib().qpsk_demod_bits_dev(self._h, d_in, n_floats, in_stride or n_floats, d_bits, bits_cap, d_n_bits, stream))
+
+    def demod_bytes_dev(self, d_in: int, n_floats: int, in_stride: int, startMarker: bytes, endMarker: bytes, d_payload: int,
+                        payload_cap: int, d_n_bytes: int, stream: int = 0):
+        s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
+        check(lib().qpsk_demod_bytes_dev(self._h, d_in, n_floats, in_stride or n_floats, _ptr(s), s.size, _ptr(e), e.size,
+                                         d_payload, payload_cap, d_n_bytes, stream))
+
+    def loop_state(self):
+        Cn = self.channels
+        ct, cf, mu, mi = (np.empty(Cn, np.float64) for _ in range(4))
+        fp, ff = np.empty(Cn, np.float32), np.empty(Cn, np.float32)
+        check(lib().qpsk_demod_loop_state(self._h, ct.ctypes.data_as(N.f64p), cf.ctypes.data_as(N.f64p), mu.ctypes.data_as(N.f64p),
+                                          mi.ctypes.data_as(N.f64p), fp.ctypes.data_as(N.f32p), ff.ctypes.data_as(N.f32p)))
+        d = dict(costas_theta=ct, costas_freq=cf, mm_mu=mu, mm_integral=mi, fll_phase=fp, fll_freq=ff)
+        return {k: (float(v[0]) if Cn == 1 else v) for k, v in d.items()}
+
+    @property
+    def in_frame(self):
+        f = np.zeros(self.channels, np.int32)
+        check(lib().qpsk_demod_in_frame(self._h, f.ctypes.data_as(N.i32p)))
+        return bool(f[0]) if self.channels == 1 else f.astype(bool)
+
+
+# ---- synthetic channel / BER ----------------------------------------------
+class SimChannel(_Handle):
+    """Two unstable LOs (TB/Simulated/LocalOscilator.cs) + AWGN (TB/HelperModels.cs) + static multipath."""
+    _destroy = "qpsk_chan_destroy"
+
+    def __init__(self, tx_freq_hz, rx_freq_hz, sample_rate_hz, tx_ppm=0.0, rx_ppm=0.0, tx_phase0=0.0, rx_phase0=0.0,
+                 noise_dbfs=-1000.0, mode=0, path_gains_iq=(), path_delays=(), seed=0, channels=1, first_channel=0):
+        super().__init__()
+        self.channels = channels
+        p = ChanParams()
+        p.tx_freq_hz, p.rx_freq_hz, p.sample_rate_hz = tx_freq_hz, rx_freq_hz, sample_rate_hz
+        p.tx_ppm, p.rx_ppm, p.tx_phase0, p.rx_phase0 = tx_ppm, rx_ppm, tx_phase0, rx_phase0
+        p.noise_dbfs, p.mode, p.n_paths, p.seed = noise_dbfs, mode, len(path_delays), seed
+        for k, d in enumerate(path_delays):
+            p.path_delay[k] = int(d)
+            p.path_gain_iq[2 * k] = float(path_gains_iq[2 * k])
+            p.path_gain_iq[2 * k + 1] = float(path_gains_iq[2 * k + 1])
+        check(lib().qpsk_chan_create(C.byref(p), channels, first_channel, C.byref(self._h)))
+
+    def apply(self, x_iq) -> np.ndarray:
+        x = _f32(x_iq)
+        n = x.shape[-1] if x.ndim == 2 else x.size
+        y = np.empty_like(x)
+        check(lib().qpsk_chan_apply(self._h, _ptr(x), n, _ptr(y)))
+        return y
+
+    def apply_dev(self, d_x: int, n_floats: int, x_stride: int, d_y: int, y_stride: int, stream: int = 0):
+        check(lib().qpsk_chan_apply_dev(self._h, d_x, n_floats, x_stride, d_y, y_stride, stream))
+
+
+def fill_bytes_dev(seed: int, first_channel: int, channels: int, n_bytes: int, d_out: int, stream: int = 0):
+    check(lib().qpsk_fill_bytes_dev(seed, first_channel, channels, n_bytes, d_out, stream))
+
+
+def unpack_bits_dev(d_bytes: int, n_bytes: int, bytes_stride: int, channels: int, d_bits: int, bits_stride: int, stream: int = 0):
+    check(lib().qpsk_unpack_bits_dev(d_bytes, n_bytes, bytes_stride, channels, d_bits, bits_stride, stream))
+
+
+def ber_count_dev(d_rx_bits: int, rx_stride: int, d_n_rx: int, d_ref_bits: int, ref_stride: int, n_ref: int, channels: int,
+                  d_counters: int, stream: int = 0):
+    check(lib().qpsk_ber_count_dev(d_rx_bits, rx_stride, d_n_rx, d_ref_bits, ref_stride, n_ref, channels, d_counters, stream))
