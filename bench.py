@@ -296,13 +296,17 @@ def main():
                "steps": k_e2e, "api": "qpsk_fir_filter (host pointers, pinned, chunked H2D/kernel/D2H pipeline)"}
         hin.free(); hout.free()
 
-    chain = None
+    chain = chain_fll = modulator = None
     if not args.no_chain:
-        try:
-            from bench_chain import run_chain  # optional: config 3 (batched demod chain)
-            chain = run_chain(Q, world, rank, local, dist if world > 1 else None)
-        except ImportError:
-            chain = None
+        import bench_chain
+        d = dist if world > 1 else None
+        torch.cuda.synchronize()
+        del y
+        torch.cuda.empty_cache()
+        k = max(1, min(args.steps, 3))
+        chain = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=False, hbm_peak=hbm_peak)
+        chain_fll = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=True, hbm_peak=hbm_peak)
+        modulator = bench_chain.run_modulator(Q, torch, d, world, rank, stream, steps=k, warmup=3, hbm_peak=hbm_peak)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -323,6 +327,8 @@ def main():
         }
         if chain is not None:
             line["chain"] = chain
+            line["chain_fll"] = chain_fll
+            line["modulator"] = modulator
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

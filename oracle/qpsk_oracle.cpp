@@ -90,7 +90,10 @@ std::vector<double> rrc_taps(double spanSymbols, double beta, int sampleRate, in
     } else {
       double num = std::sin(pi * t * (1.0 - beta)) +
                    4.0 * beta * t * std::cos(pi * t * (1.0 + beta));   // :56-57
-      double den = pi * t * (1.0 - std::pow(4.0 * beta * t, 2.0));     // :58
+      // :58  Math.Pow(x, 2.0) is modelled as the correctly rounded square x*x (glibc's pow(x, 2.0) can be
+      // one ulp off, and GCC folds pow(x, 2.0) into x*x anyway); DESIGN.md "transcendentals"
+      double fbt = 4.0 * beta * t;
+      double den = pi * t * (1.0 - fbt * fbt);
       val = num / den;
     }
     h[n] = val;

@@ -71,7 +71,8 @@ std::vector<double> design_rrc(double span_symbols, double beta, int sample_rate
       v = (beta / sqrt(2.0)) * ((1.0 + 2.0 / M_PI) * sin(M_PI / (4.0 * beta)) + (1.0 - 2.0 / M_PI) * cos(M_PI / (4.0 * beta)));
     } else {
       const double numer = sin(M_PI * t * (1.0 - beta)) + 4.0 * beta * t * cos(M_PI * t * (1.0 + beta));
-      const double denom = M_PI * t * (1.0 - pow(4.0 * beta * t, 2.0));
+      const double fbt = 4.0 * beta * t;   // Math.Pow(x, 2.0) modelled as the correctly rounded square
+      const double denom = M_PI * t * (1.0 - fbt * fbt);
       v = numer / denom;
     }
     h[(size_t)n] = v;

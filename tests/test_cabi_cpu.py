@@ -1,0 +1,103 @@
+"""CPU: the C-ABI library loads and exports every symbol include/qpskcuda.h declares; the host-side
+designers agree with the oracle; without a GPU every compute entry point fails loudly (no fallback).
+No GPU compute calls are made here.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "qpskcuda.h")
+
+
+def _declared_in_header():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"QPSK_API\s+[\w\s\*]+?\b(qpsk_\w+)\s*\(", text)))
+
+
+def test_header_compiles_as_c():
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER])
+
+
+def test_library_exports_every_declared_symbol(qp):
+    names = _declared_in_header()
+    assert len(names) >= 70
+    lib = qp._native.lib()
+    for n in names:
+        assert hasattr(lib, n), f"libqpskcuda.so does not export {n}"
+    # and the ctypes table binds exactly the header's surface
+    assert sorted(qp._native.declared_symbols()) == names
+    exported = subprocess.check_output(["nm", "-D", "--defined-only", qp._native.LIB_PATH], text=True)
+    exported = sorted(set(re.findall(r"\bT (qpsk_\w+)", exported)))
+    assert exported == names, set(exported) ^ set(names)      # nothing else leaks out of the library
+
+
+def test_sass_is_sm100a_with_bulk_copies_and_ffma2(qp):
+    sass = subprocess.check_output(["cuobjdump", "-sass", qp._native.LIB_PATH], text=True)
+    assert "sm_100a" in sass
+    assert "UBLKCP" in sass            # TMA bulk copies (cp.async.bulk) in the FIR kernel
+    assert "FFMA2" in sass             # packed fp32x2 FMA
+    assert "SYNCS" in sass             # mbarrier
+    funcs = sass.split("Function : ")
+    # kernels that restate the reference's unfused fp32 arithmetic must not contain fused multiply-adds
+    for prefix in ("_ZN4qpsk18fir_generic_kernelILb1EE", "_ZN4qpsk9mm_kernel", "_ZN4qpsk13decode_kernel"):
+        body = [f for f in funcs if f.startswith(prefix)]
+        assert body, prefix
+        assert " FFMA " not in body[0] and "FFMA2" not in body[0], prefix
+
+
+def test_status_strings_and_version(qp):
+    lib = qp._native.lib()
+    assert lib.qpsk_version() >= 100
+    for st in range(0, -9, -1):
+        assert lib.qpsk_strerror(st)
+
+
+def test_host_side_designers_match_oracle(qp, orc):
+    for span, beta, fs, rs in [(10, float(np.float32(0.4)), 10_000_000, 5_000_000), (16, 0.35, 16000, 1000), (4, 0.25, 8000, 1000),
+                               (6, 0.35, 2500, 1000), (11, 0.9, 10_000_000, 333333)]:
+        assert np.array_equal(qp.RRCFilter.generateCoefficents(span, beta, fs, rs), orc.RRCFilter.generateCoefficents(span, beta, fs, rs))
+    for sps, ro, n in [(2.0, 0.4, 40), (30.0, 0.9, 10), (4.0, 0.35, 13)]:
+        lo, up = qp.fll_design(sps, ro, n)
+        wlo, wup = orc.FLLBandEdgeFilter(sps, ro, n, 0.01).taps()
+        assert np.array_equal(lo, wlo) and np.array_equal(up, wup)
+    assert qp.mm_gains_from_bw(1e-4) == orc.mm_gains_from_bw(1e-4)
+    n = C.c_int(0)
+    assert qp._native.lib().qpsk_rrc_taps(6.0, 0.35, 4000, 1000, None, 0, C.byref(n)) == 0 and n.value == 25
+    buf = (C.c_double * 4)()
+    assert qp._native.lib().qpsk_rrc_taps(6.0, 0.35, 4000, 1000, buf, 4, C.byref(n)) == qp._native.ERR_CAPACITY
+
+
+def test_no_cpu_fallback_without_device(qp):
+    if qp.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    with pytest.raises(qp.QpskCudaError):
+        qp.ComplexFIRFilter(np.ones(4, np.float32))
+    with pytest.raises(qp.QpskCudaError):
+        qp.QPSKModulator(4000, 1000)
+    with pytest.raises(qp.QpskCudaError):
+        qp.QPSKDeModulator(4000, 1000)
+    with pytest.raises(qp.QpskCudaError):
+        qp.FLLBandEdgeFilter(4.0, 0.35, 40, 0.01)
+    # argument validation still mirrors the reference before any device work
+    with pytest.raises(qp.ArgumentException):
+        qp.ComplexFIRFilter(np.ones(3, np.float32))
+    with pytest.raises(qp.ArgumentNullException):
+        qp.ComplexFIRFilter(None)
+
+
+def test_product_never_references_the_oracle():
+    """The oracle is test infrastructure: nothing under the package (or the built library) may touch it."""
+    pkg = os.path.join(ROOT, "qpsk_modulator_demodulator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+    needed = subprocess.check_output(["readelf", "-d", os.path.join(pkg, "lib", "libqpskcuda.so")], text=True)
+    assert "oracle" not in needed
