@@ -116,72 +116,127 @@ struct TapsOf<true> {
 // ---------------------------------------------------------------------------------------------
 // the hot kernel
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// NTAP (<= 2R, even) correlation taps starting at tap index i0, circular register window w[2R]:
+// on entry w[0..R) holds xs[base+i0 .. base+i0+R); slot of element j is (j - i0) mod 2R.
+template <int R, bool CPLX, int NTAP, typename Taps>
+__device__ __forceinline__ void fir_block(const float2* __restrict__ xnext, const Taps& taps, int i0, float2 (&w)[2 * R],
+                                          float2 (&acc)[R], float2 (&accq)[CPLX ? R : 1]) {
+  constexpr int W = 2 * R;
+  const float4* xn = reinterpret_cast<const float4*>(xnext);   // xs + base + i0 + R
+#pragma unroll
+  for (int ii = 0; ii < NTAP; ii += 2) {
+    const float4 v = xn[ii >> 1];
+    w[(R + ii) % W] = make_float2(v.x, v.y);
+    w[(R + ii + 1) % W] = make_float2(v.z, v.w);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if constexpr (!CPLX) {
+        const float g = taps.g[i0 + ii + u];
+        const float2 gg = make_float2(g, g);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(ii + u + r) % W], gg, acc[r]);
+      } else {
+        const float gi = taps.gi[i0 + ii + u];
+        const float gq = taps.gq[i0 + ii + u];
+        const float2 ggi = make_float2(gi, gi), ggq = make_float2(gq, gq);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r] = ffma2(w[(ii + u + r) % W], ggi, acc[r]);
+          accq[CPLX ? r : 0] = ffma2(w[(ii + u + r) % W], ggq, accq[CPLX ? r : 0]);
+        }
+      }
+    }
+  }
+}
+
+// NT compute threads (NT/32 consumer warps) + one producer warp.  No CTA-wide barrier in the steady
+// state: the input ring is handed over with full/empty mbarriers, and every consumer warp stages
+// and TMA-stores its own 32*R outputs, so warps drift apart and their prologues/epilogues overlap the
+// other warps' FFMA2 streams.
 template <int R, int NT, bool CPLX>
-__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(NT + 32, 2)
     fir_tma_kernel(const __grid_constant__ FirArgs a, const __grid_constant__ typename TapsOf<CPLX>::type taps) {
   static_assert(R % 2 == 0, "R must be even (LDS.128 moves two samples)");
   constexpr int T = R * NT;
-  constexpr int W = 2 * R;  // circular register window
+  constexpr int W = 2 * R;   // circular register window
+  constexpr int WS = 32 * R; // outputs per consumer warp and tile
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* xs_base = reinterpret_cast<float2*>(smem_raw);
   float2* ys_base = xs_base + (size_t)a.stages * a.stage_elems;
   uint64_t* full = reinterpret_cast<uint64_t*>(ys_base + 2 * T);
+  uint64_t* empty = full + a.stages;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
 
   if (tid == 0) {
-    for (int s = 0; s < a.stages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NW);
+    }
     fence_mbar_init();
   }
   __syncthreads();
 
-  // warp 0 stages tile `tile` into ring slot `stage`: TMA bulk copies for the in-range part,
-  // plain zero stores for what lies before the stream start (stateless) or past its end.
-  auto issue = [&](long long tile, int stage) {
-    const int ch = (int)(tile / a.tiles_per_ch);
-    const int k = (int)(tile - (long long)ch * a.tiles_per_ch);
-    const long long n0 = (long long)k * T;
-    const long long s0 = n0 + a.advance - a.HL;  // stream index of xs[0] (even)
-    float2* dst = xs_base + (size_t)stage * a.stage_elems;
-    const float2* xch = a.x + (long long)ch * a.ldx;
-    uint64_t* bar = &full[stage];
-    const int E = a.E_load;
-    uint32_t tx = 0;
-    int nA = 0;
-    if (s0 < 0) {
-      nA = (int)((-s0) < (long long)E ? (-s0) : (long long)E);
-      if (a.hist_in) {
-        if (lane == 0) bulk_g2s(dst, a.hist_in + (long long)ch * a.HL + (a.HL + s0), (uint32_t)nA * 8u, bar);
-        tx += (uint32_t)nA * 8u;
-      } else {
-        for (int i = lane; i < nA; i += 32) dst[i] = make_float2(0.f, 0.f);
+  if (warp == NW) {
+    // ---------------- producer warp: stages tile + halo into the ring ----------------
+    // TMA bulk copies for the in-range part, plain zero stores for what lies before the stream start
+    // (stateless) or past its end.
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int it = 0;; ++it) {
+      const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (tile >= a.total_tiles) break;
+      if (it >= a.stages) mbar_wait(&empty[stage], parity ^ 1u);   // consumers released this slot
+      const int ch = (int)(tile / a.tiles_per_ch);
+      const int k = (int)(tile - (long long)ch * a.tiles_per_ch);
+      const long long n0 = (long long)k * T;
+      const long long s0 = n0 + a.advance - a.HL;  // stream index of xs[0] (even)
+      float2* dst = xs_base + (size_t)stage * a.stage_elems;
+      const float2* xch = a.x + (long long)ch * a.ldx;
+      uint64_t* bar = &full[stage];
+      const int E = a.E_load;
+      uint32_t tx = 0;
+      int nA = 0;
+      if (s0 < 0) {
+        nA = (int)((-s0) < (long long)E ? (-s0) : (long long)E);
+        if (a.hist_in) {
+          if (lane == 0) bulk_g2s(dst, a.hist_in + (long long)ch * a.HL + (a.HL + s0), (uint32_t)nA * 8u, bar);
+          tx += (uint32_t)nA * 8u;
+        } else {
+          for (int i = lane; i < nA; i += 32) dst[i] = make_float2(0.f, 0.f);
+        }
+      }
+      const long long m0 = s0 + nA;
+      long long avail = a.L - m0;
+      if (avail < 0) avail = 0;
+      const int nB = (int)(avail < (long long)(E - nA) ? avail : (long long)(E - nA));
+      const int nB2 = nB & ~1;
+      if (nB2 > 0) {
+        if (lane == 0) bulk_g2s(dst + nA, xch + m0, (uint32_t)nB2 * 8u, bar);
+        tx += (uint32_t)nB2 * 8u;
+      }
+      if ((nB & 1) && lane == 0) dst[nA + nB2] = xch[m0 + nB2];
+      for (int i = nA + nB + lane; i < E; i += 32) dst[i] = make_float2(0.f, 0.f);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(bar, tx);
+      if (++stage == a.stages) {
+        stage = 0;
+        parity ^= 1u;
       }
     }
-    const long long m0 = s0 + nA;
-    long long avail = a.L - m0;
-    if (avail < 0) avail = 0;
-    const int nB = (int)(avail < (long long)(E - nA) ? avail : (long long)(E - nA));
-    const int nB2 = nB & ~1;
-    if (nB2 > 0) {
-      if (lane == 0) bulk_g2s(dst + nA, xch + m0, (uint32_t)nB2 * 8u, bar);
-      tx += (uint32_t)nB2 * 8u;
-    }
-    if ((nB & 1) && lane == 0) dst[nA + nB2] = xch[m0 + nB2];
-    for (int i = nA + nB + lane; i < E; i += 32) dst[i] = make_float2(0.f, 0.f);
-    __syncwarp();
-    if (lane == 0) mbar_arrive_expect_tx(bar, tx);
-  };
-
-  if (warp == 0) {
-    for (int s = 0; s < a.stages; ++s) {
-      const long long tile = (long long)blockIdx.x + (long long)s * gridDim.x;
-      if (tile < a.total_tiles) issue(tile, s);
-    }
+    return;
   }
 
+  // ---------------- consumer warps ----------------
   const int base = tid * R;
+  float2* ys_warp = ys_base + (size_t)warp * (2 * WS);   // two buffers of WS outputs
   int stage = 0;
   uint32_t parity = 0;
   for (int it = 0;; ++it) {
@@ -209,10 +264,8 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1))
     float2 accq[CPLX ? R : 1];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
-    if (CPLX) {
 #pragma unroll
-      for (int r = 0; r < (CPLX ? R : 1); ++r) accq[r] = make_float2(0.f, 0.f);
-    }
+    for (int r = 0; r < (CPLX ? R : 1); ++r) accq[r] = make_float2(0.f, 0.f);
     const float4* xv = reinterpret_cast<const float4*>(xs + base);
 #pragma unroll
     for (int r = 0; r < R; r += 2) {
@@ -221,69 +274,27 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1))
       w[r + 1] = make_float2(v.z, v.w);
     }
     int i0 = 0;
-    for (; i0 + W <= a.G; i0 += W) {
-      const float4* xn = reinterpret_cast<const float4*>(xs + base + i0 + R);
-#pragma unroll
-      for (int ii = 0; ii < W; ii += 2) {
-        const float4 v = xn[ii >> 1];
-        w[(R + ii) % W] = make_float2(v.x, v.y);
-        w[(R + ii + 1) % W] = make_float2(v.z, v.w);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if constexpr (!CPLX) {
-            const float g = taps.g[i0 + ii + u];
-            const float2 gg = make_float2(g, g);
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(ii + u + r) % W], gg, acc[r]);
-          } else {
-            const float gi = taps.gi[i0 + ii + u];
-            const float gq = taps.gq[i0 + ii + u];
-            const float2 ggi = make_float2(gi, gi), ggq = make_float2(gq, gq);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              acc[r] = ffma2(w[(ii + u + r) % W], ggi, acc[r]);
-              accq[CPLX ? r : 0] = ffma2(w[(ii + u + r) % W], ggq, accq[CPLX ? r : 0]);
-            }
-          }
-        }
+    for (; i0 + W <= a.G; i0 += W) fir_block<R, CPLX, W>(xs + base + i0 + R, taps, i0, w, acc, accq);
+    // compile-time tail (G - i0 in {0, 2, ..., W-2}): same circular window, no register shuffling
+    {
+      const float2* xn = xs + base + i0 + R;
+      switch ((a.G - i0) >> 1) {
+#define QPSK_TAIL(K) case K: fir_block<R, CPLX, ((2 * K) < W ? (2 * K) : 0)>(xn, taps, i0, w, acc, accq); break;
+        QPSK_TAIL(1) QPSK_TAIL(2) QPSK_TAIL(3) QPSK_TAIL(4) QPSK_TAIL(5) QPSK_TAIL(6) QPSK_TAIL(7) QPSK_TAIL(8) QPSK_TAIL(9)
+        QPSK_TAIL(10) QPSK_TAIL(11) QPSK_TAIL(12) QPSK_TAIL(13) QPSK_TAIL(14) QPSK_TAIL(15)
+#undef QPSK_TAIL
+        default: break;
       }
     }
-    // remainder: two taps per step, window slid explicitly
-    for (; i0 < a.G; i0 += 2) {
-      const float4 v = *reinterpret_cast<const float4*>(xs + base + i0 + R);
-      w[R] = make_float2(v.x, v.y);
-      w[R + 1] = make_float2(v.z, v.w);
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if constexpr (!CPLX) {
-          const float g = taps.g[i0 + u];
-          const float2 gg = make_float2(g, g);
-#pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = ffma2(w[u + r], gg, acc[r]);
-        } else {
-          const float gi = taps.gi[i0 + u];
-          const float gq = taps.gq[i0 + u];
-          const float2 ggi = make_float2(gi, gi), ggq = make_float2(gq, gq);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            acc[r] = ffma2(w[u + r], ggi, acc[r]);
-            accq[CPLX ? r : 0] = ffma2(w[u + r], ggq, accq[CPLX ? r : 0]);
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) w[r] = w[r + 2];
-    }
+    // this warp is done reading the input slot
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
 
-    // ---- epilogue: registers -> smem -> TMA bulk store ----
-    if (tid == 0) bulk_wait_read<1>();  // the store issued two tiles ago has drained this ys buffer
-    __syncthreads();                    // all reads of xs[stage] done; ys[it&1] reusable
-    if (warp == 0) {
-      const long long next = tile + (long long)a.stages * gridDim.x;
-      if (next < a.total_tiles) issue(next, stage);
-    }
-    float2* ys = ys_base + (size_t)(it & 1) * T;
-    float4* yv = reinterpret_cast<float4*>(ys + base);
+    // ---- epilogue: registers -> this warp's smem slice -> TMA bulk store ----
+    float2* ys = ys_warp + (size_t)(it & 1) * WS;
+    if (lane == 0) bulk_wait_read<1>();   // the store issued two tiles ago has drained this buffer
+    __syncwarp();
+    float4* yv = reinterpret_cast<float4*>(ys + lane * R);
 #pragma unroll
     for (int r = 0; r < R; r += 2) {
       float2 o0, o1;
@@ -298,23 +309,25 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1))
       yv[r >> 1] = make_float4(o0.x, o0.y, o1.x, o1.y);
     }
     fence_proxy_async_smem();
-    __syncthreads();
-    float2* yg = a.y + (long long)ch * a.ldy + n0;
-    if ((valid & 1) == 0) {
-      if (tid == 0) {
-        bulk_s2g(yg, ys, (uint32_t)valid * 8u);
+    __syncwarp();
+    int wvalid = valid - warp * WS;
+    wvalid = wvalid < 0 ? 0 : (wvalid > WS ? WS : wvalid);
+    float2* yg = a.y + (long long)ch * a.ldy + n0 + (long long)warp * WS;
+    if ((wvalid & 1) == 0) {
+      if (lane == 0) {
+        if (wvalid > 0) bulk_s2g(yg, ys, (uint32_t)wvalid * 8u);
         bulk_commit();
       }
     } else {
-      for (int i = tid; i < valid; i += NT) yg[i] = ys[i];
-      if (tid == 0) bulk_commit();
+      for (int i = lane; i < wvalid; i += 32) yg[i] = ys[i];
+      if (lane == 0) bulk_commit();
     }
     if (++stage == a.stages) {
       stage = 0;
       parity ^= 1u;
     }
   }
-  if (tid == 0) bulk_wait<0>();
+  if (lane == 0) bulk_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -490,7 +503,7 @@ template <bool CPLX>
 int launch_tma(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, size_t smem, int grid, cudaStream_t s) {
   auto kern = fir_tma_kernel<kR, kNT, CPLX>;
   QPSK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kNT, smem, s>>>(a, taps);
+  kern<<<grid, kNT + 32, smem, s>>>(a, taps);
   QPSK_LAUNCH_CHECK();
   return QPSK_OK;
 }
@@ -532,11 +545,11 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
     a.stage_elems = a.E_load + 2;
     const size_t stage_bytes = (size_t)a.stage_elems * 8;
     const size_t out_bytes = (size_t)2 * kT * 8;
-    int stages = (int)((kSmemBudget - out_bytes - 64) / stage_bytes);
+    int stages = (int)((kSmemBudget - out_bytes - 128) / stage_bytes);
     if (stages > 4) stages = 4;
     if (stages >= 2) {
       a.stages = stages;
-      const size_t smem = (size_t)stages * stage_bytes + out_bytes + (size_t)stages * 8;
+      const size_t smem = (size_t)stages * stage_bytes + out_bytes + (size_t)stages * 16;
       long long grid = 2LL * device_sm_count();
       if (grid > a.total_tiles) grid = a.total_tiles;
       if (real_taps) {
