@@ -8,6 +8,8 @@
 // hunt, MSB-first packing into a bounded ring, end-marker search).
 // All loop / framer state lives in device memory per channel and persists across calls, so arbitrary
 // chunking of a stream gives the same output as the reference object would.
+#include <stdlib.h>
+
 #include <string>
 
 #include "fir.cuh"
@@ -66,6 +68,197 @@ __global__ void __launch_bounds__(32)
   cst_g[c] = S;
   dst_g[c] = D;
   n_bits[c] = nb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// symsync_decode_kernel: Mueller-Muller -> Costas -> decision -> bits fused, 32 channels per CTA of two
+// warps working as a pipeline, one thread per channel in each:
+//   warp 0  stages the matched-filter samples of its 32 channels through shared memory in rounds of
+//           kSsBlock samples (cp.async, double-buffered: the next round's loads fly while this one is
+//           processed, and the interpolator's data-dependent 4-sample reads hit shared memory), runs the
+//           Mueller-Muller recurrence and leaves the round's symbols in a shared queue;
+//   warp 1  runs Costas + decision + differential decode on the previous round's symbols.
+// The two recurrences are independent (MM never looks at the Costas output), so a round costs
+// max(MM, Costas) instead of their sum.  Every round is one MuellerMuller.Process() call on
+// [carried samples | block]: the reference loop is chunk-invariant (MuellerMuller.cs:122-133), so the
+// symbols are those of the one-shot call.  Requires the unlimited-room case (sps - 0.1 > 1).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSsBlock = 32;
+constexpr int kSsCarry = 4;
+constexpr int kSsPitch = kSsBlock + 1;   // odd pitch (float2): rows of different lanes fall in different banks
+constexpr int kSsSymCap = kSsBlock + 4;  // symbols one round can emit (advance >= 0.9 samples)
+constexpr int kSsSymPitch = kSsSymCap + 1;
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct SsSmem {
+  float2 raw[2][32 * kSsPitch];
+  float2 carry[32 * kSsCarry];
+  float2 symq[2][32 * kSsSymPitch];
+  int nsymq[2][32];
+};
+
+__global__ void __launch_bounds__(64)
+    symsync_decode_kernel(const MmParams MP, MmState* mm_g, const float2* __restrict__ q_in, float2* __restrict__ q_out,
+                          long long qcap, const CostasParams CP, CostasState* cst_g, DiffState* dst_g, int C,
+                          const float2* __restrict__ x, long long L, long long ldx, int diff, uint8_t* __restrict__ bits,
+                          long long ld_bits, long long* n_bits, int* n_sym_g) {
+  __shared__ SsSmem sm;
+  const int lane = threadIdx.x & 31;
+  const int role = threadIdx.x >> 5;                // 0: symbol sync, 1: Costas + decode
+  const int c0 = blockIdx.x * 32;
+  const int c_raw = c0 + lane;
+  const bool live = c_raw < C;
+  const int c = live ? c_raw : C - 1;
+  const int rounds = (int)((L + kSsBlock - 1) / kSsBlock);
+
+  // role 0 state
+  MmState S;
+  int carried = 0, n_sym = 0;
+  // role 1 state
+  CostasState K;
+  DiffState D;
+  long long nb = 0;
+  uchar2* bc = reinterpret_cast<uchar2*>(bits + (long long)c * ld_bits);
+
+  auto stage = [&](int r) {                          // lane i copies sample 32r+i of every channel of the CTA
+    const long long n0 = (long long)r * kSsBlock;
+    const int blk = (int)((L - n0) < kSsBlock ? (L - n0) : kSsBlock);
+    float2* dst = sm.raw[r & 1];
+    if (lane < blk) {
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        int ch = c0 + j;
+        if (ch >= C) ch = C - 1;
+        cp_async8(dst + j * kSsPitch + lane, x + (long long)ch * ldx + n0 + lane);
+      }
+    }
+    cp_async_commit();
+  };
+
+  if (role == 0) {
+    S = mm_g[c];
+    carried = S.queued;                              // host guarantees <= kSsCarry
+    for (int i = 0; i < carried; ++i) sm.carry[lane * kSsCarry + i] = q_in[(long long)c * qcap + i];
+    if (rounds > 0) stage(0);
+  } else {
+    K = cst_g[c];
+    D = dst_g[c];
+  }
+
+  for (int r = 0; r <= rounds; ++r) {
+    if (role == 0) {
+      if (r < rounds) {
+        if (r + 1 < rounds) {
+          stage(r + 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncwarp();
+        const long long n0 = (long long)r * kSsBlock;
+        const int blk = (int)((L - n0) < kSsBlock ? (L - n0) : kSsBlock);
+        MmView v;
+        v.queue = sm.carry + lane * kSsCarry;
+        v.in = sm.raw[r & 1] + lane * kSsPitch;
+        v.queued = carried;
+        const int count = carried + blk;
+        float2* sq = sm.symq[r & 1] + lane * kSsSymPitch;
+        int ns = 0;
+        while (S.base_index + 2 < count) {           // MuellerMuller.cs:62
+          float ci, cq;
+          mm_interp(v, S.base_index, S.mu, ci, cq);
+          const float decI = (ci >= 0.f) ? 1.f : -1.f;   // GetSignQpsk :194-198
+          const float decQ = (cq >= 0.f) ? 1.f : -1.f;
+          double advance;
+          if (S.has_prev) {
+            const double term1 = (double)S.prevDI * ci + (double)S.prevDQ * cq;     // :78
+            const double term2 = (double)decI * S.prevSI + (double)decQ * S.prevSQ; // :79
+            const double e = term1 - term2;
+            S.integral += MP.ki * e;                 // :83
+            double corr = MP.kp * e + S.integral;    // :84
+            if (corr > 0.1) corr = 0.1;              // :87-89
+            if (corr < -0.1) corr = -0.1;
+            advance = MP.sps + corr;
+          } else {
+            S.has_prev = 1;
+            advance = MP.sps;
+          }
+          S.prevSI = ci; S.prevSQ = cq; S.prevDI = decI; S.prevDQ = decQ;
+          const double newTime = S.base_index + S.mu + advance;                      // :113
+          S.base_index = (int)floor(newTime);
+          S.mu = newTime - S.base_index;
+          sq[ns++] = make_float2(ci, cq);
+          if (S.base_index + 1 >= count) break;      // :118-119
+        }
+        n_sym += ns;
+        sm.nsymq[r & 1][lane] = ns;
+        // drop consumed samples, keep at least the last three (:123-129)
+        const int consumed = min(max(0, S.base_index - 1), max(0, count - 3));
+        const int remain = count - consumed;         // <= 3 here (4 slots)
+        float2 keep[kSsCarry];
+#pragma unroll
+        for (int i = 0; i < kSsCarry; ++i) keep[i] = (i < remain) ? v.at(consumed + i) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < kSsCarry; ++i) sm.carry[lane * kSsCarry + i] = keep[i];
+        carried = remain;
+        S.base_index -= consumed;
+      }
+    } else if (r >= 1) {
+      // ---- Costas + decision + differential decode (QPSKDeModulator.cs:374-408) on round r-1 ----
+      const int b = (r - 1) & 1;
+      const int ns = sm.nsymq[b][lane];
+      const float2* sq = sm.symq[b] + lane * kSsSymPitch;
+      for (int k = 0; k < ns; ++k) {
+        const float2 in = sq[k];
+        float rI, rQ;
+        costas_step(CP, K, in.x, in.y, rI, rQ);
+        const float dI = (rI >= 0.f) ? 1.f : -1.f;
+        const float dQ = (rQ >= 0.f) ? 1.f : -1.f;
+        unsigned char b0, b1;
+        if (diff) {
+          if (!D.have_prev) {
+            D.prevI = dI; D.prevQ = dQ; D.have_prev = 1;
+            continue;
+          }
+          const float deltaI = dI * D.prevI + dQ * D.prevQ;
+          const float deltaQ = dQ * D.prevI - dI * D.prevQ;
+          D.prevI = dI; D.prevQ = dQ;
+          if (fabsf(deltaI) >= fabsf(deltaQ)) {
+            if (deltaI >= 0.f) { b0 = 0; b1 = 0; } else { b0 = 1; b1 = 1; }
+          } else {
+            if (deltaQ >= 0.f) { b0 = 0; b1 = 1; } else { b0 = 1; b1 = 0; }
+          }
+        } else {
+          if (dI < 0.f) { b0 = 0; b1 = (dQ < 0.f) ? 0 : 1; }
+          else { b0 = 1; b1 = (dQ >= 0.f) ? 1 : 0; }
+        }
+        if (live) bc[nb >> 1] = make_uchar2(b0, b1);
+        nb += 2;
+      }
+    }
+    __syncthreads();                                 // hand the round's symbol queue over / free the other one
+  }
+  if (live) {
+    if (role == 0) {
+      for (int i = 0; i < carried; ++i) q_out[(long long)c * qcap + i] = sm.carry[lane * kSsCarry + i];
+      S.queued = carried;
+      mm_g[c] = S;
+      n_sym_g[c] = n_sym;
+    } else {
+      cst_g[c] = K;
+      dst_g[c] = D;
+      n_bits[c] = nb;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -300,6 +493,8 @@ struct DemodEngine {
   std::vector<uint8_t> markers_host;
   long long ring_cap = 0;
   long long sym_ld = 0;
+  int64_t mf_ld = 0;
+  bool fuse = true;            // use symsync_decode_kernel when it applies
   cudaStream_t stream = nullptr;
 
   ~DemodEngine() {
@@ -317,6 +512,7 @@ struct DemodEngine {
     has_tsc = !blank_or_null(tsc_in);                          // :21
     if (has_tsc) tsc = tsc_in;
     sps = (double)fs / (double)rs;
+    if (const char* e = getenv("QPSK_DEMOD_FUSE")) fuse = (e[0] != '0');   // tuning knob: 0 = separate MM / decode kernels
     QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     const std::vector<double> h = design_rrc((double)span, (double)alpha, fs, rs);   // :28-32
     const std::vector<float> iq = real_taps_as_iq(h);
@@ -355,7 +551,7 @@ struct DemodEngine {
   long long bits_bound(int64_t L) const { return 2 * symbols_bound(L); }
 
   // FLL? -> MF -> MM.  Symbols in t_sym [C][sym_ld], counts in d_nsym.
-  int front(const float2* x, int64_t L, int64_t ldx, cudaStream_t s) {
+  int front(const float2* x, int64_t L, int64_t ldx, cudaStream_t s, bool run_mm = true) {
     const int64_t ld = L + (L & 1);
     QPSK_TRY(t_rrc.ensure((size_t)ld * channels));
     sym_ld = symbols_bound(L);
@@ -370,9 +566,15 @@ struct DemodEngine {
       lds = ld;
     }
     QPSK_TRY(mf.filter_dev(src, t_rrc.p, L, lds, ld, s));      // :360
+    mf_ld = ld;
+    if (!run_mm) return QPSK_OK;
     QPSK_TRY(mm.process_dev(t_rrc.p, L, ld, t_sym.p, 2 * L, sym_ld, d_nsym.p, s));   // :364-367
     return QPSK_OK;
   }
+
+  // the fused MM -> Costas -> decode kernel applies when no call can run out of output room and the MM
+  // queue holds at most kSsCarry samples (always true once every call has had room)
+  bool can_fuse() const { return fuse && (sps - 0.1 > 1.0) && mm.q_bound <= kSsCarry; }
 
   // DeModulate: bits (bytes 0/1) to out [C][ld_out], counts to n_out[C]
   int bits_dev(const float2* x, int64_t L, int64_t ldx, uint8_t* out, int64_t ld_out, long long* n_out, cudaStream_t s) {
@@ -380,7 +582,8 @@ struct DemodEngine {
       QPSK_CUDA_TRY(cudaMemsetAsync(n_out, 0, sizeof(long long) * channels, s));   // :350-351
       return QPSK_OK;
     }
-    QPSK_TRY(front(x, L, ldx, s));
+    const bool fused = can_fuse();
+    QPSK_TRY(front(x, L, ldx, s, !fused));
     const long long need = 2 * sym_ld;
     if (ld_out < need) return QPSK_ERR_CAPACITY;
     uint8_t* raw = out;
@@ -392,9 +595,19 @@ struct DemodEngine {
       raw = d_raw.p; ld_raw = ldr; n_raw = d_nraw.p;
     }
     if ((reinterpret_cast<uintptr_t>(raw) & 1) || (ld_raw & 1)) return QPSK_ERR_ARG;   // uchar2 stores
-    decode_kernel<<<(channels + 31) / 32, 32, 0, s>>>(costas.P, costas.d_state.p, d_diff.p, channels, t_sym.p, sym_ld,
-                                                      d_nsym.p, diff ? 1 : 0, raw, ld_raw, n_raw);
-    QPSK_LAUNCH_CHECK();
+    if (fused) {
+      QPSK_TRY(mm.ensure_queue(8, s));
+      symsync_decode_kernel<<<(channels + 31) / 32, 64, 0, s>>>(mm.P, mm.d_state.p, mm.d_queue[mm.qcur].p, mm.d_queue[mm.qcur ^ 1].p,
+                                                               mm.qcap, costas.P, costas.d_state.p, d_diff.p, channels, t_rrc.p, L,
+                                                               mf_ld, diff ? 1 : 0, raw, ld_raw, n_raw, d_nsym.p);
+      QPSK_LAUNCH_CHECK();
+      mm.qcur ^= 1;
+      mm.q_bound = 4;
+    } else {
+      decode_kernel<<<(channels + 31) / 32, 32, 0, s>>>(costas.P, costas.d_state.p, d_diff.p, channels, t_sym.p, sym_ld,
+                                                        d_nsym.p, diff ? 1 : 0, raw, ld_raw, n_raw);
+      QPSK_LAUNCH_CHECK();
+    }
     if (has_tsc) {
       tsc_strip_kernel<<<(channels + 3) / 4, 128, 0, s>>>(raw, ld_raw, n_raw, d_tsc.p, (int)tsc.size(), out, ld_out, n_out,
                                                           channels);

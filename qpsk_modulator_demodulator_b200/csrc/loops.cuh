@@ -158,7 +158,8 @@ struct CostasParams {
 __device__ __forceinline__ void costas_step(const CostasParams& P, CostasState& S, float inI, float inQ, float& outI,
                                             float& outQ) {
   double s, c;
-  sincos(S.theta, &s, &c);
+  if (fabs(S.theta) < 1.0e5) sincos_fast_f64(S.theta, &s, &c);   // theta stays near [-pi, pi] (:89-91)
+  else sincos(S.theta, &s, &c);
   const double mi = (double)inI * c + (double)inQ * s;   // :72
   const double mq = (double)inQ * c - (double)inI * s;   // :73
   outI = (float)mi;

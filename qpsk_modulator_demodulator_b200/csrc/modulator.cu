@@ -43,7 +43,7 @@ struct ModArgs {
   long long total;          // complex output samples per frame
   int tiles;                // per frame
   int frames;
-  int sps, M, Mp, delay;    // M taps per phase (multiple of kModR), Mp = padded row pitch (odd)
+  int sps, M, Mp, delay;    // M taps per phase, Mp = padded row pitch (odd)
   const float* poly;        // [sps][Mp]: poly[p*Mp + m] = h[p + m*sps]
   uint8_t* tile_sum;        // [frames][tiles]
   uint8_t* tile_pre;        // [frames][tiles]
@@ -72,11 +72,22 @@ __device__ __forceinline__ int frame_bit(const ModArgs& a, int f, long long k) {
   return (v >> (7 - (int)(k & 7))) & 1;         // MSB first (HelperFunctions.cs:14-29)
 }
 
+__device__ __forceinline__ int frame_byte(const ModArgs& a, int f, long long b) {
+  if (b < a.n_start) return a.meta[a.n_tsc + b];
+  if (b < a.n_start + a.n_payload) return a.payload[(long long)f * a.n_payload + (b - a.n_start)];
+  return a.meta[a.n_tsc + a.n_start + (b - a.n_start - a.n_payload)];
+}
+
 __device__ __forceinline__ int dibit_code(const ModArgs& a, int f, long long d) {
   if (d < 0 || d >= a.n_dibits) return 0;
   if (a.mode == 1) return a.payload[d];
-  // fast path: both bits in the same payload/marker byte and no TSC char involved
-  return code_from(frame_bit(a, f, 2 * d), frame_bit(a, f, 2 * d + 1), a.diff);
+  const long long k = 2 * d - a.n_tsc;
+  if (k >= 0 && (a.n_tsc & 1) == 0) {
+    // both bits sit in one framed byte, MSB first: two = b0b1; 00->0 01->1 11->2 10->3 is two ^ (two >> 1)
+    const int two = (frame_byte(a, f, k >> 3) >> (6 - (int)(k & 7))) & 3;
+    return a.diff ? (two ^ (two >> 1)) : two;
+  }
+  return code_from(frame_bit(a, f, 2 * d), frame_bit(a, f, 2 * d + 1), a.diff);   // TSC chars / odd TSC length
 }
 
 __global__ void __launch_bounds__(kModThreads) mod_tile_rot_kernel(const ModArgs a) {
@@ -123,6 +134,23 @@ __device__ __forceinline__ float2 quadrant_symbol(int q) {
   return make_float2(i, v);
 }
 
+// NTAP (<= R) polyphase taps starting at tap m0 (a multiple of R): circular window w[R] holds
+// sym[s_loc + j] for j in [-m, R-1-m] at slot (j mod R); one new symbol slides in per tap.
+template <int R, int NTAP>
+__device__ __forceinline__ void mod_block(const float2* __restrict__ sym, int s_loc, const float* __restrict__ hp, int m0,
+                                          float2 (&w)[R], float2 (&acc)[R]) {
+#pragma unroll
+  for (int u = 0; u < NTAP; ++u) {
+    const float tap = hp[m0 + u];
+    const float2 tt = make_float2(tap, tap);
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(r - u + R) % R], tt, acc[r]);   // sym[s0 + r - m]
+    w[(R - 1 - u) % R] = sym[s_loc - (m0 + u) - 1];                              // slide back by one
+  }
+}
+
+constexpr int kModMaxPer = 12;   // symbols per thread in the scan phase kept in registers
+
 __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int H = a.M;                              // halo symbols in front of the tile
@@ -139,14 +167,22 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
   for (int i = tid; i < a.sps * a.Mp; i += kModThreads) poly[i] = a.poly[i];
 
   // ---- dibit codes -> quadrants (block-wide inclusive scan) -> symbols ----
+  // thread `tid` owns the `per` consecutive symbols k0 .. k0+per-1 of the region [D0-H, D0+kTD)
   const int per = (nsym + kModThreads - 1) / kModThreads;
   const int k0 = tid * per;
-  int local = 0;
+  const bool in_regs = per <= kModMaxPer;
+  int codes[kModMaxPer];
   if (a.diff) {
-    for (int j = 0; j < per; ++j) {
-      const int k = k0 + j;
-      if (k < nsym) local += dibit_code(a, f, D0 - H + k);
+    int local = 0;
+#pragma unroll
+    for (int j = 0; j < kModMaxPer; ++j) {
+      int c = 0;
+      if (j < per && k0 + j < nsym) c = dibit_code(a, f, D0 - H + k0 + j);
+      codes[j] = c;
+      local += c;
     }
+    for (int j = kModMaxPer; j < per; ++j)
+      if (k0 + j < nsym) local += dibit_code(a, f, D0 - H + k0 + j);
     int inc = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -154,28 +190,49 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
       if (lane >= o) inc += n;
     }
     if (lane == 31) warp_tot[warp] = inc;
+    // the halo's own sum S[H-1]: the tile prefix refers to symbol D0, the scan starts H symbols earlier
     __syncthreads();
-    int base = 0;
-    for (int w = 0; w < warp; ++w) base += warp_tot[w];
-    int run = base + inc - local;                 // exclusive prefix of this thread's chunk
-    // the tile prefix refers to symbol D0: subtract the halo's own sum (written by whoever crosses H)
-    // -> first pass stores the running sums, second pass rebases; do it in one pass through smem int
-    for (int j = 0; j < per; ++j) {
-      const int k = k0 + j;
-      if (k < nsym) {
-        run += dibit_code(a, f, D0 - H + k);
-        reinterpret_cast<int*>(sym)[2 * k] = run; // temporarily: inclusive sum S[k]
-        if (k == H - 1) halo_sum_s = run;
+    int run = inc - local;                        // exclusive prefix of this thread's chunk
+    for (int wv = 0; wv < warp; ++wv) run += warp_tot[wv];
+    int S[kModMaxPer];
+#pragma unroll
+    for (int j = 0; j < kModMaxPer; ++j) {
+      run += codes[j];
+      S[j] = run;
+      if (j < per && k0 + j == H - 1) halo_sum_s = run;
+    }
+    if (!in_regs) {                               // very long filters only: spill the running sums through smem
+      int r2 = S[kModMaxPer - 1];
+      for (int j = kModMaxPer; j < per; ++j) {
+        const int k = k0 + j;
+        if (k < nsym) {
+          r2 += dibit_code(a, f, D0 - H + k);
+          reinterpret_cast<int*>(sym)[2 * k] = r2;
+          if (k == H - 1) halo_sum_s = r2;
+        }
       }
     }
     __syncthreads();
     const int pre = (int)a.tile_pre[(long long)f * a.tiles + t] - halo_sum_s;
-    for (int k = tid; k < nsym; k += kModThreads) {
-      const long long d = D0 - H + k;
-      const int S = reinterpret_cast<int*>(sym)[2 * k];
-      float2 v = make_float2(0.f, 0.f);
-      if (d >= 0 && d < a.n_dibits) v = quadrant_symbol((pre + S) & 3);
-      sym[k] = v;   // same thread reads S[k] and overwrites slot k: no hazard
+#pragma unroll
+    for (int j = 0; j < kModMaxPer; ++j) {
+      const int k = k0 + j;
+      if (j < per && k < nsym) {
+        const long long d = D0 - H + k;
+        float2 v = make_float2(0.f, 0.f);
+        if (d >= 0 && d < a.n_dibits) v = quadrant_symbol((pre + S[j]) & 3);
+        sym[k] = v;
+      }
+    }
+    for (int j = kModMaxPer; j < per; ++j) {
+      const int k = k0 + j;
+      if (k < nsym) {
+        const long long d = D0 - H + k;
+        const int Sk = reinterpret_cast<int*>(sym)[2 * k];
+        float2 v = make_float2(0.f, 0.f);
+        if (d >= 0 && d < a.n_dibits) v = quadrant_symbol((pre + Sk) & 3);
+        sym[k] = v;   // same thread reads S[k] and overwrites slot k: no hazard
+      }
     }
   } else {
     for (int k = tid; k < nsym; k += kModThreads) {
@@ -191,36 +248,56 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
   __syncthreads();
 
   // ---- polyphase FIR: item = (group of R symbols, phase) ----
+  // Each round handles G = 256/sps whole groups: the R*sps*G outputs of a round are one contiguous run of the
+  // frame, staged in shared memory (row pitch padded so the strided STS.64 are conflict-free) and written
+  // out with consecutive lanes on consecutive samples.
   constexpr int R = kModR;
-  const int items = (kTD / R) * a.sps;
+  const int sps = a.sps;
+  const int G = kModThreads / sps;                // groups per round (host guarantees sps <= 256)
+  const int row = R * sps;                        // outputs per group
+  const int pitch = (sps < 16) ? row + sps : row; // float2 units
+  float2* stage = reinterpret_cast<float2*>(poly + a.sps * a.Mp + ((a.sps * a.Mp) & 1));
   float2* outf = a.out + (long long)f * a.out_stride;
-  for (int item = tid; item < items; item += kModThreads) {
-    const int g = item / a.sps;
-    const int p = item - g * a.sps;
-    const int s_loc = H + g * R;                  // smem index of the group's first symbol
-    const float* hp = poly + p * a.Mp;
-    float2 w[R], acc[R];
+  const int n_groups = kTD / R;
+  const int gl = tid / sps;                       // group within the round
+  const int p = tid - gl * sps;
+  const float* hp = poly + p * a.Mp;
+  for (int g0 = 0; g0 < n_groups; g0 += G) {
+    const int g = g0 + gl;
+    if (gl < G && g < n_groups) {
+      const int s_loc = H + g * R;                // smem index of the group's first symbol
+      float2 w[R], acc[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      w[r] = sym[s_loc + r];
-      acc[r] = make_float2(0.f, 0.f);
-    }
-    for (int m0 = 0; m0 < a.M; m0 += R) {
-#pragma unroll
-      for (int u = 0; u < R; ++u) {
-        const float tap = hp[m0 + u];
-        const float2 tt = make_float2(tap, tap);
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(r - u + R) % R], tt, acc[r]);   // sym[s0 + r - m]
-        w[(R - 1 - u) % R] = sym[s_loc - (m0 + u) - 1];                              // slide back by one
+      for (int r = 0; r < R; ++r) {
+        w[r] = sym[s_loc + r];
+        acc[r] = make_float2(0.f, 0.f);
       }
-    }
-    const long long i0 = (D0 + (long long)g * R) * a.sps + p - a.delay;
+      int m0 = 0;
+      for (; m0 + R <= a.M; m0 += R) mod_block<R, R>(sym, s_loc, hp, m0, w, acc);
+      switch (a.M - m0) {
+        case 1: mod_block<R, 1>(sym, s_loc, hp, m0, w, acc); break;
+        case 2: mod_block<R, 2>(sym, s_loc, hp, m0, w, acc); break;
+        case 3: mod_block<R, 3>(sym, s_loc, hp, m0, w, acc); break;
+        case 4: mod_block<R, 4>(sym, s_loc, hp, m0, w, acc); break;
+        case 5: mod_block<R, 5>(sym, s_loc, hp, m0, w, acc); break;
+        case 6: mod_block<R, 6>(sym, s_loc, hp, m0, w, acc); break;
+        case 7: mod_block<R, 7>(sym, s_loc, hp, m0, w, acc); break;
+        default: break;
+      }
+      float2* srow = stage + gl * pitch + p;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const long long i = i0 + (long long)r * a.sps;
-      if (i >= 0 && i < a.total) outf[i] = acc[r];
+      for (int r = 0; r < R; ++r) srow[r * sps] = acc[r];
     }
+    __syncthreads();
+    const int ng = (n_groups - g0) < G ? (n_groups - g0) : G;
+    const int n_out = ng * row;
+    const long long i_base = (D0 + (long long)g0 * R) * sps - a.delay;
+    for (int j = tid; j < n_out; j += kModThreads) {
+      const int jr = j / row;
+      const long long i = i_base + j;
+      if (i >= 0 && i < a.total) outf[i] = stage[jr * pitch + (j - jr * row)];
+    }
+    __syncthreads();
   }
 }
 
@@ -246,9 +323,8 @@ struct ModEngine {
 
   int make_bank(int which, const std::vector<float>& h, int bank_delay_in) {
     const int n = (int)h.size();
-    int m = (n + sps - 1) / sps;
-    m = ((m + kModR - 1) / kModR) * kModR;
-    const int mp = m | 1;
+    const int m = (n + sps - 1) / sps;            // taps per phase
+    const int mp = m | 1;                          // odd row pitch: lanes of different phases hit different banks
     std::vector<float> poly((size_t)sps * mp, 0.0f);
     for (int p = 0; p < sps; ++p)
       for (int k = 0; k < m; ++k) {
@@ -337,7 +413,11 @@ struct ModEngine {
       mod_tile_scan_kernel<<<(frames + 3) / 4, 128, 0, s>>>(a);
       QPSK_LAUNCH_CHECK();
     }
-    const size_t smem = (size_t)(kTD + a.M) * sizeof(float2) + (size_t)sps * a.Mp * sizeof(float);
+    if (sps > kModThreads) return QPSK_ERR_UNSUPPORTED;
+    const int grp = kModThreads / sps;
+    const int pitch = (sps < 16) ? (kModR + 1) * sps : kModR * sps;
+    const size_t smem = (size_t)(kTD + a.M) * sizeof(float2) + (size_t)(sps * a.Mp + 1) * sizeof(float) +
+                        (size_t)grp * pitch * sizeof(float2);
     if (smem > 200 * 1024) return QPSK_ERR_UNSUPPORTED;
     QPSK_CUDA_TRY(cudaFuncSetAttribute(mod_shape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mod_shape_kernel<<<grid, kModThreads, smem, s>>>(a);

@@ -1,0 +1,15 @@
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import qpsk_modulator_demodulator_b200 as Q
+import bench_chain
+Q.set_device(0)
+ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); s = ts.cuda_stream
+which = sys.argv[1]
+if which == 'chain':
+    r = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=2, warmup=2, use_fll=False)
+elif which == 'fll':
+    r = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=2, warmup=2, use_fll=True)
+else:
+    r = bench_chain.run_modulator(Q, torch, None, 1, 0, s, steps=2, warmup=2)
+print(json.dumps(r))
