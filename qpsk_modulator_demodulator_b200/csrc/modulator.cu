@@ -6,15 +6,17 @@
 // (N-1-delay == delay for the usual odd N).
 // Here that is computed directly as a polyphase interpolator: no zero-stuffed buffer, no FFT.
 //
-//   mod_tile_rot_kernel   per tile of kTD dibits: sum of the differential rotations mod 4
-//   mod_tile_scan_kernel  one warp per frame: exclusive scan of the tile sums (the differential
-//                         encoder sym[d] = sym[d-1]*delta[d] (:137-146) is a prefix sum of quadrants)
-//   mod_shape_kernel      per (frame, tile): unpack dibits -> block scan -> symbols in shared memory
-//                         -> polyphase FIR.  One work item = (R consecutive symbols, one phase p): a
-//                         sliding register window of symbols, one shared-memory tap per step shared
-//                         by R packed FFMA2.  Lanes run over consecutive phases, so every store
-//                         instruction writes runs of sps consecutive samples.
-//   Algorithmic traffic: 8 B written per output sample, 0.25/sps B read.
+//   mod_tile_rot_kernel    per tile: sum of the differential rotations mod 4 (16 payload bits per thread)
+//   mod_tile_scan_kernel   one warp per frame: exclusive scan of the tile sums (the differential encoder
+//                          sym[d] = sym[d-1]*delta[d] (:137-146) is a prefix sum of quadrants)
+//   mod_shape_kernel<MT>   per (frame, tile): every thread unpacks 8 dibits (two framed bytes) -> block
+//                          scan -> 2048 symbols (tile + halo) in shared memory -> polyphase FIR.
+//                          A thread owns one phase p and walks groups of R = 8 consecutive symbols: the
+//                          MT = ceil(N/sps) taps of its phase stay in registers, the symbols slide through
+//                          a circular register window (one LDS.128 per two taps), 8 packed FFMA2 per tap.
+//                          Lanes run over consecutive phases, so a store instruction writes runs of sps
+//                          consecutive samples (whole 32-byte sectors for sps >= 4).
+//   Algorithmic traffic: 8 B written per output sample, 0.25/sps B read twice.
 //
 // Symbols are exactly (+-1/sqrt2, +-1/sqrt2) in fp32 (prev*delta with delta on the axes is exact), so
 // the quadrant index carries all the information: q = 0:(+,+) 1:(-,+) 2:(-,-) 3:(+,-), and the
@@ -26,10 +28,11 @@
 
 namespace qpsk {
 
-constexpr int kTD = 2048;        // dibits (symbols) per tile
 constexpr int kModThreads = 256;
-constexpr int kModR = 8;         // symbols per work item
-constexpr float kInvSqrt2 = 0.7071067811865475f;  // QPSKModulator.cs:36
+constexpr int kModR = 8;                         // symbols per group / register window
+constexpr int kModRegion = kModThreads * 8;      // symbols (halo + tile) staged per CTA: 8 per thread
+constexpr int kModMaxMT = 96;                    // taps per phase supported by the register-resident kernel
+constexpr float kInvSqrt2 = 0.7071067811865475f; // QPSKModulator.cs:36
 
 struct ModArgs {
   // source: mode 0 = framed bytes (tsc | start | payload[f] | end), mode 1 = one code byte per dibit
@@ -39,12 +42,11 @@ struct ModArgs {
   int n_tsc, n_start, n_end;
   int mode, diff;
   long long n_dibits;       // per frame
-  long long n_virtual;      // symbols incl. the zero tail that still produces output
   long long total;          // complex output samples per frame
   int tiles;                // per frame
   int frames;
-  int sps, M, Mp, delay;    // M taps per phase, Mp = padded row pitch (odd)
-  const float* poly;        // [sps][Mp]: poly[p*Mp + m] = h[p + m*sps]
+  int sps, MT, HP, TD, delay;  // MT taps per phase (padded), HP halo symbols (multiple of 8), TD = 2048 - HP
+  const float* poly;        // [sps][MT]: poly[p*MT + m] = h[p + m*sps]
   uint8_t* tile_sum;        // [frames][tiles]
   uint8_t* tile_pre;        // [frames][tiles]
   float2* out;
@@ -61,40 +63,60 @@ __device__ __forceinline__ int code_from(int b0, int b1, int diff) {
   return ((b0 != 0) << 1) | (b1 != 0);          // :150-151  (bit==0 ? -1/sqrt2 : +1/sqrt2)
 }
 
-__device__ __forceinline__ int frame_bit(const ModArgs& a, int f, long long k) {
-  if (k < a.n_tsc) return a.meta[k];
-  k -= a.n_tsc;
-  const long long b = k >> 3;
-  int v;
-  if (b < a.n_start) v = a.meta[a.n_tsc + b];
-  else if (b < a.n_start + a.n_payload) v = a.payload[(long long)f * a.n_payload + (b - a.n_start)];
-  else v = a.meta[a.n_tsc + a.n_start + (b - a.n_start - a.n_payload)];
-  return (v >> (7 - (int)(k & 7))) & 1;         // MSB first (HelperFunctions.cs:14-29)
-}
-
 __device__ __forceinline__ int frame_byte(const ModArgs& a, int f, long long b) {
   if (b < a.n_start) return a.meta[a.n_tsc + b];
   if (b < a.n_start + a.n_payload) return a.payload[(long long)f * a.n_payload + (b - a.n_start)];
   return a.meta[a.n_tsc + a.n_start + (b - a.n_start - a.n_payload)];
 }
 
+__device__ __forceinline__ int frame_bit(const ModArgs& a, int f, long long k) {
+  if (k < a.n_tsc) return a.meta[k];
+  k -= a.n_tsc;
+  return (frame_byte(a, f, k >> 3) >> (7 - (int)(k & 7))) & 1;   // MSB first (HelperFunctions.cs:14-29)
+}
+
 __device__ __forceinline__ int dibit_code(const ModArgs& a, int f, long long d) {
   if (d < 0 || d >= a.n_dibits) return 0;
   if (a.mode == 1) return a.payload[d];
-  const long long k = 2 * d - a.n_tsc;
-  if (k >= 0 && (a.n_tsc & 1) == 0) {
-    // both bits sit in one framed byte, MSB first: two = b0b1; 00->0 01->1 11->2 10->3 is two ^ (two >> 1)
-    const int two = (frame_byte(a, f, k >> 3) >> (6 - (int)(k & 7))) & 3;
-    return a.diff ? (two ^ (two >> 1)) : two;
+  return code_from(frame_bit(a, f, 2 * d), frame_bit(a, f, 2 * d + 1), a.diff);
+}
+
+// Codes of the 8 symbols d0 .. d0+7 (d0 a multiple of 8), packed MSB first: symbol j in bits [15-2j, 14-2j].
+// Symbols outside [0, n_dibits) get code 0.
+__device__ __forceinline__ unsigned chunk_codes(const ModArgs& a, int f, long long d0) {
+  if (d0 + 8 <= 0 || d0 >= a.n_dibits) return 0u;
+  if (a.mode == 0 && d0 >= 0 && d0 + 8 <= a.n_dibits && (a.n_tsc & 7) == 0) {
+    const long long k0 = 2 * d0 - a.n_tsc;       // first bit of the chunk inside the framed bytes
+    if (k0 >= 0) {
+      // 16 framed bits, MSB first; per 2-bit field b0b1: 00->0 01->1 11->2 10->3 is two ^ (two >> 1)
+      const long long b = k0 >> 3;
+      unsigned v;
+      const long long pb = b - a.n_start;
+      if (pb >= 0 && pb + 1 < a.n_payload) {
+        const uint8_t* q = a.payload + (long long)f * a.n_payload + pb;
+        v = ((unsigned)q[0] << 8) | q[1];
+      } else {
+        v = ((unsigned)frame_byte(a, f, b) << 8) | (unsigned)frame_byte(a, f, b + 1);
+      }
+      return a.diff ? (v ^ ((v >> 1) & 0x5555u)) : v;
+    }
   }
-  return code_from(frame_bit(a, f, 2 * d), frame_bit(a, f, 2 * d + 1), a.diff);   // TSC chars / odd TSC length
+  unsigned c = 0;                                 // TSC characters, odd TSC length, frame edges, code-byte mode
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) c = (c << 2) | (unsigned)dibit_code(a, f, d0 + j);
+  return c;
 }
 
 __global__ void __launch_bounds__(kModThreads) mod_tile_rot_kernel(const ModArgs a) {
   const int f = blockIdx.y, t = blockIdx.x;
-  const long long d0 = (long long)t * kTD;
+  const long long D0 = (long long)t * a.TD;
   int s = 0;
-  for (int i = threadIdx.x; i < kTD; i += kModThreads) s += dibit_code(a, f, d0 + i);
+  if (8 * (int)threadIdx.x < a.TD) {
+    unsigned c = chunk_codes(a, f, D0 + 8 * threadIdx.x);
+    c = (c & 0x3333u) + ((c >> 2) & 0x3333u);   // sum of the eight 2-bit fields
+    c = (c & 0x0F0Fu) + ((c >> 4) & 0x0F0Fu);
+    s = (int)((c & 0xFFu) + (c >> 8));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   __shared__ int ws[kModThreads / 32];
@@ -134,171 +156,141 @@ __device__ __forceinline__ float2 quadrant_symbol(int q) {
   return make_float2(i, v);
 }
 
-// NTAP (<= R) polyphase taps starting at tap m0 (a multiple of R): circular window w[R] holds
-// sym[s_loc + j] for j in [-m, R-1-m] at slot (j mod R); one new symbol slides in per tap.
-template <int R, int NTAP>
-__device__ __forceinline__ void mod_block(const float2* __restrict__ sym, int s_loc, const float* __restrict__ hp, int m0,
-                                          float2 (&w)[R], float2 (&acc)[R]) {
-#pragma unroll
-  for (int u = 0; u < NTAP; ++u) {
-    const float tap = hp[m0 + u];
-    const float2 tt = make_float2(tap, tap);
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(r - u + R) % R], tt, acc[r]);   // sym[s0 + r - m]
-    w[(R - 1 - u) % R] = sym[s_loc - (m0 + u) - 1];                              // slide back by one
-  }
-}
-
-constexpr int kModMaxPer = 12;   // symbols per thread in the scan phase kept in registers
-
+template <int MT>
 __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int H = a.M;                              // halo symbols in front of the tile
-  const int nsym = kTD + H;
-  float2* sym = reinterpret_cast<float2*>(smem_raw);           // sym[k] = symbol D0 - H + k
-  float* poly = reinterpret_cast<float*>(sym + nsym);          // [sps][Mp]
+  constexpr int R = kModR;
+  __shared__ __align__(16) float2 sym[kModRegion];             // sym[k] = symbol D0 - HP + k
   __shared__ int warp_tot[kModThreads / 32];
   __shared__ int halo_sum_s;
 
   const int f = blockIdx.y, t = blockIdx.x;
-  const long long D0 = (long long)t * kTD;
+  const long long D0 = (long long)t * a.TD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < a.sps * a.Mp; i += kModThreads) poly[i] = a.poly[i];
-
-  // ---- dibit codes -> quadrants (block-wide inclusive scan) -> symbols ----
-  // thread `tid` owns the `per` consecutive symbols k0 .. k0+per-1 of the region [D0-H, D0+kTD)
-  const int per = (nsym + kModThreads - 1) / kModThreads;
-  const int k0 = tid * per;
-  const bool in_regs = per <= kModMaxPer;
-  int codes[kModMaxPer];
-  if (a.diff) {
-    int local = 0;
+  // ---- 8 dibits per thread -> quadrants (block-wide scan) -> symbols ----
+  {
+    const long long d0 = D0 - a.HP + 8 * tid;
+    const unsigned c = chunk_codes(a, f, d0);
+    int run[8];
+    int q0 = 0;
+    if (a.diff) {
+      int acc = 0;
 #pragma unroll
-    for (int j = 0; j < kModMaxPer; ++j) {
-      int c = 0;
-      if (j < per && k0 + j < nsym) c = dibit_code(a, f, D0 - H + k0 + j);
-      codes[j] = c;
-      local += c;
-    }
-    for (int j = kModMaxPer; j < per; ++j)
-      if (k0 + j < nsym) local += dibit_code(a, f, D0 - H + k0 + j);
-    int inc = local;
+      for (int j = 0; j < 8; ++j) {
+        acc += (int)((c >> (14 - 2 * j)) & 3u);
+        run[j] = acc;
+      }
+      int inc = acc;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int n = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += n;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      if (lane == 31) warp_tot[warp] = inc;
+      // sum over the halo = exclusive prefix of chunk HP/8 (warp 0): the tile prefix refers to symbol D0
+      if (tid == (a.HP >> 3)) halo_sum_s = inc - acc;
+      __syncthreads();
+      int base = inc - acc;
+      for (int w = 0; w < warp; ++w) base += warp_tot[w];
+      q0 = (int)a.tile_pre[(long long)f * a.tiles + t] - halo_sum_s + base;
     }
-    if (lane == 31) warp_tot[warp] = inc;
-    // the halo's own sum S[H-1]: the tile prefix refers to symbol D0, the scan starts H symbols earlier
-    __syncthreads();
-    int run = inc - local;                        // exclusive prefix of this thread's chunk
-    for (int wv = 0; wv < warp; ++wv) run += warp_tot[wv];
-    int S[kModMaxPer];
+    float4* dst = reinterpret_cast<float4*>(sym + 8 * tid);
 #pragma unroll
-    for (int j = 0; j < kModMaxPer; ++j) {
-      run += codes[j];
-      S[j] = run;
-      if (j < per && k0 + j == H - 1) halo_sum_s = run;
-    }
-    if (!in_regs) {                               // very long filters only: spill the running sums through smem
-      int r2 = S[kModMaxPer - 1];
-      for (int j = kModMaxPer; j < per; ++j) {
-        const int k = k0 + j;
-        if (k < nsym) {
-          r2 += dibit_code(a, f, D0 - H + k);
-          reinterpret_cast<int*>(sym)[2 * k] = r2;
-          if (k == H - 1) halo_sum_s = r2;
-        }
-      }
-    }
-    __syncthreads();
-    const int pre = (int)a.tile_pre[(long long)f * a.tiles + t] - halo_sum_s;
+    for (int j = 0; j < 8; j += 2) {
+      float2 v[2];
 #pragma unroll
-    for (int j = 0; j < kModMaxPer; ++j) {
-      const int k = k0 + j;
-      if (j < per && k < nsym) {
-        const long long d = D0 - H + k;
-        float2 v = make_float2(0.f, 0.f);
-        if (d >= 0 && d < a.n_dibits) v = quadrant_symbol((pre + S[j]) & 3);
-        sym[k] = v;
+      for (int u = 0; u < 2; ++u) {
+        const long long d = d0 + j + u;
+        const int code = (int)((c >> (14 - 2 * (j + u))) & 3u);
+        float2 sv;
+        if (a.diff) sv = quadrant_symbol((q0 + run[j + u]) & 3);
+        else sv = make_float2((code & 2) ? kInvSqrt2 : -kInvSqrt2, (code & 1) ? kInvSqrt2 : -kInvSqrt2);
+        if (d < 0 || d >= a.n_dibits) sv = make_float2(0.f, 0.f);
+        v[u] = sv;
       }
-    }
-    for (int j = kModMaxPer; j < per; ++j) {
-      const int k = k0 + j;
-      if (k < nsym) {
-        const long long d = D0 - H + k;
-        const int Sk = reinterpret_cast<int*>(sym)[2 * k];
-        float2 v = make_float2(0.f, 0.f);
-        if (d >= 0 && d < a.n_dibits) v = quadrant_symbol((pre + Sk) & 3);
-        sym[k] = v;   // same thread reads S[k] and overwrites slot k: no hazard
-      }
-    }
-  } else {
-    for (int k = tid; k < nsym; k += kModThreads) {
-      const long long d = D0 - H + k;
-      float2 v = make_float2(0.f, 0.f);
-      if (d >= 0 && d < a.n_dibits) {
-        const int c = dibit_code(a, f, d);
-        v = make_float2((c & 2) ? kInvSqrt2 : -kInvSqrt2, (c & 1) ? kInvSqrt2 : -kInvSqrt2);
-      }
-      sym[k] = v;
+      dst[j >> 1] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
     }
   }
   __syncthreads();
 
-  // ---- polyphase FIR: item = (group of R symbols, phase) ----
-  // Each round handles G = 256/sps whole groups: the R*sps*G outputs of a round are one contiguous run of the
-  // frame, staged in shared memory (row pitch padded so the strided STS.64 are conflict-free) and written
-  // out with consecutive lanes on consecutive samples.
-  constexpr int R = kModR;
+  // ---- polyphase FIR: this thread's phase p, groups of R consecutive symbols ----
   const int sps = a.sps;
-  const int G = kModThreads / sps;                // groups per round (host guarantees sps <= 256)
-  const int row = R * sps;                        // outputs per group
-  const int pitch = (sps < 16) ? row + sps : row; // float2 units
-  float2* stage = reinterpret_cast<float2*>(poly + a.sps * a.Mp + ((a.sps * a.Mp) & 1));
-  float2* outf = a.out + (long long)f * a.out_stride;
-  const int n_groups = kTD / R;
-  const int gl = tid / sps;                       // group within the round
+  const int gl = tid / sps;                       // group slot within a round
   const int p = tid - gl * sps;
-  const float* hp = poly + p * a.Mp;
-  for (int g0 = 0; g0 < n_groups; g0 += G) {
-    const int g = g0 + gl;
-    if (gl < G && g < n_groups) {
-      const int s_loc = H + g * R;                // smem index of the group's first symbol
-      float2 w[R], acc[R];
+  const int G = kModThreads / sps;                // whole groups per round
+  if (gl >= G) return;
+  float tap[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) tap[m] = a.poly[p * MT + m];
+  const int n_groups = a.TD / R;
+  float2* ob = a.out + (long long)f * a.out_stride + (D0 * sps - a.delay);   // output of (symbol D0, phase 0)
+  const long long i_tile = D0 * sps - a.delay;    // its index in the frame
+  for (int g = gl; g < n_groups; g += G) {
+    const int s_loc = a.HP + g * R;               // smem index of the group's first symbol (multiple of 8)
+    float2 w[R], acc[R];
+    const float4* s4 = reinterpret_cast<const float4*>(sym + s_loc);
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+      const float4 v = s4[r >> 1];
+      w[r] = make_float2(v.x, v.y);
+      w[r + 1] = make_float2(v.z, v.w);
+      acc[r] = make_float2(0.f, 0.f);
+      acc[r + 1] = make_float2(0.f, 0.f);
+    }
+    // tap m multiplies sym[s0 + r - m]; slot of symbol offset j is (j mod R); one new (older) symbol per tap,
+    // fetched two at a time (sym[s_loc - m - 2], sym[s_loc - m - 1] are 16-byte aligned for even m)
+#pragma unroll
+    for (int m = 0; m < MT; m += 2) {
+      const float4 nx = *reinterpret_cast<const float4*>(sym + s_loc - m - 2);
+      {
+        const float2 tt = make_float2(tap[m], tap[m]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(r - m + 16 * R) % R], tt, acc[r]);
+        w[(R - 1 - m + 16 * R) % R] = make_float2(nx.z, nx.w);      // sym[s_loc - m - 1]
+      }
+      {
+        const float2 tt = make_float2(tap[m + 1], tap[m + 1]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(r - m - 1 + 16 * R) % R], tt, acc[r]);
+        w[(R - 2 - m + 16 * R) % R] = make_float2(nx.x, nx.y);      // sym[s_loc - m - 2]
+      }
+    }
+    const int off = g * R * sps + p;              // relative to ob, r = 0
+    const long long i0 = i_tile + off;
+    if (i0 >= 0 && i0 + (long long)(R - 1) * sps < a.total) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) ob[off + r * sps] = acc[r];
+    } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        w[r] = sym[s_loc + r];
-        acc[r] = make_float2(0.f, 0.f);
+        const long long i = i0 + (long long)r * sps;
+        if (i >= 0 && i < a.total) ob[off + r * sps] = acc[r];
       }
-      int m0 = 0;
-      for (; m0 + R <= a.M; m0 += R) mod_block<R, R>(sym, s_loc, hp, m0, w, acc);
-      switch (a.M - m0) {
-        case 1: mod_block<R, 1>(sym, s_loc, hp, m0, w, acc); break;
-        case 2: mod_block<R, 2>(sym, s_loc, hp, m0, w, acc); break;
-        case 3: mod_block<R, 3>(sym, s_loc, hp, m0, w, acc); break;
-        case 4: mod_block<R, 4>(sym, s_loc, hp, m0, w, acc); break;
-        case 5: mod_block<R, 5>(sym, s_loc, hp, m0, w, acc); break;
-        case 6: mod_block<R, 6>(sym, s_loc, hp, m0, w, acc); break;
-        case 7: mod_block<R, 7>(sym, s_loc, hp, m0, w, acc); break;
-        default: break;
-      }
-      float2* srow = stage + gl * pitch + p;
-#pragma unroll
-      for (int r = 0; r < R; ++r) srow[r * sps] = acc[r];
     }
-    __syncthreads();
-    const int ng = (n_groups - g0) < G ? (n_groups - g0) : G;
-    const int n_out = ng * row;
-    const long long i_base = (D0 + (long long)g0 * R) * sps - a.delay;
-    for (int j = tid; j < n_out; j += kModThreads) {
-      const int jr = j / row;
-      const long long i = i_base + j;
-      if (i >= 0 && i < a.total) outf[i] = stage[jr * pitch + (j - jr * row)];
-    }
-    __syncthreads();
   }
+}
+
+typedef void (*ModShapeFn)(const ModArgs);
+static ModShapeFn mod_shape_pick(int mt) {
+  switch (mt) {
+    case 4: return mod_shape_kernel<4>;
+    case 8: return mod_shape_kernel<8>;
+    case 12: return mod_shape_kernel<12>;
+    case 16: return mod_shape_kernel<16>;
+    case 20: return mod_shape_kernel<20>;
+    case 24: return mod_shape_kernel<24>;
+    case 32: return mod_shape_kernel<32>;
+    case 48: return mod_shape_kernel<48>;
+    case 64: return mod_shape_kernel<64>;
+    case 96: return mod_shape_kernel<96>;
+    default: return nullptr;
+  }
+}
+static int mod_pad_taps(int m) {
+  static const int sizes[] = {4, 8, 12, 16, 20, 24, 32, 48, 64, 96};
+  for (int v : sizes)
+    if (m <= v) return v;
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -311,7 +303,7 @@ struct ModEngine {
   int sps = 0, delay = 0;
   // two polyphase banks: [0] pulse shaping with the RRC taps, [1] the "no pulse shaping" delta
   DevBuf<float> d_poly[2];
-  int M[2] = {0, 0}, Mp[2] = {0, 0}, bank_delay[2] = {0, 0};
+  int MT[2] = {0, 0}, bank_delay[2] = {0, 0};
   DevBuf<uint8_t> d_meta, d_tile_sum, d_tile_pre, d_src;
   DevBuf<float2> d_out;
   std::vector<uint8_t> meta_host;
@@ -324,14 +316,15 @@ struct ModEngine {
   int make_bank(int which, const std::vector<float>& h, int bank_delay_in) {
     const int n = (int)h.size();
     const int m = (n + sps - 1) / sps;            // taps per phase
-    const int mp = m | 1;                          // odd row pitch: lanes of different phases hit different banks
-    std::vector<float> poly((size_t)sps * mp, 0.0f);
+    const int mt = mod_pad_taps(m);
+    MT[which] = mt; bank_delay[which] = bank_delay_in;
+    if (mt == 0) return QPSK_OK;                  // too long for the register-resident kernel: reported at run()
+    std::vector<float> poly((size_t)sps * mt, 0.0f);
     for (int p = 0; p < sps; ++p)
       for (int k = 0; k < m; ++k) {
         const long long j = p + (long long)k * sps;
-        if (j < n) poly[(size_t)p * mp + k] = h[(size_t)j];
+        if (j < n) poly[(size_t)p * mt + k] = h[(size_t)j];
       }
-    M[which] = m; Mp[which] = mp; bank_delay[which] = bank_delay_in;
     QPSK_TRY(d_poly[which].alloc(poly.size()));
     QPSK_CUDA_TRY(cudaMemcpyAsync(d_poly[which].p, poly.data(), poly.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
     QPSK_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -350,7 +343,7 @@ struct ModEngine {
     sps = fs / rs;                                  // :115 integer division
     delay = ((int)taps_d.size() - 1) / 2;           // :119
     QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    if (sps > 0 && !taps_f.empty()) {
+    if (sps > 0 && sps <= kModThreads && !taps_f.empty()) {
       // fftFilter advances by N-1 (FIRFilter.cs:130-138) while the symbols sit at delay + d*sps (:128,154):
       // tap index = i + (N-1-delay) - d*sps.  N-1-delay == delay only for odd N.
       QPSK_TRY(make_bank(0, taps_f, (int)taps_f.size() - 1 - delay));
@@ -391,15 +384,20 @@ struct ModEngine {
   // launches the kernels; `a` has source fields filled in
   int run(ModArgs a, bool pulse, int64_t n_dibits, int frames, float2* out, int64_t out_stride, cudaStream_t s) {
     const int bank = pulse ? 0 : 1;
+    if (sps > kModThreads) return QPSK_ERR_UNSUPPORTED;
+    ModShapeFn shape = mod_shape_pick(MT[bank]);
+    if (!shape) return QPSK_ERR_UNSUPPORTED;        // more than kModMaxMT taps per phase (DESIGN.md limits)
     a.diff = diff ? 1 : 0;
     a.n_dibits = n_dibits;
     a.frames = frames;
-    a.sps = sps; a.M = M[bank]; a.Mp = Mp[bank]; a.delay = bank_delay[bank];
+    a.sps = sps; a.MT = MT[bank]; a.delay = bank_delay[bank];
+    a.HP = (a.MT + 7) & ~7;
+    a.TD = kModRegion - a.HP;
     a.poly = d_poly[bank].p;
     a.total = pulse ? (2LL * delay + n_dibits * sps) : ((long long)delay + n_dibits * sps);
     // last output index + filter delay, in symbols (+1): symbols past n_dibits are zero
-    a.n_virtual = (a.total - 1 + a.delay) / sps + 1;
-    const long long tiles = (a.n_virtual + kTD - 1) / kTD;
+    const long long n_virtual = (a.total - 1 + a.delay) / sps + 1;
+    const long long tiles = (n_virtual + a.TD - 1) / a.TD;
     if (tiles > 0x7fffffffLL || frames > 65535) return QPSK_ERR_UNSUPPORTED;
     a.tiles = (int)tiles;
     a.out = out; a.out_stride = out_stride;
@@ -413,14 +411,7 @@ struct ModEngine {
       mod_tile_scan_kernel<<<(frames + 3) / 4, 128, 0, s>>>(a);
       QPSK_LAUNCH_CHECK();
     }
-    if (sps > kModThreads) return QPSK_ERR_UNSUPPORTED;
-    const int grp = kModThreads / sps;
-    const int pitch = (sps < 16) ? (kModR + 1) * sps : kModR * sps;
-    const size_t smem = (size_t)(kTD + a.M) * sizeof(float2) + (size_t)(sps * a.Mp + 1) * sizeof(float) +
-                        (size_t)grp * pitch * sizeof(float2);
-    if (smem > 200 * 1024) return QPSK_ERR_UNSUPPORTED;
-    QPSK_CUDA_TRY(cudaFuncSetAttribute(mod_shape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mod_shape_kernel<<<grid, kModThreads, smem, s>>>(a);
+    shape<<<grid, kModThreads, 0, s>>>(a);
     QPSK_LAUNCH_CHECK();
     return QPSK_OK;
   }
