@@ -173,6 +173,7 @@ def main():
     import torch
     import torch.distributed as dist
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("QPSK_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

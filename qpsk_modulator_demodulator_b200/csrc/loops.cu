@@ -232,25 +232,32 @@ __global__ void __launch_bounds__(kFllCtaThreads)
       for (int k = 0; k < K; ++k) {
         const float2 v = wp[8 * k];
         const float p1 = ta[k] * v.x, p2 = tb[k] * v.y, p3 = ta[k] * v.y, p4 = tb[k] * v.x;
-        const float nLoI = loI + (p1 - p2), nLoQ = loQ + (p3 + p4), nUpI = upI + (p1 + p2), nUpQ = upQ + (p3 - p4);
-        // lane 7's last element is out[n] itself when TAIL == 0: its term is added after the rotation (below)
-        const bool skip = (TAIL == 0) && (k == K - 1) && (g == kFllGroup - 1);
-        loI = skip ? loI : nLoI;
-        loQ = skip ? loQ : nLoQ;
-        upI = skip ? upI : nUpI;
-        upQ = skip ? upQ : nUpQ;
+        if (TAIL == 0 && k == K - 1) {
+          // lane 7's last element is out[n] itself: its term is added after the rotation (below)
+          const bool skip = g == kFllGroup - 1;
+          loI = skip ? loI : loI + (p1 - p2);
+          loQ = skip ? loQ : loQ + (p3 + p4);
+          upI = skip ? upI : upI + (p1 + p2);
+          upQ = skip ? upQ : upQ + (p3 - p4);
+        } else {
+          loI = loI + (p1 - p2);
+          loQ = loQ + (p3 + p4);
+          upI = upI + (p1 + p2);
+          upQ = upQ + (p3 - p4);
+        }
       }
+      // exchange the eight lane partials; every lane adds them in lane order 0..7 (:176-180), redundantly, so
+      // nothing but register arithmetic follows the rotation (cross-lane traffic stays off the critical path)
       mypart[g] = make_float4(loI, loQ, upI, upQ);
       __syncwarp();
       float aLoI = 0.f, aLoQ = 0.f, aUpI = 0.f, aUpQ = 0.f;
 #pragma unroll
-      for (int l = 0; l < kFllGroup - 1; ++l) {             // lanes 0..6 (:176-180)
+      for (int l = 0; l < kFllGroup - 1; ++l) {
         const float4 q = mypart[l];
         aLoI += q.x; aLoQ += q.y; aUpI += q.z; aUpQ += q.w;
       }
       float4 q7 = mypart[kFllGroup - 1];
-      // term of the newest element out[n]
-      const float n1 = newA * oI, n2 = newB * oQ, n3 = newA * oQ, n4 = newB * oI;
+      const float n1 = newA * oI, n2 = newB * oQ, n3 = newA * oQ, n4 = newB * oI;   // term of out[n]
       if (TAIL == 0) {                                       // last term of lane 7, then lane 7 joins the sum
         q7.x = q7.x + (n1 - n2); q7.y = q7.y + (n3 + n4); q7.z = q7.z + (n1 + n2); q7.w = q7.w + (n3 - n4);
         aLoI += q7.x; aLoQ += q7.y; aUpI += q7.z; aUpQ += q7.w;
