@@ -294,6 +294,61 @@ __global__ void __launch_bounds__(128)
   if (lane == 0) n_out[c] = len;
 }
 
+// Same, with the channel's bits staged in shared memory first (coalesced 16-byte loads), so the search
+// and the shifted copy read shared memory; used when a channel's raw bits fit (the usual burst sizes).
+__global__ void __launch_bounds__(128)
+    tsc_strip_smem_kernel(const uint8_t* __restrict__ raw, long long ld_raw, const long long* __restrict__ n_raw,
+                          const uint8_t* __restrict__ tsc, int T, uint8_t* __restrict__ out, long long ld_out, long long* n_out,
+                          int C, int row_bytes) {
+  extern __shared__ __align__(16) uint8_t sm_bits[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + w;
+  if (c >= C) return;
+  uint8_t* row = sm_bits + (size_t)w * row_bytes;
+  uint8_t* pat = sm_bits + (size_t)(blockDim.x >> 5) * row_bytes + (size_t)w * ((T + 15) & ~15);
+  const uint8_t* r = raw + (long long)c * ld_raw;
+  const int n = (int)n_raw[c];
+  // rows are 16-byte aligned when ld_raw is a multiple of 16 and the base is; otherwise byte loads
+  if ((((uintptr_t)r) & 15) == 0) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(r);
+    uint4* row4 = reinterpret_cast<uint4*>(row);
+    for (int i = lane; i < (n + 15) / 16; i += 32) row4[i] = r4[i];
+  } else {
+    for (int i = lane; i < n; i += 32) row[i] = r[i];
+  }
+  for (int i = lane; i < T; i += 32) pat[i] = tsc[i];
+  __syncwarp();
+  int first = -1;
+  for (int base = 0; base + T <= n; base += 32) {
+    const int idx = base + lane;
+    bool ok = idx + T <= n;
+    for (int j = 0; ok && j < T; ++j) ok = (row[idx + j] == pat[j]);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m) {
+      first = base + (__ffs(m) - 1);
+      break;
+    }
+  }
+  uint8_t* o = out + (long long)c * ld_out;
+  int len = 0;
+  if (first >= 0) {
+    const int start = first + T;
+    len = n - start;
+    if ((((uintptr_t)o) & 3) == 0) {
+      uint32_t* o4 = reinterpret_cast<uint32_t*>(o);
+      const int nw = len >> 2;
+      for (int i = lane; i < nw; i += 32) {
+        const uint8_t* sp = row + start + 4 * i;
+        o4[i] = (uint32_t)sp[0] | ((uint32_t)sp[1] << 8) | ((uint32_t)sp[2] << 16) | ((uint32_t)sp[3] << 24);
+      }
+      for (int i = 4 * nw + lane; i < len; i += 32) o[i] = row[start + i];
+    } else {
+      for (int i = lane; i < len; i += 32) o[i] = row[start + i];
+    }
+  }
+  if (lane == 0) n_out[c] = len;
+}
+
 // ---------------------------------------------------------------------------------------------
 // framer (DeModulateBytes :169-259), one thread per channel
 // ---------------------------------------------------------------------------------------------
@@ -590,7 +645,7 @@ struct DemodEngine {
     long long ld_raw = ld_out;
     long long* n_raw = n_out;
     if (has_tsc) {
-      const long long ldr = need + (need & 1);
+      const long long ldr = (need + 15) & ~15LL;
       QPSK_TRY(d_raw.ensure((size_t)ldr * channels));
       raw = d_raw.p; ld_raw = ldr; n_raw = d_nraw.p;
     }
@@ -609,8 +664,16 @@ struct DemodEngine {
       QPSK_LAUNCH_CHECK();
     }
     if (has_tsc) {
-      tsc_strip_kernel<<<(channels + 3) / 4, 128, 0, s>>>(raw, ld_raw, n_raw, d_tsc.p, (int)tsc.size(), out, ld_out, n_out,
-                                                          channels);
+      const int T = (int)tsc.size();
+      const long long row_bytes = (ld_raw + 15) & ~15LL;
+      const size_t smem = (size_t)4 * (row_bytes + ((T + 15) & ~15));
+      if (smem <= 160 * 1024 && (ld_raw & 15) == 0) {
+        QPSK_CUDA_TRY(cudaFuncSetAttribute(tsc_strip_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tsc_strip_smem_kernel<<<(channels + 3) / 4, 128, smem, s>>>(raw, ld_raw, n_raw, d_tsc.p, T, out, ld_out, n_out, channels,
+                                                                   (int)row_bytes);
+      } else {
+        tsc_strip_kernel<<<(channels + 3) / 4, 128, 0, s>>>(raw, ld_raw, n_raw, d_tsc.p, T, out, ld_out, n_out, channels);
+      }
       QPSK_LAUNCH_CHECK();
     }
     return QPSK_OK;

@@ -159,7 +159,9 @@ __device__ __forceinline__ float2 quadrant_symbol(int q) {
 template <int MT>
 __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a) {
   constexpr int R = kModR;
-  __shared__ __align__(16) float2 sym[kModRegion];             // sym[k] = symbol D0 - HP + k
+  // symbol D0 - HP + k lives at sym[k + 2*(k/8)]: two pad slots after every 8 symbols make the per-thread and
+  // per-group stride 80 B (5 x 16 B, odd), so the 128-bit accesses of a quarter-warp fall in distinct banks
+  __shared__ __align__(16) float2 sym[kModRegion + kModRegion / 4];
   __shared__ int warp_tot[kModThreads / 32];
   __shared__ int halo_sum_s;
 
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
       for (int w = 0; w < warp; ++w) base += warp_tot[w];
       q0 = (int)a.tile_pre[(long long)f * a.tiles + t] - halo_sum_s + base;
     }
-    float4* dst = reinterpret_cast<float4*>(sym + 8 * tid);
+    float4* dst = reinterpret_cast<float4*>(sym + 10 * tid);
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       float2 v[2];
@@ -226,9 +228,9 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
   float2* ob = a.out + (long long)f * a.out_stride + (D0 * sps - a.delay);   // output of (symbol D0, phase 0)
   const long long i_tile = D0 * sps - a.delay;    // its index in the frame
   for (int g = gl; g < n_groups; g += G) {
-    const int s_loc = a.HP + g * R;               // smem index of the group's first symbol (multiple of 8)
+    const float2* gs = sym + 10 * ((a.HP >> 3) + g);   // the group's first symbol (padded layout)
     float2 w[R], acc[R];
-    const float4* s4 = reinterpret_cast<const float4*>(sym + s_loc);
+    const float4* s4 = reinterpret_cast<const float4*>(gs);
 #pragma unroll
     for (int r = 0; r < R; r += 2) {
       const float4 v = s4[r >> 1];
@@ -237,22 +239,23 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
       acc[r] = make_float2(0.f, 0.f);
       acc[r + 1] = make_float2(0.f, 0.f);
     }
-    // tap m multiplies sym[s0 + r - m]; slot of symbol offset j is (j mod R); one new (older) symbol per tap,
-    // fetched two at a time (sym[s_loc - m - 2], sym[s_loc - m - 1] are 16-byte aligned for even m)
+    // tap m multiplies sym[first + r - m]; slot of symbol offset j is (j mod R); one new (older) symbol per tap,
+    // fetched two at a time (16-byte aligned for even m)
 #pragma unroll
     for (int m = 0; m < MT; m += 2) {
-      const float4 nx = *reinterpret_cast<const float4*>(sym + s_loc - m - 2);
+      // symbols (first - m - 2, first - m - 1): block ceil((m+2)/8) back, slot (8 - (m+2)%8) % 8
+      const float4 nx = *reinterpret_cast<const float4*>(gs - 10 * ((m + 2 + 7) / 8) + ((8 - ((m + 2) & 7)) & 7));
       {
         const float2 tt = make_float2(tap[m], tap[m]);
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(r - m + 16 * R) % R], tt, acc[r]);
-        w[(R - 1 - m + 16 * R) % R] = make_float2(nx.z, nx.w);      // sym[s_loc - m - 1]
+        w[(R - 1 - m + 16 * R) % R] = make_float2(nx.z, nx.w);      // symbol first - m - 1
       }
       {
         const float2 tt = make_float2(tap[m + 1], tap[m + 1]);
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(r - m - 1 + 16 * R) % R], tt, acc[r]);
-        w[(R - 2 - m + 16 * R) % R] = make_float2(nx.x, nx.y);      // sym[s_loc - m - 2]
+        w[(R - 2 - m + 16 * R) % R] = make_float2(nx.x, nx.y);      // symbol first - m - 2
       }
     }
     const int off = g * R * sps + p;              // relative to ob, r = 0
