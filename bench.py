@@ -89,6 +89,44 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the FIR kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
+def copy_ceiling(torch, hin, hout, n_bytes):
+    """Pinned-copy rates of this box (GB/s): H2D alone, D2H alone, both at once.  The host-pointer path moves
+    8 B in + 8 B out per complex sample, so `duplex_each / 8 B` is the ceiling of the e2e number."""
+    hi = torch.from_numpy(hin.array).view(torch.uint8)[:n_bytes]
+    ho = torch.from_numpy(hout.array).view(torch.uint8)[:n_bytes]
+    di = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    do = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d, d2h):
+        best = 0.0
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if h2d:
+                with torch.cuda.stream(s1):
+                    di.copy_(hi, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    ho.copy_(do, non_blocking=True)
+            torch.cuda.synchronize()
+            best = max(best, n_bytes / (time.perf_counter() - t0) / 1e9)
+        return best
+
+    r = {"h2d_gbs": run(True, False), "d2h_gbs": run(False, True), "duplex_each_gbs": run(True, True)}
+    del di, do
+    return r
+
+
 def taps_for(orc_or_q, span, sps):
     h = orc_or_q.RRCFilter.generateCoefficents(span, ALPHA, sps * 1000, 1000)
     return orc_or_q.real_taps_to_iq(h)
@@ -137,7 +175,7 @@ def run_reference(args):
     t_all, vals = [], []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        b = cpu_baseline(19)
+        b = cpu_baseline(22)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             vals.append(b["value"]); t_all.append(dt)
@@ -147,7 +185,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_all) / len(t_all), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "fir_sweep taps{33,65,129,257} (bounded sample per step: cores x 2^19 samples per tap count)"},
+        "config": {"workload": "fir_sweep taps{33,65,129,257} (bounded sample per step: cores x 2^22 samples per tap count)"},
         "cpu_baseline": b,
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -255,17 +293,33 @@ def main():
         roofs.append({"taps": nt, "ms": t, "msamples_s": n / (t * 1e-3) / 1e6, "bound": bound,
                       "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "fma_tflops": tf, "fma_frac": tf / fma_peak,
                       "frac": (gbs / hbm_peak) if bound == "hbm" else (tf / fma_peak)})
+    tr = ncu_traffic()
+    if tr is not None and tr.get("log2_samples") == args.log2_samples:
+        for r in roofs:
+            t = tr["per_taps"].get(str(r["taps"]))
+            if t:
+                r["traffic"] = t["traffic"]
+                r["algorithmic_bytes"] = 16.0 * n
     dom = max(roofs, key=lambda r: r["ms"])
+    hbm_dom = max((r for r in roofs if r["bound"] == "hbm"), key=lambda r: r["ms"], default=None)
     roofline = {
         "kernel": "fir_tma_kernel<R=10,NT=256,real taps>", "taps": dom["taps"], "bound": dom["bound"],
         "achieved": dom["hbm_gbs"] if dom["bound"] == "hbm" else dom["fma_tflops"],
         "peak": hbm_peak if dom["bound"] == "hbm" else fma_peak,
         "unit": "GB/s" if dom["bound"] == "hbm" else "TFLOP/s",
-        "frac": dom["frac"], "traffic": None,
+        "frac": dom["frac"], "traffic": dom.get("traffic"),
+        "traffic_source": (tr["source"] if tr is not None and dom.get("traffic") else None),
+        "fma_peak_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
         "peak_source": (f"HBM {peak_src} (MEASURED_PEAKS.json)" if dom["bound"] == "hbm"
                         else "FP32 FMA peak measured in this run by qpsk_measure_fma_peak (FFMA2 micro-benchmark)"),
         "algorithmic": "16 B and 4*taps flop per complex sample (DESIGN.md)",
     }
+    # the same kernel where it is HBM-bound (33 taps), against the driver-measured copy bandwidth
+    roofline_hbm = None
+    if hbm_dom is not None:
+        roofline_hbm = {"kernel": roofline["kernel"], "taps": hbm_dom["taps"], "bound": "hbm", "achieved": hbm_dom["hbm_gbs"],
+                        "peak": hbm_peak, "unit": "GB/s", "frac": hbm_dom["hbm_frac"], "traffic": hbm_dom.get("traffic"),
+                        "peak_source": f"HBM {peak_src} (MEASURED_PEAKS.json)"}
 
     # ---- e2e: host-pointer C ABI with pinned buffers -------------------------------------------
     e2e = None
@@ -277,6 +331,7 @@ def main():
         torch.cuda.synchronize()
         for _, f in filters:
             f.reset()
+        pcie = copy_ceiling(torch, hin, hout, 1 << 30)
         k_e2e = max(1, min(args.steps, 3))
         for _, f in filters[:1]:
             f.Filter(hin.array[: 1 << 20], hout.array[: 1 << 20])
@@ -294,7 +349,10 @@ def main():
         dt = float(t_e.item())
         e2e = {"value": world * k_e2e * len(filters) * n / dt / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": len(filters) * 8 * n, "d2h_bytes_per_step": len(filters) * 8 * n,
-               "steps": k_e2e, "api": "qpsk_fir_filter (host pointers, pinned, chunked H2D/kernel/D2H pipeline)"}
+               "steps": k_e2e, "api": "qpsk_fir_filter (host pointers, pinned, chunked H2D/kernel/D2H pipeline)",
+               "bound": "pcie", "pinned_copy_gbs": pcie,
+               "ceiling": world * pcie["duplex_each_gbs"] * 1e9 / 8.0 / 1e6}
+        e2e["frac_of_ceiling"] = e2e["value"] / e2e["ceiling"]
         hin.free(); hout.free()
 
     chain = chain_fll = modulator = None
@@ -311,7 +369,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(20)
+        cpu = cpu_baseline(23)
 
     if rank == 0:
         total_samples = world * args.steps * len(filters) * n
@@ -323,7 +381,7 @@ def main():
                                    f"per GPU per tap count (BASELINE.json configs[1])",
                        "l2": "inputs 2 GiB + outputs 2 GiB per launch >> 126 MB L2; no flush needed",
                        "parallelism": f"{world} independent streams, one per GPU, no collective"},
-            "roofline": roofline, "roofline_by_taps": roofs, "fma_peak_tflops_measured": fma_peak,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_by_taps": roofs, "fma_peak_tflops_measured": fma_peak,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
         if chain is not None:

@@ -63,6 +63,12 @@ QPSK_API int qpsk_device_info(int* sm_count, int* cc_major, int* cc_minor, int64
 /* pinned host memory so host entry points overlap PCIe copies with kernels (optional) */
 QPSK_API int qpsk_host_alloc(void** p, int64_t bytes);
 QPSK_API int qpsk_host_free(void* p);
+/* page-lock / unlock caller-owned memory in place (e.g. a C# float[] held by a pinned GCHandle): a GC pin keeps
+ * the array from moving but leaves it pageable, and pageable copies are staged by the driver at a fraction of the
+ * PCIe rate.  Registering once per long-lived buffer gives the host entry points the same copy rate as
+ * qpsk_host_alloc memory. */
+QPSK_API int qpsk_host_register(void* p, int64_t bytes);
+QPSK_API int qpsk_host_unregister(void* p);
 /* launches of this library's kernels issued by the calling thread since the last reset */
 QPSK_API int64_t qpsk_launch_count(void);
 QPSK_API void qpsk_launch_count_reset(void);

@@ -58,6 +58,8 @@ def _signatures():
         "qpsk_device_info": (i, [i32p, i32p, i32p, i64p]),
         "qpsk_host_alloc": (i, [vpp, i64]),
         "qpsk_host_free": (i, [vp]),
+        "qpsk_host_register": (i, [vp, i64]),
+        "qpsk_host_unregister": (i, [vp]),
         "qpsk_launch_count": (i64, []),
         "qpsk_launch_count_reset": (None, []),
         "qpsk_rrc_taps": (i, [d, d, i, i, f64p, i, i32p]),

@@ -83,6 +83,35 @@ class PinnedBuffer:
             pass
 
 
+class RegisteredArray:
+    """Page-lock a caller-owned contiguous numpy array in place (qpsk_host_register) — the Python stand-in for a C#
+    float[] held by a pinned GCHandle.  Use as a context manager or call release()."""
+
+    def __init__(self, array: np.ndarray):
+        if not array.flags["C_CONTIGUOUS"]:
+            raise N.ArgumentException("array must be contiguous")
+        self.array = array
+        self._p = array.ctypes.data
+        check(lib().qpsk_host_register(self._p, array.nbytes))
+
+    def release(self):
+        if self._p:
+            lib().qpsk_host_unregister(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self.array
+
+    def __exit__(self, *exc):
+        self.release()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 def fill_uniform_dev(seed: int, stream_id: int, first: int, n: int, d_out: int, stream: int = 0):
     check(lib().qpsk_fill_uniform_dev(seed, stream_id, first, n, d_out, stream))
 

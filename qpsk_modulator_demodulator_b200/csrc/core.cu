@@ -220,6 +220,19 @@ int qpsk_host_free(void* p) {
   return QPSK_OK;
 }
 
+int qpsk_host_register(void* p, int64_t bytes) {
+  if (!p) return QPSK_ERR_NULL;
+  if (bytes <= 0) return QPSK_ERR_RANGE;
+  QPSK_TRY(ensure_device());
+  QPSK_CUDA_TRY(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable));
+  return QPSK_OK;
+}
+int qpsk_host_unregister(void* p) {
+  if (!p) return QPSK_OK;
+  QPSK_CUDA_TRY(cudaHostUnregister(p));
+  return QPSK_OK;
+}
+
 int64_t qpsk_launch_count(void) { return tl_launches; }
 void qpsk_launch_count_reset(void) { tl_launches = 0; }
 

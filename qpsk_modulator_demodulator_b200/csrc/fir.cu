@@ -613,12 +613,13 @@ using namespace qpsk;
 
 struct qpsk_fir {
   FirEngine eng;
-  // host-pointer pipeline: H2D / kernel / D2H on three streams over two device slots
+  // host-pointer pipeline: H2D / kernel / D2H on three streams over kSlots device slots
+  static constexpr int kSlots = 3;
   cudaStream_t s_in = nullptr, s_out = nullptr;
-  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
-  DevBuf<float2> d_in[2], d_out[2];
+  cudaEvent_t ev_h2d[kSlots] = {}, ev_k[kSlots] = {}, ev_d2h[kSlots] = {};
+  DevBuf<float2> d_in[kSlots], d_out[kSlots];
   ~qpsk_fir() {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
       if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
       if (ev_k[i]) cudaEventDestroy(ev_k[i]);
       if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
@@ -630,13 +631,16 @@ struct qpsk_fir {
 
 namespace {
 
-constexpr int64_t kChunk = 8LL << 20;  // complex samples per pipelined chunk (64 MiB each way)
+// complex samples per pipelined chunk (16 MiB each way): PCIe is the bound of the host-pointer path (8 B in + 8 B
+// out per sample, full duplex), so the only losses are the pipeline fill (one chunk H2D) and drain (one chunk D2H)
+constexpr int64_t kChunk = 2LL << 20;
+constexpr int kSlots = qpsk_fir::kSlots;
 
 int fir_pipeline_init(qpsk_fir* f) {
   if (f->s_in) return QPSK_OK;
   QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&f->s_in, cudaStreamNonBlocking));
   QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kSlots; ++i) {
     QPSK_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_h2d[i], cudaEventDisableTiming));
     QPSK_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_k[i], cudaEventDisableTiming));
     QPSK_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_d2h[i], cudaEventDisableTiming));
@@ -644,11 +648,14 @@ int fir_pipeline_init(qpsk_fir* f) {
   return QPSK_OK;
 }
 
-// one stream of L complex samples, host to host, chunked so copies overlap the kernels
+// one stream of L complex samples, host to host, chunked so copies overlap the kernels.  The streaming form
+// carries the delay line from chunk to chunk; the stateless form (fftFilter alignment, output i needs inputs
+// i .. i+N-1) stages N-1 look-ahead samples with every chunk and keeps the first `len` outputs.
 int fir_host_stream(qpsk_fir* f, const float* in, float* out, int64_t L, bool stateless) {
   FirEngine& e = f->eng;
   QPSK_TRY(fir_pipeline_init(f));
-  if (stateless || L <= kChunk) {
+  const int64_t look = stateless ? (e.n_taps - 1) : 0;
+  if (L <= kChunk) {
     QPSK_TRY(f->d_in[0].ensure((size_t)L));
     QPSK_TRY(f->d_out[0].ensure((size_t)L));
     QPSK_CUDA_TRY(cudaMemcpyAsync(f->d_in[0].p, in, (size_t)L * 8, cudaMemcpyHostToDevice, e.stream));
@@ -658,21 +665,23 @@ int fir_host_stream(qpsk_fir* f, const float* in, float* out, int64_t L, bool st
     QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
     return QPSK_OK;
   }
-  for (int b = 0; b < 2; ++b) {
-    QPSK_TRY(f->d_in[b].ensure((size_t)kChunk));
-    QPSK_TRY(f->d_out[b].ensure((size_t)kChunk));
+  for (int b = 0; b < kSlots; ++b) {
+    QPSK_TRY(f->d_in[b].ensure((size_t)(kChunk + look)));
+    QPSK_TRY(f->d_out[b].ensure((size_t)(kChunk + look)));
   }
   const int64_t chunks = (L + kChunk - 1) / kChunk;
   for (int64_t c = 0; c < chunks; ++c) {
-    const int b = (int)(c & 1);
+    const int b = (int)(c % kSlots);
     const int64_t off = c * kChunk;
     const int64_t len = (L - off < kChunk) ? (L - off) : kChunk;
-    if (c >= 2) QPSK_CUDA_TRY(cudaStreamWaitEvent(f->s_in, f->ev_k[b], 0));  // slot's previous kernel done
-    QPSK_CUDA_TRY(cudaMemcpyAsync(f->d_in[b].p, in + 2 * off, (size_t)len * 8, cudaMemcpyHostToDevice, f->s_in));
+    const int64_t in_len = (L - off < len + look) ? (L - off) : (len + look);
+    if (c >= kSlots) QPSK_CUDA_TRY(cudaStreamWaitEvent(f->s_in, f->ev_k[b], 0));  // slot's previous kernel done
+    QPSK_CUDA_TRY(cudaMemcpyAsync(f->d_in[b].p, in + 2 * off, (size_t)in_len * 8, cudaMemcpyHostToDevice, f->s_in));
     QPSK_CUDA_TRY(cudaEventRecord(f->ev_h2d[b], f->s_in));
     QPSK_CUDA_TRY(cudaStreamWaitEvent(e.stream, f->ev_h2d[b], 0));
-    if (c >= 2) QPSK_CUDA_TRY(cudaStreamWaitEvent(e.stream, f->ev_d2h[b], 0));  // slot's previous D2H done
-    QPSK_TRY(e.filter_dev(f->d_in[b].p, f->d_out[b].p, len, len, len, e.stream));
+    if (c >= kSlots) QPSK_CUDA_TRY(cudaStreamWaitEvent(e.stream, f->ev_d2h[b], 0));  // slot's previous D2H done
+    QPSK_TRY(stateless ? e.fft_filter_dev(f->d_in[b].p, f->d_out[b].p, in_len, in_len, in_len, e.stream)
+                       : e.filter_dev(f->d_in[b].p, f->d_out[b].p, len, len, len, e.stream));
     QPSK_CUDA_TRY(cudaEventRecord(f->ev_k[b], e.stream));
     QPSK_CUDA_TRY(cudaStreamWaitEvent(f->s_out, f->ev_k[b], 0));
     QPSK_CUDA_TRY(cudaMemcpyAsync(out + 2 * off, f->d_out[b].p, (size_t)len * 8, cudaMemcpyDeviceToHost, f->s_out));

@@ -178,3 +178,98 @@ def test_device_resident_large_stream_linearity(gpu, orc):
     want = orc.ComplexFIRFilter(taps).Filter(seg)[2 * 64:]
     got = y[lo: lo + 2 * 1000].cpu().numpy()
     assert np.abs(got - want).max() <= REL_TOL * np.abs(want).max()
+
+
+@pytest.mark.parametrize("kind", ["pageable", "registered", "pinned"])
+def test_host_pipeline_long_stream_equals_oracle(gpu, orc, kind):
+    """Host-pointer calls longer than one pipeline chunk (2^21 samples): the chunked H2D/kernel/D2H pipeline
+    must give the one-shot stream, for the streaming form (delay line carried across chunks) and for the
+    stateless fftFilter form (N-1 look-ahead samples staged with every chunk)."""
+    taps = _rrc_iq(orc, 10, 2)
+    L = 2 * (1 << 21) + 12345
+    x0 = _rand_iq(orc, L, seed=31)
+    holders = []
+    if kind == "pinned":
+        bi, bo = gpu.PinnedBuffer(2 * L), gpu.PinnedBuffer(2 * L)
+        holders += [bi, bo]
+        x, y = bi.array, bo.array
+        x[:] = x0
+    else:
+        x, y = x0.copy(), np.empty(2 * L, np.float32)
+        if kind == "registered":
+            holders += [gpu.RegisteredArray(x), gpu.RegisteredArray(y)]
+    f = gpu.ComplexFIRFilter(taps)
+    f.Filter(x, y)
+    want = orc.ComplexFIRFilter(taps).Filter(x0)
+    assert np.abs(y - want).max() <= REL_TOL * np.abs(want).max()
+    # chunk seams: bit-identical to a device-resident one-shot run of the same kernel
+    import torch
+    dx = torch.from_numpy(x0).cuda()
+    dy = torch.empty_like(dx)
+    gpu.ComplexFIRFilter(taps).filter_dev(dx.data_ptr(), dy.data_ptr(), 2 * L)   # one launch over the whole stream
+    torch.cuda.synchronize()
+    assert np.array_equal(dy.cpu().numpy().view(np.uint32), np.asarray(y).view(np.uint32))
+    want_s = orc.ComplexFIRFilter(taps).fftFilter(x0)
+    got_s = f.fftFilter(x)
+    assert got_s.shape == want_s.shape
+    assert np.abs(got_s - want_s).max() <= REL_TOL * np.abs(want_s).max()
+    seam = 2 * (1 << 21)
+    for k in (1, 2):
+        w = slice(k * seam - 200, k * seam + 200)
+        assert np.abs(got_s[w] - want_s[w]).max() <= REL_TOL * np.abs(want_s).max()
+    for h in holders:
+        (h.free if hasattr(h, "free") else h.release)()
+
+
+def test_full_size_sweep_properties(gpu, orc):
+    """BASELINE.json configs[1] at full size (2^28 cf32 samples, 2 GiB in + 2 GiB out): no oracle at this size, so
+    check size-independent properties of every tap count of the sweep — impulse response = the taps,
+    exact homogeneity under scaling by 2, and oracle agreement on windows at the start, at tile seams deep in
+    the stream and at the very end."""
+    import torch
+    n = 1 << 28
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    s = ts.cuda_stream
+    x = torch.empty(2 * n, dtype=torch.float32, device="cuda")
+    y = torch.empty(2 * n, dtype=torch.float32, device="cuda")
+    gpu.fill_uniform_dev(1, 0, 0, 2 * n, x.data_ptr(), s)
+    torch.cuda.synchronize()
+    # unit impulses far apart (complex 1 and complex j) -> the taps come out at those offsets
+    imp = [(12345, 0), (n // 2 + 1, 1), (n - 300, 0)]
+    saved = []
+    for pos, comp in imp:
+        saved.append(x[2 * pos - 2 * 600: 2 * pos + 2 * 600].clone())
+        x[2 * pos - 2 * 600: 2 * pos + 2 * 600] = 0
+        x[2 * pos + comp] = 1.0
+    for span, sps in [(16, 2), (16, 4), (16, 8), (16, 16)]:
+        taps = _rrc_iq(orc, span, sps)
+        nt = taps.size // 2
+        f = gpu.ComplexFIRFilter(taps)
+        f.filter_dev(x.data_ptr(), y.data_ptr(), 2 * n, stream=s)
+        torch.cuda.synchronize()
+        for pos, comp in imp:
+            m = min(nt, n - pos)
+            got = y[2 * pos: 2 * (pos + m)].cpu().numpy().reshape(-1, 2)
+            assert np.array_equal(got[:, comp], taps[0:2 * m:2]), (nt, pos)
+            assert not got[:, 1 - comp].any()
+        # windows against the oracle (with enough lead-in to fill the delay line)
+        for lo in (0, 2560 * 7 - 100, n // 3, n - 5000):
+            a = max(lo - nt, 0)
+            seg = x[2 * a: 2 * min(lo + 3000, n)].cpu().numpy()
+            want = orc.ComplexFIRFilter(taps).Filter(seg)[2 * (lo - a):]
+            got = y[2 * lo: 2 * lo + want.size].cpu().numpy()
+            if a > 0:
+                # the oracle started from a zero delay line at `a`; the first nt-1 outputs after `a` differ, lo is past them
+                assert lo - a >= nt - 1
+            assert np.abs(got - want).max() <= REL_TOL * max(np.abs(want).max(), 1e-30), (nt, lo)
+        # homogeneity on a strided sample of the output: filter(2x) == 2 filter(x) exactly
+        chk = y[:: 4099].clone()
+        x.mul_(2.0)
+        f2 = gpu.ComplexFIRFilter(taps)
+        f2.filter_dev(x.data_ptr(), y.data_ptr(), 2 * n, stream=s)
+        torch.cuda.synchronize()
+        assert torch.equal(y[:: 4099], 2.0 * chk)
+        x.mul_(0.5)
+    del x, y
+    torch.cuda.empty_cache()

@@ -6,7 +6,13 @@ import bench_chain
 Q.set_device(0)
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); s = ts.cuda_stream
 which = sys.argv[1]
-if which == 'chain':
+if which == 'sweep':
+    r = {}
+    for C in (1024, 2048, 4096, 8192, 16384):
+        for fll in (False, True):
+            o = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=2, warmup=2, use_fll=fll, channels_per_gpu=C)
+            r[f"{C}{'_fll' if fll else ''}"] = {"msamples_s": o["value"], "ms": o["ms_per_step"], "launches": o["gpu_launches"]}
+elif which == 'chain':
     r = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=2, warmup=2, use_fll=False)
 elif which == 'fll':
     r = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=2, warmup=2, use_fll=True)
