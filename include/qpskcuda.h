@@ -52,6 +52,7 @@ typedef struct qpsk_costas qpsk_costas;
 typedef struct qpsk_mod qpsk_mod;
 typedef struct qpsk_demod qpsk_demod;
 typedef struct qpsk_chan qpsk_chan;
+typedef struct qpsk_chain qpsk_chain;
 
 /* ---- library / device -------------------------------------------------------------------- */
 QPSK_API int qpsk_version(void);                       /* 10000*major + 100*minor + patch         */
@@ -162,6 +163,10 @@ QPSK_API int qpsk_mod_taps(const qpsk_mod* m, double* out, int cap, int* n);    
 QPSK_API int qpsk_mod_modulate_bits(qpsk_mod* m, const char* bits, int64_t n_bits, int pulse_shaping,
                                     float* iq_out, int64_t cap_floats, int64_t* n_floats);
 /* ModulateBytes :54-72 (ModulateTextUtf8 :74-89 = this over UTF-8 bytes) */
+/* §8f-4: the same call with the bit string packed MSB-first (what BitPacker.BytesToBitString,
+ * MS/Models/HelperFunctions.cs:14-29, expands to one char per bit); identical samples */
+QPSK_API int qpsk_mod_modulate_packed(qpsk_mod* m, const uint8_t* packed_bits, int64_t n_bits, int pulse_shaping,
+                                      float* iq_out, int64_t cap_floats, int64_t* n_floats);
 QPSK_API int qpsk_mod_modulate_bytes(qpsk_mod* m, const uint8_t* payload, int64_t n_payload,
                                      const uint8_t* start_marker, int64_t n_start,
                                      const uint8_t* end_marker, int64_t n_end, int pulse_shaping,
@@ -194,6 +199,11 @@ QPSK_API int qpsk_demod_set_fir_mode(qpsk_demod* d, int mode);
 QPSK_API int qpsk_demod_bits(qpsk_demod* d, const float* iq_in, int64_t n_floats, char* bits_out,
                              int64_t cap, int64_t* n_bits);
 /* DeModulateBytes :169-259 (DeModulateTextUtf8 :262-277 = this + UTF-8 decode) */
+/* §8f-4: DeModulate with the bits packed MSB-first, 8 per byte (BitPacker.BitsToBytes(bits, 0), HelperFunctions.cs:32-57,
+ * except that a trailing incomplete byte is kept, zero-padded; n_bits[c] is the exact bit count).  packed_out is
+ * [channels][cap_bytes].  One eighth of the device-to-host traffic of the char form. */
+QPSK_API int qpsk_demod_bits_packed(qpsk_demod* d, const float* iq_in, int64_t n_floats, uint8_t* packed_out,
+                                    int64_t cap_bytes, int64_t* n_bits);
 QPSK_API int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_floats,
                               const uint8_t* start_marker, int64_t n_start,
                               const uint8_t* end_marker, int64_t n_end,
@@ -222,6 +232,42 @@ QPSK_API int qpsk_demod_loop_state(qpsk_demod* d, double* costas_theta, double* 
                                    double* mm_integral, float* fll_phase, float* fll_freq);
 /* _inFrame (:62) per channel */
 QPSK_API int qpsk_demod_in_frame(qpsk_demod* d, int* in_frame);
+
+/* ---- full receive chain: TB/Simulated/testFullDemodChain.cs:14-116, repaired ------- */
+/* FLL -> RRC matched filter -> Mueller-Muller -> Costas wired as that test does by hand (:22-45, :73-110),
+ * every block parameter explicit (upstream the test no longer constructs: SURVEY §4).  The three outputs are
+ * the payloads of the ZMQ topics the test publishes — raw little-endian cf32, byte-identical to these float
+ * buffers (:88-108): "baseband" = FLL output (one per input sample), "baseband_PostSymbolSync" = MM symbols,
+ * "baseband_PostSymbolSyncPostCostas" = Costas output.  State persists across calls (any chunking gives the
+ * same three streams). */
+typedef struct qpsk_chain_params {
+  int sample_rate, symbol_rate;      /* matched filter = RRC(rrc_span, rrc_alpha, sample_rate, symbol_rate) :22 */
+  double rrc_span, rrc_alpha;
+  float fll_sps, fll_rolloff;        /* FLLBandEdgeFilter(sps, rolloff, size, bandwidth) :23                    */
+  int fll_size;
+  float fll_bw;
+  double mm_sps, mm_kp, mm_ki;       /* MuellerMuller(sps, Kp, Ki) :35-39                                       */
+  double costas_sample_rate, costas_bw_hz, costas_damping; /* CostasLoopQpsk(SymbolRate, SymbolRate/10) :45    */
+} qpsk_chain_params;
+/* the literal values of testFullDemodChain.cs:18-45 (fs 10 MHz, Rs fs/30, span 11, alpha .9, FLL(30,.9,10,.1)) */
+QPSK_API int qpsk_chain_default_params(qpsk_chain_params* p);
+QPSK_API int qpsk_chain_create(const qpsk_chain_params* p, int channels, qpsk_chain** out);
+QPSK_API int qpsk_chain_destroy(qpsk_chain* c);
+/* matched-filter arithmetic: QPSK_FIR_FAST (default) or QPSK_FIR_EXACT (the reference's summation order) */
+QPSK_API int qpsk_chain_set_fir_mode(qpsk_chain* c, int mode);
+/* floats one call of n_floats input can emit per channel on the two symbol outputs */
+QPSK_API int qpsk_chain_symbols_bound(const qpsk_chain* c, int64_t n_floats, int64_t* cap_floats);
+/* host pointers: iq_in / baseband_out [channels][n_floats]; sync_out / costas_out [channels][sym_cap_floats];
+ * n_sym[channels] complex symbols produced */
+QPSK_API int qpsk_chain_process(qpsk_chain* c, const float* iq_in, int64_t n_floats, float* baseband_out, float* sync_out,
+                                float* costas_out, int64_t sym_cap_floats, int* n_sym);
+/* device pointers, strides in floats (even), d_n_sym int[channels] in device memory */
+QPSK_API int qpsk_chain_process_dev(qpsk_chain* c, const float* d_in, int64_t n_floats, int64_t in_stride, float* d_baseband,
+                                    int64_t bb_stride, float* d_sync, int64_t sync_stride, float* d_costas,
+                                    int64_t costas_stride, int* d_n_sym, void* stream);
+/* per-channel loop state (any pointer may be NULL) */
+QPSK_API int qpsk_chain_loop_state(qpsk_chain* c, float* fll_phase, float* fll_freq, double* mm_mu, double* costas_theta,
+                                   double* costas_freq);
 
 /* ---- synthetic channel: NCO pair + AWGN + static multipath ------------------- */
 /* NCO: TB/Simulated/LocalOscilator.cs:5-194; noise: TB/HelperModels.cs:17-45; System.Random is
@@ -255,6 +301,9 @@ QPSK_API int qpsk_unpack_bits_dev(const uint8_t* d_bytes, int64_t n_bytes, int64
                                   uint8_t* d_bits, int64_t bits_stride, void* stream);
 
 /* ---- K6  per-channel BER counters ---------------------------------------------------------- */
+/* bytes 0/1 -> MSB-first packed bytes per channel (n_bits[c] bits each, at most max_bits; trailing partial byte zero-padded) */
+QPSK_API int qpsk_pack_bits_dev(const uint8_t* d_bits, int64_t bits_stride, const int64_t* d_n_bits, int64_t max_bits,
+                                int channels, uint8_t* d_packed, int64_t packed_stride, void* stream);
 /* bits as bytes 0/1.  errors[c] = Hamming distance over min(n_rx[c], n_ref) bits + max(0, n_ref-n_rx[c])
  * (bits that never arrived count as errors, extra trailing bits are ignored);
  * counters[c] = {errors, n_ref}.  ref_stride 0 = one reference for all channels. */

@@ -47,6 +47,15 @@ class ChanParams(C.Structure):
     ]
 
 
+class ChainParams(C.Structure):
+    _fields_ = [
+        ("sample_rate", C.c_int), ("symbol_rate", C.c_int), ("rrc_span", C.c_double), ("rrc_alpha", C.c_double),
+        ("fll_sps", C.c_float), ("fll_rolloff", C.c_float), ("fll_size", C.c_int), ("fll_bw", C.c_float),
+        ("mm_sps", C.c_double), ("mm_kp", C.c_double), ("mm_ki", C.c_double),
+        ("costas_sample_rate", C.c_double), ("costas_bw_hz", C.c_double), ("costas_damping", C.c_double),
+    ]
+
+
 def _signatures():
     i, i64, u64, d, f, vp, cp = C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_float, C.c_void_p, C.c_char_p
     return {
@@ -100,6 +109,7 @@ def _signatures():
         "qpsk_mod_destroy": (i, [vp]),
         "qpsk_mod_taps": (i, [vp, f64p, i, i32p]),
         "qpsk_mod_modulate_bits": (i, [vp, cp, i64, i, vp, i64, i64p]),
+        "qpsk_mod_modulate_packed": (i, [vp, vp, i64, i, vp, i64, i64p]),
         "qpsk_mod_modulate_bytes": (i, [vp, vp, i64, vp, i64, vp, i64, i, vp, i64, i64p]),
         "qpsk_mod_modulate_frames_dev": (i, [vp, vp, i64, i, vp, i64, vp, i64, vp, i64, i64p, vp]),
         "qpsk_demod_create": (i, [i, i, f, i, d, d, d, i, cp, i, i64, vpp]),
@@ -107,6 +117,7 @@ def _signatures():
         "qpsk_demod_destroy": (i, [vp]),
         "qpsk_demod_set_fir_mode": (i, [vp, i]),
         "qpsk_demod_bits": (i, [vp, vp, i64, vp, i64, vp]),
+        "qpsk_demod_bits_packed": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bytes": (i, [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
         "qpsk_demod_constellation": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bits_dev": (i, [vp, vp, i64, i64, vp, i64, vp, vp]),
@@ -115,6 +126,14 @@ def _signatures():
         "qpsk_demod_constellation_dev": (i, [vp, vp, i64, i64, vp, i64, vp, vp]),
         "qpsk_demod_loop_state": (i, [vp, f64p, f64p, f64p, f64p, f32p, f32p]),
         "qpsk_demod_in_frame": (i, [vp, i32p]),
+        "qpsk_chain_default_params": (i, [C.POINTER(ChainParams)]),
+        "qpsk_chain_create": (i, [C.POINTER(ChainParams), i, vpp]),
+        "qpsk_chain_destroy": (i, [vp]),
+        "qpsk_chain_set_fir_mode": (i, [vp, i]),
+        "qpsk_chain_symbols_bound": (i, [vp, i64, i64p]),
+        "qpsk_chain_process": (i, [vp, vp, i64, vp, vp, vp, i64, i32p]),
+        "qpsk_chain_process_dev": (i, [vp, vp, i64, i64, vp, i64, vp, i64, vp, i64, vp, vp]),
+        "qpsk_chain_loop_state": (i, [vp, f32p, f32p, f64p, f64p, f64p]),
         "qpsk_unpack_bits_dev": (i, [vp, i64, i64, i, vp, i64, vp]),
         "qpsk_chan_create": (i, [C.POINTER(ChanParams), i, i, vpp]),
         "qpsk_chan_destroy": (i, [vp]),
@@ -122,6 +141,7 @@ def _signatures():
         "qpsk_chan_apply": (i, [vp, vp, i64, vp]),
         "qpsk_fill_uniform_dev": (i, [u64, u64, i64, i64, vp, vp]),
         "qpsk_fill_bytes_dev": (i, [u64, i, i, i64, vp, vp]),
+        "qpsk_pack_bits_dev": (i, [vp, i64, vp, i64, i, vp, i64, vp]),
         "qpsk_ber_count_dev": (i, [vp, i64, vp, vp, i64, i64, i, vp, vp]),
         "qpsk_measure_fma_peak": (i, [f64p]),
     }

@@ -193,6 +193,30 @@ __global__ void unpack_bits_kernel(const uint8_t* __restrict__ bytes, long long 
   }
 }
 
+// packed[c][k] = bits 8k..8k+7 of channel c, MSB first (BitPacker.BitsToBytes with bitOffset 0,
+// HelperFunctions.cs:32-57), except that a trailing incomplete byte is kept, zero-padded on the right — the bit
+// count travels separately.  One thread per output byte, one 8-byte load when the row is 8-byte aligned.
+__global__ void pack_bits_kernel(const uint8_t* __restrict__ bits, long long bits_stride, const long long* __restrict__ n_bits,
+                                 int C, uint8_t* __restrict__ packed, long long packed_stride, long long max_bytes) {
+  const long long total = (long long)C * max_bytes;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long c = idx / max_bytes, k = idx - c * max_bytes;
+    const long long nb = n_bits[c];
+    if (8 * k >= nb) continue;
+    const uint8_t* b = bits + c * bits_stride + 8 * k;
+    unsigned v = 0;
+    if (8 * k + 8 <= nb && ((reinterpret_cast<uintptr_t>(b) & 7) == 0)) {
+      const unsigned long long w = *reinterpret_cast<const unsigned long long*>(b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v |= (unsigned)((w >> (8 * j)) & 1ull) << (7 - j);
+    } else {
+      const int m = (int)((nb - 8 * k) < 8 ? (nb - 8 * k) : 8);
+      for (int j = 0; j < m; ++j) v |= (unsigned)(b[j] & 1u) << (7 - j);
+    }
+    packed[c * packed_stride + k] = (uint8_t)v;
+  }
+}
+
 // one warp per channel
 __global__ void __launch_bounds__(128)
     ber_kernel(const uint8_t* __restrict__ rx, long long rx_stride, const long long* __restrict__ n_rx,
@@ -346,6 +370,24 @@ int qpsk_unpack_bits_dev(const uint8_t* d_bytes, int64_t n_bytes, int64_t bytes_
   const long long cap = 16LL * device_sm_count();
   if (blocks > cap) blocks = cap;
   unpack_bits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_bytes, n_bytes, bytes_stride, channels, d_bits, bits_stride);
+  QPSK_LAUNCH_CHECK();
+  return QPSK_OK;
+}
+
+int qpsk_pack_bits_dev(const uint8_t* d_bits, int64_t bits_stride, const int64_t* d_n_bits, int64_t max_bits, int channels,
+                       uint8_t* d_packed, int64_t packed_stride, void* stream) {
+  if (channels < 0 || max_bits < 0) return QPSK_ERR_RANGE;
+  if (channels == 0 || max_bits == 0) return QPSK_OK;
+  if (!d_bits || !d_n_bits || !d_packed) return QPSK_ERR_NULL;
+  const long long max_bytes = (max_bits + 7) / 8;
+  if (channels > 1 && packed_stride < max_bytes) return QPSK_ERR_ARG;
+  QPSK_TRY(ensure_device());
+  const long long total = (long long)channels * max_bytes;
+  long long blocks = (total + 255) / 256;
+  const long long cap = 16LL * device_sm_count();
+  if (blocks > cap) blocks = cap;
+  pack_bits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_bits, bits_stride, (const long long*)d_n_bits, channels,
+                                                                 d_packed, packed_stride, max_bytes);
   QPSK_LAUNCH_CHECK();
   return QPSK_OK;
 }

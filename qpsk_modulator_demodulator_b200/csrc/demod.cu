@@ -822,6 +822,41 @@ int qpsk_demod_bits(qpsk_demod* d, const float* iq_in, int64_t n_floats, char* b
   return st;
 }
 
+int qpsk_demod_bits_packed(qpsk_demod* d, const float* iq_in, int64_t n_floats, uint8_t* packed_out, int64_t cap_bytes,
+                           int64_t* n_bits) {
+  QPSK_TRY(demod_check_in(d, iq_in, n_floats));
+  if (!n_bits) return QPSK_ERR_NULL;
+  if (cap_bytes < 0) return QPSK_ERR_RANGE;
+  DemodEngine& e = d->eng;
+  for (int c = 0; c < e.channels; ++c) n_bits[c] = 0;
+  if (n_floats == 0) return QPSK_OK;                         // :350-351
+  QPSK_TRY(ensure_device());
+  cudaStream_t s = e.stream;
+  const int64_t L = n_floats >> 1, ld = L + (L & 1);
+  QPSK_TRY(demod_stage_in(e, iq_in, L, s));
+  const long long ldb = (e.bits_bound(L) + 2 + 7) & ~7LL;    // 8-byte aligned rows for the pack kernel's wide loads
+  QPSK_TRY(e.d_bits.ensure((size_t)ldb * e.channels));
+  QPSK_TRY(e.bits_dev(e.h_in.p, L, ld, e.d_bits.p, ldb, e.d_nbits.p, s));
+  const long long ldp = ldb / 8;
+  QPSK_TRY(e.d_pk.ensure((size_t)ldp * e.channels));
+  QPSK_TRY(qpsk_pack_bits_dev(e.d_bits.p, ldb, (const int64_t*)e.d_nbits.p, ldb, e.channels, e.d_pk.p, ldp, s));
+  std::vector<long long> nb((size_t)e.channels);
+  QPSK_CUDA_TRY(cudaMemcpyAsync(nb.data(), e.d_nbits.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  int st = QPSK_OK;
+  for (int c = 0; c < e.channels; ++c) {
+    n_bits[c] = nb[(size_t)c];
+    const long long bytes = (nb[(size_t)c] + 7) / 8;
+    if (bytes > cap_bytes) { st = QPSK_ERR_CAPACITY; continue; }
+    if (bytes == 0) continue;
+    if (!packed_out) return QPSK_ERR_NULL;
+    QPSK_CUDA_TRY(cudaMemcpyAsync(packed_out + (size_t)c * cap_bytes, e.d_pk.p + (size_t)c * ldp, (size_t)bytes,
+                                  cudaMemcpyDeviceToHost, s));
+  }
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  return st;
+}
+
 int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_floats, const uint8_t* start_marker, int64_t n_start,
                      const uint8_t* end_marker, int64_t n_end, uint8_t* payload_out, int64_t cap, int64_t* n_bytes) {
   if (!d || !n_bytes) return QPSK_ERR_NULL;

@@ -428,6 +428,49 @@ struct qpsk_mod {
   ModEngine eng;
 };
 
+// Modulate(string bits, bool pulseShaping) :104-167 for a bit source `val(k)` in {0, 1, 2 = any other character}
+template <typename BitAt>
+static int mod_bits_common(qpsk_mod* m, BitAt data_bit, int64_t n_bits, int pulse_shaping, float* iq_out, int64_t cap_floats,
+                           int64_t* n_floats) {
+  ModEngine& e = m->eng;
+  int64_t nd = 0;
+  const bool pulse = pulse_shaping != 0;
+  const int64_t total = e.frame_complex(n_bits, pulse, &nd);
+  *n_floats = 2 * total;
+  if (nd == 0) return QPSK_OK;                              // :113
+  if (e.sps <= 0) return QPSK_ERR_RANGE;                    // :116-117
+  if (!iq_out) return QPSK_OK;                              // size query
+  if (cap_floats < 2 * total) return QPSK_ERR_CAPACITY;
+  QPSK_TRY(ensure_device());
+  // one code per dibit, with the reference's `c - '0'` semantics for any character
+  std::vector<uint8_t> codes((size_t)nd);
+  const int64_t nt = e.has_tsc ? (int64_t)e.tsc.size() : 0;
+  auto val = [&](int64_t k) -> int {
+    if (k < nt) {
+      const char c = e.tsc[(size_t)k];
+      return c == '0' ? 0 : (c == '1' ? 1 : 2);
+    }
+    return data_bit(k - nt);
+  };
+  for (int64_t d = 0; d < nd; ++d) {
+    const int b0 = val(2 * d), b1 = val(2 * d + 1);
+    int code;
+    if (e.diff) code = (b0 == 0 && b1 == 0) ? 0 : (b0 == 0 && b1 == 1) ? 1 : (b0 == 1 && b1 == 1) ? 2 : 3;
+    else code = ((b0 != 0) << 1) | (b1 != 0);
+    codes[(size_t)d] = (uint8_t)code;
+  }
+  QPSK_TRY(e.d_src.ensure((size_t)nd));
+  QPSK_TRY(e.d_out.ensure((size_t)total));
+  cudaStream_t s = e.stream;
+  QPSK_CUDA_TRY(cudaMemcpyAsync(e.d_src.p, codes.data(), (size_t)nd, cudaMemcpyHostToDevice, s));
+  ModArgs a{};
+  a.mode = 1; a.payload = e.d_src.p; a.meta = nullptr; a.n_payload = 0; a.n_tsc = a.n_start = a.n_end = 0;
+  QPSK_TRY(e.run(a, pulse, nd, 1, e.d_out.p, total, s));
+  QPSK_CUDA_TRY(cudaMemcpyAsync(iq_out, e.d_out.p, (size_t)total * 8, cudaMemcpyDeviceToHost, s));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  return QPSK_OK;
+}
+
 extern "C" {
 
 int qpsk_mod_create(int sample_rate, int symbol_rate, double rrc_alpha, int rrc_span, int differential,
@@ -464,40 +507,21 @@ int qpsk_mod_modulate_bits(qpsk_mod* m, const char* bits, int64_t n_bits, int pu
   if (!m || !n_floats) return QPSK_ERR_NULL;
   if (!bits && n_bits > 0) return QPSK_ERR_NULL;            // :106
   if (n_bits < 0) return QPSK_ERR_RANGE;
-  ModEngine& e = m->eng;
-  int64_t nd = 0;
-  const bool pulse = pulse_shaping != 0;
-  const int64_t total = e.frame_complex(n_bits, pulse, &nd);
-  *n_floats = 2 * total;
-  if (nd == 0) return QPSK_OK;                              // :113
-  if (e.sps <= 0) return QPSK_ERR_RANGE;                    // :116-117
-  if (!iq_out) return QPSK_OK;                              // size query
-  if (cap_floats < 2 * total) return QPSK_ERR_CAPACITY;
-  QPSK_TRY(ensure_device());
-  // chars -> one code per dibit, with the reference's `c - '0'` semantics for any character
-  std::vector<uint8_t> codes((size_t)nd);
-  const int64_t nt = e.has_tsc ? (int64_t)e.tsc.size() : 0;
-  auto val = [&](int64_t k) -> int {
-    const char c = (k < nt) ? e.tsc[(size_t)k] : bits[k - nt];
+  auto at = [&](int64_t k) -> int {
+    const char c = bits[k];
     return c == '0' ? 0 : (c == '1' ? 1 : 2);
   };
-  for (int64_t d = 0; d < nd; ++d) {
-    const int b0 = val(2 * d), b1 = val(2 * d + 1);
-    int code;
-    if (e.diff) code = (b0 == 0 && b1 == 0) ? 0 : (b0 == 0 && b1 == 1) ? 1 : (b0 == 1 && b1 == 1) ? 2 : 3;
-    else code = ((b0 != 0) << 1) | (b1 != 0);
-    codes[(size_t)d] = (uint8_t)code;
-  }
-  QPSK_TRY(e.d_src.ensure((size_t)nd));
-  QPSK_TRY(e.d_out.ensure((size_t)total));
-  cudaStream_t s = e.stream;
-  QPSK_CUDA_TRY(cudaMemcpyAsync(e.d_src.p, codes.data(), (size_t)nd, cudaMemcpyHostToDevice, s));
-  ModArgs a{};
-  a.mode = 1; a.payload = e.d_src.p; a.meta = nullptr; a.n_payload = 0; a.n_tsc = a.n_start = a.n_end = 0;
-  QPSK_TRY(e.run(a, pulse, nd, 1, e.d_out.p, total, s));
-  QPSK_CUDA_TRY(cudaMemcpyAsync(iq_out, e.d_out.p, (size_t)total * 8, cudaMemcpyDeviceToHost, s));
-  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
-  return QPSK_OK;
+  return mod_bits_common(m, at, n_bits, pulse_shaping, iq_out, cap_floats, n_floats);
+}
+
+// the same call with the bit string packed MSB-first, 8 bits per byte (what BitPacker.BytesToBitString :14-29 expands)
+int qpsk_mod_modulate_packed(qpsk_mod* m, const uint8_t* packed_bits, int64_t n_bits, int pulse_shaping, float* iq_out,
+                             int64_t cap_floats, int64_t* n_floats) {
+  if (!m || !n_floats) return QPSK_ERR_NULL;
+  if (!packed_bits && n_bits > 0) return QPSK_ERR_NULL;
+  if (n_bits < 0) return QPSK_ERR_RANGE;
+  auto at = [&](int64_t k) -> int { return (packed_bits[k >> 3] >> (7 - (int)(k & 7))) & 1; };
+  return mod_bits_common(m, at, n_bits, pulse_shaping, iq_out, cap_floats, n_floats);
 }
 
 static int mod_frames_common(qpsk_mod* m, const uint8_t* d_payloads, int64_t n_payload, int frames,

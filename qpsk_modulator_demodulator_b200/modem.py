@@ -43,6 +43,22 @@ class QPSKModulator(_Handle):
             check(lib().qpsk_mod_modulate_bits(self._h, b, len(b), int(pulseShaping), _ptr(out), out.size, C.byref(n)))
         return out
 
+    def ModulatePacked(self, packedBits: bytes, nBits: int = None, pulseShaping: bool = True) -> np.ndarray:
+        """Modulate() with the bit string packed MSB-first, 8 bits per byte: identical samples to
+        Modulate(BitPacker.BytesToBitString(packedBits)[:nBits])."""
+        if packedBits is None:
+            raise ArgumentNullException("packedBits")
+        p = _bytes_arr(packedBits)
+        nb = 8 * p.size if nBits is None else int(nBits)
+        if nb > 8 * p.size:
+            raise N.ArgumentException("nBits exceeds the packed buffer")
+        n = C.c_int64(0)
+        check(lib().qpsk_mod_modulate_packed(self._h, _ptr(p), nb, int(pulseShaping), None, 0, C.byref(n)))
+        out = np.empty(n.value, np.float32)
+        if n.value:
+            check(lib().qpsk_mod_modulate_packed(self._h, _ptr(p), nb, int(pulseShaping), _ptr(out), out.size, C.byref(n)))
+        return out
+
     def ModulateBytes(self, payload: bytes, startMarker: bytes, endMarker: bytes, pulseShaping: bool = True) -> np.ndarray:
         p, s, e = _bytes_arr(payload), _bytes_arr(startMarker), _bytes_arr(endMarker)
         n = C.c_int64(0)
@@ -113,6 +129,17 @@ class QPSKDeModulator(_Handle):
         nb = np.zeros(self.channels, np.int64)
         check(lib().qpsk_demod_bits(self._h, _ptr(x), n, _ptr(buf), cap, _ptr(nb)))
         outs = [buf[c, : nb[c]].tobytes().decode("ascii") for c in range(self.channels)]
+        return outs[0] if self.channels == 1 else outs
+
+    def DeModulatePacked(self, SamplesIQ):
+        """DeModulate() with the bits packed MSB-first (SURVEY §8f-4) -> (bytes, n_bits) (lists for batch handles);
+        a trailing incomplete byte is zero-padded on the right."""
+        x, n = self._in(SamplesIQ)
+        cap = max(n // 8 + 8, 8)
+        buf = np.zeros((self.channels, cap), np.uint8)
+        nb = np.zeros(self.channels, np.int64)
+        check(lib().qpsk_demod_bits_packed(self._h, _ptr(x), n, _ptr(buf), cap, _ptr(nb)))
+        outs = [(buf[c, : (nb[c] + 7) // 8].tobytes(), int(nb[c])) for c in range(self.channels)]
         return outs[0] if self.channels == 1 else outs
 
     def DeModulateBytes(self, samplesIQ, startMarker: bytes, endMarker: bytes, cap: int = 0):
@@ -206,6 +233,91 @@ def unpack_bits_dev(d_bytes: int, n_bytes: int, bytes_stride: int, channels: int
     check(lib().qpsk_unpack_bits_dev(d_bytes, n_bytes, bytes_stride, channels, d_bits, bits_stride, stream))
 
 
+def pack_bits_dev(d_bits: int, bits_stride: int, d_n_bits: int, max_bits: int, channels: int, d_packed: int, packed_stride: int,
+                  stream: int = 0):
+    check(lib().qpsk_pack_bits_dev(d_bits, bits_stride, d_n_bits, max_bits, channels, d_packed, packed_stride, stream))
+
+
 def ber_count_dev(d_rx_bits: int, rx_stride: int, d_n_rx: int, d_ref_bits: int, ref_stride: int, n_ref: int, channels: int,
                   d_counters: int, stream: int = 0):
     check(lib().qpsk_ber_count_dev(d_rx_bits, rx_stride, d_n_rx, d_ref_bits, ref_stride, n_ref, channels, d_counters, stream))
+
+
+# ---- §8f-2: the full receive chain of TB/Simulated/testFullDemodChain.cs, repaired -----------------
+class FullDemodChain(_Handle):
+    """FLL -> RRC matched filter -> Mueller-Muller -> Costas as testFullDemodChain.cs:22-110 wires the blocks by hand,
+    on the GPU over `channels` independent streams.  Defaults are the literal values of that test (:18-45); every
+    block parameter can be overridden by keyword (the field names of qpsk_chain_params)."""
+    _destroy = "qpsk_chain_destroy"
+    TOPICS = ("baseband", "baseband_PostSymbolSync", "baseband_PostSymbolSyncPostCostas")   # :95, :103, :110
+
+    def __init__(self, channels: int = 1, **overrides):
+        super().__init__()
+        self.channels = channels
+        p = N.ChainParams()
+        check(lib().qpsk_chain_default_params(C.byref(p)))
+        names = {f[0] for f in N.ChainParams._fields_}
+        for k, v in overrides.items():
+            if k not in names:
+                raise TypeError(f"unknown chain parameter {k!r}")
+            setattr(p, k, v)
+        self.params = p
+        check(lib().qpsk_chain_create(C.byref(p), channels, C.byref(self._h)))
+
+    def set_fir_mode(self, mode: int):
+        check(lib().qpsk_chain_set_fir_mode(self._h, mode))
+
+    def symbols_bound(self, n_floats: int) -> int:
+        b = C.c_int64(0)
+        check(lib().qpsk_chain_symbols_bound(self._h, n_floats, C.byref(b)))
+        return b.value
+
+    def Process(self, samplesIQ):
+        """-> (baseband, post_symbol_sync, post_costas): float32 interleaved IQ arrays (lists of per-channel arrays for
+        batch handles) — the payloads of the three ZMQ topics of one loop pass."""
+        if samplesIQ is None:
+            raise ArgumentNullException("samplesIQ")
+        x = _f32(samplesIQ)
+        n = x.shape[-1] if x.ndim == 2 else x.size
+        cap = max(self.symbols_bound(n), 2) if n % 2 == 0 else 2
+        bb = np.zeros((self.channels, n), np.float32)
+        sy = np.zeros((self.channels, cap), np.float32)
+        co = np.zeros((self.channels, cap), np.float32)
+        ns = np.zeros(self.channels, np.int32)
+        check(lib().qpsk_chain_process(self._h, _ptr(x), n, _ptr(bb), _ptr(sy), _ptr(co), cap, ns.ctypes.data_as(N.i32p)))
+        if self.channels == 1:
+            return bb[0], sy[0, : 2 * ns[0]].copy(), co[0, : 2 * ns[0]].copy()
+        return ([bb[c] for c in range(self.channels)], [sy[c, : 2 * ns[c]].copy() for c in range(self.channels)],
+                [co[c, : 2 * ns[c]].copy() for c in range(self.channels)])
+
+    def zmq_frames(self, samplesIQ, frame_samples: int = 4096):
+        """The multipart messages testFullDemodChain.cs:88-110 publishes for this input, in order: per
+        `frame_samples` block one ("baseband", bytes) message and, when the block produced symbols, the two symbol
+        topics.  Payloads are raw little-endian cf32 (Buffer.BlockCopy of the float arrays), what the GNU Radio
+        ZMQ SUB sources of the viewers read.  Single-channel handles only."""
+        if self.channels != 1:
+            raise N.ArgumentException("zmq_frames is per stream; use Process on batch handles")
+        x = _f32(samplesIQ)
+        out = []
+        step = 2 * frame_samples
+        for a in range(0, x.size, step):
+            bb, sy, co = self.Process(x[a:a + step])
+            out.append((self.TOPICS[0].encode(), bb.astype("<f4").tobytes()))
+            if sy.size:                                              # `if (decided.Length > 0)` :97
+                out.append((self.TOPICS[1].encode(), sy.astype("<f4").tobytes()))
+                out.append((self.TOPICS[2].encode(), co.astype("<f4").tobytes()))
+        return out
+
+    def process_dev(self, d_in: int, n_floats: int, in_stride: int, d_baseband: int, bb_stride: int, d_sync: int,
+                    sync_stride: int, d_costas: int, costas_stride: int, d_n_sym: int, stream: int = 0):
+        check(lib().qpsk_chain_process_dev(self._h, d_in, n_floats, in_stride or n_floats, d_baseband, bb_stride or n_floats,
+                                           d_sync, sync_stride, d_costas, costas_stride, d_n_sym, stream))
+
+    def loop_state(self):
+        Cn = self.channels
+        fp, ff = np.empty(Cn, np.float32), np.empty(Cn, np.float32)
+        mu, ct, cf = (np.empty(Cn, np.float64) for _ in range(3))
+        check(lib().qpsk_chain_loop_state(self._h, fp.ctypes.data_as(N.f32p), ff.ctypes.data_as(N.f32p), mu.ctypes.data_as(N.f64p),
+                                          ct.ctypes.data_as(N.f64p), cf.ctypes.data_as(N.f64p)))
+        d = dict(fll_phase=fp, fll_freq=ff, mm_mu=mu, costas_theta=ct, costas_freq=cf)
+        return {k: (float(v[0]) if Cn == 1 else v) for k, v in d.items()}

@@ -467,3 +467,69 @@ def test_batched_chain_device_resident_ber(gpu, orc):
             assert cnt_h[c].tolist() == [err, nref], (burst, c)
     assert (cnt_h[:, 1] == nref).all()
     assert (cnt_h[:, 0] == 0).mean() > 0.9, cnt_h[:, 0]                    # locked channels decode error-free
+
+
+# ---- packed-bit I/O ------------------------------------------------------------------
+@pytest.mark.parametrize("diff,tsc,nbits", [(True, TSC, 600), (False, None, 4096), (True, None, 13), (True, TSC, 0), (False, TSC, 7)])
+def test_modulate_packed_equals_bit_string(gpu, orc, diff, tsc, nbits):
+    rng = np.random.default_rng(nbits + 1)
+    packed = bytes(rng.integers(0, 256, (nbits + 7) // 8, dtype=np.uint8))
+    bits = orc.BitPacker.BytesToBitString(packed)[:nbits]
+    fs = 8_000_000
+    want = orc.QPSKModulator(fs, fs // 4, 0.35, 8, diff, tsc).Modulate(bits)
+    m = gpu.QPSKModulator(fs, fs // 4, 0.35, 8, diff, tsc)
+    got = m.ModulatePacked(packed, nbits)
+    assert got.shape == want.shape
+    assert np.array_equal(got, m.Modulate(bits))                     # bit-identical to the char-string form
+    if want.size:
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    with pytest.raises(gpu.ArgumentException):
+        m.ModulatePacked(packed, 8 * len(packed) + 1)
+
+
+@pytest.mark.parametrize("tsc", [None, TSC])
+def test_demodulate_packed_equals_bit_string(gpu, orc, tsc):
+    fs = 10_000_000
+    a = float(np.float32(0.4))
+    tx = orc.QPSKModulator(fs, fs // 2, a, 10, tsc=tsc).Modulate(_bits(1003 * 2, 41))
+    d1 = gpu.QPSKDeModulator(fs, fs // 2, a, 10, tsc=tsc)
+    d2 = gpu.QPSKDeModulator(fs, fs // 2, a, 10, tsc=tsc)
+    od = orc.QPSKDeModulator(fs, fs // 2, a, 10, tsc=tsc)
+    for _ in range(3):                                               # state carried; odd and even bit counts
+        bits = d1.DeModulate(tx)
+        packed, nb = d2.DeModulatePacked(tx)
+        assert nb == len(bits)
+        assert bits == od.DeModulate(tx)
+        full = orc.BitPacker.BitsToBytes(bits, 0)                    # drops the trailing incomplete byte
+        assert packed[: len(full)] == full
+        if nb % 8:
+            tail = bits[8 * len(full):]
+            assert packed[len(full)] == int(tail.ljust(8, "0"), 2)
+        assert len(packed) == (nb + 7) // 8
+    # batch handle: every channel equals the single-stream result
+    C = 3
+    xs = np.stack([orc.QPSKModulator(fs, fs // 2, a, 10, tsc=tsc).Modulate(_bits(800 + 2 * c, 50 + c))[: 2 * 800] for c in range(C)])
+    db = gpu.QPSKDeModulator(fs, fs // 2, a, 10, tsc=tsc, channels=C)
+    outs = db.DeModulatePacked(xs)
+    for c in range(C):
+        one = gpu.QPSKDeModulator(fs, fs // 2, a, 10, tsc=tsc).DeModulatePacked(xs[c])
+        assert outs[c] == one
+
+
+def test_pack_bits_dev_ragged(gpu):
+    import torch
+    rng = np.random.default_rng(3)
+    C, ld = 6, 1032
+    bits = rng.integers(0, 2, (C, ld), dtype=np.uint8)
+    nb = np.array([0, 1, 7, 8, 1001, 1032], np.int64)
+    db, dn = torch.from_numpy(bits).cuda(), torch.from_numpy(nb).cuda()
+    out = torch.full((C, ld // 8), 0xEE, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    gpu.pack_bits_dev(db.data_ptr(), ld, dn.data_ptr(), ld, C, out.data_ptr(), ld // 8)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    for c in range(C):
+        n = int(nb[c])
+        want = np.packbits(bits[c, :n])                               # MSB first, zero-padded tail
+        assert np.array_equal(got[c, : want.size], want)
+        assert (got[c, want.size:] == 0xEE).all()                     # nothing written past the last used byte
