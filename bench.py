@@ -355,7 +355,7 @@ def main():
         e2e["frac_of_ceiling"] = e2e["value"] / e2e["ceiling"]
         hin.free(); hout.free()
 
-    chain = chain_fll = modulator = None
+    chain = chain_fll = modulator = stream_leg = None
     if not args.no_chain:
         import bench_chain
         d = dist if world > 1 else None
@@ -366,6 +366,7 @@ def main():
         chain = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=False, hbm_peak=hbm_peak)
         chain_fll = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=True, hbm_peak=hbm_peak)
         modulator = bench_chain.run_modulator(Q, torch, d, world, rank, stream, steps=k, warmup=3, hbm_peak=hbm_peak)
+        stream_leg = bench_chain.run_stream(Q) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -388,6 +389,8 @@ def main():
             line["chain"] = chain
             line["chain_fll"] = chain_fll
             line["modulator"] = modulator
+            if stream_leg is not None:
+                line["stream"] = stream_leg
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

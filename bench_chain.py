@@ -149,3 +149,87 @@ def run_modulator(Q, torch, dist, world, rank, stream, steps=3, warmup=3, frames
         "roofline": {"kernel": "mod_shape_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": gbs / hbm_peak, "algorithmic": "8 B written per output sample + 0.25/sps B read twice"},
     }
+
+
+def run_stream(Q, blocks=400, n_payload=512, depth=4, cpu_blocks=40):
+    """SURVEY §8f-3 leg: one radio stream, one burst per block (4196 cf32 samples), host memory in and payload bytes
+    out, wall-clock timed through the public calls: (a) the per-call path DeModulateBytes(block) — H2D, chain, D2H and a
+    synchronise per block, what the reference loop does (TB/SDR/ModDemodOverSDR.cs:127-136); (b) the streaming
+    front-end push()/poll() with `depth` slots; (c) the same with CS16 ingest; (d) the oracle on one host core."""
+    import time
+    import oracle as O
+    O.build()
+    fs = 10_000_000
+    rs = fs // 2
+    alpha = float(np.float32(0.4))
+    S, E = b"S", b"E"
+    mod = O.QPSKModulator(fs, rs, alpha, 10, True, TSC)
+    tx, rx = O.NCO(100e6, fs, 1, seed=9, stream=0), O.NCO(100e6, fs, 1, seed=9, stream=1)
+    uniq = 16
+    pays = [O.fill_bytes(2026, 3, 1000 * k, n_payload) for k in range(uniq)]
+    bursts = [O.channel_apply(tx, rx, 0, mod.ModulateBytes(p, S, E)) for p in pays]
+    n = bursts[0].size
+    peak = max(float(np.abs(b).max()) for b in bursts)
+    b16 = [np.clip(np.round(b / peak * 30000.0), -32768, 32767).astype(np.int16) for b in bursts]
+    out = {"workload": f"{blocks} blocks x {n // 2} cf32 samples (one framed {n_payload}-byte burst each), single stream, "
+                       f"host buffers in, payload bytes out, depth {depth}"}
+
+    def rate(dt, nb):
+        return nb * (n // 2) / dt / 1e6
+
+    # (a) per call
+    d = Q.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC)
+    for i in range(8):
+        d.DeModulateBytes(bursts[i % uniq], S, E)
+    t0 = time.perf_counter()
+    ok = 0
+    for i in range(blocks):
+        ok += bool(d.DeModulateBytes(bursts[i % uniq], S, E))
+    out["per_call"] = {"msamples_s": rate(time.perf_counter() - t0, blocks), "frames": ok}
+    # (b) streaming, cf32
+    d2 = Q.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC)
+    st = Q.StreamingDemodulator(d2, S, E, max_block_floats=n, max_payload_bytes=2048, depth=depth)
+    for i in range(8):
+        st.push(bursts[i % uniq])
+    st.drain()
+    t0 = time.perf_counter()
+    ok = 0
+    for i in range(blocks):
+        st.push(bursts[i % uniq])
+        while True:
+            p = st.poll()
+            if p is None:
+                break
+            ok += bool(p)
+    ok += sum(bool(p) for p in st.drain())
+    out["stream"] = {"msamples_s": rate(time.perf_counter() - t0, blocks), "frames": ok,
+                     "h2d_bytes_per_block": n * 4, "d2h_bytes_per_block": 2048 + 8}
+    st.close()
+    # (c) streaming, CS16
+    d3 = Q.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC)
+    st = Q.StreamingDemodulator(d3, S, E, max_block_floats=n, max_payload_bytes=2048, depth=depth)
+    sc = peak / 30000.0
+    for i in range(8):
+        st.push_cs16(b16[i % uniq], sc)
+    st.drain()
+    t0 = time.perf_counter()
+    ok = 0
+    for i in range(blocks):
+        st.push_cs16(b16[i % uniq], sc)
+        while True:
+            p = st.poll()
+            if p is None:
+                break
+            ok += bool(p)
+    ok += sum(bool(p) for p in st.drain())
+    out["stream_cs16"] = {"msamples_s": rate(time.perf_counter() - t0, blocks), "frames": ok, "h2d_bytes_per_block": n * 2}
+    st.close()
+    # (d) oracle, one core
+    od = O.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC)
+    od.DeModulateBytes(bursts[0], S, E, cap=1 << 16)
+    t0 = time.perf_counter()
+    ok = 0
+    for i in range(cpu_blocks):
+        ok += bool(od.DeModulateBytes(bursts[(i + 1) % uniq], S, E, cap=1 << 16))
+    out["cpu_oracle_1core"] = {"msamples_s": rate(time.perf_counter() - t0, cpu_blocks), "frames": ok}
+    return out

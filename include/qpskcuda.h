@@ -53,6 +53,7 @@ typedef struct qpsk_mod qpsk_mod;
 typedef struct qpsk_demod qpsk_demod;
 typedef struct qpsk_chan qpsk_chan;
 typedef struct qpsk_chain qpsk_chain;
+typedef struct qpsk_stream qpsk_stream;
 
 /* ---- library / device -------------------------------------------------------------------- */
 QPSK_API int qpsk_version(void);                       /* 10000*major + 100*minor + patch         */
@@ -232,6 +233,39 @@ QPSK_API int qpsk_demod_loop_state(qpsk_demod* d, double* costas_theta, double* 
                                    double* mm_integral, float* fll_phase, float* fll_freq);
 /* _inFrame (:62) per channel */
 QPSK_API int qpsk_demod_in_frame(qpsk_demod* d, int* in_frame);
+QPSK_API int qpsk_demod_channels(const qpsk_demod* d, int* channels);
+
+/* ---- streaming front-end: the receive loop of TB/SDR/ModDemodOverSDR.cs:116-183 ------------- */
+/* That loop reads one MTU of cf32 samples into a caller-owned buffer and calls DeModulateTextUtf8 on it (:127-136).
+ * A qpsk_stream keeps the call order and the per-call results (block k's payload is what the k-th
+ * DeModulateBytes(block, start, end) returns on the same demodulator) but decouples the caller from the GPU:
+ * push copies the block to a pinned staging slot and enqueues H2D + chain + framer + D2H on `depth` rotating slots;
+ * poll returns finished payloads in push order.  The demodulator handle (single channel) stays owned by the caller,
+ * must outlive the stream and must not be used directly while blocks are in flight. */
+QPSK_API int qpsk_stream_create(qpsk_demod* d, int64_t max_block_floats, int64_t max_payload_bytes, int depth,
+                                const uint8_t* start_marker, int64_t n_start, const uint8_t* end_marker, int64_t n_end,
+                                qpsk_stream** out);
+QPSK_API int qpsk_stream_destroy(qpsk_stream* s);
+/* one block of interleaved cf32 (n_floats even, <= max_block_floats); returns without waiting for the GPU unless all
+ * `depth` slots are still in flight */
+QPSK_API int qpsk_stream_push(qpsk_stream* s, const float* iq, int64_t n_floats);
+/* the same block as CS16 (interleaved int16 I,Q — MS/Models/HelperFunctions.cs:75-106 writes this format); widened on the
+ * device as (float)v * scale, so PCIe carries 4 bytes per complex sample instead of 8 */
+QPSK_API int qpsk_stream_push_cs16(qpsk_stream* s, const int16_t* iq, int64_t n_int16, float scale);
+/* next block's result in push order.  *have_block = 0: nothing finished yet (wait = 0) or nothing outstanding.
+ * *n_bytes is the payload length of that block (0 = no complete frame in it, like Array.Empty :258);
+ * > cap -> QPSK_ERR_CAPACITY with the block consumed. */
+QPSK_API int qpsk_stream_poll(qpsk_stream* s, int wait, uint8_t* payload_out, int64_t cap, int64_t* n_bytes, int* have_block);
+QPSK_API int qpsk_stream_pending(qpsk_stream* s, int64_t* pushed, int64_t* polled);
+QPSK_API int qpsk_stream_flush(qpsk_stream* s);              /* wait until every pushed block has finished */
+
+/* CS16 <-> cf32.  to_cs16 follows SaveAsCs16 (HelperFunctions.cs:75-106): scale by short.MaxValue / max(|re|,|im|) in
+ * fp64 (max < 1e-12 -> 1), clamp to [short.MinValue, short.MaxValue], truncate toward zero; empty input -> QPSK_ERR_ARG
+ * (:79-80).  *max_abs receives the normalisation factor (needed to undo it).  to_cf32: out = (float)v * scale. */
+QPSK_API int qpsk_cf32_to_cs16(const float* iq, int64_t n_floats, int16_t* out, float* max_abs);
+QPSK_API int qpsk_cs16_to_cf32(const int16_t* in, int64_t n_int16, float scale, float* out);
+QPSK_API int qpsk_cf32_to_cs16_dev(const float* d_in, int64_t n_floats, int16_t* d_out, float* d_max_abs, void* stream);
+QPSK_API int qpsk_cs16_to_cf32_dev(const int16_t* d_in, int64_t n_int16, float scale, float* d_out, void* stream);
 
 /* ---- full receive chain: TB/Simulated/testFullDemodChain.cs:14-116, repaired ------- */
 /* FLL -> RRC matched filter -> Mueller-Muller -> Costas wired as that test does by hand (:22-45, :73-110),

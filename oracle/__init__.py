@@ -419,10 +419,10 @@ class QPSKDeModulator(_Handle):
         _check(lib().orc_demod_bits(self._h, _fp(x), x.size, buf, cap, C.byref(n)))
         return buf.raw[: n.value].decode("ascii")
 
-    def DeModulateBytes(self, samplesIQ, startMarker: bytes, endMarker: bytes) -> bytes:
+    def DeModulateBytes(self, samplesIQ, startMarker: bytes, endMarker: bytes, cap: int = 0) -> bytes:
         x = _f32(samplesIQ)
         s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
-        out = np.empty(x.size // 8 + 64, np.uint8)
+        out = np.empty(cap or (x.size // 8 + 64), np.uint8)          # a frame may span calls: pass cap for long ones
         n = C.c_int64(0)
         _check(lib().orc_demod_bytes(self._h, _fp(x), x.size, _up(s), s.size, _up(e), e.size, _up(out), out.size, C.byref(n)))
         return out[: n.value].tobytes()

@@ -466,3 +466,25 @@ class QPSKDeModulator:
             self._reset()
             return out
         return b""
+
+
+def save_as_cs16(iq) -> tuple:
+    """HelperFunctions.SaveAsCs16 (MS/Models/HelperFunctions.cs:75-106) without the file write: interleaved fp32 IQ
+    (the Complex[] the reference takes is built from such floats, TB/HelperModels.cs:49-58) -> (int16 I,Q,..., maxVal).
+    maxVal = max(|re|, |im|) (:83-90), 1.0 if below 1e-12 (:92); each component = (short) clamp(v / maxVal *
+    short.MaxValue) in fp64 (:97-103) — the C# cast truncates toward zero."""
+    x = np.asarray(iq, np.float32)
+    if x.size == 0:
+        raise ValueError("IQ array is empty.")                     # :79-80
+    maxv = 0.0
+    for v in x.tolist():                                           # python floats = fp64
+        a = abs(v)
+        if a > maxv:
+            maxv = a
+    norm = maxv if maxv >= 1e-12 else 1.0
+    out = np.empty(x.size, np.int16)
+    for k, v in enumerate(x.tolist()):
+        s = v / norm * 32767.0
+        s = max(-32768.0, min(32767.0, s))
+        out[k] = int(s)                                            # int() truncates toward zero
+    return out, maxv

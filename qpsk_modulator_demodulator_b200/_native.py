@@ -126,6 +126,18 @@ def _signatures():
         "qpsk_demod_constellation_dev": (i, [vp, vp, i64, i64, vp, i64, vp, vp]),
         "qpsk_demod_loop_state": (i, [vp, f64p, f64p, f64p, f64p, f32p, f32p]),
         "qpsk_demod_in_frame": (i, [vp, i32p]),
+        "qpsk_demod_channels": (i, [vp, i32p]),
+        "qpsk_stream_create": (i, [vp, i64, i64, i, vp, i64, vp, i64, vpp]),
+        "qpsk_stream_destroy": (i, [vp]),
+        "qpsk_stream_push": (i, [vp, vp, i64]),
+        "qpsk_stream_push_cs16": (i, [vp, vp, i64, f]),
+        "qpsk_stream_poll": (i, [vp, i, vp, i64, i64p, i32p]),
+        "qpsk_stream_pending": (i, [vp, i64p, i64p]),
+        "qpsk_stream_flush": (i, [vp]),
+        "qpsk_cf32_to_cs16": (i, [vp, i64, vp, f32p]),
+        "qpsk_cs16_to_cf32": (i, [vp, i64, f, vp]),
+        "qpsk_cf32_to_cs16_dev": (i, [vp, i64, vp, vp, vp]),
+        "qpsk_cs16_to_cf32_dev": (i, [vp, i64, f, vp, vp]),
         "qpsk_chain_default_params": (i, [C.POINTER(ChainParams)]),
         "qpsk_chain_create": (i, [C.POINTER(ChainParams), i, vpp]),
         "qpsk_chain_destroy": (i, [vp]),

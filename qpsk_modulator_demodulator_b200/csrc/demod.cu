@@ -919,6 +919,12 @@ int qpsk_demod_constellation(qpsk_demod* d, const float* iq_in, int64_t n_floats
   return st;
 }
 
+int qpsk_demod_channels(const qpsk_demod* d, int* channels) {
+  if (!d || !channels) return QPSK_ERR_NULL;
+  *channels = d->eng.channels;
+  return QPSK_OK;
+}
+
 int qpsk_demod_bits_dev(qpsk_demod* d, const float* d_in, int64_t n_floats, int64_t in_stride_floats, uint8_t* d_bits,
                         int64_t bits_cap, int64_t* d_n_bits, void* stream) {
   QPSK_TRY(demod_check_in(d, d_in, n_floats));

@@ -321,3 +321,73 @@ class FullDemodChain(_Handle):
                                           ct.ctypes.data_as(N.f64p), cf.ctypes.data_as(N.f64p)))
         d = dict(fll_phase=fp, fll_freq=ff, mm_mu=mu, costas_theta=ct, costas_freq=cf)
         return {k: (float(v[0]) if Cn == 1 else v) for k, v in d.items()}
+
+
+# ---- §8f-3: streaming front-end + CS16 -----------------------------------------------------------
+class StreamingDemodulator(_Handle):
+    """The receive loop of TB/SDR/ModDemodOverSDR.cs:116-183 without the per-block wait: push() a block (one radio
+    MTU), poll() payloads in push order.  Block k's payload is what the k-th DeModulateBytes(block, start, end) call
+    returns on the same QPSKDeModulator."""
+    _destroy = "qpsk_stream_destroy"
+
+    def __init__(self, demod: "QPSKDeModulator", startMarker: bytes, endMarker: bytes, max_block_floats: int,
+                 max_payload_bytes: int = 1 << 16, depth: int = 4):
+        super().__init__()
+        self.demod = demod                       # keeps the demodulator alive
+        self.max_payload = max_payload_bytes
+        s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
+        check(lib().qpsk_stream_create(demod._h, max_block_floats, max_payload_bytes, depth, _ptr(s), s.size, _ptr(e), e.size,
+                                       C.byref(self._h)))
+        self._buf = np.empty(max_payload_bytes, np.uint8)
+
+    def push(self, samplesIQ):
+        x = _f32(samplesIQ)
+        check(lib().qpsk_stream_push(self._h, _ptr(x), x.size))
+
+    def push_cs16(self, samplesI16, scale: float = 1.0 / 32768.0):
+        x = np.ascontiguousarray(samplesI16, np.int16)
+        check(lib().qpsk_stream_push_cs16(self._h, _ptr(x), x.size, scale))
+
+    def poll(self, wait: bool = False):
+        """-> payload bytes of the next finished block (b"" when it held no complete frame), or None when no block
+        is ready."""
+        n, have = C.c_int64(0), C.c_int(0)
+        check(lib().qpsk_stream_poll(self._h, int(wait), _ptr(self._buf), self._buf.size, C.byref(n), C.byref(have)))
+        if not have.value:
+            return None
+        return self._buf[: n.value].tobytes()
+
+    def pending(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(lib().qpsk_stream_pending(self._h, C.byref(a), C.byref(b)))
+        return a.value - b.value
+
+    def flush(self):
+        check(lib().qpsk_stream_flush(self._h))
+
+    def drain(self):
+        """Wait for every pushed block and return their payloads in order."""
+        out = []
+        while self.pending():
+            out.append(self.poll(wait=True))
+        return out
+
+    def close(self):
+        super().close()
+        self.demod = None
+
+
+def SaveAsCs16(iq) -> tuple:
+    """HelperFunctions.SaveAsCs16 (MS/Models/HelperFunctions.cs:75-106) without the file: -> (int16 array, maxVal)."""
+    x = _f32(iq)
+    out = np.empty(x.size, np.int16)
+    m = C.c_float(0)
+    check(lib().qpsk_cf32_to_cs16(_ptr(x), x.size, _ptr(out), C.byref(m)))
+    return out, m.value
+
+
+def Cs16ToCf32(iq16, scale: float = 1.0 / 32768.0) -> np.ndarray:
+    x = np.ascontiguousarray(iq16, np.int16)
+    out = np.empty(x.size, np.float32)
+    check(lib().qpsk_cs16_to_cf32(_ptr(x), x.size, scale, _ptr(out)))
+    return out

@@ -217,3 +217,18 @@ def test_nco_and_noise_statistics(orc):
     nz = orc.noise_iq(-20.0, 200000, 9, 2)
     assert abs(nz[0::2].std() - 0.1) < 2e-3 and abs(nz[1::2].std() - 0.1) < 2e-3 and np.abs(nz).max() <= 1.0
     assert np.array_equal(orc.noise_iq(-20.0, 100, 9, 2, first_sample=50)[:100], nz[100:200])
+
+
+def test_save_as_cs16_known_answers():
+    """SaveAsCs16 (MS/Models/HelperFunctions.cs:75-106), hand-derived: normalise by the largest |component|, scale by
+    short.MaxValue, truncate toward zero; an all-zero buffer is normalised by 1."""
+    from oracle import np_twin
+    out, m = np_twin.save_as_cs16(np.array([1.0, -1.0, 0.5, -0.5, 0.25, 0.0], np.float32))
+    assert m == 1.0
+    assert out.tolist() == [32767, -32767, 16383, -16383, 8191, 0]      # 16383.5 -> 16383, -16383.5 -> -16383
+    out, m = np_twin.save_as_cs16(np.array([2.0, -4.0], np.float32))
+    assert m == 4.0 and out.tolist() == [16383, -32767]
+    out, m = np_twin.save_as_cs16(np.zeros(4, np.float32))
+    assert m == 0.0 and out.tolist() == [0, 0, 0, 0]
+    with pytest.raises(ValueError):
+        np_twin.save_as_cs16(np.zeros(0, np.float32))

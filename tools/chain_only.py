@@ -6,7 +6,9 @@ import bench_chain
 Q.set_device(0)
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); s = ts.cuda_stream
 which = sys.argv[1]
-if which == 'sweep':
+if which == 'stream':
+    r = bench_chain.run_stream(Q)
+elif which == 'sweep':
     r = {}
     for C in (1024, 2048, 4096, 8192, 16384):
         for fll in (False, True):
