@@ -141,6 +141,86 @@ __device__ __forceinline__ void sincos_fast_f64(double x, double* sn, double* cs
   *sn = (q & 2) ? -s0 : s0;
   *cs = ((q + 1) & 2) ? -c0 : c0;
 }
+// The same function for the serial loop kernels, where it sits on the loop-carried dependency chain (one warp per
+// scheduler, nothing to hide latency behind): the 26 fp64 constants are loaded ONCE into registers through an opaque
+// asm (otherwise ptxas rematerialises each as two 32-bit immediates per use: ~50 extra issue slots per call), and the
+// quadrant fix-up is four FSELs plus a sign-bit XOR instead of fp64 negations.  Same operations in the same order as
+// sincos_fast_f64 on the value path, so the results are bit-identical to it.
+struct SinCosK {
+  double two_over_pi, p1, p2, p3;
+  double s[10], c[10];
+  double half, one;
+};
+// constant table: [0..3] 2/pi and the three Cody-Waite pieces of pi/2, [4..13] sin coefficients, [14..23] cos
+// coefficients, [24] 0.5, [25] 1.0
+static __constant__ double kSinCosTab[26] = {
+    0.63661977236758134308, 1.5707963267948966e+00, 6.123233995736766e-17, -1.4973849048591698e-33,
+    -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0, 1.0 / 6227020800.0,
+    -1.0 / 1307674368000.0, 1.0 / 355687428096000.0, -1.0 / 121645100408832000.0, 1.0 / 51090942171709440000.0,
+    1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0,
+    1.0 / 20922789888000.0, -1.0 / 6402373705728000.0, 1.0 / 2432902008176640000.0, -1.0 / 1124000727777607680000.0,
+    0.5, 1.0};
+// a volatile load ptxas can neither fold nor re-execute: the value has to stay in a register pair
+__device__ __forceinline__ double ld_const_pinned(const double* p) {
+  double v;
+  asm volatile("ld.const.f64 %0, [%1];" : "=d"(v) : "l"(__cvta_generic_to_constant(p)));
+  return v;
+}
+__device__ __forceinline__ SinCosK sincos_load_consts() {
+  SinCosK K;
+  K.two_over_pi = ld_const_pinned(&kSinCosTab[0]);
+  K.p1 = ld_const_pinned(&kSinCosTab[1]);
+  K.p2 = ld_const_pinned(&kSinCosTab[2]);
+  K.p3 = ld_const_pinned(&kSinCosTab[3]);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    K.s[i] = ld_const_pinned(&kSinCosTab[4 + i]);
+    K.c[i] = ld_const_pinned(&kSinCosTab[14 + i]);
+  }
+  K.half = ld_const_pinned(&kSinCosTab[24]);
+  K.one = ld_const_pinned(&kSinCosTab[25]);
+  return K;
+}
+__device__ __forceinline__ void sincos_fast_f64_k(double x, const SinCosK& K, double* sn, double* cs) {
+  const double k = rint(x * K.two_over_pi);
+  const int q = (int)k;                                   // off the value path: only the final selects use it
+  double r = fma(-k, K.p1, x);
+  r = fma(-k, K.p2, r);
+  r = fma(-k, K.p3, r);
+  const double z = r * r, z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+  const double a01 = fma(K.s[1], z, K.s[0]);
+  const double a23 = fma(K.s[3], z, K.s[2]);
+  const double a45 = fma(K.s[5], z, K.s[4]);
+  const double a67 = fma(K.s[7], z, K.s[6]);
+  const double a89 = fma(K.s[9], z, K.s[8]);
+  const double S = fma(a89, z8, fma(fma(a67, z2, a45), z4, fma(a23, z2, a01)));
+  const double sr = fma(r * z, S, r);
+  const double d01 = fma(K.c[1], z, K.c[0]);
+  const double d23 = fma(K.c[3], z, K.c[2]);
+  const double d45 = fma(K.c[5], z, K.c[4]);
+  const double d67 = fma(K.c[7], z, K.c[6]);
+  const double d89 = fma(K.c[9], z, K.c[8]);
+  const double Cc = fma(d89, z8, fma(fma(d67, z2, d45), z4, fma(d23, z2, d01)));
+  const double hz = K.half * z;
+  const double w = K.one - hz;
+  const double cr = w + (((K.one - w) - hz) + z2 * Cc);
+  const bool swap = (q & 1) != 0;
+  const unsigned s_flip = ((unsigned)q & 2u) << 30;        // sign bit when quadrant 2 or 3
+  const unsigned c_flip = ((unsigned)(q + 1) & 2u) << 30;  // sign bit when quadrant 1 or 2
+  const int sr_hi = __double2hiint(sr), sr_lo = __double2loint(sr);
+  const int cr_hi = __double2hiint(cr), cr_lo = __double2loint(cr);
+  const int s_hi = (swap ? cr_hi : sr_hi) ^ (int)s_flip, s_lo = swap ? cr_lo : sr_lo;
+  const int c_hi = (swap ? sr_hi : cr_hi) ^ (int)c_flip, c_lo = swap ? sr_lo : cr_lo;
+  *sn = __hiloint2double(s_hi, s_lo);
+  *cs = __hiloint2double(c_hi, c_lo);
+}
+// MathF.Sin/Cos model (see sincos_f32_exact) through the register-constant fast path
+__device__ __forceinline__ void sincos_f32_fast_k(float x, const SinCosK& K, float* s, float* c) {
+  double sd, cd;
+  sincos_fast_f64_k((double)x, K, &sd, &cd);
+  *s = (float)sd;
+  *c = (float)cd;
+}
 // MathF.Sin/Cos model through the fast path (|x| small: loop phases are bounded)
 __device__ __forceinline__ void sincos_f32_fast(float x, float* s, float* c) {
   double sd, cd;

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(32)
                   long long* n_bits) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  const SinCosK K = sincos_load_consts();
   CostasState S = cst_g[c];
   DiffState D = dst_g[c];
   const float2* sc = sym + (long long)c * ld_sym;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(32)
   for (int k = 0; k < n; ++k) {
     const float2 in = sc[k];
     float rI, rQ;
-    costas_step(P, S, in.x, in.y, rI, rQ);                 // :378
+    costas_step(P, K, S, in.x, in.y, rI, rQ);              // :378
     const float dI = (rI >= 0.f) ? 1.f : -1.f;             // GetSign (CostasLoopQpsk.cs:52-56)
     const float dQ = (rQ >= 0.f) ? 1.f : -1.f;
     unsigned char b0, b1;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(64)
   MmState S;
   int carried = 0, n_sym = 0;
   // role 1 state
+  const SinCosK SK = sincos_load_consts();
   CostasState K;
   DiffState D;
   long long nb = 0;
@@ -153,6 +155,11 @@ __global__ void __launch_bounds__(64)
     K = cst_g[c];
     D = dst_g[c];
   }
+  // Mueller-Muller loop registers.  The previous decision is +-1 and only ever multiplies (:78), so it is kept as a
+  // sign; the previous sample is kept widened (it only appears as (double)dec * prevSample, :79).
+  bool prevNegI = S.prevDI < 0.f, prevNegQ = S.prevDQ < 0.f;
+  double prevSI_d = (double)S.prevSI, prevSQ_d = (double)S.prevSQ;
+  bool has_prev = S.has_prev != 0;
 
   for (int r = 0; r <= rounds; ++r) {
     if (role == 0) {
@@ -171,33 +178,37 @@ __global__ void __launch_bounds__(64)
         v.in = sm.raw[r & 1] + lane * kSsPitch;
         v.queued = carried;
         const int count = carried + blk;
+        const double limit_d = (double)(count - 2);  // loop test in fp64: base + 2 < count  <=>  base_d < count - 2
         float2* sq = sm.symq[r & 1] + lane * kSsSymPitch;
         int ns = 0;
-        while (S.base_index + 2 < count) {           // MuellerMuller.cs:62
+        double base_d = (double)S.base_index;        // == (double)baseIndex exactly; floor() keeps it integral
+        // One pass = one symbol (MuellerMuller.cs:62-120); the loop-carried chain is mu -> interpolator -> error ->
+        // loop filter -> newTime -> floor -> mu.  Off that chain: +-1 factors are sign flips (exact), both clamp tests
+        // read the unclamped value (:87-89: 0.1 > -0.1, so the second test cannot fire after the first), floor()
+        // yields (double)baseIndex directly (no F2I -> I2F round trip), and the loop test reads the fp64 base.  The
+        // post-advance break (:118-119, base + 1 >= count) implies the loop test fails, so one test serves both.
+        while (base_d < limit_d) {                   // :62
           float ci, cq;
           mm_interp(v, S.base_index, S.mu, ci, cq);
-          const float decI = (ci >= 0.f) ? 1.f : -1.f;   // GetSignQpsk :194-198
-          const float decQ = (cq >= 0.f) ? 1.f : -1.f;
-          double advance;
-          if (S.has_prev) {
-            const double term1 = (double)S.prevDI * ci + (double)S.prevDQ * cq;     // :78
-            const double term2 = (double)decI * S.prevSI + (double)decQ * S.prevSQ; // :79
+          const bool posI = ci >= 0.f, posQ = cq >= 0.f;     // GetSignQpsk :194-198
+          const double ci_d = (double)ci, cq_d = (double)cq;
+          double advance = MP.sps;
+          if (has_prev) {
+            const double term1 = flip_sign_if(ci_d, prevNegI) + flip_sign_if(cq_d, prevNegQ);       // :78
+            const double term2 = flip_sign_if(prevSI_d, !posI) + flip_sign_if(prevSQ_d, !posQ);     // :79
             const double e = term1 - term2;
             S.integral += MP.ki * e;                 // :83
-            double corr = MP.kp * e + S.integral;    // :84
-            if (corr > 0.1) corr = 0.1;              // :87-89
-            if (corr < -0.1) corr = -0.1;
-            advance = MP.sps + corr;
-          } else {
-            S.has_prev = 1;
-            advance = MP.sps;
+            const double corr = MP.kp * e + S.integral;      // :84
+            const double cl = (corr > 0.1) ? 0.1 : ((corr < -0.1) ? -0.1 : corr);   // :87-89
+            advance = MP.sps + cl;
           }
-          S.prevSI = ci; S.prevSQ = cq; S.prevDI = decI; S.prevDQ = decQ;
-          const double newTime = S.base_index + S.mu + advance;                      // :113
-          S.base_index = (int)floor(newTime);
-          S.mu = newTime - S.base_index;
+          has_prev = true;
+          prevSI_d = ci_d; prevSQ_d = cq_d; prevNegI = !posI; prevNegQ = !posQ;
+          const double newTime = (base_d + S.mu) + advance;  // :113
+          base_d = floor(newTime);
+          S.mu = newTime - base_d;                   // :115
+          S.base_index = (int)base_d;                // :114
           sq[ns++] = make_float2(ci, cq);
-          if (S.base_index + 1 >= count) break;      // :118-119
         }
         n_sym += ns;
         sm.nsymq[r & 1][lane] = ns;
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(64)
       for (int k = 0; k < ns; ++k) {
         const float2 in = sq[k];
         float rI, rQ;
-        costas_step(CP, K, in.x, in.y, rI, rQ);
+        costas_step(CP, SK, K, in.x, in.y, rI, rQ);
         const float dI = (rI >= 0.f) ? 1.f : -1.f;
         const float dQ = (rQ >= 0.f) ? 1.f : -1.f;
         unsigned char b0, b1;
@@ -246,6 +257,11 @@ __global__ void __launch_bounds__(64)
       }
     }
     __syncthreads();                                 // hand the round's symbol queue over / free the other one
+  }
+  if (role == 0) {
+    S.has_prev = has_prev ? 1 : 0;
+    S.prevSI = (float)prevSI_d; S.prevSQ = (float)prevSQ_d;   // exact: they were widened floats
+    S.prevDI = prevNegI ? -1.f : 1.f; S.prevDQ = prevNegQ ? -1.f : 1.f;
   }
   if (live) {
     if (role == 0) {

@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kFllCtaThreads)
     tlb[t] = taps[N + NV + t];
   }
   const float newA = taps[N - 1], newB = taps[2 * N - 1];   // tap of the newest window element
+  const SinCosK SK = sincos_load_consts();
   for (int i = g; i < N; i += kFllGroup) {
     const float2 v = ring_g[(long long)i * C + c];
     myring[i] = v;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kFllCtaThreads)
     for (int n = 0; n < nb; ++n) {
       // -- critical chain: phase -> sin/cos -> rotated sample
       float s, co;
-      sincos_f32_fast(phase, &s, &co);                      // MathF.Cos/Sin(phase) :108-109
+      sincos_f32_fast_k(phase, SK, &s, &co);                // MathF.Cos/Sin(phase) :108-109
       const float2 in = myx[n];
       const float oI = in.x * co - in.y * s;                // :111
       const float oQ = in.x * s + in.y * co;                // :112
@@ -522,6 +523,7 @@ __global__ void __launch_bounds__(kLoopThreads)
                   long long L, long long ldx, long long ldy, const int* __restrict__ n_sym) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  const SinCosK K = sincos_load_consts();
   CostasState S = st_g[c];
   const long long n = n_sym ? (long long)n_sym[c] : L;
   const float2* xc = x + (long long)c * ldx;
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(kLoopThreads)
   for (long long k = 0; k < n; ++k) {
     const float2 in = xc[k];
     float oI, oQ;
-    costas_step(P, S, in.x, in.y, oI, oQ);
+    costas_step(P, K, S, in.x, in.y, oI, oQ);
     yc[k] = make_float2(oI, oQ);
   }
   st_g[c] = S;

@@ -155,23 +155,37 @@ struct CostasParams {
   double alpha, beta;
 };
 
-__device__ __forceinline__ void costas_step(const CostasParams& P, CostasState& S, float inI, float inQ, float& outI,
-                                            float& outQ) {
+// flip the sign of x when `neg` (exact: what multiplying by -1.0 does)
+__device__ __forceinline__ double flip_sign_if(double x, bool neg) {
+  return __hiloint2double(__double2hiint(x) ^ (neg ? (int)0x80000000u : 0), __double2loint(x));
+}
+
+// One CostasLoopQpsk.Process step (:63-92).  This is a loop-carried dependency chain of ~30 fp64 operations with
+// nothing to overlap it with (one stream per thread), so everything that is not arithmetic on the value path has been
+// moved off it, without changing a single rounding:
+//   * sin/cos through sincos_fast_f64_k (constants in registers, quadrant fix-up by select / sign-bit XOR); the
+//     |theta| >= 1e5 case (never reached: theta is wrapped every step, :89-91) re-evaluates with sincos() afterwards;
+//   * the decisions sign((float)mi), sign((float)mq) (:76-80) are taken on the fp64 values: (float)m >= 0 exactly when
+//     m >= -2^-150 (smaller magnitudes round to +-0 and -0.0f >= 0) — this removes an F2F -> FSETP -> FSEL -> F2F chain;
+//   * est = +-1.0, so est*m is an exact sign flip: pe = (+-mq) - (+-mi) (:82);
+//   * both wrap candidates theta -+ 2*pi are formed speculatively and selected (:89-91).
+__device__ __forceinline__ void costas_step(const CostasParams& P, const SinCosK& K, CostasState& S, float inI, float inQ,
+                                            float& outI, float& outQ) {
   double s, c;
-  if (fabs(S.theta) < 1.0e5) sincos_fast_f64(S.theta, &s, &c);   // theta stays near [-pi, pi] (:89-91)
-  else sincos(S.theta, &s, &c);
-  const double mi = (double)inI * c + (double)inQ * s;   // :72
-  const double mq = (double)inQ * c - (double)inI * s;   // :73
+  sincos_fast_f64_k(S.theta, K, &s, &c);
+  if (!(fabs(S.theta) < 1.0e5)) sincos(S.theta, &s, &c);
+  const double dI = (double)inI, dQ = (double)inQ;
+  const double mi = dI * c + dQ * s;                         // :72
+  const double mq = dQ * c - dI * s;                         // :73
   outI = (float)mi;
   outQ = (float)mq;
-  const float estI = (outI >= 0.f) ? 1.f : -1.f;
-  const float estQ = (outQ >= 0.f) ? 1.f : -1.f;
-  const double pe = (double)estI * mq - (double)estQ * mi;   // :82
-  S.freq += P.beta * pe;
-  S.theta += S.freq + P.alpha * pe;
+  const bool posI = mi >= -0x1p-150, posQ = mq >= -0x1p-150; // GetSign of the fp32 outputs (:52-56, :76-80)
+  const double pe = flip_sign_if(mq, !posI) - flip_sign_if(mi, !posQ);   // :82
+  S.freq += P.beta * pe;                                     // :85
+  const double t = S.theta + (S.freq + P.alpha * pe);        // :86
   const double kPi = 3.14159265358979323846, kTwoPi = 2.0 * kPi;
-  if (S.theta > kPi) S.theta -= kTwoPi;
-  else if (S.theta < -kPi) S.theta += kTwoPi;
+  const double t_dn = t - kTwoPi, t_up = t + kTwoPi;
+  S.theta = (t > kPi) ? t_dn : ((t < -kPi) ? t_up : t);      // :89-91
 }
 
 // ---------------------------------------------------------------------------------------------
