@@ -192,16 +192,16 @@ __global__ void __launch_bounds__(64)
           mm_interp(v, S.base_index, S.mu, ci, cq);
           const bool posI = ci >= 0.f, posQ = cq >= 0.f;     // GetSignQpsk :194-198
           const double ci_d = (double)ci, cq_d = (double)cq;
-          double advance = MP.sps;
-          if (has_prev) {
-            const double term1 = flip_sign_if(ci_d, prevNegI) + flip_sign_if(cq_d, prevNegQ);       // :78
-            const double term2 = flip_sign_if(prevSI_d, !posI) + flip_sign_if(prevSQ_d, !posQ);     // :79
-            const double e = term1 - term2;
-            S.integral += MP.ki * e;                 // :83
-            const double corr = MP.kp * e + S.integral;      // :84
-            const double cl = (corr > 0.1) ? 0.1 : ((corr < -0.1) ? -0.1 : corr);   // :87-89
-            advance = MP.sps + cl;
-          }
+          // branch-free (one basic block per symbol, so ptxas can interleave the independent work with the chain):
+          // without a previous symbol the error terms are computed and discarded (:72-97)
+          const double term1 = flip_sign_if(ci_d, prevNegI) + flip_sign_if(cq_d, prevNegQ);       // :78
+          const double term2 = flip_sign_if(prevSI_d, !posI) + flip_sign_if(prevSQ_d, !posQ);     // :79
+          const double e = term1 - term2;
+          const double integ = S.integral + MP.ki * e;       // :83
+          const double corr = MP.kp * e + integ;             // :84
+          const double cl = (corr > 0.1) ? 0.1 : ((corr < -0.1) ? -0.1 : corr);   // :87-89
+          const double advance = has_prev ? (MP.sps + cl) : MP.sps;               // :91, :96
+          S.integral = has_prev ? integ : S.integral;
           has_prev = true;
           prevSI_d = ci_d; prevSQ_d = cq_d; prevNegI = !posI; prevNegQ = !posQ;
           const double newTime = (base_d + S.mu) + advance;  // :113
@@ -225,35 +225,76 @@ __global__ void __launch_bounds__(64)
       }
     } else if (r >= 1) {
       // ---- Costas + decision + differential decode (QPSKDeModulator.cs:374-408) on round r-1 ----
+      // One basic block per symbol: the Costas recurrence is the critical chain; the decisions, the differential
+      // decode (pure predicate logic on the four sign bits: d*conj(d_prev) of two unit-corner symbols is one of
+      // 2, 2j, -2, -2j, so the float products of :397-398 reduce to XORs of signs, bit for bit) and the predicated
+      // bit store hang off it and are scheduled into its latency shadows.  The |theta| >= 1e5 case of costas_step
+      // cannot be tested inside the block without splitting it: it is accumulated in `wild` and, should it ever fire,
+      // the round is replayed from the saved state through the exact (branching) step.
       const int b = (r - 1) & 1;
       const int ns = sm.nsymq[b][lane];
       const float2* sq = sm.symq[b] + lane * kSsSymPitch;
+      const CostasState K0 = K;
+      const DiffState D0 = D;
+      const long long nb0 = nb;
+      bool wild = false;
+      bool havePrev = D.have_prev != 0, pNegI = D.prevI < 0.f, pNegQ = D.prevQ < 0.f;
+      float2 nxt = sq[0];
       for (int k = 0; k < ns; ++k) {
-        const float2 in = sq[k];
+        const float2 in = nxt;
+        nxt = sq[k + 1];                               // row pitch kSsSymCap + 1: in bounds for every k < ns
+        wild |= !(fabs(K.theta) < 1.0e5);
         float rI, rQ;
-        costas_step(CP, SK, K, in.x, in.y, rI, rQ);
-        const float dI = (rI >= 0.f) ? 1.f : -1.f;
-        const float dQ = (rQ >= 0.f) ? 1.f : -1.f;
-        unsigned char b0, b1;
+        costas_step_fast(CP, SK, K, in.x, in.y, rI, rQ);
+        const bool nI = !(rI >= 0.f), nQ = !(rQ >= 0.f);   // GetSign (CostasLoopQpsk.cs:52-56): d = -1 when !(r >= 0)
+        unsigned b0, b1;
         if (diff) {
-          if (!D.have_prev) {
-            D.prevI = dI; D.prevQ = dQ; D.have_prev = 1;
-            continue;
-          }
-          const float deltaI = dI * D.prevI + dQ * D.prevQ;
-          const float deltaQ = dQ * D.prevI - dI * D.prevQ;
-          D.prevI = dI; D.prevQ = dQ;
-          if (fabsf(deltaI) >= fabsf(deltaQ)) {
-            if (deltaI >= 0.f) { b0 = 0; b1 = 0; } else { b0 = 1; b1 = 1; }
-          } else {
-            if (deltaQ >= 0.f) { b0 = 0; b1 = 1; } else { b0 = 1; b1 = 0; }
-          }
-        } else {
-          if (dI < 0.f) { b0 = 0; b1 = (dQ < 0.f) ? 0 : 1; }
-          else { b0 = 1; b1 = (dQ >= 0.f) ? 1 : 0; }
+          const bool a = nI != pNegI, bq = nQ != pNegQ;   // dI*pI < 0, dQ*pQ < 0      (:397)
+          const bool cc = nQ != pNegI, dd = nI != pNegQ;  // dQ*pI < 0, dI*pQ < 0      (:398)
+          const bool realAxis = (a == bq);                // |deltaI| >= |deltaQ|  <=>  deltaI != 0   (:322)
+          const bool qPos = (!cc) && dd;                  // deltaQ = 2
+          b0 = realAxis ? (a ? 1u : 0u) : (qPos ? 0u : 1u);   // AppendDeltaBits :320-337
+          b1 = realAxis ? (a ? 1u : 0u) : (qPos ? 1u : 0u);
+        } else {                                          // AppendDecisionBits :304-318
+          b0 = nI ? 0u : 1u;
+          b1 = nI ? (nQ ? 0u : 1u) : (nQ ? 0u : 1u);
         }
-        if (live) bc[nb >> 1] = make_uchar2(b0, b1);
-        nb += 2;
+        const bool emit = !diff || havePrev;              // the first symbol ever is only the reference (:390-395)
+        if (live && emit) bc[nb >> 1] = make_uchar2((unsigned char)b0, (unsigned char)b1);
+        nb += emit ? 2 : 0;
+        havePrev = true;
+        pNegI = nI; pNegQ = nQ;
+      }
+      if (diff && ns > 0) { D.have_prev = 1; D.prevI = pNegI ? -1.f : 1.f; D.prevQ = pNegQ ? -1.f : 1.f; }
+      if (wild) {                                         // never in practice; exactness for any input
+        K = K0; D = D0; nb = nb0;
+        for (int k = 0; k < ns; ++k) {
+          const float2 in = sq[k];
+          float rI, rQ;
+          costas_step(CP, SK, K, in.x, in.y, rI, rQ);
+          const float dI = (rI >= 0.f) ? 1.f : -1.f;
+          const float dQ = (rQ >= 0.f) ? 1.f : -1.f;
+          unsigned char b0, b1;
+          if (diff) {
+            if (!D.have_prev) {
+              D.prevI = dI; D.prevQ = dQ; D.have_prev = 1;
+              continue;
+            }
+            const float deltaI = dI * D.prevI + dQ * D.prevQ;
+            const float deltaQ = dQ * D.prevI - dI * D.prevQ;
+            D.prevI = dI; D.prevQ = dQ;
+            if (fabsf(deltaI) >= fabsf(deltaQ)) {
+              if (deltaI >= 0.f) { b0 = 0; b1 = 0; } else { b0 = 1; b1 = 1; }
+            } else {
+              if (deltaQ >= 0.f) { b0 = 0; b1 = 1; } else { b0 = 1; b1 = 0; }
+            }
+          } else {
+            if (dI < 0.f) { b0 = 0; b1 = (dQ < 0.f) ? 0 : 1; }
+            else { b0 = 1; b1 = (dQ >= 0.f) ? 1 : 0; }
+          }
+          if (live) bc[nb >> 1] = make_uchar2(b0, b1);
+          nb += 2;
+        }
       }
     }
     __syncthreads();                                 // hand the round's symbol queue over / free the other one

@@ -169,11 +169,11 @@ __device__ __forceinline__ double flip_sign_if(double x, bool neg) {
 //     m >= -2^-150 (smaller magnitudes round to +-0 and -0.0f >= 0) — this removes an F2F -> FSETP -> FSEL -> F2F chain;
 //   * est = +-1.0, so est*m is an exact sign flip: pe = (+-mq) - (+-mi) (:82);
 //   * both wrap candidates theta -+ 2*pi are formed speculatively and selected (:89-91).
-__device__ __forceinline__ void costas_step(const CostasParams& P, const SinCosK& K, CostasState& S, float inI, float inQ,
-                                            float& outI, float& outQ) {
+// the straight-line part: valid while |theta| < 1e5 (the caller checks)
+__device__ __forceinline__ void costas_step_fast(const CostasParams& P, const SinCosK& K, CostasState& S, float inI, float inQ,
+                                                 float& outI, float& outQ) {
   double s, c;
   sincos_fast_f64_k(S.theta, K, &s, &c);
-  if (!(fabs(S.theta) < 1.0e5)) sincos(S.theta, &s, &c);
   const double dI = (double)inI, dQ = (double)inQ;
   const double mi = dI * c + dQ * s;                         // :72
   const double mq = dQ * c - dI * s;                         // :73
@@ -186,6 +186,27 @@ __device__ __forceinline__ void costas_step(const CostasParams& P, const SinCosK
   const double kPi = 3.14159265358979323846, kTwoPi = 2.0 * kPi;
   const double t_dn = t - kTwoPi, t_up = t + kTwoPi;
   S.theta = (t > kPi) ? t_dn : ((t < -kPi) ? t_up : t);      // :89-91
+}
+__device__ __forceinline__ void costas_step(const CostasParams& P, const SinCosK& K, CostasState& S, float inI, float inQ,
+                                            float& outI, float& outQ) {
+  if (fabs(S.theta) < 1.0e5) {
+    costas_step_fast(P, K, S, inI, inQ, outI, outQ);
+    return;
+  }
+  double s, c;
+  sincos(S.theta, &s, &c);
+  const double dI = (double)inI, dQ = (double)inQ;
+  const double mi = dI * c + dQ * s;
+  const double mq = dQ * c - dI * s;
+  outI = (float)mi;
+  outQ = (float)mq;
+  const double estI = (outI >= 0.f) ? 1.0 : -1.0, estQ = (outQ >= 0.f) ? 1.0 : -1.0;
+  const double pe = estI * mq - estQ * mi;
+  S.freq += P.beta * pe;
+  S.theta += S.freq + P.alpha * pe;
+  const double kPi = 3.14159265358979323846, kTwoPi = 2.0 * kPi;
+  if (S.theta > kPi) S.theta -= kTwoPi;
+  else if (S.theta < -kPi) S.theta += kTwoPi;
 }
 
 // ---------------------------------------------------------------------------------------------
