@@ -107,11 +107,13 @@ struct SsSmem {
   int nsymq[2][32];
 };
 
+template <bool DIFF>
 __global__ void __launch_bounds__(64)
     symsync_decode_kernel(const MmParams MP, MmState* mm_g, const float2* __restrict__ q_in, float2* __restrict__ q_out,
                           long long qcap, const CostasParams CP, CostasState* cst_g, DiffState* dst_g, int C,
-                          const float2* __restrict__ x, long long L, long long ldx, int diff, uint8_t* __restrict__ bits,
+                          const float2* __restrict__ x, long long L, long long ldx, uint8_t* __restrict__ bits,
                           long long ld_bits, long long* n_bits, int* n_sym_g) {
+  constexpr bool diff = DIFF;
   __shared__ SsSmem sm;
   const int lane = threadIdx.x & 31;
   const int role = threadIdx.x >> 5;                // 0: symbol sync, 1: Costas + decode
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(64)
         // read the unclamped value (:87-89: 0.1 > -0.1, so the second test cannot fire after the first), floor()
         // yields (double)baseIndex directly (no F2I -> I2F round trip), and the loop test reads the fp64 base.  The
         // post-advance break (:118-119, base + 1 >= count) implies the loop test fails, so one test serves both.
-        while (base_d < limit_d) {                   // :62
+        auto one_symbol = [&]() {
           float ci, cq;
           mm_interp(v, S.base_index, S.mu, ci, cq);
           const bool posI = ci >= 0.f, posQ = cq >= 0.f;     // GetSignQpsk :194-198
@@ -209,7 +211,15 @@ __global__ void __launch_bounds__(64)
           S.mu = newTime - base_d;                   // :115
           S.base_index = (int)base_d;                // :114
           sq[ns++] = make_float2(ci, cq);
-        }
+        };
+        // The loop test reads the newest base, i.e. it closes the dependency chain through floor -> compare -> branch.
+        // Every symbol advances time by at most sps + 0.1 (:87-91), so the first n_safe passes are known to satisfy it
+        // and run as a counted loop whose branch resolves early; only the last one or two passes are tested.
+        const double span_d = limit_d - (base_d + S.mu);
+        const double q = span_d / (MP.sps + 0.1000001);
+        int n_safe = (q > 1.0) ? (int)q - 1 : 0;       // conservative: floor(q) - 1 full advances certainly fit
+        for (int j = 0; j < n_safe; ++j) one_symbol();
+        while (base_d < limit_d) one_symbol();       // :62
         n_sym += ns;
         sm.nsymq[r & 1][lane] = ns;
         // drop consumed samples, keep at least the last three (:123-129)
@@ -238,33 +248,33 @@ __global__ void __launch_bounds__(64)
       const DiffState D0 = D;
       const long long nb0 = nb;
       bool wild = false;
-      bool havePrev = D.have_prev != 0, pNegI = D.prevI < 0.f, pNegQ = D.prevQ < 0.f;
+      // decisions as sign bits: bit 0 = I is -1, bit 1 = Q is -1; `prev` holds the previous symbol's pair
+      unsigned prev = (D.prevI < 0.f ? 1u : 0u) | (D.prevQ < 0.f ? 2u : 0u);
+      const bool skipFirst = diff && !D.have_prev;       // the first symbol ever is only the reference (:390-395)
+      // The two output bits as a function of idx = cur | prev << 2, one 16-entry table per bit.  Differential
+      // (AppendDeltaBits :320-337 on delta = d * conj(d_prev), :397-398): the four float products are +-1, so
+      // deltaI = +-2 iff the I and Q sign changes agree (then bits 00 / 11), else deltaQ = +-2 (bits 01 / 10).
+      // Absolute (AppendDecisionBits :304-318): b0 = (dI >= 0), b1 = (dQ >= 0).
+      constexpr unsigned kB0 = DIFF ? 0x3A5Cu : 0x5555u;   // enumerated from the float formulas (tests compare with the
+      constexpr unsigned kB1 = DIFF ? 0x53CAu : 0x3333u;   // unfused decode_kernel, which keeps them)
+      uchar2* bp = bc + (nb >> 1);
+      int stored = 0;
       float2 nxt = sq[0];
       for (int k = 0; k < ns; ++k) {
         const float2 in = nxt;
-        nxt = sq[k + 1];                               // row pitch kSsSymCap + 1: in bounds for every k < ns
-        wild |= !(fabs(K.theta) < 1.0e5);
+        nxt = sq[k + 1];                                 // row pitch kSsSymCap + 1: in bounds for every k < ns
         float rI, rQ;
-        costas_step_fast(CP, SK, K, in.x, in.y, rI, rQ);
-        const bool nI = !(rI >= 0.f), nQ = !(rQ >= 0.f);   // GetSign (CostasLoopQpsk.cs:52-56): d = -1 when !(r >= 0)
-        unsigned b0, b1;
-        if (diff) {
-          const bool a = nI != pNegI, bq = nQ != pNegQ;   // dI*pI < 0, dQ*pQ < 0      (:397)
-          const bool cc = nQ != pNegI, dd = nI != pNegQ;  // dQ*pI < 0, dI*pQ < 0      (:398)
-          const bool realAxis = (a == bq);                // |deltaI| >= |deltaQ|  <=>  deltaI != 0   (:322)
-          const bool qPos = (!cc) && dd;                  // deltaQ = 2
-          b0 = realAxis ? (a ? 1u : 0u) : (qPos ? 0u : 1u);   // AppendDeltaBits :320-337
-          b1 = realAxis ? (a ? 1u : 0u) : (qPos ? 1u : 0u);
-        } else {                                          // AppendDecisionBits :304-318
-          b0 = nI ? 0u : 1u;
-          b1 = nI ? (nQ ? 0u : 1u) : (nQ ? 0u : 1u);
-        }
-        const bool emit = !diff || havePrev;              // the first symbol ever is only the reference (:390-395)
-        if (live && emit) bc[nb >> 1] = make_uchar2((unsigned char)b0, (unsigned char)b1);
-        nb += emit ? 2 : 0;
-        havePrev = true;
-        pNegI = nI; pNegQ = nQ;
+        unsigned sI, sQ;
+        costas_step_fast(CP, SK, K, in.x, in.y, rI, rQ, sI, sQ, wild);
+        const unsigned cur = (sI >> 31) | (sQ >> 30);
+        const unsigned idx = cur | (prev << 2);
+        prev = cur;
+        const unsigned v = ((kB0 >> idx) & 1u) | (((kB1 >> idx) & 1u) << 8);
+        if (live && (k > 0 || !skipFirst)) bp[k - (skipFirst ? 1 : 0)] = make_uchar2((unsigned char)(v & 0xff), (unsigned char)(v >> 8));
       }
+      stored = ns - ((skipFirst && ns > 0) ? 1 : 0);
+      nb += 2LL * stored;
+      const bool pNegI = (prev & 1u) != 0, pNegQ = (prev & 2u) != 0;
       if (diff && ns > 0) { D.have_prev = 1; D.prevI = pNegI ? -1.f : 1.f; D.prevQ = pNegQ ? -1.f : 1.f; }
       if (wild) {                                         // never in practice; exactness for any input
         K = K0; D = D0; nb = nb0;
@@ -709,9 +719,10 @@ struct DemodEngine {
     if ((reinterpret_cast<uintptr_t>(raw) & 1) || (ld_raw & 1)) return QPSK_ERR_ARG;   // uchar2 stores
     if (fused) {
       QPSK_TRY(mm.ensure_queue(8, s));
-      symsync_decode_kernel<<<(channels + 31) / 32, 64, 0, s>>>(mm.P, mm.d_state.p, mm.d_queue[mm.qcur].p, mm.d_queue[mm.qcur ^ 1].p,
-                                                               mm.qcap, costas.P, costas.d_state.p, d_diff.p, channels, t_rrc.p, L,
-                                                               mf_ld, diff ? 1 : 0, raw, ld_raw, n_raw, d_nsym.p);
+      auto kern = diff ? symsync_decode_kernel<true> : symsync_decode_kernel<false>;
+      kern<<<(channels + 31) / 32, 64, 0, s>>>(mm.P, mm.d_state.p, mm.d_queue[mm.qcur].p, mm.d_queue[mm.qcur ^ 1].p, mm.qcap,
+                                              costas.P, costas.d_state.p, d_diff.p, channels, t_rrc.p, L, mf_ld, raw, ld_raw,
+                                              n_raw, d_nsym.p);
       QPSK_LAUNCH_CHECK();
       mm.qcur ^= 1;
       mm.q_bound = 4;

@@ -169,9 +169,16 @@ __device__ __forceinline__ double flip_sign_if(double x, bool neg) {
 //     m >= -2^-150 (smaller magnitudes round to +-0 and -0.0f >= 0) — this removes an F2F -> FSETP -> FSEL -> F2F chain;
 //   * est = +-1.0, so est*m is an exact sign flip: pe = (+-mq) - (+-mi) (:82);
 //   * both wrap candidates theta -+ 2*pi are formed speculatively and selected (:89-91).
-// the straight-line part: valid while |theta| < 1e5 (the caller checks)
+// |x| >= bound (or NaN) tested on the high word with an integer compare (4-cycle ALU instead of a DSETP on the
+// fp64 pipe); `bound_hi` = high word of a bound whose low word is zero
+__device__ __forceinline__ bool abs_ge_hi(double x, int bound_hi) { return (__double2hiint(x) & 0x7fffffff) >= bound_hi; }
+
+// the straight-line part: valid while |theta| < 1e5 and both mixer outputs are finite and not in the band where the
+// fp32 rounding decides the sign (`wild` reports otherwise and the caller replays through costas_step_exact).
+// sgnI/sgnQ: bit 31 set when the decision on the fp32 output is -1, i.e. when !(out >= 0).
 __device__ __forceinline__ void costas_step_fast(const CostasParams& P, const SinCosK& K, CostasState& S, float inI, float inQ,
-                                                 float& outI, float& outQ) {
+                                                 float& outI, float& outQ, unsigned& sgnI, unsigned& sgnQ, bool& wild) {
+  wild |= abs_ge_hi(S.theta, 0x40F86A00);                    // |theta| >= 1e5 or NaN
   double s, c;
   sincos_fast_f64_k(S.theta, K, &s, &c);
   const double dI = (double)inI, dQ = (double)inQ;
@@ -179,20 +186,28 @@ __device__ __forceinline__ void costas_step_fast(const CostasParams& P, const Si
   const double mq = dQ * c - dI * s;                         // :73
   outI = (float)mi;
   outQ = (float)mq;
-  const bool posI = mi >= -0x1p-150, posQ = mq >= -0x1p-150; // GetSign of the fp32 outputs (:52-56, :76-80)
-  const double pe = flip_sign_if(mq, !posI) - flip_sign_if(mi, !posQ);   // :82
+  // GetSign of the fp32 outputs (:52-56, :76-80) from the fp64 values: (float)m >= 0 exactly when m >= -2^-150
+  // (smaller magnitudes round to +-0 and -0.0f >= 0).  Outside (-2^-149, -0] that is the sign bit of m; that sliver,
+  // Inf and NaN take the replay path, so one AND per output is all that sits on the chain.
+  const int hi_i = __double2hiint(mi), hi_q = __double2hiint(mq);
+  const unsigned ui = (unsigned)hi_i, uq = (unsigned)hi_q;
+  wild |= (ui - 0x80000000u < 0x36A00000u) | ((ui & 0x7fffffffu) >= 0x7ff00000u) |      // -2^-149 < mi <= -0, Inf, NaN
+          (uq - 0x80000000u < 0x36A00000u) | ((uq & 0x7fffffffu) >= 0x7ff00000u);
+  sgnI = (unsigned)hi_i & 0x80000000u;
+  sgnQ = (unsigned)hi_q & 0x80000000u;
+  // pe = estI*mq - estQ*mi with est = +-1.0: the products are exact sign flips (:82)
+  const double a = __hiloint2double(hi_q ^ (int)sgnI, __double2loint(mq));
+  const double b = __hiloint2double(hi_i ^ (int)sgnQ, __double2loint(mi));
+  const double pe = a - b;
   S.freq += P.beta * pe;                                     // :85
   const double t = S.theta + (S.freq + P.alpha * pe);        // :86
   const double kPi = 3.14159265358979323846, kTwoPi = 2.0 * kPi;
   const double t_dn = t - kTwoPi, t_up = t + kTwoPi;
   S.theta = (t > kPi) ? t_dn : ((t < -kPi) ? t_up : t);      // :89-91
 }
-__device__ __forceinline__ void costas_step(const CostasParams& P, const SinCosK& K, CostasState& S, float inI, float inQ,
-                                            float& outI, float& outQ) {
-  if (fabs(S.theta) < 1.0e5) {
-    costas_step_fast(P, K, S, inI, inQ, outI, outQ);
-    return;
-  }
+// exact for every input: the reference's operation order with the library sincos
+__device__ __forceinline__ void costas_step_exact(const CostasParams& P, CostasState& S, float inI, float inQ, float& outI,
+                                                  float& outQ) {
   double s, c;
   sincos(S.theta, &s, &c);
   const double dI = (double)inI, dQ = (double)inQ;
@@ -207,6 +222,17 @@ __device__ __forceinline__ void costas_step(const CostasParams& P, const SinCosK
   const double kPi = 3.14159265358979323846, kTwoPi = 2.0 * kPi;
   if (S.theta > kPi) S.theta -= kTwoPi;
   else if (S.theta < -kPi) S.theta += kTwoPi;
+}
+__device__ __forceinline__ void costas_step(const CostasParams& P, const SinCosK& K, CostasState& S, float inI, float inQ,
+                                            float& outI, float& outQ) {
+  const CostasState S0 = S;
+  unsigned nI, nQ;
+  bool wild = false;
+  costas_step_fast(P, K, S, inI, inQ, outI, outQ, nI, nQ, wild);
+  if (wild) {
+    S = S0;
+    costas_step_exact(P, S, inI, inQ, outI, outQ);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
