@@ -257,9 +257,13 @@ __global__ void __launch_bounds__(64)
       // Absolute (AppendDecisionBits :304-318): b0 = (dI >= 0), b1 = (dQ >= 0).
       constexpr unsigned kB0 = DIFF ? 0x3A5Cu : 0x5555u;   // enumerated from the float formulas (tests compare with the
       constexpr unsigned kB1 = DIFF ? 0x53CAu : 0x3333u;   // unfused decode_kernel, which keeps them)
-      uchar2* bp = bc + (nb >> 1);
-      int stored = 0;
+      // Idle lanes shadow channel C-1 on identical inputs, so their stores duplicate the owner's bytes: no `live`
+      // predicate (and no branch around the store).  When the very first symbol is only a reference, its bits land on
+      // slot 0 and are overwritten by the next symbol's (the pointer is held for one pass).
+      uchar2* p = bc + (nb >> 1);
+      bool hold = skipFirst;
       float2 nxt = sq[0];
+#pragma unroll 2
       for (int k = 0; k < ns; ++k) {
         const float2 in = nxt;
         nxt = sq[k + 1];                                 // row pitch kSsSymCap + 1: in bounds for every k < ns
@@ -269,10 +273,11 @@ __global__ void __launch_bounds__(64)
         const unsigned cur = (sI >> 31) | (sQ >> 30);
         const unsigned idx = cur | (prev << 2);
         prev = cur;
-        const unsigned v = ((kB0 >> idx) & 1u) | (((kB1 >> idx) & 1u) << 8);
-        if (live && (k > 0 || !skipFirst)) bp[k - (skipFirst ? 1 : 0)] = make_uchar2((unsigned char)(v & 0xff), (unsigned char)(v >> 8));
+        *p = make_uchar2((unsigned char)((kB0 >> idx) & 1u), (unsigned char)((kB1 >> idx) & 1u));
+        p += hold ? 0 : 1;
+        hold = false;
       }
-      stored = ns - ((skipFirst && ns > 0) ? 1 : 0);
+      const int stored = ns - ((skipFirst && ns > 0) ? 1 : 0);
       nb += 2LL * stored;
       const bool pNegI = (prev & 1u) != 0, pNegQ = (prev & 2u) != 0;
       if (diff && ns > 0) { D.have_prev = 1; D.prevI = pNegI ? -1.f : 1.f; D.prevQ = pNegQ ? -1.f : 1.f; }
