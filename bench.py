@@ -333,8 +333,8 @@ def main():
             f.reset()
         pcie = copy_ceiling(torch, hin, hout, 1 << 30)
         k_e2e = max(1, min(args.steps, 5))
-        for _, f in filters[:1]:
-            f.Filter(hin.array[: 1 << 20], hout.array[: 1 << 20])
+        for _, f in filters:                                    # one untimed full step: slot buffers, streams, first DMA
+            f.Filter(hin.array, hout.array)
             f.reset()
         barrier()
         step_s = []
