@@ -214,6 +214,82 @@ __device__ __forceinline__ void sincos_fast_f64_k(double x, const SinCosK& K, do
   *sn = __hiloint2double(s_hi, s_lo);
   *cs = __hiloint2double(c_hi, c_lo);
 }
+// fp64 sin/cos of an fp32 ARGUMENT (the FLL's MathF.Sin/Cos(phase)), shortened on the dependency chain:
+//   * k = round(x*2/pi) by the 1.5*2^52 magic-number add (one DFMA + one DADD instead of DMUL + FRND.F64), the
+//     quadrant read from the low word of the same sum (no F2I);
+//   * two Cody-Waite pieces (the third, k*1.5e-33, is below half an ulp of r for every fp32 x != 0: r cannot come
+//     closer than ~1e-9 to a multiple of pi/2);
+//   * eight Taylor coefficients per polynomial (the z^8, z^9 terms are below 2^-56 of the sum for |r| <= pi/4):
+//     Estrin depth 3 instead of 4;  cos tail folded into one DFMA (exact: the compensation term is a multiple of
+//     the product's ulp).
+// Checked on the host (fma(), -ffp-contract=off) against sincos_fast_f64 for EVERY fp32 argument with |x| < 64:
+// bit-identical fp64 results (tools/sincos_check.cpp), so it is a drop-in on the FLL value path.
+struct SinCosF {
+  double two_over_pi, magic, p1, p2;
+  double s[8], c[8];
+  double half, one;
+};
+static __device__ double kSinCosTabF[22] = {
+    0.63661977236758134308, 6755399441055744.0, 1.5707963267948966e+00, 6.123233995736766e-17,
+    -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0, 1.0 / 6227020800.0,
+    -1.0 / 1307674368000.0, 1.0 / 355687428096000.0,
+    1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0,
+    1.0 / 20922789888000.0, -1.0 / 6402373705728000.0,
+    0.5, 1.0};
+// global-memory load ptxas cannot rematerialise (constant-bank loads it re-issues on every use): the value stays in
+// a register pair for the life of the kernel
+__device__ __forceinline__ double ld_global_pinned(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ SinCosF sincos_f_load_consts() {
+  SinCosF K;
+  K.two_over_pi = ld_global_pinned(&kSinCosTabF[0]);
+  K.magic = ld_global_pinned(&kSinCosTabF[1]);
+  K.p1 = ld_global_pinned(&kSinCosTabF[2]);
+  K.p2 = ld_global_pinned(&kSinCosTabF[3]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    K.s[i] = ld_global_pinned(&kSinCosTabF[4 + i]);
+    K.c[i] = ld_global_pinned(&kSinCosTabF[12 + i]);
+  }
+  K.half = ld_global_pinned(&kSinCosTabF[20]);
+  K.one = ld_global_pinned(&kSinCosTabF[21]);
+  return K;
+}
+__device__ __forceinline__ void sincos_f32arg_k(float xf, const SinCosF& K, float* sn, float* cs) {
+  const double x = (double)xf;
+  const double t = fma(x, K.two_over_pi, K.magic);
+  const double k = t - K.magic;
+  const unsigned q = (unsigned)__double2loint(t);          // k mod 2^32 (two's complement)
+  double r = fma(-k, K.p1, x);
+  r = fma(-k, K.p2, r);
+  const double z = r * r, z2 = z * z, z4 = z2 * z2;
+  const double a01 = fma(K.s[1], z, K.s[0]);
+  const double a23 = fma(K.s[3], z, K.s[2]);
+  const double a45 = fma(K.s[5], z, K.s[4]);
+  const double a67 = fma(K.s[7], z, K.s[6]);
+  const double S = fma(fma(a67, z2, a45), z4, fma(a23, z2, a01));
+  const double sr = fma(r * z, S, r);
+  const double d01 = fma(K.c[1], z, K.c[0]);
+  const double d23 = fma(K.c[3], z, K.c[2]);
+  const double d45 = fma(K.c[5], z, K.c[4]);
+  const double d67 = fma(K.c[7], z, K.c[6]);
+  const double Cc = fma(fma(d67, z2, d45), z4, fma(d23, z2, d01));
+  const double hz = K.half * z;
+  const double w = K.one - hz;
+  const double cr = w + fma(z2, Cc, (K.one - w) - hz);
+  const bool swap = (q & 1u) != 0;
+  const unsigned s_flip = (q & 2u) << 30;                   // sign bit when quadrant 2 or 3
+  const unsigned c_flip = ((q + 1u) & 2u) << 30;            // sign bit when quadrant 1 or 2
+  const int sr_hi = __double2hiint(sr), sr_lo = __double2loint(sr);
+  const int cr_hi = __double2hiint(cr), cr_lo = __double2loint(cr);
+  const int s_hi = (swap ? cr_hi : sr_hi) ^ (int)s_flip, s_lo = swap ? cr_lo : sr_lo;
+  const int c_hi = (swap ? sr_hi : cr_hi) ^ (int)c_flip, c_lo = swap ? sr_lo : cr_lo;
+  *sn = (float)__hiloint2double(s_hi, s_lo);
+  *cs = (float)__hiloint2double(c_hi, c_lo);
+}
 // MathF.Sin/Cos model (see sincos_f32_exact) through the register-constant fast path
 __device__ __forceinline__ void sincos_f32_fast_k(float x, const SinCosK& K, float* s, float* c) {
   double sd, cd;

@@ -3,6 +3,8 @@
 // Compiled with --fmad=false (see loops.cuh).
 #include "loops.cuh"
 
+#include <stdlib.h>
+
 namespace qpsk {
 
 constexpr int kLoopThreads = 32;  // one warp per CTA: spreads few streams over many SMs
@@ -373,6 +375,12 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
   if (L == 0) return QPSK_OK;
   if (!x || !y) return QPSK_ERR_NULL;
   if (!s) s = stream;
+  static const bool force_group = [] {
+    const char* e = getenv("QPSK_FLL_IMPL");                 // "group": the single-warp kernels (A/B timing, tests)
+    return e && strcmp(e, "group") == 0;
+  }();
+  if (!force_group && fll_duo_supported(n_taps))
+    return fll_duo_launch(P, d_taps.p, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
   if (FllGroupFn fn = fll_group_pick(n_taps)) {
     // 8 lanes per stream, specialised on the tap count (the default 40-tap and the 10..55-tap filters)
     const int blocks = (channels + kFllCtaStreams - 1) / kFllCtaStreams;

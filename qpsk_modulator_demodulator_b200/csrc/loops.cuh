@@ -252,6 +252,11 @@ struct FllEngine {
   int process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t ldy, cudaStream_t s);
 };
 
+// fll_duo.cu: two-warp (chain + side) FLL kernel for N = 8..48 taps, N % 8 == 0
+bool fll_duo_supported(int n_taps);
+int fll_duo_launch(const FllParams& P, const float* taps, float2* ring, int* head, float2* pf, int C, const float2* x,
+                   float2* y, long long L, long long ldx, long long ldy, cudaStream_t s);
+
 struct MmEngine {
   int channels = 1;
   MmParams P{};
