@@ -290,6 +290,34 @@ __device__ __forceinline__ void sincos_f32arg_k(float xf, const SinCosF& K, floa
   *sn = (float)__hiloint2double(s_hi, s_lo);
   *cs = (float)__hiloint2double(c_hi, c_lo);
 }
+// The same value path with the quadrant fix-up left to the caller: phi = r + q*pi/2, returns (float)sin(r),
+// (float)cos(r) and q mod 2^32.  e^{j phi} = e^{j r} * j^q, and multiplying the INPUT sample by j^q is an exact
+// swap / sign flip that does not wait for the polynomials (see fll_duo.cu), so the selects and sign XORs of
+// sincos_f32arg_k leave the dependency chain.  x is (double)phase, converted by the caller.
+__device__ __forceinline__ void sincos_f32arg_rq(double x, const SinCosF& K, float* sr_out, float* cr_out, unsigned* q_out) {
+  const double t = fma(x, K.two_over_pi, K.magic);
+  const double k = t - K.magic;
+  *q_out = (unsigned)__double2loint(t);
+  double r = fma(-k, K.p1, x);
+  r = fma(-k, K.p2, r);
+  const double z = r * r, z2 = z * z, z4 = z2 * z2;
+  const double a01 = fma(K.s[1], z, K.s[0]);
+  const double a23 = fma(K.s[3], z, K.s[2]);
+  const double a45 = fma(K.s[5], z, K.s[4]);
+  const double a67 = fma(K.s[7], z, K.s[6]);
+  const double S = fma(fma(a67, z2, a45), z4, fma(a23, z2, a01));
+  const double sr = fma(r * z, S, r);
+  const double d01 = fma(K.c[1], z, K.c[0]);
+  const double d23 = fma(K.c[3], z, K.c[2]);
+  const double d45 = fma(K.c[5], z, K.c[4]);
+  const double d67 = fma(K.c[7], z, K.c[6]);
+  const double Cc = fma(fma(d67, z2, d45), z4, fma(d23, z2, d01));
+  const double hz = K.half * z;
+  const double w = K.one - hz;
+  const double cr = w + fma(z2, Cc, (K.one - w) - hz);
+  *sr_out = (float)sr;
+  *cr_out = (float)cr;
+}
 // MathF.Sin/Cos model (see sincos_f32_exact) through the register-constant fast path
 __device__ __forceinline__ void sincos_f32_fast_k(float x, const SinCosK& K, float* s, float* c) {
   double sd, cd;

@@ -23,6 +23,8 @@
 // (phase, freq) stays uniform in the group without a broadcast on the chain.
 #include "loops.cuh"
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 namespace qpsk {
@@ -58,12 +60,58 @@ __device__ __forceinline__ void duo_mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// shared-memory accesses by 32-bit address + compile-time offset.  The chain warp's addresses are pinned in
+// registers (duo_pin): left to itself ptxas recomputes each of them from %tid inside every step (~12 integer
+// instructions per sample on a warp whose issue slots are the bottleneck).
+__device__ __forceinline__ uint32_t duo_pin(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+template <int OFF>
+__device__ __forceinline__ float4 duo_lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float2 duo_lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ void duo_sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void duo_sts64(uint32_t a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "f"(v.x), "f"(v.y) : "memory");
+}
+
+__device__ __forceinline__ bool duo_mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(duo_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 struct DuoSmem {
   float2 ring[kDuoStreams * kDuoRingStride];            // past outputs, slot = sample index & 63
   float4 lp[2][kDuoBatch][32];                          // per batch parity: stale lane partials (loI, loQ, upI, upQ)
   float2 xq[2][kDuoStreams * kDuoXStride];              // input samples, one super-batch per slot
   uint64_t lp_full[2];                                  // side -> chain: batch's partials (and inputs) are in place
   uint64_t out_full[2];                                 // chain -> side: batch's outputs are in the ring
+  float consts[4];                                      // beta, alpha, max_freq, min_freq
+  float4 exch[kDuoStreams * 9];                         // chain warp: lane prefixes of the previous step
+  uint32_t opaque[32];                                  // chain warp: see a_ex_out
 };
 
 // the four sums of one window element: (loI, loQ, upI, upQ) += tap (x) v, the reference's products and order
@@ -76,6 +124,20 @@ __device__ __forceinline__ void duo_acc(float4& a, float ta, float tb, float vx,
   a.w = a.w + (p3 - p4);
 }
 
+// The rare wrap phase = IEEERemainder(phase, 2*pi_f32) (Band-Edge Filter.cs:185-189) in five instructions instead of
+// the inlined remainderf (~80, four copies per batch).  With c = fl32(2*pi) = 13176795 * 2^-21 (odd mantissa) and
+// |phase| > c an fp32 phase is an even multiple of 2^-22 while every tie point (m + 1/2) c is an odd one, so
+// phase / c stays >= 3.8e-8 away from a tie and n = rint(phase * (1/c)) in fp64 is the exact quotient for
+// |n| < 2^20; phase - n*c is then exact in fp64 and (IEEE remainders are representable) in fp32.  A zero result
+// keeps the sign of phase, like remainderf / Math.IEEERemainder.  Checked against remainderf on the host
+// (tools/sincos_check.cpp).  The launcher keeps |phase| < 1e5 for this kernel.
+__device__ __forceinline__ float duo_wrap_phase(float phase, double pd) {
+  const double c = (double)kTwoPiF;
+  const double n = rint(pd * (1.0 / c));
+  const double r = fma(-n, c, pd);
+  return (r == 0.0) ? copysignf(0.f, phase) : (float)r;
+}
+
 template <int K, int PAIRS>
 __global__ void __launch_bounds__(64 * PAIRS)
     fll_duo_kernel(const FllParams P, const float* __restrict__ taps, float2* ring_g, int* head_g, float2* pf_g, int C,
@@ -85,8 +147,10 @@ __global__ void __launch_bounds__(64 * PAIRS)
   __shared__ __align__(16) DuoSmem smem[PAIRS];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int pair = warp >> 1;
-  const bool is_chain = (warp & 1) == 0;
+  // warps 0..PAIRS-1 are the chain warps, PAIRS..2*PAIRS-1 their side warps: with PAIRS = 4 (warps go to the four
+  // schedulers round robin) every scheduler holds one chain warp and one side warp of the CTA
+  const int pair = warp % PAIRS;
+  const bool is_chain = warp < PAIRS;
   DuoSmem& S = smem[pair];
   const int sl = lane >> 3;                                 // stream slot in the pair
   const int g = lane & 7;                                   // reference SIMD lane
@@ -189,87 +253,143 @@ __global__ void __launch_bounds__(64 * PAIRS)
   const SinCosF SK = sincos_f_load_consts();
   const float2 pf = pf_g[c];
   float phase = pf.x, freq = pf.y;
-  float4 Pp = make_float4(0.f, 0.f, 0.f, 0.f);              // this lane's prefix from the previous step
-  const float4* lp7_base = &S.lp[0][0][sl * 8 + 7];
-  // one sample step; WARM: warm-up (the output is read back from the ring, no loop update)
-  auto step = [&](auto warm_tag, long long b, int j) {
-    constexpr bool WARM = decltype(warm_tag)::value;
-    const int n = (int)(4 * b + j) & (kDuoRing - 1);
-    // known before the rotation: stale partials, previous-step prefixes of the neighbours
-    const float4 lpo = S.lp[b & 1][j][lane];
-    const float4 lp7 = lp7_base[((int)(b & 1) * kDuoBatch + j) * 32];
-    float4 Pin, P6;
-    Pin.x = __shfl_up_sync(0xffffffffu, Pp.x, 1, 8);
-    Pin.y = __shfl_up_sync(0xffffffffu, Pp.y, 1, 8);
-    Pin.z = __shfl_up_sync(0xffffffffu, Pp.z, 1, 8);
-    Pin.w = __shfl_up_sync(0xffffffffu, Pp.w, 1, 8);
-    if (!WARM) {
-      P6.x = __shfl_sync(0xffffffffu, Pp.x, 6, 8);
-      P6.y = __shfl_sync(0xffffffffu, Pp.y, 6, 8);
-      P6.z = __shfl_sync(0xffffffffu, Pp.z, 6, 8);
-      P6.w = __shfl_sync(0xffffffffu, Pp.w, 6, 8);
+  double pd = (double)phase;
+  // loop constants in registers: ptxas re-issues constant-bank loads inside the step (a dependent LDC each), so they
+  // take a detour through shared memory with a volatile load it cannot rematerialise
+  float beta, alpha, max_freq, min_freq;
+  {
+    if (lane == 0) {
+      S.consts[0] = P.beta;
+      S.consts[1] = P.alpha;
+      S.consts[2] = P.max_freq;
+      S.consts[3] = P.min_freq;
     }
-    if (g == 0) Pin = make_float4(0.f, 0.f, 0.f, 0.f);       // aLo = 0; aLo += lane 0 (:176-180)
+    __syncwarp();
+    const uint32_t a = duo_smem_u32(S.consts);
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(beta) : "r"(a));
+    asm volatile("ld.volatile.shared.f32 %0, [%1+4];" : "=f"(alpha) : "r"(a));
+    asm volatile("ld.volatile.shared.f32 %0, [%1+8];" : "=f"(max_freq) : "r"(a));
+    asm volatile("ld.volatile.shared.f32 %0, [%1+12];" : "=f"(min_freq) : "r"(a));
+  }
+  // Prefix hand-over between neighbouring lanes: lane g stores its new prefix in slot g+1 of its stream's row and
+  // reads slot g (lane g-1's value of the previous step; slot 0 stays zero: "aLo = 0; aLo += lane 0", :176-180) and
+  // slot 7 (lane 6's: P_6 of the current window).  One STS.128 + two LDS.128 per step instead of eight SHFL.
+  float4* const ex_row = S.exch + sl * 9;
+  if (g == 0) ex_row[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  ex_row[g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  const uint32_t a_ex = duo_pin(duo_smem_u32(ex_row + g));          // lane g-1's prefix
+  // this lane's slot: the address takes a round trip through shared memory (volatile load), so ptxas cannot relate
+  // it to a_ex and has to keep every prefix store ahead of the following loads (see step)
+  uint32_t a_ex_out;
+  {
+    S.opaque[lane] = duo_smem_u32(ex_row + g + 1);
+    __syncwarp();
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(a_ex_out) : "r"(duo_smem_u32(&S.opaque[lane])));
+  }
+  const uint32_t a_p6 = duo_pin(duo_smem_u32(ex_row + 7));          // lane 6's prefix
+  const uint32_t a_lp0 = duo_pin(duo_smem_u32(&S.lp[0][0][lane]));
+  const uint32_t a_l70 = duo_pin(duo_smem_u32(&S.lp[0][0][sl * 8 + 7]));
+  const uint32_t a_xq0 = duo_pin(duo_smem_u32(S.xq[0] + sl * kDuoXStride));
+  const uint32_t a_ring0 = duo_pin(duo_smem_u32(myring));
+  const bool writer = duo_pin((uint32_t)(g == 7)) != 0;
+  constexpr int kLpBatchBytes = kDuoBatch * 32 * 16;                // lp[1] - lp[0]
+  constexpr int kXqSlotBytes = kDuoStreams * kDuoXStride * 8;       // xq[1] - xq[0]
+  // one sample step; WARM: warm-up (the output is read back from the ring, no loop update).  Every shared-memory
+  // address is a per-batch base plus a compile-time offset.
+  auto step = [&](auto warm_tag, auto j_tag, uint32_t a_lp, uint32_t a_l7, uint32_t a_xq, uint32_t a_rn) {
+    constexpr bool WARM = decltype(warm_tag)::value;
+    constexpr int J = decltype(j_tag)::value;
+    // No __syncwarp between a step's prefix store and the next step's loads (it costs ~55 cycles per sample here).
+    // What it would guarantee holds anyway: the warp is converged (the only branch of a step reconverges before the
+    // store) and one warp's shared-memory accesses are performed in issue order; the store and load addresses sit in
+    // separately pinned registers, so ptxas cannot prove them disjoint and keeps the store first.
+    // known before the rotation: stale partials, previous-step prefixes of the neighbours
+    const float4 lpo = duo_lds128<J * 512>(a_lp);
+    const float4 Pin = duo_lds128<0>(a_ex);
     float oI, oQ;
+    float4 P6, L7;
     if (WARM) {
-      const float2 o = myring[n];                            // outputs of earlier calls
+      const float2 o = duo_lds64<J * 8>(a_rn);               // outputs of earlier calls
       oI = o.x;
       oQ = o.y;
     } else {
-      float s, co;
-      sincos_f32arg_k(phase, SK, &s, &co);                   // MathF.Cos/Sin(phase) :108-109
-      const float2 in = (S.xq[(b >> 2) & 1] + sl * kDuoXStride + (int)(b & 3) * kDuoBatch)[j];
-      oI = in.x * co - in.y * s;                             // :111
-      oQ = in.x * s + in.y * co;                             // :112
+      P6 = duo_lds128<0>(a_p6);
+      L7 = duo_lds128<J * 512>(a_l7);
+      const float2 in = duo_lds64<J * 8>(a_xq);
+      // MathF.Cos/Sin(phase) :108-109 and the rotation :111-112, with phase = r + q*pi/2 and the exact factor j^q
+      // applied to the input sample while the polynomials run:  out = (in * j^q) * (cos r + j sin r).  Same two
+      // products per component as in.x*cos - in.y*sin / in.x*sin + in.y*cos (signs are exact, a + b == b + a).
+      float sr, cr;
+      unsigned q;
+      sincos_f32arg_rq(pd, SK, &sr, &cr, &q);
+      const bool odd = (q & 1u) != 0;
+      const unsigned fx = ((q + 1u) & 2u) << 30;             // sign of the first component: quadrants 1, 2
+      const unsigned fy = (q & 2u) << 30;                    // sign of the second: quadrants 2, 3
+      const float ax = __uint_as_float(__float_as_uint(odd ? in.y : in.x) ^ fx);
+      const float ay = __uint_as_float(__float_as_uint(odd ? in.x : in.y) ^ fy);
+      oI = ax * cr - ay * sr;
+      oQ = ax * sr + ay * cr;
     }
     // this lane's newest element completes L_g of window n+7-g; extend that window's prefix
     float4 Lg = lpo;
     duo_acc(Lg, tA, tB, oI, oQ);
-    Pp.x = Pin.x + Lg.x;
-    Pp.y = Pin.y + Lg.y;
-    Pp.z = Pin.z + Lg.z;
-    Pp.w = Pin.w + Lg.w;
+    float4 Pn;
+    Pn.x = Pin.x + Lg.x;
+    Pn.y = Pin.y + Lg.y;
+    Pn.z = Pin.z + Lg.z;
+    Pn.w = Pin.w + Lg.w;
     if (!WARM) {
       // lane 7's role for the current window, on every lane: acc = P_6(n) + L_7(n)
-      float4 L7 = lp7;
       duo_acc(L7, nA, nBq, oI, oQ);
       const float aLoI = P6.x + L7.x, aLoQ = P6.y + L7.y, aUpI = P6.z + L7.z, aUpQ = P6.w + L7.w;
       const float powUpper = aUpI * aUpI + aUpQ * aUpQ;      // :118
       const float powLower = aLoI * aLoI + aLoQ * aLoQ;      // :119
       const float error = powLower - powUpper;               // :121
-      freq += P.beta * error;                                // :124
-      phase += freq + P.alpha * error;                       // :125
-      if (g == 7) myring[n] = make_float2(oI, oQ);
-      if (phase > kTwoPiF || phase < -kTwoPiF) phase = remainderf(phase, kTwoPiF);   // :185-189
-      if (freq > P.max_freq) freq = P.max_freq;              // :191-195
-      else if (freq < P.min_freq) freq = P.min_freq;
+      freq += beta * error;                                  // :124
+      phase += freq + alpha * error;                         // :125
+      // converted before the wrap test resolves (the wrap is rare); volatile so the two conversions are not merged
+      // into one after the branch
+      asm volatile("cvt.f64.f32 %0, %1;" : "=d"(pd) : "f"(phase));
+      if (writer) duo_sts64<J * 8>(a_rn, make_float2(oI, oQ));
+      if (phase > kTwoPiF || phase < -kTwoPiF) {             // :185-189
+        phase = duo_wrap_phase(phase, pd);
+        asm volatile("cvt.f64.f32 %0, %1;" : "=d"(pd) : "f"(phase));
+      }
+      freq = (freq > max_freq) ? max_freq : ((freq < min_freq) ? min_freq : freq);   // :191-195
     }
+    duo_sts128<0>(a_ex_out, Pn);
   };
   auto batch_done = [&](long long b) {
     __syncwarp();
     if (lane == 0) duo_mbar_arrive(&S.out_full[b & 1]);
   };
   auto batch_wait = [&](long long b) { duo_mbar_wait(&S.lp_full[b & 1], (uint32_t)(((b + 2) >> 1) & 1)); };
+  // non-blocking probe of a later batch's barrier, issued mid-batch so that its latency hides under the chain
+  auto batch_probe = [&](long long b) { return duo_mbar_test(&S.lp_full[b & 1], (uint32_t)(((b + 2) >> 1) & 1)); };
+  bool ready = false;
+  using J0 = std::integral_constant<int, 0>;
+  using J1 = std::integral_constant<int, 1>;
+  using J2 = std::integral_constant<int, 2>;
+  using J3 = std::integral_constant<int, 3>;
+  auto batch = [&](auto warm_tag, long long b, int ns) {
+    if (!ready) batch_wait(b);
+    const uint32_t par = (uint32_t)(b & 1);
+    const uint32_t a_lp = duo_pin(a_lp0 + par * kLpBatchBytes), a_l7 = duo_pin(a_l70 + par * kLpBatchBytes);
+    const uint32_t a_xq = duo_pin(a_xq0 + (uint32_t)((b >> 2) & 1) * kXqSlotBytes + (uint32_t)(b & 3) * (kDuoBatch * 8));
+    const uint32_t a_rn = duo_pin(a_ring0 + ((uint32_t)(4 * b) & (kDuoRing - 1)) * 8);
+    step(warm_tag, J0{}, a_lp, a_l7, a_xq, a_rn);
+    if (ns > 1) step(warm_tag, J1{}, a_lp, a_l7, a_xq, a_rn);
+    ready = batch_probe(b + 1);                              // (a barrier never used again just reads "not ready")
+    if (ns > 2) step(warm_tag, J2{}, a_lp, a_l7, a_xq, a_rn);
+    if (ns > 3) step(warm_tag, J3{}, a_lp, a_l7, a_xq, a_rn);
+    batch_done(b);
+  };
   // warm-up: fills the prefix pipeline from the outputs of earlier calls (steps -8..-1)
-  for (long long b = -2; b < 0; ++b) {
-    batch_wait(b);
-#pragma unroll
-    for (int j = 0; j < kDuoBatch; ++j) step(std::true_type{}, b, j);
-    batch_done(b);
-  }
+  for (long long b = -2; b < 0; ++b) batch(std::true_type{}, b, kDuoBatch);
   const long long nFull = L / kDuoBatch;
-  for (long long b = 0; b < nFull; ++b) {
-    batch_wait(b);
-#pragma unroll
-    for (int j = 0; j < kDuoBatch; ++j) step(std::false_type{}, b, j);
-    batch_done(b);
-  }
-  if (nFull < nB) {
-    batch_wait(nFull);
-    const int ns = (int)(L - 4 * nFull);
-    for (int j = 0; j < ns; ++j) step(std::false_type{}, nFull, j);
-    batch_done(nFull);
-  }
+  for (long long b = 0; b < nFull; ++b) batch(std::false_type{}, b, kDuoBatch);
+  if (nFull < nB) batch(std::false_type{}, nFull, (int)(L - 4 * nFull));
   if (live && g == 0) pf_g[c] = make_float2(phase, freq);
 }
 
@@ -295,7 +415,18 @@ bool fll_duo_supported(int n_taps) { return n_taps >= 8 && n_taps <= 48 && (n_ta
 
 int fll_duo_launch(const FllParams& P, const float* taps, float2* ring, int* head, float2* pf, int C, const float2* x,
                    float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {
-  return launch_duo<1>(P.n_taps / 8, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+  static const int pairs_env = [] {
+    const char* e = getenv("QPSK_FLL_PAIRS");                // 1, 2 or 4 warp pairs per CTA (timing experiments)
+    return e ? atoi(e) : 0;
+  }();
+  // measured on a B200 (tools/fll_only.py, 40 taps): up to ~1300 streams one pair per CTA spreads the chain warps
+  // over all SMs (356 cycles per sample at 1024 streams against 421); beyond that four pairs per CTA, one chain and
+  // one side warp per scheduler, keep two chain warps off the same scheduler (4096 streams: 580 against 724)
+  const int pairs = pairs_env ? pairs_env : (C <= 1280 ? 1 : 4);
+  const int K = P.n_taps / 8;
+  if (pairs == 1) return launch_duo<1>(K, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+  if (pairs == 2) return launch_duo<2>(K, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+  return launch_duo<4>(K, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
 }
 
 }  // namespace qpsk

@@ -379,9 +379,14 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
     const char* e = getenv("QPSK_FLL_IMPL");                 // "group": the single-warp kernels (A/B timing, tests)
     return e && strcmp(e, "group") == 0;
   }();
-  if (!force_group && fll_duo_supported(n_taps))
+  // The two-warp kernel evaluates sin/cos and the phase wrap with short-range formulas (|phase| < 1e5): the loop
+  // keeps |phase| <= 2*pi + max|freq|, so only a caller-set state or an absurd frequency limit (sps < 1e-3) can
+  // leave that range — those calls take the generic kernels, which use the library routines.
+  const bool wild = state_wild || !(P.max_freq < 1e4f);
+  state_wild = false;                                          // any kernel leaves the state wrapped and clamped
+  if (!force_group && !wild && fll_duo_supported(n_taps))
     return fll_duo_launch(P, d_taps.p, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
-  if (FllGroupFn fn = fll_group_pick(n_taps)) {
+  if (FllGroupFn fn = wild ? nullptr : fll_group_pick(n_taps)) {
     // 8 lanes per stream, specialised on the tap count (the default 40-tap and the 10..55-tap filters)
     const int blocks = (channels + kFllCtaStreams - 1) / kFllCtaStreams;
     fn<<<blocks, kFllCtaThreads, 0, s>>>(P, d_taps.p, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy);
@@ -657,7 +662,11 @@ int qpsk_fll_set_state(qpsk_fll* f, const float* phase, const float* freq) {
   QPSK_TRY(ensure_device());
   FllEngine& e = f->eng;
   std::vector<float2> h((size_t)e.channels);
-  for (int c = 0; c < e.channels; ++c) h[(size_t)c] = make_float2(phase[c], freq[c]);
+  e.state_wild = false;
+  for (int c = 0; c < e.channels; ++c) {
+    h[(size_t)c] = make_float2(phase[c], freq[c]);
+    if (!(fabsf(phase[c]) < 1e4f) || !(fabsf(freq[c]) < 1e4f)) e.state_wild = true;   // see FllEngine::process_dev
+  }
   QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
   QPSK_CUDA_TRY(cudaMemcpy(e.d_pf.p, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
   return QPSK_OK;

@@ -246,6 +246,7 @@ struct FllEngine {
   DevBuf<float2> d_ring;     // [N][C] ring of past outputs
   DevBuf<int> d_head;        // [C]
   DevBuf<float2> d_pf;       // [C] (phase, freq)
+  bool state_wild = false;   // a caller-set (phase, freq) outside the fast kernel's range is pending
   cudaStream_t stream = nullptr;
   ~FllEngine();
   int init(float sps, float rolloff, int size, float bw, int channels_in);

@@ -70,6 +70,41 @@ def test_fll_batch_and_state(gpu, orc):
     assert _close(g1.Process(x[0]), o1.Process(x[0]))
 
 
+@pytest.mark.parametrize("size", [40, 16, 8, 48])
+def test_fll_two_warp_kernel_sizes_and_chunking(gpu, orc, size):
+    """N % 8 == 0 takes the two-warp kernel (csrc/fll_duo.cu): odd chunk lengths exercise the partial last batch,
+    the warm-up from the carried ring and the flush bookkeeping; outputs and state must stay bit-identical."""
+    x, _ = _qpsk_burst(orc, 900, sps=4, alpha=0.35, cfo=0.03, noise=0.05, seed=size)
+    want_f = orc.FLLBandEdgeFilter(4.0, 0.35, size, 0.05)
+    got_f = gpu.FLLBandEdgeFilter(4.0, 0.35, size, 0.05)
+    cuts = [0, 2, 2 * 4, 2 * 9, 2 * 28, 2 * 61, 2 * 62, 2 * 200, 2 * 777, x.size]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        want = want_f.Process(x[a:b])
+        got = got_f.Process(x[a:b])
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (size, a, b)
+    assert got_f.state == want_f.state
+
+
+def test_fll_phase_wrap_and_wild_state(gpu, orc):
+    """A large loop bandwidth drives the phase past +-2*pi every few samples (the wrap path, Band-Edge Filter.cs:185-189);
+    a caller-set phase far outside the loop's range must take the generic kernel and still match."""
+    x, _ = _qpsk_burst(orc, 600, sps=2, alpha=0.5, cfo=0.2, noise=0.02, seed=5)
+    for state in [None, (3.0e4, 0.5), (-7.0, -3.0)]:
+        want_f = orc.FLLBandEdgeFilter(2.0, 0.5, 40, 0.5)
+        got_f = gpu.FLLBandEdgeFilter(2.0, 0.5, 40, 0.5)
+        if state is not None:
+            want_f.state = state
+            got_f.state = state
+        for a, b in [(0, 2 * 301), (2 * 301, x.size)]:
+            want = want_f.Process(x[a:b])
+            got = got_f.Process(x[a:b])
+            assert _close(got, want)
+            assert np.mean(got.view(np.uint32) == want.view(np.uint32)) > 0.999
+        pw, fw = want_f.state
+        pg, fg = got_f.state
+        assert abs(pw - pg) <= 1e-4 * max(1.0, abs(pw)) and abs(fw - fg) <= 1e-5 * max(abs(fw), 1e-3)
+
+
 def test_fll_errors(gpu, orc):
     for mod in (gpu, orc):
         for args in [(0.0, 0.5, 10, 0.1), (2.0, -0.1, 10, 0.1), (2.0, 1.5, 10, 0.1), (2.0, 0.5, 0, 0.1), (2.0, 0.5, 10, 0.0)]:

@@ -56,7 +56,25 @@ template <int V> void run(const char* name) {
   }
   printf("%s: total %lld, fp32 mismatches sin %lld cos %lld, fp64 diffs %lld\n", name, tot, bad_s, bad_c, bad64);
 }
+// csrc/fll_duo.cu duo_wrap_phase vs remainderf, every fp32 with 2*pi < |x| < 1e5
+static void check_wrap() {
+  const float cf = 6.2831854820251464844f;
+  const double c = cf;
+  long long bad = 0, n = 0;
+  #pragma omp parallel for reduction(+:bad,n) schedule(static)
+  for (uint32_t b = 0x40C90FDBu; b < 0x47C35000u; ++b)
+    for (int sg = 0; sg < 2; ++sg) {
+      uint32_t bb = b | (sg ? 0x80000000u : 0);
+      float x; memcpy(&x, &bb, 4);
+      const float want = remainderf(x, cf);
+      const double pd = x, nn = rint(pd * (1.0 / c)), r = fma(-nn, c, pd);
+      const float got = (r == 0.0) ? copysignf(0.f, x) : (float)r;
+      bad += memcmp(&want, &got, 4) != 0; n++;
+    }
+  printf("wrap: %lld args, mismatches vs remainderf %lld\n", n, bad);
+}
 int main() {
+  check_wrap();
   long long ds=0,dc=0,n=0;
   #pragma omp parallel for reduction(+:ds,dc,n) schedule(dynamic,1)
   for (int blk = 0; blk < 512; ++blk) {
