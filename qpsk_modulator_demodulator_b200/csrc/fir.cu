@@ -153,6 +153,30 @@ __device__ __forceinline__ void fir_block(const float2* __restrict__ xnext, cons
   }
 }
 
+// Tile walk of a persistent CTA: tile = blockIdx.x + it*gridDim.x split into (channel, tile within the channel)
+// incrementally — one division per kernel instead of one per tile (a 64-bit division costs ~70 instructions and a
+// dependent I2F / MUFU.RCP / F2I chain in front of every tile's first LDS).
+struct TileWalk {
+  long long tile;
+  int ch, k, tiles_per_ch, step_ch, step_k;
+  __device__ __forceinline__ explicit TileWalk(int tpc) : tiles_per_ch(tpc) {
+    tile = blockIdx.x;
+    ch = (int)(blockIdx.x / (unsigned)tpc);
+    k = (int)(blockIdx.x - (unsigned)ch * (unsigned)tpc);
+    step_ch = (int)(gridDim.x / (unsigned)tpc);
+    step_k = (int)(gridDim.x - (unsigned)step_ch * (unsigned)tpc);
+  }
+  __device__ __forceinline__ void next() {
+    tile += gridDim.x;
+    ch += step_ch;
+    k += step_k;
+    if (k >= tiles_per_ch) {
+      k -= tiles_per_ch;
+      ++ch;
+    }
+  }
+};
+
 // NT compute threads (NT/32 consumer warps) + one producer warp.  No CTA-wide barrier in the steady
 // state: the input ring is handed over with full/empty mbarriers, and every consumer warp stages
 // and TMA-stores its own 32*R outputs, so warps drift apart and their prologues/epilogues overlap the
@@ -190,12 +214,11 @@ __global__ void __launch_bounds__(NT + 32, 2)
     // (stateless) or past its end.
     int stage = 0;
     uint32_t parity = 0;
-    for (int it = 0;; ++it) {
-      const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
-      if (tile >= a.total_tiles) break;
+    TileWalk w(a.tiles_per_ch);
+    for (int it = 0; w.tile < a.total_tiles; ++it, w.next()) {
       if (it >= a.stages) mbar_wait(&empty[stage], parity ^ 1u);   // consumers released this slot
-      const int ch = (int)(tile / a.tiles_per_ch);
-      const int k = (int)(tile - (long long)ch * a.tiles_per_ch);
+      const int ch = w.ch;
+      const int k = w.k;
       const long long n0 = (long long)k * T;
       const long long s0 = n0 + a.advance - a.HL;  // stream index of xs[0] (even)
       float2* dst = xs_base + (size_t)stage * a.stage_elems;
@@ -239,14 +262,13 @@ __global__ void __launch_bounds__(NT + 32, 2)
   float2* ys_warp = ys_base + (size_t)warp * (2 * WS);   // two buffers of WS outputs
   int stage = 0;
   uint32_t parity = 0;
-  for (int it = 0;; ++it) {
-    const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
-    if (tile >= a.total_tiles) break;
+  TileWalk tw(a.tiles_per_ch);
+  for (int it = 0; tw.tile < a.total_tiles; ++it, tw.next()) {
     mbar_wait(&full[stage], parity);
     const float2* xs = xs_base + (size_t)stage * a.stage_elems;
 
-    const int ch = (int)(tile / a.tiles_per_ch);
-    const int k = (int)(tile - (long long)ch * a.tiles_per_ch);
+    const int ch = tw.ch;
+    const int k = tw.k;
     const long long n0 = (long long)k * T;
     const long long left = a.L - n0;
     const int valid = (int)(left < (long long)T ? left : (long long)T);
