@@ -112,7 +112,10 @@ __global__ void __launch_bounds__(64)
     symsync_decode_kernel(const MmParams MP, MmState* mm_g, const float2* __restrict__ q_in, float2* __restrict__ q_out,
                           long long qcap, const CostasParams CP, CostasState* cst_g, DiffState* dst_g, int C,
                           const float2* __restrict__ x, long long L, long long ldx, uint8_t* __restrict__ bits,
-                          long long ld_bits, long long* n_bits, int* n_sym_g) {
+                          long long ld_bits, long long* n_bits, int* n_sym_g, int append) {
+  // append != 0: this launch continues a call split into time chunks (DemodEngine::bits_dev): bits and counts go on
+  // from where the previous chunk left them.  A chunk boundary on a multiple of kSsBlock samples is exactly a round
+  // boundary of the single launch (same carried samples, same rebased base_index), so the split is bit-neutral.
   constexpr bool diff = DIFF;
   __shared__ SsSmem sm;
   const int lane = threadIdx.x & 31;
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(64)
   const SinCosK SK = sincos_load_consts();
   CostasState K;
   DiffState D;
-  long long nb = 0;
+  long long nb = (append && role == 1) ? n_bits[c] : 0;
   uchar2* bc = reinterpret_cast<uchar2*>(bits + (long long)c * ld_bits);
 
   auto stage = [&](int r) {                          // lane i copies sample 32r+i of every channel of the CTA
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(64)
 
   if (role == 0) {
     S = mm_g[c];
+    if (append) n_sym = n_sym_g[c];
     carried = S.queued;                              // host guarantees <= kSsCarry
     for (int i = 0; i < carried; ++i) sm.carry[lane * kSsCarry + i] = q_in[(long long)c * qcap + i];
     if (rounds > 0) stage(0);
@@ -623,9 +627,15 @@ struct DemodEngine {
   int64_t mf_ld = 0;
   bool fuse = true;            // use symsync_decode_kernel when it applies
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;               // front-end stream of the time-chunk pipeline
+  cudaEvent_t ev_in = nullptr;
+  std::vector<cudaEvent_t> ev_chunk;
 
   ~DemodEngine() {
     if (stream) cudaStreamDestroy(stream);
+    if (side) cudaStreamDestroy(side);
+    if (ev_in) cudaEventDestroy(ev_in);
+    for (cudaEvent_t e : ev_chunk) cudaEventDestroy(e);
   }
 
   int init(int fs, int rs, float alpha, int span, double sym_bw, double costas_bw, double cfo_bw, int diff_in,
@@ -699,6 +709,30 @@ struct DemodEngine {
     return QPSK_OK;
   }
 
+  // Time-chunk pipeline of bits_dev (FLL path): number of chunks for an L-sample call.  QPSK_DEMOD_CHUNKS overrides
+  // (1 = off).  Short calls and small batches stay on one stream: the split costs two launches and a warm-up per chunk.
+  int pipeline_chunks(int64_t L) const {
+    static const int env = [] {
+      const char* e = getenv("QPSK_DEMOD_CHUNKS");
+      return e ? atoi(e) : 0;
+    }();
+    int n = env > 0 ? env : 4;
+    if (n > 16) n = 16;
+    if (env <= 0 && (channels < 256 || L < 2048)) n = 1;
+    while (n > 1 && L < (int64_t)n * 8 * kSsBlock) --n;
+    return n;
+  }
+  int ensure_pipeline(int chunks) {
+    if (!side) QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    if (!ev_in) QPSK_CUDA_TRY(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    while ((int)ev_chunk.size() < chunks) {
+      cudaEvent_t e = nullptr;
+      QPSK_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev_chunk.push_back(e);
+    }
+    return QPSK_OK;
+  }
+
   // the fused MM -> Costas -> decode kernel applies when no call can run out of output room and the MM
   // queue holds at most kSsCarry samples (always true once every call has had room)
   bool can_fuse() const { return fuse && (sps - 0.1 > 1.0) && mm.q_bound <= kSsCarry; }
@@ -710,7 +744,18 @@ struct DemodEngine {
       return QPSK_OK;
     }
     const bool fused = can_fuse();
-    QPSK_TRY(front(x, L, ldx, s, !fused));
+    const int chunks = (fused && use_fll) ? pipeline_chunks(L) : 1;
+    if (chunks > 1) {
+      // sizes only; the front end runs chunk by chunk below
+      const int64_t ld = L + (L & 1);
+      QPSK_TRY(t_rrc.ensure((size_t)ld * channels));
+      QPSK_TRY(t_fll.ensure((size_t)ld * channels));
+      sym_ld = symbols_bound(L);
+      if (sym_ld < 1) sym_ld = 1;
+      mf_ld = ld;
+    } else {
+      QPSK_TRY(front(x, L, ldx, s, !fused));
+    }
     const long long need = 2 * sym_ld;
     if (ld_out < need) return QPSK_ERR_CAPACITY;
     uint8_t* raw = out;
@@ -722,12 +767,36 @@ struct DemodEngine {
       raw = d_raw.p; ld_raw = ldr; n_raw = d_nraw.p;
     }
     if ((reinterpret_cast<uintptr_t>(raw) & 1) || (ld_raw & 1)) return QPSK_ERR_ARG;   // uchar2 stores
-    if (fused) {
+    if (fused && chunks > 1) {
+      // FLL -> MF of time chunk t+1 on the side stream while MM -> Costas -> decode of chunk t runs on the caller's:
+      // every stage carries its state from chunk to chunk exactly (FLL ring/phase, MF delay line, MM queue, Costas,
+      // differential reference), so the split changes nothing but the schedule.
+      QPSK_TRY(mm.ensure_queue(8, s));
+      QPSK_TRY(ensure_pipeline(chunks));
+      auto kern = diff ? symsync_decode_kernel<true> : symsync_decode_kernel<false>;
+      const int64_t step = ((L + chunks - 1) / chunks + kSsBlock - 1) / kSsBlock * kSsBlock;
+      QPSK_CUDA_TRY(cudaEventRecord(ev_in, s));
+      QPSK_CUDA_TRY(cudaStreamWaitEvent(side, ev_in, 0));     // inputs (and the previous call) are complete
+      int t = 0;
+      for (int64_t n0 = 0; n0 < L; n0 += step, ++t) {
+        const int64_t len = (L - n0 < step) ? (L - n0) : step;
+        QPSK_TRY(fll.process_dev(x + n0, t_fll.p + n0, len, ldx, mf_ld, side));        // the call at :359
+        QPSK_TRY(mf.filter_dev(t_fll.p + n0, t_rrc.p + n0, len, mf_ld, mf_ld, side));  // :360
+        QPSK_CUDA_TRY(cudaEventRecord(ev_chunk[(size_t)t], side));
+        QPSK_CUDA_TRY(cudaStreamWaitEvent(s, ev_chunk[(size_t)t], 0));
+        kern<<<(channels + 31) / 32, 64, 0, s>>>(mm.P, mm.d_state.p, mm.d_queue[mm.qcur].p, mm.d_queue[mm.qcur ^ 1].p,
+                                                mm.qcap, costas.P, costas.d_state.p, d_diff.p, channels, t_rrc.p + n0, len,
+                                                mf_ld, raw, ld_raw, n_raw, d_nsym.p, t > 0 ? 1 : 0);
+        QPSK_LAUNCH_CHECK();
+        mm.qcur ^= 1;
+      }
+      mm.q_bound = 4;
+    } else if (fused) {
       QPSK_TRY(mm.ensure_queue(8, s));
       auto kern = diff ? symsync_decode_kernel<true> : symsync_decode_kernel<false>;
       kern<<<(channels + 31) / 32, 64, 0, s>>>(mm.P, mm.d_state.p, mm.d_queue[mm.qcur].p, mm.d_queue[mm.qcur ^ 1].p, mm.qcap,
                                               costas.P, costas.d_state.p, d_diff.p, channels, t_rrc.p, L, mf_ld, raw, ld_raw,
-                                              n_raw, d_nsym.p);
+                                              n_raw, d_nsym.p, 0);
       QPSK_LAUNCH_CHECK();
       mm.qcur ^= 1;
       mm.q_bound = 4;

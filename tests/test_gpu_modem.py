@@ -253,6 +253,39 @@ def test_demod_full_chain_with_fll_matches_oracle(gpu, orc):
     assert abs(ws["costas_theta"] - gs["costas_theta"]) <= 1e-5 * max(1.0, abs(ws["costas_theta"]))
 
 
+def test_demod_fll_time_chunk_pipeline_matches_oracle(gpu, orc):
+    """256 channels x 5700 samples with the FLL on: bits_dev splits the call into time chunks (FLL -> MF of chunk t+1 on
+    a side stream, MM -> Costas -> decode of chunk t on the caller's).  Every channel must still equal its own
+    single-stream oracle, over two calls (state carried), with a call length that is not a multiple of the chunk."""
+    fs, rs, Cn = 2000, 1000, 256
+    rng = np.random.default_rng(11)
+    rows = []
+    for c in range(Cn):
+        payload = bytes(rng.integers(0, 256, 700, dtype=np.uint8))
+        x = orc.QPSKModulator(fs, rs, 0.35, 10, True, TSC).ModulateBytes(payload, b"<<", b">>")
+        z = (x[0::2] + 1j * x[1::2]) * np.exp(1j * (0.05 * c + 2e-4 * (c % 17) * np.arange(x.size // 2)))
+        z = z + 0.01 * (rng.standard_normal(z.size) + 1j * rng.standard_normal(z.size))
+        y = np.empty_like(x)
+        y[0::2], y[1::2] = z.real, z.imag
+        rows.append(y)
+    L = min(r.size for r in rows)
+    Y = np.stack([r[:L] for r in rows]).astype(np.float32)
+    assert L // 2 >= 5000
+    kw = dict(RrcAlpha=float(np.float32(0.35)), rrcSpan=10, SymbolSyncBandwith=0.002, CostasLoopBandwith=120.0,
+              CFOLoopBandwith=float(np.float32(0.01)), use_fll=True)   # no TSC strip: the raw bit stream is compared
+    gd = gpu.QPSKDeModulator(fs, rs, channels=Cn, **kw)
+    gd.set_fir_mode(gpu.FIR_EXACT)
+    cut = 2 * 2237                                    # both calls are long enough to be split (>= 2048 samples)
+    got = [gd.DeModulate(np.ascontiguousarray(Y[:, :cut])), gd.DeModulate(np.ascontiguousarray(Y[:, cut:]))]
+    bad = 0
+    for c in range(Cn):
+        od = orc.QPSKDeModulator(fs, rs, **kw)
+        want = [od.DeModulate(Y[c, :cut]), od.DeModulate(Y[c, cut:])]
+        bad += (want[0] != got[0][c]) + (want[1] != got[1][c])
+    assert bad == 0
+    assert min(len(g) for g in got[0]) > 2000 and min(len(g) for g in got[1]) > 2000
+
+
 def test_demod_batch_channels_match_single_streams(gpu, orc):
     fs, rs, Cn = 4000, 1000, 6
     xs = []
