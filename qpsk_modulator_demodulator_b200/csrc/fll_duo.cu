@@ -89,6 +89,22 @@ __device__ __forceinline__ void duo_sts64(uint32_t a, float2 v) {
   asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "f"(v.x), "f"(v.y) : "memory");
 }
 
+// side-warp wait: try_wait with a suspend-time hint, so the waiting warp sleeps in hardware until the phase completes
+// (or ~2 us pass) instead of spinning through the issue slots of a chain warp on the same scheduler
+__device__ __forceinline__ void duo_mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(duo_smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "memory");
+  } while (!ok);
+}
 __device__ __forceinline__ bool duo_mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -195,7 +211,7 @@ __global__ void __launch_bounds__(64 * PAIRS)
     if (g + 8 < L) xr1 = xc[g + 8];
     long long flushed = 0;
     for (long long b = -2; b < nB; ++b) {
-      if (b >= 0) duo_mbar_wait(&S.out_full[b & 1], (uint32_t)((b >> 1) & 1));   // chain finished batch b-2
+      if (b >= 0) duo_mbar_wait_sleepy(&S.out_full[b & 1], (uint32_t)((b >> 1) & 1));   // chain finished batch b-2
       if (b >= 0 && (b & 3) == 0) {
         const long long sb = b >> 2;
         float2* q = S.xq[sb & 1] + sl * kDuoXStride;
@@ -236,7 +252,7 @@ __global__ void __launch_bounds__(64 * PAIRS)
     // the chain's last batch
     {
       const long long bl = nB - 1;
-      duo_mbar_wait(&S.out_full[bl & 1], (uint32_t)(((bl + 2) >> 1) & 1));
+      duo_mbar_wait_sleepy(&S.out_full[bl & 1], (uint32_t)(((bl + 2) >> 1) & 1));
     }
     if (live) {
       for (long long i = flushed + g; i < L; i += 8) yc[i] = myring[(int)i & (kDuoRing - 1)];
