@@ -107,26 +107,60 @@ __device__ __forceinline__ unsigned chunk_codes(const ModArgs& a, int f, long lo
   return c;
 }
 
+// one warp per tile (8 tiles per CTA): every lane sums the rotations of its 8-symbol chunks lane, lane+32, ...
+// (the first version spent a 256-thread CTA on a tile, 16 payload bits per thread: 2.1 M warps for 134 MB)
 __global__ void __launch_bounds__(kModThreads) mod_tile_rot_kernel(const ModArgs a) {
-  const int f = blockIdx.y, t = blockIdx.x;
+  const int f = blockIdx.y;
+  const int t = blockIdx.x * (kModThreads / 32) + (threadIdx.x >> 5);
+  if (t >= a.tiles) return;
+  const int lane = threadIdx.x & 31;
   const long long D0 = (long long)t * a.TD;
-  int s = 0;
-  if (8 * (int)threadIdx.x < a.TD) {
-    unsigned c = chunk_codes(a, f, D0 + 8 * threadIdx.x);
+  unsigned s = 0;
+  // Interior tiles (all TD dibits inside the payload bytes, dibits byte-aligned): the sum of the 2-bit rotation codes
+  // does not depend on the order of the dibits, so the bytes are summed 16 per lane as 32-bit words (aligned loads +
+  // funnel shifts), code = v ^ ((v >> 1) & 0x5555...) per field exactly as in chunk_codes.
+  if (a.mode == 0 && a.diff && (a.n_tsc & 7) == 0 && (a.TD & 3) == 0) {
+    const long long k0 = 2 * D0 - a.n_tsc;                   // first framed bit of the tile
+    const long long pb = (k0 >> 3) - a.n_start;              // its payload byte
+    const int nbytes = a.TD >> 2;
+    if (k0 >= 0 && (k0 & 7) == 0 && pb >= 0 && pb + nbytes <= a.n_payload) {
+      const uint8_t* q = a.payload + (long long)f * a.n_payload + pb;
+      const int off = (int)(reinterpret_cast<uintptr_t>(q) & 3u);
+      const int sh = 8 * off;
+      const uint32_t* qa = reinterpret_cast<const uint32_t*>(q - off);         // aligned word holding q[0]
+      for (int b0 = 16 * lane; b0 < nbytes; b0 += 512) {
+        const int nb = (nbytes - b0 < 16) ? (nbytes - b0) : 16;               // bytes of this lane's piece
+        const uint32_t* w = qa + (b0 >> 2);
+        uint32_t cur = w[0];                                                  // holds q[b0]
+        for (int i = 0; 4 * i < nb; ++i) {
+          const int left = nb - 4 * i;
+          const int take = left < 4 ? left : 4;
+          // w[i+1] is read only when it holds a byte of the piece (an aligned word that overlaps the row is readable)
+          const uint32_t nxt = (off + take > 4 || 4 * (i + 1) < nb) ? w[i + 1] : 0u;
+          uint32_t v = __funnelshift_r(cur, nxt, sh);                         // bytes q[b0+4i .. +3], little endian
+          if (take < 4) v &= (1u << (8 * take)) - 1u;                         // zero bytes add nothing (00 -> +0)
+          uint32_t c = v ^ ((v >> 1) & 0x55555555u);
+          c = (c & 0x33333333u) + ((c >> 2) & 0x33333333u);
+          c = (c & 0x0F0F0F0Fu) + ((c >> 4) & 0x0F0F0F0Fu);
+          s += (c * 0x01010101u) >> 24;
+          cur = nxt;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) a.tile_sum[(long long)f * a.tiles + t] = (uint8_t)(s & 3u);
+      return;
+    }
+  }
+  for (int k = lane; 8 * k < a.TD; k += 32) {
+    unsigned c = chunk_codes(a, f, D0 + 8 * k);
     c = (c & 0x3333u) + ((c >> 2) & 0x3333u);   // sum of the eight 2-bit fields
     c = (c & 0x0F0Fu) + ((c >> 4) & 0x0F0Fu);
-    s = (int)((c & 0xFFu) + (c >> 8));
+    s += (c & 0xFFu) + (c >> 8);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  __shared__ int ws[kModThreads / 32];
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tot = 0;
-    for (int w = 0; w < kModThreads / 32; ++w) tot += ws[w];
-    a.tile_sum[(long long)f * a.tiles + t] = (uint8_t)(tot & 3);
-  }
+  if (lane == 0) a.tile_sum[(long long)f * a.tiles + t] = (uint8_t)(s & 3u);
 }
 
 __global__ void mod_tile_scan_kernel(const ModArgs a) {
@@ -409,7 +443,8 @@ struct ModEngine {
     a.tile_sum = d_tile_sum.p; a.tile_pre = d_tile_pre.p;
     const dim3 grid((unsigned)tiles, (unsigned)frames);
     if (diff) {
-      mod_tile_rot_kernel<<<grid, kModThreads, 0, s>>>(a);
+      const dim3 grid_rot((unsigned)((tiles + kModThreads / 32 - 1) / (kModThreads / 32)), (unsigned)frames);
+      mod_tile_rot_kernel<<<grid_rot, kModThreads, 0, s>>>(a);
       QPSK_LAUNCH_CHECK();
       mod_tile_scan_kernel<<<(frames + 3) / 4, 128, 0, s>>>(a);
       QPSK_LAUNCH_CHECK();

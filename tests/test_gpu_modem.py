@@ -118,6 +118,28 @@ def test_modulate_frames_dev_batch(gpu, orc):
         assert not out_h[f, ff:].any()                                      # nothing written past the frame
 
 
+@pytest.mark.parametrize("n_payload,start", [(3001, b"S"), (3002, b"ST"), (3003, b"STA"), (2999, b"STAR"), (4097, b"STARTS")])
+def test_modulate_frames_dev_alignments(gpu, orc, n_payload, start):
+    """The differential pre-pass sums interior tiles as 32-bit words: every byte alignment of the tile start
+    (row pitch and start-marker length both shift it) must give the oracle's symbols."""
+    import torch
+    frames = 5
+    m = gpu.QPSKModulator(4000, 1000, 0.35, 10, True, TSC)
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    s = ts.cuda_stream
+    pay = torch.empty((frames, n_payload), dtype=torch.uint8, device="cuda")
+    gpu.fill_bytes_dev(6, 7, frames, n_payload, pay.data_ptr(), s)
+    ff = m.frame_floats(n_payload, start, b"END")
+    out = torch.zeros((frames, ff), dtype=torch.float32, device="cuda")
+    assert m.modulate_frames_dev(pay.data_ptr(), n_payload, frames, start, b"END", out.data_ptr(), ff, s) == ff
+    torch.cuda.synchronize()
+    pay_h, out_h = pay.cpu().numpy(), out.cpu().numpy()
+    om = orc.QPSKModulator(4000, 1000, 0.35, 10, True, TSC)
+    for f in range(frames):
+        assert _close(out_h[f], om.ModulateBytes(pay_h[f].tobytes(), start, b"END"))
+
+
 def test_modulator_linearity_of_frames(gpu):
     """Full-size property (no oracle): every frame of a large batch equals the same frame done alone."""
     import torch
