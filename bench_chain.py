@@ -95,7 +95,7 @@ def run_chain(Q, torch, dist, world, rank, stream, steps=3, warmup=3, channels_p
                 "bit_errors": int(allc[:, 0].sum()), "bits": int(allc[:, 1].sum()),
                 "gathered_with": "all_gather (NCCL)" if dist is not None else "single rank"},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                     "note": "8 B/sample algorithmic; the serial loops run one thread per channel and are "
+                     "note": "8 B/sample algorithmic; the serial loops (8 lanes per stream in the FLL, one lane per channel in MM / Costas) are "
                              "dependent-issue-latency bound, not HBM bound (DESIGN.md)"},
     }
 

@@ -219,7 +219,7 @@ def fll_design(sps: float, rolloff: float, filterSize: int):
 
 
 class FLLBandEdgeFilter(_Handle):
-    """FLLBandEdgeFilter (MS/Models/Band-Edge Filter.cs:14-203) on the GPU, one thread per stream."""
+    """FLLBandEdgeFilter (MS/Models/Band-Edge Filter.cs:14-203) on the GPU: 8 lanes per stream (the reference's 8 SIMD lanes), a chain warp and a side warp per four streams (csrc/fll_duo.cu)."""
     _destroy = "qpsk_fll_destroy"
 
     def __init__(self, sps, rolloff, filterSize, bandwidth, channels: int = 1):
