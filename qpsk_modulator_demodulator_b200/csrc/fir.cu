@@ -23,6 +23,8 @@
 // pointers, and tap counts beyond the parameter-space table.
 #include "fir.cuh"
 
+#include <stdlib.h>
+
 namespace qpsk {
 
 // ---------------------------------------------------------------------------------------------
@@ -182,7 +184,7 @@ struct TileWalk {
 // and TMA-stores its own 32*R outputs, so warps drift apart and their prologues/epilogues overlap the
 // other warps' FFMA2 streams.
 template <int R, int NT, bool CPLX>
-__global__ void __launch_bounds__(NT + 32, 2)
+__global__ void __launch_bounds__(NT + 32, R <= 6 ? 3 : 2)
     fir_tma_kernel(const __grid_constant__ FirArgs a, const __grid_constant__ typename TapsOf<CPLX>::type taps) {
   static_assert(R % 2 == 0, "R must be even (LDS.128 moves two samples)");
   constexpr int T = R * NT;
@@ -521,13 +523,41 @@ constexpr int kNT = 256;
 constexpr int kT = kR * kNT;
 constexpr int kSmemBudget = 112 * 1024;  // per CTA, two CTAs per SM
 
-template <bool CPLX>
-int launch_tma(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, size_t smem, int grid, cudaStream_t s) {
-  auto kern = fir_tma_kernel<kR, kNT, CPLX>;
+// tile geometry of the TMA kernel: R outputs per thread, NT compute threads, CTAs per SM.  The production choice is
+// (10, 256, 2); QPSK_FIR_CFG=<index> selects another entry for tuning runs.  Measured on a B200, 2^28 samples, ms for
+// 33 / 65 / 129 / 257 taps:  (10,256,2) 0.79 1.32 2.37 4.46 | (10,320,2) 0.79 1.29 2.43 4.72 | (14,224,2) 0.83 1.40
+// 2.56 4.97 | (6,256,3) 0.92 1.52 2.73 5.15 | (10,192,3) 0.88 1.52 2.78 5.35 | (14,192,2) 0.96 1.64 3.01 5.80 |
+// (10,288,2) 0.91 1.59 3.01 5.85: eight consumer warps per CTA (four per scheduler with two CTAs) beat both fewer,
+// fatter threads and warp counts that do not divide over the four schedulers.
+struct FirCfg {
+  int R, NT, per_sm;
+};
+constexpr FirCfg kFirCfgs[] = {{10, 256, 2}, {10, 320, 2}, {14, 224, 2}, {6, 256, 3}};
+inline int fir_cfg_index() {
+  static const int idx = [] {
+    const char* e = getenv("QPSK_FIR_CFG");
+    const int i = e ? atoi(e) : 0;
+    return (i >= 0 && i < (int)(sizeof(kFirCfgs) / sizeof(kFirCfgs[0]))) ? i : 0;
+  }();
+  return idx;
+}
+
+template <int R, int NT, bool CPLX>
+int launch_tma_cfg(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, size_t smem, int grid, cudaStream_t s) {
+  auto kern = fir_tma_kernel<R, NT, CPLX>;
   QPSK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kNT + 32, smem, s>>>(a, taps);
+  kern<<<grid, NT + 32, smem, s>>>(a, taps);
   QPSK_LAUNCH_CHECK();
   return QPSK_OK;
+}
+template <bool CPLX>
+int launch_tma(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, size_t smem, int grid, cudaStream_t s) {
+  switch (fir_cfg_index()) {
+    case 1: return launch_tma_cfg<10, 320, CPLX>(a, taps, smem, grid, s);
+    case 2: return launch_tma_cfg<14, 224, CPLX>(a, taps, smem, grid, s);
+    case 3: return launch_tma_cfg<6, 256, CPLX>(a, taps, smem, grid, s);
+    default: return launch_tma_cfg<kR, kNT, CPLX>(a, taps, smem, grid, s);
+  }
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -545,7 +575,10 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
   const int hl = stateless ? (N - 1) : HL;
   const int G = (hl + 1 + 1) & ~1;
 
-  bool use_tma = (mode == QPSK_FIR_FAST || stateless) && G <= kMaxG && hl <= kT;
+  const FirCfg cfg = kFirCfgs[fir_cfg_index()];
+  const int T = cfg.R * cfg.NT;
+  const int smem_budget = (cfg.per_sm == 2) ? kSmemBudget : (224 * 1024 / cfg.per_sm);
+  bool use_tma = (mode == QPSK_FIR_FAST || stateless) && G <= kMaxG && hl <= T;
   if (use_tma) {
     if (!aligned16(x) || !aligned16(y)) use_tma = false;
     if (channels > 1 && ((ldx & 1) || (ldy & 1))) use_tma = false;
@@ -560,19 +593,19 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
     FirArgs a;
     a.x = x; a.y = y; a.ldx = ldx; a.ldy = ldy; a.L = L;
     a.hist_in = hin; a.hist_out = hout;
-    a.tiles_per_ch = (int)((L + kT - 1) / kT);
+    a.tiles_per_ch = (int)((L + T - 1) / T);
     a.total_tiles = (long long)a.tiles_per_ch * channels;
     a.HL = hl; a.G = G; a.advance = advance;
-    a.E_load = kT + G;
+    a.E_load = T + G;
     a.stage_elems = a.E_load + 2;
     const size_t stage_bytes = (size_t)a.stage_elems * 8;
-    const size_t out_bytes = (size_t)2 * kT * 8;
-    int stages = (int)((kSmemBudget - out_bytes - 128) / stage_bytes);
+    const size_t out_bytes = (size_t)2 * T * 8;
+    int stages = (int)((smem_budget - out_bytes - 128) / stage_bytes);
     if (stages > 4) stages = 4;
     if (stages >= 2) {
       a.stages = stages;
       const size_t smem = (size_t)stages * stage_bytes + out_bytes + (size_t)stages * 16;
-      long long grid = 2LL * device_sm_count();
+      long long grid = (long long)cfg.per_sm * device_sm_count();
       if (grid > a.total_tiles) grid = a.total_tiles;
       if (real_taps) {
         TapsReal t;
