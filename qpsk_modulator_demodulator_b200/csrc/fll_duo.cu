@@ -32,8 +32,8 @@ namespace qpsk {
 namespace {
 
 constexpr int kDuoStreams = 4;            // streams per warp pair
-constexpr int kDuoRing = 64;              // ring slots per stream (power of two, >= N + 16)
-constexpr int kDuoRingStride = kDuoRing + 2;   // float2; 528 B: 16-byte aligned rows, streams 4 banks apart
+// ring slots per stream: a power of two >= N + 16 (64 up to 48 taps, 128 up to 55); rows are RING + 2 float2 long
+// (16-byte aligned, the four streams' rows 4 banks apart)
 constexpr int kDuoBatch = 4;              // samples per hand-over
 constexpr int kDuoSuper = 16;             // samples per global-memory transaction and stream
 constexpr int kDuoXStride = kDuoSuper + 2;
@@ -119,8 +119,9 @@ __device__ __forceinline__ bool duo_mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+template <int RING>
 struct DuoSmem {
-  float2 ring[kDuoStreams * kDuoRingStride];            // past outputs, slot = sample index & 63
+  float2 ring[kDuoStreams * (RING + 2)];                // past outputs, slot = sample index & (RING - 1)
   float4 lp[2][kDuoBatch][32];                          // per batch parity: stale lane partials (loI, loQ, upI, upQ)
   float2 xq[2][kDuoStreams * kDuoXStride];              // input samples, one super-batch per slot
   uint64_t lp_full[2];                                  // side -> chain: batch's partials (and inputs) are in place
@@ -154,27 +155,31 @@ __device__ __forceinline__ float duo_wrap_phase(float phase, double pd) {
   return (r == 0.0) ? copysignf(0.f, phase) : (float)r;
 }
 
-template <int K, int PAIRS>
+template <int K, int TAIL, int PAIRS>
 __global__ void __launch_bounds__(64 * PAIRS)
     fll_duo_kernel(const FllParams P, const float* __restrict__ taps, float2* ring_g, int* head_g, float2* pf_g, int C,
                    const float2* __restrict__ x, float2* __restrict__ y, long long L, long long ldx, long long ldy) {
-  constexpr int N = 8 * K;
-  static_assert(N + 16 <= kDuoRing, "ring too small");
-  __shared__ __align__(16) DuoSmem smem[PAIRS];
+  constexpr int N = 8 * K + TAIL;                           // 8-lane vector part + scalar tail (FIRFilter.cs:165-192)
+  constexpr int kDuoRing = (N + 16 <= 64) ? 64 : 128;
+  constexpr int kDuoRingStride = kDuoRing + 2;
+  // warm-up batches (even, so that batch parity stays b & 1): the prefix of window 0 starts TAIL + 7 steps early
+  constexpr int WB = (TAIL <= 1) ? 2 : 4;
+  static_assert(4 * WB >= TAIL + 7, "warm-up too short");
+  __shared__ __align__(16) DuoSmem<kDuoRing> smem[PAIRS];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // warps 0..PAIRS-1 are the chain warps, PAIRS..2*PAIRS-1 their side warps: with PAIRS = 4 (warps go to the four
   // schedulers round robin) every scheduler holds one chain warp and one side warp of the CTA
   const int pair = warp % PAIRS;
   const bool is_chain = warp < PAIRS;
-  DuoSmem& S = smem[pair];
+  DuoSmem<kDuoRing>& S = smem[pair];
   const int sl = lane >> 3;                                 // stream slot in the pair
   const int g = lane & 7;                                   // reference SIMD lane
   const int c_raw = (blockIdx.x * PAIRS + pair) * kDuoStreams + sl;
   const bool live = c_raw < C;
   const int c = live ? c_raw : C - 1;                       // idle groups shadow the last stream, no stores
   float2* myring = S.ring + sl * kDuoRingStride;
-  const long long nB = (L + kDuoBatch - 1) / kDuoBatch;     // batches of real samples; batches -2, -1 are the warm-up
+  const long long nB = (L + kDuoBatch - 1) / kDuoBatch;     // batches of real samples; batches -WB..-1 are the warm-up
 
   if (lane == 0 && is_chain) {
     duo_mbar_init(&S.lp_full[0], 1);
@@ -210,8 +215,9 @@ __global__ void __launch_bounds__(64 * PAIRS)
     if (g < L) xr0 = xc[g];
     if (g + 8 < L) xr1 = xc[g + 8];
     long long flushed = 0;
-    for (long long b = -2; b < nB; ++b) {
-      if (b >= 0) duo_mbar_wait_sleepy(&S.out_full[b & 1], (uint32_t)((b >> 1) & 1));   // chain finished batch b-2
+    for (long long b = -WB; b < nB; ++b) {
+      // chain finished batch b-2 (its phase index on barrier b & 1 is (b - 2 + WB) / 2)
+      if (b >= 2 - WB) duo_mbar_wait_sleepy(&S.out_full[b & 1], (uint32_t)(((b - 2 + WB) >> 1) & 1));
       if (b >= 0 && (b & 3) == 0) {
         const long long sb = b >> 2;
         float2* q = S.xq[sb & 1] + sl * kDuoXStride;
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(64 * PAIRS)
     // the chain's last batch
     {
       const long long bl = nB - 1;
-      duo_mbar_wait_sleepy(&S.out_full[bl & 1], (uint32_t)(((bl + 2) >> 1) & 1));
+      duo_mbar_wait_sleepy(&S.out_full[bl & 1], (uint32_t)(((bl + WB) >> 1) & 1));
     }
     if (live) {
       for (long long i = flushed + g; i < L; i += 8) yc[i] = myring[(int)i & (kDuoRing - 1)];
@@ -265,7 +271,18 @@ __global__ void __launch_bounds__(64 * PAIRS)
 
   // =========================================== CHAIN warp ===========================================
   const float tA = taps[g + 8 * (K - 1)], tB = taps[N + g + 8 * (K - 1)];   // tap of this lane's newest element
-  const float nA = taps[N - 1], nBq = taps[2 * N - 1];                        // lane 7's: tap of out[n] in window n
+  const float nA = taps[8 * K - 1], nBq = taps[N + 8 * K - 1];                // lane 7's newest element (TAIL == 0: out[n] in window n)
+  // scalar tail (TAIL > 0): window m adds  tail_j (x) out[m-TAIL+1+j], j = 0..TAIL-1, after the lane sum.  At step n stage j
+  // extends window n+TAIL-1-j with out[n]: T_j = T_{j-1}(previous step) + tail_j (x) out[n], T_{-1} = lane 7's prefix of
+  // the previous step; every lane runs all stages (register arithmetic only), the last one closes window n.
+  float tTa[TAIL > 0 ? TAIL : 1], tTb[TAIL > 0 ? TAIL : 1];
+  float4 Tt[TAIL > 0 ? TAIL : 1];
+#pragma unroll
+  for (int j = 0; j < (TAIL > 0 ? TAIL : 1); ++j) {
+    tTa[j] = (TAIL > 0) ? taps[8 * K + j] : 0.f;
+    tTb[j] = (TAIL > 0) ? taps[N + 8 * K + j] : 0.f;
+    Tt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const SinCosF SK = sincos_f_load_consts();
   const float2 pf = pf_g[c];
   float phase = pf.x, freq = pf.y;
@@ -303,7 +320,7 @@ __global__ void __launch_bounds__(64 * PAIRS)
     __syncwarp();
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(a_ex_out) : "r"(duo_smem_u32(&S.opaque[lane])));
   }
-  const uint32_t a_p6 = duo_pin(duo_smem_u32(ex_row + 7));          // lane 6's prefix
+  const uint32_t a_p6 = duo_pin(duo_smem_u32(ex_row + (TAIL == 0 ? 7 : 8)));   // lane 6's prefix (TAIL > 0: lane 7's)
   const uint32_t a_lp0 = duo_pin(duo_smem_u32(&S.lp[0][0][lane]));
   const uint32_t a_l70 = duo_pin(duo_smem_u32(&S.lp[0][0][sl * 8 + 7]));
   const uint32_t a_xq0 = duo_pin(duo_smem_u32(S.xq[0] + sl * kDuoXStride));
@@ -331,7 +348,7 @@ __global__ void __launch_bounds__(64 * PAIRS)
       oQ = o.y;
     } else {
       P6 = duo_lds128<0>(a_p6);
-      L7 = duo_lds128<J * 512>(a_l7);
+      if (TAIL == 0) L7 = duo_lds128<J * 512>(a_l7);
       const float2 in = duo_lds64<J * 8>(a_xq);
       // MathF.Cos/Sin(phase) :108-109 and the rotation :111-112, with phase = r + q*pi/2 and the exact factor j^q
       // applied to the input sample while the polynomials run:  out = (in * j^q) * (cos r + j sin r).  Same two
@@ -355,10 +372,29 @@ __global__ void __launch_bounds__(64 * PAIRS)
     Pn.y = Pin.y + Lg.y;
     Pn.z = Pin.z + Lg.z;
     Pn.w = Pin.w + Lg.w;
+    float aLoI = 0.f, aLoQ = 0.f, aUpI = 0.f, aUpQ = 0.f;
+    if (TAIL > 0) {
+      // tail stages, newest window last; warm-up steps run them too (they fill the pipeline)
+      float4 P7;
+      if constexpr (WARM) P7 = duo_lds128<0>(a_p6);
+      else P7 = P6;
+#pragma unroll
+      for (int j = TAIL - 1; j >= 1; --j) {
+        float4 v = Tt[j - 1];
+        duo_acc(v, tTa[j], tTb[j], oI, oQ);
+        Tt[j] = v;
+      }
+      float4 v0 = P7;
+      duo_acc(v0, tTa[0], tTb[0], oI, oQ);
+      Tt[0] = v0;
+      aLoI = Tt[TAIL - 1].x; aLoQ = Tt[TAIL - 1].y; aUpI = Tt[TAIL - 1].z; aUpQ = Tt[TAIL - 1].w;
+    }
     if (!WARM) {
-      // lane 7's role for the current window, on every lane: acc = P_6(n) + L_7(n)
-      duo_acc(L7, nA, nBq, oI, oQ);
-      const float aLoI = P6.x + L7.x, aLoQ = P6.y + L7.y, aUpI = P6.z + L7.z, aUpQ = P6.w + L7.w;
+      if (TAIL == 0) {
+        // lane 7's role for the current window, on every lane: acc = P_6(n) + L_7(n)
+        duo_acc(L7, nA, nBq, oI, oQ);
+        aLoI = P6.x + L7.x; aLoQ = P6.y + L7.y; aUpI = P6.z + L7.z; aUpQ = P6.w + L7.w;
+      }
       const float powUpper = aUpI * aUpI + aUpQ * aUpQ;      // :118
       const float powLower = aLoI * aLoI + aLoQ * aLoQ;      // :119
       const float error = powLower - powUpper;               // :121
@@ -380,9 +416,9 @@ __global__ void __launch_bounds__(64 * PAIRS)
     __syncwarp();
     if (lane == 0) duo_mbar_arrive(&S.out_full[b & 1]);
   };
-  auto batch_wait = [&](long long b) { duo_mbar_wait(&S.lp_full[b & 1], (uint32_t)(((b + 2) >> 1) & 1)); };
+  auto batch_wait = [&](long long b) { duo_mbar_wait(&S.lp_full[b & 1], (uint32_t)(((b + WB) >> 1) & 1)); };
   // non-blocking probe of a later batch's barrier, issued mid-batch so that its latency hides under the chain
-  auto batch_probe = [&](long long b) { return duo_mbar_test(&S.lp_full[b & 1], (uint32_t)(((b + 2) >> 1) & 1)); };
+  auto batch_probe = [&](long long b) { return duo_mbar_test(&S.lp_full[b & 1], (uint32_t)(((b + WB) >> 1) & 1)); };
   bool ready = false;
   using J0 = std::integral_constant<int, 0>;
   using J1 = std::integral_constant<int, 1>;
@@ -401,48 +437,61 @@ __global__ void __launch_bounds__(64 * PAIRS)
     if (ns > 3) step(warm_tag, J3{}, a_lp, a_l7, a_xq, a_rn);
     batch_done(b);
   };
-  // warm-up: fills the prefix pipeline from the outputs of earlier calls (steps -8..-1)
-  for (long long b = -2; b < 0; ++b) batch(std::true_type{}, b, kDuoBatch);
+  // warm-up: fills the prefix (and tail) pipeline from the outputs of earlier calls (steps -4*WB..-1)
+  for (long long b = -WB; b < 0; ++b) batch(std::true_type{}, b, kDuoBatch);
   const long long nFull = L / kDuoBatch;
   for (long long b = 0; b < nFull; ++b) batch(std::false_type{}, b, kDuoBatch);
   if (nFull < nB) batch(std::false_type{}, nFull, (int)(L - 4 * nFull));
   if (live && g == 0) pf_g[c] = make_float2(phase, freq);
 }
 
-template <int PAIRS>
-int launch_duo(int K, const FllParams& P, const float* taps, float2* ring, int* head, float2* pf, int C, const float2* x,
-               float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {
+template <int K, int PAIRS>
+int launch_duo_tail(int tail, const FllParams& P, const float* taps, float2* ring, int* head, float2* pf, int C, const float2* x,
+                    float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {
   const int per_cta = PAIRS * kDuoStreams;
   const int blocks = (C + per_cta - 1) / per_cta;
-  switch (K) {
-#define QPSK_DUO_CASE(KK) \
-  case KK: fll_duo_kernel<KK, PAIRS><<<blocks, 64 * PAIRS, 0, s>>>(P, taps, ring, head, pf, C, x, y, L, ldx, ldy); break;
-    QPSK_DUO_CASE(1) QPSK_DUO_CASE(2) QPSK_DUO_CASE(3) QPSK_DUO_CASE(4) QPSK_DUO_CASE(5) QPSK_DUO_CASE(6)
+  switch (tail) {
+#define QPSK_DUO_CASE(TT) \
+  case TT: fll_duo_kernel<K, TT, PAIRS><<<blocks, 64 * PAIRS, 0, s>>>(P, taps, ring, head, pf, C, x, y, L, ldx, ldy); break;
+    QPSK_DUO_CASE(0) QPSK_DUO_CASE(1) QPSK_DUO_CASE(2) QPSK_DUO_CASE(3) QPSK_DUO_CASE(4) QPSK_DUO_CASE(5) QPSK_DUO_CASE(6)
+    QPSK_DUO_CASE(7)
 #undef QPSK_DUO_CASE
     default: return QPSK_ERR_UNSUPPORTED;
   }
   QPSK_LAUNCH_CHECK();
   return QPSK_OK;
 }
+template <int PAIRS>
+int launch_duo(int n_taps, const FllParams& P, const float* taps, float2* ring, int* head, float2* pf, int C, const float2* x,
+               float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {
+  const int tail = n_taps & 7;
+  switch (n_taps >> 3) {
+    case 1: return launch_duo_tail<1, PAIRS>(tail, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+    case 2: return launch_duo_tail<2, PAIRS>(tail, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+    case 3: return launch_duo_tail<3, PAIRS>(tail, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+    case 4: return launch_duo_tail<4, PAIRS>(tail, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+    case 5: return launch_duo_tail<5, PAIRS>(tail, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+    case 6: return launch_duo_tail<6, PAIRS>(tail, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+    default: return QPSK_ERR_UNSUPPORTED;
+  }
+}
 
 }  // namespace
 
-bool fll_duo_supported(int n_taps) { return n_taps >= 8 && n_taps <= 48 && (n_taps & 7) == 0; }
+bool fll_duo_supported(int n_taps) { return n_taps >= 8 && n_taps <= 55; }
 
 int fll_duo_launch(const FllParams& P, const float* taps, float2* ring, int* head, float2* pf, int C, const float2* x,
                    float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {
   static const int pairs_env = [] {
-    const char* e = getenv("QPSK_FLL_PAIRS");                // 1, 2 or 4 warp pairs per CTA (timing experiments)
+    const char* e = getenv("QPSK_FLL_PAIRS");                // 1 or 4 warp pairs per CTA (timing experiments)
     return e ? atoi(e) : 0;
   }();
   // measured on a B200 (tools/fll_only.py, 40 taps): up to ~1300 streams one pair per CTA spreads the chain warps
   // over all SMs (356 cycles per sample at 1024 streams against 421); beyond that four pairs per CTA, one chain and
   // one side warp per scheduler, keep two chain warps off the same scheduler (4096 streams: 580 against 724)
   const int pairs = pairs_env ? pairs_env : (C <= 1280 ? 1 : 4);
-  const int K = P.n_taps / 8;
-  if (pairs == 1) return launch_duo<1>(K, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
-  if (pairs == 2) return launch_duo<2>(K, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
-  return launch_duo<4>(K, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+  if (pairs == 1) return launch_duo<1>(P.n_taps, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
+  return launch_duo<4>(P.n_taps, P, taps, ring, head, pf, C, x, y, L, ldx, ldy, s);
 }
 
 }  // namespace qpsk

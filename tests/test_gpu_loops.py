@@ -70,9 +70,9 @@ def test_fll_batch_and_state(gpu, orc):
     assert _close(g1.Process(x[0]), o1.Process(x[0]))
 
 
-@pytest.mark.parametrize("size", [40, 16, 8, 48])
+@pytest.mark.parametrize("size", [40, 16, 8, 48, 10, 13, 9, 23, 31, 55, 33, 52])
 def test_fll_two_warp_kernel_sizes_and_chunking(gpu, orc, size):
-    """N % 8 == 0 takes the two-warp kernel (csrc/fll_duo.cu): odd chunk lengths exercise the partial last batch,
+    """8 <= N <= 55 takes the two-warp kernel (csrc/fll_duo.cu; N % 8 != 0 adds the scalar-tail stages): odd chunk lengths exercise the partial last batch,
     the warm-up from the carried ring and the flush bookkeeping; outputs and state must stay bit-identical."""
     x, _ = _qpsk_burst(orc, 900, sps=4, alpha=0.35, cfo=0.03, noise=0.05, seed=size)
     want_f = orc.FLLBandEdgeFilter(4.0, 0.35, size, 0.05)
