@@ -160,6 +160,7 @@ static __constant__ double kSinCosTab[26] = {
     1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0,
     1.0 / 20922789888000.0, -1.0 / 6402373705728000.0, 1.0 / 2432902008176640000.0, -1.0 / 1124000727777607680000.0,
     0.5, 1.0};
+static __constant__ double kSinCosMagic = 6755399441055744.0;   // 1.5 * 2^52: x + magic rounds x to an integer
 // a volatile load ptxas can neither fold nor re-execute: the value has to stay in a register pair
 __device__ __forceinline__ double ld_const_pinned(const double* p) {
   double v;
@@ -317,6 +318,35 @@ __device__ __forceinline__ void sincos_f32arg_rq(double x, const SinCosF& K, flo
   const double cr = w + fma(z2, Cc, (K.one - w) - hz);
   *sr_out = (float)sr;
   *cr_out = (float)cr;
+}
+// fp64 argument, reduced pair + quadrant, for the Costas step (|theta| <= pi + |step|): the chain-shortening of
+// sincos_f32arg_rq (magic-number quadrant, two Cody-Waite pieces, 8 coefficients — the first dropped terms are
+// r z^9/19! and z^9/18!, below 1e-19 of the result for |r| <= pi/4 — and the cos tail in one DFMA) on the constants
+// of SinCosK.  Against sincos_fast_f64_k the value can differ in the last bit only where x*2/pi lies within an ulp
+// of a half-integer (the quadrant may then be the neighbour's: an equally valid reduction) — the Costas tests pin
+// bits exactly and loop state to 1e-5.
+__device__ __forceinline__ void sincos_rq_f64_k(double x, const SinCosK& K, double magic, double* sr_out, double* cr_out,
+                                                unsigned* q_out) {
+  const double t = fma(x, K.two_over_pi, magic);
+  const double k = t - magic;
+  *q_out = (unsigned)__double2loint(t);
+  double r = fma(-k, K.p1, x);
+  r = fma(-k, K.p2, r);
+  const double z = r * r, z2 = z * z, z4 = z2 * z2;
+  const double a01 = fma(K.s[1], z, K.s[0]);
+  const double a23 = fma(K.s[3], z, K.s[2]);
+  const double a45 = fma(K.s[5], z, K.s[4]);
+  const double a67 = fma(K.s[7], z, K.s[6]);
+  const double S = fma(fma(a67, z2, a45), z4, fma(a23, z2, a01));
+  *sr_out = fma(r * z, S, r);
+  const double d01 = fma(K.c[1], z, K.c[0]);
+  const double d23 = fma(K.c[3], z, K.c[2]);
+  const double d45 = fma(K.c[5], z, K.c[4]);
+  const double d67 = fma(K.c[7], z, K.c[6]);
+  const double Cc = fma(fma(d67, z2, d45), z4, fma(d23, z2, d01));
+  const double hz = K.half * z;
+  const double w = K.one - hz;
+  *cr_out = w + fma(z2, Cc, (K.one - w) - hz);
 }
 // MathF.Sin/Cos model (see sincos_f32_exact) through the register-constant fast path
 __device__ __forceinline__ void sincos_f32_fast_k(float x, const SinCosK& K, float* s, float* c) {

@@ -107,6 +107,13 @@ struct SsSmem {
   int nsymq[2][32];
 };
 
+// a ? x : y on doubles as an explicit selp (two SELs, never a branch)
+__device__ __forceinline__ double sel_f64(bool a, double x, double y) {
+  double r;
+  asm("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\nselp.f64 %0, %1, %2, p;\n}" : "=d"(r) : "d"(x), "d"(y), "r"((unsigned)a));
+  return r;
+}
+
 template <bool DIFF>
 __global__ void __launch_bounds__(64)
     symsync_decode_kernel(const MmParams MP, MmState* mm_g, const float2* __restrict__ q_in, float2* __restrict__ q_out,
@@ -131,6 +138,7 @@ __global__ void __launch_bounds__(64)
   int carried = 0, n_sym = 0;
   // role 1 state
   const SinCosK SK = sincos_load_consts();
+  const double magic = ld_const_pinned(&kSinCosMagic);
   CostasState K;
   DiffState D;
   long long nb = (append && role == 1) ? n_bits[c] : 0;
@@ -151,32 +159,31 @@ __global__ void __launch_bounds__(64)
     cp_async_commit();
   };
 
+  // The Costas warp (which has the slack) also stages the samples: round r+1 is requested at the top of round r and
+  // waited for before the barrier that ends it, so the Mueller-Muller warp finds its round in shared memory.
   if (role == 0) {
     S = mm_g[c];
     if (append) n_sym = n_sym_g[c];
     carried = S.queued;                              // host guarantees <= kSsCarry
     for (int i = 0; i < carried; ++i) sm.carry[lane * kSsCarry + i] = q_in[(long long)c * qcap + i];
-    if (rounds > 0) stage(0);
   } else {
+    if (rounds > 0) stage(0);
     K = cst_g[c];
     D = dst_g[c];
+    cp_async_wait<0>();
   }
+  __syncthreads();
   // Mueller-Muller loop registers.  The previous decision is +-1 and only ever multiplies (:78), so it is kept as a
   // sign; the previous sample is kept widened (it only appears as (double)dec * prevSample, :79).
   bool prevNegI = S.prevDI < 0.f, prevNegQ = S.prevDQ < 0.f;
   double prevSI_d = (double)S.prevSI, prevSQ_d = (double)S.prevSQ;
   bool has_prev = S.has_prev != 0;
 
+  // 1 / (largest advance per symbol), rounded down a little: the counted loop below must stay conservative
+  const double inv_max_adv = (1.0 / (MP.sps + 0.1000001)) * (1.0 - 1e-12);
   for (int r = 0; r <= rounds; ++r) {
     if (role == 0) {
       if (r < rounds) {
-        if (r + 1 < rounds) {
-          stage(r + 1);
-          cp_async_wait<1>();
-        } else {
-          cp_async_wait<0>();
-        }
-        __syncwarp();
         const long long n0 = (long long)r * kSsBlock;
         const int blk = (int)((L - n0) < kSsBlock ? (L - n0) : kSsBlock);
         MmView v;
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(64)
         // read the unclamped value (:87-89: 0.1 > -0.1, so the second test cannot fire after the first), floor()
         // yields (double)baseIndex directly (no F2I -> I2F round trip), and the loop test reads the fp64 base.  The
         // post-advance break (:118-119, base + 1 >= count) implies the loop test fails, so one test serves both.
+        const double adv_hi = MP.sps + 0.1, adv_lo = MP.sps + (-0.1);            // sps + clamp(corr) at the two rails
         auto one_symbol = [&]() {
           float ci, cq;
           mm_interp(v, S.base_index, S.mu, ci, cq);
@@ -205,22 +213,33 @@ __global__ void __launch_bounds__(64)
           const double e = term1 - term2;
           const double integ = S.integral + MP.ki * e;       // :83
           const double corr = MP.kp * e + integ;             // :84
-          const double cl = (corr > 0.1) ? 0.1 : ((corr < -0.1) ? -0.1 : corr);   // :87-89
-          const double advance = has_prev ? (MP.sps + cl) : MP.sps;               // :91, :96
+          // clamp (:87-89), advance (:91, :96) and newTime (:113) with the selects moved to the end: the three
+          // possible advances sps + 0.1, sps - 0.1, sps do not depend on the error, so their newTime candidates
+          // are formed early and the two compares run beside the adds of the unclamped candidate — same operations
+          // on the selected path, ~20 cycles less on the loop-carried chain
+          const double bm = base_d + S.mu;
+          const double nt_c = bm + (MP.sps + corr);
+          const bool hi = corr > 0.1, lo = corr < -0.1;
+          // selp through inline PTX: left to itself the compiler folds the candidates back into bm + select(advance)
+          // and branches on the compares
+          const double nt_cl = sel_f64(hi, bm + adv_hi, sel_f64(lo, bm + adv_lo, nt_c));
+          const double newTime = sel_f64(has_prev, nt_cl, bm + MP.sps);
           S.integral = has_prev ? integ : S.integral;
           has_prev = true;
           prevSI_d = ci_d; prevSQ_d = cq_d; prevNegI = !posI; prevNegQ = !posQ;
-          const double newTime = (base_d + S.mu) + advance;  // :113
-          base_d = floor(newTime);
+          // floor (:114) by a round-down add of 2^52 (0 <= newTime < 2^31): one DADD.RM instead of FRND.F64.FLOOR on
+          // the XU pipe, and the integer index is the low word of the same sum (no F2I in front of the next LDS)
+          const double fl52 = __dadd_rd(newTime, 4503599627370496.0);
+          S.base_index = __double2loint(fl52);       // :114
+          base_d = fl52 - 4503599627370496.0;        // == floor(newTime), exact
           S.mu = newTime - base_d;                   // :115
-          S.base_index = (int)base_d;                // :114
           sq[ns++] = make_float2(ci, cq);
         };
         // The loop test reads the newest base, i.e. it closes the dependency chain through floor -> compare -> branch.
         // Every symbol advances time by at most sps + 0.1 (:87-91), so the first n_safe passes are known to satisfy it
         // and run as a counted loop whose branch resolves early; only the last one or two passes are tested.
         const double span_d = limit_d - (base_d + S.mu);
-        const double q = span_d / (MP.sps + 0.1000001);
+        const double q = span_d * inv_max_adv;       // (a product instead of a ~60-instruction fp64 division per round)
         int n_safe = (q > 1.0) ? (int)q - 1 : 0;       // conservative: floor(q) - 1 full advances certainly fit
         for (int j = 0; j < n_safe; ++j) one_symbol();
         while (base_d < limit_d) one_symbol();       // :62
@@ -237,7 +256,10 @@ __global__ void __launch_bounds__(64)
         carried = remain;
         S.base_index -= consumed;
       }
-    } else if (r >= 1) {
+    } else if (r + 1 < rounds) {
+      stage(r + 1);                                  // in flight during this round's Costas work
+    }
+    if (role == 1 && r >= 1) {
       // ---- Costas + decision + differential decode (QPSKDeModulator.cs:374-408) on round r-1 ----
       // One basic block per symbol: the Costas recurrence is the critical chain; the decisions, the differential
       // decode (pure predicate logic on the four sign bits: d*conj(d_prev) of two unit-corner symbols is one of
@@ -273,7 +295,7 @@ __global__ void __launch_bounds__(64)
         nxt = sq[k + 1];                                 // row pitch kSsSymCap + 1: in bounds for every k < ns
         float rI, rQ;
         unsigned sI, sQ;
-        costas_step_fast(CP, SK, K, in.x, in.y, rI, rQ, sI, sQ, wild);
+        costas_step_fast2(CP, SK, magic, K, in.x, in.y, rI, rQ, sI, sQ, wild);
         const unsigned cur = (sI >> 31) | (sQ >> 30);
         const unsigned idx = cur | (prev << 2);
         prev = cur;
@@ -316,6 +338,7 @@ __global__ void __launch_bounds__(64)
         }
       }
     }
+    if (role == 1) cp_async_wait<0>();               // the next round's samples have landed
     __syncthreads();                                 // hand the round's symbol queue over / free the other one
   }
   if (role == 0) {

@@ -205,6 +205,44 @@ __device__ __forceinline__ void costas_step_fast(const CostasParams& P, const Si
   const double t_dn = t - kTwoPi, t_up = t + kTwoPi;
   S.theta = (t > kPi) ? t_dn : ((t < -kPi) ? t_up : t);      // :89-91
 }
+// costas_step_fast with the shortened sincos and the quadrant applied to the INPUT sample: theta = r + q*pi/2 and
+// x * e^{-j theta} = (x * (-j)^q) * (cos r - j sin r); the factor (-j)^q is an exact swap / sign flip that runs while
+// the polynomials are evaluated, and the mixer forms the same two products per component as :72-73 (signs are exact,
+// a + b == b + a), so the select / XOR fix-up of the sin/cos pair leaves the dependency chain.
+__device__ __forceinline__ void costas_step_fast2(const CostasParams& P, const SinCosK& K, double magic, CostasState& S, float inI,
+                                                  float inQ, float& outI, float& outQ, unsigned& sgnI, unsigned& sgnQ,
+                                                  bool& wild) {
+  wild |= abs_ge_hi(S.theta, 0x40F86A00);                    // |theta| >= 1e5 or NaN
+  double sr, cr;
+  unsigned q;
+  sincos_rq_f64_k(S.theta, K, magic, &sr, &cr, &q);
+  const double dI = (double)inI, dQ = (double)inQ;
+  // x' = x * (-j)^q:  q=0 (I, Q)   q=1 (Q, -I)   q=2 (-I, -Q)   q=3 (-Q, I)
+  const bool odd = (q & 1u) != 0;
+  const int fI = (int)((q & 2u) << 30);                      // sign of the first component: quadrants 2, 3
+  const int fQ = (int)(((q + 1u) & 2u) << 30);               // sign of the second: quadrants 1, 2
+  const double aI0 = odd ? dQ : dI, aQ0 = odd ? dI : dQ;
+  const double aI = __hiloint2double(__double2hiint(aI0) ^ fI, __double2loint(aI0));
+  const double aQ = __hiloint2double(__double2hiint(aQ0) ^ fQ, __double2loint(aQ0));
+  const double mi = aI * cr + aQ * sr;                       // :72
+  const double mq = aQ * cr - aI * sr;                       // :73
+  outI = (float)mi;
+  outQ = (float)mq;
+  const int hi_i = __double2hiint(mi), hi_q = __double2hiint(mq);
+  const unsigned ui = (unsigned)hi_i, uq = (unsigned)hi_q;
+  wild |= (ui - 0x80000000u < 0x36A00000u) | ((ui & 0x7fffffffu) >= 0x7ff00000u) |      // -2^-149 < mi <= -0, Inf, NaN
+          (uq - 0x80000000u < 0x36A00000u) | ((uq & 0x7fffffffu) >= 0x7ff00000u);
+  sgnI = (unsigned)hi_i & 0x80000000u;
+  sgnQ = (unsigned)hi_q & 0x80000000u;
+  const double a = __hiloint2double(hi_q ^ (int)sgnI, __double2loint(mq));
+  const double b = __hiloint2double(hi_i ^ (int)sgnQ, __double2loint(mi));
+  const double pe = a - b;                                   // :82
+  S.freq += P.beta * pe;                                     // :85
+  const double t = S.theta + (S.freq + P.alpha * pe);        // :86
+  const double kPi = 3.14159265358979323846, kTwoPi = 2.0 * kPi;
+  const double t_dn = t - kTwoPi, t_up = t + kTwoPi;
+  S.theta = (t > kPi) ? t_dn : ((t < -kPi) ? t_up : t);      // :89-91
+}
 // exact for every input: the reference's operation order with the library sincos
 __device__ __forceinline__ void costas_step_exact(const CostasParams& P, CostasState& S, float inI, float inQ, float& outI,
                                                   float& outQ) {

@@ -6,6 +6,7 @@ import bench_chain
 Q.set_device(0)
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); s = ts.cuda_stream
 which = sys.argv[1]
+ST = int(sys.argv[2]) if len(sys.argv) > 2 else 2   # timed steps
 if which == 'stream':
     r = bench_chain.run_stream(Q)
 elif which == 'sweep':
@@ -15,9 +16,9 @@ elif which == 'sweep':
             o = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=2, warmup=2, use_fll=fll, channels_per_gpu=C)
             r[f"{C}{'_fll' if fll else ''}"] = {"msamples_s": o["value"], "ms": o["ms_per_step"], "launches": o["gpu_launches"]}
 elif which == 'chain':
-    r = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=2, warmup=2, use_fll=False)
+    r = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=ST, warmup=3, use_fll=False)
 elif which == 'fll':
-    r = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=2, warmup=2, use_fll=True)
+    r = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=ST, warmup=3, use_fll=True)
 else:
     r = bench_chain.run_modulator(Q, torch, None, 1, 0, s, steps=2, warmup=2)
 print(json.dumps(r))
