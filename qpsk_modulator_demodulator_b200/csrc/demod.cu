@@ -433,7 +433,26 @@ __global__ void __launch_bounds__(128)
   if (first >= 0) {
     const int start = first + T;
     len = n - start;
-    if ((((uintptr_t)o) & 3) == 0) {
+    if (len >= 64) {
+      // shifted copy, 16 bytes per lane and pass: up to 15 head bytes bring the output to a 16-byte boundary, then five
+      // aligned shared-memory words are funnel-shifted into four output words (the staged row is 16-byte aligned and
+      // the words around the payload lie inside the CTA's shared memory; only bytes below n enter the result)
+      const int head = (int)((16 - (((uintptr_t)o) & 15)) & 15);
+      if (lane < head) o[lane] = row[start + lane];
+      const int st2 = start + head, len2 = len - head;
+      const int sh = (st2 & 3) * 8;
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(row) + (st2 >> 2);
+      uint4* o16 = reinterpret_cast<uint4*>(o + head);
+      const int nq = len2 >> 4;
+      for (int i = lane; i < nq; i += 32) {
+        const uint32_t* w = rw + 4 * i;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        const uint32_t w4 = sh ? w[4] : 0u;
+        o16[i] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                            __funnelshift_r(w3, w4, sh));
+      }
+      for (int i = 16 * nq + lane; i < len2; i += 32) o[head + i] = row[st2 + i];
+    } else if ((((uintptr_t)o) & 3) == 0) {
       uint32_t* o4 = reinterpret_cast<uint32_t*>(o);
       const int nw = len >> 2;
       for (int i = lane; i < nw; i += 32) {
