@@ -367,8 +367,11 @@ def main():
         del y
         torch.cuda.empty_cache()
         k = max(1, min(args.steps, 3))
-        chain = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=False, hbm_peak=hbm_peak)
-        chain_fll = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=True, hbm_peak=hbm_peak)
+        cpu_legs = rank == 0 and world == 1 and not args.no_cpu
+        chain = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=False, hbm_peak=hbm_peak,
+                                      cpu=cpu_legs)
+        chain_fll = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=True, hbm_peak=hbm_peak,
+                                          cpu=cpu_legs)
         modulator = bench_chain.run_modulator(Q, torch, d, world, rank, stream, steps=k, warmup=3, hbm_peak=hbm_peak)
         stream_leg = bench_chain.run_stream(Q) if (rank == 0 and world == 1 and not args.no_cpu) else None
 

@@ -20,8 +20,38 @@ import numpy as np
 TSC = "11001010011101100100100110101100" + "01110100111001011010001101101001"
 
 
+def _chain_cpu_baseline(rx_host, fs, rs, alpha, use_fll, bursts_per_core=128, passes=16):
+    """The oracle's restatement of the same demodulator chain (QPSKDeModulator.DeModulate) on all host cores: one
+    demodulator per core fed `bursts_per_core` bursts back to back, threads = cores (the library releases the GIL)."""
+    import os
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    n = min(rx_host.shape[0], cores * bursts_per_core)
+    rows = [rx_host[c] for c in range(n)]
+
+    def work(t):
+        done = 0
+        d = O.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC, use_fll=use_fll)   # one stream of bursts per core
+        for _ in range(passes):
+            for c in range(t, n, cores):
+                d.DeModulate(rows[c])
+                done += rows[c].size // 2
+        return done
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        samples = sum(ex.map(work, range(cores)))
+    dt = time.perf_counter() - t0
+    return {"value": samples / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port", "seconds": dt,
+            "sample": f"{passes} passes over {n} of the bursts ({n // cores} per core), C++ restatement of QPSKDeModulator.DeModulate"
+                      f"{' with the FLL' if use_fll else ''}, one demodulator per core"}
+
+
 def run_chain(Q, torch, dist, world, rank, stream, steps=3, warmup=3, channels_per_gpu=2048, use_fll=False,
-              n_payload=512, hbm_peak=6461.8):
+              n_payload=512, hbm_peak=6461.8, cpu=False):
     from qpsk_modulator_demodulator_b200 import shard
     fs = 10_000_000
     rs = fs // 2
@@ -84,7 +114,12 @@ def run_chain(Q, torch, dist, world, rank, stream, steps=3, warmup=3, channels_p
     allc = allc.cpu().numpy().astype(np.int64)
     samples = total_channels * (ff // 2) * steps
     gbs = 8.0 * samples / world / (ms * 1e-3) / 1e9   # per GPU: 8 B read per complex sample (fused ideal)
+    cpu_leg = None
+    if cpu and rank == 0:
+        ncpu = min(C, 128 * (__import__("os").cpu_count() or 1))
+        cpu_leg = _chain_cpu_baseline(rx[0][:ncpu].cpu().numpy(), fs, rs, alpha, use_fll)
     return {
+        "cpu_baseline": cpu_leg,
         "workload": f"{total_channels} channels ({C}/GPU) x {ff // 2} cf32 samples per burst, "
                     f"{'FLL -> ' if use_fll else ''}MF(21 taps) -> MM -> Costas -> decode -> TSC strip -> BER; {K} burst sets cycled "
                     f"({set_bytes * K / 1e6:.0f} MB > L2)",
