@@ -1,5 +1,5 @@
-// fll_duo.cu — K4, the band-edge FLL (MS/Models/Band-Edge Filter.cs:102-129,185-195) for N = 8*K taps:
-// two warps per four streams, the per-sample recurrence alone on one of them.
+// fll_duo.cu — K4, the band-edge FLL (MS/Models/Band-Edge Filter.cs:102-129,185-195) for N = 8*K + TAIL taps,
+// 8 <= N <= 55: two warps per four streams, the per-sample recurrence alone on one of them.
 //
 // Why two warps.  With a few thousand streams there is about one FLL warp per warp scheduler, and a lone warp
 // issues in order: every instruction that is not on the loop-carried chain
@@ -12,15 +12,18 @@
 //     flush, state load/store).  It runs one batch (4 samples) ahead and hands results over through shared memory
 //     with mbarriers; its latencies never touch the chain.
 //
-// Order of additions (bit-identical to ComplexDotWindow, FIRFilter.cs:165-192, for N % 8 == 0):
+// Order of additions (bit-identical to ComplexDotWindow, FIRFilter.cs:165-192):
 //   window n, SIMD lane l:   L_l(n) = (((0 + e_{l}) + e_{l+8}) + ...) + e_{l+8(K-1)},  e_i = tap_rev[i] (x) out[n-(N-1)+i]
-//   horizontal sum:          acc(n) = ((((((0 + L_0) + L_1) + ...) + L_6) + L_7
-// The last element of lane l in window m is out[m-7+l], so at step n (out[n] just computed) GPU lane g finishes
-// L_g of window m = n+7-g and extends that window's prefix  P_g(m) = P_{g-1}(m) + L_g(m)  with the value lane g-1
-// produced one step earlier (one SHFL, issued before the rotation is known): the horizontal sum is a systolic
-// pipeline across the 8 lanes and across time, and nothing but register arithmetic follows the rotation.  Every
-// lane also plays lane 7's role for the current window (acc(n) = P_6(n) + L_7(n)), redundantly, so the loop state
-// (phase, freq) stays uniform in the group without a broadcast on the chain.
+//   horizontal sum:          P_7(n) = ((((((0 + L_0) + L_1) + ...) + L_6) + L_7
+//   scalar tail (:183-192):  acc(n) = (P_7(n) + e_{8K}) + ... + e_{N-1}                      (TAIL = N % 8 elements)
+// The last vector element of lane l in window m is out[m-TAIL-7+l], so at step n (out[n] just computed) GPU lane g
+// finishes L_g of window m = n+TAIL+7-g and extends that window's prefix  P_g(m) = P_{g-1}(m) + L_g(m)  with the value
+// lane g-1 produced one step earlier (handed over through shared memory, read before the rotation is known): the
+// horizontal sum is a systolic pipeline across the 8 lanes and across time, and nothing but register arithmetic
+// follows the rotation.  TAIL == 0: every lane also plays lane 7's role for the current window (acc(n) = P_6(n) +
+// L_7(n)), redundantly, so the loop state (phase, freq) stays uniform in the group without a broadcast on the chain.
+// TAIL > 0: the tail elements are TAIL more pipeline stages, T_j = T_{j-1} + e_{8K+j}, that every lane runs in registers
+// from lane 7's prefix of the previous step; the last stage closes window n.
 #include "loops.cuh"
 
 #include <stdlib.h>
