@@ -229,7 +229,28 @@ __global__ void __launch_bounds__(128)
   const long long have = n_rx[c];
   const long long n = have < n_ref ? have : n_ref;
   unsigned err = 0;
-  for (long long i = lane; i < n; i += 32) err += (r[i] != f[i]) ? 1u : 0u;
+  // head bytes up to a 4-byte boundary of r, then one aligned word of r against two aligned words of f funnel-shifted
+  // to the same bytes (byte loads made this a 128-iteration latency chain per lane), then the tail bytes
+  const long long head = (long long)((4 - (reinterpret_cast<uintptr_t>(r) & 3)) & 3) < n
+                             ? (long long)((4 - (reinterpret_cast<uintptr_t>(r) & 3)) & 3) : n;
+  if (lane < head) err += (r[lane] != f[lane]) ? 1u : 0u;
+  const long long nw = (n - head) >> 2;
+  if (nw > 0) {
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(r + head);
+    const uint8_t* fb = f + head;
+    const int foff = (int)(reinterpret_cast<uintptr_t>(fb) & 3);
+    const uint32_t* fw = reinterpret_cast<const uint32_t*>(fb - foff);
+    const int sh = 8 * foff;
+#pragma unroll 4
+    for (long long i = lane; i < nw; i += 32) {
+      const uint32_t a = rw[i];
+      const uint32_t lo = fw[i];
+      const uint32_t hi = sh ? fw[i + 1] : 0u;               // holds bytes of this word whenever sh != 0
+      const uint32_t b = __funnelshift_r(lo, hi, sh);
+      err += (unsigned)__popc(__vcmpne4(a, b)) >> 3;
+    }
+  }
+  for (long long i = head + 4 * nw + lane; i < n; i += 32) err += (r[i] != f[i]) ? 1u : 0u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
   if (lane == 0) {

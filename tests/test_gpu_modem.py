@@ -473,6 +473,36 @@ def test_ber_counters_and_unpack(gpu):
     assert got[:, 1].tolist() == [nref] * Cn
 
 
+@pytest.mark.parametrize("rx_stride,ref_stride,n_ref", [(1203, 1001, 997), (1202, 1000, 1000), (1201, 1003, 999), (1207, 1006, 3)])
+def test_ber_counters_unaligned_rows(gpu, rx_stride, ref_stride, n_ref):
+    """ber_kernel compares word-wise with funnel shifts: odd row pitches put every channel's rx / ref row at a
+    different byte alignment; arbitrary byte values (not only 0/1) must still compare as bytes."""
+    import torch
+    rng = np.random.default_rng(rx_stride)
+    Cn = 9
+    ref = rng.integers(0, 256, (Cn, ref_stride), dtype=np.uint8)
+    rx = rng.integers(0, 256, (Cn, rx_stride), dtype=np.uint8)
+    n_rx = rng.integers(0, n_ref + 40, Cn).astype(np.int64)
+    n_rx[0], n_rx[1] = n_ref, 0
+    for c in range(Cn):
+        m = int(min(n_rx[c], n_ref))
+        rx[c, :m] = ref[c, :m]
+        if m:
+            idx = rng.choice(m, min(m, 5 + c), replace=False)
+            rx[c, idx] ^= rng.integers(1, 256, idx.size, dtype=np.uint8)
+    want = [int((rx[c, :min(n_rx[c], n_ref)] != ref[c, :min(n_rx[c], n_ref)]).sum() + max(0, n_ref - n_rx[c])) for c in range(Cn)]
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    s = ts.cuda_stream
+    d_rx, d_ref, d_n = torch.from_numpy(rx).cuda(), torch.from_numpy(ref).cuda(), torch.from_numpy(n_rx).cuda()
+    cnt = torch.zeros((Cn, 2), dtype=torch.int32, device="cuda")
+    gpu.ber_count_dev(d_rx.data_ptr(), rx_stride, d_n.data_ptr(), d_ref.data_ptr(), ref_stride, n_ref, Cn, cnt.data_ptr(), s)
+    torch.cuda.synchronize()
+    got = cnt.cpu().numpy()
+    assert got[:, 0].tolist() == want
+    assert got[:, 1].tolist() == [n_ref] * Cn
+
+
 def test_batched_chain_device_resident_ber(gpu, orc):
     """config 3/4 at test size, fully device-resident: payload -> modulate -> channel -> demod -> BER.
     Parameters of testAtDataLevel.cs (the configuration in which the reference loops lock)."""
