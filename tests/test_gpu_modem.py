@@ -555,6 +555,25 @@ def test_batched_chain_device_resident_ber(gpu, orc):
 
 
 # ---- packed-bit I/O ------------------------------------------------------------------
+@pytest.mark.parametrize("tlen", [1, 3, 8, 31, 32, 33, 63, 64, 65, 100])
+def test_demod_tsc_strip_lengths(gpu, orc, tlen):
+    """TSC strip (QPSKDeModulator.cs:413-422): the bit-parallel search serves 1..64-bit sequences, longer ones take the
+    byte search; both must cut where the oracle's IndexOf does (or return "" when the sequence is absent)."""
+    rng = np.random.default_rng(100 + tlen)
+    tsc = "".join(rng.choice(["0", "1"], tlen))
+    fs, rs = 4000, 1000
+    mod = orc.QPSKModulator(fs, rs, 0.35, 10, True, tsc)
+    x = np.concatenate([mod.Modulate(_bits(2 * (150 + 7 * k), 7 + k)) for k in range(3)])
+    kw = dict(RrcAlpha=0.35, rrcSpan=10, SymbolSyncBandwith=0.002, tsc=tsc)
+    want = orc.QPSKDeModulator(fs, rs, **kw).DeModulate(x)
+    got = gpu.QPSKDeModulator(fs, rs, **kw).DeModulate(x)
+    assert got == want
+    # a sequence that is not in the stream, and one with a character that is neither '0' nor '1'
+    for absent in ("01" * 30 + "0011", tsc[:-1] + "x" if tlen > 1 else "x"):
+        kw2 = dict(kw, tsc=absent)
+        assert gpu.QPSKDeModulator(fs, rs, **kw2).DeModulate(x) == orc.QPSKDeModulator(fs, rs, **kw2).DeModulate(x)
+
+
 @pytest.mark.parametrize("diff,tsc,nbits", [(True, TSC, 600), (False, None, 4096), (True, None, 13), (True, TSC, 0), (False, TSC, 7)])
 def test_modulate_packed_equals_bit_string(gpu, orc, diff, tsc, nbits):
     rng = np.random.default_rng(nbits + 1)
