@@ -355,6 +355,222 @@ __global__ void __launch_bounds__(NT + 32, R <= 6 ? 3 : 2)
 }
 
 // ---------------------------------------------------------------------------------------------
+// fir_exact_real_kernel: QPSK_FIR_EXACT for real taps on the TMA pipeline
+// ---------------------------------------------------------------------------------------------
+// ComplexDotWindow's arithmetic (FIRFilter.cs:144-211, Vector<float>.Count == 8) bit for bit: window element i (oldest
+// first) goes to lane partial i mod 8, each product and each sum rounded separately (no FMA), lanes added 0..7, then the
+// N mod 8 tail elements one by one.  With real taps (imaginary parts +0, FIRFilter.cs users: QPSKDeModulator.cs:278-288)
+// the reference's complex product tI = hi*xI - hq*xQ, tQ = hi*xQ + hq*xI reduces to (hi*xI, hi*xQ): the hq terms are +-0,
+// and adding +-0 to an accumulator that starts at +0 never changes it (an accumulator is +0 or nonzero, never -0), so
+// dropping them leaves every bit of every partial sum unchanged.  That makes it two packed instructions per tap and
+// output (one mul.rn.f32x2 and two add.rn.f32) instead of eight scalar ones — about half the speed of the FMA kernel, against a
+// fourteenth for the one-thread-per-output kernel below.
+// Thread = 2 consecutive outputs (16-byte stride: conflict-free LDS/STS), 8 lane partials each, 8 taps per block with
+// a 9-sample register window; the tile pipeline (producer warp, full/empty mbarriers, per-warp TMA store) is the FMA
+// kernel's.
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+// The sum that follows a product is formed with the scalar add.rn intrinsics: ptxas contracts mul.rn.f32x2 feeding
+// add.rn.f32x2 into FFMA2 (even under --fmad=false), which rounds once where the reference rounds twice; scalar
+// add.rn is never contracted.  Sums of sums (the lane reduction) may use the packed add.
+__device__ __forceinline__ float2 fadd2_after_mul(float2 a, float2 prod) {
+  return make_float2(__fadd_rn(a.x, prod.x), __fadd_rn(a.y, prod.y));
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT + 32, 3)
+    fir_exact_real_kernel(const __grid_constant__ FirArgs a, const __grid_constant__ TapsReal taps, const int n_taps) {
+  constexpr int R = 2;
+  constexpr int T = R * NT;
+  constexpr int WS = 32 * R;   // outputs per consumer warp and tile
+  constexpr int NW = NT / 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* xs_base = reinterpret_cast<float2*>(smem_raw);
+  float2* ys_base = xs_base + (size_t)a.stages * a.stage_elems;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ys_base + 2 * T);
+  uint64_t* empty = full + a.stages;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // producer warp: the FMA kernel's staging (tile + halo by TMA bulk copies, zeros outside the stream)
+    int stage = 0;
+    uint32_t parity = 0;
+    TileWalk w(a.tiles_per_ch);
+    for (int it = 0; w.tile < a.total_tiles; ++it, w.next()) {
+      if (it >= a.stages) mbar_wait(&empty[stage], parity ^ 1u);
+      const int ch = w.ch;
+      const long long n0 = (long long)w.k * T;
+      const long long s0 = n0 + a.advance - a.HL;
+      float2* dst = xs_base + (size_t)stage * a.stage_elems;
+      const float2* xch = a.x + (long long)ch * a.ldx;
+      uint64_t* bar = &full[stage];
+      const int E = a.E_load;
+      uint32_t tx = 0;
+      int nA = 0;
+      if (s0 < 0) {
+        nA = (int)((-s0) < (long long)E ? (-s0) : (long long)E);
+        if (a.hist_in) {
+          if (lane == 0) bulk_g2s(dst, a.hist_in + (long long)ch * a.HL + (a.HL + s0), (uint32_t)nA * 8u, bar);
+          tx += (uint32_t)nA * 8u;
+        } else {
+          for (int i = lane; i < nA; i += 32) dst[i] = make_float2(0.f, 0.f);
+        }
+      }
+      const long long m0 = s0 + nA;
+      long long avail = a.L - m0;
+      if (avail < 0) avail = 0;
+      const int nB = (int)(avail < (long long)(E - nA) ? avail : (long long)(E - nA));
+      const int nB2 = nB & ~1;
+      if (nB2 > 0) {
+        if (lane == 0) bulk_g2s(dst + nA, xch + m0, (uint32_t)nB2 * 8u, bar);
+        tx += (uint32_t)nB2 * 8u;
+      }
+      if ((nB & 1) && lane == 0) dst[nA + nB2] = xch[m0 + nB2];
+      for (int i = nA + nB + lane; i < E; i += 32) dst[i] = make_float2(0.f, 0.f);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(bar, tx);
+      if (++stage == a.stages) {
+        stage = 0;
+        parity ^= 1u;
+      }
+    }
+    return;
+  }
+
+  // consumer warps
+  const int lead = a.HL - (n_taps - 1);      // 0 or 1: xs index of window element 0 relative to the output index
+  const int n_vec = n_taps & ~7;
+  const int base = tid * R;
+  float2* ys_warp = ys_base + (size_t)warp * (2 * WS);
+  int stage = 0;
+  uint32_t parity = 0;
+  TileWalk tw(a.tiles_per_ch);
+  for (int it = 0; tw.tile < a.total_tiles; ++it, tw.next()) {
+    mbar_wait(&full[stage], parity);
+    const float2* xs = xs_base + (size_t)stage * a.stage_elems;
+    const int ch = tw.ch;
+    const long long n0 = (long long)tw.k * T;
+    const long long left = a.L - n0;
+    const int valid = (int)(left < (long long)T ? left : (long long)T);
+    if (a.hist_out && tw.k == a.tiles_per_ch - 1) {
+      const int off = (int)(a.L - n0);
+      float2* ho = a.hist_out + (long long)ch * a.HL;
+      for (int i = tid; i < a.HL; i += NT) ho[i] = xs[off + i];
+    }
+    float2 lp[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int l = 0; l < 8; ++l) lp[r][l] = make_float2(0.f, 0.f);
+    const float2* xw = xs + base + lead;         // window element i of output r is xw[i + r]
+    float2 w0 = xw[0];
+    for (int ib = 0; ib < n_vec; ib += 8) {
+      float2 wv[9];
+      wv[0] = w0;
+#pragma unroll
+      for (int j = 1; j < 9; ++j) wv[j] = xw[ib + j];
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const float g = taps.g[ib + l + lead];
+        const float2 gg = make_float2(g, g);
+#pragma unroll
+        for (int r = 0; r < R; ++r) lp[r][l] = fadd2_after_mul(lp[r][l], fmul2(wv[l + r], gg));
+      }
+      w0 = wv[8];
+    }
+    float2 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int l = 0; l < 8; ++l) acc[r] = fadd2(acc[r], lp[r][l]);   // lanes 0..7 (:176-180)
+    }
+    for (int i = n_vec; i < n_taps; ++i) {                             // scalar tail (:183-192)
+      const float g = taps.g[i + lead];
+      const float2 gg = make_float2(g, g);
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fadd2_after_mul(acc[r], fmul2(xw[i + r], gg));
+    }
+    // Non-finite results: an infinite SAMPLE makes the reference's hq*x terms NaN (0 * Inf), which the reduction above
+    // does not model — recompute such outputs with the full complex product (an overflow to Inf gives the same value
+    // either way).
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!(fabsf(acc[r].x) <= 3.402823466e+38f) || !(fabsf(acc[r].y) <= 3.402823466e+38f)) {
+        float lI[8], lQ[8];
+        for (int l = 0; l < 8; ++l) lI[l] = lQ[l] = 0.f;
+        for (int i = 0; i < n_vec; ++i) {
+          const float2 xv = xw[i + r];
+          const float hi = taps.g[i + lead], hq = 0.f;
+          lI[i & 7] = __fadd_rn(lI[i & 7], __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y)));
+          lQ[i & 7] = __fadd_rn(lQ[i & 7], __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x)));
+        }
+        float aI = 0.f, aQ = 0.f;
+        for (int l = 0; l < 8; ++l) {
+          aI = __fadd_rn(aI, lI[l]);
+          aQ = __fadd_rn(aQ, lQ[l]);
+        }
+        for (int i = n_vec; i < n_taps; ++i) {
+          const float2 xv = xw[i + r];
+          const float hi = taps.g[i + lead], hq = 0.f;
+          aI = __fadd_rn(aI, __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y)));
+          aQ = __fadd_rn(aQ, __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x)));
+        }
+        acc[r] = make_float2(aI, aQ);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+
+    float2* ys = ys_warp + (size_t)(it & 1) * WS;
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+    *reinterpret_cast<float4*>(ys + lane * R) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+    fence_proxy_async_smem();
+    __syncwarp();
+    int wvalid = valid - warp * WS;
+    wvalid = wvalid < 0 ? 0 : (wvalid > WS ? WS : wvalid);
+    float2* yg = a.y + (long long)ch * a.ldy + n0 + (long long)warp * WS;
+    if ((wvalid & 1) == 0) {
+      if (lane == 0) {
+        if (wvalid > 0) bulk_s2g(yg, ys, (uint32_t)wvalid * 8u);
+        bulk_commit();
+      }
+    } else {
+      for (int i = lane; i < wvalid; i += 32) yg[i] = ys[i];
+      if (lane == 0) bulk_commit();
+    }
+    if (++stage == a.stages) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  if (lane == 0) bulk_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic kernel: exact reference order / unaligned / very long filters
 // ---------------------------------------------------------------------------------------------
 struct GenArgs {
@@ -627,6 +843,45 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
       }
       if (!stateless) cur ^= 1;
       return QPSK_OK;
+    }
+  }
+
+  // QPSK_FIR_EXACT with real taps: the reference's summation order on the TMA pipeline (fir_exact_real_kernel)
+  if (mode == QPSK_FIR_EXACT && !stateless && real_taps && N >= 8 && aligned16(x) && aligned16(y) &&
+      !(channels > 1 && ((ldx & 1) || (ldy & 1)))) {
+    constexpr int kENT = 256, kET = 2 * kENT;
+    const int GE = (HL + 1 + 1) & ~1;
+    if (GE <= kMaxG && HL <= kET) {
+      FirArgs a;
+      a.x = x; a.y = y; a.ldx = ldx; a.ldy = ldy; a.L = L;
+      a.hist_in = hin; a.hist_out = hout;
+      a.tiles_per_ch = (int)((L + kET - 1) / kET);
+      a.total_tiles = (long long)a.tiles_per_ch * channels;
+      a.HL = HL; a.G = GE; a.advance = 0;
+      a.E_load = kET + GE;
+      a.stage_elems = a.E_load + 2;
+      const size_t stage_bytes = (size_t)a.stage_elems * 8;
+      const size_t out_bytes = (size_t)2 * kET * 8;
+      int stages = (int)((72 * 1024 - out_bytes - 128) / stage_bytes);
+      if (stages > 4) stages = 4;
+      if (stages >= 2) {
+        a.stages = stages;
+        const size_t smem = (size_t)stages * stage_bytes + out_bytes + (size_t)stages * 16;
+        long long grid = 3LL * device_sm_count();
+        if (grid > a.total_tiles) grid = a.total_tiles;
+        TapsReal t;
+        memset(&t, 0, sizeof t);
+        for (int i = 0; i <= HL; ++i) {
+          const int j = HL - i;
+          t.g[i] = (j < N) ? taps_iq[2 * j] : 0.0f;
+        }
+        auto kern = fir_exact_real_kernel<kENT>;
+        QPSK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(int)grid, kENT + 32, smem, s>>>(a, t, N);
+        QPSK_LAUNCH_CHECK();
+        cur ^= 1;
+        return QPSK_OK;
+      }
     }
   }
 

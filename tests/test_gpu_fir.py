@@ -58,6 +58,36 @@ def test_exact_mode_is_bit_identical_to_reference_order(gpu, orc, ntaps, cplx):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("ntaps", [8, 9, 16, 24, 41, 64, 130])
+def test_exact_mode_real_taps_special_values(gpu, orc, ntaps):
+    """The exact-order TMA kernel for real taps drops the reference's (+-0 * sample) terms; that must stay bit-neutral
+    for zeros of either sign, denormals and exact cancellations, and infinite / NaN samples (where 0 * Inf = NaN in the
+    reference) must come out as the reference's NaNs.  Several tiles, chunked calls, odd lengths."""
+    rng = np.random.default_rng(7 * ntaps)
+    taps = np.zeros(2 * ntaps, np.float32)
+    taps[0::2] = (rng.standard_normal(ntaps) / np.sqrt(ntaps)).astype(np.float32)
+    taps[2 * (ntaps // 3)] = 0.0                      # a zero tap
+    if ntaps > 10:
+        taps[2 * 5 + 1] = -0.0                        # an imaginary part of -0 is still "real taps"
+    x = _rand_iq(orc, 3001, seed=ntaps)
+    x[100:160] = 0.0
+    x[200:230] = -0.0
+    x[300:310] = np.float32(1e-42)                    # denormals
+    x[400] = np.inf
+    x[1501] = -np.inf
+    x[2200] = np.nan
+    x[2600:2604] = [1.0, -1.0, -1.0, 1.0]
+    want_f = orc.ComplexFIRFilter(taps)
+    got_f = gpu.ComplexFIRFilter(taps)
+    got_f.set_mode(gpu.FIR_EXACT)
+    for a, b in [(0, 2 * 700), (2 * 700, 2 * 701), (2 * 701, x.size)]:
+        want = want_f.Filter(x[a:b])
+        got = got_f.Filter(x[a:b])
+        wn, gn = np.isnan(want), np.isnan(got)
+        assert np.array_equal(wn, gn)
+        assert np.array_equal(got.view(np.uint32)[~wn], want.view(np.uint32)[~wn])
+
+
 @pytest.mark.parametrize("mode", ["fast", "exact"])
 def test_chunked_equals_one_shot(gpu, orc, mode):
     """State carried across calls: arbitrary chunking gives the same stream."""
