@@ -85,6 +85,22 @@ def test_fll_two_warp_kernel_sizes_and_chunking(gpu, orc, size):
     assert got_f.state == want_f.state
 
 
+@pytest.mark.parametrize("channels,size", [(700, 40), (1500, 40), (1500, 13)])
+def test_fll_many_channels_identical_streams(gpu, orc, channels, size):
+    """Every channel gets the same samples: all rows of the batched output must equal the oracle's single stream bit
+    for bit.  Loads every SM with chain / side warp pairs (one pair per CTA below 1280 streams, four above), which is
+    where a hand-over or ordering bug between the two warps would show."""
+    x, _ = _qpsk_burst(orc, 1200, sps=4, alpha=0.35, cfo=0.02, noise=0.05, seed=3)
+    X = np.ascontiguousarray(np.broadcast_to(x, (channels, x.size)))
+    f = gpu.FLLBandEdgeFilter(4.0, 0.35, size, 0.05, channels=channels)
+    o = orc.FLLBandEdgeFilter(4.0, 0.35, size, 0.05)
+    cut = 2 * 1111
+    for a, b in [(0, cut), (cut, x.size)]:
+        want = o.Process(x[a:b])
+        got = f.Process(np.ascontiguousarray(X[:, a:b]))
+        assert np.array_equal(got.view(np.uint32), np.broadcast_to(want.view(np.uint32), got.shape))
+
+
 def test_fll_phase_wrap_and_wild_state(gpu, orc):
     """A large loop bandwidth drives the phase past +-2*pi every few samples (the wrap path, Band-Edge Filter.cs:185-189);
     a caller-set phase far outside the loop's range must take the generic kernel and still match."""
