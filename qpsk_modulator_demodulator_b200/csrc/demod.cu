@@ -867,7 +867,9 @@ struct DemodEngine {
       QPSK_TRY(mm.ensure_queue(8, s));
       QPSK_TRY(ensure_pipeline(chunks));
       auto kern = diff ? symsync_decode_kernel<true> : symsync_decode_kernel<false>;
-      const int64_t step = ((L + chunks - 1) / chunks + kSsBlock - 1) / kSsBlock * kSsBlock;
+      // equal chunks except a half-size last one: the FLL on the side stream is the critical resource throughout, so
+      // what is left exposed at the end is the last chunk's MM -> Costas -> decode
+      const int64_t step = ((2 * L + 2 * chunks - 2) / (2 * chunks - 1) + kSsBlock - 1) / kSsBlock * kSsBlock;
       QPSK_CUDA_TRY(cudaEventRecord(ev_in, s));
       QPSK_CUDA_TRY(cudaStreamWaitEvent(side, ev_in, 0));     // inputs (and the previous call) are complete
       int t = 0;
