@@ -366,7 +366,7 @@ def main():
         torch.cuda.synchronize()
         del y
         torch.cuda.empty_cache()
-        k = max(1, min(args.steps, 3))
+        k = max(1, min(args.steps, 10))
         cpu_legs = rank == 0 and world == 1 and not args.no_cpu
         chain = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=False, hbm_peak=hbm_peak,
                                       cpu=cpu_legs)
