@@ -163,6 +163,21 @@ def test_batch_channels_are_independent(gpu, orc):
         assert np.abs(got[c] - want).max() <= REL_TOL * np.abs(want).max()
 
 
+def test_exact_mode_batch_channels(gpu, orc):
+    """QPSK_FIR_EXACT over several channels with an even row pitch (TMA path) and with an odd one (generic kernel):
+    every channel bit-identical to its own single-stream oracle, state carried over two calls."""
+    taps = _rrc_iq(orc, 10, 4)
+    C = 5
+    for L in (3000, 3001):
+        x = np.stack([_rand_iq(orc, L, seed=31, stream=c) for c in range(C)])
+        f = gpu.ComplexFIRFilter(taps, channels=C)
+        f.set_mode(gpu.FIR_EXACT)
+        got = np.concatenate([f.Filter(np.ascontiguousarray(x[:, :2 * 1700])), f.Filter(np.ascontiguousarray(x[:, 2 * 1700:]))], axis=1)
+        for c in range(C):
+            want = orc.ComplexFIRFilter(taps).Filter(x[c])
+            assert np.array_equal(got[c].view(np.uint32), want.view(np.uint32)), (L, c)
+
+
 def test_error_behaviour_matches_reference(gpu, orc):
     Q, O = gpu, orc
     for mod in (Q, O):

@@ -101,6 +101,23 @@ def test_fll_many_channels_identical_streams(gpu, orc, channels, size):
         assert np.array_equal(got.view(np.uint32), np.broadcast_to(want.view(np.uint32), got.shape))
 
 
+@pytest.mark.parametrize("sps,size,L", [(0.5, 40, 300), (1.0, 10, 1), (3.0, 24, 2), (4.0, 40, 3), (2.0, 55, 5), (16.0, 8, 77)])
+def test_fll_two_warp_kernel_short_calls_and_odd_rates(gpu, orc, sps, size, L):
+    """Calls shorter than one hand-over batch (1..5 samples), repeated, and symbol rates that make the frequency limit
+    large (sps 0.5: +-8 pi per sample, the phase wraps on most samples)."""
+    x, _ = _qpsk_burst(orc, 400, sps=4, alpha=0.35, cfo=0.05, noise=0.05, seed=int(10 * sps) + size)
+    want_f = orc.FLLBandEdgeFilter(sps, 0.35, size, 0.2)
+    got_f = gpu.FLLBandEdgeFilter(sps, 0.35, size, 0.2)
+    pos = 0
+    for k in range(12):
+        n = L if k % 3 else L + 4 * k
+        want = want_f.Process(x[pos:pos + 2 * n])
+        got = got_f.Process(x[pos:pos + 2 * n])
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (k, n)
+        pos += 2 * n
+    assert got_f.state == want_f.state
+
+
 def test_fll_phase_wrap_and_wild_state(gpu, orc):
     """A large loop bandwidth drives the phase past +-2*pi every few samples (the wrap path, Band-Edge Filter.cs:185-189);
     a caller-set phase far outside the loop's range must take the generic kernel and still match."""
