@@ -199,16 +199,24 @@ QPSK_API int qpsk_demod_set_fir_mode(qpsk_demod* d, int mode);
  * other host entry points below). */
 QPSK_API int qpsk_demod_bits(qpsk_demod* d, const float* iq_in, int64_t n_floats, char* bits_out,
                              int64_t cap, int64_t* n_bits);
-/* DeModulateBytes :169-259 (DeModulateTextUtf8 :262-277 = this + UTF-8 decode) */
 /* §8f-4: DeModulate with the bits packed MSB-first, 8 per byte (BitPacker.BitsToBytes(bits, 0), HelperFunctions.cs:32-57,
  * except that a trailing incomplete byte is kept, zero-padded; n_bits[c] is the exact bit count).  packed_out is
  * [channels][cap_bytes].  One eighth of the device-to-host traffic of the char form. */
 QPSK_API int qpsk_demod_bits_packed(qpsk_demod* d, const float* iq_in, int64_t n_floats, uint8_t* packed_out,
                                     int64_t cap_bytes, int64_t* n_bits);
+/* DeModulateBytes :169-259 (DeModulateTextUtf8 :262-277 = this + UTF-8 decode) */
 QPSK_API int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_floats,
                               const uint8_t* start_marker, int64_t n_start,
                               const uint8_t* end_marker, int64_t n_end,
                               uint8_t* payload_out, int64_t cap, int64_t* n_bytes);
+/* The framer half of DeModulateBytes (:182-259: carry + offset hunt :185-236, ring append and end-marker search
+ * :238-258) on bits the caller already holds — what DeModulateBytes does after its DeModulate call (:177), sharing the
+ * handle's framer state with qpsk_demod_bytes.  bits is HOST memory, [channels][bits_stride], one byte 0/1 per bit,
+ * n_bits[channels] of them used; a channel with n_bits == 0 returns nothing and keeps its state (:179-180). */
+QPSK_API int qpsk_demod_frame_bits(qpsk_demod* d, const uint8_t* bits, int64_t bits_stride, const int64_t* n_bits,
+                                   const uint8_t* start_marker, int64_t n_start,
+                                   const uint8_t* end_marker, int64_t n_end,
+                                   uint8_t* payload_out, int64_t cap, int64_t* n_bytes);
 /* deModulateConstellation :427-455 */
 QPSK_API int qpsk_demod_constellation(qpsk_demod* d, const float* iq_in, int64_t n_floats,
                                       float* sym_iq_out, int64_t cap_floats, int64_t* n_sym);

@@ -105,6 +105,7 @@ def _declare(L):
         "orc_demod_destroy": (None, [vp]),
         "orc_demod_bits": (i, [vp, _f32p, i64, cp, i64, i64p]),
         "orc_demod_bytes": (i, [vp, _f32p, i64, _u8p, i64, _u8p, i64, _u8p, i64, i64p]),
+        "orc_demod_frame_bits": (i, [vp, C.c_char_p, i64, _u8p, i64, _u8p, i64, _u8p, i64, i64p]),
         "orc_demod_constellation": (i, [vp, _f32p, i64, _f32p, i64, i64p]),
         "orc_demod_loop_state": (None, [vp, _f64p, _f64p, _f64p, _f64p, _f32p, _f32p]),
         "orc_demod_in_frame": (i, [vp]),
@@ -391,7 +392,7 @@ class QPSKModulator(_Handle):
         _check(lib().orc_mod_modulate_bytes(*args, _fp(out), out.size, C.byref(n)))
         return out
 
-    def ModulateTextUtf8(self, text: str, startMarker="", endMarker="", pulseShaping=True) -> np.ndarray:
+    def ModulateTextUtf8(self, text: str, startMarker="\x02", endMarker="\x03", pulseShaping=True) -> np.ndarray:
         if text is None:
             raise ArgumentNullException()
         return self.ModulateBytes(text.encode("utf-8"), startMarker.encode("utf-8"), endMarker.encode("utf-8"), pulseShaping)
@@ -427,7 +428,16 @@ class QPSKDeModulator(_Handle):
         _check(lib().orc_demod_bytes(self._h, _fp(x), x.size, _up(s), s.size, _up(e), e.size, _up(out), out.size, C.byref(n)))
         return out[: n.value].tobytes()
 
-    def DeModulateTextUtf8(self, samplesIQ, startMarker="", endMarker="") -> str:
+    def FrameBits(self, bits: str, startMarker: bytes, endMarker: bytes, cap: int = 0) -> bytes:
+        """DeModulateBytes from the point where it holds rxBits (:179-259)."""
+        s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
+        raw = bits.encode("ascii")
+        out = np.empty(cap or (len(raw) // 8 + 64), np.uint8)
+        n = C.c_int64(0)
+        _check(lib().orc_demod_frame_bits(self._h, raw, len(raw), _up(s), s.size, _up(e), e.size, _up(out), out.size, C.byref(n)))
+        return out[: n.value].tobytes()
+
+    def DeModulateTextUtf8(self, samplesIQ, startMarker="\x02", endMarker="\x03") -> str:
         p = self.DeModulateBytes(samplesIQ, startMarker.encode("utf-8"), endMarker.encode("utf-8"))
         return p.decode("utf-8", errors="replace") if p else ""
 

@@ -432,7 +432,12 @@ class QPSKDeModulator:
     def DeModulateBytes(self, iq, sm: bytes, em: bytes) -> bytes:
         if len(sm) == 0 or len(em) == 0:
             raise ValueError("marker")
-        rx = self.DeModulate(iq)
+        return self.FrameBits(self.DeModulate(iq), sm, em)
+
+    def FrameBits(self, rx: str, sm: bytes, em: bytes) -> bytes:
+        """DeModulateBytes from the point where it holds rxBits (MS/QPSKDeModulator.cs:179-259)."""
+        if len(sm) == 0 or len(em) == 0:
+            raise ValueError("marker")
         if rx == "":
             return b""
         if not self.in_frame:

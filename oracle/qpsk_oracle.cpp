@@ -659,6 +659,14 @@ struct Demod {
     payload.clear();
     if (ns == 0 || ne == 0) return ORC_ERR_ARG;            // :174-175
     std::string rxBits = demodulate(in, nFloats);
+    return frame_bits(rxBits, sm, ns, em, ne, payload);
+  }
+
+  // the rest of DeModulateBytes after its DeModulate call — :179-259 (test hook: the framer on given bits)
+  int frame_bits(const std::string& rxBits, const uint8_t* sm, int64_t ns, const uint8_t* em, int64_t ne,
+                 std::vector<uint8_t>& payload) {
+    payload.clear();
+    if (ns == 0 || ne == 0) return ORC_ERR_ARG;            // :174-175
     if (rxBits.empty()) return ORC_OK;                     // :179-180
     if (!inFrame) {
       std::string cand = searchCarryBits + rxBits;         // :185
@@ -1001,6 +1009,17 @@ ORC_API int orc_demod_bytes(void* h, const float* in, int64_t n_floats, const ui
   if ((n_floats & 1) != 0) return ORC_ERR_ARG;
   std::vector<uint8_t> p;
   int st = ((Demod*)h)->demodulate_bytes(in, n_floats, sm, ns, em, ne, p);
+  if (st != ORC_OK) return st;
+  *n_bytes = (int64_t)p.size();
+  if ((int64_t)p.size() > cap) return ORC_ERR_CAPACITY;
+  if (!p.empty()) std::memcpy(out, p.data(), p.size());
+  return ORC_OK;
+}
+ORC_API int orc_demod_frame_bits(void* h, const char* bits, int64_t n_bits, const uint8_t* sm, int64_t ns,
+                                 const uint8_t* em, int64_t ne, uint8_t* out, int64_t cap, int64_t* n_bytes) {
+  if (!h || !n_bytes) return ORC_ERR_NULL;
+  std::vector<uint8_t> p;
+  int st = ((Demod*)h)->frame_bits(std::string(bits ? bits : "", (size_t)n_bits), sm, ns, em, ne, p);
   if (st != ORC_OK) return st;
   *n_bytes = (int64_t)p.size();
   if ((int64_t)p.size() > cap) return ORC_ERR_CAPACITY;

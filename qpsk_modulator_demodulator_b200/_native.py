@@ -119,6 +119,7 @@ def _signatures():
         "qpsk_demod_bits": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bits_packed": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bytes": (i, [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
+        "qpsk_demod_frame_bits": (i, [vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp]),
         "qpsk_demod_constellation": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bits_dev": (i, [vp, vp, i64, i64, vp, i64, vp, vp]),
         "qpsk_demod_bits_bound": (i, [vp, i64, i64p]),

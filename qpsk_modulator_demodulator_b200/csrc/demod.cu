@@ -519,7 +519,9 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---------------------------------------------------------------------------------------------
-// framer (DeModulateBytes :169-259), one thread per channel
+// framer (DeModulateBytes :169-259), one warp per channel: the byte packing, the eight bit-offset marker hunts, the
+// ring append, the end-marker search and the payload copy are each spread over the 32 lanes; the decisions (which
+// offset wins, where the frame ends, overflow -> reset) are the reference's, taken warp-uniformly.
 // ---------------------------------------------------------------------------------------------
 struct FramerState {
   int in_frame;
@@ -548,144 +550,176 @@ struct FramerArgs {
   int C;
 };
 
-struct FramerCtx {
-  FramerState S;
-  uint8_t* ring;
-  long long ring_cap;
-};
+constexpr int kFramerWarps = 4;           // channels per CTA
 
 __device__ __forceinline__ void framer_reset(FramerState& S) {   // ResetFramer :159-167
   S.in_frame = 0; S.pack_byte = 0; S.pack_bits = 0; S.carry_len = 0; S.ring_count = 0;
 }
 
-// AppendBitsToRing :108-129 over bits[from, to) of a bit accessor.  Returns bytes produced or -1.
-template <typename BitAt>
-__device__ __forceinline__ long long framer_append(FramerCtx& X, BitAt bit_at, long long from, long long to) {
-  long long produced = 0;
-  int pb = X.S.pack_byte, nb = X.S.pack_bits;
-  for (long long k = from; k < to; ++k) {
-    pb = ((pb << 1) | (bit_at(k) ? 1 : 0)) & 0xFF;
-    if (++nb == 8) {
-      if (X.S.ring_count >= X.ring_cap) {          // RingTryWriteByte :96-104
-        X.S.pack_byte = pb; X.S.pack_bits = nb;
-        return -1;
-      }
-      X.ring[X.S.ring_count++] = (uint8_t)pb;
-      ++produced;
-      nb = 0; pb = 0;
-    }
-  }
-  X.S.pack_byte = pb; X.S.pack_bits = nb;
-  return produced;
+// byte i of the packed candidate read at bit offset o: pk[i] holds candidate bits 8i .. 8i+7, MSB first, and the
+// byte after the last packed one is zero (BitsToBytes at offset o, HelperFunctions.cs:32-52, without re-packing)
+__device__ __forceinline__ int framer_pk_byte(const uint8_t* pk, long long i, int o) {
+  const int hi = pk[i], lo = pk[i + 1];
+  return ((hi << o) | (lo >> (8 - o))) & 0xFF;
 }
 
-// RingIndexOf :133-149
-__device__ __forceinline__ long long framer_ring_index_of(const FramerCtx& X, const uint8_t* pat, int np, long long from) {
+// RingIndexOf :133-149, positions spread over the lanes; the lowest matching index wins
+__device__ __forceinline__ long long framer_ring_index_of(const uint8_t* ring, long long ring_count, const uint8_t* pat, int np,
+                                                          long long from, int lane) {
   if (np == 0) return 0;
-  if (X.S.ring_count < np) return -1;
-  const long long last = X.S.ring_count - np;
-  for (long long i = (from > 0 ? from : 0); i <= last; ++i) {
-    bool ok = true;
-    for (int j = 0; j < np; ++j)
-      if (X.ring[i + j] != pat[j]) { ok = false; break; }
-    if (ok) return i;
+  if (ring_count < np) return -1;
+  const long long last = ring_count - np;
+  for (long long base = (from > 0 ? from : 0); base <= last; base += 32) {
+    const long long i = base + lane;
+    bool ok = i <= last;
+    if (ok) {
+      for (int j = 0; j < np; ++j)
+        if (ring[i + j] != pat[j]) { ok = false; break; }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m) return base + (__ffs(m) - 1);
   }
   return -1;
 }
 
-__device__ __forceinline__ void framer_emit(const FramerArgs& a, int c, const FramerCtx& X, long long end_at) {
+// RingCopyOut :151-157 + the length the caller sees
+__device__ __forceinline__ void framer_emit(const FramerArgs& a, int c, const uint8_t* ring, long long end_at, int lane) {
   uint8_t* out = a.payload + (long long)c * a.payload_cap;
   const long long ncopy = end_at < a.payload_cap ? end_at : a.payload_cap;
-  for (long long i = 0; i < ncopy; ++i) out[i] = X.ring[i];     // RingCopyOut :151-157
-  a.n_payload[c] = end_at;
+  for (long long i = lane; i < ncopy; i += 32) out[i] = ring[i];
+  if (lane == 0) a.n_payload[c] = end_at;
 }
 
-__global__ void __launch_bounds__(32) framer_kernel(const FramerArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.C) return;
+__global__ void __launch_bounds__(32 * kFramerWarps) framer_kernel(const FramerArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kFramerWarps + (threadIdx.x >> 5);
+  if (c >= a.C) return;                                          // warp-uniform
   const long long n_rx = a.n_rx[c];
-  a.n_payload[c] = 0;
+  if (lane == 0) a.n_payload[c] = 0;
   if (n_rx == 0) return;                                         // :179-180
-  FramerCtx X;
-  X.S = a.st[c];
-  X.ring = a.ring + (long long)c * a.ring_cap;
-  X.ring_cap = a.ring_cap;
+  FramerState S = a.st[c];
+  uint8_t* ring = a.ring + (long long)c * a.ring_cap;
   const uint8_t* rx = a.rx + (long long)c * a.ld_rx;
   const uint8_t* sm = a.markers;
   const uint8_t* em = a.markers + a.ns;
-  if (!X.S.in_frame) {
+  __syncwarp();                                                  // every lane has read the state before lane 0 rewrites it
+  if (!S.in_frame) {
     uint8_t* carry = a.carry + (long long)c * a.carry_cap;
-    const int cl = X.S.carry_len;
+    const int cl = S.carry_len;
     const long long cand_len = cl + n_rx;                        // :185
-    auto cand = [&](long long k) -> int { return (k < cl) ? carry[k] : rx[k - cl]; };
     // pack the candidate bits once (offset 0); byte i at bit offset o is a shift of two neighbours
     uint8_t* pk = a.pk + (long long)c * a.pk_ld;
     const long long nb0 = (cand_len + 7) >> 3;
-    for (long long i = 0; i < nb0; ++i) {
+    for (long long i = lane; i < nb0; i += 32) {
       int v = 0;
+#pragma unroll
       for (int j = 0; j < 8; ++j) {
         const long long k = 8 * i + j;
-        v = (v << 1) | ((k < cand_len) ? cand(k) : 0);
+        int bit = 0;
+        if (k < cand_len) bit = (k < cl) ? carry[k] : rx[k - cl];
+        v = (v << 1) | bit;
       }
       pk[i] = (uint8_t)v;
     }
-    pk[nb0] = 0;
-    for (int o = 0; o < 8; ++o) {                                // :187
-      const long long usable = cand_len - o;
-      if (usable < 8) continue;                                  // BitsToBytes -> empty (:190)
-      const long long nB = usable >> 3;
-      if (a.ns > nB) continue;                                   // IndexOf -> -1
-      long long s = -1;
-      for (long long i = 0; i + a.ns <= nB && s < 0; ++i) {
-        bool ok = true;
-        for (int j = 0; j < a.ns; ++j) {
-          const int hi = pk[i + j], lo = pk[i + j + 1];
-          const int b = o ? (((hi << o) | (lo >> (8 - o))) & 0xFF) : hi;
-          if (b != sm[j]) { ok = false; break; }
+    if (lane == 0) pk[nb0] = 0;
+    __syncwarp();
+    // one pass over the byte positions: first[o] = lowest byte index at which the start marker sits at bit offset o
+    // (IndexOf of BitsToBytes(candidate, o), :187-196); the lowest offset that has one wins, as in the reference's loop
+    long long first[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) first[o] = -1;
+    const long long n_pos = ((cand_len >> 3) >= a.ns) ? (cand_len >> 3) - a.ns + 1 : 0;   // positions valid at offset 0
+    for (long long base = 0; base < n_pos; base += 32) {
+      const long long i = base + lane;
+      unsigned hit = 0;
+      if (i < n_pos) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          // offset o has nB = (cand_len - o) >> 3 bytes (none when fewer than 8 bits are usable, :190)
+          if (i + a.ns > ((cand_len - o) >> 3)) continue;
+          bool ok = true;
+          for (int j = 0; j < a.ns; ++j)
+            if (framer_pk_byte(pk, i + j, o) != sm[j]) { ok = false; break; }
+          if (ok) hit |= 1u << o;
         }
-        if (ok) s = i;
       }
-      if (s < 0) continue;
-      const long long marker_end = o + 8 * (s + a.ns);           // :198
-      if (marker_end > cand_len) continue;
-      X.S.in_frame = 1;                                          // :202-207
-      X.S.ring_count = 0; X.S.pack_byte = 0; X.S.pack_bits = 0;
-      const long long appended = framer_append(X, cand, marker_end, cand_len);   // :210-211
-      if (appended < 0) {                                        // :212-217
-        framer_reset(X.S);
-        a.st[c] = X.S;
+      if (!__any_sync(0xffffffffu, hit != 0)) continue;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const unsigned m = __ballot_sync(0xffffffffu, (hit >> o) & 1u);
+        if (m && first[o] < 0) first[o] = base + (__ffs(m) - 1);
+      }
+      if (first[0] >= 0) break;                                  // nothing can beat offset 0
+    }
+    int o_win = -1;
+    long long s = -1;
+#pragma unroll
+    for (int o = 7; o >= 0; --o)
+      if (first[o] >= 0) { o_win = o; s = first[o]; }
+    if (o_win >= 0) {
+      const long long marker_end = o_win + 8 * (s + a.ns);       // :198
+      S.in_frame = 1;                                            // :202-207
+      // AppendBitsToRing(candidate, marker_end) :210-211: whole bytes are the offset-o bytes after the marker
+      const long long total = cand_len - marker_end;
+      const long long appended = total >> 3;
+      const int rem = (int)(total & 7);
+      if (appended > a.ring_cap) {                               // RingTryWriteByte fails :96-104 -> :212-217
+        framer_reset(S);
+        if (lane == 0) a.st[c] = S;
         return;
       }
-      const long long end_at = framer_ring_index_of(X, em, a.ne, X.S.ring_count - (appended + a.ne));   // :220
+      for (long long j = lane; j < appended; j += 32) ring[j] = (uint8_t)framer_pk_byte(pk, s + a.ns + j, o_win);
+      S.ring_count = appended;
+      S.pack_bits = rem;
+      S.pack_byte = rem ? (framer_pk_byte(pk, s + a.ns + appended, o_win) >> (8 - rem)) : 0;
+      __syncwarp();
+      const long long end_at = framer_ring_index_of(ring, S.ring_count, em, a.ne, S.ring_count - (appended + a.ne), lane);   // :220
       if (end_at >= 0) {
-        framer_emit(a, c, X, end_at);
-        framer_reset(X.S);
+        framer_emit(a, c, ring, end_at, lane);
+        framer_reset(S);
       }
-      a.st[c] = X.S;
+      if (lane == 0) a.st[c] = S;
       return;                                                    // :226 / :229
     }
-    // no start marker: keep a tail so it can span calls (:233-235)
+    // no start marker: keep a tail so it can span calls (:233-235); the bits come back out of the packed copy
     const long long keep = cand_len < (long long)(a.ns * 8 + 7) ? cand_len : (long long)(a.ns * 8 + 7);
     const long long src0 = cand_len - keep;
-    for (long long i = 0; i < keep; ++i) carry[i] = (uint8_t)cand(src0 + i);   // src index >= i: in-order copy is safe
-    X.S.carry_len = (int)keep;
-    a.st[c] = X.S;
+    for (long long i = lane; i < keep; i += 32) {
+      const long long k = src0 + i;
+      carry[i] = (uint8_t)((pk[k >> 3] >> (7 - (int)(k & 7))) & 1);
+    }
+    S.carry_len = (int)keep;
+    if (lane == 0) a.st[c] = S;
     return;
   }
-  // already inside a frame (:238-258)
-  auto rxbit = [&](long long k) -> int { return rx[k]; };
-  const long long appended = framer_append(X, rxbit, 0, n_rx);
-  if (appended < 0) {
-    framer_reset(X.S);
-    a.st[c] = X.S;
+  // already inside a frame (:238-258): the bit stream is the pending pack bits followed by this call's bits
+  const int nb_old = S.pack_bits, pb_old = S.pack_byte;
+  const long long total = nb_old + n_rx;
+  const long long appended = total >> 3;
+  auto stream_bit = [&](long long q) -> int { return (q < nb_old) ? ((pb_old >> (nb_old - 1 - (int)q)) & 1) : (int)rx[q - nb_old]; };
+  if (S.ring_count + appended > a.ring_cap) {                    // RingTryWriteByte fails :96-104 -> :241-246
+    framer_reset(S);
+    if (lane == 0) a.st[c] = S;
     return;
   }
-  const long long end_at = framer_ring_index_of(X, em, a.ne, X.S.ring_count - (appended + a.ne));
+  for (long long j = lane; j < appended; j += 32) {
+    int v = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v = (v << 1) | stream_bit(8 * j + t);
+    ring[S.ring_count + j] = (uint8_t)v;
+  }
+  int pb = 0;
+  for (long long q = 8 * appended; q < total; ++q) pb = (pb << 1) | stream_bit(q);
+  S.pack_byte = pb;
+  S.pack_bits = (int)(total & 7);
+  S.ring_count += appended;
+  __syncwarp();
+  const long long end_at = framer_ring_index_of(ring, S.ring_count, em, a.ne, S.ring_count - (appended + a.ne), lane);
   if (end_at >= 0) {
-    framer_emit(a, c, X, end_at);
-    framer_reset(X.S);
+    framer_emit(a, c, ring, end_at, lane);
+    framer_reset(S);
   }
-  a.st[c] = X.S;
+  if (lane == 0) a.st[c] = S;
 }
 
 __global__ void bits_to_chars_kernel(const uint8_t* in, char* out, long long n) {
@@ -950,6 +984,15 @@ struct DemodEngine {
     const long long ldb = bits_bound(L) + 2;
     QPSK_TRY(d_bits.ensure((size_t)ldb * channels));
     QPSK_TRY(bits_dev(x, L, ldx, d_bits.p, ldb, d_nbits.p, s));
+    return frame_dev(d_bits.p, ldb, d_nbits.p, sm, ns, em, ne, payload, cap, n_payload, s);
+  }
+
+  // the framer of DeModulateBytes (:182-259) over bits [C][ldb] (one 0/1 byte each), n_bits[C] of them per channel
+  int frame_dev(const uint8_t* bits, long long ldb, const long long* n_bits, const uint8_t* sm, int64_t ns, const uint8_t* em,
+                int64_t ne, uint8_t* payload, int64_t cap, long long* n_payload, cudaStream_t s) {
+    if (ns == 0 || ne == 0) return QPSK_ERR_ARG;               // :174-175
+    if (!sm || !em) return QPSK_ERR_NULL;
+    if (ns > kMaxMarkerBytes || ne > kMaxMarkerBytes) return QPSK_ERR_UNSUPPORTED;
     QPSK_TRY(upload_markers(sm, ns, em, ne, s));
     const int carry_cap = kMaxMarkerBytes * 8 + 8;
     if (!d_carry.p) {
@@ -960,9 +1003,9 @@ struct DemodEngine {
     QPSK_TRY(d_pk.ensure((size_t)pk_ld * channels));
     FramerArgs a;
     a.st = d_framer.p; a.carry = d_carry.p; a.carry_cap = carry_cap; a.ring = d_ring.p; a.ring_cap = ring_cap;
-    a.pk = d_pk.p; a.pk_ld = pk_ld; a.rx = d_bits.p; a.ld_rx = ldb; a.n_rx = d_nbits.p; a.markers = d_markers.p;
+    a.pk = d_pk.p; a.pk_ld = pk_ld; a.rx = bits; a.ld_rx = ldb; a.n_rx = n_bits; a.markers = d_markers.p;
     a.ns = (int)ns; a.ne = (int)ne; a.payload = payload; a.payload_cap = cap; a.n_payload = n_payload; a.C = channels;
-    framer_kernel<<<(channels + 31) / 32, 32, 0, s>>>(a);
+    framer_kernel<<<(channels + kFramerWarps - 1) / kFramerWarps, 32 * kFramerWarps, 0, s>>>(a);
     QPSK_LAUNCH_CHECK();
     return QPSK_OK;
   }
@@ -1111,6 +1154,46 @@ int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_floats, const 
   const int64_t pcap = cap > 0 ? cap : 1;
   QPSK_TRY(e.d_payload.ensure((size_t)pcap * e.channels));
   QPSK_TRY(e.bytes_dev(e.h_in.p, L, ld, start_marker, n_start, end_marker, n_end, e.d_payload.p, pcap, e.d_npayload.p, s));
+  std::vector<long long> np((size_t)e.channels);
+  QPSK_CUDA_TRY(cudaMemcpyAsync(np.data(), e.d_npayload.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  int st = QPSK_OK;
+  for (int c = 0; c < e.channels; ++c) {
+    n_bytes[c] = np[(size_t)c];
+    if (np[(size_t)c] > cap) { st = QPSK_ERR_CAPACITY; continue; }
+    if (np[(size_t)c] == 0) continue;
+    if (!payload_out) return QPSK_ERR_NULL;
+    QPSK_CUDA_TRY(cudaMemcpy(payload_out + (size_t)c * cap, e.d_payload.p + (size_t)c * pcap, (size_t)np[(size_t)c],
+                             cudaMemcpyDeviceToHost));
+  }
+  return st;
+}
+
+int qpsk_demod_frame_bits(qpsk_demod* d, const uint8_t* bits, int64_t bits_stride, const int64_t* n_bits,
+                          const uint8_t* start_marker, int64_t n_start, const uint8_t* end_marker, int64_t n_end,
+                          uint8_t* payload_out, int64_t cap, int64_t* n_bytes) {
+  if (!d || !n_bytes || !n_bits) return QPSK_ERR_NULL;
+  if (n_start == 0 || n_end == 0) return QPSK_ERR_ARG;       // :174-175
+  if (bits_stride < 0 || cap < 0) return QPSK_ERR_RANGE;
+  DemodEngine& e = d->eng;
+  long long max_bits = 0;
+  for (int c = 0; c < e.channels; ++c) {
+    n_bytes[c] = 0;
+    if (n_bits[c] < 0 || n_bits[c] > bits_stride) return QPSK_ERR_RANGE;
+    if (n_bits[c] > max_bits) max_bits = n_bits[c];
+  }
+  if (max_bits == 0) return QPSK_OK;                         // :179-180 for every channel
+  if (!bits) return QPSK_ERR_NULL;
+  QPSK_TRY(ensure_device());
+  cudaStream_t s = e.stream;
+  const long long ldb = max_bits;
+  QPSK_TRY(e.d_bits.ensure((size_t)ldb * e.channels));
+  QPSK_CUDA_TRY(cudaMemcpy2DAsync(e.d_bits.p, (size_t)ldb, bits, (size_t)bits_stride, (size_t)max_bits, (size_t)e.channels,
+                                  cudaMemcpyHostToDevice, s));
+  QPSK_CUDA_TRY(cudaMemcpyAsync(e.d_nbits.p, n_bits, sizeof(long long) * e.channels, cudaMemcpyHostToDevice, s));
+  const int64_t pcap = cap > 0 ? cap : 1;
+  QPSK_TRY(e.d_payload.ensure((size_t)pcap * e.channels));
+  QPSK_TRY(e.frame_dev(e.d_bits.p, ldb, e.d_nbits.p, start_marker, n_start, end_marker, n_end, e.d_payload.p, pcap, e.d_npayload.p, s));
   std::vector<long long> np((size_t)e.channels);
   QPSK_CUDA_TRY(cudaMemcpyAsync(np.data(), e.d_npayload.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
   QPSK_CUDA_TRY(cudaStreamSynchronize(s));

@@ -69,7 +69,7 @@ class QPSKModulator(_Handle):
             check(lib().qpsk_mod_modulate_bytes(*args, _ptr(out), out.size, C.byref(n)))
         return out
 
-    def ModulateTextUtf8(self, text: str, startMarker="", endMarker="", pulseShaping=True) -> np.ndarray:
+    def ModulateTextUtf8(self, text: str, startMarker="\x02", endMarker="\x03", pulseShaping=True) -> np.ndarray:
         if text is None:
             raise ArgumentNullException("text")
         return self.ModulateBytes(text.encode("utf-8"), startMarker.encode("utf-8"), endMarker.encode("utf-8"), pulseShaping)
@@ -152,7 +152,28 @@ class QPSKDeModulator(_Handle):
         outs = [out[c, : nb[c]].tobytes() for c in range(self.channels)]
         return outs[0] if self.channels == 1 else outs
 
-    def DeModulateTextUtf8(self, samplesIQ, startMarker="", endMarker=""):
+    def FrameBits(self, bits, startMarker: bytes, endMarker: bytes, cap: int = 0):
+        """The framer half of DeModulateBytes (MS/QPSKDeModulator.cs:182-259) on bits already demodulated: a '0'/'1'
+        string (one channel) or a list of them (one per channel, lengths may differ).  Shares the framer state with
+        DeModulateBytes."""
+        rows = [bits] if isinstance(bits, (str, bytes)) else list(bits)
+        if len(rows) != self.channels:
+            raise N.ArgumentException("one bit string per channel")
+        nb_in = np.array([len(r) for r in rows], np.int64)
+        ld = max(int(nb_in.max()), 1)
+        b = np.zeros((self.channels, ld), np.uint8)
+        for c, r in enumerate(rows):
+            raw = np.frombuffer(r.encode("ascii") if isinstance(r, str) else bytes(r), np.uint8)
+            b[c, : raw.size] = raw & 1                       # '0' = 0x30, '1' = 0x31
+        s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
+        cap = cap or max(ld // 8 + 64, 64)
+        out = np.zeros((self.channels, cap), np.uint8)
+        nb = np.zeros(self.channels, np.int64)
+        check(lib().qpsk_demod_frame_bits(self._h, _ptr(b), ld, _ptr(nb_in), _ptr(s), s.size, _ptr(e), e.size, _ptr(out), cap, _ptr(nb)))
+        outs = [out[c, : nb[c]].tobytes() for c in range(self.channels)]
+        return outs[0] if self.channels == 1 else outs
+
+    def DeModulateTextUtf8(self, samplesIQ, startMarker="\x02", endMarker="\x03"):
         p = self.DeModulateBytes(samplesIQ, startMarker.encode("utf-8"), endMarker.encode("utf-8"))
         return _decode_utf8(p) if self.channels == 1 else [_decode_utf8(b) for b in p]
 

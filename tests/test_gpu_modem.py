@@ -376,6 +376,90 @@ def test_framer_ring_overflow_resets(gpu, orc):
         assert gd.in_frame == od.in_frame
 
 
+def _framer_streams(rng, channels, sm, em, max_payload=40):
+    bits_of = lambda b: "".join(format(v, "08b") for v in b)
+    rows = []
+    for _ in range(channels):
+        t = ""
+        for _f in range(int(rng.integers(1, 6))):
+            t += "".join(rng.choice(["0", "1"], int(rng.integers(0, 50))))
+            body = rng.integers(0, 256, int(rng.integers(0, max_payload)), dtype=np.uint8).tobytes()
+            if rng.random() < 0.3:
+                body = body[: len(body) // 2] + sm + body[len(body) // 2:]      # a start marker inside the payload
+            t += bits_of(sm + body + em)
+        t += "".join(rng.choice(["0", "1"], int(rng.integers(0, 50))))
+        rows.append(t)
+    return rows
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels,markers,ring", [(1, (b"S", b"E"), 1 << 20), (5, (b"\xa5START\x5a", b"\x5aSTOP\xa5"), 1 << 20),
+                                                   (37, (b"AB", b"YZ"), 24), (130, (b"\x00", b"\xff\xff"), 1 << 20),
+                                                   (3, (bytes(range(1, 41)), b"\x7e"), 16)])
+def test_framer_on_bits_ragged_channels(gpu, orc, channels, markers, ring):
+    """The warp-per-channel framer kernel on its own (QPSKDeModulator.cs:179-259): ragged per-channel bit chunks
+    (including empty ones), frames at every bit offset, markers split across calls, start markers inside payloads, ring
+    overflow -> reset; payloads and the in-frame flag must equal the oracle's after every call."""
+    sm, em = markers
+    rng = np.random.default_rng(100 + channels)
+    rows = _framer_streams(rng, channels, sm, em)
+    gd = gpu.QPSKDeModulator(4000, 1000, max_frame_bytes=ring, channels=channels)
+    ods = [orc.QPSKDeModulator(4000, 1000, ring_capacity=ring) for _ in range(channels)]
+    pos = [0] * channels
+    got_frames = 0
+    while any(pos[c] < len(rows[c]) for c in range(channels)):
+        big = rng.random() < 0.2
+        take = [int(rng.integers(0, 400 if big else 70)) for _ in range(channels)]
+        chunks = [rows[c][pos[c]:pos[c] + take[c]] for c in range(channels)]
+        pos = [pos[c] + take[c] for c in range(channels)]
+        got = gd.FrameBits(chunks if channels > 1 else chunks[0], sm, em, cap=4096)
+        got = got if channels > 1 else [got]
+        for c in range(channels):
+            want = ods[c].FrameBits(chunks[c], sm, em, cap=4096)
+            assert got[c] == want, (c, pos[c])
+            got_frames += bool(want)
+        inf = np.atleast_1d(gd.in_frame)
+        assert [bool(v) for v in inf] == [bool(o.in_frame) for o in ods]
+    assert got_frames > 0 or ring < 64
+
+
+@pytest.mark.gpu
+def test_framer_on_bits_long_call(gpu, orc):
+    """One call holding many frames' worth of bits (only the first frame comes out, the rest is dropped exactly as the
+    reference drops it, :226-229) and a frame that spans three calls."""
+    sm, em = b"<<", b">>"
+    rng = np.random.default_rng(5)
+    bits_of = lambda b: "".join(format(v, "08b") for v in b)
+    payloads = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (700, 3, 1500)]
+    t = "101" + "".join(bits_of(sm + p + em) + "0110" for p in payloads)
+    gd, od = gpu.QPSKDeModulator(4000, 1000), orc.QPSKDeModulator(4000, 1000)
+    assert gd.FrameBits(t, sm, em, cap=8192) == od.FrameBits(t, sm, em, cap=8192) == payloads[0]
+    long_frame = "1" * 5 + bits_of(sm + bytes(range(256)) * 20 + em)
+    third = len(long_frame) // 3
+    for a in (0, third, 2 * third):
+        part = long_frame[a:a + third] if a < 2 * third else long_frame[a:]
+        g, w = gd.FrameBits(part, sm, em, cap=8192), od.FrameBits(part, sm, em, cap=8192)
+        assert g == w
+        assert gd.in_frame == od.in_frame
+    assert w == bytes(range(256)) * 20
+
+
+@pytest.mark.gpu
+def test_text_default_markers_roundtrip(gpu, orc):
+    """Default STX / ETX markers (QPSKModulator.cs:76-77, QPSKDeModulator.cs:264-265) through both text calls."""
+    fs, rs = 4000, 1000
+    gm, om = gpu.QPSKModulator(fs, rs, 0.35, 10), orc.QPSKModulator(fs, rs, 0.35, 10)
+    x = om.ModulateTextUtf8("warm-up burst")
+    y = om.ModulateTextUtf8("héllo, wörld")
+    assert _close(gm.ModulateTextUtf8("héllo, wörld"), y)
+    assert _close(gm.ModulateTextUtf8("héllo, wörld", "\x02", "\x03"), y)
+    kw = dict(RrcAlpha=0.35, rrcSpan=10, SymbolSyncBandwith=0.002)
+    gd, od = gpu.QPSKDeModulator(fs, rs, **kw), orc.QPSKDeModulator(fs, rs, **kw)
+    gd.set_fir_mode(gpu.FIR_EXACT)
+    for burst in (x, y, y):
+        assert gd.DeModulateTextUtf8(burst) == od.DeModulateTextUtf8(burst)
+
+
 def test_demod_error_behaviour(gpu, orc):
     for mod in (gpu, orc):
         d = mod.QPSKDeModulator(4000, 1000)

@@ -107,6 +107,40 @@ def test_framer(orc):
     assert any(outs)
 
 
+def test_framer_on_bits(orc):
+    """The framer alone (QPSKDeModulator.cs:179-259) on random bit chunks with frames at every bit offset."""
+    sm, em = b"\xa5ST", b"EN\x5a"
+    rng = np.random.default_rng(11)
+    bits_of = lambda b: "".join(format(v, "08b") for v in b)
+    od = orc.QPSKDeModulator(4000, 1000)
+    td = T.QPSKDeModulator(4000, 1000)
+    frames = 0
+    for trial in range(400):
+        n = int(rng.integers(0, 80))
+        if rng.random() < 0.3:
+            pad = "".join(rng.choice(["0", "1"], int(rng.integers(0, 9))))
+            chunk = (pad + bits_of(sm + rng.integers(0, 256, int(rng.integers(0, 6)), dtype=np.uint8).tobytes() + em))[: n + 30]
+        else:
+            chunk = "".join(rng.choice(["0", "1"], n))
+        w, g = od.FrameBits(chunk, sm, em, cap=4096), td.FrameBits(chunk, sm, em)
+        assert w == g, trial
+        assert od.in_frame == td.in_frame
+        frames += bool(w) or (od.in_frame is False and chunk.endswith(bits_of(em)))
+    assert frames > 5
+
+
+def test_text_marker_defaults(orc):
+    """ModulateTextUtf8 / DeModulateTextUtf8 default to STX / ETX (QPSKModulator.cs:76-77, QPSKDeModulator.cs:264-265)."""
+    import inspect
+    import qpsk_modulator_demodulator_b200.modem as M
+    for cls in (orc.QPSKModulator, M.QPSKModulator):
+        p = inspect.signature(cls.ModulateTextUtf8).parameters
+        assert (p["startMarker"].default, p["endMarker"].default) == ("\x02", "\x03")
+    for cls in (orc.QPSKDeModulator, M.QPSKDeModulator):
+        p = inspect.signature(cls.DeModulateTextUtf8).parameters
+        assert (p["startMarker"].default, p["endMarker"].default) == ("\x02", "\x03")
+
+
 def test_bitpacker(orc):
     data = bytes(range(0, 256, 7))
     s = orc.BitPacker.BytesToBitString(data)
