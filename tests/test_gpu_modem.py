@@ -638,6 +638,73 @@ def test_batched_chain_device_resident_ber(gpu, orc):
     assert (cnt_h[:, 0] == 0).mean() > 0.9, cnt_h[:, 0]                    # locked channels decode error-free
 
 
+@pytest.mark.parametrize("use_fll", [False, True])
+def test_full_size_channel_set_config4(gpu, orc, use_fll):
+    """BASELINE configs[3] at full size on one GPU: 16384 impaired channels (config 3's 1024 bursts are a subset), device
+    resident end to end.  No oracle run at this size, so: (i) oracle bits on a few channels spread over the set, every
+    burst; (ii) batch-position independence — a block of channels cut out of the set and run through a fresh 48-channel
+    demodulator gives the same bits and counts; (iii) the BER counters equal a host recount; (iv) locked channels
+    decode error-free."""
+    import torch
+    fs = 10_000_000
+    rs = fs // 2
+    Cn, n_payload, seed = 16384, 512, 33
+    lo, hi = 9001, 9049                                                    # the cut-out block (straddles CTA boundaries)
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    s = ts.cuda_stream
+    mod = gpu.QPSKModulator(fs, rs, ALPHA04, 10, True, TSC)
+    pay = torch.empty((Cn, n_payload), dtype=torch.uint8, device="cuda")
+    gpu.fill_bytes_dev(seed, 0, Cn, n_payload, pay.data_ptr(), s)
+    ff = mod.frame_floats(n_payload, b"S", b"E")
+    tx = torch.empty((Cn, ff), dtype=torch.float32, device="cuda")
+    mod.modulate_frames_dev(pay.data_ptr(), n_payload, Cn, b"S", b"E", tx.data_ptr(), ff, s)
+    ch = gpu.SimChannel(100e6, 100e6, fs, 1, 1, noise_dbfs=-40.0, mode=1, seed=seed, channels=Cn)
+    rxs = torch.empty_like(tx)
+    kw = dict(RrcAlpha=ALPHA04, rrcSpan=10, tsc=TSC, use_fll=use_fll)
+    dem = gpu.QPSKDeModulator(fs, rs, channels=Cn, **kw)
+    sub = gpu.QPSKDeModulator(fs, rs, channels=hi - lo, **kw)
+    dem.set_fir_mode(gpu.FIR_EXACT)
+    sub.set_fir_mode(gpu.FIR_EXACT)
+    cap = dem.bits_bound(ff)
+    bits = torch.zeros((Cn, cap), dtype=torch.uint8, device="cuda")
+    nb = torch.zeros(Cn, dtype=torch.int64, device="cuda")
+    sbits = torch.zeros((hi - lo, cap), dtype=torch.uint8, device="cuda")
+    snb = torch.zeros(hi - lo, dtype=torch.int64, device="cuda")
+    nref = 8 * (n_payload + 2)
+    ref = torch.empty((Cn, nref), dtype=torch.uint8, device="cuda")
+    framed = torch.cat([torch.full((Cn, 1), ord("S"), dtype=torch.uint8, device="cuda"), pay,
+                        torch.full((Cn, 1), ord("E"), dtype=torch.uint8, device="cuda")], dim=1).contiguous()
+    gpu.unpack_bits_dev(framed.data_ptr(), n_payload + 2, n_payload + 2, Cn, ref.data_ptr(), nref, s)
+    cnt = torch.zeros((Cn, 2), dtype=torch.int32, device="cuda")
+    check = (0, 4097, lo + 5, Cn - 1)
+    ods = {c: orc.QPSKDeModulator(fs, rs, **kw) for c in check}
+    for burst in range(4):
+        ch.apply_dev(tx.data_ptr(), ff, ff, rxs.data_ptr(), ff, s)
+        dem.demod_bits_dev(rxs.data_ptr(), ff, ff, bits.data_ptr(), cap, nb.data_ptr(), s)
+        gpu.ber_count_dev(bits.data_ptr(), cap, nb.data_ptr(), ref.data_ptr(), nref, nref, Cn, cnt.data_ptr(), s)
+        block = rxs[lo:hi].contiguous()
+        sub.demod_bits_dev(block.data_ptr(), ff, ff, sbits.data_ptr(), cap, snb.data_ptr(), s)
+        torch.cuda.synchronize()
+        nb_h = nb.cpu().numpy()
+        assert torch.equal(snb, nb[lo:hi]), burst                          # (ii)
+        for k in range(hi - lo):
+            assert torch.equal(sbits[k, : nb_h[lo + k]], bits[lo + k, : nb_h[lo + k]]), (burst, lo + k)
+        for c, od in ods.items():                                          # (i)
+            want = od.DeModulate(rxs[c].cpu().numpy())
+            got = "".join("1" if b else "0" for b in bits[c, : nb_h[c]].cpu().numpy())
+            assert got == want, (burst, c)
+    # (iii) the counters of the last burst against a recount on the host (bits past the reference count as errors)
+    cnt_h, bits_h, ref_h = cnt.cpu().numpy(), bits.cpu().numpy(), ref.cpu().numpy()
+    for c in list(range(0, Cn, 1021)) + [Cn - 1]:
+        n = min(int(nb_h[c]), nref)
+        err = int((bits_h[c, :n] != ref_h[c, :n]).sum()) + (nref - n)
+        assert cnt_h[c].tolist() == [err, nref], c
+    locked = float((cnt_h[:, 0] == 0).mean())
+    print(f"config4 use_fll={use_fll}: error-free channels in burst 4: {locked:.3f}")
+    assert locked > (0.2 if use_fll else 0.5), locked                     # (iv) measured 0.67 / 0.51: the rest lose a burst exactly as the reference does
+
+
 # ---- SURVEY §8f-4: packed-bit I/O ------------------------------------------------------------------
 @pytest.mark.parametrize("tlen", [1, 3, 8, 31, 32, 33, 63, 64, 65, 100])
 def test_demod_tsc_strip_lengths(gpu, orc, tlen):
