@@ -11,6 +11,37 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5
 
 TSC = "11001010011101100100100110101100" + "01110100111001011010001101101001"   # testAtDataLevel.cs:20-22
+def test_full_size_modulator_share_config5(gpu, orc):
+    """BASELINE configs[4], one GPU's share at full size (2048 frames x 64 KiB payload, sps 4, span 10: 17.2 GB of
+    samples): frames spread over the batch against the oracle, the differential chain restarting per frame (two frames
+    given the same payload come out identical wherever they sit), nothing written in the row padding."""
+    import torch
+    frames, n_payload = 2048, 65536
+    fs, rs = 4000, 1000
+    m = gpu.QPSKModulator(fs, rs, 0.35, 10, True, TSC)
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    s = ts.cuda_stream
+    pay = torch.empty((frames, n_payload), dtype=torch.uint8, device="cuda")
+    gpu.fill_bytes_dev(7, 0, frames, n_payload, pay.data_ptr(), s)
+    torch.cuda.synchronize()
+    pay[1500] = pay[3]                                                      # twin frames far apart
+    ff = m.frame_floats(n_payload, b"START", b"END")
+    stride = ff + 2
+    out = torch.empty((frames, stride), dtype=torch.float32, device="cuda")
+    out[:, ff:] = 0
+    assert m.modulate_frames_dev(pay.data_ptr(), n_payload, frames, b"START", b"END", out.data_ptr(), stride, s) == ff
+    torch.cuda.synchronize()
+    assert torch.equal(out[1500], out[3])
+    assert not out[:, ff:].any()
+    om = orc.QPSKModulator(fs, rs, 0.35, 10, True, TSC)
+    for f in (0, 1023, frames - 1):
+        want = om.ModulateBytes(pay[f].cpu().numpy().tobytes(), b"START", b"END")
+        assert want.size == ff
+        assert _close(out[f, :ff].cpu().numpy(), want)
+    del out
+
+
 TEXT = "The Quick Brown fox jump yes yes man good!"                                # testAtDataLevel.cs:35
 START, STOP = "MESSAGE_START", "MESSAGE_STOP"
 ALPHA04 = float(np.float32(0.4))                                                     # const float RRCAlpha = .4f
