@@ -16,6 +16,41 @@ from .api import _Handle, _bytes_arr, _f32, _ptr
 
 
 # ---- a6 ---------------------------------------------------------------------------------------
+class FormatException(ValueError):
+    """System.FormatException (BitPacker.BitsToBytes on a character other than '0' / '1')."""
+
+
+class BitPacker:
+    """HelperFunctions.BitPacker (MS/Models/HelperFunctions.cs:11-70): host-side string helpers, MSB first.  They stay
+    host code in the C# deployment too (the device works on packed bits: qpsk_unpack_bits_dev / qpsk_pack_bits_dev and
+    the framer kernel); mirrored here so that callers of the reference's helpers find them."""
+
+    @staticmethod
+    def BytesToBitString(data) -> str:                                          # :14-29
+        a = np.frombuffer(bytes(data), np.uint8)
+        if a.size == 0:
+            return ""
+        return (np.unpackbits(a) + ord("0")).astype(np.uint8).tobytes().decode("ascii")
+
+    @staticmethod
+    def BitsToBytes(bits: str, bitOffset: int) -> bytes:                        # :32-57
+        if bits is None:
+            raise N.ArgumentNullException("bits")
+        if not 0 <= bitOffset <= 7:
+            raise N.ArgumentOutOfRangeException("bitOffset")
+        usable = len(bits) - bitOffset
+        if usable < 8:
+            return b""
+        raw = np.frombuffer(bits[bitOffset: bitOffset + 8 * (usable // 8)].encode("latin-1", "replace"), np.uint8)
+        if ((raw != ord("0")) & (raw != ord("1"))).any():
+            raise FormatException("Bit string must contain only '0'/'1'.")
+        return np.packbits(raw & 1).tobytes()
+
+    @staticmethod
+    def IndexOf(haystack, needle) -> int:                                       # :59-69
+        return bytes(haystack).find(bytes(needle))
+
+
 class QPSKModulator(_Handle):
     """QPSKModulator (MS/QPSKModulator.cs:18-168) on the GPU: polyphase RRC pulse shaping."""
     _destroy = "qpsk_mod_destroy"

@@ -129,6 +129,25 @@ def test_framer_on_bits(orc):
     assert frames > 5
 
 
+def test_bitpacker_mirror(orc):
+    """The product's host-side BitPacker mirror (HelperFunctions.cs:11-70) against the oracle's."""
+    import qpsk_modulator_demodulator_b200.modem as M
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 2, 17, 300):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        s = orc.BitPacker.BytesToBitString(data)
+        assert M.BitPacker.BytesToBitString(data) == s
+        for off in range(8):
+            assert M.BitPacker.BitsToBytes(s + "101", off) == orc.BitPacker.BitsToBytes(s + "101", off)
+    assert M.BitPacker.BitsToBytes("1010101", 0) == b""                      # fewer than 8 usable bits (:38-39)
+    with pytest.raises(ValueError):
+        M.BitPacker.BitsToBytes("10101010", 8)                                # :35
+    with pytest.raises(M.FormatException):
+        M.BitPacker.BitsToBytes("1010x010", 0)                                # :50
+    for hay, nee in ((b"abcabc", b"ca"), (b"abc", b""), (b"ab", b"abc"), (b"", b""), (b"xyz", b"q")):
+        assert M.BitPacker.IndexOf(hay, nee) == orc.BitPacker.IndexOf(hay, nee)
+
+
 def test_text_marker_defaults(orc):
     """ModulateTextUtf8 / DeModulateTextUtf8 default to STX / ETX (QPSKModulator.cs:76-77, QPSKDeModulator.cs:264-265)."""
     import inspect
