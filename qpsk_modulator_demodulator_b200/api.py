@@ -224,7 +224,7 @@ class FLLBandEdgeFilter(_Handle):
 
     def __init__(self, sps, rolloff, filterSize, bandwidth, channels: int = 1):
         super().__init__()
-        self.filterSize = filterSize
+        self.sps, self.rolloff, self.filterSize, self.bandwidth = sps, rolloff, filterSize, bandwidth   # public fields :19-22
         self.channels = channels
         self._design = (sps, rolloff, filterSize)
         check(lib().qpsk_fll_create_batch(sps, rolloff, filterSize, bandwidth, channels, C.byref(self._h)))
@@ -255,6 +255,23 @@ class FLLBandEdgeFilter(_Handle):
         p = _f32(np.broadcast_to(np.asarray(pf[0], np.float32), (self.channels,)))
         f = _f32(np.broadcast_to(np.asarray(pf[1], np.float32), (self.channels,)))
         check(lib().qpsk_fll_set_state(self._h, p.ctypes.data_as(N.f32p), f.ctypes.data_as(N.f32p)))
+
+    # the reference's public loop-state fields (Band-Edge Filter.cs:25-26), readable and writable between calls
+    @property
+    def phase(self):
+        return self.state[0]
+
+    @phase.setter
+    def phase(self, v):
+        self.state = (v, self.state[1])
+
+    @property
+    def freq(self):
+        return self.state[1]
+
+    @freq.setter
+    def freq(self, v):
+        self.state = (self.state[0], v)
 
 
 # ---- a9 ---------------------------------------------------------------------------------------
@@ -314,6 +331,11 @@ class CostasLoopQpsk(_Handle):
         cap = y.shape[-1] if y.ndim == 2 else y.size
         check(lib().qpsk_costas_process(self._h, _ptr(x), _ptr(y), n, cap))
         return y
+
+    @staticmethod
+    def GetSign(i, q):
+        """GetSign :52-56 — (di, dq) = (+-1, +-1), zero counts as positive."""
+        return (1.0 if np.float32(i) >= 0 else -1.0), (1.0 if np.float32(q) >= 0 else -1.0)
 
     def GetState(self):
         t = np.empty(self.channels, np.float64)

@@ -59,6 +59,7 @@ class QPSKModulator(_Handle):
         super().__init__()
         t = None if tsc is None else tsc.encode("ascii")
         check(lib().qpsk_mod_create(SampleRate, SymbolRate, RrcAlpha, rrcSpan, int(differentialEncoding), t, C.byref(self._h)))
+        self.baudRate = 2 * SymbolRate // 8                                     # QPSKModulator.cs:34 (long arithmetic)
 
     def getCoeef(self) -> np.ndarray:
         n = C.c_int(0)

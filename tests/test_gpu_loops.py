@@ -68,6 +68,15 @@ def test_fll_batch_and_state(gpu, orc):
     o1 = orc.FLLBandEdgeFilter(4.0, 0.35, 40, 0.02)
     o1.state = (0.5, 0.01)
     assert _close(g1.Process(x[0]), o1.Process(x[0]))
+    # the reference's public fields (Band-Edge Filter.cs:19-26): design parameters, and phase / freq writable between calls
+    assert (g1.sps, g1.rolloff, g1.filterSize, g1.bandwidth) == (4.0, 0.35, 40, 0.02)
+    assert (g1.phase, g1.freq) == o1.state
+    g1.phase, g1.freq = 1.25, -0.002
+    o1.state = (1.25, -0.002)
+    assert (g1.phase, g1.freq) == (np.float32(1.25), np.float32(-0.002))
+    assert _close(g1.Process(x[1]), o1.Process(x[1]))
+    assert gpu.CostasLoopQpsk.GetSign(0.0, -1e-30) == (1.0, -1.0)            # CostasLoopQpsk.cs:52-56
+    assert gpu.QPSKModulator(10_000_000, 5_000_000).baudRate == 1_250_000    # QPSKModulator.cs:34
 
 
 @pytest.mark.parametrize("size", [40, 16, 8, 48, 10, 13, 9, 23, 31, 55, 33, 52])
