@@ -837,7 +837,9 @@ struct DemodEngine {
   }
 
   // Time-chunk pipeline of bits_dev (FLL path): number of chunks for an L-sample call.  QPSK_DEMOD_CHUNKS overrides
-  // (1 = off).  Short calls and small batches stay on one stream: the split costs two launches and a warm-up per chunk.
+  // (1 = off).  Short calls stay on one stream: the split costs two launches and a warm-up per chunk.  The channel count
+  // does not matter: a single stream gains as much as a full batch (1.10 -> 0.84 ms for 4196 samples), because the FLL
+  // and the symbol stages are each latency-bound on their own warps.
   int pipeline_chunks(int64_t L) const {
     static const int env = [] {
       const char* e = getenv("QPSK_DEMOD_CHUNKS");
@@ -845,7 +847,7 @@ struct DemodEngine {
     }();
     int n = env > 0 ? env : 4;
     if (n > 16) n = 16;
-    if (env <= 0 && (channels < 256 || L < 2048)) n = 1;
+    if (env <= 0 && L < 2048) n = 1;
     while (n > 1 && L < (int64_t)n * 8 * kSsBlock) --n;
     return n;
   }
