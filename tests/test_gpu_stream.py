@@ -57,6 +57,32 @@ def test_stream_one_burst_per_block_equals_per_call_oracle(gpu, orc, depth):
     st.close()
 
 
+def test_stream_with_fll_time_chunk_pipeline(gpu, orc):
+    """FLL opt-in under the front-end: every block is long enough (>= 2048 samples) for the demodulator's time-chunk
+    pipeline, whose side stream and events then run beneath the front-end's copy / compute streams.  Payload of block k
+    = the oracle's k-th DeModulateBytes call with the FLL."""
+    mod = orc.QPSKModulator(FS, RS, ALPHA, SPAN, True, TSC)
+    rng = np.random.default_rng(12)
+    pays = [rng.integers(0, 256, int(rng.integers(300, 700)), dtype=np.uint8).tobytes() for _ in range(7)]
+    tx, rx = orc.NCO(100e6, FS, 1, seed=12, stream=0), orc.NCO(100e6, FS, 1, seed=12, stream=1)
+    bursts = [orc.channel_apply(tx, rx, 0, mod.ModulateBytes(p, START, END)) for p in pays]
+    assert min(b.size for b in bursts) >= 2 * 2048
+    od = orc.QPSKDeModulator(FS, RS, ALPHA, SPAN, tsc=TSC, use_fll=True)
+    want = [od.DeModulateBytes(b, START, END, cap=1 << 16) for b in bursts]
+    gd = gpu.QPSKDeModulator(FS, RS, ALPHA, SPAN, tsc=TSC, use_fll=True)
+    gd.set_fir_mode(gpu.FIR_EXACT)
+    st = gpu.StreamingDemodulator(gd, START, END, max_block_floats=max(b.size for b in bursts), max_payload_bytes=1 << 16, depth=3)
+    got = []
+    for b in bursts:
+        st.push(b)
+        p = st.poll()
+        if p is not None:
+            got.append(p)
+    got += st.drain()
+    assert got == want
+    st.close()
+
+
 @pytest.mark.parametrize("mtu", [2040, 1000])
 def test_stream_mtu_blocks_equal_per_call_oracle(gpu, orc, mtu):
     """A continuous stream cut at radio-MTU boundaries (ModDemodOverSDR.cs:127-136): whatever each per-block call
