@@ -46,9 +46,29 @@ struct ChanArgs {
 __device__ __forceinline__ void nco_update_freq(const NcoParams& P, NcoState& S) {   // :181-186
   S.cur_freq = P.base_freq * (1.0 + S.total_ppm * 1e-6);
 }
+// fmod(x, 2 pi) for the phases an NCO produces.  fmod is exact — its result x - k*y (k = trunc(x/y)) is representable — so
+// one FMA with the right k returns it bit for bit; k from a product with 1/y can be off by one either way, which the sign
+// / range of the remainder shows.  Anything outside [0, 1e9) goes to the library routine.
+__device__ __forceinline__ double fmod_two_pi(double x) {
+  const double y = 2.0 * 3.14159265358979323846;
+  if (x >= 0.0 && x < 1e9) {
+    if (x < y) return x;
+    double k = floor(x * (1.0 / y));
+    double r = __fma_rn(-k, y, x);
+    if (r < 0.0) {
+      k -= 1.0;
+      r = __fma_rn(-k, y, x);
+    } else if (r >= y) {
+      k += 1.0;
+      r = __fma_rn(-k, y, x);
+    }
+    return r;
+  }
+  return fmod(x, y);
+}
 __device__ __forceinline__ void nco_wrap(NcoState& S) {                              // :188-193
   const double two_pi = 2.0 * 3.14159265358979323846;
-  S.phase = fmod(S.phase, two_pi);
+  S.phase = fmod_two_pi(S.phase);
   if (S.phase < 0) S.phase += two_pi;
 }
 __device__ __forceinline__ void nco_init(const NcoParams& P, NcoState& S, unsigned long long seed, unsigned long long stream) {
@@ -63,11 +83,15 @@ __device__ __forceinline__ void nco_init(const NcoParams& P, NcoState& S, unsign
   nco_update_freq(P, S);
   nco_wrap(S);
 }
-__device__ __forceinline__ void nco_next(const NcoParams& P, NcoState& S, unsigned long long seed, unsigned long long stream,
-                                         double& re, double& im) {                   // :69-79
-  if (P.max_ppm <= 0.0) {                                                            // :144-149
-    S.cur_freq = P.base_freq;
-  } else {
+// NextSample() :69-79 up to the new phase; the caller takes e^{j phase} (:77).  `inc` is the phase increment of :73,
+// 2 pi f / fs: the reference recomputes it for every sample, but its operands only change when the drift step below fires
+// (every drift_interval samples), so the quotient is cached between steps — same operands, same value.
+__device__ __forceinline__ double nco_increment(const NcoParams& P, const NcoState& S) {
+  return 2.0 * 3.14159265358979323846 * S.cur_freq / P.fs;                           // :73
+}
+__device__ __forceinline__ void nco_advance(const NcoParams& P, NcoState& S, unsigned long long seed, unsigned long long stream,
+                                            double& inc) {
+  if (P.max_ppm > 0.0) {                                                             // :144-149 (else: cur_freq = base_freq)
     S.drift_counter++;
     if (S.drift_counter >= P.drift_interval) {
       S.drift_counter = 0;
@@ -78,12 +102,11 @@ __device__ __forceinline__ void nco_next(const NcoParams& P, NcoState& S, unsign
       if (S.total_ppm > P.max_ppm) { S.total_ppm = P.max_ppm; S.drift_ppm = S.total_ppm - S.static_ppm; }
       else if (S.total_ppm < -P.max_ppm) { S.total_ppm = -P.max_ppm; S.drift_ppm = S.total_ppm - S.static_ppm; }
       nco_update_freq(P, S);
+      inc = nco_increment(P, S);
     }
   }
-  const double inc = 2.0 * 3.14159265358979323846 * S.cur_freq / P.fs;               // :73
   S.phase += inc;
   nco_wrap(S);
-  sincos(S.phase, &im, &re);
 }
 
 struct ChanState {
@@ -104,72 +127,108 @@ __global__ void chan_init_kernel(const ChanArgs a, ChanState* st) {
   st[c] = S;
 }
 
-__global__ void __launch_bounds__(32)
-    chan_apply_kernel(const ChanArgs a, ChanState* st, float2* hist, const float2* __restrict__ x, long long L, long long ldx,
-                      float2* __restrict__ y, long long ldy) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// The simulator in three passes.  Only the NCO phase is a recurrence (phase += inc, wrap, a drift step every millisecond
+// of samples: LocalOscilator.cs:69-79,144-186); everything else — e^{j phase} of both oscillators, the Box-Muller noise
+// pair, the multipath sum, the two complex mixes — depends on the sample index alone.
+//   chan_phase_kernel   one thread per (channel, oscillator): the phase sequence, to scratch [C][ldp] doubles
+//   chan_mix_kernel     one thread per sample: the rest, operation by operation as before
+//   chan_hist_kernel    one thread per channel: slides the multipath history
+// (The one-thread-per-channel version did all of it in the serial loop: 6.1 ms for 2048 channels x 4196 samples.)
+__global__ void __launch_bounds__(64)
+    chan_phase_kernel(const ChanArgs a, ChanState* st, long long L, double* __restrict__ ph_tx, double* __restrict__ ph_rx,
+                      long long ldp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = idx >> 1, which = idx & 1;
   if (c >= a.C) return;
   const unsigned long long ch = (unsigned long long)(a.first_channel + c);
-  ChanState S = st[c];
-  const float2* xc = x + (long long)c * ldx;
-  float2* yc = y + (long long)c * ldy;
-  float2* hc = hist + (long long)c * kPathHist;   // last kPathHist inputs of earlier calls, oldest first
+  const NcoParams P = which ? a.rx : a.tx;
+  NcoState S = which ? st[c].rx : st[c].tx;
+  double* out = (which ? ph_rx : ph_tx) + (long long)c * ldp;
+  if (P.max_ppm <= 0.0) S.cur_freq = P.base_freq;                                    // :144-149, every sample in the reference
+  double inc = nco_increment(P, S);
   for (long long n = 0; n < L; ++n) {
-    float xr, xi;
-    if (a.n_paths > 0) {
-      float accR = 0.f, accI = 0.f;
-      for (int k = 0; k < a.n_paths; ++k) {
-        const long long m = n - a.delay[k];
-        const float2 v = (m >= 0) ? xc[m] : hc[kPathHist + m];
-        const float gr = a.gain[2 * k], gi = a.gain[2 * k + 1];
-        const float p1 = gr * v.x, p2 = gi * v.y, p3 = gr * v.y, p4 = gi * v.x;
-        accR = accR + (p1 - p2);
-        accI = accI + (p3 + p4);
-      }
-      xr = accR; xi = accI;
-    } else {
-      const float2 v = xc[n];
-      xr = v.x; xi = v.y;
-    }
-    double tr, ti, rr, ri;
-    nco_next(a.tx, S.tx, a.seed, 4 * ch + 0, tr, ti);
-    nco_next(a.rx, S.rx, a.seed, 4 * ch + 1, rr, ri);
-    ri = -ri;                                                    // Complex.Conjugate
-    double dr = (double)xr, di = (double)xi, yr, yi;
-    if (a.mode == 0) {                                           // x * (tx * conj(rx))
-      const double pr = tr * rr - ti * ri, pi = tr * ri + ti * rr;
-      yr = dr * pr - di * pi; yi = dr * pi + di * pr;
-    } else {                                                     // ((x + noise) * tx) * conj(rx)
-      if (a.noise_rms > 0.f) {
-        const unsigned long long k = 2ULL * S.noise_pos;
-        const double u1 = 1.0 - rng_double(a.seed, 4 * ch + 2, k);
-        const double u2 = 1.0 - rng_double(a.seed, 4 * ch + 2, k + 1);
-        const double mag = sqrt(-2.0 * log(u1)) * (double)a.noise_rms;
-        const double ph = 2.0 * 3.14159265358979323846 * u2;
-        double sn, cs;
-        sincos(ph, &sn, &cs);
-        float ni = (float)(mag * cs), nq = (float)(mag * sn);
-        ni = fminf(fmaxf(ni, -1.f), 1.f);
-        nq = fminf(fmaxf(nq, -1.f), 1.f);
-        dr = dr + (double)ni; di = di + (double)nq;
-      }
-      const double ar = dr * tr - di * ti, ai = dr * ti + di * tr;
-      yr = ar * rr - ai * ri; yi = ar * ri + ai * rr;
-    }
-    S.noise_pos++;
-    yc[n] = make_float2((float)yr, (float)yi);
+    nco_advance(P, S, a.seed, 4 * ch + (unsigned long long)which, inc);
+    out[n] = S.phase;
   }
-  if (a.n_paths > 0) {
-    // slide the multipath history: keep the newest kPathHist inputs of (history ++ x)
-    if (L >= kPathHist) {
-      for (int i = 0; i < kPathHist; ++i) hc[i] = xc[L - kPathHist + i];
-    } else {
-      const int keep = kPathHist - (int)L;
-      for (int i = 0; i < keep; ++i) hc[i] = hc[i + (int)L];
-      for (int i = 0; i < (int)L; ++i) hc[keep + i] = xc[i];
+  if (which) {
+    st[c].rx = S;
+  } else {
+    st[c].tx = S;
+    st[c].noise_pos += (unsigned long long)L;        // the mixing pass of this slab counts back from here
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    chan_mix_kernel(const ChanArgs a, const ChanState* __restrict__ st, const float2* __restrict__ hist, const float2* __restrict__ x,
+                    long long n0, long long Ls, long long ldx, float2* __restrict__ y, long long ldy,
+                    const double* __restrict__ ph_tx, const double* __restrict__ ph_rx, long long ldp) {
+  for (int c = blockIdx.y; c < a.C; c += gridDim.y) {
+    const unsigned long long ch = (unsigned long long)(a.first_channel + c);
+    const float2* xc = x + (long long)c * ldx;
+    float2* yc = y + (long long)c * ldy;
+    const float2* hc = hist + (long long)c * kPathHist;   // last kPathHist inputs of earlier calls, oldest first
+    const unsigned long long pos0 = st[c].noise_pos - (unsigned long long)Ls;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < Ls; i += (long long)gridDim.x * blockDim.x) {
+      const long long n = n0 + i;
+      float xr, xi;
+      if (a.n_paths > 0) {
+        float accR = 0.f, accI = 0.f;
+        for (int k = 0; k < a.n_paths; ++k) {
+          const long long m = n - a.delay[k];
+          const float2 v = (m >= 0) ? xc[m] : hc[kPathHist + m];
+          const float gr = a.gain[2 * k], gi = a.gain[2 * k + 1];
+          const float p1 = gr * v.x, p2 = gi * v.y, p3 = gr * v.y, p4 = gi * v.x;
+          accR = accR + (p1 - p2);
+          accI = accI + (p3 + p4);
+        }
+        xr = accR; xi = accI;
+      } else {
+        const float2 v = xc[n];
+        xr = v.x; xi = v.y;
+      }
+      double tr, ti, rr, ri;
+      sincos(ph_tx[(long long)c * ldp + i], &ti, &tr);             // NextSample :77
+      sincos(ph_rx[(long long)c * ldp + i], &ri, &rr);
+      ri = -ri;                                                    // Complex.Conjugate
+      double dr = (double)xr, di = (double)xi, yr, yi;
+      if (a.mode == 0) {                                           // x * (tx * conj(rx))
+        const double pr = tr * rr - ti * ri, pi = tr * ri + ti * rr;
+        yr = dr * pr - di * pi; yi = dr * pi + di * pr;
+      } else {                                                     // ((x + noise) * tx) * conj(rx)
+        if (a.noise_rms > 0.f) {
+          const unsigned long long k = 2ULL * (pos0 + (unsigned long long)i);
+          const double u1 = 1.0 - rng_double(a.seed, 4 * ch + 2, k);
+          const double u2 = 1.0 - rng_double(a.seed, 4 * ch + 2, k + 1);
+          const double mag = sqrt(-2.0 * log(u1)) * (double)a.noise_rms;
+          const double ph = 2.0 * 3.14159265358979323846 * u2;
+          double sn, cs;
+          sincos(ph, &sn, &cs);
+          float ni = (float)(mag * cs), nq = (float)(mag * sn);
+          ni = fminf(fmaxf(ni, -1.f), 1.f);
+          nq = fminf(fmaxf(nq, -1.f), 1.f);
+          dr = dr + (double)ni; di = di + (double)nq;
+        }
+        const double ar = dr * tr - di * ti, ai = dr * ti + di * tr;
+        yr = ar * rr - ai * ri; yi = ar * ri + ai * rr;
+      }
+      yc[n] = make_float2((float)yr, (float)yi);
     }
   }
-  st[c] = S;
+}
+
+// slide the multipath history: keep the newest kPathHist inputs of (history ++ x)
+__global__ void chan_hist_kernel(const ChanArgs a, float2* hist, const float2* __restrict__ x, long long L, long long ldx) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const float2* xc = x + (long long)c * ldx;
+  float2* hc = hist + (long long)c * kPathHist;
+  if (L >= kPathHist) {
+    for (int i = 0; i < kPathHist; ++i) hc[i] = xc[L - kPathHist + i];
+  } else {
+    const int keep = kPathHist - (int)L;
+    for (int i = 0; i < keep; ++i) hc[i] = hc[i + (int)L];
+    for (int i = 0; i < (int)L; ++i) hc[keep + i] = xc[i];
+  }
 }
 
 __global__ void fill_bytes_kernel(unsigned long long seed, int first_channel, int C, long long n, uint8_t* out) {
@@ -268,6 +327,7 @@ struct qpsk_chan {
   int channels = 0;
   DevBuf<ChanState> d_state;
   DevBuf<float2> d_hist, d_in, d_out;
+  DevBuf<double> d_phase;          // [2][channels][slab] oscillator phases of the slab being mixed
   cudaStream_t stream = nullptr;
   ~qpsk_chan() {
     if (stream) cudaStreamDestroy(stream);
@@ -342,9 +402,30 @@ int qpsk_chan_apply_dev(qpsk_chan* c, const float* d_x, int64_t n_floats, int64_
   if (!d_x || !d_y) return QPSK_ERR_NULL;
   QPSK_TRY(ensure_device());
   cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
-  chan_apply_kernel<<<(c->channels + 31) / 32, 32, 0, s>>>(c->args, c->d_state.p, c->d_hist.p, (const float2*)d_x, n_floats >> 1,
-                                                           x_stride_floats >> 1, (float2*)d_y, y_stride_floats >> 1);
-  QPSK_LAUNCH_CHECK();
+  // time slabs bound the phase scratch (2 x 128 MB); an in-place call is allowed without multipath only, as before
+  const long long L = n_floats >> 1;
+  const int C = c->channels;
+  long long slab = (16LL << 20) / C;
+  if (slab < 256) slab = 256;
+  if (slab > L) slab = L;
+  QPSK_TRY(c->d_phase.ensure((size_t)2 * C * slab));
+  double* ph_tx = c->d_phase.p;
+  double* ph_rx = c->d_phase.p + (size_t)C * slab;
+  for (long long n0 = 0; n0 < L; n0 += slab) {
+    const long long Ls = (L - n0 < slab) ? (L - n0) : slab;
+    chan_phase_kernel<<<(2 * C + 63) / 64, 64, 0, s>>>(c->args, c->d_state.p, Ls, ph_tx, ph_rx, slab);
+    QPSK_LAUNCH_CHECK();
+    long long bx = (Ls + 255) / 256;
+    if (bx > 64) bx = 64;
+    chan_mix_kernel<<<dim3((unsigned)bx, (unsigned)(C < 65535 ? C : 65535)), 256, 0, s>>>(
+        c->args, c->d_state.p, c->d_hist.p, (const float2*)d_x, n0, Ls, x_stride_floats >> 1, (float2*)d_y, y_stride_floats >> 1, ph_tx,
+        ph_rx, slab);
+    QPSK_LAUNCH_CHECK();
+  }
+  if (c->args.n_paths > 0) {
+    chan_hist_kernel<<<(C + 127) / 128, 128, 0, s>>>(c->args, c->d_hist.p, (const float2*)d_x, L, x_stride_floats >> 1);
+    QPSK_LAUNCH_CHECK();
+  }
   return QPSK_OK;
 }
 
