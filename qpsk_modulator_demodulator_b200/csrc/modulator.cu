@@ -190,7 +190,9 @@ __device__ __forceinline__ float2 quadrant_symbol(int q) {
   return make_float2(i, v);
 }
 
-template <int MT>
+// SPS > 0: samples per symbol known at compile time (2, 4, 8 — the store offsets r*sps become immediates and tid / sps a
+// shift); SPS == 0: read from the arguments.
+template <int MT, int SPS = 0>
 __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a) {
   constexpr int R = kModR;
   // symbol D0 - HP + k lives at sym[k + 2*(k/8)]: two pad slots after every 8 symbols make the per-thread and
@@ -231,17 +233,20 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
       q0 = (int)a.tile_pre[(long long)f * a.tiles + t] - halo_sum_s + base;
     }
     float4* dst = reinterpret_cast<float4*>(sym + 10 * tid);
+    const bool inside = d0 >= 0 && d0 + 8 <= a.n_dibits;      // all eight symbols exist (every chunk but the frame's edges)
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       float2 v[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const long long d = d0 + j + u;
         const int code = (int)((c >> (14 - 2 * (j + u))) & 3u);
         float2 sv;
         if (a.diff) sv = quadrant_symbol((q0 + run[j + u]) & 3);
         else sv = make_float2((code & 2) ? kInvSqrt2 : -kInvSqrt2, (code & 1) ? kInvSqrt2 : -kInvSqrt2);
-        if (d < 0 || d >= a.n_dibits) sv = make_float2(0.f, 0.f);
+        if (!inside) {
+          const long long d = d0 + j + u;
+          if (d < 0 || d >= a.n_dibits) sv = make_float2(0.f, 0.f);
+        }
         v[u] = sv;
       }
       dst[j >> 1] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
   __syncthreads();
 
   // ---- polyphase FIR: this thread's phase p, groups of R consecutive symbols ----
-  const int sps = a.sps;
+  const int sps = SPS > 0 ? SPS : a.sps;
   const int gl = tid / sps;                       // group slot within a round
   const int p = tid - gl * sps;
   const int G = kModThreads / sps;                // whole groups per round
@@ -308,7 +313,24 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
 }
 
 typedef void (*ModShapeFn)(const ModArgs);
-static ModShapeFn mod_shape_pick(int mt) {
+template <int SPS>
+static ModShapeFn mod_shape_pick_sps(int mt) {
+  switch (mt) {
+    case 4: return mod_shape_kernel<4, SPS>;
+    case 8: return mod_shape_kernel<8, SPS>;
+    case 12: return mod_shape_kernel<12, SPS>;
+    case 16: return mod_shape_kernel<16, SPS>;
+    case 20: return mod_shape_kernel<20, SPS>;
+    case 24: return mod_shape_kernel<24, SPS>;
+    default: return nullptr;
+  }
+}
+static ModShapeFn mod_shape_pick(int mt, int sps) {
+  ModShapeFn f = nullptr;
+  if (sps == 2) f = mod_shape_pick_sps<2>(mt);
+  else if (sps == 4) f = mod_shape_pick_sps<4>(mt);
+  else if (sps == 8) f = mod_shape_pick_sps<8>(mt);
+  if (f) return f;
   switch (mt) {
     case 4: return mod_shape_kernel<4>;
     case 8: return mod_shape_kernel<8>;
@@ -422,7 +444,7 @@ struct ModEngine {
   int run(ModArgs a, bool pulse, int64_t n_dibits, int frames, float2* out, int64_t out_stride, cudaStream_t s) {
     const int bank = pulse ? 0 : 1;
     if (sps > kModThreads) return QPSK_ERR_UNSUPPORTED;
-    ModShapeFn shape = mod_shape_pick(MT[bank]);
+    ModShapeFn shape = mod_shape_pick(MT[bank], sps);
     if (!shape) return QPSK_ERR_UNSUPPORTED;        // more than kModMaxMT taps per phase (DESIGN.md limits)
     a.diff = diff ? 1 : 0;
     a.n_dibits = n_dibits;
