@@ -279,18 +279,22 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
       acc[r + 1] = make_float2(0.f, 0.f);
     }
     // tap m multiplies sym[first + r - m]; slot of symbol offset j is (j mod R); one new (older) symbol per tap,
-    // fetched two at a time (16-byte aligned for even m)
+    // fetched two at a time (16-byte aligned for even m).  MT = span + 1 is odd for the usual N = span*sps + 1: the last
+    // tap then stands alone and needs no fetch (padding it to a pair cost R FFMA2 and one LDS.128 per group).
 #pragma unroll
     for (int m = 0; m < MT; m += 2) {
+      constexpr int kLast = MT - 1;
+      const bool pair = m < kLast;                 // compile-time after unrolling
+      float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
       // symbols (first - m - 2, first - m - 1): block ceil((m+2)/8) back, slot (8 - (m+2)%8) % 8
-      const float4 nx = *reinterpret_cast<const float4*>(gs - 10 * ((m + 2 + 7) / 8) + ((8 - ((m + 2) & 7)) & 7));
+      if (pair) nx = *reinterpret_cast<const float4*>(gs - 10 * ((m + 2 + 7) / 8) + ((8 - ((m + 2) & 7)) & 7));
       {
         const float2 tt = make_float2(tap[m], tap[m]);
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(r - m + 16 * R) % R], tt, acc[r]);
-        w[(R - 1 - m + 16 * R) % R] = make_float2(nx.z, nx.w);      // symbol first - m - 1
+        if (pair) w[(R - 1 - m + 16 * R) % R] = make_float2(nx.z, nx.w);      // symbol first - m - 1
       }
-      {
+      if (pair) {
         const float2 tt = make_float2(tap[m + 1], tap[m + 1]);
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = ffma2(w[(r - m - 1 + 16 * R) % R], tt, acc[r]);
@@ -317,9 +321,15 @@ template <int SPS>
 static ModShapeFn mod_shape_pick_sps(int mt) {
   switch (mt) {
     case 4: return mod_shape_kernel<4, SPS>;
+    case 5: return mod_shape_kernel<5, SPS>;
+    case 7: return mod_shape_kernel<7, SPS>;
     case 8: return mod_shape_kernel<8, SPS>;
+    case 9: return mod_shape_kernel<9, SPS>;
+    case 11: return mod_shape_kernel<11, SPS>;
     case 12: return mod_shape_kernel<12, SPS>;
+    case 13: return mod_shape_kernel<13, SPS>;
     case 16: return mod_shape_kernel<16, SPS>;
+    case 17: return mod_shape_kernel<17, SPS>;
     case 20: return mod_shape_kernel<20, SPS>;
     case 24: return mod_shape_kernel<24, SPS>;
     default: return nullptr;
@@ -333,7 +343,13 @@ static ModShapeFn mod_shape_pick(int mt, int sps) {
   if (f) return f;
   switch (mt) {
     case 4: return mod_shape_kernel<4>;
+    case 5: return mod_shape_kernel<5>;
+    case 7: return mod_shape_kernel<7>;
     case 8: return mod_shape_kernel<8>;
+    case 9: return mod_shape_kernel<9>;
+    case 11: return mod_shape_kernel<11>;
+    case 13: return mod_shape_kernel<13>;
+    case 17: return mod_shape_kernel<17>;
     case 12: return mod_shape_kernel<12>;
     case 16: return mod_shape_kernel<16>;
     case 20: return mod_shape_kernel<20>;
@@ -346,7 +362,7 @@ static ModShapeFn mod_shape_pick(int mt, int sps) {
   }
 }
 static int mod_pad_taps(int m) {
-  static const int sizes[] = {4, 8, 12, 16, 20, 24, 32, 48, 64, 96};
+  static const int sizes[] = {4, 5, 7, 8, 9, 11, 12, 13, 16, 17, 20, 24, 32, 48, 64, 96};   // span + 1 for the usual spans, exactly
   for (int v : sizes)
     if (m <= v) return v;
   return 0;
