@@ -209,15 +209,20 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
   {
     const long long d0 = D0 - a.HP + 8 * tid;
     const unsigned c = chunk_codes(a, f, d0);
-    int run[8];
-    int q0 = 0;
+    // The eight 2-bit codes spread to one nibble each (symbol j in nibble 7-j), so that the running rotation of all eight
+    // symbols is three shift-add steps on the packed word (every sum is only needed mod 4: the mask keeps each nibble
+    // below 4, no carry ever crosses a nibble) instead of eight serial adds.
+    unsigned x = c & 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    unsigned sI, sQ;                                // sign of I / Q of symbol j in bit 4*(7-j)
     if (a.diff) {
-      int acc = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc += (int)((c >> (14 - 2 * j)) & 3u);
-        run[j] = acc;
-      }
+      unsigned pre = x;                             // nibble 7-j: sum of the codes of symbols 0..j, mod 4
+      pre = (pre + (pre >> 4)) & 0x33333333u;
+      pre = (pre + (pre >> 8)) & 0x33333333u;
+      pre = (pre + (pre >> 16)) & 0x33333333u;
+      const int acc = (int)(pre & 3u);              // the chunk's total rotation
       int inc = acc;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -230,8 +235,17 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
       __syncthreads();
       int base = inc - acc;
       for (int w = 0; w < warp; ++w) base += warp_tot[w];
-      q0 = (int)a.tile_pre[(long long)f * a.tiles + t] - halo_sum_s + base;
+      const unsigned q0 = (unsigned)((int)a.tile_pre[(long long)f * a.tiles + t] - halo_sum_s + base) & 3u;
+      const unsigned q = (pre + q0 * 0x11111111u) & 0x33333333u;      // quadrant of every symbol
+      // quadrant_symbol: q = 0:(+,+) 1:(-,+) 2:(-,-) 3:(+,-)  ->  I negative iff bit0 ^ bit1, Q negative iff bit1
+      sI = (q ^ (q >> 1)) & 0x11111111u;
+      sQ = (q >> 1) & 0x11111111u;
+    } else {
+      // :150-151  bit == 0 ? -1/sqrt2 : +1/sqrt2, I from the first bit of the dibit, Q from the second
+      sI = (~x >> 1) & 0x11111111u;
+      sQ = ~x & 0x11111111u;
     }
+    const unsigned kMag = __float_as_uint(kInvSqrt2);
     float4* dst = reinterpret_cast<float4*>(sym + 10 * tid);
     const bool inside = d0 >= 0 && d0 + 8 <= a.n_dibits;      // all eight symbols exist (every chunk but the frame's edges)
 #pragma unroll
@@ -239,10 +253,8 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
       float2 v[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int code = (int)((c >> (14 - 2 * (j + u))) & 3u);
-        float2 sv;
-        if (a.diff) sv = quadrant_symbol((q0 + run[j + u]) & 3);
-        else sv = make_float2((code & 2) ? kInvSqrt2 : -kInvSqrt2, (code & 1) ? kInvSqrt2 : -kInvSqrt2);
+        const int sh = 31 - 4 * (7 - (j + u));      // moves the symbol's sign bit to bit 31
+        float2 sv = make_float2(__uint_as_float(kMag | ((sI << sh) & 0x80000000u)), __uint_as_float(kMag | ((sQ << sh) & 0x80000000u)));
         if (!inside) {
           const long long d = d0 + j + u;
           if (d < 0 || d >= a.n_dibits) sv = make_float2(0.f, 0.f);
