@@ -52,17 +52,13 @@ __device__ __forceinline__ void nco_update_freq(const NcoParams& P, NcoState& S)
 __device__ __forceinline__ double fmod_two_pi(double x) {
   const double y = 2.0 * 3.14159265358979323846;
   if (x >= 0.0 && x < 1e9) {
-    if (x < y) return x;
-    double k = floor(x * (1.0 / y));
-    double r = __fma_rn(-k, y, x);
-    if (r < 0.0) {
-      k -= 1.0;
-      r = __fma_rn(-k, y, x);
-    } else if (r >= y) {
-      k += 1.0;
-      r = __fma_rn(-k, y, x);
-    }
-    return r;
+    // branch-free on the recurrence: the three candidate remainders (k - 1, k, k + 1) are independent FMAs, the right one
+    // is the one in [0, y)
+    const double k = floor(x * (1.0 / y));
+    const double r0 = __fma_rn(-k, y, x);
+    const double rm = __fma_rn(-(k - 1.0), y, x);
+    const double rp = __fma_rn(-(k + 1.0), y, x);
+    return (r0 < 0.0) ? rm : ((r0 >= y) ? rp : r0);
   }
   return fmod(x, y);
 }
