@@ -485,22 +485,32 @@ struct ModEngine {
     // last output index + filter delay, in symbols (+1): symbols past n_dibits are zero
     const long long n_virtual = (a.total - 1 + a.delay) / sps + 1;
     const long long tiles = (n_virtual + a.TD - 1) / a.TD;
-    if (tiles > 0x7fffffffLL || frames > 65535) return QPSK_ERR_UNSUPPORTED;
+    if (tiles > 0x7fffffffLL) return QPSK_ERR_UNSUPPORTED;
     a.tiles = (int)tiles;
-    a.out = out; a.out_stride = out_stride;
-    QPSK_TRY(d_tile_sum.ensure((size_t)tiles * frames));
-    QPSK_TRY(d_tile_pre.ensure((size_t)tiles * frames));
+    a.out_stride = out_stride;
+    // frames ride on gridDim.y (<= 65535): larger batches go in slices, each with its own view of the frame arrays
+    constexpr int kFrameSlice = 65535;
+    const int slice = frames < kFrameSlice ? frames : kFrameSlice;
+    QPSK_TRY(d_tile_sum.ensure((size_t)tiles * slice));
+    QPSK_TRY(d_tile_pre.ensure((size_t)tiles * slice));
     a.tile_sum = d_tile_sum.p; a.tile_pre = d_tile_pre.p;
-    const dim3 grid((unsigned)tiles, (unsigned)frames);
-    if (diff) {
-      const dim3 grid_rot((unsigned)((tiles + kModThreads / 32 - 1) / (kModThreads / 32)), (unsigned)frames);
-      mod_tile_rot_kernel<<<grid_rot, kModThreads, 0, s>>>(a);
-      QPSK_LAUNCH_CHECK();
-      mod_tile_scan_kernel<<<(frames + 3) / 4, 128, 0, s>>>(a);
+    const uint8_t* payload0 = a.payload;
+    for (int f0 = 0; f0 < frames; f0 += kFrameSlice) {
+      const int nf = (frames - f0 < kFrameSlice) ? (frames - f0) : kFrameSlice;
+      a.frames = nf;
+      if (a.mode == 0 && payload0) a.payload = payload0 + (long long)f0 * a.n_payload;
+      a.out = out + (long long)f0 * out_stride;
+      const dim3 grid((unsigned)tiles, (unsigned)nf);
+      if (diff) {
+        const dim3 grid_rot((unsigned)((tiles + kModThreads / 32 - 1) / (kModThreads / 32)), (unsigned)nf);
+        mod_tile_rot_kernel<<<grid_rot, kModThreads, 0, s>>>(a);
+        QPSK_LAUNCH_CHECK();
+        mod_tile_scan_kernel<<<(nf + 3) / 4, 128, 0, s>>>(a);
+        QPSK_LAUNCH_CHECK();
+      }
+      shape<<<grid, kModThreads, 0, s>>>(a);
       QPSK_LAUNCH_CHECK();
     }
-    shape<<<grid, kModThreads, 0, s>>>(a);
-    QPSK_LAUNCH_CHECK();
     return QPSK_OK;
   }
 };

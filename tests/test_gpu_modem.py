@@ -11,6 +11,26 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5
 
 TSC = "11001010011101100100100110101100" + "01110100111001011010001101101001"   # testAtDataLevel.cs:20-22
+def test_modulate_frames_dev_more_than_one_grid_of_frames(gpu, orc):
+    """Frame batches beyond gridDim.y (65535) go through in slices: 70000 short frames, spot-checked around the seam."""
+    import torch
+    frames, n_payload = 70000, 6
+    m = gpu.QPSKModulator(4000, 1000, 0.35, 6, True, TSC)
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    s = ts.cuda_stream
+    pay = torch.empty((frames, n_payload), dtype=torch.uint8, device="cuda")
+    gpu.fill_bytes_dev(9, 0, frames, n_payload, pay.data_ptr(), s)
+    ff = m.frame_floats(n_payload, b"S", b"E")
+    out = torch.zeros((frames, ff), dtype=torch.float32, device="cuda")
+    assert m.modulate_frames_dev(pay.data_ptr(), n_payload, frames, b"S", b"E", out.data_ptr(), ff, s) == ff
+    torch.cuda.synchronize()
+    om = orc.QPSKModulator(4000, 1000, 0.35, 6, True, TSC)
+    for f in (0, 65534, 65535, 65536, frames - 1):
+        want = om.ModulateBytes(pay[f].cpu().numpy().tobytes(), b"S", b"E")
+        assert _close(out[f].cpu().numpy(), want), f
+
+
 def test_full_size_modulator_share_config5(gpu, orc):
     """BASELINE configs[4], one GPU's share at full size (2048 frames x 64 KiB payload, sps 4, span 10: 17.2 GB of
     samples): frames spread over the batch against the oracle, the differential chain restarting per frame (two frames
