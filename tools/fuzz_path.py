@@ -6,6 +6,7 @@ draws its design parameters, sizes, channel count and chunking at random and fee
   costas  CostasLoopQpsk.Process: outputs bit-identical, (theta, freq) to 1e-11 (fp64 sin/cos ulps)
   demod   QPSKDeModulator.DeModulate in exact mode, with / without FLL, TSC, differential: bit strings identical
   mod     QPSKModulator.Modulate: within 1e-5 x max|y|
+  framer  the framer half of DeModulateBytes on random bit chunks (qpsk_demod_frame_bits): payloads and in-frame flags identical
 usage: python tools/fuzz_path.py [cases per family] [seed] [families, comma separated]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,7 +18,7 @@ O.build()
 Q.set_device(0)
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-fams = sys.argv[3].split(",") if len(sys.argv) > 3 else ["fir", "mm", "costas", "demod", "mod"]
+fams = sys.argv[3].split(",") if len(sys.argv) > 3 else ["fir", "mm", "costas", "demod", "mod", "framer"]
 rng = np.random.default_rng(seed)
 TOL = 1e-5
 bad = {}
@@ -202,7 +203,44 @@ def fuzz_mod():
             note("mod", dict(sps=sps, alpha=alpha, span=span, diff=diff, tsc=None if tsc is None else len(tsc), nb=nb, shaping=shaping))
 
 
+def fuzz_framer():
+    bits_of = lambda b: "".join(format(v, "08b") for v in b)
+    for k in range(cases):
+        sm = rng.integers(0, 256, int(rng.choice([1, 1, 2, 5, 13, 40])), dtype=np.uint8).tobytes()
+        em = rng.integers(0, 256, int(rng.choice([1, 2, 4, 9])), dtype=np.uint8).tobytes()
+        C = int(rng.choice([1, 1, 3, 7, 33, 70]))
+        ring = int(rng.choice([8, 32, 1 << 20]))
+        rows = []
+        for c in range(C):
+            t = ""
+            for _f in range(int(rng.integers(1, 5))):
+                t += "".join(rng.choice(["0", "1"], int(rng.integers(0, 60))))
+                body = rng.integers(0, 256, int(rng.integers(0, 50)), dtype=np.uint8).tobytes()
+                if rng.random() < 0.2:
+                    body = body[: len(body) // 2] + sm + body[len(body) // 2:]
+                frame = bits_of(sm + body + em)
+                if rng.random() < 0.15:
+                    frame = frame[: int(rng.integers(0, len(frame)))]          # a frame cut short
+                t += frame
+            rows.append(t + "".join(rng.choice(["0", "1"], int(rng.integers(0, 60)))))
+        gd = Q.QPSKDeModulator(4000, 1000, max_frame_bytes=ring, channels=C)
+        ods = [O.QPSKDeModulator(4000, 1000, ring_capacity=ring) for _ in range(C)]
+        pos = [0] * C
+        info = dict(ns=len(sm), ne=len(em), C=C, ring=ring)
+        while any(pos[c] < len(rows[c]) for c in range(C)):
+            hi = int(rng.choice([20, 90, 600]))
+            take = [int(rng.integers(0, hi)) for _ in range(C)]
+            chunks = [rows[c][pos[c]:pos[c] + take[c]] for c in range(C)]
+            pos = [pos[c] + take[c] for c in range(C)]
+            got = gd.FrameBits(chunks if C > 1 else chunks[0], sm, em, cap=4096)
+            got = got if C > 1 else [got]
+            inf = np.atleast_1d(gd.in_frame)
+            for c in range(C):
+                if got[c] != ods[c].FrameBits(chunks[c], sm, em, cap=4096) or bool(inf[c]) != bool(ods[c].in_frame):
+                    note("framer", dict(info, c=c, pos=pos[c]))
+
+
 for f in fams:
-    {"fir": fuzz_fir, "mm": fuzz_mm, "costas": fuzz_costas, "demod": fuzz_demod, "mod": fuzz_mod}[f]()
+    {"framer": fuzz_framer, "fir": fuzz_fir, "mm": fuzz_mm, "costas": fuzz_costas, "demod": fuzz_demod, "mod": fuzz_mod}[f]()
     print(f"fuzz_path[{f}]: {cases} cases, {bad.get(f, 0) + sum(v for k2, v in bad.items() if k2.startswith(f + '.'))} mismatching", flush=True)
 sys.exit(1 if bad else 0)
