@@ -101,3 +101,24 @@ def test_product_never_references_the_oracle():
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
     needed = subprocess.check_output(["readelf", "-d", os.path.join(pkg, "lib", "libqpskcuda.so")], text=True)
     assert "oracle" not in needed
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs without a GPU (the CPU arm the driver times next to ours) and prints one JSON
+    line with the contract's keys; under torchrun only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Msamples/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["metric"].startswith("Msamples/s RRC FIR")
+    r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"), cwd=root)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
