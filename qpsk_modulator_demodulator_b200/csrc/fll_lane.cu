@@ -1,0 +1,176 @@
+// fll_lane.cu — K4 for large batches: the band-edge FLL (MS/Models/Band-Edge Filter.cs:102-129,185-195) with one LANE
+// per stream.
+//
+// The two-warp kernel (fll_duo.cu) spreads one stream over 8 lanes and two warps to shorten the per-sample recurrence;
+// that costs ~44 warp instructions per stream and sample, and from ~4096 streams on the issue slots, not the latency,
+// set its time (1.7 / 3.1 / 5.4 ms at 4096 / 8192 / 16384 streams x 4196 samples).  Here a lane runs a whole stream the
+// way one CPU thread of the reference does — the 8 SIMD-lane partial sums of ComplexDotWindow (FIRFilter.cs:165-192)
+// are 8 register accumulators per sum, added in lane order, then the scalar tail — so a sample costs ~27 warp
+// instructions per stream (~850 per warp), no cross-lane traffic and no hand-over; 32 streams per warp, one warp per
+// CTA.  Measured: 2.9 / 3.0 / 3.2 / 4.5 ms at 2048 / 4096 / 8192 / 16384 streams — a latency floor of ~1370 cycles per
+// sample on one in-order warp, so it is the choice only for the largest batches (FllEngine::process_dev).  Known slack:
+// the taps travel constant bank -> uniform register -> register (120 moves per sample); a broadcast LDS.128 per four
+// taps would remove most of them.
+//   * taps: kernel parameters (constant bank);
+//   * ring of past outputs: shared memory, [2N][32] — every sample is written at `pos` and `pos + N`, so the
+//     chronological window is the N slots after `pos` with compile-time offsets (no modulo, no index arithmetic);
+//   * input / output: staged through shared memory in rounds of 32 samples, coalesced 256-byte row reads and writes.
+// State layout in device memory is the generic one (ring [N][C] + head, (phase, freq)), so calls may alternate between
+// this kernel and the others.  sin/cos and the phase wrap are the short-range forms of the two-warp kernel (the
+// launcher keeps |phase| < 1e4 here too).  Compiled with --fmad=false.
+#include "loops.cuh"
+
+namespace qpsk {
+
+namespace {
+
+constexpr int kLaneBlock = 32;            // samples per staged round
+constexpr int kLanePitch = 33;            // float2 row pitch of the staging tiles
+
+template <int N>
+struct LaneTaps {
+  float i[N], q[N];                       // reversed lower-filter taps (rev[k] = lower[N-1-k])
+};
+
+// remainderf(phase, 2 pi) for |phase| < 1e5, as in fll_duo.cu (exact fp64 quotient, exact remainder; a zero keeps the
+// sign of phase like Math.IEEERemainder)
+__device__ __forceinline__ float lane_wrap_phase(float phase) {
+  const double c = (double)kTwoPiF;
+  const double pd = (double)phase;
+  const double n = rint(pd * (1.0 / c));
+  const double r = fma(-n, c, pd);
+  return (r == 0.0) ? copysignf(0.f, phase) : (float)r;
+}
+
+template <int N>
+__global__ void __launch_bounds__(32)
+    fll_lane_kernel(const FllParams P, const __grid_constant__ LaneTaps<N> T, float2* ring_g, int* head_g, float2* pf_g, int C,
+                    const float2* __restrict__ x, float2* __restrict__ y, long long L, long long ldx, long long ldy) {
+  __shared__ float2 ring[2 * N][32];
+  __shared__ float2 xin[kLaneBlock][kLanePitch];
+  __shared__ float2 yout[kLaneBlock][kLanePitch];
+  const int lane = threadIdx.x;
+  const int c0 = blockIdx.x * 32;
+  const int c = c0 + lane;
+  const bool live = c < C;
+  const int cc = live ? c : C - 1;        // idle lanes shadow the last stream (their results are dropped)
+
+  // chronological order, oldest first, into slots 0..N-1 and their mirrors: the next write goes to slot 0
+  {
+    const int head = head_g[cc];
+    for (int j = 0; j < N; ++j) {
+      int k = head + j;
+      if (k >= N) k -= N;
+      const float2 v = ring_g[(long long)k * C + cc];
+      ring[j][lane] = v;
+      ring[j + N][lane] = v;
+    }
+  }
+  const float2 pf = pf_g[cc];
+  float phase = pf.x, freq = pf.y;
+  int pos = 0;
+  const int rows = (C - c0 < 32) ? (C - c0) : 32;
+
+  for (long long n0 = 0; n0 < L; n0 += kLaneBlock) {
+    const int blk = (int)((L - n0 < kLaneBlock) ? (L - n0) : kLaneBlock);
+    // stage: lane l fetches sample n0 + l of every stream of the CTA
+    if (lane < blk) {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int ch = c0 + (r < rows ? r : rows - 1);
+        xin[lane][r] = x[(long long)ch * ldx + n0 + lane];
+      }
+    }
+    __syncwarp();
+    for (int sidx = 0; sidx < blk; ++sidx) {
+      const float2 in = xin[sidx][lane];
+      float s, cs;
+      sincos_f32_fast(phase, &s, &cs);                 // MathF.Cos/Sin(phase) :108-109
+      const float oI = in.x * cs - in.y * s;           // :111
+      const float oQ = in.x * s + in.y * cs;           // :112
+      yout[sidx][lane] = make_float2(oI, oQ);
+      ring[pos][lane] = make_float2(oI, oQ);           // over the oldest sample, and its mirror
+      ring[pos + N][lane] = make_float2(oI, oQ);
+      const float2* win = &ring[pos + 1][lane];        // window element i (oldest first) at win[i * 32]
+      pos = (pos + 1 == N) ? 0 : pos + 1;
+      // ComplexDotWindow (FIRFilter.cs:165-192) for both band-edge filters at once: upper = conj(lower)
+      // (Band-Edge Filter.cs:176-178) shares the four products, see fll_step
+      float loI[8], loQ[8], upI[8], upQ[8];
+#pragma unroll
+      for (int l = 0; l < 8; ++l) loI[l] = loQ[l] = upI[l] = upQ[l] = 0.f;
+      constexpr int nVec = N - (N & 7);
+#pragma unroll
+      for (int i = 0; i < nVec; ++i) {
+        const float2 v = win[i * 32];
+        const float a = T.i[i], b = T.q[i];
+        const float p1 = a * v.x, p2 = b * v.y, p3 = a * v.y, p4 = b * v.x;
+        loI[i & 7] = loI[i & 7] + (p1 - p2);
+        loQ[i & 7] = loQ[i & 7] + (p3 + p4);
+        upI[i & 7] = upI[i & 7] + (p1 + p2);
+        upQ[i & 7] = upQ[i & 7] + (p3 - p4);
+      }
+      float aLoI = 0.f, aLoQ = 0.f, aUpI = 0.f, aUpQ = 0.f;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        aLoI += loI[l]; aLoQ += loQ[l]; aUpI += upI[l]; aUpQ += upQ[l];
+      }
+#pragma unroll
+      for (int i = nVec; i < N; ++i) {
+        const float2 v = win[i * 32];
+        const float a = T.i[i], b = T.q[i];
+        const float p1 = a * v.x, p2 = b * v.y, p3 = a * v.y, p4 = b * v.x;
+        aLoI += (p1 - p2); aLoQ += (p3 + p4); aUpI += (p1 + p2); aUpQ += (p3 - p4);
+      }
+      const float powUpper = aUpI * aUpI + aUpQ * aUpQ;  // :118
+      const float powLower = aLoI * aLoI + aLoQ * aLoQ;  // :119
+      const float error = powLower - powUpper;           // :121
+      freq += P.beta * error;                            // :124
+      phase += freq + P.alpha * error;                   // :125
+      if (phase > kTwoPiF || phase < -kTwoPiF) phase = lane_wrap_phase(phase);   // :185-189
+      if (freq > P.max_freq) freq = P.max_freq;          // :191-195
+      else if (freq < P.min_freq) freq = P.min_freq;
+    }
+    __syncwarp();
+    // flush: lane l writes sample n0 + l of every live stream
+    if (lane < blk) {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r)
+        if (r < rows) y[(long long)(c0 + r) * ldy + n0 + lane] = yout[lane][r];
+    }
+    __syncwarp();
+  }
+  if (live) {
+    // oldest first from slot `pos`; head = 0 in the generic layout
+    for (int j = 0; j < N; ++j) ring_g[(long long)j * C + c] = ring[pos + j][lane];
+    head_g[c] = 0;
+    pf_g[c] = make_float2(phase, freq);
+  }
+}
+
+template <int N>
+int fll_lane_launch_n(const FllParams& P, const std::vector<float>& lower, float2* ring, int* head, float2* pf, int C,
+                      const float2* x, float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {
+  LaneTaps<N> T;
+  for (int k = 0; k < N; ++k) {
+    T.i[k] = lower[2 * (size_t)(N - 1 - k)];
+    T.q[k] = lower[2 * (size_t)(N - 1 - k) + 1];
+  }
+  fll_lane_kernel<N><<<(C + 31) / 32, 32, 0, s>>>(P, T, ring, head, pf, C, x, y, L, ldx, ldy);
+  QPSK_LAUNCH_CHECK();
+  return QPSK_OK;
+}
+
+}  // namespace
+
+bool fll_lane_supported(int n_taps) { return n_taps == 40 || n_taps == 10; }
+
+int fll_lane_launch(const FllParams& P, const std::vector<float>& lower, float2* ring, int* head, float2* pf, int C,
+                    const float2* x, float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {
+  switch (P.n_taps) {
+    case 40: return fll_lane_launch_n<40>(P, lower, ring, head, pf, C, x, y, L, ldx, ldy, s);   // QPSKDeModulator.cs:35
+    case 10: return fll_lane_launch_n<10>(P, lower, ring, head, pf, C, x, y, L, ldx, ldy, s);   // testFullDemodChain.cs:24
+    default: return QPSK_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace qpsk

@@ -375,18 +375,33 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
   if (L == 0) return QPSK_OK;
   if (!x || !y) return QPSK_ERR_NULL;
   if (!s) s = stream;
-  static const bool force_group = [] {
-    const char* e = getenv("QPSK_FLL_IMPL");                 // "group": the single-warp kernels (A/B timing, tests)
-    return e && strcmp(e, "group") == 0;
+  static const int force_impl = [] {
+    const char* e = getenv("QPSK_FLL_IMPL");                 // "group": the single-warp kernels, "thread": one thread per
+    if (e && strcmp(e, "group") == 0) return 1;              // stream (A/B timing, tests)
+    if (e && strcmp(e, "thread") == 0) return 2;
+    if (e && strcmp(e, "lane") == 0) return 3;               // "lane": one lane per stream at any stream count
+    if (e && strcmp(e, "duo") == 0) return 4;                // "duo": never the lane kernel
+    return 0;
   }();
+  // From about 12000 streams on, the issue slots bound the two-warp kernel (44 warp instructions per stream and sample) and
+  // one lane per stream is ahead: 4.49 against 5.40 ms at 16384 streams x 4196 samples, but 3.24 against 3.06 ms at 8192
+  // (its floor is ~2.9 ms: ~1370 cycles per sample on one in-order warp).  tools/fll_impl_sweep.py; QPSK_FLL_LANE_MIN
+  // overrides.
+  static const int lane_min = [] {
+    const char* e = getenv("QPSK_FLL_LANE_MIN");
+    return e ? atoi(e) : 12288;
+  }();
+  const bool force_group = force_impl == 1 || force_impl == 2;
   // The two-warp kernel evaluates sin/cos and the phase wrap with short-range formulas (|phase| < 1e5): the loop
   // keeps |phase| <= 2*pi + max|freq|, so only a caller-set state or an absurd frequency limit (sps < 1e-3) can
   // leave that range — those calls take the generic kernels, which use the library routines.
   const bool wild = state_wild || !(P.max_freq < 1e4f);
   state_wild = false;                                          // any kernel leaves the state wrapped and clamped
+  if (!force_group && !wild && fll_lane_supported(n_taps) && force_impl != 4 && (force_impl == 3 || channels >= lane_min))
+    return fll_lane_launch(P, lower, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
   if (!force_group && !wild && fll_duo_supported(n_taps))
     return fll_duo_launch(P, d_taps.p, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
-  if (FllGroupFn fn = wild ? nullptr : fll_group_pick(n_taps)) {
+  if (FllGroupFn fn = (wild || force_impl == 2) ? nullptr : fll_group_pick(n_taps)) {
     // 8 lanes per stream, specialised on the tap count (the default 40-tap and the 10..55-tap filters)
     const int blocks = (channels + kFllCtaStreams - 1) / kFllCtaStreams;
     fn<<<blocks, kFllCtaThreads, 0, s>>>(P, d_taps.p, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy);
@@ -398,7 +413,7 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
     const int Np = n_taps + (n_taps & 1);
     const size_t smem = (size_t)(2 * Np + 4) * sizeof(float) + (size_t)kFllCtaStreams * kFllGroup * sizeof(float4) +
                         (size_t)2 * kFllCtaStreams * kFllBlock * sizeof(float2) + (size_t)kFllCtaStreams * n_taps * sizeof(float2);
-    if (smem <= 200 * 1024) {
+    if (smem <= 200 * 1024 && force_impl != 2) {
       const int blocks = (channels + kFllCtaStreams - 1) / kFllCtaStreams;
       QPSK_CUDA_TRY(cudaFuncSetAttribute(fll_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       fll_group_kernel<<<blocks, kFllCtaThreads, smem, s>>>(P, d_taps.p, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy);

@@ -296,6 +296,11 @@ bool fll_duo_supported(int n_taps);
 int fll_duo_launch(const FllParams& P, const float* taps, float2* ring, int* head, float2* pf, int C, const float2* x,
                    float2* y, long long L, long long ldx, long long ldy, cudaStream_t s);
 
+// fll_lane.cu: one lane per stream, for large batches (40 and 10 taps)
+bool fll_lane_supported(int n_taps);
+int fll_lane_launch(const FllParams& P, const std::vector<float>& lower, float2* ring, int* head, float2* pf, int C,
+                    const float2* x, float2* y, long long L, long long ldx, long long ldy, cudaStream_t s);
+
 struct MmEngine {
   int channels = 1;
   MmParams P{};

@@ -9,9 +9,10 @@ import qpsk_modulator_demodulator_b200 as Q
 Q.set_device(0)
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+SIZES = [int(v) for v in os.environ["FUZZ_SIZES"].split(",")] if os.environ.get("FUZZ_SIZES") else None   # e.g. 10,40 with QPSK_FLL_IMPL=lane
 bad = 0
 for k in range(cases):
-    size = int(rng.integers(1, 70))
+    size = int(rng.choice(SIZES)) if SIZES else int(rng.integers(1, 70))
     sps = float(np.float32(rng.choice([0.7, 1.0, 2.0, 3.0, 4.0, 8.0, 30.0])))
     rolloff = float(np.float32(rng.uniform(0.05, 1.0)))
     bw = float(np.float32(10 ** rng.uniform(-4, -0.3)))
