@@ -8,10 +8,8 @@
 // are 8 register accumulators per sum, added in lane order, then the scalar tail — so a sample costs ~27 warp
 // instructions per stream (~850 per warp), no cross-lane traffic and no hand-over; 32 streams per warp, one warp per
 // CTA.  Measured: 2.9 / 3.0 / 3.2 / 4.5 ms at 2048 / 4096 / 8192 / 16384 streams — a latency floor of ~1370 cycles per
-// sample on one in-order warp, so it is the choice only for the largest batches (FllEngine::process_dev).  Known slack:
-// the taps travel constant bank -> uniform register -> register (120 moves per sample); a broadcast LDS.128 per four
-// taps would remove most of them.
-//   * taps: kernel parameters (constant bank);
+// sample on one in-order warp, so it is the choice only for the largest batches (FllEngine::process_dev).
+//   * taps: kernel parameters, copied once to shared memory and read with broadcast LDS.128 (two taps each);
 //   * ring of past outputs: shared memory, [2N][32] — every sample is written at `pos` and `pos + N`, so the
 //     chronological window is the N slots after `pos` with compile-time offsets (no modulo, no index arithmetic);
 //   * input / output: staged through shared memory in rounds of 32 samples, coalesced 256-byte row reads and writes.
@@ -49,7 +47,13 @@ __global__ void __launch_bounds__(32)
   __shared__ float2 ring[2 * N][32];
   __shared__ float2 xin[kLaneBlock][kLanePitch];
   __shared__ float2 yout[kLaneBlock][kLanePitch];
+  // taps as (a_i, b_i, a_{i+1}, b_{i+1}): one broadcast LDS.128 per two taps (straight from the constant bank they took a
+  // uniform load and a move each, ~170 instructions per sample)
+  __shared__ __align__(16) float4 tap4[(N + 1) / 2];
   const int lane = threadIdx.x;
+  for (int k = lane; k < (N + 1) / 2; k += 32)
+    tap4[k] = make_float4(T.i[2 * k], T.q[2 * k], (2 * k + 1 < N) ? T.i[2 * k + 1] : 0.f, (2 * k + 1 < N) ? T.q[2 * k + 1] : 0.f);
+  __syncwarp();
   const int c0 = blockIdx.x * 32;
   const int c = c0 + lane;
   const bool live = c < C;
@@ -102,7 +106,8 @@ __global__ void __launch_bounds__(32)
 #pragma unroll
       for (int i = 0; i < nVec; ++i) {
         const float2 v = win[i * 32];
-        const float a = T.i[i], b = T.q[i];
+        const float4 t4 = tap4[i >> 1];
+        const float a = (i & 1) ? t4.z : t4.x, b = (i & 1) ? t4.w : t4.y;
         const float p1 = a * v.x, p2 = b * v.y, p3 = a * v.y, p4 = b * v.x;
         loI[i & 7] = loI[i & 7] + (p1 - p2);
         loQ[i & 7] = loQ[i & 7] + (p3 + p4);
@@ -117,7 +122,8 @@ __global__ void __launch_bounds__(32)
 #pragma unroll
       for (int i = nVec; i < N; ++i) {
         const float2 v = win[i * 32];
-        const float a = T.i[i], b = T.q[i];
+        const float4 t4 = tap4[i >> 1];
+        const float a = (i & 1) ? t4.z : t4.x, b = (i & 1) ? t4.w : t4.y;
         const float p1 = a * v.x, p2 = b * v.y, p3 = a * v.y, p4 = b * v.x;
         aLoI += (p1 - p2); aLoQ += (p3 + p4); aUpI += (p1 + p2); aUpQ += (p3 - p4);
       }
