@@ -122,3 +122,28 @@ def test_bench_reference_arm_contract():
     r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                         capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"), cwd=root)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_csharp_bindings_match_the_header():
+    """integration/csharp cannot be compiled here (no .NET): at least every P/Invoke it declares must name an entry point
+    of include/qpskcuda.h with the same number of parameters, and the shim must only call bindings that exist."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "qpskcuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"QPSK_API\s+[\w\s\*]+?\b(qpsk_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    native = open(os.path.join(root, "integration", "csharp", "QpskCuda.Native.cs")).read()
+    native = re.sub(r"//[^\n]*", " ", native)
+    bound = {}
+    for m in re.finditer(r"static\s+extern\s+\w+\s+(qpsk_\w+)\s*\(([^;]*?)\)\s*;", native, flags=re.S):
+        args = m.group(2).strip()
+        bound[m.group(1)] = 0 if args == "" else len(args.split(","))
+    assert len(bound) >= 30
+    for name, n in bound.items():
+        assert name in protos, f"{name} is not declared in qpskcuda.h"
+        assert n == protos[name], f"{name}: {n} parameters in C#, {protos[name]} in the header"
+    shim = open(os.path.join(root, "integration", "csharp", "QpskCuda.Shim.cs")).read()
+    used = set(re.findall(r"QpskCuda\.(qpsk_\w+)\s*\(", shim))
+    assert used and used <= set(bound), sorted(used - set(bound))
