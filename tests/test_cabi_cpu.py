@@ -144,6 +144,31 @@ def test_csharp_bindings_match_the_header():
     for name, n in bound.items():
         assert name in protos, f"{name} is not declared in qpskcuda.h"
         assert n == protos[name], f"{name}: {n} parameters in C#, {protos[name]} in the header"
+    # parameter by parameter: the C# type must marshal as the C type (int64_t <-> long, T* <-> T* / out T / in T,
+    # handles <-> IntPtr, handle out-parameters <-> out IntPtr, const char* <-> byte* / string)
+    ok_map = {
+        "int": [("", "int")], "int64_t": [("", "long")], "float": [("", "float")], "double": [("", "double")],
+        "float*": [("", "float*"), ("out", "float"), ("in", "float")], "double*": [("", "double*"), ("out", "double")],
+        "int*": [("", "int*"), ("out", "int")], "int64_t*": [("", "long*"), ("out", "long")],
+        "uint8_t*": [("", "byte*")], "char*": [("", "byte*"), ("", "string?"), ("", "string")], "void*": [("", "IntPtr"), ("", "void*")],
+    }
+    cargs = {}
+    for m in re.finditer(r"QPSK_API\s+[\w\s\*]+?\b(qpsk_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        a = m.group(2).strip()
+        cargs[m.group(1)] = [] if a in ("", "void") else [v.strip() for v in a.split(",")]
+    for m in re.finditer(r"static\s+extern\s+\w+\s+(qpsk_\w+)\s*\(([^;]*?)\)\s*;", native, flags=re.S):
+        for ca, sa in zip(cargs[m.group(1)], [v for v in m.group(2).split(",") if v.strip()]):
+            ct = re.sub(r"\s+", " ", re.sub(r"\bconst\b", "", ca)).strip()
+            ct = re.match(r"(.*?)(\w+)$", ct).group(1).strip().replace(" *", "*")
+            mm = re.match(r"(?:(out|in|ref)\s+)?([\w\?\*]+)\s+\w+$", sa.strip())
+            got = (mm.group(1) or "", mm.group(2))
+            if re.match(r"qpsk_\w+\*\*$", ct):
+                good = got == ("out", "IntPtr")
+            elif re.match(r"qpsk_\w+\*$", ct):
+                good = got == ("", "IntPtr")
+            else:
+                good = got in ok_map.get(ct, [])
+            assert good, f"{m.group(1)}: C `{ca}` against C# `{sa.strip()}`"
     shim = open(os.path.join(root, "integration", "csharp", "QpskCuda.Shim.cs")).read()
     used = set(re.findall(r"QpskCuda\.(qpsk_\w+)\s*\(", shim))
     assert used and used <= set(bound), sorted(used - set(bound))
