@@ -1,13 +1,32 @@
 // integration/csharp/QpskCuda.Shim.cs — the reference's public classes on the hot path with their bodies replaced by
-// calls into libqpskcuda.so.  Same namespaces, class names, constructor and method signatures, defaults and exceptions as
-// Modulation-Simulation/{Models/FIRFilter.cs, Models/RRC-filter.cs, Models/Band-Edge Filter.cs, Models/MuellerMuller.cs,
-// Models/CostasLoopQpsk.cs, QPSKModulator.cs, QPSKDeModulator.cs}; each member cites the line it stands in for.
-// Loop and filter state lives on the device inside the native handle, one handle per object, exactly as the managed
-// objects were one per stream.  HelperFunctions (BitPacker, SaveAsCs16, ...) and RealFIRFilter stay as they are.
-// Not built in this repository: the image has no .NET toolchain.
+// calls into libqpskcuda.so.  Same namespaces, class names, constructor and method signatures, defaults, RETURN VALUES and
+// exceptions as Modulation-Simulation/{Models/FIRFilter.cs, Models/RRC-filter.cs, Models/Band-Edge Filter.cs,
+// Models/MuellerMuller.cs, Models/CostasLoopQpsk.cs, QPSKModulator.cs, QPSKDeModulator.cs}; each member cites the line it
+// stands in for.  The managed argument checks of the reference run BEFORE the native call, in the reference's order, so a
+// caller sees the same exception type and parameter name.  Loop and filter state lives on the device inside the native
+// handle, one handle per object, exactly as the managed objects were one per stream.  HelperFunctions (BitPacker,
+// SaveAsCs16, ...) and RealFIRFilter stay as they are.
+// Not built in this repository: the image has no .NET toolchain.  tests/test_cabi_cpu.py checks every binding against the
+// header and every Process() return expression against the reference's convention.
 using System;
+using System.Runtime.InteropServices;
 using System.Text;
 using QPSK.Native;
+
+namespace QPSK.Native
+{
+    // Owns one native handle.  The reference classes are not IDisposable and existing callers never dispose them, so the
+    // device buffers and CUDA streams behind a handle are released by the SafeHandle's critical finaliser once the managed
+    // object is unreachable; Dispose() on the shim classes is an optional early release.
+    internal sealed class QpskHandle : SafeHandle
+    {
+        readonly Func<IntPtr, int> _destroy;
+        public QpskHandle(IntPtr h, Func<IntPtr, int> destroy) : base(IntPtr.Zero, true) { _destroy = destroy; SetHandle(h); }
+        public override bool IsInvalid => handle == IntPtr.Zero;
+        protected override bool ReleaseHandle() => _destroy(handle) == 0;
+        public IntPtr Ptr => (IsClosed || IsInvalid) ? throw new ObjectDisposedException(nameof(QpskHandle)) : handle;
+    }
+}
 
 namespace QPSK.Models
 {
@@ -24,14 +43,19 @@ namespace QPSK.Models
 
     public sealed unsafe class ComplexFIRFilter : IDisposable
     {
-        readonly IntPtr _h;
+        readonly QpskHandle _o;
+        IntPtr _h => _o.Ptr;
         public readonly float[] taps;                                                // FIRFilter.cs:11
         public ComplexFIRFilter(float[] tapsInterleavedIQ)                         // :29
         {
-            if (tapsInterleavedIQ == null) throw new ArgumentNullException(nameof(tapsInterleavedIQ));
+            if (tapsInterleavedIQ == null) throw new ArgumentNullException(nameof(tapsInterleavedIQ));                                        // :31
+            if ((tapsInterleavedIQ.Length & 1) != 0) throw new ArgumentException("Taps must be interleaved IQ with even length.", nameof(tapsInterleavedIQ));   // :32
+            if (tapsInterleavedIQ.Length == 0) throw new ArgumentException("Taps cannot be empty.", nameof(tapsInterleavedIQ));               // :33
             taps = (float[])tapsInterleavedIQ.Clone();
+            IntPtr h;
             fixed (float* t = tapsInterleavedIQ)
-                QpskCuda.Check(QpskCuda.qpsk_fir_create(t, tapsInterleavedIQ.Length, out _h), nameof(tapsInterleavedIQ));
+                QpskCuda.Check(QpskCuda.qpsk_fir_create(t, tapsInterleavedIQ.Length, out h), nameof(tapsInterleavedIQ));
+            _o = new QpskHandle(h, QpskCuda.qpsk_fir_destroy);
         }
         public void Filter(float inI, float inQ, out float outI, out float outQ)   // :59  one sample = a 2-float span
         {
@@ -39,48 +63,60 @@ namespace QPSK.Models
             io[0] = inI; io[1] = inQ;
             QpskCuda.Check(QpskCuda.qpsk_fir_filter(_h, io, io + 2, 2, 2));
             outI = io[2]; outQ = io[3];
+            GC.KeepAlive(this);
         }
         public void Filter(ReadOnlySpan<float> iqIn, Span<float> iqOut)            // :80  streaming, delay line on the device
         {
+            if ((iqIn.Length & 1) != 0) throw new ArgumentException("Input must be interleaved IQ with even length.", nameof(iqIn));   // :82
+            if (iqOut.Length < iqIn.Length) throw new ArgumentException("Output span is too small.", nameof(iqOut));                  // :83
             fixed (float* i = iqIn) fixed (float* o = iqOut)
                 QpskCuda.Check(QpskCuda.qpsk_fir_filter(_h, i, o, iqIn.Length, iqOut.Length), nameof(iqIn));
+            GC.KeepAlive(this);
         }
         public float[] fftFilter(float[] iqData)                                   // :96  stateless, offset N-1
         {
-            if (iqData == null) throw new ArgumentNullException(nameof(iqData));
-            var y = new float[(iqData.Length & 1) == 0 ? iqData.Length : 0];
+            if (iqData == null) throw new ArgumentNullException(nameof(iqData));                                                       // :98
+            if ((iqData.Length & 1) != 0) throw new ArgumentException("Data must be interleaved IQ with even length.", nameof(iqData));   // :99
+            if (iqData.Length == 0) return Array.Empty<float>();                                                                      // :100
+            var y = new float[iqData.Length];
             fixed (float* i = iqData) fixed (float* o = y)
                 QpskCuda.Check(QpskCuda.qpsk_fir_fft_filter(_h, i, o, iqData.Length), nameof(iqData));
+            GC.KeepAlive(this);
             return y;
         }
-        public void Dispose() => QpskCuda.qpsk_fir_destroy(_h);
+        public void Dispose() => _o.Dispose();
     }
 
     public sealed unsafe class FLLBandEdgeFilter : IDisposable
     {
-        readonly IntPtr _h;
+        readonly QpskHandle _o;
+        IntPtr _h => _o.Ptr;
         public float sps, rolloff, bandwidth;                                        // Band-Edge Filter.cs:19-22
         public int filterSize;
         public float phase                                                           // :25 (a public field upstream)
         {
-            get { QpskCuda.Check(QpskCuda.qpsk_fll_get_state(_h, out float p, out _)); return p; }
-            set { QpskCuda.Check(QpskCuda.qpsk_fll_get_state(_h, out _, out float f)); QpskCuda.Check(QpskCuda.qpsk_fll_set_state(_h, in value, in f)); }
+            get { QpskCuda.Check(QpskCuda.qpsk_fll_get_state(_h, out float p, out _)); GC.KeepAlive(this); return p; }
+            set { QpskCuda.Check(QpskCuda.qpsk_fll_get_state(_h, out _, out float f)); QpskCuda.Check(QpskCuda.qpsk_fll_set_state(_h, in value, in f)); GC.KeepAlive(this); }
         }
         public float freq                                                            // :26
         {
-            get { QpskCuda.Check(QpskCuda.qpsk_fll_get_state(_h, out _, out float f)); return f; }
-            set { QpskCuda.Check(QpskCuda.qpsk_fll_get_state(_h, out float p, out _)); QpskCuda.Check(QpskCuda.qpsk_fll_set_state(_h, in p, in value)); }
+            get { QpskCuda.Check(QpskCuda.qpsk_fll_get_state(_h, out _, out float f)); GC.KeepAlive(this); return f; }
+            set { QpskCuda.Check(QpskCuda.qpsk_fll_get_state(_h, out float p, out _)); QpskCuda.Check(QpskCuda.qpsk_fll_set_state(_h, in p, in value)); GC.KeepAlive(this); }
         }
         public FLLBandEdgeFilter(float sps, float rolloff, int filterSize, float bandwidth)   // :40 (range checks :42-45 -> status -3)
         {
             this.sps = sps; this.rolloff = rolloff; this.filterSize = filterSize; this.bandwidth = bandwidth;
-            QpskCuda.Check(QpskCuda.qpsk_fll_create(sps, rolloff, filterSize, bandwidth, out _h));
+            QpskCuda.Check(QpskCuda.qpsk_fll_create(sps, rolloff, filterSize, bandwidth, out IntPtr h));
+            _o = new QpskHandle(h, QpskCuda.qpsk_fll_destroy);
         }
         public int Process(ReadOnlySpan<float> inputIQ, Span<float> outputIQ)       // :64
         {
+            if ((inputIQ.Length & 1) != 0) throw new ArgumentException("Input must be interleaved IQ with even length.", nameof(inputIQ));   // :66
+            if (outputIQ.Length < inputIQ.Length) throw new ArgumentException("Output span is too small.", nameof(outputIQ));              // :68
             fixed (float* i = inputIQ) fixed (float* o = outputIQ)
                 QpskCuda.Check(QpskCuda.qpsk_fll_process(_h, i, o, inputIQ.Length, outputIQ.Length), nameof(inputIQ));
-            return inputIQ.Length;
+            GC.KeepAlive(this);
+            return inputIQ.Length >> 1;                                              // complex samples processed (:71, :86)
         }
         public float[] Process(float[] inputIQ)                                      // :90
         {
@@ -95,45 +131,55 @@ namespace QPSK.Models
             io[0] = inI; io[1] = inQ;
             QpskCuda.Check(QpskCuda.qpsk_fll_process(_h, io, io + 2, 2, 2));
             outI = io[2]; outQ = io[3];
+            GC.KeepAlive(this);
         }
-        public void Dispose() => QpskCuda.qpsk_fll_destroy(_h);
+        public void Dispose() => _o.Dispose();
     }
 
     public sealed unsafe class MuellerMuller : IDisposable
     {
-        readonly IntPtr _h;
+        readonly QpskHandle _o;
+        IntPtr _h => _o.Ptr;
         public MuellerMuller(double samplesPerSymbol, double kp, double ki)          // MuellerMuller.cs:38
         {
-            QpskCuda.Check(QpskCuda.qpsk_mm_create(samplesPerSymbol, kp, ki, out _h));
+            QpskCuda.Check(QpskCuda.qpsk_mm_create(samplesPerSymbol, kp, ki, out IntPtr h));
+            _o = new QpskHandle(h, QpskCuda.qpsk_mm_destroy);
         }
         public int Process(ReadOnlySpan<float> incomingMfSamplesIQ, Span<float> outputSymbolsIQ)   // :52
         {
+            if ((incomingMfSamplesIQ.Length & 1) != 0)
+                throw new ArgumentException("Input must be interleaved IQ with even length.", nameof(incomingMfSamplesIQ));   // :54-55
             int nSym;
             fixed (float* i = incomingMfSamplesIQ) fixed (float* o = outputSymbolsIQ)
                 QpskCuda.Check(QpskCuda.qpsk_mm_process(_h, i, incomingMfSamplesIQ.Length, o, outputSymbolsIQ.Length, out nSym),
                                nameof(incomingMfSamplesIQ));
-            return 2 * nSym;      // the native call counts symbols, the reference returns floats written (:135)
+            GC.KeepAlive(this);
+            return nSym;          // outSymbols: complex symbols written (:135); QPSKDeModulator.cs:364-375 loops k < nSymbols over it
         }
         public float[] Process(float[] incomingMfSamplesIQ)                          // :141
         {
             if (incomingMfSamplesIQ == null) throw new ArgumentNullException(nameof(incomingMfSamplesIQ));
             if ((incomingMfSamplesIQ.Length & 1) != 0)
                 throw new ArgumentException("Input must be interleaved IQ with even length.", nameof(incomingMfSamplesIQ));
-            var tmp = new float[incomingMfSamplesIQ.Length];
-            int n = Process(incomingMfSamplesIQ.AsSpan(), tmp.AsSpan());
-            var y = new float[n];
-            Array.Copy(tmp, y, n);
+            int maxSymbols = incomingMfSamplesIQ.Length >> 1;                        // :148
+            var tmp = new float[maxSymbols << 1];                                    // :149
+            int n = Process(incomingMfSamplesIQ.AsSpan(), tmp.AsSpan());             // :151
+            if (n == maxSymbols) return tmp;                                         // :152
+            var y = new float[n << 1];                                               // :154
+            Array.Copy(tmp, y, y.Length);
             return y;
         }
-        public void Dispose() => QpskCuda.qpsk_mm_destroy(_h);
+        public void Dispose() => _o.Dispose();
     }
 
     public sealed unsafe class CostasLoopQpsk : IDisposable
     {
-        readonly IntPtr _h;
+        readonly QpskHandle _o;
+        IntPtr _h => _o.Ptr;
         public CostasLoopQpsk(double sampleRate, double loopBandwidthHz, double damping = 0.707)   // CostasLoopQpsk.cs:29
         {
-            QpskCuda.Check(QpskCuda.qpsk_costas_create(sampleRate, loopBandwidthHz, damping, out _h));
+            QpskCuda.Check(QpskCuda.qpsk_costas_create(sampleRate, loopBandwidthHz, damping, out IntPtr h));
+            _o = new QpskHandle(h, QpskCuda.qpsk_costas_destroy);
         }
         public static void GetSign(float i, float q, out float di, out float dq)    // :52 (pure host helper, unchanged)
         {
@@ -146,12 +192,16 @@ namespace QPSK.Models
             io[0] = inI; io[1] = inQ;
             QpskCuda.Check(QpskCuda.qpsk_costas_process(_h, io, io + 2, 2, 2));
             outI = io[2]; outQ = io[3];
+            GC.KeepAlive(this);
         }
         public int Process(ReadOnlySpan<float> iqIn, Span<float> iqOut)             // :98
         {
+            if ((iqIn.Length & 1) != 0) throw new ArgumentException("Input must be interleaved IQ with even length.", nameof(iqIn));   // :100
+            if (iqOut.Length < iqIn.Length) throw new ArgumentException("Output span is too small.", nameof(iqOut));                  // :102
             fixed (float* i = iqIn) fixed (float* o = iqOut)
                 QpskCuda.Check(QpskCuda.qpsk_costas_process(_h, i, o, iqIn.Length, iqOut.Length), nameof(iqIn));
-            return iqIn.Length;
+            GC.KeepAlive(this);
+            return iqIn.Length >> 1;                                                 // complex samples processed (:105, :113)
         }
         public float[] Process(float[] iqIn)                                         // :119
         {
@@ -163,9 +213,10 @@ namespace QPSK.Models
         public (double theta, double freq) GetState()                                // :130
         {
             QpskCuda.Check(QpskCuda.qpsk_costas_get_state(_h, out double t, out double f));
+            GC.KeepAlive(this);
             return (t, f);
         }
-        public void Dispose() => QpskCuda.qpsk_costas_destroy(_h);
+        public void Dispose() => _o.Dispose();
     }
 }
 
@@ -173,24 +224,29 @@ namespace QPSK
 {
     public sealed unsafe class QPSKModulator : IDisposable
     {
-        readonly IntPtr _h;
+        readonly QpskHandle _o;
+        IntPtr _h => _o.Ptr;
         public long baudRate;                                                        // QPSKModulator.cs:34
         public QPSKModulator(int SampleRate, int SymbolRate, double RrcAlpha = 0.9, int rrcSpan = 6,
                              bool differentialEncoding = true, string? tsc = null)   // :18
         {
             baudRate = 2L * SymbolRate / 8L;
-            QpskCuda.Check(QpskCuda.qpsk_mod_create(SampleRate, SymbolRate, RrcAlpha, rrcSpan, differentialEncoding ? 1 : 0, tsc, out _h));
+            QpskCuda.Check(QpskCuda.qpsk_mod_create(SampleRate, SymbolRate, RrcAlpha, rrcSpan, differentialEncoding ? 1 : 0, tsc, out IntPtr h));
+            _o = new QpskHandle(h, QpskCuda.qpsk_mod_destroy);
         }
         public double[] getCoeef()                                                   // :32
         {
             QpskCuda.Check(QpskCuda.qpsk_mod_taps(_h, null, 0, out int n));
             var h = new double[n];
             fixed (double* p = h) QpskCuda.Check(QpskCuda.qpsk_mod_taps(_h, p, n, out n));
+            GC.KeepAlive(this);
             return h;
         }
         public float[] ModulateBytes(ReadOnlySpan<byte> payload, ReadOnlySpan<byte> startMarker, ReadOnlySpan<byte> endMarker,
                                      bool pulseShaping = true)                      // :54  framing START|payload|END on the device
         {
+            if (startMarker.Length == 0) throw new ArgumentException("startMarker cannot be empty.", nameof(startMarker));   // :60
+            if (endMarker.Length == 0) throw new ArgumentException("endMarker cannot be empty.", nameof(endMarker));         // :61
             int ps = pulseShaping ? 1 : 0;
             fixed (byte* p = payload) fixed (byte* s = startMarker) fixed (byte* e = endMarker)
             {
@@ -201,15 +257,17 @@ namespace QPSK
                     fixed (float* o = y)
                         QpskCuda.Check(QpskCuda.qpsk_mod_modulate_bytes(_h, p, payload.Length, s, startMarker.Length, e, endMarker.Length,
                                                                         ps, o, n, out n));
+                GC.KeepAlive(this);
                 return y;
             }
         }
         public float[] ModulateTextUtf8(string text, string startMarker = "\u0002", string endMarker = "\u0003",
                                         bool pulseShaping = true, Encoding? encoding = null)   // :74  stays managed + ModulateBytes
         {
+            if (text == null) throw new ArgumentNullException(nameof(text));         // :81
             encoding ??= Encoding.UTF8;
-            return ModulateBytes(encoding.GetBytes(text ?? string.Empty), encoding.GetBytes(startMarker ?? string.Empty),
-                                 encoding.GetBytes(endMarker ?? string.Empty), pulseShaping);
+            // GetBytes(null) throws ArgumentNullException, as upstream (:85-86)
+            return ModulateBytes(encoding.GetBytes(text), encoding.GetBytes(startMarker), encoding.GetBytes(endMarker), pulseShaping);
         }
         public float[] Modulate(string data, bool pulseShaping = true)              // :104
         {
@@ -223,33 +281,40 @@ namespace QPSK
                 if (n > 0)
                     fixed (float* o = y)
                         QpskCuda.Check(QpskCuda.qpsk_mod_modulate_bits(_h, b, bits.Length, ps, o, n, out n));
+                GC.KeepAlive(this);
                 return y;
             }
         }
-        public void Dispose() => QpskCuda.qpsk_mod_destroy(_h);
+        public void Dispose() => _o.Dispose();
     }
 
     public sealed unsafe class QPSKDeModulator : IDisposable
     {
-        readonly IntPtr _h;
+        readonly QpskHandle _o;
+        IntPtr _h => _o.Ptr;
         public QPSKDeModulator(int SampleRate, int SymbolRate, float RrcAlpha = 0.9f, int rrcSpan = 6,
                                double SymbolSyncBandwith = 0.0001, double CostasLoopBandwith = 120, double CFOLoopBandwith = 0.0001f,
                                bool differentialEncoding = true, string? tsc = null)   // QPSKDeModulator.cs:11
         {
             // use_fll = 0: the fll.Process call is commented out upstream (:359, :435); max_frame_bytes = 0: library default
             QpskCuda.Check(QpskCuda.qpsk_demod_create(SampleRate, SymbolRate, RrcAlpha, rrcSpan, SymbolSyncBandwith, CostasLoopBandwith,
-                                                      CFOLoopBandwith, differentialEncoding ? 1 : 0, tsc, 0, 0, out _h));
+                                                      CFOLoopBandwith, differentialEncoding ? 1 : 0, tsc, 0, 0, out IntPtr h));
+            _o = new QpskHandle(h, QpskCuda.qpsk_demod_destroy);
         }
         public byte[] DeModulateBytes(ReadOnlySpan<float> samplesIQ, ReadOnlySpan<byte> startMarker, ReadOnlySpan<byte> endMarker)   // :169
         {
-            if (startMarker.Length == 0) throw new ArgumentException("startMarker cannot be empty.", nameof(startMarker));
-            if (endMarker.Length == 0) throw new ArgumentException("endMarker cannot be empty.", nameof(endMarker));
+            if (startMarker.Length == 0) throw new ArgumentException("startMarker cannot be empty.", nameof(startMarker));   // :174
+            if (endMarker.Length == 0) throw new ArgumentException("endMarker cannot be empty.", nameof(endMarker));         // :175
+            if ((samplesIQ.Length & 1) != 0)
+                throw new ArgumentException("Samples must be interleaved IQ with even length.", nameof(samplesIQ));         // :347-348 via :177
             // a frame may have been accumulating on the device over earlier calls: size for the library's frame bound (1 MiB)
             var buf = new byte[Math.Max(samplesIQ.Length / 8 + 64, 1 << 20)];
             fixed (float* i = samplesIQ) fixed (byte* s = startMarker) fixed (byte* e = endMarker) fixed (byte* o = buf)
             {
                 QpskCuda.Check(QpskCuda.qpsk_demod_bytes(_h, i, samplesIQ.Length, s, startMarker.Length, e, endMarker.Length, o, buf.Length,
                                                          out long n), nameof(samplesIQ));
+                GC.KeepAlive(this);
+                if (n == 0) return Array.Empty<byte>();                              // :180, :258
                 var payload = new byte[n];
                 Array.Copy(buf, payload, n);
                 return payload;
@@ -262,27 +327,38 @@ namespace QPSK
             byte[] p = DeModulateBytes(samplesIQ, encoding.GetBytes(startMarker), encoding.GetBytes(endMarker));
             return p.Length == 0 ? string.Empty : encoding.GetString(p);
         }
-        public string DeModulate(float[] SamplesIQ) => DeModulate(SamplesIQ.AsSpan());   // :339
+        public string DeModulate(float[] SamplesIQ)                                  // :339
+        {
+            if (SamplesIQ == null) throw new ArgumentNullException(nameof(SamplesIQ));   // :341
+            return DeModulate(SamplesIQ.AsSpan());
+        }
         public string DeModulate(ReadOnlySpan<float> SamplesIQ)                      // :345  '0'/'1' chars, TSC already stripped
         {
+            if ((SamplesIQ.Length & 1) != 0)
+                throw new ArgumentException("Samples must be interleaved IQ with even length.", nameof(SamplesIQ));   // :347-348
+            if (SamplesIQ.Length == 0) return "";                                    // :350-351
             var buf = new byte[Math.Max(SamplesIQ.Length, 16)];
             fixed (float* i = SamplesIQ) fixed (byte* o = buf)
             {
                 QpskCuda.Check(QpskCuda.qpsk_demod_bits(_h, i, SamplesIQ.Length, o, buf.Length, out long n), nameof(SamplesIQ));
+                GC.KeepAlive(this);
                 return Encoding.ASCII.GetString(buf, 0, (int)n);
             }
         }
         public float[] deModulateConstellation(ReadOnlySpan<float> SamplesIQ)        // :427
         {
+            if ((SamplesIQ.Length & 1) != 0)
+                throw new ArgumentException("Samples must be interleaved IQ with even length.", nameof(SamplesIQ));   // :430
             var buf = new float[Math.Max(SamplesIQ.Length, 2)];
             fixed (float* i = SamplesIQ) fixed (float* o = buf)
             {
                 QpskCuda.Check(QpskCuda.qpsk_demod_constellation(_h, i, SamplesIQ.Length, o, buf.Length, out long nSym), nameof(SamplesIQ));
-                var y = new float[2 * nSym];
-                Array.Copy(buf, y, 2 * nSym);
+                GC.KeepAlive(this);
+                var y = new float[nSym << 1];                                        // :446
+                Array.Copy(buf, y, y.Length);
                 return y;
             }
         }
-        public void Dispose() => QpskCuda.qpsk_demod_destroy(_h);
+        public void Dispose() => _o.Dispose();
     }
 }

@@ -232,13 +232,15 @@ class FLLBandEdgeFilter(_Handle):
     def taps(self):
         return fll_design(*self._design)
 
-    def Process(self, inputIQ, out_len=None) -> np.ndarray:
+    def Process(self, inputIQ, outputIQ=None, out_len=None):
+        """Process(float[]) :90-96 -> the output array; with `outputIQ` given it is Process(ReadOnlySpan<float>,
+        Span<float>) :64-87: writes into the caller's array and returns the number of COMPLEX samples processed (:71, :86)."""
         x = _f32(inputIQ)
         n = x.shape[-1] if x.ndim == 2 else x.size
-        y = np.empty(x.shape if out_len is None else out_len, np.float32)
+        y = outputIQ if outputIQ is not None else np.empty(x.shape if out_len is None else out_len, np.float32)
         cap = y.shape[-1] if y.ndim == 2 else y.size
         check(lib().qpsk_fll_process(self._h, _ptr(x), _ptr(y), n, cap))
-        return y
+        return (n >> 1) if outputIQ is not None else y
 
     def process_dev(self, d_in, d_out, n_floats, in_stride=0, out_stride=0, stream=0):
         check(lib().qpsk_fll_process_dev(self._h, d_in, d_out, n_floats, in_stride or n_floats, out_stride or n_floats, stream))
@@ -284,15 +286,23 @@ class MuellerMuller(_Handle):
         self.channels = channels
         check(lib().qpsk_mm_create_batch(samplesPerSymbol, kp, ki, channels, C.byref(self._h)))
 
-    def Process(self, incomingMfSamplesIQ, cap_floats=None):
-        """Returns the symbols (interleaved IQ).  Batch handles: list of per-channel arrays."""
+    def Process(self, incomingMfSamplesIQ, outputSymbolsIQ=None, cap_floats=None):
+        """Process(float[]) :141-157 -> the symbols (interleaved IQ, `n << 1` floats; batch handles: list of per-channel
+        arrays).  With `outputSymbolsIQ` given it is Process(ReadOnlySpan<float>, Span<float>) :52-136: writes into the
+        caller's array ([channels][cap] for batch handles) and returns outSymbols, the number of complex SYMBOLS written
+        (:135; an int for one channel, an int array per channel for batch handles)."""
         x = _f32(incomingMfSamplesIQ)
         n = x.shape[-1] if x.ndim == 2 else x.size
+        ns = np.zeros(self.channels, np.int32)
+        if outputSymbolsIQ is not None:
+            y = outputSymbolsIQ
+            cap = y.shape[-1] if y.ndim == 2 else y.size
+            check(lib().qpsk_mm_process(self._h, _ptr(x), n, _ptr(y), cap, ns.ctypes.data_as(N.i32p)))
+            return int(ns[0]) if self.channels == 1 else ns
         cap = n if cap_floats is None else cap_floats
         y = np.zeros((self.channels, max(cap, 0)), np.float32)
-        ns = np.zeros(self.channels, np.int32)
         check(lib().qpsk_mm_process(self._h, _ptr(x), n, _ptr(y), cap, ns.ctypes.data_as(N.i32p)))
-        outs = [y[c, : 2 * ns[c]].copy() for c in range(self.channels)]
+        outs = [y[c, : int(ns[c]) << 1].copy() for c in range(self.channels)]
         return outs[0] if self.channels == 1 else outs
 
     @property
@@ -324,13 +334,15 @@ class CostasLoopQpsk(_Handle):
         self.channels = channels
         check(lib().qpsk_costas_create_batch(sampleRate, loopBandwidthHz, damping, channels, C.byref(self._h)))
 
-    def Process(self, iqIn, out_len=None) -> np.ndarray:
+    def Process(self, iqIn, iqOut=None, out_len=None):
+        """Process(float[]) :119-125 -> the output array; with `iqOut` given it is Process(ReadOnlySpan<float>, Span<float>)
+        :98-114: writes into the caller's array and returns the number of COMPLEX samples processed (:105, :113)."""
         x = _f32(iqIn)
         n = x.shape[-1] if x.ndim == 2 else x.size
-        y = np.empty(x.shape if out_len is None else out_len, np.float32)
+        y = iqOut if iqOut is not None else np.empty(x.shape if out_len is None else out_len, np.float32)
         cap = y.shape[-1] if y.ndim == 2 else y.size
         check(lib().qpsk_costas_process(self._h, _ptr(x), _ptr(y), n, cap))
-        return y
+        return (n >> 1) if iqOut is not None else y
 
     @staticmethod
     def GetSign(i, q):

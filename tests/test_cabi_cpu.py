@@ -172,3 +172,129 @@ def test_csharp_bindings_match_the_header():
     shim = open(os.path.join(root, "integration", "csharp", "QpskCuda.Shim.cs")).read()
     used = set(re.findall(r"QpskCuda\.(qpsk_\w+)\s*\(", shim))
     assert used and used <= set(bound), sorted(used - set(bound))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# what the C# shim RETURNS (round-1 review: three span overloads returned float counts where the reference returns complex
+# counts).  The shim cannot be compiled here, so its method bodies are parsed and every value-returning member on the path
+# is checked against (i) a table of the reference's conventions and (ii), when /root/reference is present, the reference's
+# own source text of the same member.
+# ---------------------------------------------------------------------------------------------------------------------
+def _cs_strip(text):
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    return re.sub(r"//[^\n]*", " ", text)
+
+
+def _cs_method_body(text, cls, sig_regex):
+    """Body (between the outer braces) of the first member of class `cls` whose signature matches `sig_regex`."""
+    m = re.search(r"\bclass\s+" + re.escape(cls) + r"\b", text)
+    assert m, cls
+    i = text.index("{", m.end())
+    depth, j = 0, i
+    while True:                      # class extent
+        if text[j] == "{":
+            depth += 1
+        elif text[j] == "}":
+            depth -= 1
+            if depth == 0:
+                break
+        j += 1
+    body = text[i:j]
+    m = re.search(sig_regex, body)
+    assert m, (cls, sig_regex)
+    i = body.index("{", m.end())
+    depth, j = 0, i
+    while True:
+        if body[j] == "{":
+            depth += 1
+        elif body[j] == "}":
+            depth -= 1
+            if depth == 0:
+                break
+        j += 1
+    return body[i + 1:j]
+
+
+def _cs_last_return(body):
+    r = re.findall(r"\breturn\s+([^;]+);", body)
+    assert r, body
+    return re.sub(r"\s+", "", r[-1])
+
+
+def _cs_resolve(body, expr):
+    """`return n;` -> the initialiser of `int n = ...;` in the same body (one level)."""
+    m = re.search(r"\bint\s+" + re.escape(expr) + r"\s*=\s*([^;]+);", body)
+    return re.sub(r"\s+", "", m.group(1)) if m else expr
+
+
+SPAN2 = r"\(\s*ReadOnlySpan<float>\s+(\w+)\s*,\s*Span<float>\s+(\w+)\s*\)"
+# (class, reference file, signature, expected return as a function of the first parameter name `x`)
+RETURNS = [
+    ("FLLBandEdgeFilter", "Models/Band-Edge Filter.cs", r"public\s+int\s+Process" + SPAN2, "{x}.Length>>1"),
+    ("CostasLoopQpsk", "Models/CostasLoopQpsk.cs", r"public\s+int\s+Process" + SPAN2, "{x}.Length>>1"),
+    ("MuellerMuller", "Models/MuellerMuller.cs", r"public\s+int\s+Process" + SPAN2, "<symbols>"),
+]
+
+
+def test_csharp_shim_return_values_follow_the_reference():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = _cs_strip(open(os.path.join(root, "integration", "csharp", "QpskCuda.Shim.cs")).read())
+    ref_root = "/root/reference/Modulation-Simulation"
+    for cls, ref_file, sig, want in RETURNS:
+        body = _cs_method_body(shim, cls, sig)
+        x = re.search(sig, shim[shim.index("class " + cls):]).group(1)
+        got = _cs_resolve(body, _cs_last_return(body))
+        if want == "<symbols>":
+            # the count the native call reports in its `out int nSym` (complex symbols), unscaled
+            m = re.search(r"qpsk_mm_process\s*\([^;]*out\s+(\w+)\s*\)", body)
+            assert m and got == m.group(1), (cls, got)
+        else:
+            assert got == want.format(x=x), (cls, got)
+        if os.path.isdir(ref_root):
+            ref = _cs_strip(open(os.path.join(ref_root, ref_file), errors="replace").read())
+            rbody = _cs_method_body(ref, cls, sig)
+            rx = re.search(sig, ref[ref.index("class " + cls):]).group(1)
+            rgot = _cs_last_return(rbody) if want == "<symbols>" else _cs_resolve(rbody, _cs_last_return(rbody))
+            if want == "<symbols>":
+                assert rgot == "outSymbols" and re.search(r"outSymbols\+\+", re.sub(r"\s+", "", rbody)), rgot
+            else:
+                assert rgot == want.format(x=rx), (cls, rgot)
+    # allocating overloads: array sizes in floats = 2 x complex count (MuellerMuller.cs:148-156, QPSKDeModulator.cs:446)
+    mm = re.sub(r"\s+", "", _cs_method_body(shim, "MuellerMuller", r"public\s+float\[\]\s+Process\s*\(\s*float\[\]"))
+    assert "newfloat[maxSymbols<<1]" in mm and "newfloat[n<<1]" in mm and "if(n==maxSymbols)returntmp;" in mm
+    con = re.sub(r"\s+", "", _cs_method_body(shim, "QPSKDeModulator", r"public\s+float\[\]\s+deModulateConstellation"))
+    assert "newfloat[nSym<<1]" in con
+    if os.path.isdir(ref_root):
+        rmm = re.sub(r"\s+", "", _cs_method_body(_cs_strip(open(os.path.join(ref_root, "Models/MuellerMuller.cs")).read()),
+                                                 "MuellerMuller", r"public\s+float\[\]\s+Process\s*\(\s*float\[\]"))
+        assert "newfloat[maxSymbols<<1]" in rmm and "newfloat[n<<1]" in rmm
+    # the reference's callers use the MM count as a SYMBOL count: the demodulator loops k < nSymbols over 2-float steps
+    # (QPSKDeModulator.cs:364-375); a shim returning floats would make them read twice too far
+    if os.path.isdir(ref_root):
+        dem = re.sub(r"\s+", "", _cs_strip(open(os.path.join(ref_root, "QPSKDeModulator.cs")).read()))
+        assert "intnSymbols=symbolSync.Process(" in dem and "k<nSymbols" in dem
+
+
+def test_csharp_shim_owns_handles_safely_and_checks_arguments_first():
+    """handles must not leak when callers never Dispose (the reference classes are not IDisposable), and the
+    reference's managed argument checks must run ahead of the native call with the reference's exception types."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = _cs_strip(open(os.path.join(root, "integration", "csharp", "QpskCuda.Shim.cs")).read())
+    assert re.search(r"class\s+QpskHandle\s*:\s*SafeHandle", shim) and "ReleaseHandle()" in shim
+    for cls, destroy in [("ComplexFIRFilter", "qpsk_fir_destroy"), ("FLLBandEdgeFilter", "qpsk_fll_destroy"),
+                         ("MuellerMuller", "qpsk_mm_destroy"), ("CostasLoopQpsk", "qpsk_costas_destroy"),
+                         ("QPSKModulator", "qpsk_mod_destroy"), ("QPSKDeModulator", "qpsk_demod_destroy")]:
+        seg = shim[shim.index("class " + cls):]
+        seg = seg[:seg.index("public void Dispose()") + 60]
+        assert "new QpskHandle(h, QpskCuda." + destroy + ")" in seg, cls
+        assert "readonly IntPtr" not in seg, cls
+    ctor = _cs_method_body(shim, "ComplexFIRFilter", r"public\s+ComplexFIRFilter\s*\(")
+    flat = re.sub(r"\s+", "", ctor)
+    # FIRFilter.cs:31-33: null -> ArgumentNullException; odd or EMPTY -> ArgumentException, before qpsk_fir_create
+    assert flat.index("thrownewArgumentNullException") < flat.index("Length&1") < flat.index("Length==0") < flat.index("qpsk_fir_create")
+    assert flat.count("thrownewArgumentException(") == 2
+    mod = re.sub(r"\s+", "", _cs_method_body(shim, "QPSKModulator", r"public\s+float\[\]\s+ModulateTextUtf8"))
+    assert mod.index("if(text==null)thrownewArgumentNullException(nameof(text))") < mod.index("ModulateBytes(")   # QPSKModulator.cs:81
+    for cls, name in [("QPSKModulator", "ModulateBytes"), ("QPSKDeModulator", "DeModulateBytes")]:
+        b = re.sub(r"\s+", "", _cs_method_body(shim, cls, r"public\s+\w+\[\]\s+" + name))
+        assert b.index('startMarker.Length==0') < b.index('endMarker.Length==0') < b.index("QpskCuda.qpsk_"), (cls, name)
