@@ -185,7 +185,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_all) / len(t_all), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "fir_sweep taps{33,65,129,257} (bounded sample per step: cores x 2^22 samples per tap count)"},
+        "config": {"workload": "fir_sweep taps{33,65,129,257} (bounded sample per step: cores x 2^22 samples per tap count)",
+                   "same_config": False,
+                   "sample_note": "same filters, same input distribution and the same metric as the GPU arm, on a bounded sample: one "
+                                  "independent stream of 2^22 samples per host core and tap count instead of one 2^28-sample stream "
+                                  "(throughput of this per-sample loop does not depend on the stream length).  All host cores are "
+                                  "used; the reference library itself is single-threaded (cpu_baseline.single_thread_value)"},
         "cpu_baseline": b,
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -203,6 +208,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-chain", action="store_true")
+    ap.add_argument("--no-scaling-legs", action="store_true", help="skip the 16384-channel strong / saturated chain legs")
+    ap.add_argument("--channels-total", type=int, default=16384, help="BASELINE.json configs[3]: size of the fixed channel set")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -211,7 +218,8 @@ def main():
     import torch
     import torch.distributed as dist
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("QPSK_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+    # NCCL_DEBUG / NCCL_DEBUG_FILE are left exactly as the launcher set them (the driver reads the communicator's rank
+    # count from that log); the JSON line is printed last, after the process group is gone
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,6 +234,20 @@ def main():
         dist.barrier()
     import qpsk_modulator_demodulator_b200 as Q
     Q.set_device(local)
+    build_id = Q._native.build_id()          # lib() already refused a library that is not the build of this tree
+    # the library's own NCCL communicator (qpsk_comm_*): what gathers the BER counters; its id travels over torch's store
+    comm = None
+    if world > 1:
+        from qpsk_modulator_demodulator_b200 import shard
+
+        def exchange(ident):
+            t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if ident is not None:
+                t.copy_(torch.frombuffer(bytearray(ident), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().numpy().tobytes())
+
+        comm = shard.CounterComm(world, rank, exchange)
 
     n = 1 << args.log2_samples
     # an explicit (non-default) stream: a NULL stream handle means "the handle's own stream" in the C ABI,
@@ -277,6 +299,7 @@ def main():
     barrier()
     launches = Q.launch_count()
     ms = e0.elapsed_time(e1)
+    kernels = {nt: f.last_kernel() for nt, f in filters}     # what the library actually launched for each tap count
     clk = clocks.stop() if rank == 0 else None
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -290,7 +313,7 @@ def main():
         gbs = 16.0 * n / (t * 1e-3) / 1e9
         tf = 4.0 * nt * n / (t * 1e-3) / 1e12
         bound = "hbm" if (16.0 * n / (hbm_peak * 1e9)) >= (4.0 * nt * n / (fma_peak * 1e12)) else "fma"
-        roofs.append({"taps": nt, "ms": t, "msamples_s": n / (t * 1e-3) / 1e6, "bound": bound,
+        roofs.append({"taps": nt, "kernel": kernels[nt], "ms": t, "msamples_s": n / (t * 1e-3) / 1e6, "bound": bound,
                       "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "fma_tflops": tf, "fma_frac": tf / fma_peak,
                       "frac": (gbs / hbm_peak) if bound == "hbm" else (tf / fma_peak)})
     tr = ncu_traffic()
@@ -303,7 +326,7 @@ def main():
     dom = max(roofs, key=lambda r: r["ms"])
     hbm_dom = max((r for r in roofs if r["bound"] == "hbm"), key=lambda r: r["ms"], default=None)
     roofline = {
-        "kernel": "fir_tma_kernel<R=10,NT=256,real taps>", "taps": dom["taps"], "bound": dom["bound"],
+        "kernel": dom["kernel"], "taps": dom["taps"], "bound": dom["bound"],
         "achieved": dom["hbm_gbs"] if dom["bound"] == "hbm" else dom["fma_tflops"],
         "peak": hbm_peak if dom["bound"] == "hbm" else fma_peak,
         "unit": "GB/s" if dom["bound"] == "hbm" else "TFLOP/s",
@@ -368,10 +391,31 @@ def main():
         torch.cuda.empty_cache()
         k = max(1, min(args.steps, 10))
         cpu_legs = rank == 0 and world == 1 and not args.no_cpu
-        chain = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=False, hbm_peak=hbm_peak,
-                                      cpu=cpu_legs)
-        chain_fll = bench_chain.run_chain(Q, torch, d, world, rank, stream, steps=k, warmup=3, use_fll=True, hbm_peak=hbm_peak,
-                                          cpu=cpu_legs)
+        # config 3 / config 4's per-GPU share: 2048 channels per GPU (weak: 16384 channels at N = 8).  At N = 1 every
+        # channel is replayed through the oracle; at N > 1, 128 channels per rank.
+        par = None if world == 1 else 128
+        common = dict(steps=k, warmup=3, hbm_peak=hbm_peak, comm=comm)
+        chain = bench_chain.run_chain(Q, torch, d, world, rank, stream, use_fll=False, cpu=cpu_legs, parity_channels=par,
+                                      label="weak: 2048 channels per GPU", **common)
+        chain_fll = bench_chain.run_chain(Q, torch, d, world, rank, stream, use_fll=True, cpu=cpu_legs, parity_channels=par,
+                                          label="weak: 2048 channels per GPU", **common)
+        # config 4 proper: the FIXED 16384-channel set sharded over the GPUs (strong scaling: 16384 / N per GPU), and the
+        # saturated weak case (16384 channels on every GPU).  At N = 1 the two coincide.
+        scaling_legs = {}
+        if not args.no_scaling_legs:
+            tot = args.channels_total
+            for fll in (False, True):
+                key = "chain_fll" if fll else "chain"
+                strong = bench_chain.run_chain(Q, torch, d, world, rank, stream, use_fll=fll, channels_per_gpu=tot // world,
+                                               parity_channels=(256 if world == 1 else 64) if not args.no_cpu else 0,
+                                               label=f"strong: {tot} channels in total, {tot // world} per GPU", **common)
+                scaling_legs[key + "_strong"] = strong
+                if world == 1:
+                    scaling_legs[key + "_saturated"] = dict(strong, label=f"saturated weak: {tot} channels per GPU (same run as the strong leg at N = 1)")
+                else:
+                    scaling_legs[key + "_saturated"] = bench_chain.run_chain(
+                        Q, torch, d, world, rank, stream, use_fll=fll, channels_per_gpu=tot, parity_channels=0,
+                        label=f"saturated weak: {tot} channels per GPU", **common)
         modulator = bench_chain.run_modulator(Q, torch, d, world, rank, stream, steps=k, warmup=3, hbm_peak=hbm_peak)
         stream_leg = bench_chain.run_stream(Q) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
@@ -391,16 +435,28 @@ def main():
                        "parallelism": f"{world} independent streams, one per GPU, no collective"},
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_by_taps": roofs, "fma_peak_tflops_measured": fma_peak,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "build_id": build_id,
+            "scaling_note": "`scaling: weak` refers to `value` (one independent 2^28-sample FIR stream per GPU, no communication). "
+                            "The chain legs state their own: chain / chain_fll are weak (2048 channels per GPU), *_strong shard a "
+                            "fixed 16384-channel set (config 4), *_saturated put 16384 channels on every GPU",
         }
+        if comm is not None:
+            line["comm"] = dict(comm.info(), api="qpsk_comm_create / qpsk_ber_gather (ncclAllGather behind the C ABI)")
         if chain is not None:
             line["chain"] = chain
             line["chain_fll"] = chain_fll
+            line.update(scaling_legs)
             line["modulator"] = modulator
             if stream_leg is not None:
                 line["stream"] = stream_leg
-        print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

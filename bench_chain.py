@@ -20,38 +20,50 @@ import numpy as np
 TSC = "11001010011101100100100110101100" + "01110100111001011010001101101001"
 
 
-def _chain_cpu_baseline(rx_host, fs, rs, alpha, use_fll, bursts_per_core=128, passes=16):
-    """The oracle's restatement of the same demodulator chain (QPSKDeModulator.DeModulate) on all host cores: one
-    demodulator per core fed `bursts_per_core` bursts back to back, threads = cores (the library releases the GIL)."""
+def _oracle_replay(sets_host, order, channels, fs, rs, alpha, use_fll):
+    """The oracle's restatement of QPSKDeModulator.DeModulate on all host cores, fed — per checked channel — exactly the
+    sequence of bursts the GPU demodulator saw (warm-up and timed steps, state carried from burst to burst).  Returns the
+    bit string of the LAST burst per channel, the wall time and the samples processed: it is both the parity checker of
+    the benchmarked run and the CPU baseline of this leg (`kind: "port"`)."""
     import os
     import time
     from concurrent.futures import ThreadPoolExecutor
     import oracle as O
     O.build()
     cores = os.cpu_count() or 1
-    n = min(rx_host.shape[0], cores * bursts_per_core)
-    rows = [rx_host[c] for c in range(n)]
+    last = [None] * len(channels)
 
     def work(t):
         done = 0
-        d = O.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC, use_fll=use_fll)   # one stream of bursts per core
-        for _ in range(passes):
-            for c in range(t, n, cores):
-                d.DeModulate(rows[c])
-                done += rows[c].size // 2
+        for j in range(t, len(channels), cores):
+            c = channels[j]
+            d = O.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC, use_fll=use_fll)
+            b = ""
+            for k in order:
+                b = d.DeModulate(sets_host[k][c])
+                done += sets_host[k][c].size // 2
+            last[j] = b
         return done
 
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=cores) as ex:
+    with ThreadPoolExecutor(max_workers=cores) as ex:            # the oracle library releases the GIL
         samples = sum(ex.map(work, range(cores)))
     dt = time.perf_counter() - t0
-    return {"value": samples / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port", "seconds": dt,
-            "sample": f"{passes} passes over {n} of the bursts ({n // cores} per core), C++ restatement of QPSKDeModulator.DeModulate"
-                      f"{' with the FLL' if use_fll else ''}, one demodulator per core"}
+    return last, dt, samples, cores
+
+
+def _count_errors(bits: str, ref: np.ndarray) -> int:
+    """qpsk_ber_count_dev's rule on the host: Hamming distance over min(n_rx, n_ref) + the bits that never arrived."""
+    rx = np.frombuffer(bits.encode("ascii"), np.uint8) & 1
+    n = min(rx.size, ref.size)
+    return int((rx[:n] != ref[:n]).sum()) + max(0, ref.size - rx.size)
 
 
 def run_chain(Q, torch, dist, world, rank, stream, steps=3, warmup=3, channels_per_gpu=2048, use_fll=False,
-              n_payload=512, hbm_peak=6461.8, cpu=False):
+              n_payload=512, hbm_peak=6461.8, cpu=False, comm=None, parity_channels=None, fir_mode=None, label=None):
+    """One chain leg.  `fir_mode` None = the demodulator's default matched-filter arithmetic (QPSK_FIR_EXACT).
+    parity_channels: how many of this rank's channels are replayed through the oracle and compared bit for bit with what
+    the TIMED run left in its output buffers (None = all when `cpu`, else 0)."""
     from qpsk_modulator_demodulator_b200 import shard
     fs = 10_000_000
     rs = fs // 2
@@ -76,63 +88,124 @@ def run_chain(Q, torch, dist, world, rank, stream, steps=3, warmup=3, channels_p
     rx = [torch.empty((C, ff), dtype=torch.float32, device="cuda") for _ in range(K)]
     for k in range(K):
         chan.apply_dev(tx.data_ptr(), ff, ff, rx[k].data_ptr(), ff, stream)
-    dem = Q.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC, use_fll=use_fll, channels=C)
-    cap = dem.bits_bound(ff)
-    bits = torch.zeros((C, cap), dtype=torch.uint8, device="cuda")
-    nb = torch.zeros(C, dtype=torch.int64, device="cuda")
     nref = 8 * (n_payload + 2)
     framed = torch.cat([torch.full((C, 1), ord("S"), dtype=torch.uint8, device="cuda"), pay,
                         torch.full((C, 1), ord("E"), dtype=torch.uint8, device="cuda")], dim=1).contiguous()
     ref = torch.empty((C, nref), dtype=torch.uint8, device="cuda")
     Q.unpack_bits_dev(framed.data_ptr(), n_payload + 2, n_payload + 2, C, ref.data_ptr(), nref, stream)
-    cnt = torch.zeros((C, 2), dtype=torch.int32, device="cuda")
-
-    def step(i):
-        r = rx[i % K]
-        dem.demod_bits_dev(r.data_ptr(), ff, ff, bits.data_ptr(), cap, nb.data_ptr(), stream)
-        Q.ber_count_dev(bits.data_ptr(), cap, nb.data_ptr(), ref.data_ptr(), nref, nref, C, cnt.data_ptr(), stream)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(warmup):
-        step(i)
-    barrier()
-    Q.launch_count_reset()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        step(warmup + i)
-    e1.record()
-    barrier()
-    launches = Q.launch_count()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    allc = shard.gather_counters(cnt, dist)          # the one collective of the path: per-channel BER counters
-    allc = allc.cpu().numpy().astype(np.int64)
+    def timed(mode):
+        """warm-up + timed steps on a fresh demodulator; returns (ms, launches, bits, n_bits, counters) of the last step"""
+        dem = Q.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC, use_fll=use_fll, channels=C)
+        if mode is not None:
+            dem.set_fir_mode(mode)
+        cap = dem.bits_bound(ff)
+        bits = torch.zeros((C, cap), dtype=torch.uint8, device="cuda")
+        nb = torch.zeros(C, dtype=torch.int64, device="cuda")
+        cnt = torch.zeros((C, 2), dtype=torch.int32, device="cuda")
+
+        def step(i):
+            r = rx[i % K]
+            dem.demod_bits_dev(r.data_ptr(), ff, ff, bits.data_ptr(), cap, nb.data_ptr(), stream)
+            Q.ber_count_dev(bits.data_ptr(), cap, nb.data_ptr(), ref.data_ptr(), nref, nref, C, cnt.data_ptr(), stream)
+
+        for i in range(warmup):
+            step(i)
+        barrier()
+        Q.launch_count_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(warmup + i)
+        e1.record()
+        barrier()
+        launches = Q.launch_count()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), int(launches), bits, nb, cnt
+
+    ms, launches, bits, nb, cnt = timed(fir_mode)
+    # the one collective of the path: per-channel BER counters, through the library's own NCCL communicator when there is
+    # one (qpsk_ber_gather, what a C# host calls), else torch.distributed
+    if comm is not None:
+        allc = comm.gather(cnt.data_ptr(), C, total_channels).astype(np.int64)
+        gathered = "qpsk_ber_gather (ncclAllGather behind the C ABI)"
+    else:
+        allc = shard.gather_counters(cnt, dist).cpu().numpy().astype(np.int64)
+        gathered = "all_gather (torch.distributed)" if dist is not None else "single rank"
     samples = total_channels * (ff // 2) * steps
     gbs = 8.0 * samples / world / (ms * 1e-3) / 1e9   # per GPU: 8 B read per complex sample (fused ideal)
-    cpu_leg = None
-    if cpu and rank == 0:
-        ncpu = min(C, 128 * (__import__("os").cpu_count() or 1))
-        cpu_leg = _chain_cpu_baseline(rx[0][:ncpu].cpu().numpy(), fs, rs, alpha, use_fll)
+
+    # ---- parity of THIS run: its last step's bits against the oracle fed the same burst sequence -------------------
+    n_par = (C if cpu else 0) if parity_channels is None else min(parity_channels, C)
+    parity = cpu_leg = None
+    if n_par > 0:
+        order = [i % K for i in range(warmup + steps)]
+        chans = [int(c) for c in np.unique(np.linspace(0, C - 1, n_par).astype(np.int64))]
+        idx = torch.tensor(chans, device="cuda")
+        sets_host = {k: rx[k][idx].cpu().numpy() for k in sorted(set(order))}
+        remap = list(range(len(chans)))
+        want, dt, n_samp, cores = _oracle_replay(sets_host, order, remap, fs, rs, alpha, use_fll)
+        ref_h = ref[idx].cpu().numpy()
+
+        def gpu_strings(b, n):
+            bh, nh = b[idx].cpu().numpy(), n[idx].cpu().numpy()
+            return [(bh[j, : nh[j]] + 48).astype(np.uint8).tobytes().decode("ascii") for j in range(len(chans))]
+
+        got = gpu_strings(bits, nb)
+        cnt_h = cnt[idx].cpu().numpy().astype(np.int64)
+        o_err = [_count_errors(w, ref_h[j]) for j, w in enumerate(want)]
+        mode_name = "fast" if fir_mode == Q.FIR_FAST else "exact"
+        parity = {"channels_checked": len(chans), "bursts_per_channel": len(order),
+                  "what": "bits left by the LAST timed step vs the oracle fed the same burst sequence per channel (state carried)",
+                  f"mismatch_{mode_name}": sum(g != w for g, w in zip(got, want)),
+                  "oracle_bit_errors": int(sum(o_err)), "gpu_bit_errors": int(cnt_h[:, 0].sum()),
+                  "ber_counters_equal": bool(all(int(cnt_h[j, 0]) == o_err[j] for j in range(len(chans)))),
+                  "oracle_error_free_channels": int(sum(e == 0 for e in o_err))}
+        # the other matched-filter mode on the same sequence (untimed here; "fast_mf" below times it)
+        other = Q.FIR_FAST if mode_name == "exact" else Q.FIR_EXACT
+        _, _, bits2, nb2, _ = timed(other)
+        parity[f"mismatch_{'fast' if other == Q.FIR_FAST else 'exact'}"] = sum(g != w for g, w in zip(gpu_strings(bits2, nb2), want))
+        cpu_leg = {"value": n_samp / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port", "seconds": dt,
+                   "sample": f"{len(order)} bursts x {len(chans)} channels, C++ restatement of QPSKDeModulator.DeModulate"
+                             f"{' with the FLL' if use_fll else ''}, one demodulator per channel, {cores} threads — the run whose bits "
+                             "the parity block compares"}
+        if dist is not None:
+            keys = [k for k in parity if isinstance(parity[k], int) and not isinstance(parity[k], bool) and k != "bursts_per_channel"]
+            t = torch.tensor([parity[k] for k in keys] + [int(parity["ber_counters_equal"])], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            for k, v in zip(keys, t.tolist()):
+                parity[k] = int(v)
+            parity["ber_counters_equal"] = bool(t[-1].item() == world)
+            parity["summed_over_ranks"] = world
+    fast = None
+    if fir_mode is None and cpu:
+        ms_f, _, _, _, cnt_f = timed(Q.FIR_FAST)
+        fast = {"value": samples / (ms_f * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_f / steps,
+                "bit_errors": int(cnt_f[:, 0].sum().item()),
+                "note": "same leg with qpsk_demod_set_fir_mode(QPSK_FIR_FAST): FMA-accumulated matched filter (parity.mismatch_fast "
+                        "counts the channels whose bits differ from the oracle's)"}
     return {
-        "cpu_baseline": cpu_leg,
+        "label": label, "cpu_baseline": cpu_leg, "parity": parity, "fast_mf": fast,
+        "mf_mode": "fast" if fir_mode == Q.FIR_FAST else "exact (default: the reference's summation order)",
         "impairments": "two unstable LOs (100 MHz, 1 ppm static error + random-walk drift each), AWGN -40 dBFS, static two-path "
                        "multipath (echo 0.12+0.08j, 3 samples late), regenerated on the device per channel from the counter RNG",
         "workload": f"{total_channels} channels ({C}/GPU) x {ff // 2} cf32 samples per burst, "
                     f"{'FLL -> ' if use_fll else ''}MF(21 taps) -> MM -> Costas -> decode -> TSC strip -> BER; {K} burst sets cycled "
                     f"({set_bytes * K / 1e6:.0f} MB > L2)",
+        "channels_total": total_channels, "channels_per_gpu": C,
         "value": samples / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms / steps, "steps": steps,
         "gpu_launches": int(launches),
         "ber": {"channels": int(allc.shape[0]), "bits_per_channel": nref,
                 "error_free_channels": int((allc[:, 0] == 0).sum()),
                 "bit_errors": int(allc[:, 0].sum()), "bits": int(allc[:, 1].sum()),
-                "gathered_with": "all_gather (NCCL)" if dist is not None else "single rank"},
+                "gathered_with": gathered},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                      "note": "8 B/sample algorithmic; the serial loops (8 lanes per stream in the FLL, one lane per channel in MM / Costas) are "
                              "dependent-issue-latency bound, not HBM bound (DESIGN.md)"},

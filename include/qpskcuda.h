@@ -57,6 +57,9 @@ typedef struct qpsk_stream qpsk_stream;
 
 /* ---- library / device -------------------------------------------------------------------- */
 QPSK_API int qpsk_version(void);                       /* 10000*major + 100*minor + patch         */
+/* build stamp: hash of the kernel sources, this header, the nvcc flags and version the library was compiled from (16 hex
+ * chars).  The Python host refuses a library whose stamp differs from the source tree next to it; bench.py prints it. */
+QPSK_API const char* qpsk_build_id(void);
 QPSK_API const char* qpsk_strerror(int status);
 QPSK_API const char* qpsk_last_cuda_error(void);       /* thread-local text of the last CUDA error */
 QPSK_API int qpsk_device_count(int* n);
@@ -91,6 +94,8 @@ QPSK_API int qpsk_fir_destroy(qpsk_fir* f);
 QPSK_API int qpsk_fir_reset(qpsk_fir* f);                      /* zero the delay line(s)          */
 QPSK_API int qpsk_fir_set_mode(qpsk_fir* f, int mode);
 QPSK_API int qpsk_fir_num_taps(const qpsk_fir* f, int* n_complex);
+/* name of the kernel the handle's last filter call launched (which of the kernels in DESIGN.md §3 served it) */
+QPSK_API int qpsk_fir_last_kernel(const qpsk_fir* f, char* name, int cap);
 /* Filter(ReadOnlySpan<float>, Span<float>) :80-91 — streaming, same length, history kept.
  * out_cap_floats < n_floats -> QPSK_ERR_ARG (:83); odd n_floats -> QPSK_ERR_ARG (:82).
  * Batch handles: in/out are [channels][n_floats] contiguous. */
@@ -193,6 +198,9 @@ QPSK_API int qpsk_demod_create_batch(int sample_rate, int symbol_rate, float rrc
                                      int differential, const char* tsc_bits, int use_fll,
                                      int64_t max_frame_bytes, int channels, qpsk_demod** out);
 QPSK_API int qpsk_demod_destroy(qpsk_demod* d);
+/* matched-filter arithmetic.  Default QPSK_FIR_EXACT: bits, frames and payloads are then those of the reference's
+ * summation order bit for bit.  QPSK_FIR_FAST accumulates with FMA (outputs within ~1e-7 relative): a decision can differ
+ * only where a decision variable lies that close to zero (bench.py counts such channels on its own bursts). */
 QPSK_API int qpsk_demod_set_fir_mode(qpsk_demod* d, int mode);
 /* DeModulate(ReadOnlySpan<float>) :345-425 -> '0'/'1' chars (not NUL-terminated).  Batch handles:
  * iq_in [channels][n_floats], bits_out [channels][cap], n_bits[channels] (same layout rule for the
@@ -209,6 +217,11 @@ QPSK_API int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_float
                               const uint8_t* start_marker, int64_t n_start,
                               const uint8_t* end_marker, int64_t n_end,
                               uint8_t* payload_out, int64_t cap, int64_t* n_bytes);
+/* After qpsk_demod_bytes / qpsk_demod_frame_bits returned QPSK_ERR_CAPACITY (n_bytes[c] > cap for some channel): the
+ * frames that call completed are still at the head of the framer ring until the next call on the handle, and this copies
+ * them out ([channels][cap], n_bytes[channels] as before).  A frame that grew over several calls (the MTU-block loop of
+ * TB/SDR/ModDemodOverSDR.cs:127-136) can therefore exceed a buffer sized from one call's samples without being lost. */
+QPSK_API int qpsk_demod_last_payload(qpsk_demod* d, uint8_t* payload_out, int64_t cap, int64_t* n_bytes);
 /* The framer half of DeModulateBytes (:182-259: carry + offset hunt :185-236, ring append and end-marker search
  * :238-258) on bits the caller already holds — what DeModulateBytes does after its DeModulate call (:177), sharing the
  * handle's framer state with qpsk_demod_bytes.  bits is HOST memory, [channels][bits_stride], one byte 0/1 per bit,
@@ -242,6 +255,8 @@ QPSK_API int qpsk_demod_loop_state(qpsk_demod* d, double* costas_theta, double* 
 /* _inFrame (:62) per channel */
 QPSK_API int qpsk_demod_in_frame(qpsk_demod* d, int* in_frame);
 QPSK_API int qpsk_demod_channels(const qpsk_demod* d, int* channels);
+/* the CUDA device the handle was created on (every call on the handle runs there, whatever qpsk_set_device says now) */
+QPSK_API int qpsk_demod_device(const qpsk_demod* d, int* ordinal);
 
 /* ---- streaming front-end: the receive loop of TB/SDR/ModDemodOverSDR.cs:116-183 ------------- */
 /* That loop reads one MTU of cf32 samples into a caller-owned buffer and calls DeModulateTextUtf8 on it (:127-136).
@@ -352,6 +367,29 @@ QPSK_API int qpsk_pack_bits_dev(const uint8_t* d_bits, int64_t bits_stride, cons
 QPSK_API int qpsk_ber_count_dev(const uint8_t* d_rx_bits, int64_t rx_stride, const int64_t* d_n_rx,
                                 const uint8_t* d_ref_bits, int64_t ref_stride, int64_t n_ref,
                                 int channels, uint32_t* d_counters, void* stream);
+
+/* ---- the one collective: all-gather of the per-channel BER counters over NCCL ------------------------ */
+/* Channels are independent and sharded in contiguous blocks, one block per GPU (channel c on rank floor(c*G/C)); nothing is
+ * exchanged on the data path.  After a run each rank holds {errors, bits}[channels_local] from qpsk_ber_count_dev; these
+ * calls collect the whole table on every rank.  One communicator per process (or thread) and GPU: rank 0 makes the id,
+ * ships its QPSK_COMM_ID_BYTES to the other ranks by any means (a file, a socket, MPI, torch.distributed's store), and
+ * all ranks call qpsk_comm_create — a collective — on the device chosen with qpsk_set_device.  NCCL is loaded with
+ * dlopen("libnccl.so.2"); without it these calls return QPSK_ERR_UNSUPPORTED and nothing else in the library is affected. */
+typedef struct qpsk_comm qpsk_comm;
+#define QPSK_COMM_ID_BYTES 128
+QPSK_API int qpsk_comm_unique_id(uint8_t* id, int cap);                       /* ncclGetUniqueId */
+QPSK_API int qpsk_comm_create(const uint8_t* id, int n_ranks, int rank, qpsk_comm** out);   /* ncclCommInitRank */
+QPSK_API int qpsk_comm_destroy(qpsk_comm* c);
+/* what the communicator itself reports (ncclCommCount / ncclCommUserRank) and the NCCL version in use */
+QPSK_API int qpsk_comm_info(qpsk_comm* c, int* n_ranks, int* rank, int* nccl_version);
+/* d_counters: this rank's uint32 {errors, bits}[channels_local] in device memory; channels_max = the largest block of any
+ * rank (blocks differ by at most one channel when G does not divide C).  d_all (device, every rank):
+ * [n_ranks][channels_max][2], rank r's block at row r*channels_max, rows past a rank's own count {0, 0}.  Enqueued on
+ * `stream` (NULL = the communicator's own), no synchronisation. */
+QPSK_API int qpsk_ber_gather_dev(qpsk_comm* c, const uint32_t* d_counters, int channels_local, int channels_max,
+                                 uint32_t* d_all, void* stream);
+/* the same into host memory (all_host[n_ranks*channels_max*2]); d_counters must be complete when it is called */
+QPSK_API int qpsk_ber_gather(qpsk_comm* c, const uint32_t* d_counters, int channels_local, int channels_max, uint32_t* all_host);
 
 /* ---- measurement helpers ------------------------------------------------------------------- */
 /* FP32 FMA-pipe peak (TFLOP/s) by a register-resident FFMA micro-benchmark, for the roofline */

@@ -68,6 +68,7 @@ internal static unsafe partial class QpskCuda
     [DllImport(Lib)] internal static extern int qpsk_demod_bits(IntPtr h, float* iqIn, long nFloats, byte* bitsOut, long cap, out long nBits);
     [DllImport(Lib)] internal static extern int qpsk_demod_bytes(IntPtr h, float* iqIn, long nFloats, byte* start, long nStart,
                                                                  byte* end, long nEnd, byte* payloadOut, long cap, out long nBytes);
+    [DllImport(Lib)] internal static extern int qpsk_demod_last_payload(IntPtr h, byte* payloadOut, long cap, out long nBytes);
     [DllImport(Lib)] internal static extern int qpsk_demod_constellation(IntPtr h, float* iqIn, long nFloats, float* symOut, long capFloats, out long nSym);
     [DllImport(Lib)] internal static extern int qpsk_demod_frame_bits(IntPtr h, byte* bits01, long bitsStride, long* nBits, byte* start, long nStart,
                                                                       byte* end, long nEnd, byte* payloadOut, long cap, long* nBytes);

@@ -307,12 +307,21 @@ namespace QPSK
             if (endMarker.Length == 0) throw new ArgumentException("endMarker cannot be empty.", nameof(endMarker));         // :175
             if ((samplesIQ.Length & 1) != 0)
                 throw new ArgumentException("Samples must be interleaved IQ with even length.", nameof(samplesIQ));         // :347-348 via :177
-            // a frame may have been accumulating on the device over earlier calls: size for the library's frame bound (1 MiB)
-            var buf = new byte[Math.Max(samplesIQ.Length / 8 + 64, 1 << 20)];
+            var buf = new byte[samplesIQ.Length / 8 + 64];                            // what this call's samples alone can carry
             fixed (float* i = samplesIQ) fixed (byte* s = startMarker) fixed (byte* e = endMarker) fixed (byte* o = buf)
             {
-                QpskCuda.Check(QpskCuda.qpsk_demod_bytes(_h, i, samplesIQ.Length, s, startMarker.Length, e, endMarker.Length, o, buf.Length,
-                                                         out long n), nameof(samplesIQ));
+                int st = QpskCuda.qpsk_demod_bytes(_h, i, samplesIQ.Length, s, startMarker.Length, e, endMarker.Length, o, buf.Length,
+                                                   out long n);
+                if (st == -6)
+                {
+                    // QPSK_ERR_CAPACITY: the frame accumulated on the device over earlier calls (MTU-block streaming) and is
+                    // longer than this call's buffer; it is still in the framer ring, fetch it at its reported size
+                    var big = new byte[n];
+                    fixed (byte* b = big) QpskCuda.Check(QpskCuda.qpsk_demod_last_payload(_h, b, big.Length, out n));
+                    GC.KeepAlive(this);
+                    return big;
+                }
+                QpskCuda.Check(st, nameof(samplesIQ));
                 GC.KeepAlive(this);
                 if (n == 0) return Array.Empty<byte>();                              // :180, :258
                 var payload = new byte[n];

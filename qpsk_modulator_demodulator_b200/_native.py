@@ -60,6 +60,7 @@ def _signatures():
     i, i64, u64, d, f, vp, cp = C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_float, C.c_void_p, C.c_char_p
     return {
         "qpsk_version": (i, []),
+        "qpsk_build_id": (cp, []),
         "qpsk_strerror": (cp, [i]),
         "qpsk_last_cuda_error": (cp, []),
         "qpsk_device_count": (i, [i32p]),
@@ -78,6 +79,7 @@ def _signatures():
         "qpsk_fir_reset": (i, [vp]),
         "qpsk_fir_set_mode": (i, [vp, i]),
         "qpsk_fir_num_taps": (i, [vp, i32p]),
+        "qpsk_fir_last_kernel": (i, [vp, cp, i]),
         "qpsk_fir_filter": (i, [vp, vp, vp, i64, i64]),
         "qpsk_fir_fft_filter": (i, [vp, vp, vp, i64]),
         "qpsk_fir_filter_dev": (i, [vp, vp, vp, i64, i64, i64, vp]),
@@ -119,6 +121,7 @@ def _signatures():
         "qpsk_demod_bits": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bits_packed": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bytes": (i, [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
+        "qpsk_demod_last_payload": (i, [vp, vp, i64, vp]),
         "qpsk_demod_frame_bits": (i, [vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp]),
         "qpsk_demod_constellation": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bits_dev": (i, [vp, vp, i64, i64, vp, i64, vp, vp]),
@@ -128,6 +131,7 @@ def _signatures():
         "qpsk_demod_loop_state": (i, [vp, f64p, f64p, f64p, f64p, f32p, f32p]),
         "qpsk_demod_in_frame": (i, [vp, i32p]),
         "qpsk_demod_channels": (i, [vp, i32p]),
+        "qpsk_demod_device": (i, [vp, i32p]),
         "qpsk_stream_create": (i, [vp, i64, i64, i, vp, i64, vp, i64, vpp]),
         "qpsk_stream_destroy": (i, [vp]),
         "qpsk_stream_push": (i, [vp, vp, i64]),
@@ -157,6 +161,12 @@ def _signatures():
         "qpsk_pack_bits_dev": (i, [vp, i64, vp, i64, i, vp, i64, vp]),
         "qpsk_ber_count_dev": (i, [vp, i64, vp, vp, i64, i64, i, vp, vp]),
         "qpsk_measure_fma_peak": (i, [f64p]),
+        "qpsk_comm_unique_id": (i, [vp, i]),
+        "qpsk_comm_create": (i, [vp, i, i, vpp]),
+        "qpsk_comm_destroy": (i, [vp]),
+        "qpsk_comm_info": (i, [vp, i32p, i32p, i32p]),
+        "qpsk_ber_gather_dev": (i, [vp, vp, i, i, vp, vp]),
+        "qpsk_ber_gather": (i, [vp, vp, i, i, vp]),
     }
 
 
@@ -175,8 +185,30 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
+        _check_stamp(L)
         _lib = L
     return _lib
+
+
+def build_id() -> str:
+    """Stamp of the loaded library (hash of the sources, header, nvcc flags and version it was compiled from)."""
+    return lib().qpsk_build_id().decode()
+
+
+def _check_stamp(L):
+    """A library that travels with a source tree must be the build of THAT tree: file times do not survive the copy to
+    the GPU box, so the stamp compiled into the library is compared with the hash of the sources next to it."""
+    if os.environ.get("QPSK_SKIP_BUILD_CHECK") == "1" or not os.path.isdir(os.path.join(_HERE, "csrc")):
+        return
+    from . import build as _b
+    try:
+        want = _b.source_id()
+    except RuntimeError:          # no nvcc: the tree cannot be rebuilt here, nothing to compare against
+        return
+    got = L.qpsk_build_id().decode()
+    if got != want:
+        raise QpskCudaError(f"{LIB_PATH} carries build stamp {got} but the sources next to it hash to {want}: stale library, "
+                            "run `python -m qpsk_modulator_demodulator_b200.build`")
 
 
 def declared_symbols():

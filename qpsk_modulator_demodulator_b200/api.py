@@ -172,6 +172,11 @@ class ComplexFIRFilter(_Handle):
     def reset(self):
         check(lib().qpsk_fir_reset(self._h))
 
+    def last_kernel(self) -> str:
+        buf = C.create_string_buffer(128)
+        check(lib().qpsk_fir_last_kernel(self._h, buf, 128))
+        return buf.value.decode()
+
     def Filter(self, iqIn, iqOut=None, out_len=None) -> np.ndarray:
         """Filter(ReadOnlySpan<float>, Span<float>) :80-91.  Batch handles: shape [channels, n_floats]."""
         x = _f32(iqIn)

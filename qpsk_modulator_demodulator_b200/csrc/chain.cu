@@ -20,6 +20,7 @@ namespace qpsk {
 
 struct ChainEngine {
   int channels = 1;
+  int device = 0;
   FllEngine fll;
   FirEngine mf;
   MmEngine mm;
@@ -39,6 +40,7 @@ struct ChainEngine {
     // the reference ctor (MuellerMuller.cs:38-50) validates nothing; with sps <= 0.1 its loop (:62-120) never advances
     if (!(p.mm_sps > 0.1)) return QPSK_ERR_UNSUPPORTED;
     QPSK_TRY(ensure_device());
+    device = current_device();
     channels = channels_in;
     mm_sps = p.mm_sps;
     QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -124,7 +126,7 @@ int qpsk_chain_create(const qpsk_chain_params* p, int channels, qpsk_chain** out
 
 int qpsk_chain_destroy(qpsk_chain* c) {
   if (c) {
-    cudaSetDevice(current_device());
+    cudaSetDevice(c->eng.device);
     if (c->eng.stream) cudaStreamSynchronize(c->eng.stream);
     delete c;
   }
@@ -153,7 +155,7 @@ int qpsk_chain_process_dev(qpsk_chain* c, const float* d_in, int64_t n_floats, i
   if ((n_floats & 1) || (in_stride & 1) || (bb_stride & 1) || (sync_stride & 1) || (costas_stride & 1)) return QPSK_ERR_ARG;
   if (n_floats > 0 && (!d_in || !d_baseband || !d_sync || !d_costas)) return QPSK_ERR_NULL;
   if (c->eng.channels > 1 && (in_stride < n_floats || bb_stride < n_floats)) return QPSK_ERR_ARG;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(c->eng.device));
   return c->eng.process_dev((const float2*)d_in, n_floats >> 1, in_stride >> 1, (float2*)d_baseband, bb_stride >> 1,
                             (float2*)d_sync, sync_stride >> 1, (float2*)d_costas, costas_stride >> 1, d_n_sym,
                             (cudaStream_t)stream);
@@ -170,7 +172,7 @@ int qpsk_chain_process(qpsk_chain* c, const float* iq_in, int64_t n_floats, floa
     return QPSK_OK;
   }
   if (!iq_in || !baseband_out || !sync_out || !costas_out) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(c->eng.device));
   const int64_t L = n_floats >> 1;
   const int64_t ld = L + (L & 1);
   const int64_t lds = e.symbols_bound(L);
@@ -196,7 +198,7 @@ int qpsk_chain_process(qpsk_chain* c, const float* iq_in, int64_t n_floats, floa
 int qpsk_chain_loop_state(qpsk_chain* c, float* fll_phase, float* fll_freq, double* mm_mu, double* costas_theta,
                           double* costas_freq) {
   if (!c) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(c->eng.device));
   ChainEngine& e = c->eng;
   QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
   QPSK_CUDA_TRY(cudaDeviceSynchronize());

@@ -321,6 +321,7 @@ using namespace qpsk;
 struct qpsk_chan {
   ChanArgs args;
   int channels = 0;
+  int device = 0;
   DevBuf<ChanState> d_state;
   DevBuf<float2> d_hist, d_in, d_out;
   DevBuf<double> d_phase;          // [2][channels][slab] oscillator phases of the slab being mixed
@@ -344,6 +345,7 @@ int qpsk_chan_create(const qpsk_chan_params* p, int channels, int first_channel,
   QPSK_TRY(ensure_device());
   qpsk_chan* c = new (std::nothrow) qpsk_chan();
   if (!c) return QPSK_ERR_NOMEM;
+  c->device = current_device();
   ChanArgs& a = c->args;
   auto nco = [&](double f, double ppm, double ph) {
     NcoParams n;
@@ -396,7 +398,7 @@ int qpsk_chan_apply_dev(qpsk_chan* c, const float* d_x, int64_t n_floats, int64_
   if ((n_floats & 1) || (x_stride_floats & 1) || (y_stride_floats & 1)) return QPSK_ERR_ARG;
   if (n_floats == 0) return QPSK_OK;
   if (!d_x || !d_y) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(c->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
   // time slabs bound the phase scratch (2 x 128 MB); an in-place call is allowed without multipath only, as before
   const long long L = n_floats >> 1;
@@ -431,7 +433,7 @@ int qpsk_chan_apply(qpsk_chan* c, const float* x, int64_t n_floats, float* y) {
   if (n_floats & 1) return QPSK_ERR_ARG;
   if (n_floats == 0) return QPSK_OK;
   if (!x || !y) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(c->device));
   const size_t tot = (size_t)(n_floats >> 1) * c->channels;
   QPSK_TRY(c->d_in.ensure(tot));
   QPSK_TRY(c->d_out.ensure(tot));

@@ -39,9 +39,10 @@ void count_launch(int n = 1);
     QPSK_CUDA_TRY(cudaGetLastError());           \
   } while (0)
 
-int current_device();          // ordinal chosen by qpsk_set_device (default 0)
-int ensure_device();           // cudaSetDevice(current) + arch check; status code
-int device_sm_count();
+int current_device();          // ordinal handles created by THIS thread get: the thread's qpsk_set_device choice, else the
+                               // process-wide one (last qpsk_set_device of any thread), else 0
+int ensure_device(int dev = -1);  // cudaSetDevice(dev, or current_device()) + arch check; status code
+int device_sm_count();         // of the device the calling thread has current (call after ensure_device)
 
 // RAII device buffer
 template <typename T>

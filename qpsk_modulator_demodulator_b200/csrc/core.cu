@@ -1,6 +1,8 @@
 // core.cu — library/device plumbing and the host-side filter designers (a1, a7).
 #include <math.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "design.h"
 
@@ -8,7 +10,11 @@ namespace qpsk {
 
 static thread_local std::string tl_cuda_error;
 static thread_local int64_t tl_launches = 0;
-static int g_device = 0;
+// Device selection: handles record the ordinal they were created on and every entry point selects it, so the choice below
+// only matters at creation time.  qpsk_set_device sets the calling thread's choice and the process-wide default that
+// threads which never chose fall back to; two threads driving two GPUs do not see each other's choice.
+static std::atomic<int> g_device{0};
+static thread_local int tl_device = -1;
 
 void set_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
   char buf[512];
@@ -16,38 +22,44 @@ void set_cuda_error(cudaError_t e, const char* what, const char* file, int line)
   tl_cuda_error = buf;
   (void)cudaGetLastError();  // clear the sticky-less error state
 }
+void set_text_error(const char* text) { tl_cuda_error = text ? text : ""; }
 void count_launch(int n) { tl_launches += n; }
-int current_device() { return g_device; }
+int current_device() { return tl_device >= 0 ? tl_device : g_device.load(std::memory_order_relaxed); }
 
-int ensure_device() {
+int ensure_device(int dev) {
+  if (dev < 0) dev = current_device();
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
     if (e != cudaSuccess) set_cuda_error(e, "cudaGetDeviceCount", __FILE__, __LINE__);
     return QPSK_ERR_NO_DEVICE;
   }
-  if (g_device >= n) return QPSK_ERR_NO_DEVICE;
-  QPSK_CUDA_TRY(cudaSetDevice(g_device));
+  if (dev >= n) return QPSK_ERR_NO_DEVICE;
+  QPSK_CUDA_TRY(cudaSetDevice(dev));
   static thread_local int checked_dev = -1;
-  if (checked_dev != g_device) {
+  if (checked_dev != dev) {
     int major = 0;
-    QPSK_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, g_device));
+    QPSK_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) {  // the fatbin holds sm_100a SASS only
       tl_cuda_error = "libqpskcuda is built for sm_100a (B200) only";
       return QPSK_ERR_NO_DEVICE;
     }
-    checked_dev = g_device;
+    checked_dev = dev;
   }
   return QPSK_OK;
 }
 
 int device_sm_count() {
-  static int cached[64] = {0};
-  int d = g_device;
-  if (d < 64 && cached[d]) return cached[d];
+  static std::atomic<int> cached[64];
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) d = current_device();
+  if (d >= 0 && d < 64) {
+    const int c = cached[d].load(std::memory_order_relaxed);
+    if (c) return c;
+  }
   int n = 148;
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
-  if (d < 64) cached[d] = n;
+  if (d >= 0 && d < 64) cached[d].store(n, std::memory_order_relaxed);
   return n;
 }
 
@@ -156,7 +168,15 @@ using namespace qpsk;
 
 extern "C" {
 
-int qpsk_version(void) { return 100; }
+int qpsk_version(void) { return 200; }
+
+// build stamp (build.py: hash of csrc/, include/qpskcuda.h, the nvcc flags and version); the "QPSK_BUILD_ID=" marker lets
+// build.py read it from the file without loading the library
+#ifndef QPSK_BUILD_ID_STR
+#define QPSK_BUILD_ID_STR "unstamped000000"
+#endif
+static const char kBuildId[] = "QPSK_BUILD_ID=" QPSK_BUILD_ID_STR;
+const char* qpsk_build_id(void) { return kBuildId + 14; }
 
 const char* qpsk_strerror(int s) {
   switch (s) {
@@ -189,17 +209,16 @@ int qpsk_device_count(int* n) {
 
 int qpsk_set_device(int ordinal) {
   if (ordinal < 0) return QPSK_ERR_RANGE;
-  int prev = g_device;
-  g_device = ordinal;
-  int st = ensure_device();
-  if (st != QPSK_OK) g_device = prev;
-  return st;
+  QPSK_TRY(ensure_device(ordinal));
+  tl_device = ordinal;
+  g_device.store(ordinal, std::memory_order_relaxed);
+  return QPSK_OK;
 }
 
 int qpsk_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes) {
   QPSK_TRY(ensure_device());
   cudaDeviceProp p;
-  QPSK_CUDA_TRY(cudaGetDeviceProperties(&p, g_device));
+  QPSK_CUDA_TRY(cudaGetDeviceProperties(&p, current_device()));
   if (sm_count) *sm_count = p.multiProcessorCount;
   if (cc_major) *cc_major = p.major;
   if (cc_minor) *cc_minor = p.minor;

@@ -734,6 +734,7 @@ constexpr int kMaxMarkerBytes = 256;
 
 struct DemodEngine {
   int channels = 1;
+  int device = 0;              // every entry point selects it (handles own their device, qpskcuda.h)
   bool diff = true, has_tsc = false, use_fll = false;
   std::string tsc;
   double sps = 0.0;
@@ -749,6 +750,7 @@ struct DemodEngine {
   DevBuf<FramerState> d_framer;
   DevBuf<float2> h_in, h_out;       // device staging for the host entry points
   std::vector<uint8_t> markers_host;
+  std::vector<long long> last_np;   // payload lengths of the last host framer call (qpsk_demod_last_payload)
   long long ring_cap = 0;
   long long sym_ld = 0;
   int64_t mf_ld = 0;
@@ -770,6 +772,7 @@ struct DemodEngine {
     if (channels_in <= 0) return QPSK_ERR_RANGE;
     if (rs == 0) return QPSK_ERR_RANGE;                        // DivideByZeroException upstream
     QPSK_TRY(ensure_device());
+    device = current_device();
     channels = channels_in;
     diff = diff_in != 0;
     use_fll = use_fll_in != 0;
@@ -781,6 +784,9 @@ struct DemodEngine {
     const std::vector<double> h = design_rrc((double)span, (double)alpha, fs, rs);   // :28-32
     const std::vector<float> iq = real_taps_as_iq(h);
     QPSK_TRY(mf.init(iq.data(), (int)iq.size(), channels));
+    // demodulated bits are compared bit for bit with the reference: the matched filter defaults to the reference's own
+    // summation order (FIRFilter.cs:165-192); QPSK_FIR_FAST (FMA accumulation, ~1e-7 relative) is the opt-in
+    mf.mode = QPSK_FIR_EXACT;
     QPSK_TRY(fll.init((float)(fs / rs), alpha, 40, (float)cfo_bw, channels));        // :35 (integer division)
     double kp, ki;
     mm_gains(sym_bw, &kp, &ki);                                // :39-55
@@ -872,6 +878,14 @@ struct DemodEngine {
       QPSK_CUDA_TRY(cudaMemsetAsync(n_out, 0, sizeof(long long) * channels, s));   // :350-351
       return QPSK_OK;
     }
+    // every capacity / alignment check comes BEFORE the first stage that advances state (matched-filter delay line, loop
+    // state, MM queue): a refused call must leave the stream where it was
+    {
+      long long sl = symbols_bound(L);
+      if (sl < 1) sl = 1;
+      if (ld_out < 2 * sl) return QPSK_ERR_CAPACITY;
+      if (!has_tsc && ((reinterpret_cast<uintptr_t>(out) & 1) || (ld_out & 1))) return QPSK_ERR_ARG;   // uchar2 stores
+    }
     const bool fused = can_fuse();
     const int chunks = (fused && use_fll) ? pipeline_chunks(L) : 1;
     if (chunks > 1) {
@@ -958,8 +972,12 @@ struct DemodEngine {
       QPSK_CUDA_TRY(cudaMemsetAsync(n_out, 0, sizeof(int) * channels, s));
       return QPSK_OK;
     }
+    {
+      long long sl = symbols_bound(L);                         // refuse before any stage consumes the samples
+      if (sl < 1) sl = 1;
+      if (ld_out < sl) return QPSK_ERR_CAPACITY;
+    }
     QPSK_TRY(front(x, L, ldx, s));
-    if (ld_out < sym_ld) return QPSK_ERR_CAPACITY;
     QPSK_TRY(costas.process_dev(t_sym.p, out, sym_ld, sym_ld, ld_out, d_nsym.p, s));   // :447-452
     QPSK_CUDA_TRY(cudaMemcpyAsync(n_out, d_nsym.p, sizeof(int) * channels, cudaMemcpyDeviceToDevice, s));
     return QPSK_OK;
@@ -1080,7 +1098,7 @@ int qpsk_demod_bits(qpsk_demod* d, const float* iq_in, int64_t n_floats, char* b
   DemodEngine& e = d->eng;
   for (int c = 0; c < e.channels; ++c) n_bits[c] = 0;
   if (n_floats == 0) return QPSK_OK;                         // :350-351
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(d->eng.device));
   cudaStream_t s = e.stream;
   const int64_t L = n_floats >> 1, ld = L + (L & 1);
   QPSK_TRY(demod_stage_in(e, iq_in, L, s));
@@ -1113,7 +1131,7 @@ int qpsk_demod_bits_packed(qpsk_demod* d, const float* iq_in, int64_t n_floats, 
   DemodEngine& e = d->eng;
   for (int c = 0; c < e.channels; ++c) n_bits[c] = 0;
   if (n_floats == 0) return QPSK_OK;                         // :350-351
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(d->eng.device));
   cudaStream_t s = e.stream;
   const int64_t L = n_floats >> 1, ld = L + (L & 1);
   QPSK_TRY(demod_stage_in(e, iq_in, L, s));
@@ -1149,14 +1167,15 @@ int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_floats, const 
   for (int c = 0; c < e.channels; ++c) n_bytes[c] = 0;
   if (n_floats == 0) return QPSK_OK;
   if (cap < 0) return QPSK_ERR_RANGE;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(d->eng.device));
   cudaStream_t s = e.stream;
   const int64_t L = n_floats >> 1, ld = L + (L & 1);
   QPSK_TRY(demod_stage_in(e, iq_in, L, s));
   const int64_t pcap = cap > 0 ? cap : 1;
   QPSK_TRY(e.d_payload.ensure((size_t)pcap * e.channels));
   QPSK_TRY(e.bytes_dev(e.h_in.p, L, ld, start_marker, n_start, end_marker, n_end, e.d_payload.p, pcap, e.d_npayload.p, s));
-  std::vector<long long> np((size_t)e.channels);
+  std::vector<long long>& np = e.last_np;
+  np.assign((size_t)e.channels, 0);
   QPSK_CUDA_TRY(cudaMemcpyAsync(np.data(), e.d_npayload.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
   QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   int st = QPSK_OK;
@@ -1166,6 +1185,26 @@ int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_floats, const 
     if (np[(size_t)c] == 0) continue;
     if (!payload_out) return QPSK_ERR_NULL;
     QPSK_CUDA_TRY(cudaMemcpy(payload_out + (size_t)c * cap, e.d_payload.p + (size_t)c * pcap, (size_t)np[(size_t)c],
+                             cudaMemcpyDeviceToHost));
+  }
+  return st;
+}
+
+int qpsk_demod_last_payload(qpsk_demod* d, uint8_t* payload_out, int64_t cap, int64_t* n_bytes) {
+  if (!d || !n_bytes) return QPSK_ERR_NULL;
+  if (cap < 0) return QPSK_ERR_RANGE;
+  DemodEngine& e = d->eng;
+  QPSK_TRY(ensure_device(e.device));
+  int st = QPSK_OK;
+  for (int c = 0; c < e.channels; ++c) {
+    const long long n = (size_t)c < e.last_np.size() ? e.last_np[(size_t)c] : 0;
+    n_bytes[c] = n;
+    if (n == 0) continue;
+    if (n > cap) { st = QPSK_ERR_CAPACITY; continue; }
+    if (!payload_out) return QPSK_ERR_NULL;
+    // a completed frame stays at the head of the channel's ring until the next framer call starts a new one
+    // (ResetFramer :159-167 clears the counters, not the bytes)
+    QPSK_CUDA_TRY(cudaMemcpy(payload_out + (size_t)c * cap, e.d_ring.p + (size_t)c * (size_t)e.ring_cap, (size_t)n,
                              cudaMemcpyDeviceToHost));
   }
   return st;
@@ -1186,7 +1225,7 @@ int qpsk_demod_frame_bits(qpsk_demod* d, const uint8_t* bits, int64_t bits_strid
   }
   if (max_bits == 0) return QPSK_OK;                         // :179-180 for every channel
   if (!bits) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(d->eng.device));
   cudaStream_t s = e.stream;
   const long long ldb = max_bits;
   QPSK_TRY(e.d_bits.ensure((size_t)ldb * e.channels));
@@ -1196,7 +1235,8 @@ int qpsk_demod_frame_bits(qpsk_demod* d, const uint8_t* bits, int64_t bits_strid
   const int64_t pcap = cap > 0 ? cap : 1;
   QPSK_TRY(e.d_payload.ensure((size_t)pcap * e.channels));
   QPSK_TRY(e.frame_dev(e.d_bits.p, ldb, e.d_nbits.p, start_marker, n_start, end_marker, n_end, e.d_payload.p, pcap, e.d_npayload.p, s));
-  std::vector<long long> np((size_t)e.channels);
+  std::vector<long long>& np = e.last_np;
+  np.assign((size_t)e.channels, 0);
   QPSK_CUDA_TRY(cudaMemcpyAsync(np.data(), e.d_npayload.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
   QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   int st = QPSK_OK;
@@ -1218,7 +1258,7 @@ int qpsk_demod_constellation(qpsk_demod* d, const float* iq_in, int64_t n_floats
   DemodEngine& e = d->eng;
   for (int c = 0; c < e.channels; ++c) n_sym[c] = 0;
   if (n_floats == 0) return QPSK_OK;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(d->eng.device));
   cudaStream_t s = e.stream;
   const int64_t L = n_floats >> 1, ld = L + (L & 1);
   QPSK_TRY(demod_stage_in(e, iq_in, L, s));
@@ -1242,6 +1282,12 @@ int qpsk_demod_constellation(qpsk_demod* d, const float* iq_in, int64_t n_floats
   return st;
 }
 
+int qpsk_demod_device(const qpsk_demod* d, int* ordinal) {
+  if (!d || !ordinal) return QPSK_ERR_NULL;
+  *ordinal = d->eng.device;
+  return QPSK_OK;
+}
+
 int qpsk_demod_channels(const qpsk_demod* d, int* channels) {
   if (!d || !channels) return QPSK_ERR_NULL;
   *channels = d->eng.channels;
@@ -1253,7 +1299,7 @@ int qpsk_demod_bits_dev(qpsk_demod* d, const float* d_in, int64_t n_floats, int6
   QPSK_TRY(demod_check_in(d, d_in, n_floats));
   if (!d_bits || !d_n_bits) return QPSK_ERR_NULL;
   if (in_stride_floats & 1) return QPSK_ERR_ARG;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(d->eng.device));
   DemodEngine& e = d->eng;
   cudaStream_t s = stream ? (cudaStream_t)stream : e.stream;
   return e.bits_dev((const float2*)d_in, n_floats >> 1, in_stride_floats >> 1, d_bits, bits_cap, (long long*)d_n_bits, s);
@@ -1277,7 +1323,7 @@ int qpsk_demod_bytes_dev(qpsk_demod* d, const float* d_in, int64_t n_floats, int
   if (!d_payload || !d_n_bytes) return QPSK_ERR_NULL;
   if (in_stride_floats & 1) return QPSK_ERR_ARG;
   if (payload_cap <= 0) return QPSK_ERR_RANGE;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(d->eng.device));
   DemodEngine& e = d->eng;
   cudaStream_t s = stream ? (cudaStream_t)stream : e.stream;
   if (n_floats == 0) {
@@ -1293,7 +1339,7 @@ int qpsk_demod_constellation_dev(qpsk_demod* d, const float* d_in, int64_t n_flo
   QPSK_TRY(demod_check_in(d, d_in, n_floats));
   if (!d_sym || !d_n_sym) return QPSK_ERR_NULL;
   if ((in_stride_floats & 1) || (sym_stride_floats & 1)) return QPSK_ERR_ARG;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(d->eng.device));
   DemodEngine& e = d->eng;
   cudaStream_t s = stream ? (cudaStream_t)stream : e.stream;
   return e.constellation_dev((const float2*)d_in, n_floats >> 1, in_stride_floats >> 1, (float2*)d_sym, sym_stride_floats >> 1,
@@ -1303,7 +1349,7 @@ int qpsk_demod_constellation_dev(qpsk_demod* d, const float* d_in, int64_t n_flo
 int qpsk_demod_loop_state(qpsk_demod* d, double* costas_theta, double* costas_freq, double* mm_mu, double* mm_integral,
                           float* fll_phase, float* fll_freq) {
   if (!d) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(d->eng.device));
   DemodEngine& e = d->eng;
   QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
   QPSK_CUDA_TRY(cudaDeviceSynchronize());
@@ -1327,7 +1373,7 @@ int qpsk_demod_loop_state(qpsk_demod* d, double* costas_theta, double* costas_fr
 
 int qpsk_demod_in_frame(qpsk_demod* d, int* in_frame) {
   if (!d || !in_frame) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(d->eng.device));
   DemodEngine& e = d->eng;
   QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
   std::vector<FramerState> fs((size_t)e.channels);

@@ -678,6 +678,7 @@ int FirEngine::init(const float* taps_in, int n_floats, int channels_in) {
   if ((n_floats & 1) != 0 || n_floats == 0) return QPSK_ERR_ARG;  // FIRFilter.cs:32-33
   if (channels_in <= 0) return QPSK_ERR_RANGE;
   QPSK_TRY(ensure_device());
+  device = current_device();
   n_taps = n_floats >> 1;
   channels = channels_in;
   taps_iq.assign(taps_in, taps_in + n_floats);
@@ -766,6 +767,13 @@ int launch_tma_cfg(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, si
   QPSK_LAUNCH_CHECK();
   return QPSK_OK;
 }
+inline const char* tma_kernel_name(bool cplx) {
+  static const char* const real_names[] = {"fir_tma_kernel<R=10,NT=256,real taps>", "fir_tma_kernel<R=10,NT=320,real taps>",
+                                           "fir_tma_kernel<R=14,NT=224,real taps>", "fir_tma_kernel<R=6,NT=256,real taps>"};
+  static const char* const cplx_names[] = {"fir_tma_kernel<R=10,NT=256,complex taps>", "fir_tma_kernel<R=10,NT=320,complex taps>",
+                                           "fir_tma_kernel<R=14,NT=224,complex taps>", "fir_tma_kernel<R=6,NT=256,complex taps>"};
+  return (cplx ? cplx_names : real_names)[fir_cfg_index()];
+}
 template <bool CPLX>
 int launch_tma(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, size_t smem, int grid, cudaStream_t s) {
   switch (fir_cfg_index()) {
@@ -783,7 +791,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t ldy, bool stateless, cudaStream_t s) {
   if (L == 0) return QPSK_OK;
   if (!x || !y) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(device));
   if (!s) s = stream;
   const int N = n_taps;
   // geometry: y[n0+q] = sum_i g[i]*xs[q+i], xs[0] = stream index n0 + advance - hl, g[i] = h[hl-i]
@@ -841,6 +849,7 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
         }
         QPSK_TRY(launch_tma<true>(a, t, smem, (int)grid, s));
       }
+      last_kernel = tma_kernel_name(!real_taps);
       if (!stateless) cur ^= 1;
       return QPSK_OK;
     }
@@ -879,6 +888,7 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
         QPSK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(int)grid, kENT + 32, smem, s>>>(a, t, N);
         QPSK_LAUNCH_CHECK();
+        last_kernel = "fir_exact_real_kernel<NT=256>";
         cur ^= 1;
         return QPSK_OK;
       }
@@ -898,6 +908,7 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
   else
     fir_generic_kernel<false><<<(int)blocks, 256, 0, s>>>(g);
   QPSK_LAUNCH_CHECK();
+  last_kernel = (mode == QPSK_FIR_EXACT && !stateless) ? "fir_generic_kernel<EXACT>" : "fir_generic_kernel";
   if (!stateless) {
     const int tot = channels * HL;
     fir_hist_update_kernel<<<(tot + 255) / 256, 256, 0, s>>>(x, ldx, L, hin, hout, channels, HL);
@@ -1038,7 +1049,7 @@ int qpsk_fir_create(const float* taps_iq, int n_floats, qpsk_fir** out) {
 }
 int qpsk_fir_destroy(qpsk_fir* f) {
   if (f) {
-    cudaSetDevice(current_device());
+    cudaSetDevice(f->eng.device);
     if (f->eng.stream) cudaStreamSynchronize(f->eng.stream);
     delete f;
   }
@@ -1046,9 +1057,15 @@ int qpsk_fir_destroy(qpsk_fir* f) {
 }
 int qpsk_fir_reset(qpsk_fir* f) {
   if (!f) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(f->eng.device));
   QPSK_TRY(f->eng.reset(f->eng.stream));
   QPSK_CUDA_TRY(cudaStreamSynchronize(f->eng.stream));
+  return QPSK_OK;
+}
+int qpsk_fir_last_kernel(const qpsk_fir* f, char* name, int cap) {
+  if (!f || !name) return QPSK_ERR_NULL;
+  if (cap < 1) return QPSK_ERR_RANGE;
+  snprintf(name, (size_t)cap, "%s", f->eng.last_kernel);
   return QPSK_OK;
 }
 int qpsk_fir_set_mode(qpsk_fir* f, int mode) {
@@ -1070,7 +1087,7 @@ int qpsk_fir_filter(qpsk_fir* f, const float* in, float* out, int64_t n_floats, 
   if (out_cap_floats < n_floats) return QPSK_ERR_ARG;      // FIRFilter.cs:83
   if (n_floats == 0) return QPSK_OK;
   if (!in || !out) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(f->eng.device));
   const int64_t L = n_floats >> 1;
   return (f->eng.channels == 1) ? fir_host_stream(f, in, out, L, false) : fir_host_batch(f, in, out, L, false);
 }
@@ -1081,7 +1098,7 @@ int qpsk_fir_fft_filter(qpsk_fir* f, const float* in, float* out, int64_t n_floa
   if ((n_floats & 1) != 0) return QPSK_ERR_ARG;            // :99
   if (n_floats == 0) return QPSK_OK;                       // :100
   if (!out) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(f->eng.device));
   const int64_t L = n_floats >> 1;
   return (f->eng.channels == 1) ? fir_host_stream(f, in, out, L, true) : fir_host_batch(f, in, out, L, true);
 }
@@ -1116,12 +1133,12 @@ int qpsk_fir_fft_filter_dev(qpsk_fir* f, const float* d_in, float* d_out, int64_
 
 int qpsk_fir_get_state(qpsk_fir* f, float* hist_iq, int64_t cap_floats) {
   if (!f) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(f->eng.device));
   return f->eng.get_state(hist_iq, cap_floats);
 }
 int qpsk_fir_set_state(qpsk_fir* f, const float* hist_iq, int64_t n_floats) {
   if (!f) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(f->eng.device));
   return f->eng.set_state(hist_iq, n_floats);
 }
 

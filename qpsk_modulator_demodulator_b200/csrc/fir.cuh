@@ -10,6 +10,7 @@ struct FirEngine {
   int n_taps = 0;          // complex taps N
   bool real_taps = false;  // every imaginary part is +-0 -> 1 FFMA2 per tap per sample
   int channels = 1;
+  int device = 0;              // ordinal the state and streams live on (fixed at init)
   int mode = QPSK_FIR_FAST;
   std::vector<float> taps_iq;  // h[j], interleaved, as given
   int HL = 0;                  // history length kept per channel (even, >= N-1)
@@ -17,6 +18,7 @@ struct FirEngine {
   int cur = 0;
   DevBuf<float> d_taps;        // [2][N] planar h (generic kernel)
   cudaStream_t stream = nullptr;  // owned
+  const char* last_kernel = "";  // the kernel the last filter call launched (measurement: bench.py names it in `roofline`)
 
   ~FirEngine();
   int init(const float* taps_iq_in, int n_floats, int channels_in);

@@ -345,6 +345,7 @@ int FllEngine::init(float sps, float rolloff, int size, float bw, int channels_i
   if (channels_in <= 0) return QPSK_ERR_RANGE;
   if (size > 2048) return QPSK_ERR_UNSUPPORTED;              // per-thread ring lives in shared memory
   QPSK_TRY(ensure_device());
+  device = current_device();
   channels = channels_in;
   n_taps = size;
   P.alpha = 0.0f;                        // :55
@@ -487,6 +488,7 @@ MmEngine::~MmEngine() {
 int MmEngine::init(double sps, double kp, double ki, int channels_in) {
   if (channels_in <= 0) return QPSK_ERR_RANGE;
   QPSK_TRY(ensure_device());
+  device = current_device();
   channels = channels_in;
   P.sps = sps; P.kp = kp; P.ki = ki;
   QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -572,6 +574,7 @@ CostasEngine::~CostasEngine() {
 int CostasEngine::init(double fs, double bw, double damping, int channels_in) {
   if (channels_in <= 0) return QPSK_ERR_RANGE;
   QPSK_TRY(ensure_device());
+  device = current_device();
   channels = channels_in;
   costas_gains(fs, bw, damping, &P.alpha, &P.beta);
   QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -643,7 +646,7 @@ int qpsk_fll_process(qpsk_fll* f, const float* in, float* out, int64_t n_floats,
   if (out_cap_floats < n_floats) return QPSK_ERR_ARG;    // :68-69
   if (n_floats == 0) return QPSK_OK;
   if (!in || !out) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(f->eng.device));
   FllEngine& e = f->eng;
   const int64_t L = n_floats >> 1;
   const size_t tot = (size_t)L * e.channels;
@@ -659,12 +662,12 @@ int qpsk_fll_process_dev(qpsk_fll* f, const float* d_in, float* d_out, int64_t n
   if (!f) return QPSK_ERR_NULL;
   if (n_floats < 0) return QPSK_ERR_RANGE;
   if ((n_floats & 1) || (is & 1) || (os & 1)) return QPSK_ERR_ARG;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(f->eng.device));
   return f->eng.process_dev((const float2*)d_in, (float2*)d_out, n_floats >> 1, is >> 1, os >> 1, (cudaStream_t)stream);
 }
 int qpsk_fll_get_state(qpsk_fll* f, float* phase, float* freq) {
   if (!f || !phase || !freq) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(f->eng.device));
   FllEngine& e = f->eng;
   std::vector<float2> h((size_t)e.channels);
   QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
@@ -674,7 +677,7 @@ int qpsk_fll_get_state(qpsk_fll* f, float* phase, float* freq) {
 }
 int qpsk_fll_set_state(qpsk_fll* f, const float* phase, const float* freq) {
   if (!f || !phase || !freq) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(f->eng.device));
   FllEngine& e = f->eng;
   std::vector<float2> h((size_t)e.channels);
   e.state_wild = false;
@@ -712,7 +715,7 @@ int qpsk_mm_process(qpsk_mm* m, const float* in, int64_t n_floats, float* out, i
   if ((n_floats & 1) != 0) return QPSK_ERR_ARG;          // MuellerMuller.cs:54-55
   if (n_floats > 0 && !in) return QPSK_ERR_NULL;
   if (cap_floats > 0 && !out) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(m->eng.device));
   MmEngine& e = m->eng;
   const int64_t L = n_floats >> 1;
   const int64_t cap_sym = cap_floats >> 1;
@@ -738,13 +741,13 @@ int qpsk_mm_process_dev(qpsk_mm* m, const float* d_in, int64_t n_floats, int64_t
   if (!m) return QPSK_ERR_NULL;
   if (n_floats < 0 || cap_floats < 0) return QPSK_ERR_RANGE;
   if ((n_floats & 1) || (is & 1) || (os & 1)) return QPSK_ERR_ARG;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(m->eng.device));
   return m->eng.process_dev((const float2*)d_in, n_floats >> 1, is >> 1, (float2*)d_out, cap_floats, os >> 1, d_n_sym,
                             (cudaStream_t)stream);
 }
 int qpsk_mm_get_state(qpsk_mm* m, int* base_index, double* mu, double* integral, int* queued) {
   if (!m) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(m->eng.device));
   MmEngine& e = m->eng;
   std::vector<MmState> h((size_t)e.channels);
   QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
@@ -786,7 +789,7 @@ int qpsk_costas_process(qpsk_costas* c, const float* in, float* out, int64_t n_f
   if (out_cap_floats < n_floats) return QPSK_ERR_ARG;    // :102-103
   if (n_floats == 0) return QPSK_OK;
   if (!in || !out) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(c->eng.device));
   CostasEngine& e = c->eng;
   const int64_t L = n_floats >> 1;
   const size_t tot = (size_t)L * e.channels;
@@ -803,12 +806,12 @@ int qpsk_costas_process_dev(qpsk_costas* c, const float* d_in, float* d_out, int
   if (!c) return QPSK_ERR_NULL;
   if (n_floats < 0) return QPSK_ERR_RANGE;
   if ((n_floats & 1) || (is & 1) || (os & 1)) return QPSK_ERR_ARG;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(c->eng.device));
   return c->eng.process_dev((const float2*)d_in, (float2*)d_out, n_floats >> 1, is >> 1, os >> 1, d_n_sym, (cudaStream_t)stream);
 }
 int qpsk_costas_get_state(qpsk_costas* c, double* theta, double* freq) {
   if (!c || !theta || !freq) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(c->eng.device));
   CostasEngine& e = c->eng;
   std::vector<CostasState> h((size_t)e.channels);
   QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));

@@ -278,6 +278,7 @@ __device__ __forceinline__ void costas_step(const CostasParams& P, const SinCosK
 // ---------------------------------------------------------------------------------------------
 struct FllEngine {
   int channels = 1, n_taps = 0;
+  int device = 0;
   FllParams P{};
   std::vector<float> lower, upper;
   DevBuf<float> d_taps;      // [2][N] reversed lower taps, planar
@@ -303,6 +304,7 @@ int fll_lane_launch(const FllParams& P, const std::vector<float>& lower, float2*
 
 struct MmEngine {
   int channels = 1;
+  int device = 0;
   MmParams P{};
   DevBuf<MmState> d_state;
   DevBuf<float2> d_queue[2];  // [C][qcap], ping-pong
@@ -319,6 +321,7 @@ struct MmEngine {
 
 struct CostasEngine {
   int channels = 1;
+  int device = 0;
   CostasParams P{};
   DevBuf<CostasState> d_state;
   cudaStream_t stream = nullptr;

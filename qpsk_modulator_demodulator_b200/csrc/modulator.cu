@@ -383,6 +383,7 @@ static int mod_pad_taps(int m) {
 // ---------------------------------------------------------------------------------------------
 struct ModEngine {
   int fs = 0, rs = 0;
+  int device = 0;
   bool diff = true, has_tsc = false;
   std::string tsc;
   std::vector<double> taps_d;
@@ -421,6 +422,7 @@ struct ModEngine {
   int init(int fs_in, int rs_in, double alpha, int span, int diff_in, const char* tsc_in) {
     if (rs_in == 0) return QPSK_ERR_RANGE;
     QPSK_TRY(ensure_device());
+    device = current_device();
     fs = fs_in; rs = rs_in; diff = diff_in != 0;
     has_tsc = !blank_or_null(tsc_in);              // :27
     if (has_tsc) tsc = tsc_in;
@@ -536,7 +538,7 @@ static int mod_bits_common(qpsk_mod* m, BitAt data_bit, int64_t n_bits, int puls
   if (e.sps <= 0) return QPSK_ERR_RANGE;                    // :116-117
   if (!iq_out) return QPSK_OK;                              // size query
   if (cap_floats < 2 * total) return QPSK_ERR_CAPACITY;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(m->eng.device));
   // one code per dibit, with the reference's `c - '0'` semantics for any character
   std::vector<uint8_t> codes((size_t)nd);
   const int64_t nt = e.has_tsc ? (int64_t)e.tsc.size() : 0;
@@ -635,7 +637,7 @@ static int mod_frames_common(qpsk_mod* m, const uint8_t* d_payloads, int64_t n_p
   if (!d_out) return QPSK_OK;                                // size query
   if (n_payload > 0 && !d_payloads) return QPSK_ERR_NULL;
   if (frames > 1 && out_stride_c < total) return QPSK_ERR_ARG;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(m->eng.device));
   QPSK_TRY(e.upload_meta(sm, ns, em, ne, s));
   ModArgs a{};
   a.mode = 0; a.payload = d_payloads; a.meta = e.d_meta.p; a.n_payload = n_payload;
@@ -656,7 +658,7 @@ int qpsk_mod_modulate_bytes(qpsk_mod* m, const uint8_t* payload, int64_t n_paylo
   *n_floats = ff;
   if (ff == 0 || !iq_out) return QPSK_OK;
   if (cap_floats < ff) return QPSK_ERR_CAPACITY;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(m->eng.device));
   cudaStream_t s = e.stream;
   QPSK_TRY(e.d_src.ensure((size_t)(n_payload > 0 ? n_payload : 1)));
   QPSK_TRY(e.d_out.ensure((size_t)(ff >> 1)));

@@ -88,6 +88,7 @@ using namespace qpsk;
 
 struct qpsk_stream {
   qpsk_demod* demod = nullptr;
+  int device = 0;
   int depth = 0;
   int64_t max_block_floats = 0, max_payload = 0;
   std::vector<uint8_t> start, end;
@@ -152,7 +153,7 @@ int stream_push_common(qpsk_stream* st, const void* data, int64_t n_items, bool 
   if ((n_items & 1) != 0) return QPSK_ERR_ARG;               // interleaved IQ (QPSKDeModulator.cs:347-348)
   if (n_items > st->max_block_floats) return QPSK_ERR_CAPACITY;
   if (n_items > 0 && !data) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(st->device));
   const int i = (int)(st->pushed % st->depth);
   qpsk_stream::Slot& s = st->slots[(size_t)i];
   QPSK_TRY(retire_slot(st, i, st->pushed - st->depth));
@@ -192,9 +193,12 @@ int qpsk_stream_create(qpsk_demod* d, int64_t max_block_floats, int64_t max_payl
   int ch = 0;
   QPSK_TRY(qpsk_demod_channels(d, &ch));
   if (ch != 1) return QPSK_ERR_UNSUPPORTED;                   // one radio stream per front-end
-  QPSK_TRY(ensure_device());
+  int dev = 0;
+  QPSK_TRY(qpsk_demod_device(d, &dev));                       // the front-end lives on the demodulator's device
+  QPSK_TRY(ensure_device(dev));
   qpsk_stream* st = new (std::nothrow) qpsk_stream();
   if (!st) return QPSK_ERR_NOMEM;
+  st->device = dev;
   st->demod = d;
   st->depth = depth;
   st->max_block_floats = max_block_floats;
@@ -231,7 +235,7 @@ int qpsk_stream_create(qpsk_demod* d, int64_t max_block_floats, int64_t max_payl
 
 int qpsk_stream_destroy(qpsk_stream* st) {
   if (st) {
-    cudaSetDevice(current_device());
+    cudaSetDevice(st->device);
     delete st;
   }
   return QPSK_OK;
@@ -257,7 +261,7 @@ int qpsk_stream_poll(qpsk_stream* st, int wait, uint8_t* payload_out, int64_t ca
   *n_bytes = 0;
   *have_block = 0;
   if (st->polled >= st->pushed) return QPSK_OK;              // nothing outstanding
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(st->device));
   const uint8_t* src = nullptr;
   long long n = 0;
   bool from_spill = false;
@@ -298,7 +302,7 @@ int qpsk_stream_poll(qpsk_stream* st, int wait, uint8_t* payload_out, int64_t ca
 
 int qpsk_stream_flush(qpsk_stream* st) {
   if (!st) return QPSK_ERR_NULL;
-  QPSK_TRY(ensure_device());
+  QPSK_TRY(ensure_device(st->device));
   QPSK_CUDA_TRY(cudaStreamSynchronize(st->s_copy));
   QPSK_CUDA_TRY(cudaStreamSynchronize(st->s_comp));
   return QPSK_OK;

@@ -184,9 +184,22 @@ class QPSKDeModulator(_Handle):
         cap = cap or max(n // 8 + 64, 64)
         out = np.zeros((self.channels, cap), np.uint8)
         nb = np.zeros(self.channels, np.int64)
-        check(lib().qpsk_demod_bytes(self._h, _ptr(x), n, _ptr(s), s.size, _ptr(e), e.size, _ptr(out), cap, _ptr(nb)))
+        st = lib().qpsk_demod_bytes(self._h, _ptr(x), n, _ptr(s), s.size, _ptr(e), e.size, _ptr(out), cap, _ptr(nb))
+        out = self._refetch(st, out, nb)
         outs = [out[c, : nb[c]].tobytes() for c in range(self.channels)]
         return outs[0] if self.channels == 1 else outs
+
+    def _refetch(self, st, out, nb):
+        """A frame that accumulated on the device over several calls can be longer than a buffer sized from this call's
+        samples (the MTU-block loop of TB/SDR/ModDemodOverSDR.cs:127-136): on QPSK_ERR_CAPACITY the completed frames are
+        still in the framer ring, so they are fetched again into a buffer of the reported size instead of being lost."""
+        if st != N.ERR_CAPACITY:
+            check(st)
+            return out
+        cap = int(nb.max())
+        out = np.zeros((self.channels, cap), np.uint8)
+        check(lib().qpsk_demod_last_payload(self._h, _ptr(out), cap, _ptr(nb)))
+        return out
 
     def FrameBits(self, bits, startMarker: bytes, endMarker: bytes, cap: int = 0):
         """The framer half of DeModulateBytes (MS/QPSKDeModulator.cs:182-259) on bits already demodulated: a '0'/'1'
@@ -205,7 +218,8 @@ class QPSKDeModulator(_Handle):
         cap = cap or max(ld // 8 + 64, 64)
         out = np.zeros((self.channels, cap), np.uint8)
         nb = np.zeros(self.channels, np.int64)
-        check(lib().qpsk_demod_frame_bits(self._h, _ptr(b), ld, _ptr(nb_in), _ptr(s), s.size, _ptr(e), e.size, _ptr(out), cap, _ptr(nb)))
+        st = lib().qpsk_demod_frame_bits(self._h, _ptr(b), ld, _ptr(nb_in), _ptr(s), s.size, _ptr(e), e.size, _ptr(out), cap, _ptr(nb))
+        out = self._refetch(st, out, nb)
         outs = [out[c, : nb[c]].tobytes() for c in range(self.channels)]
         return outs[0] if self.channels == 1 else outs
 

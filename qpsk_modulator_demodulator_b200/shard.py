@@ -42,3 +42,51 @@ def gather_counters(local_counters, dist=None, counts=None):
     parts = [torch.zeros_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded)
     return torch.cat([p[:n] for p, n in zip(parts, counts)], dim=0)
+
+
+class CounterComm:
+    """The same gather through the C ABI (qpsk_comm_* / qpsk_ber_gather, csrc/comm.cu): an NCCL communicator owned by
+    libqpskcuda.so, what a C# host would use.  `exchange(id_bytes_or_None) -> id_bytes` ships rank 0's 128-byte id to the
+    other ranks (torch.distributed broadcast in bench.py; any transport in a C# host)."""
+
+    def __init__(self, world: int, rank: int, exchange):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _native as N
+        self._N, self._C, self._np = N, C, np
+        self.world, self.rank = world, rank
+        ident = np.zeros(128, np.uint8)
+        if rank == 0:
+            N.check(N.lib().qpsk_comm_unique_id(ident.ctypes.data, 128))
+        ident = np.frombuffer(exchange(ident.tobytes() if rank == 0 else None), np.uint8).copy()
+        self._h = C.c_void_p()
+        N.check(N.lib().qpsk_comm_create(ident.ctypes.data, world, rank, C.byref(self._h)))
+
+    def info(self) -> dict:
+        C = self._C
+        n, r, v = C.c_int(), C.c_int(), C.c_int()
+        self._N.check(self._N.lib().qpsk_comm_info(self._h, C.byref(n), C.byref(r), C.byref(v)))
+        return {"n_ranks": n.value, "rank": r.value, "nccl_version": v.value}
+
+    def gather(self, d_counters: int, channels_local: int, channels_total: int):
+        """d_counters: device pointer to uint32 {errors, bits}[channels_local] (complete).  Returns the [channels_total, 2]
+        table in channel order (numpy, identical on every rank)."""
+        np = self._np
+        counts = [channel_range(r, self.world, channels_total) for r in range(self.world)]
+        width = max(b - a for a, b in counts)
+        out = np.zeros((self.world, max(width, 1), 2), np.uint32)
+        self._N.check(self._N.lib().qpsk_ber_gather(self._h, d_counters, channels_local, max(width, 1), out.ctypes.data))
+        return np.concatenate([out[r, : b - a] for r, (a, b) in enumerate(counts)], axis=0)
+
+    def close(self):
+        if self._h:
+            self._N.lib().qpsk_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

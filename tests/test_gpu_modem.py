@@ -233,8 +233,7 @@ def test_datalevel_roundtrip_matches_oracle(gpu, orc, fir_mode):
     bursts = _datalevel_bursts(orc, 8)
     od = orc.QPSKDeModulator(fs, fs // 2, ALPHA04, 10, tsc=TSC)
     gd = gpu.QPSKDeModulator(fs, fs // 2, ALPHA04, 10, tsc=TSC)
-    if fir_mode == "exact":
-        gd.set_fir_mode(gpu.FIR_EXACT)
+    gd.set_fir_mode(gpu.FIR_EXACT if fir_mode == "exact" else gpu.FIR_FAST)
     texts = []
     for y in bursts:
         want = od.DeModulateTextUtf8(y, START, STOP)
@@ -254,9 +253,8 @@ def test_datalevel_bits_and_constellation(gpu, orc, fir_mode):
     bursts = _datalevel_bursts(orc, 5, seed=11)
     od, od2 = (orc.QPSKDeModulator(fs, fs // 2, ALPHA04, 10, tsc=TSC) for _ in range(2))
     gd, gd2 = (gpu.QPSKDeModulator(fs, fs // 2, ALPHA04, 10, tsc=TSC) for _ in range(2))
-    if fir_mode == "exact":
-        gd.set_fir_mode(gpu.FIR_EXACT)
-        gd2.set_fir_mode(gpu.FIR_EXACT)
+    for g in (gd, gd2):
+        g.set_fir_mode(gpu.FIR_EXACT if fir_mode == "exact" else gpu.FIR_FAST)
     for y in bursts:
         assert gd.DeModulate(y) == od.DeModulate(y)                        # bits bit-exact
         wc, gc = od2.deModulateConstellation(y), gd2.deModulateConstellation(y)
