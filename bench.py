@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-chain", action="store_true")
+    ap.add_argument("--no-decimate", action="store_true")
     ap.add_argument("--no-scaling-legs", action="store_true", help="skip the 16384-channel strong / saturated chain legs")
     ap.add_argument("--channels-total", type=int, default=16384, help="BASELINE.json configs[3]: size of the fixed channel set")
     args = ap.parse_args()
@@ -344,6 +345,32 @@ def main():
                         "peak": hbm_peak, "unit": "GB/s", "frac": hbm_dom["hbm_frac"], "traffic": hbm_dom.get("traffic"),
                         "peak_source": f"HBM {peak_src} (MEASURED_PEAKS.json)"}
 
+    # ---- decimate-by-D matched filter (north_star (2)): 8 + 8/D B and 4N/D flop per INPUT sample ----------
+    decimate = []
+    if not args.no_decimate:
+        for span, sps, dec in ((16, 2, 2), (16, 4, 2), (16, 8, 2), (16, 4, 4), (16, 8, 8), (16, 16, 16)):
+            t = taps_for(Q, span, sps)
+            nt = t.size // 2
+            f = Q.ComplexFIRFilter(t)
+            for _ in range(2):
+                f.decimate_dev(x.data_ptr(), 2 * n, dec, y.data_ptr(), 2 * n, stream=stream)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            ev0.record()
+            for _ in range(reps):
+                f.decimate_dev(x.data_ptr(), 2 * n, dec, y.data_ptr(), 2 * n, stream=stream)
+            ev1.record()
+            torch.cuda.synchronize()
+            tms = ev0.elapsed_time(ev1) / reps
+            gbs = (8.0 + 8.0 / dec) * n / (tms * 1e-3) / 1e9
+            tf = 4.0 * nt / dec * n / (tms * 1e-3) / 1e12
+            bound = "hbm" if ((8.0 + 8.0 / dec) / (hbm_peak * 1e9)) >= (4.0 * nt / dec / (fma_peak * 1e12)) else "fma"
+            decimate.append({"taps": nt, "decim": dec, "kernel": f.last_kernel(), "ms": tms, "msamples_s_in": n / (tms * 1e-3) / 1e6,
+                             "bound": bound, "hbm_gbs": gbs, "fma_tflops": tf,
+                             "frac": gbs / hbm_peak if bound == "hbm" else tf / fma_peak,
+                             "algorithmic": "8 + 8/D B and 4*taps/D flop per input sample"})
+            del f
+
     # ---- e2e: host-pointer C ABI with pinned buffers -------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -433,7 +460,7 @@ def main():
                                    f"per GPU per tap count (BASELINE.json configs[1])",
                        "l2": "inputs 2 GiB + outputs 2 GiB per launch >> 126 MB L2; no flush needed",
                        "parallelism": f"{world} independent streams, one per GPU, no collective"},
-            "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_by_taps": roofs, "fma_peak_tflops_measured": fma_peak,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_by_taps": roofs, "decimate": decimate, "fma_peak_tflops_measured": fma_peak,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "build_id": build_id,
             "scaling_note": "`scaling: weak` refers to `value` (one independent 2^28-sample FIR stream per GPU, no communication). "

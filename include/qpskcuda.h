@@ -108,6 +108,19 @@ QPSK_API int qpsk_fir_filter_dev(qpsk_fir* f, const float* d_in, float* d_out, i
                                  int64_t in_stride_floats, int64_t out_stride_floats, void* stream);
 QPSK_API int qpsk_fir_fft_filter_dev(qpsk_fir* f, const float* d_in, float* d_out, int64_t n_floats,
                                      int64_t in_stride_floats, int64_t out_stride_floats, void* stream);
+/* Decimate-by-D matched filter (north_star item (2); SURVEY §8d "decimate-by-D variant").  The reference's matched filter is
+ * non-decimating (FIRFilter.cs:80-91, called at QPSKDeModulator.cs:360), so this is defined by it: the streaming Filter()
+ * output kept at indices 0, D, 2D, ... of the samples passed to this call since the handle's creation, its last reset or a
+ * change of D — counted ACROSS calls, so any chunking gives the same decimated stream: y_dec[m] = y[m*D].  Only the kept outputs are computed: 4N/D flop (real taps) and
+ * 8 + 8/D bytes per input sample.  Shares the delay line with qpsk_fir_filter (the calls may be mixed).  Each channel
+ * gets ceil((n - skip)/D) outputs; *n_out_floats = floats written per channel.  out_cap too small -> QPSK_ERR_CAPACITY
+ * with no state consumed.  D = 2, 4, 8, 16 with real taps in QPSK_FIR_FAST mode run fir_decim_kernel; every other case
+ * (QPSK_FIR_EXACT: bit-identical to the subsampled exact filter) filters at full rate and keeps every D-th sample. */
+QPSK_API int qpsk_fir_decimate(qpsk_fir* f, const float* iq_in, int64_t n_floats, int decim, float* iq_out,
+                               int64_t out_cap_floats, int64_t* n_out_floats);
+QPSK_API int qpsk_fir_decimate_dev(qpsk_fir* f, const float* d_in, int64_t n_floats, int64_t in_stride_floats, int decim,
+                                   float* d_out, int64_t out_cap_floats, int64_t out_stride_floats, int64_t* n_out_floats,
+                                   void* stream);
 /* delay-line checkpoint: the last N-1 inputs per channel, oldest first, [channels][2*(N-1)] */
 QPSK_API int qpsk_fir_get_state(qpsk_fir* f, float* hist_iq, int64_t cap_floats);
 QPSK_API int qpsk_fir_set_state(qpsk_fir* f, const float* hist_iq, int64_t n_floats);

@@ -84,6 +84,8 @@ def _signatures():
         "qpsk_fir_fft_filter": (i, [vp, vp, vp, i64]),
         "qpsk_fir_filter_dev": (i, [vp, vp, vp, i64, i64, i64, vp]),
         "qpsk_fir_fft_filter_dev": (i, [vp, vp, vp, i64, i64, i64, vp]),
+        "qpsk_fir_decimate": (i, [vp, vp, i64, i, vp, i64, i64p]),
+        "qpsk_fir_decimate_dev": (i, [vp, vp, i64, i64, i, vp, i64, i64, i64p, vp]),
         "qpsk_fir_get_state": (i, [vp, f32p, i64]),
         "qpsk_fir_set_state": (i, [vp, f32p, i64]),
         "qpsk_fll_design": (i, [f, f, i, f32p, f32p]),

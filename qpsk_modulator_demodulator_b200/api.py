@@ -197,6 +197,25 @@ class ComplexFIRFilter(_Handle):
         check(lib().qpsk_fir_fft_filter(self._h, _ptr(x), _ptr(y), n))
         return y
 
+    def Decimate(self, iqIn, decim: int, out_cap_floats=None):
+        """Decimate-by-D matched filter (north_star (2)): Filter() kept at stream indices 0, D, 2D, ... across calls.
+        Returns the kept samples (interleaved IQ; [channels, n] for batch handles)."""
+        x = _f32(iqIn)
+        n = x.shape[-1] if x.ndim == 2 else x.size
+        cap = (2 * ((n // 2 + decim - 1) // max(decim, 1)) + 2) if out_cap_floats is None else out_cap_floats
+        y = np.zeros((self.channels, max(cap, 0)), np.float32)
+        no = C.c_int64(0)
+        check(lib().qpsk_fir_decimate(self._h, _ptr(x), n, decim, _ptr(y), cap, C.byref(no)))
+        y = y[:, : no.value]
+        return y[0].copy() if self.channels == 1 and x.ndim == 1 else y.copy()
+
+    def decimate_dev(self, d_in: int, n_floats: int, decim: int, d_out: int, out_cap_floats: int, in_stride: int = 0,
+                     out_stride: int = 0, stream: int = 0) -> int:
+        no = C.c_int64(0)
+        check(lib().qpsk_fir_decimate_dev(self._h, d_in, n_floats, in_stride or n_floats, decim, d_out, out_cap_floats,
+                                          out_stride or out_cap_floats, C.byref(no), stream))
+        return no.value
+
     def filter_dev(self, d_in: int, d_out: int, n_floats: int, in_stride: int = 0, out_stride: int = 0, stream: int = 0):
         check(lib().qpsk_fir_filter_dev(self._h, d_in, d_out, n_floats, in_stride or n_floats, out_stride or n_floats, stream))
 

@@ -42,6 +42,10 @@ void count_launch(int n = 1);
 int current_device();          // ordinal handles created by THIS thread get: the thread's qpsk_set_device choice, else the
                                // process-wide one (last qpsk_set_device of any thread), else 0
 int ensure_device(int dev = -1);  // cudaSetDevice(dev, or current_device()) + arch check; status code
+// Raise a kernel's dynamic shared-memory limit to the device's opt-in maximum, once per (kernel, device).  The limit is a
+// per-function, per-context setting: setting it to each launch's own size from several host threads races (thread A
+// lowers it between thread B's set and launch -> cudaErrorInvalidValue on B's launch).
+int allow_max_dynamic_smem(const void* kernel);
 int device_sm_count();         // of the device the calling thread has current (call after ensure_device)
 
 // RAII device buffer

@@ -2,6 +2,9 @@
 #include <math.h>
 
 #include <atomic>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 #include "design.h"
@@ -46,6 +49,20 @@ int ensure_device(int dev) {
     }
     checked_dev = dev;
   }
+  return QPSK_OK;
+}
+
+int allow_max_dynamic_smem(const void* kernel) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  QPSK_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({kernel, dev})) return QPSK_OK;
+  int max_optin = 0;
+  QPSK_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  QPSK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+  done.insert({kernel, dev});
   return QPSK_OK;
 }
 

@@ -114,19 +114,129 @@ __device__ __forceinline__ double sel_f64(bool a, double x, double y) {
   return r;
 }
 
-template <bool DIFF>
-__global__ void __launch_bounds__(64)
+// ---- matched filter fused into the symbol-stage kernel (MFW > 0) --------------------------------------------------
+// MFW extra warps run the RRC matched filter (ComplexFIRFilter.Filter :80-91 as called at QPSKDeModulator.cs:360) in the
+// reference's own summation order — ComplexDotWindow's 8 lane partials, lanes added 0..7, then the N mod 8 tail, every
+// product and sum rounded separately (FIRFilter.cs:165-192; the same arithmetic as fir_exact_real_kernel, bit for bit) —
+// one round AHEAD of the Mueller-Muller warp, from a shared-memory ring of the last 128 RAW input samples per channel.
+// The chain then reads each input sample from HBM once (8 B / sample, the fused-ideal traffic of SURVEY §8d) and the
+// filtered samples never leave the SM: no matched-filter launch, no [channels][samples] scratch round trip.
+constexpr int kMfRing = 128;              // raw samples kept per channel (4 rounds): N - 1 <= 64 taps of history
+constexpr int kMfRingPitch = kMfRing + 1; // odd pitch (float2): the 32 channels of a warp fall in different banks
+constexpr int kMfMaxTaps = 65;
+struct MfTaps {
+  float rev[kMfMaxTaps + 7];              // rev[i] = h[N-1-i]: window element i (oldest first) meets tap rev[i]
+  int n_taps;
+};
+struct MfArgs {
+  const float2* hist_in;                  // [C][HL] delay line of the FirEngine (newest last)
+  float2* hist_out;
+  int HL;
+};
+__device__ float2 g_neg_zero2 = {-0.0f, -0.0f};
+// products rounded on their own: fma(x, g, -0) == round(x*g) exactly (the -0 addend changes neither value nor sign), and
+// with the addend loaded at run time ptxas cannot contract the product into the add that follows (it does contract
+// mul.rn.f32x2 feeding add.rn.f32x2 into one FFMA2, which would round once where the reference rounds twice)
+__device__ __forceinline__ float2 mul2_rounded(float2 x, float2 g, float2 nz) { return ffma2(x, g, nz); }
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+
+// outputs j0 .. j1-1 (< blk) of round q for this lane's channel: sample n = 32q + j, window element i = raw[n-(N-1)+i]
+__device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, const MfTaps& T, float2 nz, int q, int j0, int j1,
+                                         int blk, float2* __restrict__ out_ch) {
+  const int N = T.n_taps;
+  const int n_vec = N & ~7;
+  for (int j = j0; j < j1 && j < blk; j += 2) {
+    const int first = q * kSsBlock + j - (N - 1);
+    float2 lp[2][8];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int l = 0; l < 8; ++l) lp[r][l] = make_float2(0.f, 0.f);
+    float2 w0 = ring_ch[first & (kMfRing - 1)];
+    for (int ib = 0; ib < n_vec; ib += 8) {
+      float2 wv[9];
+      wv[0] = w0;
+#pragma unroll
+      for (int k = 1; k < 9; ++k) wv[k] = ring_ch[(first + ib + k) & (kMfRing - 1)];
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const float g = T.rev[ib + l];
+        const float2 gg = make_float2(g, g);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) lp[r][l] = add2_rn(lp[r][l], mul2_rounded(wv[l + r], gg, nz));
+      }
+      w0 = wv[8];
+    }
+    float2 acc[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int l = 0; l < 8; ++l) acc[r] = add2_rn(acc[r], lp[r][l]);            // lanes 0..7 (:176-180)
+    }
+    for (int i = n_vec; i < N; ++i) {                                             // scalar tail (:183-192)
+      const float g = T.rev[i];
+      const float2 gg = make_float2(g, g);
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+        acc[r] = add2_rn(acc[r], mul2_rounded(ring_ch[(first + i + r) & (kMfRing - 1)], gg, nz));
+    }
+    // an infinite SAMPLE makes the reference's hq*x terms NaN (hq = +0: 0 * Inf), which the real-tap reduction does not
+    // model: recompute such outputs with the full complex product (see fir_exact_real_kernel)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (!(fabsf(acc[r].x) <= 3.402823466e+38f) || !(fabsf(acc[r].y) <= 3.402823466e+38f)) {
+        float lI[8], lQ[8];
+        for (int l = 0; l < 8; ++l) lI[l] = lQ[l] = 0.f;
+        const float hq = 0.f;
+        for (int i = 0; i < n_vec; ++i) {
+          const float2 xv = ring_ch[(first + i + r) & (kMfRing - 1)];
+          const float hi = T.rev[i];
+          lI[i & 7] = __fadd_rn(lI[i & 7], __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y)));
+          lQ[i & 7] = __fadd_rn(lQ[i & 7], __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x)));
+        }
+        float aI = 0.f, aQ = 0.f;
+        for (int l = 0; l < 8; ++l) {
+          aI = __fadd_rn(aI, lI[l]);
+          aQ = __fadd_rn(aQ, lQ[l]);
+        }
+        for (int i = n_vec; i < N; ++i) {
+          const float2 xv = ring_ch[(first + i + r) & (kMfRing - 1)];
+          const float hi = T.rev[i];
+          aI = __fadd_rn(aI, __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y)));
+          aQ = __fadd_rn(aQ, __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x)));
+        }
+        acc[r] = make_float2(aI, aQ);
+      }
+    }
+    out_ch[j] = acc[0];
+    if (j + 1 < blk) out_ch[j + 1] = acc[1];
+  }
+}
+
+template <bool DIFF, int MFW>
+__global__ void __launch_bounds__(64 + 32 * MFW, MFW == 2 ? 3 : (MFW == 4 ? 2 : 1))
     symsync_decode_kernel(const MmParams MP, MmState* mm_g, const float2* __restrict__ q_in, float2* __restrict__ q_out,
                           long long qcap, const CostasParams CP, CostasState* cst_g, DiffState* dst_g, int C,
                           const float2* __restrict__ x, long long L, long long ldx, uint8_t* __restrict__ bits,
-                          long long ld_bits, long long* n_bits, int* n_sym_g, int append) {
+                          long long ld_bits, long long* n_bits, int* n_sym_g, int append, const __grid_constant__ MfTaps MT,
+                          const MfArgs MA) {
+  // MFW > 0: x is the RAW input (or the FLL output) and MFW extra warps run the matched filter one round ahead; MFW == 0:
+  // x is the matched-filter output (MT / MA unused).
   // append != 0: this launch continues a call split into time chunks (DemodEngine::bits_dev): bits and counts go on
   // from where the previous chunk left them.  A chunk boundary on a multiple of kSsBlock samples is exactly a round
   // boundary of the single launch (same carried samples, same rebased base_index), so the split is bit-neutral.
   constexpr bool diff = DIFF;
   __shared__ SsSmem sm;
+  extern __shared__ __align__(16) float2 mf_ring[];   // [32][kMfRingPitch] when MFW > 0
   const int lane = threadIdx.x & 31;
-  const int role = threadIdx.x >> 5;                // 0: symbol sync, 1: Costas + decode
+  const int role = threadIdx.x >> 5;                // 0: symbol sync, 1: Costas + decode, 2..: matched filter
   const int c0 = blockIdx.x * 32;
   const int c_raw = c0 + lane;
   const bool live = c_raw < C;
@@ -147,17 +257,25 @@ __global__ void __launch_bounds__(64)
   auto stage = [&](int r) {                          // lane i copies sample 32r+i of every channel of the CTA
     const long long n0 = (long long)r * kSsBlock;
     const int blk = (int)((L - n0) < kSsBlock ? (L - n0) : kSsBlock);
-    float2* dst = sm.raw[r & 1];
+    // MFW == 0: straight into the round's double buffer; MFW > 0: into the raw ring (slot = sample index mod 128)
+    float2* dst = (MFW > 0) ? (mf_ring + ((int)(n0 + lane) & (kMfRing - 1))) : (sm.raw[r & 1] + lane);
+    constexpr int pitch = (MFW > 0) ? kMfRingPitch : kSsPitch;
     if (lane < blk) {
 #pragma unroll 8
       for (int j = 0; j < 32; ++j) {
         int ch = c0 + j;
         if (ch >= C) ch = C - 1;
-        cp_async8(dst + j * kSsPitch + lane, x + (long long)ch * ldx + n0 + lane);
+        cp_async8(dst + j * pitch, x + (long long)ch * ldx + n0 + lane);
       }
     }
     cp_async_commit();
   };
+  constexpr int kAhead = (MFW > 0) ? 2 : 1;          // rounds the staging runs ahead of the Mueller-Muller warp
+  float2 nz = make_float2(0.f, 0.f);
+  if (MFW > 0 && role >= 2) {
+    asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(nz.x), "=f"(nz.y) : "l"(&g_neg_zero2));
+  }
+  const int mf_per = (MFW > 0) ? (kSsBlock / (MFW > 0 ? MFW : 1)) : 0;   // outputs per matched-filter warp and round
 
   // The Costas warp (which has the slack) also stages the samples: round r+1 is requested at the top of round r and
   // waited for before the barrier that ends it, so the Mueller-Muller warp finds its round in shared memory.
@@ -166,13 +284,26 @@ __global__ void __launch_bounds__(64)
     if (append) n_sym = n_sym_g[c];
     carried = S.queued;                              // host guarantees <= kSsCarry
     for (int i = 0; i < carried; ++i) sm.carry[lane * kSsCarry + i] = q_in[(long long)c * qcap + i];
-  } else {
+  } else if (role == 1) {
     if (rounds > 0) stage(0);
+    if (MFW > 0 && rounds > 1) stage(1);
     K = cst_g[c];
     D = dst_g[c];
     cp_async_wait<0>();
+  } else {
+    // the filter's delay line: samples -1 .. -(N-1) of this call are the newest entries of the FirEngine history
+    for (int k = 1; k < MT.n_taps; ++k)
+      if ((k - 1) % MFW == role - 2)
+        mf_ring[lane * kMfRingPitch + ((-k) & (kMfRing - 1))] = MA.hist_in[(long long)c * MA.HL + MA.HL - k];
   }
   __syncthreads();
+  if (MFW > 0) {
+    if (role >= 2 && rounds > 0) {
+      const int blk0 = (int)(L < kSsBlock ? L : kSsBlock);
+      mf_round(mf_ring + lane * kMfRingPitch, MT, nz, 0, (role - 2) * mf_per, (role - 1) * mf_per, blk0, sm.raw[0] + lane * kSsPitch);
+    }
+    __syncthreads();
+  }
   // Mueller-Muller loop registers.  The previous decision is +-1 and only ever multiplies (:78), so it is kept as a
   // sign; the previous sample is kept widened (it only appears as (double)dec * prevSample, :79).
   bool prevNegI = S.prevDI < 0.f, prevNegQ = S.prevDQ < 0.f;
@@ -256,8 +387,14 @@ __global__ void __launch_bounds__(64)
         carried = remain;
         S.base_index -= consumed;
       }
+    } else if (role == 1) {
+      if (r + kAhead < rounds) stage(r + kAhead);    // in flight during this round's Costas work
     } else if (r + 1 < rounds) {
-      stage(r + 1);                                  // in flight during this round's Costas work
+      // matched filter of round r+1 (its raw samples landed before the barrier that ended round r-1)
+      const long long n1 = (long long)(r + 1) * kSsBlock;
+      const int blk1 = (int)((L - n1) < kSsBlock ? (L - n1) : kSsBlock);
+      mf_round(mf_ring + lane * kMfRingPitch, MT, nz, r + 1, (role - 2) * mf_per, (role - 1) * mf_per, blk1,
+               sm.raw[(r + 1) & 1] + lane * kSsPitch);
     }
     if (role == 1 && r >= 1) {
       // ---- Costas + decision + differential decode (QPSKDeModulator.cs:374-408) on round r-1 ----
@@ -352,10 +489,16 @@ __global__ void __launch_bounds__(64)
       S.queued = carried;
       mm_g[c] = S;
       n_sym_g[c] = n_sym;
-    } else {
+    } else if (role == 1) {
       cst_g[c] = K;
       dst_g[c] = D;
       n_bits[c] = nb;
+    } else {
+      // the delay line after this call: the last HL samples of (history ++ x), as FirEngine keeps it
+      for (int i = role - 2; i < MA.HL; i += (MFW > 0 ? MFW : 1)) {
+        const long long m = L - MA.HL + i;
+        MA.hist_out[(long long)c * MA.HL + i] = (m < 0) ? MA.hist_in[(long long)c * MA.HL + MA.HL + m] : x[(long long)c * ldx + m];
+      }
     }
   }
 }
@@ -871,6 +1014,57 @@ struct DemodEngine {
   // the fused MM -> Costas -> decode kernel applies when no call can run out of output room and the MM
   // queue holds at most kSsCarry samples (always true once every call has had room)
   bool can_fuse() const { return fuse && (sps - 0.1 > 1.0) && mm.q_bound <= kSsCarry; }
+  // ... and it takes the matched filter in as well (MFW extra warps, see symsync_decode_kernel) when the filter runs in
+  // the reference's summation order (the demodulator's default), has real taps and at most 65 of them.
+  // QPSK_DEMOD_FUSE_MF=0 keeps the separate matched-filter launch (A/B runs).
+  bool can_fuse_mf() const {
+    static const bool env_on = [] {
+      const char* e = getenv("QPSK_DEMOD_FUSE_MF");
+      return !(e && e[0] == '0');
+    }();
+    return env_on && mf.mode == QPSK_FIR_EXACT && mf.real_taps && mf.n_taps <= kMfMaxTaps && mf.n_taps >= 1;
+  }
+  int mf_warps() const { return mf.n_taps <= 24 ? 2 : 4; }
+
+  // one launch of the symbol-stage kernel over `len` samples at `xin` (matched-filter output, or — with_mf — its input)
+  int launch_symsync(const float2* xin, int64_t len, int64_t ldin, uint8_t* raw, long long ld_raw, long long* n_raw, int append,
+                     bool with_mf, cudaStream_t s) {
+    MfTaps mt;
+    memset(&mt, 0, sizeof mt);
+    MfArgs ma;
+    ma.hist_in = nullptr; ma.hist_out = nullptr; ma.HL = 0;
+    const int grid = (channels + 31) / 32;
+#define QPSK_SS_ARGS mm.P, mm.d_state.p, mm.d_queue[mm.qcur].p, mm.d_queue[mm.qcur ^ 1].p, mm.qcap, costas.P, costas.d_state.p, \
+                     d_diff.p, channels, xin, len, ldin, raw, ld_raw, n_raw, d_nsym.p, append, mt, ma
+    if (!with_mf) {
+      if (diff) symsync_decode_kernel<true, 0><<<grid, 64, 0, s>>>(QPSK_SS_ARGS);
+      else symsync_decode_kernel<false, 0><<<grid, 64, 0, s>>>(QPSK_SS_ARGS);
+    } else {
+      const int N = mf.n_taps;
+      mt.n_taps = N;
+      for (int i = 0; i < N; ++i) mt.rev[i] = mf.taps_iq[2 * (N - 1 - i)];
+      ma.hist_in = mf.hist[mf.cur].p; ma.hist_out = mf.hist[mf.cur ^ 1].p; ma.HL = mf.HL;
+      const size_t smem = (size_t)32 * kMfRingPitch * sizeof(float2);
+      const int w = mf_warps();
+      const void* kp = nullptr;
+      if (w == 2) kp = diff ? (const void*)symsync_decode_kernel<true, 2> : (const void*)symsync_decode_kernel<false, 2>;
+      else kp = diff ? (const void*)symsync_decode_kernel<true, 4> : (const void*)symsync_decode_kernel<false, 4>;
+      QPSK_TRY(allow_max_dynamic_smem(kp));
+      if (w == 2) {
+        if (diff) symsync_decode_kernel<true, 2><<<grid, 128, smem, s>>>(QPSK_SS_ARGS);
+        else symsync_decode_kernel<false, 2><<<grid, 128, smem, s>>>(QPSK_SS_ARGS);
+      } else {
+        if (diff) symsync_decode_kernel<true, 4><<<grid, 192, smem, s>>>(QPSK_SS_ARGS);
+        else symsync_decode_kernel<false, 4><<<grid, 192, smem, s>>>(QPSK_SS_ARGS);
+      }
+      mf.cur ^= 1;                                   // the kernel left the advanced delay line in the other buffer
+    }
+#undef QPSK_SS_ARGS
+    QPSK_LAUNCH_CHECK();
+    mm.qcur ^= 1;
+    mm.q_bound = 4;
+    return QPSK_OK;
+  }
 
   // DeModulate: bits (bytes 0/1) to out [C][ld_out], counts to n_out[C]
   int bits_dev(const float2* x, int64_t L, int64_t ldx, uint8_t* out, int64_t ld_out, long long* n_out, cudaStream_t s) {
@@ -887,17 +1081,35 @@ struct DemodEngine {
       if (!has_tsc && ((reinterpret_cast<uintptr_t>(out) & 1) || (ld_out & 1))) return QPSK_ERR_ARG;   // uchar2 stores
     }
     const bool fused = can_fuse();
+    const bool fuse_mf = fused && can_fuse_mf();
     const int chunks = (fused && use_fll) ? pipeline_chunks(L) : 1;
+    const float2* sym_in = nullptr;                  // what the symbol-stage kernel reads in the single-launch case
+    int64_t sym_in_ld = 0;
     if (chunks > 1) {
       // sizes only; the front end runs chunk by chunk below
       const int64_t ld = L + (L & 1);
-      QPSK_TRY(t_rrc.ensure((size_t)ld * channels));
+      if (!fuse_mf) QPSK_TRY(t_rrc.ensure((size_t)ld * channels));
       QPSK_TRY(t_fll.ensure((size_t)ld * channels));
       sym_ld = symbols_bound(L);
       if (sym_ld < 1) sym_ld = 1;
       mf_ld = ld;
+    } else if (fuse_mf) {
+      // FLL (when on) in front; the matched filter runs inside the symbol-stage kernel
+      const int64_t ld = L + (L & 1);
+      sym_ld = symbols_bound(L);
+      if (sym_ld < 1) sym_ld = 1;
+      sym_in = x;
+      sym_in_ld = ldx;
+      if (use_fll) {
+        QPSK_TRY(t_fll.ensure((size_t)ld * channels));
+        QPSK_TRY(fll.process_dev(x, t_fll.p, L, ldx, ld, s));   // the call at :359
+        sym_in = t_fll.p;
+        sym_in_ld = ld;
+      }
     } else {
       QPSK_TRY(front(x, L, ldx, s, !fused));
+      sym_in = t_rrc.p;
+      sym_in_ld = mf_ld;
     }
     const long long need = 2 * sym_ld;
     if (ld_out < need) return QPSK_ERR_CAPACITY;
@@ -916,7 +1128,6 @@ struct DemodEngine {
       // differential reference), so the split changes nothing but the schedule.
       QPSK_TRY(mm.ensure_queue(8, s));
       QPSK_TRY(ensure_pipeline(chunks));
-      auto kern = diff ? symsync_decode_kernel<true> : symsync_decode_kernel<false>;
       // equal chunks except a half-size last one: the FLL on the side stream is the critical resource throughout, so
       // what is left exposed at the end is the last chunk's MM -> Costas -> decode
       const int64_t step = ((2 * L + 2 * chunks - 2) / (2 * chunks - 1) + kSsBlock - 1) / kSsBlock * kSsBlock;
@@ -926,25 +1137,14 @@ struct DemodEngine {
       for (int64_t n0 = 0; n0 < L; n0 += step, ++t) {
         const int64_t len = (L - n0 < step) ? (L - n0) : step;
         QPSK_TRY(fll.process_dev(x + n0, t_fll.p + n0, len, ldx, mf_ld, side));        // the call at :359
-        QPSK_TRY(mf.filter_dev(t_fll.p + n0, t_rrc.p + n0, len, mf_ld, mf_ld, side));  // :360
+        if (!fuse_mf) QPSK_TRY(mf.filter_dev(t_fll.p + n0, t_rrc.p + n0, len, mf_ld, mf_ld, side));  // :360
         QPSK_CUDA_TRY(cudaEventRecord(ev_chunk[(size_t)t], side));
         QPSK_CUDA_TRY(cudaStreamWaitEvent(s, ev_chunk[(size_t)t], 0));
-        kern<<<(channels + 31) / 32, 64, 0, s>>>(mm.P, mm.d_state.p, mm.d_queue[mm.qcur].p, mm.d_queue[mm.qcur ^ 1].p,
-                                                mm.qcap, costas.P, costas.d_state.p, d_diff.p, channels, t_rrc.p + n0, len,
-                                                mf_ld, raw, ld_raw, n_raw, d_nsym.p, t > 0 ? 1 : 0);
-        QPSK_LAUNCH_CHECK();
-        mm.qcur ^= 1;
+        QPSK_TRY(launch_symsync((fuse_mf ? t_fll.p : t_rrc.p) + n0, len, mf_ld, raw, ld_raw, n_raw, t > 0 ? 1 : 0, fuse_mf, s));
       }
-      mm.q_bound = 4;
     } else if (fused) {
       QPSK_TRY(mm.ensure_queue(8, s));
-      auto kern = diff ? symsync_decode_kernel<true> : symsync_decode_kernel<false>;
-      kern<<<(channels + 31) / 32, 64, 0, s>>>(mm.P, mm.d_state.p, mm.d_queue[mm.qcur].p, mm.d_queue[mm.qcur ^ 1].p, mm.qcap,
-                                              costas.P, costas.d_state.p, d_diff.p, channels, t_rrc.p, L, mf_ld, raw, ld_raw,
-                                              n_raw, d_nsym.p, 0);
-      QPSK_LAUNCH_CHECK();
-      mm.qcur ^= 1;
-      mm.q_bound = 4;
+      QPSK_TRY(launch_symsync(sym_in, L, sym_in_ld, raw, ld_raw, n_raw, 0, fuse_mf, s));
     } else {
       decode_kernel<<<(channels + 31) / 32, 32, 0, s>>>(costas.P, costas.d_state.p, d_diff.p, channels, t_sym.p, sym_ld,
                                                         d_nsym.p, diff ? 1 : 0, raw, ld_raw, n_raw);
@@ -956,7 +1156,7 @@ struct DemodEngine {
       const int words_per_row = (int)((row_bytes + 31) / 32 + 4);          // packed bits of a row + two zero words
       const size_t smem = (size_t)4 * (row_bytes + ((T + 15) & ~15)) + (size_t)4 * words_per_row * sizeof(uint32_t);
       if (smem <= 160 * 1024 && (ld_raw & 15) == 0) {
-        QPSK_CUDA_TRY(cudaFuncSetAttribute(tsc_strip_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QPSK_TRY(allow_max_dynamic_smem((const void*)tsc_strip_smem_kernel));
         tsc_strip_smem_kernel<<<(channels + 3) / 4, 128, smem, s>>>(raw, ld_raw, n_raw, d_tsc.p, T, out, ld_out, n_out, channels,
                                                                    (int)row_bytes, words_per_row);
       } else {

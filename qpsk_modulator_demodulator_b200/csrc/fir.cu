@@ -666,6 +666,133 @@ __global__ void fir_hist_update_kernel(const float2* x, long long ldx, long long
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fir_decim_kernel: decimate-by-D streaming FIR, real taps (north_star (2), SURVEY §8d "decimate-by-D variant")
+// ---------------------------------------------------------------------------------------------
+// y_dec[m] = y[skip + m*D], y the full-rate streaming output of Filter() (FIRFilter.cs:80-91; the reference's matched
+// filter is non-decimating, so the oracle is its output subsampled).  Only the kept outputs are computed: 4N/D flop and
+// 8 + 8/D bytes per INPUT sample.  Polyphase form: with tap index i = k*D + p,
+//     y_dec[m] = sum_p sum_k g[k*D + p] * x_p[m + k],     x_p[j] = xs[j*D + p]
+// i.e. D non-decimating sub-filters of K = ceil(G/D) taps, each on one phase of the input.  A thread owns RO consecutive
+// decimated outputs and, phase pair by phase pair (one LDS.128 = phases p, p+1 of one input position), slides a register
+// window over k: 2*RO packed FFMA2 per LDS.128, the same ratio as fir_tma_kernel.
+// Staging: the tile (+ halo) is read with coalesced 8-byte loads into a PADDED shared-memory layout — 16 bytes after every
+// thread span of RO*D samples when D >= 4 — so that the thread stride in 16-byte chunks is odd (RO*D/2 + 1; RO*D/2 = 7
+// itself for D = 2) and the LDS.128 of a quarter-warp fall in 8 different bank groups for every D.  A dense (TMA) layout
+// cannot be conflict-free here: RO*D/2 is even for every D >= 4.  No mbarrier ring: 2-3 resident CTAs per SM overlap one
+// CTA's loads with another's FFMA2 stream (the kernel is HBM-bound for all but D = 2 with long filters).
+struct DecArgs {
+  const float2* x;
+  float2* y;
+  long long ldx, ldy, L;       // input samples per channel
+  const float2* hist_in;       // [C][HL]
+  long long n_out;             // decimated outputs per channel
+  long long total_tiles;
+  int tiles_per_ch;
+  int HL, K, skip;             // K polyphase taps per phase; first kept output at input index `skip`
+};
+
+template <int RO, int NSTEP, int DEC>
+__device__ __forceinline__ void dec_block(const float2* __restrict__ xk, const TapsReal& taps, int t0, float2 (&wA)[2 * RO],
+                                          float2 (&wB)[2 * RO], float2 (&acc)[RO]) {
+  // NSTEP (<= 2*RO) polyphase taps starting at k0 (t0 = k0*DEC + 2*pair); on entry slots 0..RO-1 of the circular windows
+  // hold elements k0 .. k0+RO-1 of the two phases; xk = address of element k0 (first phase), pads not yet applied.
+  constexpr int W = 2 * RO;
+  constexpr int PADS = (DEC == 2) ? 0 : 2;
+#pragma unroll
+  for (int kk = 0; kk < NSTEP; ++kk) {
+    // element k0 + kk + RO: (kk + RO) / RO thread spans further on
+    const float4 v = *reinterpret_cast<const float4*>(xk + (kk + RO) * DEC + PADS * ((kk + RO) / RO));
+    wA[(kk + RO) % W] = make_float2(v.x, v.y);
+    wB[(kk + RO) % W] = make_float2(v.z, v.w);
+    const float ga = taps.g[t0 + kk * DEC], gb = taps.g[t0 + kk * DEC + 1];
+    const float2 gga = make_float2(ga, ga), ggb = make_float2(gb, gb);
+#pragma unroll
+    for (int r = 0; r < RO; ++r) {
+      acc[r] = ffma2(wA[(kk + r) % W], gga, acc[r]);
+      acc[r] = ffma2(wB[(kk + r) % W], ggb, acc[r]);
+    }
+  }
+}
+
+template <int RO, int NT, int DEC>
+__global__ void __launch_bounds__(NT, 2)
+    fir_decim_kernel(const __grid_constant__ DecArgs a, const __grid_constant__ TapsReal taps) {
+  static_assert(DEC % 2 == 0, "phases are handled in pairs (one LDS.128)");
+  constexpr int SPAN = RO * DEC;                 // input samples under one thread's outputs
+  constexpr int PADS = (DEC == 2) ? 0 : 2;       // float2 slots of padding after every span
+  constexpr int PITCH = SPAN + PADS;
+  constexpr int T_OUT = RO * NT;
+  constexpr int W = 2 * RO;
+  extern __shared__ __align__(16) unsigned char smem_dec[];
+  float2* xs = reinterpret_cast<float2*>(smem_dec);
+  const int tid = threadIdx.x;
+  const int K = a.K;
+  const int E = (T_OUT + K) * DEC;               // staged samples: the tile, the halo and the window's one-step look-ahead
+  for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+    const int ch = (int)(tile / a.tiles_per_ch);
+    const int kt = (int)(tile - (long long)ch * a.tiles_per_ch);
+    const long long m0 = (long long)kt * T_OUT;
+    const long long s0 = (long long)a.skip + m0 * DEC - a.HL;          // stream index of logical xs[0]
+    const float2* xch = a.x + (long long)ch * a.ldx;
+    const float2* hch = a.hist_in + (long long)ch * a.HL;
+    for (int e = tid; e < E; e += NT) {
+      const long long s = s0 + e;
+      float2 v = make_float2(0.f, 0.f);
+      if (s < 0) {
+        if (s >= -(long long)a.HL) v = hch[a.HL + s];
+      } else if (s < a.L) {
+        v = xch[s];
+      }
+      xs[e + PADS * (e / SPAN)] = v;
+    }
+    __syncthreads();
+    float2 acc[RO];
+#pragma unroll
+    for (int r = 0; r < RO; ++r) acc[r] = make_float2(0.f, 0.f);
+    const float2* xb = xs + tid * PITCH;
+    for (int pair = 0; pair < DEC / 2; ++pair) {
+      float2 wA[W], wB[W];
+      const float2* xp = xb + 2 * pair;
+#pragma unroll
+      for (int j = 0; j < RO; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(xp + j * DEC);
+        wA[j] = make_float2(v.x, v.y);
+        wB[j] = make_float2(v.z, v.w);
+      }
+      int k0 = 0;
+      for (; k0 + W <= K; k0 += W)               // k0 is a multiple of 2*RO: element k0 lies k0/RO spans further on
+        dec_block<RO, W, DEC>(xp + k0 * DEC + PADS * (k0 / RO), taps, k0 * DEC + 2 * pair, wA, wB, acc);
+      const float2* xk = xp + k0 * DEC + PADS * (k0 / RO);
+      const int t0 = k0 * DEC + 2 * pair;
+      switch (K - k0) {
+#define QPSK_DTAIL(S) case S: dec_block<RO, (S < W ? S : 0), DEC>(xk, taps, t0, wA, wB, acc); break;
+        QPSK_DTAIL(1) QPSK_DTAIL(2) QPSK_DTAIL(3) QPSK_DTAIL(4) QPSK_DTAIL(5) QPSK_DTAIL(6) QPSK_DTAIL(7) QPSK_DTAIL(8)
+        QPSK_DTAIL(9) QPSK_DTAIL(10) QPSK_DTAIL(11) QPSK_DTAIL(12) QPSK_DTAIL(13)
+#undef QPSK_DTAIL
+        default: break;
+      }
+    }
+    float2* yc = a.y + (long long)ch * a.ldy + m0 + (long long)tid * RO;
+    const long long left = a.n_out - (m0 + (long long)tid * RO);
+#pragma unroll
+    for (int r = 0; r < RO; ++r)
+      if (r < left) yc[r] = acc[r];
+    __syncthreads();                             // the tile's samples are dead: the next tile may overwrite them
+  }
+}
+
+__global__ void fir_subsample_kernel(const float2* __restrict__ y, long long ldy, long long skip, int dec, long long n_out,
+                                     float2* __restrict__ out, long long ldo, int C) {
+  const long long total = (long long)C * n_out;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx / n_out);
+    const long long m = idx - (long long)ch * n_out;
+    out[(long long)ch * ldo + m] = y[(long long)ch * ldy + skip + m * dec];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // FirEngine
 // ---------------------------------------------------------------------------------------------
@@ -706,6 +833,7 @@ int FirEngine::reset(cudaStream_t s) {
   QPSK_TRY(hist[0].zero(s));
   QPSK_TRY(hist[1].zero(s));
   cur = 0;
+  dec_skip = 0;
   return QPSK_OK;
 }
 
@@ -762,7 +890,7 @@ inline int fir_cfg_index() {
 template <int R, int NT, bool CPLX>
 int launch_tma_cfg(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, size_t smem, int grid, cudaStream_t s) {
   auto kern = fir_tma_kernel<R, NT, CPLX>;
-  QPSK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  QPSK_TRY(allow_max_dynamic_smem((const void*)kern));
   kern<<<grid, NT + 32, smem, s>>>(a, taps);
   QPSK_LAUNCH_CHECK();
   return QPSK_OK;
@@ -885,7 +1013,7 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
           t.g[i] = (j < N) ? taps_iq[2 * j] : 0.0f;
         }
         auto kern = fir_exact_real_kernel<kENT>;
-        QPSK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QPSK_TRY(allow_max_dynamic_smem((const void*)kern));
         kern<<<(int)grid, kENT + 32, smem, s>>>(a, t, N);
         QPSK_LAUNCH_CHECK();
         last_kernel = "fir_exact_real_kernel<NT=256>";
@@ -915,6 +1043,90 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
     QPSK_LAUNCH_CHECK();
     cur ^= 1;
   }
+  return QPSK_OK;
+}
+
+
+int FirEngine::decimate_dev(const float2* x, int64_t L, int64_t ldx, int dec, float2* y, int64_t cap, int64_t ldy, int64_t* n_out,
+                            cudaStream_t s) {
+  if (!n_out) return QPSK_ERR_NULL;
+  *n_out = 0;
+  if (dec < 1) return QPSK_ERR_RANGE;
+  if (dec != dec_last) {          // a new decimation factor restarts the phase at the next input sample
+    dec_skip = 0;
+    dec_last = dec;
+  }
+  const int64_t nout = (L > dec_skip) ? (L - dec_skip + dec - 1) / dec : 0;
+  if (cap < nout) return QPSK_ERR_CAPACITY;          // before anything advances
+  if (L == 0) return QPSK_OK;
+  if (!x || (nout > 0 && !y)) return QPSK_ERR_NULL;
+  QPSK_TRY(ensure_device(device));
+  if (!s) s = stream;
+  const int64_t skip = dec_skip;
+  const int N = n_taps;
+  int K = (HL + 1 + dec - 1) / dec;
+  const bool fast = mode == QPSK_FIR_FAST && real_taps && (dec == 2 || dec == 4 || dec == 8 || dec == 16) &&
+                    (long long)K * dec <= kMaxG && nout > 0;
+  bool launched = false;
+  if (fast) {
+    DecArgs a;
+    a.x = x; a.y = y; a.ldx = ldx; a.ldy = ldy; a.L = L;
+    a.hist_in = hist[cur].p; a.n_out = nout; a.HL = HL; a.skip = (int)skip; a.K = K; a.tiles_per_ch = 0; a.total_tiles = 0;
+    TapsReal t;
+    memset(&t, 0, sizeof t);
+    for (int i = 0; i <= HL; ++i) {
+      const int j = HL - i;
+      t.g[i] = (j < N) ? taps_iq[2 * j] : 0.0f;
+    }
+    auto go = [&](auto kern, int T_OUT, int SPAN, int PADS) -> int {
+      a.tiles_per_ch = (int)((nout + T_OUT - 1) / T_OUT);
+      a.total_tiles = (long long)a.tiles_per_ch * channels;
+      const int E = (T_OUT + K) * dec;
+      const size_t smem = (size_t)(E + PADS * (E / SPAN + 1)) * sizeof(float2);
+      if (smem > 200 * 1024) return QPSK_ERR_UNSUPPORTED;
+      QPSK_TRY(allow_max_dynamic_smem((const void*)kern));
+      long long per_sm = (long long)(224 * 1024) / (long long)(smem + 1024);
+      if (per_sm > 3) per_sm = 3;
+      if (per_sm < 1) per_sm = 1;
+      long long grid = per_sm * device_sm_count();
+      if (grid > a.total_tiles) grid = a.total_tiles;
+      kern<<<(int)grid, (dec == 2 || dec == 4) ? 256 : (dec == 8 ? 128 : 64), smem, s>>>(a, t);
+      QPSK_LAUNCH_CHECK();
+      return QPSK_OK;
+    };
+    int st = QPSK_ERR_UNSUPPORTED;
+    switch (dec) {
+      case 2: st = go(fir_decim_kernel<7, 256, 2>, 7 * 256, 14, 0); last_kernel = "fir_decim_kernel<RO=7,NT=256,D=2>"; break;
+      case 4: st = go(fir_decim_kernel<7, 256, 4>, 7 * 256, 28, 2); last_kernel = "fir_decim_kernel<RO=7,NT=256,D=4>"; break;
+      case 8: st = go(fir_decim_kernel<7, 128, 8>, 7 * 128, 56, 2); last_kernel = "fir_decim_kernel<RO=7,NT=128,D=8>"; break;
+      case 16: st = go(fir_decim_kernel<7, 64, 16>, 7 * 64, 112, 2); last_kernel = "fir_decim_kernel<RO=7,NT=64,D=16>"; break;
+    }
+    if (st == QPSK_OK) launched = true;
+    else if (st != QPSK_ERR_UNSUPPORTED) return st;
+  }
+  if (launched) {
+    // the delay line advances exactly as Filter() would advance it
+    const int tot = channels * HL;
+    fir_hist_update_kernel<<<(tot + 255) / 256, 256, 0, s>>>(x, ldx, L, hist[cur].p, hist[cur ^ 1].p, channels, HL);
+    QPSK_LAUNCH_CHECK();
+    cur ^= 1;
+  } else {
+    // any other case (complex taps, QPSK_FIR_EXACT, odd or large D, very long filters): the full-rate filter into
+    // scratch, then the kept samples — same values by construction
+    const int64_t ld = L + (L & 1);
+    QPSK_TRY(dec_tmp.ensure((size_t)ld * channels));
+    QPSK_TRY(run(x, dec_tmp.p, L, ldx, ld, false, s));
+    if (nout > 0) {
+      const long long total = (long long)channels * nout;
+      long long blocks = (total + 255) / 256;
+      const long long capb = 32LL * device_sm_count();
+      if (blocks > capb) blocks = capb;
+      fir_subsample_kernel<<<(int)blocks, 256, 0, s>>>(dec_tmp.p, ld, skip, dec, nout, y, ldy, channels);
+      QPSK_LAUNCH_CHECK();
+    }
+  }
+  dec_skip = (L > skip) ? (skip + nout * dec - L) : (skip - L);
+  *n_out = nout;
   return QPSK_OK;
 }
 
@@ -1090,6 +1302,56 @@ int qpsk_fir_filter(qpsk_fir* f, const float* in, float* out, int64_t n_floats, 
   QPSK_TRY(ensure_device(f->eng.device));
   const int64_t L = n_floats >> 1;
   return (f->eng.channels == 1) ? fir_host_stream(f, in, out, L, false) : fir_host_batch(f, in, out, L, false);
+}
+
+
+// decimating matched filter (north_star (2)): host pointers, [channels][n_floats] in, [channels][out_cap_floats] out
+int qpsk_fir_decimate(qpsk_fir* f, const float* in, int64_t n_floats, int decim, float* out, int64_t out_cap_floats,
+                      int64_t* n_out_floats) {
+  if (!f || !n_out_floats) return QPSK_ERR_NULL;
+  *n_out_floats = 0;
+  if (n_floats < 0 || decim < 1 || out_cap_floats < 0) return QPSK_ERR_RANGE;
+  if ((n_floats & 1) != 0) return QPSK_ERR_ARG;            // FIRFilter.cs:82
+  if (n_floats == 0) return QPSK_OK;
+  if (!in) return QPSK_ERR_NULL;
+  FirEngine& e = f->eng;
+  QPSK_TRY(ensure_device(e.device));
+  const int64_t L = n_floats >> 1, ld = L + (L & 1);
+  const int64_t cap = out_cap_floats >> 1;
+  const int64_t ldo = (L + decim - 1) / decim + 2;
+  QPSK_TRY(f->d_in[0].ensure((size_t)ld * e.channels));
+  QPSK_TRY(f->d_out[0].ensure((size_t)ldo * e.channels));
+  int64_t nout = 0;
+  // capacity is judged inside decimate_dev before any state moves; the staging copy does not touch the handle's state
+  QPSK_CUDA_TRY(cudaMemcpy2DAsync(f->d_in[0].p, (size_t)ld * 8, in, (size_t)L * 8, (size_t)L * 8, (size_t)e.channels,
+                                  cudaMemcpyHostToDevice, e.stream));
+  QPSK_TRY(e.decimate_dev(f->d_in[0].p, L, ld, decim, f->d_out[0].p, cap < ldo ? cap : ldo, ldo, &nout, e.stream));
+  if (nout > 0) {
+    if (!out) return QPSK_ERR_NULL;
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)out_cap_floats * 4, f->d_out[0].p, (size_t)ldo * 8, (size_t)nout * 8,
+                                    (size_t)e.channels, cudaMemcpyDeviceToHost, e.stream));
+  }
+  QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
+  *n_out_floats = 2 * nout;
+  return QPSK_OK;
+}
+
+int qpsk_fir_decimate_dev(qpsk_fir* f, const float* d_in, int64_t n_floats, int64_t in_stride_floats, int decim, float* d_out,
+                          int64_t out_cap_floats, int64_t out_stride_floats, int64_t* n_out_floats, void* stream) {
+  if (!f || !n_out_floats) return QPSK_ERR_NULL;
+  *n_out_floats = 0;
+  if (n_floats < 0 || decim < 1 || out_cap_floats < 0) return QPSK_ERR_RANGE;
+  if ((n_floats & 1) != 0) return QPSK_ERR_ARG;
+  if (n_floats == 0) return QPSK_OK;
+  if (!d_in) return QPSK_ERR_NULL;
+  if ((in_stride_floats & 1) || (out_stride_floats & 1)) return QPSK_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(d_in) & 7) || (reinterpret_cast<uintptr_t>(d_out) & 7)) return QPSK_ERR_ARG;
+  if (f->eng.channels > 1 && (in_stride_floats < n_floats || out_stride_floats < out_cap_floats)) return QPSK_ERR_ARG;
+  int64_t nout = 0;
+  QPSK_TRY(f->eng.decimate_dev((const float2*)d_in, n_floats >> 1, in_stride_floats >> 1, decim, (float2*)d_out, out_cap_floats >> 1,
+                               out_stride_floats >> 1, &nout, (cudaStream_t)stream));
+  *n_out_floats = 2 * nout;
+  return QPSK_OK;
 }
 
 int qpsk_fir_fft_filter(qpsk_fir* f, const float* in, float* out, int64_t n_floats) {

@@ -27,6 +27,13 @@ struct FirEngine {
   int filter_dev(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t ldy, cudaStream_t s);
   // stateless fftFilter alignment (:96-141)
   int fft_filter_dev(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t ldy, cudaStream_t s);
+  // decimate-by-`dec` streaming filter: the Filter() output kept at stream indices 0, dec, 2*dec, ... (counted across
+  // calls: `dec_skip` input samples are still to pass before the next kept one).  *n_out = outputs per channel.
+  int decimate_dev(const float2* x, int64_t L, int64_t ldx, int dec, float2* y, int64_t cap, int64_t ldy, int64_t* n_out,
+                   cudaStream_t s);
+  int64_t dec_skip = 0;
+  int dec_last = 0;            // decimation factor of the previous call (a change restarts the phase)
+  DevBuf<float2> dec_tmp;      // full-rate scratch of the fallback path
   int get_state(float* hist_iq, int64_t cap_floats);
   int set_state(const float* hist_iq, int64_t n_floats);
 

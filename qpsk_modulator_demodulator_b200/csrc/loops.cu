@@ -416,7 +416,7 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
                         (size_t)2 * kFllCtaStreams * kFllBlock * sizeof(float2) + (size_t)kFllCtaStreams * n_taps * sizeof(float2);
     if (smem <= 200 * 1024 && force_impl != 2) {
       const int blocks = (channels + kFllCtaStreams - 1) / kFllCtaStreams;
-      QPSK_CUDA_TRY(cudaFuncSetAttribute(fll_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      QPSK_TRY(allow_max_dynamic_smem((const void*)fll_group_kernel));
       fll_group_kernel<<<blocks, kFllCtaThreads, smem, s>>>(P, d_taps.p, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy);
       QPSK_LAUNCH_CHECK();
       return QPSK_OK;
@@ -426,7 +426,7 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
   const int blocks = (channels + threads - 1) / threads;
   const size_t smem = (size_t)(2 * n_taps + 2) * sizeof(float) + (size_t)n_taps * threads * sizeof(float2);
   if (smem > 200 * 1024) return QPSK_ERR_UNSUPPORTED;
-  QPSK_CUDA_TRY(cudaFuncSetAttribute(fll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  QPSK_TRY(allow_max_dynamic_smem((const void*)fll_kernel));
   fll_kernel<<<blocks, threads, smem, s>>>(P, d_taps.p, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy);
   QPSK_LAUNCH_CHECK();
   return QPSK_OK;
