@@ -190,6 +190,12 @@ QPSK_API int qpsk_mod_modulate_bytes(qpsk_mod* m, const uint8_t* payload, int64_
                                      const uint8_t* start_marker, int64_t n_start,
                                      const uint8_t* end_marker, int64_t n_end, int pulse_shaping,
                                      float* iq_out, int64_t cap_floats, int64_t* n_floats);
+/* batch, host memory: ModulateBytes :54-72 over `frames` payloads ([frames][n_payload]) -> [frames][out_stride_floats]
+ * samples, frames in groups through a 3-slot kernel / copy-out pipeline (the call is bound by the device-to-host copy:
+ * 32*sps output bytes per payload byte).  iq_out == NULL: size query. */
+QPSK_API int qpsk_mod_modulate_frames(qpsk_mod* m, const uint8_t* payloads, int64_t n_payload, int frames,
+                                      const uint8_t* start_marker, int64_t n_start, const uint8_t* end_marker, int64_t n_end,
+                                      float* iq_out, int64_t out_stride_floats, int64_t* frame_floats);
 /* batch, device-resident: `frames` payloads of n_payload bytes each ([frames][n_payload], device),
  * each framed START|payload|END (+TSC), differential reference reset per frame (:126); writes
  * [frames][frame_floats] to d_iq_out.  *frame_floats is set even when d_iq_out==NULL. */
@@ -230,6 +236,12 @@ QPSK_API int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_float
                               const uint8_t* start_marker, int64_t n_start,
                               const uint8_t* end_marker, int64_t n_end,
                               uint8_t* payload_out, int64_t cap, int64_t* n_bytes);
+/* DeModulateBytes on CS16 samples (interleaved int16 I, Q: the format SaveAsCs16 writes, MS/Models/HelperFunctions.cs:75-106,
+ * and SDR drivers deliver, cf. TB/SDR/ModDemodOverSDR.cs:63-73): widened on the device as (float)v * scale, so the
+ * host-to-device copy carries 4 bytes per complex sample instead of 8.  iq_in is [channels][n_int16]. */
+QPSK_API int qpsk_demod_bytes_cs16(qpsk_demod* d, const int16_t* iq_in, int64_t n_int16, float scale,
+                                   const uint8_t* start_marker, int64_t n_start, const uint8_t* end_marker, int64_t n_end,
+                                   uint8_t* payload_out, int64_t cap, int64_t* n_bytes);
 /* After qpsk_demod_bytes / qpsk_demod_frame_bits returned QPSK_ERR_CAPACITY (n_bytes[c] > cap for some channel): the
  * frames that call completed are still at the head of the framer ring until the next call on the handle, and this copies
  * them out ([channels][cap], n_bytes[channels] as before).  A frame that grew over several calls (the MTU-block loop of

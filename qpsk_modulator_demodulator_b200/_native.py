@@ -115,6 +115,7 @@ def _signatures():
         "qpsk_mod_modulate_bits": (i, [vp, cp, i64, i, vp, i64, i64p]),
         "qpsk_mod_modulate_packed": (i, [vp, vp, i64, i, vp, i64, i64p]),
         "qpsk_mod_modulate_bytes": (i, [vp, vp, i64, vp, i64, vp, i64, i, vp, i64, i64p]),
+        "qpsk_mod_modulate_frames": (i, [vp, vp, i64, i, vp, i64, vp, i64, vp, i64, i64p]),
         "qpsk_mod_modulate_frames_dev": (i, [vp, vp, i64, i, vp, i64, vp, i64, vp, i64, i64p, vp]),
         "qpsk_demod_create": (i, [i, i, f, i, d, d, d, i, cp, i, i64, vpp]),
         "qpsk_demod_create_batch": (i, [i, i, f, i, d, d, d, i, cp, i, i64, i, vpp]),
@@ -123,6 +124,7 @@ def _signatures():
         "qpsk_demod_bits": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bits_packed": (i, [vp, vp, i64, vp, i64, vp]),
         "qpsk_demod_bytes": (i, [vp, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
+        "qpsk_demod_bytes_cs16": (i, [vp, vp, i64, f, vp, i64, vp, i64, vp, i64, vp]),
         "qpsk_demod_last_payload": (i, [vp, vp, i64, vp]),
         "qpsk_demod_frame_bits": (i, [vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp]),
         "qpsk_demod_constellation": (i, [vp, vp, i64, vp, i64, vp]),

@@ -61,7 +61,10 @@ int allow_max_dynamic_smem(const void* kernel) {
   if (done.count({kernel, dev})) return QPSK_OK;
   int max_optin = 0;
   QPSK_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  QPSK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+  cudaFuncAttributes fa;
+  QPSK_CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+  // the opt-in limit covers static + dynamic shared memory together
+  QPSK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - (int)fa.sharedSizeBytes));
   done.insert({kernel, dev});
   return QPSK_OK;
 }

@@ -875,6 +875,17 @@ __global__ void bits_to_chars_kernel(const uint8_t* in, char* out, long long n) 
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxMarkerBytes = 256;
 
+// samples still in HOST memory: the chain then runs as a pipeline over time chunks — the copy of chunk t+1 (and, for CS16,
+// its widening to cf32) is in flight on the side stream while the chain works on chunk t
+struct HostSrc {
+  const void* p = nullptr;      // [channels][ld] complex samples: float2, or int16 pairs when cs16
+  int64_t ld = 0;               // complex samples between consecutive channels
+  bool cs16 = false;
+  float scale = 1.0f;           // cf32 = (float)int16 * scale
+};
+int cs16_to_cf32_launch(const int16_t* d_in, long long ld_in, float scale, float2* d_out, long long ld_out, long long L, int channels,
+                        cudaStream_t s);   // stream.cu
+
 struct DemodEngine {
   int channels = 1;
   int device = 0;              // every entry point selects it (handles own their device, qpskcuda.h)
@@ -892,6 +903,7 @@ struct DemodEngine {
   DevBuf<DiffState> d_diff;
   DevBuf<FramerState> d_framer;
   DevBuf<float2> h_in, h_out;       // device staging for the host entry points
+  DevBuf<int16_t> h_cs16;           // CS16 staging ([channels][2*ld] int16)
   std::vector<uint8_t> markers_host;
   std::vector<long long> last_np;   // payload lengths of the last host framer call (qpsk_demod_last_payload)
   long long ring_cap = 0;
@@ -1000,6 +1012,26 @@ struct DemodEngine {
     while (n > 1 && L < (int64_t)n * 8 * kSsBlock) --n;
     return n;
   }
+  // host-source calls: chunks of >= 2 MiB of samples (below that a copy does not reach the PCIe rate), at most 16
+  int host_chunks(int64_t L, bool cs16) const {
+    const double bytes = (double)L * channels * (cs16 ? 4.0 : 8.0);
+    int n = (int)(bytes / (2.0 * 1024 * 1024));
+    if (n > 16) n = 16;
+    if (n < 1) n = 1;
+    while (n > 1 && L < (int64_t)n * 8 * kSsBlock) --n;
+    return n;
+  }
+  // copy (and widen) samples [n0, n0+len) of every channel from the host source into h_in, on stream `st`
+  int stage_host_chunk(const HostSrc& hs, int64_t n0, int64_t len, int64_t ld, cudaStream_t st) {
+    if (!hs.cs16) {
+      QPSK_CUDA_TRY(cudaMemcpy2DAsync(h_in.p + n0, (size_t)ld * 8, (const float2*)hs.p + n0, (size_t)hs.ld * 8, (size_t)len * 8,
+                                      (size_t)channels, cudaMemcpyHostToDevice, st));
+      return QPSK_OK;
+    }
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(h_cs16.p + 2 * n0, (size_t)ld * 4, (const int16_t*)hs.p + 2 * n0, (size_t)hs.ld * 4,
+                                    (size_t)len * 4, (size_t)channels, cudaMemcpyHostToDevice, st));
+    return cs16_to_cf32_launch(h_cs16.p + 2 * n0, ld, hs.scale, h_in.p + n0, ld, len, channels, st);
+  }
   int ensure_pipeline(int chunks) {
     if (!side) QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     if (!ev_in) QPSK_CUDA_TRY(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
@@ -1067,7 +1099,9 @@ struct DemodEngine {
   }
 
   // DeModulate: bits (bytes 0/1) to out [C][ld_out], counts to n_out[C]
-  int bits_dev(const float2* x, int64_t L, int64_t ldx, uint8_t* out, int64_t ld_out, long long* n_out, cudaStream_t s) {
+  // hs != nullptr: the samples are in host memory (x / ldx ignored): staged into h_in chunk by chunk
+  int bits_dev(const float2* x, int64_t L, int64_t ldx, uint8_t* out, int64_t ld_out, long long* n_out, cudaStream_t s,
+               const HostSrc* hs = nullptr) {
     if (L == 0) {
       QPSK_CUDA_TRY(cudaMemsetAsync(n_out, 0, sizeof(long long) * channels, s));   // :350-351
       return QPSK_OK;
@@ -1082,14 +1116,25 @@ struct DemodEngine {
     }
     const bool fused = can_fuse();
     const bool fuse_mf = fused && can_fuse_mf();
-    const int chunks = (fused && use_fll) ? pipeline_chunks(L) : 1;
+    const bool from_host = hs != nullptr && hs->p != nullptr;
+    int chunks = (fused && use_fll) ? pipeline_chunks(L) : 1;
+    if (from_host) {
+      const int64_t ld = L + (L & 1);
+      QPSK_TRY(h_in.ensure((size_t)ld * channels));
+      if (hs->cs16) QPSK_TRY(h_cs16.ensure((size_t)2 * ld * channels));
+      x = h_in.p;
+      ldx = ld;
+      const int hc = fused ? host_chunks(L, hs->cs16) : 1;
+      if (hc > chunks) chunks = hc;
+      if (chunks == 1) QPSK_TRY(stage_host_chunk(*hs, 0, L, ld, s));
+    }
     const float2* sym_in = nullptr;                  // what the symbol-stage kernel reads in the single-launch case
     int64_t sym_in_ld = 0;
     if (chunks > 1) {
       // sizes only; the front end runs chunk by chunk below
       const int64_t ld = L + (L & 1);
       if (!fuse_mf) QPSK_TRY(t_rrc.ensure((size_t)ld * channels));
-      QPSK_TRY(t_fll.ensure((size_t)ld * channels));
+      if (use_fll) QPSK_TRY(t_fll.ensure((size_t)ld * channels));
       sym_ld = symbols_bound(L);
       if (sym_ld < 1) sym_ld = 1;
       mf_ld = ld;
@@ -1136,11 +1181,22 @@ struct DemodEngine {
       int t = 0;
       for (int64_t n0 = 0; n0 < L; n0 += step, ++t) {
         const int64_t len = (L - n0 < step) ? (L - n0) : step;
-        QPSK_TRY(fll.process_dev(x + n0, t_fll.p + n0, len, ldx, mf_ld, side));        // the call at :359
-        if (!fuse_mf) QPSK_TRY(mf.filter_dev(t_fll.p + n0, t_rrc.p + n0, len, mf_ld, mf_ld, side));  // :360
+        if (from_host) QPSK_TRY(stage_host_chunk(*hs, n0, len, mf_ld, side));            // PCIe copy of this chunk
+        const float2* src = x + n0;
+        int64_t lds = ldx;
+        if (use_fll) {
+          QPSK_TRY(fll.process_dev(src, t_fll.p + n0, len, lds, mf_ld, side));           // the call at :359
+          src = t_fll.p + n0;
+          lds = mf_ld;
+        }
+        if (!fuse_mf) {
+          QPSK_TRY(mf.filter_dev(src, t_rrc.p + n0, len, lds, mf_ld, side));             // :360
+          src = t_rrc.p + n0;
+          lds = mf_ld;
+        }
         QPSK_CUDA_TRY(cudaEventRecord(ev_chunk[(size_t)t], side));
         QPSK_CUDA_TRY(cudaStreamWaitEvent(s, ev_chunk[(size_t)t], 0));
-        QPSK_TRY(launch_symsync((fuse_mf ? t_fll.p : t_rrc.p) + n0, len, mf_ld, raw, ld_raw, n_raw, t > 0 ? 1 : 0, fuse_mf, s));
+        QPSK_TRY(launch_symsync(src, len, lds, raw, ld_raw, n_raw, t > 0 ? 1 : 0, fuse_mf, s));
       }
     } else if (fused) {
       QPSK_TRY(mm.ensure_queue(8, s));
@@ -1197,13 +1253,13 @@ struct DemodEngine {
 
   // DeModulateBytes: payload bytes to payload [C][cap], full lengths to n_payload[C]
   int bytes_dev(const float2* x, int64_t L, int64_t ldx, const uint8_t* sm, int64_t ns, const uint8_t* em, int64_t ne,
-                uint8_t* payload, int64_t cap, long long* n_payload, cudaStream_t s) {
+                uint8_t* payload, int64_t cap, long long* n_payload, cudaStream_t s, const HostSrc* hs = nullptr) {
     if (ns == 0 || ne == 0) return QPSK_ERR_ARG;               // :174-175
     if (!sm || !em) return QPSK_ERR_NULL;
     if (ns > kMaxMarkerBytes || ne > kMaxMarkerBytes) return QPSK_ERR_UNSUPPORTED;
     const long long ldb = bits_bound(L) + 2;
     QPSK_TRY(d_bits.ensure((size_t)ldb * channels));
-    QPSK_TRY(bits_dev(x, L, ldx, d_bits.p, ldb, d_nbits.p, s));
+    QPSK_TRY(bits_dev(x, L, ldx, d_bits.p, ldb, d_nbits.p, s, hs));
     return frame_dev(d_bits.p, ldb, d_nbits.p, sm, ns, em, ne, payload, cap, n_payload, s);
   }
 
@@ -1358,6 +1414,36 @@ int qpsk_demod_bits_packed(qpsk_demod* d, const float* iq_in, int64_t n_floats, 
   return st;
 }
 
+// host samples -> payload bytes: the chain runs as a pipeline over time chunks (HostSrc), the payloads come back in one
+// 2-D copy whose width is the longest payload of the call
+static int demod_bytes_host(qpsk_demod* d, const HostSrc& hs, int64_t L, const uint8_t* start_marker, int64_t n_start,
+                            const uint8_t* end_marker, int64_t n_end, uint8_t* payload_out, int64_t cap, int64_t* n_bytes) {
+  DemodEngine& e = d->eng;
+  cudaStream_t s = e.stream;
+  // device payload rows: what one call can complete is bounded by the framer ring, and by `cap` when the caller gave less
+  const int64_t pcap = cap > 0 ? (cap < e.ring_cap ? cap : e.ring_cap) : 1;
+  QPSK_TRY(e.d_payload.ensure((size_t)pcap * e.channels));
+  QPSK_TRY(e.bytes_dev(nullptr, L, 0, start_marker, n_start, end_marker, n_end, e.d_payload.p, pcap, e.d_npayload.p, s, &hs));
+  std::vector<long long>& np = e.last_np;
+  np.assign((size_t)e.channels, 0);
+  QPSK_CUDA_TRY(cudaMemcpyAsync(np.data(), e.d_npayload.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  int st = QPSK_OK;
+  long long widest = 0;
+  for (int c = 0; c < e.channels; ++c) {
+    n_bytes[c] = np[(size_t)c];
+    if (np[(size_t)c] > cap) st = QPSK_ERR_CAPACITY;         // the frame stays in the ring: qpsk_demod_last_payload
+    else if (np[(size_t)c] > widest) widest = np[(size_t)c];
+  }
+  if (widest > 0) {
+    if (!payload_out) return QPSK_ERR_NULL;
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(payload_out, (size_t)cap, e.d_payload.p, (size_t)pcap, (size_t)widest, (size_t)e.channels,
+                                    cudaMemcpyDeviceToHost, s));
+    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  return st;
+}
+
 int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_floats, const uint8_t* start_marker, int64_t n_start,
                      const uint8_t* end_marker, int64_t n_end, uint8_t* payload_out, int64_t cap, int64_t* n_bytes) {
   if (!d || !n_bytes) return QPSK_ERR_NULL;
@@ -1368,26 +1454,27 @@ int qpsk_demod_bytes(qpsk_demod* d, const float* iq_in, int64_t n_floats, const 
   if (n_floats == 0) return QPSK_OK;
   if (cap < 0) return QPSK_ERR_RANGE;
   QPSK_TRY(ensure_device(d->eng.device));
-  cudaStream_t s = e.stream;
-  const int64_t L = n_floats >> 1, ld = L + (L & 1);
-  QPSK_TRY(demod_stage_in(e, iq_in, L, s));
-  const int64_t pcap = cap > 0 ? cap : 1;
-  QPSK_TRY(e.d_payload.ensure((size_t)pcap * e.channels));
-  QPSK_TRY(e.bytes_dev(e.h_in.p, L, ld, start_marker, n_start, end_marker, n_end, e.d_payload.p, pcap, e.d_npayload.p, s));
-  std::vector<long long>& np = e.last_np;
-  np.assign((size_t)e.channels, 0);
-  QPSK_CUDA_TRY(cudaMemcpyAsync(np.data(), e.d_npayload.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
-  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
-  int st = QPSK_OK;
-  for (int c = 0; c < e.channels; ++c) {
-    n_bytes[c] = np[(size_t)c];
-    if (np[(size_t)c] > cap) { st = QPSK_ERR_CAPACITY; continue; }
-    if (np[(size_t)c] == 0) continue;
-    if (!payload_out) return QPSK_ERR_NULL;
-    QPSK_CUDA_TRY(cudaMemcpy(payload_out + (size_t)c * cap, e.d_payload.p + (size_t)c * pcap, (size_t)np[(size_t)c],
-                             cudaMemcpyDeviceToHost));
-  }
-  return st;
+  HostSrc hs;
+  hs.p = iq_in; hs.ld = n_floats >> 1; hs.cs16 = false;
+  return demod_bytes_host(d, hs, n_floats >> 1, start_marker, n_start, end_marker, n_end, payload_out, cap, n_bytes);
+}
+
+// the same call on CS16 samples (interleaved int16 I, Q — the format SaveAsCs16 writes, HelperFunctions.cs:75-106, and SDR
+// drivers deliver): widened on the device as (float)v * scale, so PCIe carries 4 bytes per complex sample instead of 8
+int qpsk_demod_bytes_cs16(qpsk_demod* d, const int16_t* iq_in, int64_t n_int16, float scale, const uint8_t* start_marker,
+                          int64_t n_start, const uint8_t* end_marker, int64_t n_end, uint8_t* payload_out, int64_t cap,
+                          int64_t* n_bytes) {
+  if (!d || !n_bytes) return QPSK_ERR_NULL;
+  if (n_start == 0 || n_end == 0) return QPSK_ERR_ARG;
+  QPSK_TRY(demod_check_in(d, iq_in, n_int16));
+  DemodEngine& e = d->eng;
+  for (int c = 0; c < e.channels; ++c) n_bytes[c] = 0;
+  if (n_int16 == 0) return QPSK_OK;
+  if (cap < 0) return QPSK_ERR_RANGE;
+  QPSK_TRY(ensure_device(d->eng.device));
+  HostSrc hs;
+  hs.p = iq_in; hs.ld = n_int16 >> 1; hs.cs16 = true; hs.scale = scale;
+  return demod_bytes_host(d, hs, n_int16 >> 1, start_marker, n_start, end_marker, n_end, payload_out, cap, n_bytes);
 }
 
 int qpsk_demod_last_payload(qpsk_demod* d, uint8_t* payload_out, int64_t cap, int64_t* n_bytes) {

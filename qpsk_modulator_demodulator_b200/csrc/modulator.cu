@@ -523,6 +523,20 @@ using namespace qpsk;
 
 struct qpsk_mod {
   ModEngine eng;
+  // host batch pipeline (qpsk_mod_modulate_frames): payload H2D + shaping kernel on eng.stream, samples D2H on s_out,
+  // kSlots groups of frames in flight
+  static constexpr int kSlots = 3;
+  cudaStream_t s_out = nullptr;
+  cudaEvent_t ev_k[kSlots] = {}, ev_d2h[kSlots] = {};
+  DevBuf<uint8_t> d_pay[kSlots];
+  DevBuf<float2> d_grp[kSlots];
+  ~qpsk_mod() {
+    for (int i = 0; i < kSlots; ++i) {
+      if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+      if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+    }
+    if (s_out) cudaStreamDestroy(s_out);
+  }
 };
 
 // Modulate(string bits, bool pulseShaping) :104-167 for a bit source `val(k)` in {0, 1, 2 = any other character}
@@ -666,6 +680,61 @@ int qpsk_mod_modulate_bytes(qpsk_mod* m, const uint8_t* payload, int64_t n_paylo
   QPSK_TRY(mod_frames_common(m, e.d_src.p, n_payload, 1, start_marker, n_start, end_marker, n_end, pulse_shaping, e.d_out.p,
                              ff >> 1, &ff, s));
   QPSK_CUDA_TRY(cudaMemcpyAsync(iq_out, e.d_out.p, (size_t)ff * 4, cudaMemcpyDeviceToHost, s));
+  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  return QPSK_OK;
+}
+
+// ModulateBytes over a batch of frames, host memory in and out: payloads [frames][n_payload] -> samples
+// [frames][out_stride_floats].  The output is 32*sps times the input (8 B per sample, 4*sps samples per payload byte), so
+// the call is bound by the device-to-host copy: groups of frames (~32 MiB of samples) go through a 3-slot pipeline, the
+// shaping kernel of group g+1 running while group g is copied out.
+int qpsk_mod_modulate_frames(qpsk_mod* m, const uint8_t* payloads, int64_t n_payload, int frames, const uint8_t* start_marker,
+                             int64_t n_start, const uint8_t* end_marker, int64_t n_end, float* iq_out, int64_t out_stride_floats,
+                             int64_t* frame_floats) {
+  if (!m) return QPSK_ERR_NULL;
+  if (out_stride_floats & 1) return QPSK_ERR_ARG;
+  int64_t ff = 0;
+  QPSK_TRY(mod_frames_common(m, nullptr, n_payload, frames, start_marker, n_start, end_marker, n_end, 1, nullptr, 0, &ff, nullptr));
+  if (frame_floats) *frame_floats = ff;
+  if (ff == 0 || frames == 0 || !iq_out) return QPSK_OK;
+  if (n_payload > 0 && !payloads) return QPSK_ERR_NULL;
+  if (frames > 1 && out_stride_floats < ff) return QPSK_ERR_ARG;
+  ModEngine& e = m->eng;
+  QPSK_TRY(ensure_device(e.device));
+  if (!m->s_out) {
+    QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < qpsk_mod::kSlots; ++i) {
+      QPSK_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_k[i], cudaEventDisableTiming));
+      QPSK_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_d2h[i], cudaEventDisableTiming));
+    }
+  }
+  const int64_t fc = ff >> 1;                                 // complex samples per frame
+  const int64_t stride_c = fc + (fc & 1);                     // device rows stay 16-byte aligned
+  int64_t G = (32LL << 20) / (stride_c * 8);
+  if (G < 1) G = 1;
+  if (G > frames) G = frames;
+  for (int b = 0; b < qpsk_mod::kSlots; ++b) {
+    QPSK_TRY(m->d_grp[b].ensure((size_t)(G * stride_c)));
+    QPSK_TRY(m->d_pay[b].ensure((size_t)(G * (n_payload > 0 ? n_payload : 1))));
+  }
+  cudaStream_t s = e.stream;
+  int g = 0;
+  for (int64_t f0 = 0; f0 < frames; f0 += G, ++g) {
+    const int b = g % qpsk_mod::kSlots;
+    const int nf = (int)((frames - f0 < G) ? (frames - f0) : G);
+    if (g >= qpsk_mod::kSlots) QPSK_CUDA_TRY(cudaStreamWaitEvent(s, m->ev_d2h[b], 0));   // the slot's previous copy-out is done
+    if (n_payload > 0)
+      QPSK_CUDA_TRY(cudaMemcpyAsync(m->d_pay[b].p, payloads + (size_t)f0 * n_payload, (size_t)nf * n_payload, cudaMemcpyHostToDevice, s));
+    int64_t ff2 = 0;
+    QPSK_TRY(mod_frames_common(m, m->d_pay[b].p, n_payload, nf, start_marker, n_start, end_marker, n_end, 1, m->d_grp[b].p, stride_c,
+                               &ff2, s));
+    QPSK_CUDA_TRY(cudaEventRecord(m->ev_k[b], s));
+    QPSK_CUDA_TRY(cudaStreamWaitEvent(m->s_out, m->ev_k[b], 0));
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(iq_out + (size_t)f0 * out_stride_floats, (size_t)out_stride_floats * 4, m->d_grp[b].p,
+                                    (size_t)stride_c * 8, (size_t)fc * 8, (size_t)nf, cudaMemcpyDeviceToHost, m->s_out));
+    QPSK_CUDA_TRY(cudaEventRecord(m->ev_d2h[b], m->s_out));
+  }
+  QPSK_CUDA_TRY(cudaStreamSynchronize(m->s_out));
   QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   return QPSK_OK;
 }

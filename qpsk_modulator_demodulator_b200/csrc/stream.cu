@@ -74,12 +74,32 @@ __global__ void cf32_to_cs16_kernel(const float* __restrict__ x, long long n, co
   }
 }
 
+// rows of `L` complex samples: out[c][n] = (float)in[c][n] * scale (one int16 pair -> one float2 per thread and pass)
+__global__ void cs16_rows_to_cf32_kernel(const int16_t* __restrict__ in, long long ld_in, float scale, float2* __restrict__ out,
+                                         long long ld_out, long long L, int C) {
+  const long long total = (long long)C * L;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx / L);
+    const long long n = idx - (long long)c * L;
+    const short2 v = reinterpret_cast<const short2*>(in + 2 * (long long)c * ld_in)[n];
+    out[(long long)c * ld_out + n] = make_float2((float)v.x * scale, (float)v.y * scale);
+  }
+}
+
 inline int grid_for(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
   const long long cap = 16LL * device_sm_count();
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
+}
+
+int cs16_to_cf32_launch(const int16_t* d_in, long long ld_in, float scale, float2* d_out, long long ld_out, long long L, int channels,
+                        cudaStream_t s) {
+  if (L <= 0 || channels <= 0) return QPSK_OK;
+  cs16_rows_to_cf32_kernel<<<grid_for((long long)channels * L, 256), 256, 0, s>>>(d_in, ld_in, scale, d_out, ld_out, L, channels);
+  QPSK_LAUNCH_CHECK();
+  return QPSK_OK;
 }
 
 }  // namespace qpsk

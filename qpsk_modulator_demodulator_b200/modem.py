@@ -118,6 +118,25 @@ class QPSKModulator(_Handle):
                                                  C.byref(n), None))
         return n.value
 
+    def ModulateFrames(self, payloads, startMarker: bytes, endMarker: bytes, out=None, out_ptr: int = 0, out_stride_floats: int = 0):
+        """ModulateBytes over a batch: payloads [frames, n_payload] uint8 (host) -> samples [frames, frame_floats] (host),
+        frame groups pipelined through the device (qpsk_mod_modulate_frames).  `out_ptr` / `out_stride_floats`: write into
+        caller memory (e.g. a pinned buffer) instead of allocating."""
+        p = np.ascontiguousarray(payloads, dtype=np.uint8)
+        frames, n_payload = p.shape
+        s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
+        ff = self.frame_floats(n_payload, startMarker, endMarker)
+        if out_ptr:
+            dst, stride = out_ptr, out_stride_floats or ff
+        else:
+            if out is None:
+                out = np.empty((frames, ff), np.float32)
+            dst, stride = out.ctypes.data, out.shape[1]
+        n = C.c_int64(0)
+        check(lib().qpsk_mod_modulate_frames(self._h, _ptr(p), n_payload, frames, _ptr(s), s.size, _ptr(e), e.size, dst, stride,
+                                             C.byref(n)))
+        return out
+
     def modulate_frames_dev(self, d_payloads: int, n_payload: int, frames: int, startMarker: bytes, endMarker: bytes,
                             d_out: int, out_stride_floats: int, stream: int = 0) -> int:
         """[frames][n_payload] device bytes -> [frames][out_stride_floats] device cf32; returns floats per frame."""
@@ -188,6 +207,31 @@ class QPSKDeModulator(_Handle):
         out = self._refetch(st, out, nb)
         outs = [out[c, : nb[c]].tobytes() for c in range(self.channels)]
         return outs[0] if self.channels == 1 else outs
+
+    def DeModulateBytesCs16(self, samplesCs16, scale: float, startMarker: bytes, endMarker: bytes, cap: int = 0):
+        """DeModulateBytes on CS16 samples (int16 I, Q pairs; [channels, n] for batch handles), widened on the device as
+        (float)v * scale: half the host-to-device bytes of the cf32 call, identical payloads when the cf32 samples are
+        exactly int16 * scale."""
+        x = np.ascontiguousarray(samplesCs16, dtype=np.int16)
+        n = x.shape[-1] if x.ndim == 2 else x.size
+        s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
+        cap = cap or max(n // 8 + 64, 64)
+        out = np.zeros((self.channels, cap), np.uint8)
+        nb = np.zeros(self.channels, np.int64)
+        st = lib().qpsk_demod_bytes_cs16(self._h, _ptr(x), n, scale, _ptr(s), s.size, _ptr(e), e.size, _ptr(out), cap, _ptr(nb))
+        out = self._refetch(st, out, nb)
+        outs = [out[c, : nb[c]].tobytes() for c in range(self.channels)]
+        return outs[0] if self.channels == 1 else outs
+
+    def demod_bytes_host_ptr(self, in_ptr: int, n_floats: int, startMarker: bytes, endMarker: bytes, out: np.ndarray, nb: np.ndarray,
+                             cs16_scale: float = None):
+        """The raw host entry point on caller-owned memory (pinned / registered / pageable): in_ptr -> [channels][n_floats]
+        float32 (or int16 when cs16_scale is given), payloads into out [channels, cap], lengths into nb.  Returns the status."""
+        s, e = _bytes_arr(startMarker), _bytes_arr(endMarker)
+        if cs16_scale is None:
+            return lib().qpsk_demod_bytes(self._h, in_ptr, n_floats, _ptr(s), s.size, _ptr(e), e.size, _ptr(out), out.shape[1], _ptr(nb))
+        return lib().qpsk_demod_bytes_cs16(self._h, in_ptr, n_floats, cs16_scale, _ptr(s), s.size, _ptr(e), e.size, _ptr(out),
+                                           out.shape[1], _ptr(nb))
 
     def _refetch(self, st, out, nb):
         """A frame that accumulated on the device over several calls can be longer than a buffer sized from this call's
