@@ -127,6 +127,23 @@ def copy_ceiling(torch, hin, hout, n_bytes):
     return r
 
 
+def pin_to_gpu_cores(index: int):
+    """Bind this rank to the CPU cores NVML reports as local to its GPU (the NUMA node its PCIe root hangs off), so that the
+    pinned staging buffers of the host-pointer legs are allocated and copied from local memory.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cores = [c for c in cores if c < (os.cpu_count() or 1)]
+        if cores:
+            os.sched_setaffinity(0, cores)
+        return {"cores": len(cores), "first": cores[0] if cores else None, "of": os.cpu_count()}
+    except Exception as e:   # noqa: BLE001 - reported in the JSON line
+        return {"error": repr(e)[:120]}
+
+
 def taps_for(orc_or_q, span, sps):
     h = orc_or_q.RRCFilter.generateCoefficents(span, ALPHA, sps * 1000, 1000)
     return orc_or_q.real_taps_to_iq(h)
@@ -225,6 +242,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # N > 1 only: at N = 1 the CPU-baseline legs of the same process use every host core
+    affinity = pin_to_gpu_cores(local) if world > 1 else {"cores": os.cpu_count(), "note": "unpinned at N = 1"}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -444,6 +463,12 @@ def main():
                         Q, torch, d, world, rank, stream, use_fll=fll, channels_per_gpu=tot, parity_channels=0,
                         label=f"saturated weak: {tot} channels per GPU", **common)
         modulator = bench_chain.run_modulator(Q, torch, d, world, rank, stream, steps=k, warmup=3, hbm_peak=hbm_peak)
+        chain_e2e = chain_fll_e2e = modulator_e2e = None
+        if not args.no_e2e:
+            ks = max(1, min(args.steps, 5))
+            chain_e2e = bench_chain.run_chain_e2e(Q, torch, d, world, rank, stream, steps=ks, use_fll=False)
+            chain_fll_e2e = bench_chain.run_chain_e2e(Q, torch, d, world, rank, stream, steps=ks, use_fll=True)
+            modulator_e2e = bench_chain.run_modulator_e2e(Q, torch, d, world, rank, steps=min(ks, 3))
         stream_leg = bench_chain.run_stream(Q) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
     cpu = None
@@ -462,7 +487,7 @@ def main():
                        "parallelism": f"{world} independent streams, one per GPU, no collective"},
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_by_taps": roofs, "decimate": decimate, "fma_peak_tflops_measured": fma_peak,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-            "build_id": build_id,
+            "build_id": build_id, "cpu_affinity": affinity,
             "scaling_note": "`scaling: weak` refers to `value` (one independent 2^28-sample FIR stream per GPU, no communication). "
                             "The chain legs state their own: chain / chain_fll are weak (2048 channels per GPU), *_strong shard a "
                             "fixed 16384-channel set (config 4), *_saturated put 16384 channels on every GPU",
@@ -474,6 +499,10 @@ def main():
             line["chain_fll"] = chain_fll
             line.update(scaling_legs)
             line["modulator"] = modulator
+            if chain_e2e is not None:
+                chain["e2e"] = chain_e2e
+                chain_fll["e2e"] = chain_fll_e2e
+                modulator["e2e"] = modulator_e2e
             if stream_leg is not None:
                 line["stream"] = stream_leg
     if comm is not None:

@@ -345,3 +345,130 @@ def run_stream(Q, blocks=400, n_payload=512, depth=4, cpu_blocks=40):
         ok += bool(od.DeModulateBytes(bursts[(i + 1) % uniq], S, E, cap=1 << 16))
     out["cpu_oracle_1core"] = {"msamples_s": rate(time.perf_counter() - t0, cpu_blocks), "frames": ok}
     return out
+
+
+def _median(v):
+    v = sorted(v)
+    return v[len(v) // 2]
+
+
+def run_chain_e2e(Q, torch, dist, world, rank, stream, steps=5, channels_per_gpu=2048, use_fll=False, n_payload=512):
+    """End-to-end chain leg: what the modem ships.  HOST samples in ([channels][n_floats], 8 B — or 4 B as CS16 — per complex
+    sample), payload BYTES out, through the host entry point qpsk_demod_bytes / qpsk_demod_bytes_cs16 (DeModulateBytes): the
+    copy of time chunk t+1 runs under the chain on chunk t, the payloads come back in one copy.  Wall-clock per call
+    (H2D + FLL? + MF + MM + Costas + decode + TSC strip + framer + D2H inside), median step, max over ranks.  The same call is
+    timed on page-locked (qpsk_host_alloc), registered-in-place (qpsk_host_register: a C# float[] pinned by a GCHandle)
+    and pageable memory."""
+    import time
+    from qpsk_modulator_demodulator_b200 import shard
+    fs = 10_000_000
+    rs = fs // 2
+    alpha = float(np.float32(0.4))
+    C = channels_per_gpu
+    first, _ = shard.channel_range(rank, world, C * world)
+    seed = 2026
+    mod = Q.QPSKModulator(fs, rs, alpha, 10, True, TSC)
+    pay = torch.empty((C, n_payload), dtype=torch.uint8, device="cuda")
+    Q.fill_bytes_dev(seed, first, C, n_payload, pay.data_ptr(), stream)
+    ff = mod.frame_floats(n_payload, b"S", b"E")
+    tx = torch.empty((C, ff), dtype=torch.float32, device="cuda")
+    mod.modulate_frames_dev(pay.data_ptr(), n_payload, C, b"S", b"E", tx.data_ptr(), ff, stream)
+    chan = Q.SimChannel(100e6, 100e6, fs, 1, 1, noise_dbfs=-40.0, mode=1, path_gains_iq=(1.0, 0.0, 0.12, 0.08), path_delays=(0, 3),
+                        seed=seed, channels=C, first_channel=first)
+    rx = torch.empty((C, ff), dtype=torch.float32, device="cuda")
+    chan.apply_dev(tx.data_ptr(), ff, ff, rx.data_ptr(), ff, stream)
+    torch.cuda.synchronize()
+    pay_h = pay.cpu().numpy()
+    n = C * ff
+    pinned = Q.PinnedBuffer(n)
+    torch.from_numpy(pinned.array).copy_(rx.reshape(-1))
+    torch.cuda.synchronize()
+    pageable = np.array(pinned.array, copy=True)
+    registered = np.array(pinned.array, copy=True)
+    peak = float(np.abs(pageable).max())
+    scale = float(np.float32(peak / 30000.0))
+    cs16_pin = Q.PinnedBuffer((n + 1) // 2)                     # n int16 values in n/2 floats of pinned memory
+    cs16 = cs16_pin.array.view(np.int16)[:n]
+    cs16[:] = np.clip(np.round(pageable / scale), -32768, 32767).astype(np.int16)
+    cap = n_payload + 64
+    out = np.zeros((C, cap), np.uint8)
+    nb = np.zeros(C, np.int64)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def leg(ptr, cs16_scale=None, n_items=ff):
+        dem = Q.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC, use_fll=use_fll, channels=C, max_frame_bytes=2 * cap)
+        for _ in range(2):
+            st = dem.demod_bytes_host_ptr(ptr, n_items, b"S", b"E", out, nb, cs16_scale)
+            assert st == 0, st
+        barrier()
+        Q.launch_count_reset()
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            st = dem.demod_bytes_host_ptr(ptr, n_items, b"S", b"E", out, nb, cs16_scale)
+            ts.append(time.perf_counter() - t0)
+            assert st == 0, st
+        launches = Q.launch_count()
+        t = torch.tensor([_median(ts)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        good = int(sum(out[c, : nb[c]].tobytes() == pay_h[c].tobytes() for c in range(C)))
+        return {"value": world * C * (ff // 2) / float(t.item()) / 1e6, "unit": "Msamples/s", "ms_per_step": 1e3 * float(t.item()),
+                "step_ms": [round(1e3 * v, 3) for v in ts], "frames_recovered": good, "gpu_launches_per_step": launches // steps}
+
+    res = {"workload": f"{C * world} channels ({C}/GPU) x {ff // 2} samples per burst, host samples in, payload bytes out "
+                       f"({'FLL -> ' if use_fll else ''}MF -> MM -> Costas -> decode -> TSC strip -> framer), impairments as in `chain`",
+           "api": "qpsk_demod_bytes / qpsk_demod_bytes_cs16 (DeModulateBytes, host pointers; time-chunk copy pipeline)",
+           "timing": "wall clock around the call, median step, max over ranks",
+           "h2d_bytes_per_step": C * ff * 4, "d2h_bytes_per_step": C * cap + 8 * C}
+    res["pinned"] = leg(pinned.array.ctypes.data)
+    with Q.RegisteredArray(registered):
+        res["registered"] = leg(registered.ctypes.data)
+    res["pageable"] = leg(pageable.ctypes.data)
+    res["cs16_pinned"] = dict(leg(cs16.ctypes.data, scale, ff), h2d_bytes_per_step=C * ff * 2)
+    res["value"], res["unit"] = res["pinned"]["value"], "Msamples/s"
+    pinned.free()
+    cs16_pin.free()
+    return res
+
+
+def run_modulator_e2e(Q, torch, dist, world, rank, steps=3, frames_per_gpu=256, n_payload=65536):
+    """End-to-end modulator leg: HOST payload bytes in, HOST samples out (qpsk_mod_modulate_frames: ModulateBytes over a batch,
+    frame groups pipelined kernel / copy-out).  32*sps output bytes per payload byte: bound by the device-to-host copy."""
+    import time
+    fs, rs = 4000, 1000
+    F = frames_per_gpu
+    mod = Q.QPSKModulator(fs, rs, 0.35, 10, True, TSC)
+    rng = np.random.default_rng(100 + rank)
+    pay = rng.integers(0, 256, (F, n_payload), dtype=np.uint8)
+    ff = mod.frame_floats(n_payload, b"START", b"END")
+    outp = Q.PinnedBuffer(F * ff)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    mod.ModulateFrames(pay, b"START", b"END", out_ptr=outp.array.ctypes.data, out_stride_floats=ff)
+    barrier()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        mod.ModulateFrames(pay, b"START", b"END", out_ptr=outp.array.ctypes.data, out_stride_floats=ff)
+        ts.append(time.perf_counter() - t0)
+    t = torch.tensor([_median(ts)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    res = {"workload": f"{F * world} frames ({F}/GPU) x {n_payload} B payload, host bytes in, host samples out (sps 4, span 10, TSC, "
+                       f"differential); {F * ff * 4 / 1e9:.2f} GB of samples per GPU per step",
+           "api": "qpsk_mod_modulate_frames (host pointers, pinned output; 3-slot kernel / copy-out pipeline)",
+           "value": world * F * (ff // 2) / dt / 1e6, "unit": "Msamples/s (output)", "ms_per_step": 1e3 * dt,
+           "step_ms": [round(1e3 * v, 2) for v in ts], "h2d_bytes_per_step": F * n_payload, "d2h_bytes_per_step": F * ff * 4,
+           "d2h_gbs": F * ff * 4 / dt / 1e9, "bound": "pcie (device-to-host)"}
+    outp.free()
+    return res
