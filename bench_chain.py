@@ -390,7 +390,7 @@ def run_chain_e2e(Q, torch, dist, world, rank, stream, steps=5, channels_per_gpu
     cs16_pin = Q.PinnedBuffer((n + 1) // 2)                     # n int16 values in n/2 floats of pinned memory
     cs16 = cs16_pin.array.view(np.int16)[:n]
     cs16[:] = np.clip(np.round(pageable / scale), -32768, 32767).astype(np.int16)
-    cap = n_payload + 64
+    cap = 2 * (n_payload + 64)                                  # = the framer ring bound below: every completed frame fits
     out = np.zeros((C, cap), np.uint8)
     nb = np.zeros(C, np.int64)
 
@@ -400,7 +400,7 @@ def run_chain_e2e(Q, torch, dist, world, rank, stream, steps=5, channels_per_gpu
         torch.cuda.synchronize()
 
     def leg(ptr, cs16_scale=None, n_items=ff):
-        dem = Q.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC, use_fll=use_fll, channels=C, max_frame_bytes=2 * cap)
+        dem = Q.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC, use_fll=use_fll, channels=C, max_frame_bytes=cap)
         for _ in range(2):
             st = dem.demod_bytes_host_ptr(ptr, n_items, b"S", b"E", out, nb, cs16_scale)
             assert st == 0, st
