@@ -361,6 +361,7 @@ def run_chain_e2e(Q, torch, dist, world, rank, stream, steps=5, channels_per_gpu
     and pageable memory."""
     import time
     from qpsk_modulator_demodulator_b200 import shard
+    SM, EM = b"MESSAGE_START", b"MESSAGE_STOP"                   # testAtDataLevel.cs:33-34
     fs = 10_000_000
     rs = fs // 2
     alpha = float(np.float32(0.4))
@@ -370,9 +371,9 @@ def run_chain_e2e(Q, torch, dist, world, rank, stream, steps=5, channels_per_gpu
     mod = Q.QPSKModulator(fs, rs, alpha, 10, True, TSC)
     pay = torch.empty((C, n_payload), dtype=torch.uint8, device="cuda")
     Q.fill_bytes_dev(seed, first, C, n_payload, pay.data_ptr(), stream)
-    ff = mod.frame_floats(n_payload, b"S", b"E")
+    ff = mod.frame_floats(n_payload, SM, EM)
     tx = torch.empty((C, ff), dtype=torch.float32, device="cuda")
-    mod.modulate_frames_dev(pay.data_ptr(), n_payload, C, b"S", b"E", tx.data_ptr(), ff, stream)
+    mod.modulate_frames_dev(pay.data_ptr(), n_payload, C, SM, EM, tx.data_ptr(), ff, stream)
     chan = Q.SimChannel(100e6, 100e6, fs, 1, 1, noise_dbfs=-40.0, mode=1, path_gains_iq=(1.0, 0.0, 0.12, 0.08), path_delays=(0, 3),
                         seed=seed, channels=C, first_channel=first)
     rx = torch.empty((C, ff), dtype=torch.float32, device="cuda")
@@ -402,14 +403,14 @@ def run_chain_e2e(Q, torch, dist, world, rank, stream, steps=5, channels_per_gpu
     def leg(ptr, cs16_scale=None, n_items=ff):
         dem = Q.QPSKDeModulator(fs, rs, alpha, 10, tsc=TSC, use_fll=use_fll, channels=C, max_frame_bytes=cap)
         for _ in range(2):
-            st = dem.demod_bytes_host_ptr(ptr, n_items, b"S", b"E", out, nb, cs16_scale)
+            st = dem.demod_bytes_host_ptr(ptr, n_items, SM, EM, out, nb, cs16_scale)
             assert st == 0, st
         barrier()
         Q.launch_count_reset()
         ts = []
         for _ in range(steps):
             t0 = time.perf_counter()
-            st = dem.demod_bytes_host_ptr(ptr, n_items, b"S", b"E", out, nb, cs16_scale)
+            st = dem.demod_bytes_host_ptr(ptr, n_items, SM, EM, out, nb, cs16_scale)
             ts.append(time.perf_counter() - t0)
             assert st == 0, st
         launches = Q.launch_count()

@@ -103,7 +103,6 @@ __device__ __forceinline__ void cp_async_wait() {
 struct SsSmem {
   float2 raw[2][32 * kSsPitch];
   float2 carry[32 * kSsCarry];
-  float2 symq[2][32 * kSsSymPitch];
   int nsymq[2][32];
 };
 
@@ -121,8 +120,9 @@ __device__ __forceinline__ double sel_f64(bool a, double x, double y) {
 // one round AHEAD of the Mueller-Muller warp, from a shared-memory ring of the last 128 RAW input samples per channel.
 // The chain then reads each input sample from HBM once (8 B / sample, the fused-ideal traffic of SURVEY §8d) and the
 // filtered samples never leave the SM: no matched-filter launch, no [channels][samples] scratch round trip.
-constexpr int kMfRing = 128;              // raw samples kept per channel (4 rounds): N - 1 <= 64 taps of history
-constexpr int kMfRingPitch = kMfRing + 1; // odd pitch (float2): the 32 channels of a warp fall in different banks
+// raw samples kept per channel: the round being filtered, N-1 samples of history before it and the round in flight —
+// 96 slots (3 rounds) while N - 1 <= 32, else 128; rows are ring_n + 1 float2 apart (odd pitch: the 32 channels of a warp
+// fall in different banks)
 constexpr int kMfMaxTaps = 65;
 struct MfTaps {
   float rev[kMfMaxTaps + 7];              // rev[i] = h[N-1-i]: window element i (oldest first) meets tap rev[i]
@@ -146,57 +146,74 @@ __device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
   return d;
 }
 
-// outputs j0 .. j1-1 (< blk) of round q for this lane's channel: sample n = 32q + j, window element i = raw[n-(N-1)+i]
-__device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, const MfTaps& T, float2 nz, int q, int j0, int j1,
-                                         int blk, float2* __restrict__ out_ch) {
+// outputs j0 .. j1-1 (< blk) of round q for this lane's channel: sample n = 32q + j, window element i = raw[n-(N-1)+i].
+// Four outputs per pass (32 independent lane partials: the warp runs alone on its scheduler, so the parallelism has to come
+// from inside the thread), the tail samples fetched ahead of the lane sums.
+constexpr int kMfR = 4;
+__device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int ring_n, const MfTaps& T, float2 nz, int q, int j0,
+                                         int j1, int blk, float2* __restrict__ out_ch) {
+  auto wrap = [ring_n](int i) { return i >= ring_n ? i - ring_n : i; };   // 0 <= i < 2*ring_n
   const int N = T.n_taps;
   const int n_vec = N & ~7;
-  for (int j = j0; j < j1 && j < blk; j += 2) {
+  const int n_tail = N - n_vec;                   // 0..7
+  for (int j = j0; j < j1 && j < blk; j += kMfR) {
     const int first = q * kSsBlock + j - (N - 1);
-    float2 lp[2][8];
+    int bmod = first % ring_n;                      // slot of window element 0 (first may be negative)
+    if (bmod < 0) bmod += ring_n;
+    const int fmod = bmod;
+    float2 lp[kMfR][8];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < kMfR; ++r)
 #pragma unroll
       for (int l = 0; l < 8; ++l) lp[r][l] = make_float2(0.f, 0.f);
-    float2 w0 = ring_ch[first & (kMfRing - 1)];
-    for (int ib = 0; ib < n_vec; ib += 8) {
-      float2 wv[9];
-      wv[0] = w0;
+    float2 wv[8 + kMfR - 1];
 #pragma unroll
-      for (int k = 1; k < 9; ++k) wv[k] = ring_ch[(first + ib + k) & (kMfRing - 1)];
+    for (int k = 0; k < kMfR - 1; ++k) wv[k] = ring_ch[wrap(bmod + k)];
+    for (int ib = 0; ib < n_vec; ib += 8) {
+#pragma unroll
+      for (int k = kMfR - 1; k < 8 + kMfR - 1; ++k) wv[k] = ring_ch[wrap(bmod + k)];
+      bmod = wrap(bmod + 8);
 #pragma unroll
       for (int l = 0; l < 8; ++l) {
         const float g = T.rev[ib + l];
         const float2 gg = make_float2(g, g);
 #pragma unroll
-        for (int r = 0; r < 2; ++r) lp[r][l] = add2_rn(lp[r][l], mul2_rounded(wv[l + r], gg, nz));
+        for (int r = 0; r < kMfR; ++r) lp[r][l] = add2_rn(lp[r][l], mul2_rounded(wv[l + r], gg, nz));
       }
-      w0 = wv[8];
-    }
-    float2 acc[2];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+      for (int k = 0; k < kMfR - 1; ++k) wv[k] = wv[8 + k];
+    }
+    // tail window: elements n_vec .. N-1 (+ kMfR-1), loaded before the dependent lane sums start
+    float2 tw[7 + kMfR - 1];
+#pragma unroll
+    for (int k = 0; k < 7 + kMfR - 1; ++k)
+      tw[k] = (k < n_tail + kMfR - 1) ? ring_ch[wrap(bmod + k)] : make_float2(0.f, 0.f);
+    float2 acc[kMfR];
+#pragma unroll
+    for (int r = 0; r < kMfR; ++r) {
       acc[r] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int l = 0; l < 8; ++l) acc[r] = add2_rn(acc[r], lp[r][l]);            // lanes 0..7 (:176-180)
     }
-    for (int i = n_vec; i < N; ++i) {                                             // scalar tail (:183-192)
-      const float g = T.rev[i];
-      const float2 gg = make_float2(g, g);
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
-        acc[r] = add2_rn(acc[r], mul2_rounded(ring_ch[(first + i + r) & (kMfRing - 1)], gg, nz));
+    for (int i = 0; i < 7; ++i) {                                                  // scalar tail (:183-192)
+      if (i < n_tail) {
+        const float g = T.rev[n_vec + i];
+        const float2 gg = make_float2(g, g);
+#pragma unroll
+        for (int r = 0; r < kMfR; ++r) acc[r] = add2_rn(acc[r], mul2_rounded(tw[i + r], gg, nz));
+      }
     }
     // an infinite SAMPLE makes the reference's hq*x terms NaN (hq = +0: 0 * Inf), which the real-tap reduction does not
     // model: recompute such outputs with the full complex product (see fir_exact_real_kernel)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
+#pragma unroll 1
+    for (int r = 0; r < kMfR; ++r) {
       if (!(fabsf(acc[r].x) <= 3.402823466e+38f) || !(fabsf(acc[r].y) <= 3.402823466e+38f)) {
         float lI[8], lQ[8];
         for (int l = 0; l < 8; ++l) lI[l] = lQ[l] = 0.f;
         const float hq = 0.f;
         for (int i = 0; i < n_vec; ++i) {
-          const float2 xv = ring_ch[(first + i + r) & (kMfRing - 1)];
+          const float2 xv = ring_ch[(fmod + i + r) % ring_n];
           const float hi = T.rev[i];
           lI[i & 7] = __fadd_rn(lI[i & 7], __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y)));
           lQ[i & 7] = __fadd_rn(lQ[i & 7], __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x)));
@@ -207,26 +224,31 @@ __device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, con
           aQ = __fadd_rn(aQ, lQ[l]);
         }
         for (int i = n_vec; i < N; ++i) {
-          const float2 xv = ring_ch[(first + i + r) & (kMfRing - 1)];
+          const float2 xv = ring_ch[(fmod + i + r) % ring_n];
           const float hi = T.rev[i];
           aI = __fadd_rn(aI, __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y)));
           aQ = __fadd_rn(aQ, __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x)));
         }
-        acc[r] = make_float2(aI, aQ);
+        const float2 fix = make_float2(aI, aQ);
+        // acc[] must keep compile-time indices (registers): select instead of a dynamically indexed store
+#pragma unroll
+        for (int rr = 0; rr < kMfR; ++rr)
+          if (rr == r) acc[rr] = fix;
       }
     }
-    out_ch[j] = acc[0];
-    if (j + 1 < blk) out_ch[j + 1] = acc[1];
+#pragma unroll
+    for (int r = 0; r < kMfR; ++r)
+      if (j + r < blk) out_ch[j + r] = acc[r];
   }
 }
 
 template <bool DIFF, int MFW>
-__global__ void __launch_bounds__(64 + 32 * MFW, MFW == 2 ? 3 : (MFW == 4 ? 2 : 1))
+__global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? 3 : (MFW == 4 ? 2 : 1)))
     symsync_decode_kernel(const MmParams MP, MmState* mm_g, const float2* __restrict__ q_in, float2* __restrict__ q_out,
                           long long qcap, const CostasParams CP, CostasState* cst_g, DiffState* dst_g, int C,
                           const float2* __restrict__ x, long long L, long long ldx, uint8_t* __restrict__ bits,
                           long long ld_bits, long long* n_bits, int* n_sym_g, int append, const __grid_constant__ MfTaps MT,
-                          const MfArgs MA) {
+                          const MfArgs MA, const int ring_n, const int sym_pitch) {
   // MFW > 0: x is the RAW input (or the FLL output) and MFW extra warps run the matched filter one round ahead; MFW == 0:
   // x is the matched-filter output (MT / MA unused).
   // append != 0: this launch continues a call split into time chunks (DemodEngine::bits_dev): bits and counts go on
@@ -234,7 +256,12 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 2 ? 3 : (MFW == 4 ? 2 : 
   // boundary of the single launch (same carried samples, same rebased base_index), so the split is bit-neutral.
   constexpr bool diff = DIFF;
   __shared__ SsSmem sm;
-  extern __shared__ __align__(16) float2 mf_ring[];   // [32][kMfRingPitch] when MFW > 0
+  // dynamic shared memory: the symbol queues [2][32][sym_pitch] (sym_pitch - 1 = most symbols one round can emit at this
+  // samples-per-symbol rate), then — MFW > 0 — the raw-sample ring [32][ring_n + 1]
+  extern __shared__ __align__(16) float2 dyn_smem[];
+  float2* const symq0 = dyn_smem;
+  float2* const mf_ring = dyn_smem + 2 * 32 * sym_pitch;
+  const int ring_pitch = ring_n + 1;
   const int lane = threadIdx.x & 31;
   const int role = threadIdx.x >> 5;                // 0: symbol sync, 1: Costas + decode, 2..: matched filter
   const int c0 = blockIdx.x * 32;
@@ -258,8 +285,8 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 2 ? 3 : (MFW == 4 ? 2 : 
     const long long n0 = (long long)r * kSsBlock;
     const int blk = (int)((L - n0) < kSsBlock ? (L - n0) : kSsBlock);
     // MFW == 0: straight into the round's double buffer; MFW > 0: into the raw ring (slot = sample index mod 128)
-    float2* dst = (MFW > 0) ? (mf_ring + ((int)(n0 + lane) & (kMfRing - 1))) : (sm.raw[r & 1] + lane);
-    constexpr int pitch = (MFW > 0) ? kMfRingPitch : kSsPitch;
+    float2* dst = (MFW > 0) ? (mf_ring + (int)((n0 + lane) % ring_n)) : (sm.raw[r & 1] + lane);
+    const int pitch = (MFW > 0) ? ring_pitch : kSsPitch;
     if (lane < blk) {
 #pragma unroll 8
       for (int j = 0; j < 32; ++j) {
@@ -294,13 +321,14 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 2 ? 3 : (MFW == 4 ? 2 : 
     // the filter's delay line: samples -1 .. -(N-1) of this call are the newest entries of the FirEngine history
     for (int k = 1; k < MT.n_taps; ++k)
       if ((k - 1) % MFW == role - 2)
-        mf_ring[lane * kMfRingPitch + ((-k) & (kMfRing - 1))] = MA.hist_in[(long long)c * MA.HL + MA.HL - k];
+        mf_ring[lane * ring_pitch + (ring_n - k)] = MA.hist_in[(long long)c * MA.HL + MA.HL - k];
   }
   __syncthreads();
   if (MFW > 0) {
     if (role >= 2 && rounds > 0) {
       const int blk0 = (int)(L < kSsBlock ? L : kSsBlock);
-      mf_round(mf_ring + lane * kMfRingPitch, MT, nz, 0, (role - 2) * mf_per, (role - 1) * mf_per, blk0, sm.raw[0] + lane * kSsPitch);
+      mf_round(mf_ring + lane * ring_pitch, ring_n, MT, nz, 0, (role - 2) * mf_per, (role - 1) * mf_per, blk0,
+               sm.raw[0] + lane * kSsPitch);
     }
     __syncthreads();
   }
@@ -323,7 +351,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 2 ? 3 : (MFW == 4 ? 2 : 
         v.queued = carried;
         const int count = carried + blk;
         const double limit_d = (double)(count - 2);  // loop test in fp64: base + 2 < count  <=>  base_d < count - 2
-        float2* sq = sm.symq[r & 1] + lane * kSsSymPitch;
+        float2* sq = symq0 + ((r & 1) * 32 + lane) * sym_pitch;
         int ns = 0;
         double base_d = (double)S.base_index;        // == (double)baseIndex exactly; floor() keeps it integral
         // One pass = one symbol (MuellerMuller.cs:62-120); the loop-carried chain is mu -> interpolator -> error ->
@@ -393,7 +421,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 2 ? 3 : (MFW == 4 ? 2 : 
       // matched filter of round r+1 (its raw samples landed before the barrier that ended round r-1)
       const long long n1 = (long long)(r + 1) * kSsBlock;
       const int blk1 = (int)((L - n1) < kSsBlock ? (L - n1) : kSsBlock);
-      mf_round(mf_ring + lane * kMfRingPitch, MT, nz, r + 1, (role - 2) * mf_per, (role - 1) * mf_per, blk1,
+      mf_round(mf_ring + lane * ring_pitch, ring_n, MT, nz, r + 1, (role - 2) * mf_per, (role - 1) * mf_per, blk1,
                sm.raw[(r + 1) & 1] + lane * kSsPitch);
     }
     if (role == 1 && r >= 1) {
@@ -406,7 +434,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 2 ? 3 : (MFW == 4 ? 2 : 
       // the round is replayed from the saved state through the exact (branching) step.
       const int b = (r - 1) & 1;
       const int ns = sm.nsymq[b][lane];
-      const float2* sq = sm.symq[b] + lane * kSsSymPitch;
+      const float2* sq = symq0 + (b * 32 + lane) * sym_pitch;
       const CostasState K0 = K;
       const DiffState D0 = D;
       const long long nb0 = nb;
@@ -429,7 +457,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 2 ? 3 : (MFW == 4 ? 2 : 
 #pragma unroll 2
       for (int k = 0; k < ns; ++k) {
         const float2 in = nxt;
-        nxt = sq[k + 1];                                 // row pitch kSsSymCap + 1: in bounds for every k < ns
+        nxt = sq[k + 1];                                 // row pitch >= symbols per round + 1: in bounds for every k < ns
         float rI, rQ;
         unsigned sI, sQ;
         costas_step_fast2(CP, SK, magic, K, in.x, in.y, rI, rQ, sI, sQ, wild);
@@ -1056,7 +1084,21 @@ struct DemodEngine {
     }();
     return env_on && mf.mode == QPSK_FIR_EXACT && mf.real_taps && mf.n_taps <= kMfMaxTaps && mf.n_taps >= 1;
   }
-  int mf_warps() const { return mf.n_taps <= 24 ? 2 : 4; }
+  // matched-filter warps per 32-channel CTA.  One round costs a Mueller-Muller warp ~340 cycles per symbol; the filter
+  // needs ~70 issue slots per tap for the round's 32 outputs.  Small batches have SMs to spare and take the latency-safe
+  // choice; from ~8192 channels on the CTAs have to share SMs, and a single filter warp keeps four CTAs resident per SM
+  // (QPSK_DEMOD_MF_WARPS overrides).
+  int mf_warps() const {
+    static const int env = [] {
+      const char* e = getenv("QPSK_DEMOD_MF_WARPS");
+      return e ? atoi(e) : 0;
+    }();
+    if (env == 1 || env == 2 || env == 4) return env;
+    const double round_cycles = 340.0 * (double)kSsBlock / sps;
+    const double mf_slots = 100.0 * mf.n_taps;
+    if (channels >= 8192 && mf_slots <= 0.5 * round_cycles) return 1;
+    return (mf_slots <= 0.8 * round_cycles) ? 2 : 4;
+  }
 
   // one launch of the symbol-stage kernel over `len` samples at `xin` (matched-filter output, or — with_mf — its input)
   int launch_symsync(const float2* xin, int64_t len, int64_t ldin, uint8_t* raw, long long ld_raw, long long* n_raw, int append,
@@ -1066,23 +1108,33 @@ struct DemodEngine {
     MfArgs ma;
     ma.hist_in = nullptr; ma.hist_out = nullptr; ma.HL = 0;
     const int grid = (channels + 31) / 32;
+    // most symbols one round of kSsBlock samples (+ the carried ones) can emit: every symbol advances >= sps - 0.1
+    int sym_cap = (int)((double)(kSsBlock + kSsCarry) / (sps - 0.1)) + 2;
+    if (sym_cap > kSsSymCap) sym_cap = kSsSymCap;
+    const int sym_pitch = (sym_cap + 1) | 1;         // + 1: the decode loop reads one slot ahead; odd: bank spread
+    const int ring_n = (mf.n_taps - 1 <= 32) ? 96 : 128;
+    const size_t symq_bytes = (size_t)2 * 32 * sym_pitch * sizeof(float2);
 #define QPSK_SS_ARGS mm.P, mm.d_state.p, mm.d_queue[mm.qcur].p, mm.d_queue[mm.qcur ^ 1].p, mm.qcap, costas.P, costas.d_state.p, \
-                     d_diff.p, channels, xin, len, ldin, raw, ld_raw, n_raw, d_nsym.p, append, mt, ma
+                     d_diff.p, channels, xin, len, ldin, raw, ld_raw, n_raw, d_nsym.p, append, mt, ma, ring_n, sym_pitch
     if (!with_mf) {
-      if (diff) symsync_decode_kernel<true, 0><<<grid, 64, 0, s>>>(QPSK_SS_ARGS);
-      else symsync_decode_kernel<false, 0><<<grid, 64, 0, s>>>(QPSK_SS_ARGS);
+      if (diff) symsync_decode_kernel<true, 0><<<grid, 64, symq_bytes, s>>>(QPSK_SS_ARGS);
+      else symsync_decode_kernel<false, 0><<<grid, 64, symq_bytes, s>>>(QPSK_SS_ARGS);
     } else {
       const int N = mf.n_taps;
       mt.n_taps = N;
       for (int i = 0; i < N; ++i) mt.rev[i] = mf.taps_iq[2 * (N - 1 - i)];
       ma.hist_in = mf.hist[mf.cur].p; ma.hist_out = mf.hist[mf.cur ^ 1].p; ma.HL = mf.HL;
-      const size_t smem = (size_t)32 * kMfRingPitch * sizeof(float2);
+      const size_t smem = symq_bytes + (size_t)32 * (ring_n + 1) * sizeof(float2);
       const int w = mf_warps();
       const void* kp = nullptr;
-      if (w == 2) kp = diff ? (const void*)symsync_decode_kernel<true, 2> : (const void*)symsync_decode_kernel<false, 2>;
+      if (w == 1) kp = diff ? (const void*)symsync_decode_kernel<true, 1> : (const void*)symsync_decode_kernel<false, 1>;
+      else if (w == 2) kp = diff ? (const void*)symsync_decode_kernel<true, 2> : (const void*)symsync_decode_kernel<false, 2>;
       else kp = diff ? (const void*)symsync_decode_kernel<true, 4> : (const void*)symsync_decode_kernel<false, 4>;
       QPSK_TRY(allow_max_dynamic_smem(kp));
-      if (w == 2) {
+      if (w == 1) {
+        if (diff) symsync_decode_kernel<true, 1><<<grid, 96, smem, s>>>(QPSK_SS_ARGS);
+        else symsync_decode_kernel<false, 1><<<grid, 96, smem, s>>>(QPSK_SS_ARGS);
+      } else if (w == 2) {
         if (diff) symsync_decode_kernel<true, 2><<<grid, 128, smem, s>>>(QPSK_SS_ARGS);
         else symsync_decode_kernel<false, 2><<<grid, 128, smem, s>>>(QPSK_SS_ARGS);
       } else {

@@ -716,18 +716,26 @@ __device__ __forceinline__ void dec_block(const float2* __restrict__ xk, const T
   }
 }
 
-template <int RO, int NT, int DEC>
-__global__ void __launch_bounds__(NT, 2)
+// Threads = NTO output chunks x NG phase groups: group g of a chunk handles DEC/2/NG of the phase pairs and the groups'
+// partial sums are added through shared memory, so that every decimation factor stages the same ~3600-sample tile with
+// the same 256 threads (a wider D would otherwise leave a handful of threads to load a tile).
+template <int RO, int NTO, int NG, int DEC>
+__global__ void __launch_bounds__(NTO * NG, 3)
     fir_decim_kernel(const __grid_constant__ DecArgs a, const __grid_constant__ TapsReal taps) {
-  static_assert(DEC % 2 == 0, "phases are handled in pairs (one LDS.128)");
+  static_assert(DEC % 2 == 0 && (DEC / 2) % NG == 0, "phase pairs split evenly over the groups");
+  constexpr int NT = NTO * NG;
   constexpr int SPAN = RO * DEC;                 // input samples under one thread's outputs
   constexpr int PADS = (DEC == 2) ? 0 : 2;       // float2 slots of padding after every span
   constexpr int PITCH = SPAN + PADS;
-  constexpr int T_OUT = RO * NT;
+  constexpr int T_OUT = RO * NTO;
   constexpr int W = 2 * RO;
+  constexpr int PP = DEC / 2 / NG;               // phase pairs per group
+  constexpr int LB = 8;                          // staged loads in flight per thread
   extern __shared__ __align__(16) unsigned char smem_dec[];
-  float2* xs = reinterpret_cast<float2*>(smem_dec);
+  float2* ys = reinterpret_cast<float2*>(smem_dec);          // [NG][T_OUT] partial sums
+  float2* xs = ys + NG * T_OUT;
   const int tid = threadIdx.x;
+  const int to = tid % NTO, grp = tid / NTO;
   const int K = a.K;
   const int E = (T_OUT + K) * DEC;               // staged samples: the tile, the halo and the window's one-step look-ahead
   for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
@@ -737,22 +745,34 @@ __global__ void __launch_bounds__(NT, 2)
     const long long s0 = (long long)a.skip + m0 * DEC - a.HL;          // stream index of logical xs[0]
     const float2* xch = a.x + (long long)ch * a.ldx;
     const float2* hch = a.hist_in + (long long)ch * a.HL;
-    for (int e = tid; e < E; e += NT) {
-      const long long s = s0 + e;
-      float2 v = make_float2(0.f, 0.f);
-      if (s < 0) {
-        if (s >= -(long long)a.HL) v = hch[a.HL + s];
-      } else if (s < a.L) {
-        v = xch[s];
+    for (int e0 = tid; e0 < E; e0 += NT * LB) {
+      float2 v[LB];
+#pragma unroll
+      for (int b = 0; b < LB; ++b) {             // LB independent loads, then LB stores: the loads overlap
+        const int e = e0 + b * NT;
+        const long long sidx = s0 + e;
+        v[b] = make_float2(0.f, 0.f);
+        if (e < E) {
+          if (sidx < 0) {
+            if (sidx >= -(long long)a.HL) v[b] = hch[a.HL + sidx];
+          } else if (sidx < a.L) {
+            v[b] = xch[sidx];
+          }
+        }
       }
-      xs[e + PADS * (e / SPAN)] = v;
+#pragma unroll
+      for (int b = 0; b < LB; ++b) {
+        const int e = e0 + b * NT;
+        if (e < E) xs[e + PADS * (e / SPAN)] = v[b];
+      }
     }
     __syncthreads();
     float2 acc[RO];
 #pragma unroll
     for (int r = 0; r < RO; ++r) acc[r] = make_float2(0.f, 0.f);
-    const float2* xb = xs + tid * PITCH;
-    for (int pair = 0; pair < DEC / 2; ++pair) {
+    const float2* xb = xs + to * PITCH;
+    for (int pp = 0; pp < PP; ++pp) {
+      const int pair = grp * PP + pp;
       float2 wA[W], wB[W];
       const float2* xp = xb + 2 * pair;
 #pragma unroll
@@ -774,12 +794,24 @@ __global__ void __launch_bounds__(NT, 2)
         default: break;
       }
     }
-    float2* yc = a.y + (long long)ch * a.ldy + m0 + (long long)tid * RO;
-    const long long left = a.n_out - (m0 + (long long)tid * RO);
+    // partial sums -> shared memory -> one coalesced store per output (the groups' partials added on the way out)
+    float2* yp = ys + grp * T_OUT + to * RO;
 #pragma unroll
-    for (int r = 0; r < RO; ++r)
-      if (r < left) yc[r] = acc[r];
-    __syncthreads();                             // the tile's samples are dead: the next tile may overwrite them
+    for (int r = 0; r < RO; ++r) yp[r] = acc[r];
+    __syncthreads();
+    float2* yc = a.y + (long long)ch * a.ldy + m0;
+    const long long left = a.n_out - m0;
+    for (int o = tid; o < T_OUT && o < left; o += NT) {
+      float2 sum = ys[o];
+#pragma unroll
+      for (int g2 = 1; g2 < NG; ++g2) {
+        const float2 p = ys[g2 * T_OUT + o];
+        sum.x += p.x;
+        sum.y += p.y;
+      }
+      yc[o] = sum;
+    }
+    __syncthreads();                             // tile and partial sums are dead: the next tile may overwrite them
   }
 }
 
@@ -1078,11 +1110,12 @@ int FirEngine::decimate_dev(const float2* x, int64_t L, int64_t ldx, int dec, fl
       const int j = HL - i;
       t.g[i] = (j < N) ? taps_iq[2 * j] : 0.0f;
     }
-    auto go = [&](auto kern, int T_OUT, int SPAN, int PADS) -> int {
+    auto go = [&](auto kern, int NTO, int NG, int PADS) -> int {
+      const int T_OUT = 7 * NTO, SPAN = 7 * dec;
       a.tiles_per_ch = (int)((nout + T_OUT - 1) / T_OUT);
       a.total_tiles = (long long)a.tiles_per_ch * channels;
       const int E = (T_OUT + K) * dec;
-      const size_t smem = (size_t)(E + PADS * (E / SPAN + 1)) * sizeof(float2);
+      const size_t smem = (size_t)(NG * T_OUT + E + PADS * (E / SPAN + 1)) * sizeof(float2);
       if (smem > 200 * 1024) return QPSK_ERR_UNSUPPORTED;
       QPSK_TRY(allow_max_dynamic_smem((const void*)kern));
       long long per_sm = (long long)(224 * 1024) / (long long)(smem + 1024);
@@ -1090,16 +1123,16 @@ int FirEngine::decimate_dev(const float2* x, int64_t L, int64_t ldx, int dec, fl
       if (per_sm < 1) per_sm = 1;
       long long grid = per_sm * device_sm_count();
       if (grid > a.total_tiles) grid = a.total_tiles;
-      kern<<<(int)grid, (dec == 2 || dec == 4) ? 256 : (dec == 8 ? 128 : 64), smem, s>>>(a, t);
+      kern<<<(int)grid, NTO * NG, smem, s>>>(a, t);
       QPSK_LAUNCH_CHECK();
       return QPSK_OK;
     };
     int st = QPSK_ERR_UNSUPPORTED;
     switch (dec) {
-      case 2: st = go(fir_decim_kernel<7, 256, 2>, 7 * 256, 14, 0); last_kernel = "fir_decim_kernel<RO=7,NT=256,D=2>"; break;
-      case 4: st = go(fir_decim_kernel<7, 256, 4>, 7 * 256, 28, 2); last_kernel = "fir_decim_kernel<RO=7,NT=256,D=4>"; break;
-      case 8: st = go(fir_decim_kernel<7, 128, 8>, 7 * 128, 56, 2); last_kernel = "fir_decim_kernel<RO=7,NT=128,D=8>"; break;
-      case 16: st = go(fir_decim_kernel<7, 64, 16>, 7 * 64, 112, 2); last_kernel = "fir_decim_kernel<RO=7,NT=64,D=16>"; break;
+      case 2: st = go(fir_decim_kernel<7, 256, 1, 2>, 256, 1, 0); last_kernel = "fir_decim_kernel<RO=7,NTO=256,NG=1,D=2>"; break;
+      case 4: st = go(fir_decim_kernel<7, 128, 2, 4>, 128, 2, 2); last_kernel = "fir_decim_kernel<RO=7,NTO=128,NG=2,D=4>"; break;
+      case 8: st = go(fir_decim_kernel<7, 64, 4, 8>, 64, 4, 2); last_kernel = "fir_decim_kernel<RO=7,NTO=64,NG=4,D=8>"; break;
+      case 16: st = go(fir_decim_kernel<7, 32, 8, 16>, 32, 8, 2); last_kernel = "fir_decim_kernel<RO=7,NTO=32,NG=8,D=16>"; break;
     }
     if (st == QPSK_OK) launched = true;
     else if (st != QPSK_ERR_UNSUPPORTED) return st;

@@ -112,7 +112,7 @@ def test_decimate_dev_full_size_properties(gpu, orc):
         f = gpu.ComplexFIRFilter(taps)
         assert f.decimate_dev(x.data_ptr(), 2 * n, dec, y.data_ptr(), y.numel(), stream=s) == y.numel()
         torch.cuda.synchronize()
-        tile = 7 * (256 if dec == 2 else 128)                   # decimated outputs per tile
+        tile = 7 * (256 if dec == 2 else 64)                    # decimated outputs per tile
         for m0 in (0, tile - 3, 5 * tile - 3, n // dec - 300):
             a = max(0, m0 * dec - 200)                          # input window with 200 samples of run-in (> 128 taps)
             b = min(n, (m0 + 300) * dec)

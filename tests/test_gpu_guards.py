@@ -76,7 +76,7 @@ def test_fir_dev_outputs_stay_in_bounds_and_repeat(gpu, L):
 def test_decimate_dev_outputs_stay_in_bounds_and_repeat(gpu, dec):
     import torch
     taps = gpu.real_taps_to_iq(gpu.RRCFilter.generateCoefficents(16, 0.35, 4000, 1000))
-    for L in (1, dec - 1, dec, 7 * 256 * dec - 1, 7 * 256 * dec + 1, 30011):
+    for L in (1, dec - 1, dec, 7 * 256 * dec - 1, 7 * 256 * dec + 1, 7 * 32 * dec + 1, 30011):
         if L < 1:
             continue
         C = 2

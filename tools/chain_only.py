@@ -13,7 +13,7 @@ elif which == 'sweep':
     r = {}
     for C in (1024, 2048, 4096, 8192, 16384):
         for fll in (False, True):
-            o = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=2, warmup=2, use_fll=fll, channels_per_gpu=C)
+            o = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=3, warmup=2, use_fll=fll, channels_per_gpu=C, parity_channels=0)
             r[f"{C}{'_fll' if fll else ''}"] = {"msamples_s": o["value"], "ms": o["ms_per_step"], "launches": o["gpu_launches"]}
 elif which == 'chain':
     r = bench_chain.run_chain(Q, torch, None, 1, 0, s, steps=ST, warmup=3, use_fll=False)
