@@ -146,13 +146,42 @@ __device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
   return d;
 }
 
+// One output through the reference's full complex product (hq = +0): the path for outputs whose real-tap reduction came
+// out non-finite — an infinite SAMPLE makes the reference's hq*x terms NaN (0 * Inf), which the reduction does not model
+// (see fir_exact_real_kernel).  Out of line: it practically never runs.
+__device__ __noinline__ float2 mf_output_full(const float2* __restrict__ ring_ch, int ring_n, const MfTaps& T, int fmod) {
+  const int N = T.n_taps;
+  const int n_vec = N & ~7;
+  float lI[8], lQ[8];
+  for (int l = 0; l < 8; ++l) lI[l] = lQ[l] = 0.f;
+  const float hq = 0.f;
+  for (int i = 0; i < n_vec; ++i) {
+    const float2 xv = ring_ch[(fmod + i) % ring_n];
+    const float hi = T.rev[i];
+    lI[i & 7] = __fadd_rn(lI[i & 7], __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y)));
+    lQ[i & 7] = __fadd_rn(lQ[i & 7], __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x)));
+  }
+  float aI = 0.f, aQ = 0.f;
+  for (int l = 0; l < 8; ++l) {
+    aI = __fadd_rn(aI, lI[l]);
+    aQ = __fadd_rn(aQ, lQ[l]);
+  }
+  for (int i = n_vec; i < N; ++i) {
+    const float2 xv = ring_ch[(fmod + i) % ring_n];
+    const float hi = T.rev[i];
+    aI = __fadd_rn(aI, __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y)));
+    aQ = __fadd_rn(aQ, __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x)));
+  }
+  return make_float2(aI, aQ);
+}
+
 // outputs j0 .. j1-1 (< blk) of round q for this lane's channel: sample n = 32q + j, window element i = raw[n-(N-1)+i].
 // Four outputs per pass (32 independent lane partials: the warp runs alone on its scheduler, so the parallelism has to come
-// from inside the thread), the tail samples fetched ahead of the lane sums.
+// from inside the thread).  All register arrays keep compile-time indices; the ring wrap is resolved once per block of
+// eight taps (warp-uniform branch), so the common case loads with immediate offsets.
 constexpr int kMfR = 4;
 __device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int ring_n, const MfTaps& T, float2 nz, int q, int j0,
                                          int j1, int blk, float2* __restrict__ out_ch) {
-  auto wrap = [ring_n](int i) { return i >= ring_n ? i - ring_n : i; };   // 0 <= i < 2*ring_n
   const int N = T.n_taps;
   const int n_vec = N & ~7;
   const int n_tail = N - n_vec;                   // 0..7
@@ -167,12 +196,21 @@ __device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int
 #pragma unroll
       for (int l = 0; l < 8; ++l) lp[r][l] = make_float2(0.f, 0.f);
     float2 wv[8 + kMfR - 1];
-#pragma unroll
-    for (int k = 0; k < kMfR - 1; ++k) wv[k] = ring_ch[wrap(bmod + k)];
+    // window elements bmod + k0 .. bmod + k1 - 1 into wv[k0 .. k1)
+#define QPSK_MF_LOAD(DST, K0, K1)                                                             \
+    if (bmod + (K1) <= ring_n) {                                                              \
+      _Pragma("unroll") for (int k = (K0); k < (K1); ++k) DST[k] = ring_ch[bmod + k];          \
+    } else {                                                                                  \
+      _Pragma("unroll") for (int k = (K0); k < (K1); ++k) {                                    \
+        const int idx = bmod + k;                                                             \
+        DST[k] = ring_ch[idx >= ring_n ? idx - ring_n : idx];                                 \
+      }                                                                                       \
+    }
+    QPSK_MF_LOAD(wv, 0, kMfR - 1)
     for (int ib = 0; ib < n_vec; ib += 8) {
-#pragma unroll
-      for (int k = kMfR - 1; k < 8 + kMfR - 1; ++k) wv[k] = ring_ch[wrap(bmod + k)];
-      bmod = wrap(bmod + 8);
+      QPSK_MF_LOAD(wv, kMfR - 1, 8 + kMfR - 1)
+      bmod += 8;
+      if (bmod >= ring_n) bmod -= ring_n;
 #pragma unroll
       for (int l = 0; l < 8; ++l) {
         const float g = T.rev[ib + l];
@@ -183,11 +221,11 @@ __device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int
 #pragma unroll
       for (int k = 0; k < kMfR - 1; ++k) wv[k] = wv[8 + k];
     }
-    // tail window: elements n_vec .. N-1 (+ kMfR-1), loaded before the dependent lane sums start
+    // tail window: elements n_vec .. N-1 (+ kMfR-1); loaded in full (slots past the window hold other valid samples of
+    // the ring and are multiplied by nothing) before the dependent lane sums start
     float2 tw[7 + kMfR - 1];
-#pragma unroll
-    for (int k = 0; k < 7 + kMfR - 1; ++k)
-      tw[k] = (k < n_tail + kMfR - 1) ? ring_ch[wrap(bmod + k)] : make_float2(0.f, 0.f);
+    QPSK_MF_LOAD(tw, 0, 7 + kMfR - 1)
+#undef QPSK_MF_LOAD
     float2 acc[kMfR];
 #pragma unroll
     for (int r = 0; r < kMfR; ++r) {
@@ -204,37 +242,18 @@ __device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int
         for (int r = 0; r < kMfR; ++r) acc[r] = add2_rn(acc[r], mul2_rounded(tw[i + r], gg, nz));
       }
     }
-    // an infinite SAMPLE makes the reference's hq*x terms NaN (hq = +0: 0 * Inf), which the real-tap reduction does not
-    // model: recompute such outputs with the full complex product (see fir_exact_real_kernel)
-#pragma unroll 1
-    for (int r = 0; r < kMfR; ++r) {
-      if (!(fabsf(acc[r].x) <= 3.402823466e+38f) || !(fabsf(acc[r].y) <= 3.402823466e+38f)) {
-        float lI[8], lQ[8];
-        for (int l = 0; l < 8; ++l) lI[l] = lQ[l] = 0.f;
-        const float hq = 0.f;
-        for (int i = 0; i < n_vec; ++i) {
-          const float2 xv = ring_ch[(fmod + i + r) % ring_n];
-          const float hi = T.rev[i];
-          lI[i & 7] = __fadd_rn(lI[i & 7], __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y)));
-          lQ[i & 7] = __fadd_rn(lQ[i & 7], __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x)));
-        }
-        float aI = 0.f, aQ = 0.f;
-        for (int l = 0; l < 8; ++l) {
-          aI = __fadd_rn(aI, lI[l]);
-          aQ = __fadd_rn(aQ, lQ[l]);
-        }
-        for (int i = n_vec; i < N; ++i) {
-          const float2 xv = ring_ch[(fmod + i + r) % ring_n];
-          const float hi = T.rev[i];
-          aI = __fadd_rn(aI, __fsub_rn(__fmul_rn(hi, xv.x), __fmul_rn(hq, xv.y)));
-          aQ = __fadd_rn(aQ, __fadd_rn(__fmul_rn(hi, xv.y), __fmul_rn(hq, xv.x)));
-        }
-        const float2 fix = make_float2(aI, aQ);
-        // acc[] must keep compile-time indices (registers): select instead of a dynamically indexed store
+    bool bad = false;
 #pragma unroll
-        for (int rr = 0; rr < kMfR; ++rr)
-          if (rr == r) acc[rr] = fix;
-      }
+    for (int r = 0; r < kMfR; ++r)
+      bad |= !(fabsf(acc[r].x) <= 3.402823466e+38f) || !(fabsf(acc[r].y) <= 3.402823466e+38f);
+    if (bad) {
+#pragma unroll
+      for (int r = 0; r < kMfR; ++r)
+        if (!(fabsf(acc[r].x) <= 3.402823466e+38f) || !(fabsf(acc[r].y) <= 3.402823466e+38f)) {
+          int fm = fmod + r;
+          if (fm >= ring_n) fm -= ring_n;
+          acc[r] = mf_output_full(ring_ch, ring_n, T, fm);
+        }
     }
 #pragma unroll
     for (int r = 0; r < kMfR; ++r)

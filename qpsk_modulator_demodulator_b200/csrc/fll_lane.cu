@@ -25,6 +25,28 @@ namespace {
 constexpr int kLaneBlock = 32;            // samples per staged round
 constexpr int kLanePitch = 33;            // float2 row pitch of the staging tiles
 
+// packed (I, Q) arithmetic with every product and sum rounded on its own, as RyuJIT emits them:
+//   product  fma.rn.f32x2 with an addend of -0 loaded at run time: fma(x, g, -0) == round(x*g) exactly, and ptxas cannot
+//            contract it into the add that follows (it does contract mul.rn.f32x2 + add.rn.f32x2 into one FFMA2);
+//   sum      add.rn.f32x2 / sub.rn.f32x2 (FADD2, the subtraction as an operand negation).
+// One FFMA2, two FMUL and four FADD2 per tap instead of four FMUL and eight FADD: the same 12 FP32-pipe cycles, 7 issue
+// slots instead of 12 — and this kernel runs one warp per scheduler, i.e. it is bound by its own issue stream.
+__device__ float2 g_lane_neg_zero2 = {-0.0f, -0.0f};
+__device__ __forceinline__ float2 lane_add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 lane_sub2(float2 a, float2 b) {
+  float2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+
 template <int N>
 struct LaneTaps {
   float i[N], q[N];                       // reversed lower-filter taps (rev[k] = lower[N-1-k])
@@ -72,6 +94,8 @@ __global__ void __launch_bounds__(32)
   }
   const float2 pf = pf_g[cc];
   float phase = pf.x, freq = pf.y;
+  float2 nz;
+  asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(nz.x), "=f"(nz.y) : "l"(&g_lane_neg_zero2));
   int pos = 0;
   const int rows = (C - c0 < 32) ? (C - c0) : 32;
 
@@ -99,34 +123,39 @@ __global__ void __launch_bounds__(32)
       pos = (pos + 1 == N) ? 0 : pos + 1;
       // ComplexDotWindow (FIRFilter.cs:165-192) for both band-edge filters at once: upper = conj(lower)
       // (Band-Edge Filter.cs:176-178) shares the four products, see fll_step
-      float loI[8], loQ[8], upI[8], upQ[8];
+      // lo[l] = (loI, loQ), up[l] = (upI, upQ).  With P = (p1, p3) = a*(vI, vQ) and D = (-p2, p4) = ((-b)*vQ, b*vI):
+      //   lo += P + D = (p1 - p2, p3 + p4)      up += P - D = (p1 + p2, p3 - p4)      (fll_step's four sums, same roundings)
+      float2 lo[8], up[8];
 #pragma unroll
-      for (int l = 0; l < 8; ++l) loI[l] = loQ[l] = upI[l] = upQ[l] = 0.f;
+      for (int l = 0; l < 8; ++l) lo[l] = up[l] = make_float2(0.f, 0.f);
       constexpr int nVec = N - (N & 7);
 #pragma unroll
       for (int i = 0; i < nVec; ++i) {
         const float2 v = win[i * 32];
         const float4 t4 = tap4[i >> 1];
         const float a = (i & 1) ? t4.z : t4.x, b = (i & 1) ? t4.w : t4.y;
-        const float p1 = a * v.x, p2 = b * v.y, p3 = a * v.y, p4 = b * v.x;
-        loI[i & 7] = loI[i & 7] + (p1 - p2);
-        loQ[i & 7] = loQ[i & 7] + (p3 + p4);
-        upI[i & 7] = upI[i & 7] + (p1 + p2);
-        upQ[i & 7] = upQ[i & 7] + (p3 - p4);
+        const float2 Pp = ffma2(v, make_float2(a, a), nz);
+        const float2 Dd = make_float2(__fmul_rn(-b, v.y), __fmul_rn(b, v.x));
+        lo[i & 7] = lane_add2(lo[i & 7], lane_add2(Pp, Dd));
+        up[i & 7] = lane_add2(up[i & 7], lane_sub2(Pp, Dd));
       }
-      float aLoI = 0.f, aLoQ = 0.f, aUpI = 0.f, aUpQ = 0.f;
+      float2 aLo = make_float2(0.f, 0.f), aUp = make_float2(0.f, 0.f);
 #pragma unroll
       for (int l = 0; l < 8; ++l) {
-        aLoI += loI[l]; aLoQ += loQ[l]; aUpI += upI[l]; aUpQ += upQ[l];
+        aLo = lane_add2(aLo, lo[l]);
+        aUp = lane_add2(aUp, up[l]);
       }
 #pragma unroll
       for (int i = nVec; i < N; ++i) {
         const float2 v = win[i * 32];
         const float4 t4 = tap4[i >> 1];
         const float a = (i & 1) ? t4.z : t4.x, b = (i & 1) ? t4.w : t4.y;
-        const float p1 = a * v.x, p2 = b * v.y, p3 = a * v.y, p4 = b * v.x;
-        aLoI += (p1 - p2); aLoQ += (p3 + p4); aUpI += (p1 + p2); aUpQ += (p3 - p4);
+        const float2 Pp = ffma2(v, make_float2(a, a), nz);
+        const float2 Dd = make_float2(__fmul_rn(-b, v.y), __fmul_rn(b, v.x));
+        aLo = lane_add2(aLo, lane_add2(Pp, Dd));
+        aUp = lane_add2(aUp, lane_sub2(Pp, Dd));
       }
+      const float aLoI = aLo.x, aLoQ = aLo.y, aUpI = aUp.x, aUpQ = aUp.y;
       const float powUpper = aUpI * aUpI + aUpQ * aUpQ;  // :118
       const float powLower = aLoI * aLoI + aLoQ * aLoQ;  // :119
       const float error = powLower - powUpper;           // :121
