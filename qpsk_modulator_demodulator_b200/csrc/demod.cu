@@ -178,12 +178,17 @@ __device__ __noinline__ float2 mf_output_full(const float2* __restrict__ ring_ch
 // outputs j0 .. j1-1 (< blk) of round q for this lane's channel: sample n = 32q + j, window element i = raw[n-(N-1)+i].
 // Four outputs per pass (32 independent lane partials: the warp runs alone on its scheduler, so the parallelism has to come
 // from inside the thread).  All register arrays keep compile-time indices; the ring wrap is resolved once per block of
-// eight taps (warp-uniform branch), so the common case loads with immediate offsets.
+// eight taps (warp-uniform branch), so the common case loads with immediate offsets.  NB >= 0: the filter has exactly NB
+// blocks of eight taps (+ a tail of < 8) and its taps sit in registers `tg` (the modem's usual 17 / 21 taps: NB = 2);
+// NB < 0: any length, taps read from the constant bank.
 constexpr int kMfR = 4;
-__device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int ring_n, const MfTaps& T, float2 nz, int q, int j0,
-                                         int j1, int blk, float2* __restrict__ out_ch) {
+constexpr int kMfRegTaps = 31;                    // taps held in registers by the NB = 1..3 variants
+template <int NB>
+__device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int ring_n, const MfTaps& T,
+                                         const float (&tg)[kMfRegTaps], float2 nz, int q, int j0, int j1, int blk,
+                                         float2* __restrict__ out_ch) {
   const int N = T.n_taps;
-  const int n_vec = N & ~7;
+  const int n_vec = (NB >= 0) ? 8 * NB : (N & ~7);
   const int n_tail = N - n_vec;                   // 0..7
   for (int j = j0; j < j1 && j < blk; j += kMfR) {
     const int first = q * kSsBlock + j - (N - 1);
@@ -196,7 +201,7 @@ __device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int
 #pragma unroll
       for (int l = 0; l < 8; ++l) lp[r][l] = make_float2(0.f, 0.f);
     float2 wv[8 + kMfR - 1];
-    // window elements bmod + k0 .. bmod + k1 - 1 into wv[k0 .. k1)
+    // window elements bmod + k0 .. bmod + k1 - 1 into DST[k0 .. k1)
 #define QPSK_MF_LOAD(DST, K0, K1)                                                             \
     if (bmod + (K1) <= ring_n) {                                                              \
       _Pragma("unroll") for (int k = (K0); k < (K1); ++k) DST[k] = ring_ch[bmod + k];          \
@@ -206,23 +211,37 @@ __device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int
         DST[k] = ring_ch[idx >= ring_n ? idx - ring_n : idx];                                 \
       }                                                                                       \
     }
-    QPSK_MF_LOAD(wv, 0, kMfR - 1)
-    for (int ib = 0; ib < n_vec; ib += 8) {
-      QPSK_MF_LOAD(wv, kMfR - 1, 8 + kMfR - 1)
-      bmod += 8;
-      if (bmod >= ring_n) bmod -= ring_n;
-#pragma unroll
-      for (int l = 0; l < 8; ++l) {
-        const float g = T.rev[ib + l];
-        const float2 gg = make_float2(g, g);
-#pragma unroll
-        for (int r = 0; r < kMfR; ++r) lp[r][l] = add2_rn(lp[r][l], mul2_rounded(wv[l + r], gg, nz));
-      }
-#pragma unroll
-      for (int k = 0; k < kMfR - 1; ++k) wv[k] = wv[8 + k];
+#define QPSK_MF_BLOCK(TAP)                                                                    \
+    {                                                                                         \
+      QPSK_MF_LOAD(wv, kMfR - 1, 8 + kMfR - 1)                                                \
+      bmod += 8;                                                                              \
+      if (bmod >= ring_n) bmod -= ring_n;                                                     \
+      _Pragma("unroll") for (int l = 0; l < 8; ++l) {                                          \
+        const float g = TAP(l);                                                               \
+        const float2 gg = make_float2(g, g);                                                  \
+        _Pragma("unroll") for (int r = 0; r < kMfR; ++r)                                       \
+            lp[r][l] = add2_rn(lp[r][l], mul2_rounded(wv[l + r], gg, nz));                    \
+      }                                                                                       \
+      _Pragma("unroll") for (int k = 0; k < kMfR - 1; ++k) wv[k] = wv[8 + k];                  \
     }
-    // tail window: elements n_vec .. N-1 (+ kMfR-1); loaded in full (slots past the window hold other valid samples of
-    // the ring and are multiplied by nothing) before the dependent lane sums start
+    QPSK_MF_LOAD(wv, 0, kMfR - 1)
+    if constexpr (NB >= 0) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+#define QPSK_TAP_REG(l) tg[8 * b + (l)]
+        QPSK_MF_BLOCK(QPSK_TAP_REG)
+#undef QPSK_TAP_REG
+      }
+    } else {
+      for (int ib = 0; ib < n_vec; ib += 8) {
+#define QPSK_TAP_LDC(l) T.rev[ib + (l)]
+        QPSK_MF_BLOCK(QPSK_TAP_LDC)
+#undef QPSK_TAP_LDC
+      }
+    }
+#undef QPSK_MF_BLOCK
+    // tail window: elements n_vec .. N-1 (+ kMfR-1); loaded in full (slots past the window hold other samples of the ring
+    // and meet no tap) before the dependent lane sums start
     float2 tw[7 + kMfR - 1];
     QPSK_MF_LOAD(tw, 0, 7 + kMfR - 1)
 #undef QPSK_MF_LOAD
@@ -235,12 +254,12 @@ __device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int
     }
 #pragma unroll
     for (int i = 0; i < 7; ++i) {                                                  // scalar tail (:183-192)
-      if (i < n_tail) {
-        const float g = T.rev[n_vec + i];
-        const float2 gg = make_float2(g, g);
+      if (i >= n_tail) break;                                                      // warp-uniform
+      float g;
+      if constexpr (NB >= 0) g = tg[8 * NB + i]; else g = T.rev[n_vec + i];
+      const float2 gg = make_float2(g, g);
 #pragma unroll
-        for (int r = 0; r < kMfR; ++r) acc[r] = add2_rn(acc[r], mul2_rounded(tw[i + r], gg, nz));
-      }
+      for (int r = 0; r < kMfR; ++r) acc[r] = add2_rn(acc[r], mul2_rounded(tw[i + r], gg, nz));
     }
     bool bad = false;
 #pragma unroll
@@ -322,6 +341,24 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? 3 : 
     asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(nz.x), "=f"(nz.y) : "l"(&g_neg_zero2));
   }
   const int mf_per = (MFW > 0) ? (kSsBlock / (MFW > 0 ? MFW : 1)) : 0;   // outputs per matched-filter warp and round
+  // the filter's taps in registers when there are few enough (NB = 1..3 blocks of eight + tail)
+  float tg[kMfRegTaps];
+  const int mf_nb = (MFW > 0 && MT.n_taps >= 8 && MT.n_taps <= kMfRegTaps) ? (MT.n_taps >> 3) : -1;
+  if (MFW > 0 && role >= 2) {
+#pragma unroll
+    for (int i = 0; i < kMfRegTaps; ++i) tg[i] = MT.rev[i];
+  }
+  auto mf_dispatch = [&](int q, int blk_q) {
+    const float2* rc = mf_ring + lane * ring_pitch;
+    float2* oc = sm.raw[q & 1] + lane * kSsPitch;
+    const int j0 = (role - 2) * mf_per, j1 = (role - 1) * mf_per;
+    switch (mf_nb) {
+      case 1: mf_round<1>(rc, ring_n, MT, tg, nz, q, j0, j1, blk_q, oc); break;
+      case 2: mf_round<2>(rc, ring_n, MT, tg, nz, q, j0, j1, blk_q, oc); break;
+      case 3: mf_round<3>(rc, ring_n, MT, tg, nz, q, j0, j1, blk_q, oc); break;
+      default: mf_round<-1>(rc, ring_n, MT, tg, nz, q, j0, j1, blk_q, oc); break;
+    }
+  };
 
   // The Costas warp (which has the slack) also stages the samples: round r+1 is requested at the top of round r and
   // waited for before the barrier that ends it, so the Mueller-Muller warp finds its round in shared memory.
@@ -346,8 +383,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? 3 : 
   if (MFW > 0) {
     if (role >= 2 && rounds > 0) {
       const int blk0 = (int)(L < kSsBlock ? L : kSsBlock);
-      mf_round(mf_ring + lane * ring_pitch, ring_n, MT, nz, 0, (role - 2) * mf_per, (role - 1) * mf_per, blk0,
-               sm.raw[0] + lane * kSsPitch);
+      mf_dispatch(0, blk0);
     }
     __syncthreads();
   }
@@ -440,8 +476,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? 3 : 
       // matched filter of round r+1 (its raw samples landed before the barrier that ended round r-1)
       const long long n1 = (long long)(r + 1) * kSsBlock;
       const int blk1 = (int)((L - n1) < kSsBlock ? (L - n1) : kSsBlock);
-      mf_round(mf_ring + lane * ring_pitch, ring_n, MT, nz, r + 1, (role - 2) * mf_per, (role - 1) * mf_per, blk1,
-               sm.raw[(r + 1) & 1] + lane * kSsPitch);
+      mf_dispatch(r + 1, blk1);
     }
     if (role == 1 && r >= 1) {
       // ---- Costas + decision + differential decode (QPSKDeModulator.cs:374-408) on round r-1 ----
@@ -1114,9 +1149,9 @@ struct DemodEngine {
     }();
     if (env == 1 || env == 2 || env == 4) return env;
     const double round_cycles = 340.0 * (double)kSsBlock / sps;
-    const double mf_slots = 100.0 * mf.n_taps;
-    if (channels >= 8192 && mf_slots <= 0.5 * round_cycles) return 1;
-    return (mf_slots <= 0.8 * round_cycles) ? 2 : 4;
+    const double mf_slots = 110.0 * mf.n_taps;       // issue slots for the 32 outputs of one round (~3.4 per tap and output)
+    if (channels >= 8192) return (mf_slots <= 0.6 * round_cycles) ? 1 : 2;
+    return (mf_slots <= 0.2 * round_cycles) ? 2 : 4;
   }
 
   // one launch of the symbol-stage kernel over `len` samples at `xin` (matched-filter output, or — with_mf — its input)
