@@ -280,8 +280,10 @@ __device__ __forceinline__ void mf_round(const float2* __restrict__ ring_ch, int
   }
 }
 
-template <bool DIFF, int MFW>
-__global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? 3 : (MFW == 4 ? 2 : 1)))
+// DENSE: compiled for four resident CTAs per SM (a 128-register cap: some spills in the filter warps) — the choice when
+// the batch has more 32-channel CTAs than three per SM can hold, where one wave beats two
+template <bool DIFF, int MFW, bool DENSE = false>
+__global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? (DENSE ? 4 : 3) : (MFW == 4 ? 2 : 1)))
     symsync_decode_kernel(const MmParams MP, MmState* mm_g, const float2* __restrict__ q_in, float2* __restrict__ q_out,
                           long long qcap, const CostasParams CP, CostasState* cst_g, DiffState* dst_g, int C,
                           const float2* __restrict__ x, long long L, long long ldx, uint8_t* __restrict__ bits,
@@ -1150,8 +1152,7 @@ struct DemodEngine {
     if (env == 1 || env == 2 || env == 4) return env;
     const double round_cycles = 340.0 * (double)kSsBlock / sps;
     const double mf_slots = 110.0 * mf.n_taps;       // issue slots for the 32 outputs of one round (~3.4 per tap and output)
-    if (channels >= 8192) return (mf_slots <= 0.6 * round_cycles) ? 1 : 2;
-    return (mf_slots <= 0.2 * round_cycles) ? 2 : 4;
+    return (mf_slots <= 0.6 * round_cycles) ? 2 : 4;
   }
 
   // one launch of the symbol-stage kernel over `len` samples at `xin` (matched-filter output, or — with_mf — its input)
@@ -1181,13 +1182,18 @@ struct DemodEngine {
       const size_t smem = symq_bytes + (size_t)32 * (ring_n + 1) * sizeof(float2);
       const int w = mf_warps();
       const void* kp = nullptr;
+      const bool dense = w == 2 && grid > 3 * device_sm_count();
       if (w == 1) kp = diff ? (const void*)symsync_decode_kernel<true, 1> : (const void*)symsync_decode_kernel<false, 1>;
+      else if (w == 2 && dense) kp = diff ? (const void*)symsync_decode_kernel<true, 2, true> : (const void*)symsync_decode_kernel<false, 2, true>;
       else if (w == 2) kp = diff ? (const void*)symsync_decode_kernel<true, 2> : (const void*)symsync_decode_kernel<false, 2>;
       else kp = diff ? (const void*)symsync_decode_kernel<true, 4> : (const void*)symsync_decode_kernel<false, 4>;
       QPSK_TRY(allow_max_dynamic_smem(kp));
       if (w == 1) {
         if (diff) symsync_decode_kernel<true, 1><<<grid, 96, smem, s>>>(QPSK_SS_ARGS);
         else symsync_decode_kernel<false, 1><<<grid, 96, smem, s>>>(QPSK_SS_ARGS);
+      } else if (w == 2 && dense) {
+        if (diff) symsync_decode_kernel<true, 2, true><<<grid, 128, smem, s>>>(QPSK_SS_ARGS);
+        else symsync_decode_kernel<false, 2, true><<<grid, 128, smem, s>>>(QPSK_SS_ARGS);
       } else if (w == 2) {
         if (diff) symsync_decode_kernel<true, 2><<<grid, 128, smem, s>>>(QPSK_SS_ARGS);
         else symsync_decode_kernel<false, 2><<<grid, 128, smem, s>>>(QPSK_SS_ARGS);
