@@ -1138,6 +1138,9 @@ struct DemodEngine {
       const char* e = getenv("QPSK_DEMOD_FUSE_MF");
       return !(e && e[0] == '0');
     }();
+    // a lone CTA gains nothing from the fusion (the separate filter launch costs ~5 us) and its rounds run ~10 % slower
+    // with the filter warps on board: one radio stream (qpsk_stream_*, per-call DeModulateBytes) keeps the separate kernel
+    if (channels < 32) return false;
     return env_on && mf.mode == QPSK_FIR_EXACT && mf.real_taps && mf.n_taps <= kMfMaxTaps && mf.n_taps >= 1;
   }
   // matched-filter warps per 32-channel CTA.  One round costs a Mueller-Muller warp ~340 cycles per symbol; the filter
