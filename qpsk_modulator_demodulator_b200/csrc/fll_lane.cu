@@ -182,6 +182,167 @@ __global__ void __launch_bounds__(32)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// fll_pair_kernel: TWO lanes per stream, 16 streams per warp.  The lane-per-stream kernel above leaves 512 warps for 592
+// warp schedulers at 16384 streams — one in-order warp per scheduler, bound by its own issue stream and every stall in
+// it.  Here lane 2s + h of a warp owns the SIMD-lane partials 4h .. 4h+3 of stream s (ComplexDotWindow's eight partial
+// sums, FIRFilter.cs:165-192): half the taps per lane, twice the warps (two per scheduler at 16384 streams), and the
+// ordered horizontal sum ((((0 + L0) + L1) + ...) + L7) crosses the pair once — lane 2s sums L0..L3, hands the four values
+// over with shuffles, lane 2s+1 adds L4..L7 and the scalar tail, and the error goes back with one more shuffle, so both
+// lanes carry identical (phase, freq).  Same roundings in the same order as fll_step; same state layout in device memory.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kPairStreams = 16;
+constexpr int kPairPitch = 17;            // float2 row pitch of the staging tiles (odd)
+
+template <int N>
+__global__ void __launch_bounds__(32)
+    fll_pair_kernel(const FllParams P, const __grid_constant__ LaneTaps<N> T, float2* ring_g, int* head_g, float2* pf_g, int C,
+                    const float2* __restrict__ x, float2* __restrict__ y, long long L, long long ldx, long long ldy) {
+  __shared__ float2 ring[2 * N][kPairStreams];
+  __shared__ float2 xin[kLaneBlock][kPairPitch];
+  __shared__ float2 yout[kLaneBlock][kPairPitch];
+  __shared__ __align__(16) float4 tap4[(N + 1) / 2];
+  const int lane = threadIdx.x;
+  const int st = lane >> 1, h = lane & 1;
+  for (int k = lane; k < (N + 1) / 2; k += 32)
+    tap4[k] = make_float4(T.i[2 * k], T.q[2 * k], (2 * k + 1 < N) ? T.i[2 * k + 1] : 0.f, (2 * k + 1 < N) ? T.q[2 * k + 1] : 0.f);
+  const int c0 = blockIdx.x * kPairStreams;
+  const int c = c0 + st;
+  const bool live = c < C;
+  const int cc = live ? c : C - 1;        // idle pairs shadow the last stream (their results are dropped)
+  {
+    const int head = head_g[cc];
+    for (int j = h; j < N; j += 2) {      // the pair shares the copy
+      int k = head + j;
+      if (k >= N) k -= N;
+      const float2 v = ring_g[(long long)k * C + cc];
+      ring[j][st] = v;
+      ring[j + N][st] = v;
+    }
+  }
+  __syncwarp();
+  const float2 pf = pf_g[cc];
+  float phase = pf.x, freq = pf.y;
+  float2 nz;
+  asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(nz.x), "=f"(nz.y) : "l"(&g_lane_neg_zero2));
+  int pos = 0;
+  const int rows = (C - c0 < kPairStreams) ? (C - c0) : kPairStreams;
+  constexpr int nVec = N - (N & 7);
+
+  for (long long n0 = 0; n0 < L; n0 += kLaneBlock) {
+    const int blk = (int)((L - n0 < kLaneBlock) ? (L - n0) : kLaneBlock);
+    if (lane < blk) {                     // stage: lane l fetches sample n0 + l of every stream of the CTA
+#pragma unroll 8
+      for (int r = 0; r < kPairStreams; ++r) {
+        const int ch = c0 + (r < rows ? r : rows - 1);
+        xin[lane][r] = x[(long long)ch * ldx + n0 + lane];
+      }
+    }
+    __syncwarp();
+    for (int sidx = 0; sidx < blk; ++sidx) {
+      const float2 in = xin[sidx][st];
+      float sn, cs;
+      sincos_f32_fast(phase, &sn, &cs);                // MathF.Cos/Sin(phase) :108-109 (both lanes of the pair)
+      const float oI = in.x * cs - in.y * sn;          // :111
+      const float oQ = in.x * sn + in.y * cs;          // :112
+      if (h == 0) {
+        yout[sidx][st] = make_float2(oI, oQ);
+        ring[pos][st] = make_float2(oI, oQ);           // over the oldest sample ...
+      } else {
+        ring[pos + N][st] = make_float2(oI, oQ);       // ... and its mirror
+      }
+      __syncwarp();
+      // window element i (oldest first) at win[i * 16]; this lane takes the elements with (i & 7) >> 2 == h
+      const int wb = pos + 1;                          // window start (slots wb .. wb + N - 1, thanks to the mirror)
+      const float2* win = &ring[wb + 4 * h][st];
+      pos = (pos + 1 == N) ? 0 : pos + 1;
+      float2 lo[4], up[4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) lo[l] = up[l] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < nVec; b += 8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 v = win[(b + j) * kPairStreams];
+          const float4 t4 = tap4[(b >> 1) + 2 * h + (j >> 1)];       // taps b + 4h + j (pairs (0,1), (2,3))
+          const float a = (j & 1) ? t4.z : t4.x, bq = (j & 1) ? t4.w : t4.y;
+          const float2 Pp = ffma2(v, make_float2(a, a), nz);
+          const float2 Dd = make_float2(__fmul_rn(-bq, v.y), __fmul_rn(bq, v.x));
+          lo[j] = lane_add2(lo[j], lane_add2(Pp, Dd));
+          up[j] = lane_add2(up[j], lane_sub2(Pp, Dd));
+        }
+      }
+      // lanes 0..3 summed by the even lane, handed over, lanes 4..7 added by the odd lane (:176-180)
+      float2 aLo = make_float2(0.f, 0.f), aUp = make_float2(0.f, 0.f);
+      if (h == 0) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          aLo = lane_add2(aLo, lo[l]);
+          aUp = lane_add2(aUp, up[l]);
+        }
+      }
+      const float gLoI = __shfl_xor_sync(0xffffffffu, aLo.x, 1), gLoQ = __shfl_xor_sync(0xffffffffu, aLo.y, 1);
+      const float gUpI = __shfl_xor_sync(0xffffffffu, aUp.x, 1), gUpQ = __shfl_xor_sync(0xffffffffu, aUp.y, 1);
+      float error = 0.f;
+      if (h == 1) {
+        aLo = make_float2(gLoI, gLoQ);
+        aUp = make_float2(gUpI, gUpQ);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          aLo = lane_add2(aLo, lo[l]);
+          aUp = lane_add2(aUp, up[l]);
+        }
+#pragma unroll
+        for (int i = nVec; i < N; ++i) {                               // scalar tail (:183-192)
+          const float2 v = ring[wb + i][st];
+          const float4 t4 = tap4[i >> 1];
+          const float a = (i & 1) ? t4.z : t4.x, bq = (i & 1) ? t4.w : t4.y;
+          const float2 Pp = ffma2(v, make_float2(a, a), nz);
+          const float2 Dd = make_float2(__fmul_rn(-bq, v.y), __fmul_rn(bq, v.x));
+          aLo = lane_add2(aLo, lane_add2(Pp, Dd));
+          aUp = lane_add2(aUp, lane_sub2(Pp, Dd));
+        }
+        const float powUpper = aUp.x * aUp.x + aUp.y * aUp.y;          // :118
+        const float powLower = aLo.x * aLo.x + aLo.y * aLo.y;          // :119
+        error = powLower - powUpper;                                   // :121
+      }
+      error = __shfl_sync(0xffffffffu, error, lane | 1);               // both lanes of the pair update the same state
+      freq += P.beta * error;                            // :124
+      phase += freq + P.alpha * error;                   // :125
+      if (phase > kTwoPiF || phase < -kTwoPiF) phase = lane_wrap_phase(phase);   // :185-189
+      if (freq > P.max_freq) freq = P.max_freq;          // :191-195
+      else if (freq < P.min_freq) freq = P.min_freq;
+    }
+    __syncwarp();
+    if (lane < blk) {                     // flush: lane l writes sample n0 + l of every live stream
+#pragma unroll 8
+      for (int r = 0; r < kPairStreams; ++r)
+        if (r < rows) y[(long long)(c0 + r) * ldy + n0 + lane] = yout[lane][r];
+    }
+    __syncwarp();
+  }
+  if (live) {
+    for (int j = h; j < N; j += 2) ring_g[(long long)j * C + c] = ring[pos + j][st];   // oldest first from slot `pos`
+    if (h == 0) {
+      head_g[c] = 0;
+      pf_g[c] = make_float2(phase, freq);
+    }
+  }
+}
+
+template <int N>
+int fll_pair_launch_n(const FllParams& P, const std::vector<float>& lower, float2* ring, int* head, float2* pf, int C,
+                      const float2* x, float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {
+  LaneTaps<N> T;
+  for (int k = 0; k < N; ++k) {
+    T.i[k] = lower[2 * (size_t)(N - 1 - k)];
+    T.q[k] = lower[2 * (size_t)(N - 1 - k) + 1];
+  }
+  fll_pair_kernel<N><<<(C + kPairStreams - 1) / kPairStreams, 32, 0, s>>>(P, T, ring, head, pf, C, x, y, L, ldx, ldy);
+  QPSK_LAUNCH_CHECK();
+  return QPSK_OK;
+}
+
 template <int N>
 int fll_lane_launch_n(const FllParams& P, const std::vector<float>& lower, float2* ring, int* head, float2* pf, int C,
                       const float2* x, float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {
@@ -198,6 +359,15 @@ int fll_lane_launch_n(const FllParams& P, const std::vector<float>& lower, float
 }  // namespace
 
 bool fll_lane_supported(int n_taps) { return n_taps == 40 || n_taps == 10; }
+
+int fll_pair_launch(const FllParams& P, const std::vector<float>& lower, float2* ring, int* head, float2* pf, int C,
+                    const float2* x, float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {
+  switch (P.n_taps) {
+    case 40: return fll_pair_launch_n<40>(P, lower, ring, head, pf, C, x, y, L, ldx, ldy, s);
+    case 10: return fll_pair_launch_n<10>(P, lower, ring, head, pf, C, x, y, L, ldx, ldy, s);
+    default: return QPSK_ERR_UNSUPPORTED;
+  }
+}
 
 int fll_lane_launch(const FllParams& P, const std::vector<float>& lower, float2* ring, int* head, float2* pf, int C,
                     const float2* x, float2* y, long long L, long long ldx, long long ldy, cudaStream_t s) {

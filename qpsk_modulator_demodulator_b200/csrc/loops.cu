@@ -382,6 +382,7 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
     if (e && strcmp(e, "thread") == 0) return 2;
     if (e && strcmp(e, "lane") == 0) return 3;               // "lane": one lane per stream at any stream count
     if (e && strcmp(e, "duo") == 0) return 4;                // "duo": never the lane kernel
+    if (e && strcmp(e, "pair") == 0) return 5;               // "pair": two lanes per stream at any stream count
     return 0;
   }();
   // From about 12000 streams on, the issue slots bound the two-warp kernel (44 warp instructions per stream and sample) and
@@ -392,12 +393,14 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
     const char* e = getenv("QPSK_FLL_LANE_MIN");
     return e ? atoi(e) : 12288;
   }();
-  const bool force_group = force_impl == 1 || force_impl == 2;
+  const bool force_group = force_impl == 1 || force_impl == 2;   // (3 = lane, 4 = duo, 5 = pair)
   // The two-warp kernel evaluates sin/cos and the phase wrap with short-range formulas (|phase| < 1e5): the loop
   // keeps |phase| <= 2*pi + max|freq|, so only a caller-set state or an absurd frequency limit (sps < 1e-3) can
   // leave that range — those calls take the generic kernels, which use the library routines.
   const bool wild = state_wild || !(P.max_freq < 1e4f);
   state_wild = false;                                          // any kernel leaves the state wrapped and clamped
+  if (!force_group && !wild && fll_lane_supported(n_taps) && force_impl == 5)
+    return fll_pair_launch(P, lower, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
   if (!force_group && !wild && fll_lane_supported(n_taps) && force_impl != 4 && (force_impl == 3 || channels >= lane_min))
     return fll_lane_launch(P, lower, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
   if (!force_group && !wild && fll_duo_supported(n_taps))

@@ -301,6 +301,9 @@ int fll_duo_launch(const FllParams& P, const float* taps, float2* ring, int* hea
 bool fll_lane_supported(int n_taps);
 int fll_lane_launch(const FllParams& P, const std::vector<float>& lower, float2* ring, int* head, float2* pf, int C,
                     const float2* x, float2* y, long long L, long long ldx, long long ldy, cudaStream_t s);
+// ... and two lanes per stream (16 streams per warp): twice the warps, half the taps per lane
+int fll_pair_launch(const FllParams& P, const std::vector<float>& lower, float2* ring, int* head, float2* pf, int C,
+                    const float2* x, float2* y, long long L, long long ldx, long long ldy, cudaStream_t s);
 
 struct MmEngine {
   int channels = 1;
