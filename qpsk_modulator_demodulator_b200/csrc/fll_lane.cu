@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(32)
   float phase = pf.x, freq = pf.y;
   float2 nz;
   asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(nz.x), "=f"(nz.y) : "l"(&g_lane_neg_zero2));
+  const SinCosK SK = sincos_load_consts();  // sin/cos constants pinned in registers (same arithmetic as sincos_f32_fast)
   int pos = 0;
   const int rows = (C - c0 < 32) ? (C - c0) : 32;
 
@@ -112,25 +113,20 @@ __global__ void __launch_bounds__(32)
     __syncwarp();
     for (int sidx = 0; sidx < blk; ++sidx) {
       const float2 in = xin[sidx][lane];
-      float s, cs;
-      sincos_f32_fast(phase, &s, &cs);                 // MathF.Cos/Sin(phase) :108-109
-      const float oI = in.x * cs - in.y * s;           // :111
-      const float oQ = in.x * s + in.y * cs;           // :112
-      yout[sidx][lane] = make_float2(oI, oQ);
-      ring[pos][lane] = make_float2(oI, oQ);           // over the oldest sample, and its mirror
-      ring[pos + N][lane] = make_float2(oI, oQ);
-      const float2* win = &ring[pos + 1][lane];        // window element i (oldest first) at win[i * 32]
-      pos = (pos + 1 == N) ? 0 : pos + 1;
-      // ComplexDotWindow (FIRFilter.cs:165-192) for both band-edge filters at once: upper = conj(lower)
-      // (Band-Edge Filter.cs:176-178) shares the four products, see fll_step
-      // lo[l] = (loI, loQ), up[l] = (upI, upQ).  With P = (p1, p3) = a*(vI, vQ) and D = (-p2, p4) = ((-b)*vQ, b*vI):
-      //   lo += P + D = (p1 - p2, p3 + p4)      up += P - D = (p1 + p2, p3 - p4)      (fll_step's four sums, same roundings)
+      // The window of this sample is the N-1 outputs already in the ring followed by the output about to be computed.
+      // Everything that multiplies the N-1 old elements comes FIRST in program order: it does not depend on the phase, so
+      // the in-order warp issues it inside the stalls of the sin/cos chain below (and its loads do not have to wait for
+      // this sample's store to the same array).  The newest element meets its tap from registers, last in its partial sum —
+      // the reference's order of additions (FIRFilter.cs:165-192) is unchanged.
+      const float2* win = &ring[pos + 1][lane];        // window element i (oldest first) at win[i * 32], i < N-1
       float2 lo[8], up[8];
 #pragma unroll
       for (int l = 0; l < 8; ++l) lo[l] = up[l] = make_float2(0.f, 0.f);
       constexpr int nVec = N - (N & 7);
+      constexpr int kNew = N - 1;                      // window index of the newest element
 #pragma unroll
       for (int i = 0; i < nVec; ++i) {
+        if (i == kNew) continue;
         const float2 v = win[i * 32];
         const float4 t4 = tap4[i >> 1];
         const float a = (i & 1) ? t4.z : t4.x, b = (i & 1) ? t4.w : t4.y;
@@ -138,6 +134,22 @@ __global__ void __launch_bounds__(32)
         const float2 Dd = make_float2(__fmul_rn(-b, v.y), __fmul_rn(b, v.x));
         lo[i & 7] = lane_add2(lo[i & 7], lane_add2(Pp, Dd));
         up[i & 7] = lane_add2(up[i & 7], lane_sub2(Pp, Dd));
+      }
+      float2 told[(N & 7) ? (N & 7) : 1];              // old tail elements, fetched early
+#pragma unroll
+      for (int i = nVec; i < N - 1; ++i) told[i - nVec] = win[i * 32];
+      float s, cs;
+      sincos_f32_fast_k(phase, SK, &s, &cs);           // MathF.Cos/Sin(phase) :108-109
+      const float oI = in.x * cs - in.y * s;           // :111
+      const float oQ = in.x * s + in.y * cs;           // :112
+      const float2 vnew = make_float2(oI, oQ);
+      if (kNew < nVec) {                               // N % 8 == 0: the newest element closes SIMD-lane partial 7
+        const float4 t4 = tap4[kNew >> 1];
+        const float a = (kNew & 1) ? t4.z : t4.x, b = (kNew & 1) ? t4.w : t4.y;
+        const float2 Pp = ffma2(vnew, make_float2(a, a), nz);
+        const float2 Dd = make_float2(__fmul_rn(-b, vnew.y), __fmul_rn(b, vnew.x));
+        lo[kNew & 7] = lane_add2(lo[kNew & 7], lane_add2(Pp, Dd));
+        up[kNew & 7] = lane_add2(up[kNew & 7], lane_sub2(Pp, Dd));
       }
       float2 aLo = make_float2(0.f, 0.f), aUp = make_float2(0.f, 0.f);
 #pragma unroll
@@ -147,7 +159,7 @@ __global__ void __launch_bounds__(32)
       }
 #pragma unroll
       for (int i = nVec; i < N; ++i) {
-        const float2 v = win[i * 32];
+        const float2 v = (i == kNew) ? vnew : told[(i - nVec) < ((N & 7) ? (N & 7) : 1) ? (i - nVec) : 0];
         const float4 t4 = tap4[i >> 1];
         const float a = (i & 1) ? t4.z : t4.x, b = (i & 1) ? t4.w : t4.y;
         const float2 Pp = ffma2(v, make_float2(a, a), nz);
@@ -164,6 +176,10 @@ __global__ void __launch_bounds__(32)
       if (phase > kTwoPiF || phase < -kTwoPiF) phase = lane_wrap_phase(phase);   // :185-189
       if (freq > P.max_freq) freq = P.max_freq;          // :191-195
       else if (freq < P.min_freq) freq = P.min_freq;
+      yout[sidx][lane] = vnew;
+      ring[pos][lane] = vnew;                          // over the oldest sample, and its mirror
+      ring[pos + N][lane] = vnew;
+      pos = (pos + 1 == N) ? 0 : pos + 1;
     }
     __syncwarp();
     // flush: lane l writes sample n0 + l of every live stream
@@ -225,6 +241,7 @@ __global__ void __launch_bounds__(32)
   float phase = pf.x, freq = pf.y;
   float2 nz;
   asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(nz.x), "=f"(nz.y) : "l"(&g_lane_neg_zero2));
+  const SinCosK SK = sincos_load_consts();
   int pos = 0;
   const int rows = (C - c0 < kPairStreams) ? (C - c0) : kPairStreams;
   constexpr int nVec = N - (N & 7);
@@ -241,29 +258,24 @@ __global__ void __launch_bounds__(32)
     __syncwarp();
     for (int sidx = 0; sidx < blk; ++sidx) {
       const float2 in = xin[sidx][st];
-      float sn, cs;
-      sincos_f32_fast(phase, &sn, &cs);                // MathF.Cos/Sin(phase) :108-109 (both lanes of the pair)
-      const float oI = in.x * cs - in.y * sn;          // :111
-      const float oQ = in.x * sn + in.y * cs;          // :112
-      if (h == 0) {
-        yout[sidx][st] = make_float2(oI, oQ);
-        ring[pos][st] = make_float2(oI, oQ);           // over the oldest sample ...
-      } else {
-        ring[pos + N][st] = make_float2(oI, oQ);       // ... and its mirror
-      }
-      __syncwarp();
-      // window element i (oldest first) at win[i * 16]; this lane takes the elements with (i & 7) >> 2 == h
-      const int wb = pos + 1;                          // window start (slots wb .. wb + N - 1, thanks to the mirror)
-      const float2* win = &ring[wb + 4 * h][st];
-      pos = (pos + 1 == N) ? 0 : pos + 1;
+      // old window elements first (independent of the phase: they fill the stalls of the sin/cos chain), the newest element
+      // — window index N-1, i.e. the odd lane's last tap — from registers afterwards; see fll_lane_kernel
+      const int wb = pos + 1;                          // window start (slots wb .. wb + N - 2 hold the N-1 old outputs)
+      const float2* win = &ring[wb + 4 * h][st];       // this lane takes the elements with (i & 7) >> 2 == h
+      constexpr int kNew = N - 1;
       float2 lo[4], up[4];
 #pragma unroll
       for (int l = 0; l < 4; ++l) lo[l] = up[l] = make_float2(0.f, 0.f);
+      float2 vlast = make_float2(0.f, 0.f);            // element b + 4h + j of the last block / j = 3 (old for the even lane)
 #pragma unroll
       for (int b = 0; b < nVec; b += 8) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 v = win[(b + j) * kPairStreams];
+          if (b + 4 + j == kNew) {                     // the odd lane's copy of this slot is the element being computed
+            vlast = v;
+            continue;
+          }
           const float4 t4 = tap4[(b >> 1) + 2 * h + (j >> 1)];       // taps b + 4h + j (pairs (0,1), (2,3))
           const float a = (j & 1) ? t4.z : t4.x, bq = (j & 1) ? t4.w : t4.y;
           const float2 Pp = ffma2(v, make_float2(a, a), nz);
@@ -271,6 +283,25 @@ __global__ void __launch_bounds__(32)
           lo[j] = lane_add2(lo[j], lane_add2(Pp, Dd));
           up[j] = lane_add2(up[j], lane_sub2(Pp, Dd));
         }
+      }
+      float2 told[(N & 7) ? (N & 7) : 1];              // old tail elements (only the odd lane uses them)
+#pragma unroll
+      for (int i = nVec; i < N - 1; ++i) told[i - nVec] = ring[wb + i][st];
+      float sn, cs;
+      sincos_f32_fast_k(phase, SK, &sn, &cs);          // MathF.Cos/Sin(phase) :108-109 (both lanes of the pair)
+      const float oI = in.x * cs - in.y * sn;          // :111
+      const float oQ = in.x * sn + in.y * cs;          // :112
+      const float2 vnew = make_float2(oI, oQ);
+      if (kNew < nVec) {
+        // last block, j = 3: window element N-5 (old, loaded above) for the even lane, N-1 (the new output) for the odd one
+        constexpr int b = nVec - 8, j = 3;
+        const float2 v = h ? vnew : vlast;
+        const float4 t4 = tap4[(b >> 1) + 2 * h + (j >> 1)];
+        const float a = t4.z, bq = t4.w;
+        const float2 Pp = ffma2(v, make_float2(a, a), nz);
+        const float2 Dd = make_float2(__fmul_rn(-bq, v.y), __fmul_rn(bq, v.x));
+        lo[j] = lane_add2(lo[j], lane_add2(Pp, Dd));
+        up[j] = lane_add2(up[j], lane_sub2(Pp, Dd));
       }
       // lanes 0..3 summed by the even lane, handed over, lanes 4..7 added by the odd lane (:176-180)
       float2 aLo = make_float2(0.f, 0.f), aUp = make_float2(0.f, 0.f);
@@ -294,7 +325,7 @@ __global__ void __launch_bounds__(32)
         }
 #pragma unroll
         for (int i = nVec; i < N; ++i) {                               // scalar tail (:183-192)
-          const float2 v = ring[wb + i][st];
+          const float2 v = (i == kNew) ? vnew : told[(i - nVec) < ((N & 7) ? (N & 7) : 1) ? (i - nVec) : 0];
           const float4 t4 = tap4[i >> 1];
           const float a = (i & 1) ? t4.z : t4.x, bq = (i & 1) ? t4.w : t4.y;
           const float2 Pp = ffma2(v, make_float2(a, a), nz);
@@ -312,6 +343,14 @@ __global__ void __launch_bounds__(32)
       if (phase > kTwoPiF || phase < -kTwoPiF) phase = lane_wrap_phase(phase);   // :185-189
       if (freq > P.max_freq) freq = P.max_freq;          // :191-195
       else if (freq < P.min_freq) freq = P.min_freq;
+      if (h == 0) {
+        yout[sidx][st] = vnew;
+        ring[pos][st] = vnew;                          // over the oldest sample ...
+      } else {
+        ring[pos + N][st] = vnew;                      // ... and its mirror
+      }
+      pos = (pos + 1 == N) ? 0 : pos + 1;
+      __syncwarp();                                    // the next sample's window loads see both copies
     }
     __syncwarp();
     if (lane < blk) {                     // flush: lane l writes sample n0 + l of every live stream
