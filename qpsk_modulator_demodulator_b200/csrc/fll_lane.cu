@@ -210,16 +210,38 @@ __global__ void __launch_bounds__(32)
 constexpr int kPairStreams = 16;
 constexpr int kPairPitch = 17;            // float2 row pitch of the staging tiles (odd)
 
+// One tap of both band-edge filters on window element v (fll_step's four sums, same roundings): lo += P + D, up += P - D
+// with P = a*(vI, vQ), D = ((-b)*vQ, b*vI).
+__device__ __forceinline__ void pair_tap(float2 v, float a, float bq, float2 nz, float2& lo, float2& up) {
+  const float2 Pp = ffma2(v, make_float2(a, a), nz);
+  const float2 Dd = make_float2(__fmul_rn(-bq, v.y), __fmul_rn(bq, v.x));
+  lo = lane_add2(lo, lane_add2(Pp, Dd));
+  up = lane_add2(up, lane_sub2(Pp, Dd));
+}
+__device__ __forceinline__ float2 sel2(bool c, float2 a, float2 b) { return make_float2(c ? a.x : b.x, c ? a.y : b.y); }
+
+// Software pipeline (one in-order warp per scheduler has nothing else to hide the recurrence behind): while the chain of
+// sample n runs — phase -> sin/cos -> rotate -> newest tap -> error -> phase — the warp accumulates window n+1 over every
+// element that is already in the ring (all but out[n] and out[n+1]), in the same basic block, so that ptxas interleaves the
+// two streams.  Window n+1's elements N-2 (= out[n]) and N-1 (= out[n+1]) are each the LAST addition of their SIMD-lane
+// partial (or the last two tail elements), so adding them late keeps the reference's order of additions.  The loop body
+// is branch-free (lane roles, the phase wrap and the clamps are selects) for the same reason.
 template <int N>
 __global__ void __launch_bounds__(32)
     fll_pair_kernel(const FllParams P, const __grid_constant__ LaneTaps<N> T, float2* ring_g, int* head_g, float2* pf_g, int C,
                     const float2* __restrict__ x, float2* __restrict__ y, long long L, long long ldx, long long ldy) {
-  __shared__ float2 ring[2 * N][kPairStreams];
-  __shared__ float2 xin[kLaneBlock][kPairPitch];
+  constexpr int nVec = N - (N & 7);
+  constexpr int kTail = N & 7;
+  static_assert(nVec >= 8 && (kTail == 0 || kTail >= 2), "the two newest elements are both in the last block or both in the tail");
+  constexpr bool kNewInVec = kTail == 0;               // N % 8 == 0: elements N-2, N-1 are partials 6, 7 (the odd lane's j = 2, 3)
+  __shared__ float2 ring[2 * N + 2][kPairStreams];     // + 2 rows: the odd lane's (unused) look at the slots of elements still to come
+  __shared__ float2 xin[2][kLaneBlock][kPairPitch];
   __shared__ float2 yout[kLaneBlock][kPairPitch];
   __shared__ __align__(16) float4 tap4[(N + 1) / 2];
   const int lane = threadIdx.x;
-  const int st = lane >> 1, h = lane & 1;
+  const int st = lane >> 1;
+  const bool odd = (lane & 1) != 0;
+  const int h = lane & 1;
   for (int k = lane; k < (N + 1) / 2; k += 32)
     tap4[k] = make_float4(T.i[2 * k], T.q[2 * k], (2 * k + 1 < N) ? T.i[2 * k + 1] : 0.f, (2 * k + 1 < N) ? T.q[2 * k + 1] : 0.f);
   const int c0 = blockIdx.x * kPairStreams;
@@ -236,6 +258,20 @@ __global__ void __launch_bounds__(32)
       ring[j + N][st] = v;
     }
   }
+  const int rows = (C - c0 < kPairStreams) ? (C - c0) : kPairStreams;
+  auto stage = [&](int buf, long long n0) {            // lane l fetches sample n0 + l of every stream of the CTA (cp.async)
+    const int blk = (int)((L - n0 < kLaneBlock) ? (L - n0) : kLaneBlock);
+    if (lane < blk) {
+#pragma unroll 8
+      for (int r = 0; r < kPairStreams; ++r) {
+        const int ch = c0 + (r < rows ? r : rows - 1);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&xin[buf][lane][r]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(x + (long long)ch * ldx + n0 + lane) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (L > 0) stage(0, 0);
   __syncwarp();
   const float2 pf = pf_g[cc];
   float phase = pf.x, freq = pf.y;
@@ -243,116 +279,158 @@ __global__ void __launch_bounds__(32)
   asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(nz.x), "=f"(nz.y) : "l"(&g_lane_neg_zero2));
   const SinCosK SK = sincos_load_consts();
   int pos = 0;
-  const int rows = (C - c0 < kPairStreams) ? (C - c0) : kPairStreams;
-  constexpr int nVec = N - (N & 7);
 
-  for (long long n0 = 0; n0 < L; n0 += kLaneBlock) {
-    const int blk = (int)((L - n0 < kLaneBlock) ? (L - n0) : kLaneBlock);
-    if (lane < blk) {                     // stage: lane l fetches sample n0 + l of every stream of the CTA
-#pragma unroll 8
-      for (int r = 0; r < kPairStreams; ++r) {
-        const int ch = c0 + (r < rows ? r : rows - 1);
-        xin[lane][r] = x[(long long)ch * ldx + n0 + lane];
+  // window element i of the window starting at slot `wb`, this lane's share of block b: elements b + 4h + j
+  // taps of element i: tap4[i >> 1].{x,y} (even i) / .{z,w} (odd i)
+#define PAIR_TAP_OF(i, A, B)                                  \
+  const float4 t4_##A = tap4[(i) >> 1];                       \
+  const float A = ((i) & 1) ? t4_##A.z : t4_##A.x, B = ((i) & 1) ? t4_##A.w : t4_##A.y;
+
+  // partial sums of the CURRENT window over everything but its newest element (prologue: all N-1 old outputs are in the ring)
+  float2 clo[4], cup[4];
+  float2 ctail[kTail > 2 ? kTail - 2 : 1];             // old tail elements nVec .. N-3 of the current window
+  float2 vprev = ring[N - 1][st];                      // out[n-1]: the newest output so far (slot pos + N - 1 with pos = 0)
+  {
+    const float2* win = &ring[1 + 4 * h][st];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) clo[l] = cup[l] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int b = 0; b < nVec; b += 8) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kNewInVec && b == nVec - 8 && j == 3) continue;   // slot of the element still to come (the odd lane's)
+        const float2 v = win[(b + j) * kPairStreams];
+        const float4 t4 = tap4[(b >> 1) + 2 * h + (j >> 1)];
+        pair_tap(v, (j & 1) ? t4.z : t4.x, (j & 1) ? t4.w : t4.y, nz, clo[j], cup[j]);
       }
     }
+    if (kNewInVec) {
+      // the even lane's j = 3 of the last block is element N-5 (old); the odd lane's is the newest, added in the loop
+      const float2 v = ring[1 + (nVec - 8) + 3][st];     // element nVec - 5 (even lane's view)
+      const float4 t4 = tap4[((nVec - 8) >> 1) + 1];
+      float2 l3 = clo[3], u3 = cup[3];
+      pair_tap(v, t4.z, t4.w, nz, l3, u3);
+      clo[3] = sel2(odd, clo[3], l3);
+      cup[3] = sel2(odd, cup[3], u3);
+    }
+#pragma unroll
+    for (int i = nVec; i < N - 2; ++i) ctail[i - nVec] = ring[1 + i][st];
+  }
+
+  int buf = 0;
+  for (long long n0 = 0; n0 < L; n0 += kLaneBlock, buf ^= 1) {
+    const int blk = (int)((L - n0 < kLaneBlock) ? (L - n0) : kLaneBlock);
+    if (n0 + kLaneBlock < L) stage(buf ^ 1, n0 + kLaneBlock);         // next round in flight during this one
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncwarp();
     for (int sidx = 0; sidx < blk; ++sidx) {
-      const float2 in = xin[sidx][st];
-      // old window elements first (independent of the phase: they fill the stalls of the sin/cos chain), the newest element
-      // — window index N-1, i.e. the odd lane's last tap — from registers afterwards; see fll_lane_kernel
-      const int wb = pos + 1;                          // window start (slots wb .. wb + N - 2 hold the N-1 old outputs)
-      const float2* win = &ring[wb + 4 * h][st];       // this lane takes the elements with (i & 7) >> 2 == h
-      constexpr int kNew = N - 1;
-      float2 lo[4], up[4];
+      const float2 in = xin[buf][sidx][st];
+      const int wb = pos + 1;                          // slot of window n's element 0; window n+1 starts one slot later
+      // ---- window n+1, elements 0 .. N-3 (slots wb+1 .. wb+N-2: all written in earlier iterations) ----
+      float2 nlo[4], nup[4];
 #pragma unroll
-      for (int l = 0; l < 4; ++l) lo[l] = up[l] = make_float2(0.f, 0.f);
-      float2 vlast = make_float2(0.f, 0.f);            // element b + 4h + j of the last block / j = 3 (old for the even lane)
+      for (int l = 0; l < 4; ++l) nlo[l] = nup[l] = make_float2(0.f, 0.f);
+      const float2* win1 = &ring[wb + 1 + 4 * h][st];
+      float2 vE = make_float2(0.f, 0.f);               // even lane's element N-5 of window n+1 (slot shared with the odd lane's N-1)
+      float2 vD = make_float2(0.f, 0.f);               // even lane's element N-6 (odd lane: N-2 = out[n], not in the ring yet)
 #pragma unroll
       for (int b = 0; b < nVec; b += 8) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 v = win[(b + j) * kPairStreams];
-          if (b + 4 + j == kNew) {                     // the odd lane's copy of this slot is the element being computed
-            vlast = v;
+          if (kNewInVec && b == nVec - 8 && j >= 2) {  // the odd lane's elements N-2 / N-1: deferred for BOTH lanes
+            const float2 v = win1[(b + j) * kPairStreams];   // (the even lane's value is its real, old element; the odd lane's is stale)
+            if (j == 2) vD = v; else vE = v;
             continue;
           }
-          const float4 t4 = tap4[(b >> 1) + 2 * h + (j >> 1)];       // taps b + 4h + j (pairs (0,1), (2,3))
-          const float a = (j & 1) ? t4.z : t4.x, bq = (j & 1) ? t4.w : t4.y;
-          const float2 Pp = ffma2(v, make_float2(a, a), nz);
-          const float2 Dd = make_float2(__fmul_rn(-bq, v.y), __fmul_rn(bq, v.x));
-          lo[j] = lane_add2(lo[j], lane_add2(Pp, Dd));
-          up[j] = lane_add2(up[j], lane_sub2(Pp, Dd));
+          const float2 v = win1[(b + j) * kPairStreams];
+          const float4 t4 = tap4[(b >> 1) + 2 * h + (j >> 1)];
+          pair_tap(v, (j & 1) ? t4.z : t4.x, (j & 1) ? t4.w : t4.y, nz, nlo[j], nup[j]);
         }
       }
-      float2 told[(N & 7) ? (N & 7) : 1];              // old tail elements (only the odd lane uses them)
+      float2 ntail[kTail > 2 ? kTail - 2 : 1];
 #pragma unroll
-      for (int i = nVec; i < N - 1; ++i) told[i - nVec] = ring[wb + i][st];
+      for (int i = nVec; i < N - 2; ++i) ntail[i - nVec] = ring[wb + 1 + i][st];
+      // ---- chain of sample n ----
       float sn, cs;
       sincos_f32_fast_k(phase, SK, &sn, &cs);          // MathF.Cos/Sin(phase) :108-109 (both lanes of the pair)
       const float oI = in.x * cs - in.y * sn;          // :111
       const float oQ = in.x * sn + in.y * cs;          // :112
       const float2 vnew = make_float2(oI, oQ);
-      if (kNew < nVec) {
-        // last block, j = 3: window element N-5 (old, loaded above) for the even lane, N-1 (the new output) for the odd one
-        constexpr int b = nVec - 8, j = 3;
-        const float2 v = h ? vnew : vlast;
-        const float4 t4 = tap4[(b >> 1) + 2 * h + (j >> 1)];
-        const float a = t4.z, bq = t4.w;
-        const float2 Pp = ffma2(v, make_float2(a, a), nz);
-        const float2 Dd = make_float2(__fmul_rn(-bq, v.y), __fmul_rn(bq, v.x));
-        lo[j] = lane_add2(lo[j], lane_add2(Pp, Dd));
-        up[j] = lane_add2(up[j], lane_sub2(Pp, Dd));
+      if (kNewInVec) {
+        // window n: its last element (N-1 = out[n]) closes the odd lane's partial 3; the even lane's partial 3 is complete
+        const float4 t4 = tap4[((nVec - 8) >> 1) + 2 * 1 + 1];        // taps N-2, N-1 of the odd lane
+        float2 l3 = clo[3], u3 = cup[3];
+        pair_tap(vnew, t4.z, t4.w, nz, l3, u3);
+        clo[3] = sel2(odd, l3, clo[3]);
+        cup[3] = sel2(odd, u3, cup[3]);
       }
-      // lanes 0..3 summed by the even lane, handed over, lanes 4..7 added by the odd lane (:176-180)
-      float2 aLo = make_float2(0.f, 0.f), aUp = make_float2(0.f, 0.f);
-      if (h == 0) {
+      // lanes 0..3 summed by the even lane, handed over, lanes 4..7 added by the odd lane (:176-180): both lanes run both
+      // passes (no divergence), each keeps the one that is its own
+      float2 sLo = make_float2(0.f, 0.f), sUp = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          aLo = lane_add2(aLo, lo[l]);
-          aUp = lane_add2(aUp, up[l]);
+      for (int l = 0; l < 4; ++l) {
+        sLo = lane_add2(sLo, clo[l]);
+        sUp = lane_add2(sUp, cup[l]);
+      }
+      float2 aLo = make_float2(__shfl_xor_sync(0xffffffffu, sLo.x, 1), __shfl_xor_sync(0xffffffffu, sLo.y, 1));
+      float2 aUp = make_float2(__shfl_xor_sync(0xffffffffu, sUp.x, 1), __shfl_xor_sync(0xffffffffu, sUp.y, 1));
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {                    // meaningful on the odd lane: (even lane's sum + L4) + L5 ...
+        aLo = lane_add2(aLo, clo[l]);
+        aUp = lane_add2(aUp, cup[l]);
+      }
+      if (!kNewInVec) {                                // scalar tail (:183-192): old elements, then out[n-1], then out[n]
+#pragma unroll
+        for (int i = nVec; i < N - 2; ++i) {
+          PAIR_TAP_OF(i, ta, tb)
+          pair_tap(ctail[i - nVec], ta, tb, nz, aLo, aUp);
+        }
+        {
+          PAIR_TAP_OF(N - 2, ta, tb)
+          pair_tap(vprev, ta, tb, nz, aLo, aUp);
+        }
+        {
+          PAIR_TAP_OF(N - 1, ta, tb)
+          pair_tap(vnew, ta, tb, nz, aLo, aUp);
         }
       }
-      const float gLoI = __shfl_xor_sync(0xffffffffu, aLo.x, 1), gLoQ = __shfl_xor_sync(0xffffffffu, aLo.y, 1);
-      const float gUpI = __shfl_xor_sync(0xffffffffu, aUp.x, 1), gUpQ = __shfl_xor_sync(0xffffffffu, aUp.y, 1);
-      float error = 0.f;
-      if (h == 1) {
-        aLo = make_float2(gLoI, gLoQ);
-        aUp = make_float2(gUpI, gUpQ);
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          aLo = lane_add2(aLo, lo[l]);
-          aUp = lane_add2(aUp, up[l]);
-        }
-#pragma unroll
-        for (int i = nVec; i < N; ++i) {                               // scalar tail (:183-192)
-          const float2 v = (i == kNew) ? vnew : told[(i - nVec) < ((N & 7) ? (N & 7) : 1) ? (i - nVec) : 0];
-          const float4 t4 = tap4[i >> 1];
-          const float a = (i & 1) ? t4.z : t4.x, bq = (i & 1) ? t4.w : t4.y;
-          const float2 Pp = ffma2(v, make_float2(a, a), nz);
-          const float2 Dd = make_float2(__fmul_rn(-bq, v.y), __fmul_rn(bq, v.x));
-          aLo = lane_add2(aLo, lane_add2(Pp, Dd));
-          aUp = lane_add2(aUp, lane_sub2(Pp, Dd));
-        }
-        const float powUpper = aUp.x * aUp.x + aUp.y * aUp.y;          // :118
-        const float powLower = aLo.x * aLo.x + aLo.y * aLo.y;          // :119
-        error = powLower - powUpper;                                   // :121
-      }
-      error = __shfl_sync(0xffffffffu, error, lane | 1);               // both lanes of the pair update the same state
+      const float powUpper = aUp.x * aUp.x + aUp.y * aUp.y;            // :118
+      const float powLower = aLo.x * aLo.x + aLo.y * aLo.y;            // :119
+      float error = powLower - powUpper;                               // :121
+      error = __shfl_sync(0xffffffffu, error, lane | 1);               // the odd lane's: both lanes update the same state
       freq += P.beta * error;                            // :124
-      phase += freq + P.alpha * error;                   // :125
-      if (phase > kTwoPiF || phase < -kTwoPiF) phase = lane_wrap_phase(phase);   // :185-189
-      if (freq > P.max_freq) freq = P.max_freq;          // :191-195
-      else if (freq < P.min_freq) freq = P.min_freq;
-      if (h == 0) {
+      const float p1 = phase + (freq + P.alpha * error); // :125
+      const float pw = lane_wrap_phase(p1);
+      phase = (p1 > kTwoPiF || p1 < -kTwoPiF) ? pw : p1; // :185-189
+      freq = (freq > P.max_freq) ? P.max_freq : ((freq < P.min_freq) ? P.min_freq : freq);   // :191-195
+      // ---- window n+1 becomes the current one: out[n] is its element N-2 ----
+      if (kNewInVec) {
+        // the odd lane's j = 2 (element N-2 = out[n]); the even lane's j = 2, 3 are its old elements N-6, N-5 (vD, vE)
+        const float4 t4 = tap4[((nVec - 8) >> 1) + 2 * h + 1];
+        pair_tap(sel2(odd, vnew, vD), t4.x, t4.y, nz, nlo[2], nup[2]);
+        float2 l3 = nlo[3], u3 = nup[3];
+        pair_tap(vE, t4.z, t4.w, nz, l3, u3);
+        nlo[3] = sel2(odd, nlo[3], l3);
+        nup[3] = sel2(odd, nup[3], u3);
+      }
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        clo[l] = nlo[l];
+        cup[l] = nup[l];
+      }
+#pragma unroll
+      for (int i = 0; i < (kTail > 2 ? kTail - 2 : 1); ++i) ctail[i] = ntail[i];
+      vprev = vnew;
+      if (!odd) {
         yout[sidx][st] = vnew;
         ring[pos][st] = vnew;                          // over the oldest sample ...
       } else {
         ring[pos + N][st] = vnew;                      // ... and its mirror
       }
       pos = (pos + 1 == N) ? 0 : pos + 1;
-      __syncwarp();                                    // the next sample's window loads see both copies
+      __syncwarp();                                    // the next iteration's window loads see both copies
     }
-    __syncwarp();
     if (lane < blk) {                     // flush: lane l writes sample n0 + l of every live stream
 #pragma unroll 8
       for (int r = 0; r < kPairStreams; ++r)
@@ -360,6 +438,7 @@ __global__ void __launch_bounds__(32)
     }
     __syncwarp();
   }
+#undef PAIR_TAP_OF
   if (live) {
     for (int j = h; j < N; j += 2) ring_g[(long long)j * C + c] = ring[pos + j][st];   // oldest first from slot `pos`
     if (h == 0) {
