@@ -277,7 +277,10 @@ __global__ void __launch_bounds__(32)
   float phase = pf.x, freq = pf.y;
   float2 nz;
   asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(nz.x), "=f"(nz.y) : "l"(&g_lane_neg_zero2));
-  const SinCosK SK = sincos_load_consts();
+  // The pair's ODD lane carries the recurrence (its partial sums end with the newest outputs); the even lane runs the same
+  // instructions on its own copy of (phase, freq), which nothing reads — no broadcast of the error sits on the chain.
+  // sin/cos: the short-range form of the two-warp kernel (sincos_f32arg_rq: |phase| < 64, see FllEngine::process_dev).
+  const SinCosF SKF = sincos_f_load_consts();
   int pos = 0;
 
   // window element i of the window starting at slot `wb`, this lane's share of block b: elements b + 4h + j
@@ -352,10 +355,20 @@ __global__ void __launch_bounds__(32)
 #pragma unroll
       for (int i = nVec; i < N - 2; ++i) ntail[i - nVec] = ring[wb + 1 + i][st];
       // ---- chain of sample n ----
-      float sn, cs;
-      sincos_f32_fast_k(phase, SK, &sn, &cs);          // MathF.Cos/Sin(phase) :108-109 (both lanes of the pair)
-      const float oI = in.x * cs - in.y * sn;          // :111
-      const float oQ = in.x * sn + in.y * cs;          // :112
+      // MathF.Cos/Sin(phase) :108-109 and the rotation :111-112 with phase = r + q*pi/2 and the exact factor j^q applied to
+      // the input sample while the polynomials run: out = (in * j^q) * (cos r + j sin r) — the same two products per
+      // component as in.x*cos - in.y*sin / in.x*sin + in.y*cos (signs are exact, a + b == b + a); see fll_duo.cu
+      float sr, cr;
+      unsigned q;
+      sincos_f32arg_rq((double)phase, SKF, &sr, &cr, &q);
+      const bool qodd = (q & 1u) != 0;
+      const unsigned fx = ((q + 1u) & 2u) << 30;       // sign of the first component: quadrants 1, 2
+      const unsigned fy = (q & 2u) << 30;              // sign of the second: quadrants 2, 3
+      const float ax = __uint_as_float(__float_as_uint(qodd ? in.y : in.x) ^ fx);
+      const float ay = __uint_as_float(__float_as_uint(qodd ? in.x : in.y) ^ fy);
+      const float oI = ax * cr - ay * sr;
+      const float oQ = ax * sr + ay * cr;
+      // the odd lane's output is the stream's; the even lane needs it only where it shares the odd lane's instructions
       const float2 vnew = make_float2(oI, oQ);
       if (kNewInVec) {
         // window n: its last element (N-1 = out[n]) closes the odd lane's partial 3; the even lane's partial 3 is complete
@@ -397,8 +410,7 @@ __global__ void __launch_bounds__(32)
       }
       const float powUpper = aUp.x * aUp.x + aUp.y * aUp.y;            // :118
       const float powLower = aLo.x * aLo.x + aLo.y * aLo.y;            // :119
-      float error = powLower - powUpper;                               // :121
-      error = __shfl_sync(0xffffffffu, error, lane | 1);               // the odd lane's: both lanes update the same state
+      const float error = powLower - powUpper;                         // :121 (the odd lane's is the stream's)
       freq += P.beta * error;                            // :124
       const float p1 = phase + (freq + P.alpha * error); // :125
       const float pw = lane_wrap_phase(p1);
@@ -422,11 +434,10 @@ __global__ void __launch_bounds__(32)
 #pragma unroll
       for (int i = 0; i < (kTail > 2 ? kTail - 2 : 1); ++i) ctail[i] = ntail[i];
       vprev = vnew;
-      if (!odd) {
+      if (odd) {
         yout[sidx][st] = vnew;
-        ring[pos][st] = vnew;                          // over the oldest sample ...
-      } else {
-        ring[pos + N][st] = vnew;                      // ... and its mirror
+        ring[pos][st] = vnew;                          // over the oldest sample, and its mirror
+        ring[pos + N][st] = vnew;
       }
       pos = (pos + 1 == N) ? 0 : pos + 1;
       __syncwarp();                                    // the next iteration's window loads see both copies
@@ -441,7 +452,7 @@ __global__ void __launch_bounds__(32)
 #undef PAIR_TAP_OF
   if (live) {
     for (int j = h; j < N; j += 2) ring_g[(long long)j * C + c] = ring[pos + j][st];   // oldest first from slot `pos`
-    if (h == 0) {
+    if (odd) {
       head_g[c] = 0;
       pf_g[c] = make_float2(phase, freq);
     }

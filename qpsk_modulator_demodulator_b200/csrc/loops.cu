@@ -399,7 +399,10 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
   // leave that range — those calls take the generic kernels, which use the library routines.
   const bool wild = state_wild || !(P.max_freq < 1e4f);
   state_wild = false;                                          // any kernel leaves the state wrapped and clamped
-  if (!force_group && !wild && fll_lane_supported(n_taps) && force_impl == 5)
+  // the pair kernel's sin/cos is the |phase| < 64 form: a caller-set phase beyond that goes through the lane kernel once
+  const bool far = state_far;
+  state_far = false;
+  if (!force_group && !wild && !far && fll_lane_supported(n_taps) && force_impl == 5)
     return fll_pair_launch(P, lower, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
   if (!force_group && !wild && fll_lane_supported(n_taps) && force_impl != 4 && (force_impl == 3 || channels >= lane_min))
     return fll_lane_launch(P, lower, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
@@ -684,9 +687,11 @@ int qpsk_fll_set_state(qpsk_fll* f, const float* phase, const float* freq) {
   FllEngine& e = f->eng;
   std::vector<float2> h((size_t)e.channels);
   e.state_wild = false;
+  e.state_far = false;
   for (int c = 0; c < e.channels; ++c) {
     h[(size_t)c] = make_float2(phase[c], freq[c]);
     if (!(fabsf(phase[c]) < 1e4f) || !(fabsf(freq[c]) < 1e4f)) e.state_wild = true;   // see FllEngine::process_dev
+    if (!(fabsf(phase[c]) < 32.0f)) e.state_far = true;
   }
   QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
   QPSK_CUDA_TRY(cudaMemcpy(e.d_pf.p, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));

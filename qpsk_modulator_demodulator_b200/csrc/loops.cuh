@@ -286,6 +286,7 @@ struct FllEngine {
   DevBuf<int> d_head;        // [C]
   DevBuf<float2> d_pf;       // [C] (phase, freq)
   bool state_wild = false;   // a caller-set (phase, freq) outside the fast kernel's range is pending
+  bool state_far = false;    // a caller-set |phase| >= 32 is pending (the pair kernel's short-range sin/cos)
   cudaStream_t stream = nullptr;
   ~FllEngine();
   int init(float sps, float rolloff, int size, float bw, int channels_in);
