@@ -385,13 +385,21 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
     if (e && strcmp(e, "pair") == 0) return 5;               // "pair": two lanes per stream at any stream count
     return 0;
   }();
-  // From about 12000 streams on, the issue slots bound the two-warp kernel (44 warp instructions per stream and sample) and
-  // one lane per stream is ahead: 4.49 against 5.40 ms at 16384 streams x 4196 samples, but 3.24 against 3.06 ms at 8192
-  // (its floor is ~2.9 ms: ~1370 cycles per sample on one in-order warp).  tools/fll_impl_sweep.py; QPSK_FLL_LANE_MIN
-  // overrides.
+  // Kernel choice by stream count (40 taps, 4196 samples, ms; tools/fll_only.py):
+  //   streams   1024   2048   4096   8192   16384
+  //   duo       0.76   0.90   1.25   2.46   4.49    two warps per four streams: shortest recurrence (356 cycles / sample),
+  //                                                   44 warp instructions per stream and sample -> issue-bound from ~4096
+  //   pair      1.45   1.45   1.45   1.47   2.35    two lanes per stream, software-pipelined (680 cycles / sample, ~21 issue
+  //                                                   slots per stream and sample)
+  //   lane      2.28   2.40   2.50   2.50   2.52    one lane per stream (the general sin/cos: any |phase| < 1e5)
+  // QPSK_FLL_PAIR_MIN overrides the crossover.
+  static const int pair_min = [] {
+    const char* e = getenv("QPSK_FLL_PAIR_MIN");
+    return e ? atoi(e) : 5120;
+  }();
   static const int lane_min = [] {
     const char* e = getenv("QPSK_FLL_LANE_MIN");
-    return e ? atoi(e) : 12288;
+    return e ? atoi(e) : (1 << 30);
   }();
   const bool force_group = force_impl == 1 || force_impl == 2;   // (3 = lane, 4 = duo, 5 = pair)
   // The two-warp kernel evaluates sin/cos and the phase wrap with short-range formulas (|phase| < 1e5): the loop
@@ -402,9 +410,11 @@ int FllEngine::process_dev(const float2* x, float2* y, int64_t L, int64_t ldx, i
   // the pair kernel's sin/cos is the |phase| < 64 form: a caller-set phase beyond that goes through the lane kernel once
   const bool far = state_far;
   state_far = false;
-  if (!force_group && !wild && !far && fll_lane_supported(n_taps) && force_impl == 5)
+  if (!force_group && !wild && !far && fll_lane_supported(n_taps) && force_impl != 3 && force_impl != 4 &&
+      (force_impl == 5 || channels >= pair_min))
     return fll_pair_launch(P, lower, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
-  if (!force_group && !wild && fll_lane_supported(n_taps) && force_impl != 4 && (force_impl == 3 || channels >= lane_min))
+  if (!force_group && !wild && fll_lane_supported(n_taps) && force_impl != 4 &&
+      (force_impl == 3 || channels >= lane_min || (far && channels >= pair_min)))
     return fll_lane_launch(P, lower, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
   if (!force_group && !wild && fll_duo_supported(n_taps))
     return fll_duo_launch(P, d_taps.p, d_ring.p, d_head.p, d_pf.p, channels, x, y, L, ldx, ldy, s);
