@@ -1,0 +1,28 @@
+#!/bin/bash
+# ncu evidence of one round (run under gpurun on ONE GPU, after the same commands have exited 0 without ncu).
+# usage: bash tools/gpu_profiles.sh <tag>
+set -u
+TAG=${1:-r02}
+OUT=gpurun_out
+mkdir -p $OUT
+B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-scaling-legs"
+$B > $OUT/${TAG}_plain_bench.json 2> $OUT/${TAG}_plain_bench.err || { echo "plain bench failed"; exit 1; }
+# 1. launch list of the bench (cold-cache, serialised: shares, not absolutes)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/${TAG}_launches_bench.csv $B > $OUT/${TAG}_ncu_launch.log 2>&1
+echo "launch list rc=$?"
+# 2. FIR kernel, one launch per tap count (the timed region: skip warm-up launches 3 x 4)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fir_tma -s 12 -c 4 -f -o $OUT/${TAG}_prof_fir $B --no-chain --no-decimate > $OUT/${TAG}_ncu_fir.log 2>&1
+echo "fir rc=$?"
+# 3. decimating FIR: first timed launch of each (taps, D) = launches 2, 9, 16, ... of the 7 per configuration
+timeout 900 ncu --set full --clock-control none -k regex:fir_decim -c 42 -f -o $OUT/${TAG}_prof_decim $B --no-chain > $OUT/${TAG}_ncu_decim.log 2>&1
+echo "decim rc=$?"
+# 4. chain at 2048 channels, every stage one launch (no time-chunk pipeline): FLL (duo), fused MF + symbol stage, TSC strip, BER
+QPSK_DEMOD_CHUNKS=1 python tools/chain_only.py fll 2 > $OUT/${TAG}_plain_chain_fll.log 2>&1
+QPSK_DEMOD_CHUNKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fll_duo|symsync|tsc_strip|ber_kernel" -s 12 -c 4 -f \
+  -o $OUT/${TAG}_prof_chain python tools/chain_only.py fll 2 > $OUT/${TAG}_ncu_chain.log 2>&1
+echo "chain rc=$?"
+# 5. the 16384-channel set on one GPU: fll_pair_kernel + the dense symbol-stage kernel
+QPSK_DEMOD_CHUNKS=1 SWEEP=16384 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fll_pair|symsync" -s 4 -c 2 -f \
+  -o $OUT/${TAG}_prof_chain16k python tools/fll_impl_sweep.py > $OUT/${TAG}_ncu_chain16k.log 2>&1
+echo "chain16k rc=$?"
+ls -la $OUT/${TAG}_prof_*.ncu-rep
