@@ -13,8 +13,9 @@ echo "launch list rc=$?"
 # 2. FIR kernel, one launch per tap count (the timed region: skip warm-up launches 3 x 4)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fir_tma -s 12 -c 4 -f -o $OUT/${TAG}_prof_fir $B --no-chain --no-decimate > $OUT/${TAG}_ncu_fir.log 2>&1
 echo "fir rc=$?"
-# 3. decimating FIR: first timed launch of each (taps, D) = launches 2, 9, 16, ... of the 7 per configuration
-timeout 900 ncu --set full --clock-control none -k regex:fir_decim -c 42 -f -o $OUT/${TAG}_prof_decim $B --no-chain > $OUT/${TAG}_ncu_decim.log 2>&1
+# 3. decimating FIR: one launch per (taps, D) of the bench's `decimate` leg
+python tools/decim_probe.py > $OUT/${TAG}_plain_decim.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:fir_decim -c 6 -f -o $OUT/${TAG}_prof_decim python tools/decim_probe.py > $OUT/${TAG}_ncu_decim.log 2>&1
 echo "decim rc=$?"
 # 4. chain at 2048 channels, every stage one launch (no time-chunk pipeline): FLL (duo), fused MF + symbol stage, TSC strip, BER
 QPSK_DEMOD_CHUNKS=1 python tools/chain_only.py fll 2 > $OUT/${TAG}_plain_chain_fll.log 2>&1
@@ -25,4 +26,13 @@ echo "chain rc=$?"
 QPSK_DEMOD_CHUNKS=1 SWEEP=16384 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fll_pair|symsync" -s 4 -c 2 -f \
   -o $OUT/${TAG}_prof_chain16k python tools/fll_impl_sweep.py > $OUT/${TAG}_ncu_chain16k.log 2>&1
 echo "chain16k rc=$?"
+# condense on the box: the reports themselves are too big to travel back (64 MiB limit)
+for k in fir decim chain chain16k; do
+  python tools/ncu_summary.py $OUT/${TAG}_prof_$k.ncu-rep $OUT/${TAG}_ncu_full_${k}_summary.csv
+done
+for k in chain chain16k; do
+  python tools/ncu_src.py $OUT/${TAG}_prof_$k.ncu-rep 40 > $OUT/${TAG}_ncu_src_$k.txt 2>&1
+done
 ls -la $OUT/${TAG}_prof_*.ncu-rep
+rm -f $OUT/${TAG}_prof_decim.ncu-rep $OUT/${TAG}_prof_chain16k.ncu-rep $OUT/${TAG}_prof_fir.ncu-rep
+du -sh $OUT
