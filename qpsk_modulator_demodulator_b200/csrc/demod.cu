@@ -86,7 +86,10 @@ __global__ void __launch_bounds__(32)
 // ---------------------------------------------------------------------------------------------
 constexpr int kSsBlock = 32;
 constexpr int kSsCarry = 4;
-constexpr int kSsPitch = kSsBlock + 1;   // odd pitch (float2): rows of different lanes fall in different banks
+// a channel's row of a round: [kSsCarry slots for the samples carried over from the previous round, right-aligned | the
+// round's kSsBlock samples | 1 pad] — carried samples and block are contiguous, so the interpolator's four samples are four
+// unconditional loads at (row + kSsCarry - carried + index).  Odd pitch (float2): rows of different lanes fall in different banks.
+constexpr int kSsPitch = kSsCarry + kSsBlock + 1;
 constexpr int kSsSymCap = kSsBlock + 4;  // symbols one round can emit (advance >= 0.9 samples)
 constexpr int kSsSymPitch = kSsSymCap + 1;
 
@@ -102,7 +105,6 @@ __device__ __forceinline__ void cp_async_wait() {
 
 struct SsSmem {
   float2 raw[2][32 * kSsPitch];
-  float2 carry[32 * kSsCarry];
   int nsymq[2][32];
 };
 
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? (DEN
     const long long n0 = (long long)r * kSsBlock;
     const int blk = (int)((L - n0) < kSsBlock ? (L - n0) : kSsBlock);
     // MFW == 0: straight into the round's double buffer; MFW > 0: into the raw ring (slot = sample index mod 128)
-    float2* dst = (MFW > 0) ? (mf_ring + (int)((n0 + lane) % ring_n)) : (sm.raw[r & 1] + lane);
+    float2* dst = (MFW > 0) ? (mf_ring + (int)((n0 + lane) % ring_n)) : (sm.raw[r & 1] + kSsCarry + lane);
     const int pitch = (MFW > 0) ? ring_pitch : kSsPitch;
     if (lane < blk) {
 #pragma unroll 8
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? (DEN
   }
   auto mf_dispatch = [&](int q, int blk_q) {
     const float2* rc = mf_ring + lane * ring_pitch;
-    float2* oc = sm.raw[q & 1] + lane * kSsPitch;
+    float2* oc = sm.raw[q & 1] + lane * kSsPitch + kSsCarry;
     const int j0 = (role - 2) * mf_per, j1 = (role - 1) * mf_per;
     switch (mf_nb) {
       case 1: mf_round<1>(rc, ring_n, MT, tg, nz, q, j0, j1, blk_q, oc); break;
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? (DEN
     S = mm_g[c];
     if (append) n_sym = n_sym_g[c];
     carried = S.queued;                              // host guarantees <= kSsCarry
-    for (int i = 0; i < carried; ++i) sm.carry[lane * kSsCarry + i] = q_in[(long long)c * qcap + i];
+    for (int i = 0; i < carried; ++i) sm.raw[0][lane * kSsPitch + kSsCarry - carried + i] = q_in[(long long)c * qcap + i];
   } else if (role == 1) {
     if (rounds > 0) stage(0);
     if (MFW > 0 && rounds > 1) stage(1);
@@ -402,10 +404,8 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? (DEN
       if (r < rounds) {
         const long long n0 = (long long)r * kSsBlock;
         const int blk = (int)((L - n0) < kSsBlock ? (L - n0) : kSsBlock);
-        MmView v;
-        v.queue = sm.carry + lane * kSsCarry;
-        v.in = sm.raw[r & 1] + lane * kSsPitch;
-        v.queued = carried;
+        // logical buffer [carried samples | block] = row + kSsCarry - carried .. (one contiguous run)
+        const float2* vbuf = sm.raw[r & 1] + lane * kSsPitch + (kSsCarry - carried);
         const int count = carried + blk;
         const double limit_d = (double)(count - 2);  // loop test in fp64: base + 2 < count  <=>  base_d < count - 2
         float2* sq = symq0 + ((r & 1) * 32 + lane) * sym_pitch;
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? (DEN
         const double adv_hi = MP.sps + 0.1, adv_lo = MP.sps + (-0.1);            // sps + clamp(corr) at the two rails
         auto one_symbol = [&]() {
           float ci, cq;
-          mm_interp(v, S.base_index, S.mu, ci, cq);
+          mm_interp_lin(vbuf, S.base_index, S.mu, ci, cq);
           const bool posI = ci >= 0.f, posQ = cq >= 0.f;     // GetSignQpsk :194-198
           const double ci_d = (double)ci, cq_d = (double)cq;
           // branch-free (one basic block per symbol, so ptxas can interleave the independent work with the chain):
@@ -464,11 +464,12 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? (DEN
         // drop consumed samples, keep at least the last three (:123-129)
         const int consumed = min(max(0, S.base_index - 1), max(0, count - 3));
         const int remain = count - consumed;         // <= 3 here (4 slots)
-        float2 keep[kSsCarry];
+        // ... into the carry slots of the NEXT round's row, right-aligned against its block (the filter warps / cp.async
+        // only write the block part of that row)
+        float2* nrow = sm.raw[(r + 1) & 1] + lane * kSsPitch + (kSsCarry - remain);
 #pragma unroll
-        for (int i = 0; i < kSsCarry; ++i) keep[i] = (i < remain) ? v.at(consumed + i) : make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < kSsCarry; ++i) sm.carry[lane * kSsCarry + i] = keep[i];
+        for (int i = 0; i < kSsCarry; ++i)
+          if (i < remain) nrow[i] = vbuf[consumed + i];
         carried = remain;
         S.base_index -= consumed;
       }
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(64 + 32 * MFW, MFW == 1 ? 4 : (MFW == 2 ? (DEN
   }
   if (live) {
     if (role == 0) {
-      for (int i = 0; i < carried; ++i) q_out[(long long)c * qcap + i] = sm.carry[lane * kSsCarry + i];
+      for (int i = 0; i < carried; ++i) q_out[(long long)c * qcap + i] = sm.raw[rounds & 1][lane * kSsPitch + kSsCarry - carried + i];
       S.queued = carried;
       mm_g[c] = S;
       n_sym_g[c] = n_sym;

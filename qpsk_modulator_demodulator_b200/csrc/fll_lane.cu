@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(32)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kPairStreams = 16;
 constexpr int kPairPitch = 17;            // float2 row pitch of the staging tiles (odd)
+constexpr int kPairRing = 18;             // float2 row pitch of the output ring (see fll_pair_kernel)
 
 // One tap of both band-edge filters on window element v (fll_step's four sums, same roundings): lo += P + D, up += P - D
 // with P = a*(vI, vQ), D = ((-b)*vQ, b*vI).
@@ -234,7 +235,10 @@ __global__ void __launch_bounds__(32)
   constexpr int kTail = N & 7;
   static_assert(nVec >= 8 && (kTail == 0 || kTail >= 2), "the two newest elements are both in the last block or both in the tail");
   constexpr bool kNewInVec = kTail == 0;               // N % 8 == 0: elements N-2, N-1 are partials 6, 7 (the odd lane's j = 2, 3)
-  __shared__ float2 ring[2 * N + 2][kPairStreams];     // + 2 rows: the odd lane's (unused) look at the slots of elements still to come
+  // + 2 rows: the odd lane's (unused) look at the slots of elements still to come.  Row pitch 18 float2 = 36 words: the two
+  // lanes of a pair read rows four apart (4 * 36 = 144 = 16 mod 32 banks), so the even lanes of a half-warp use banks 0-15
+  // and the odd lanes 16-31 — with the natural pitch of 16 they collide on every window load (173 M conflicts per call in ncu)
+  __shared__ float2 ring[2 * N + 2][kPairRing];
   __shared__ float2 xin[2][kLaneBlock][kPairPitch];
   __shared__ float2 yout[kLaneBlock][kPairPitch];
   __shared__ __align__(16) float4 tap4[(N + 1) / 2];
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(32)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (kNewInVec && b == nVec - 8 && j == 3) continue;   // slot of the element still to come (the odd lane's)
-        const float2 v = win[(b + j) * kPairStreams];
+        const float2 v = win[(b + j) * kPairRing];
         const float4 t4 = tap4[(b >> 1) + 2 * h + (j >> 1)];
         pair_tap(v, (j & 1) ? t4.z : t4.x, (j & 1) ? t4.w : t4.y, nz, clo[j], cup[j]);
       }
@@ -342,11 +346,11 @@ __global__ void __launch_bounds__(32)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (kNewInVec && b == nVec - 8 && j >= 2) {  // the odd lane's elements N-2 / N-1: deferred for BOTH lanes
-            const float2 v = win1[(b + j) * kPairStreams];   // (the even lane's value is its real, old element; the odd lane's is stale)
+            const float2 v = win1[(b + j) * kPairRing];   // (the even lane's value is its real, old element; the odd lane's is stale)
             if (j == 2) vD = v; else vE = v;
             continue;
           }
-          const float2 v = win1[(b + j) * kPairStreams];
+          const float2 v = win1[(b + j) * kPairRing];
           const float4 t4 = tap4[(b >> 1) + 2 * h + (j >> 1)];
           pair_tap(v, (j & 1) ? t4.z : t4.x, (j & 1) ? t4.w : t4.y, nz, nlo[j], nup[j]);
         }

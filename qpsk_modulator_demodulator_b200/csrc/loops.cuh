@@ -115,6 +115,20 @@ __device__ __forceinline__ void mm_interp(const MmView& v, int n, double mu, flo
   oQ = c_m1 * xm1.y + c_0 * x0.y + c_1 * x1.y + c_2 * x2.y;
 }
 
+// the same on a contiguous buffer (symsync_decode_kernel keeps [carried | block] in one run): four unconditional loads
+__device__ __forceinline__ void mm_interp_lin(const float2* __restrict__ b, int n, double mu, float& oI, float& oQ) {
+  const float2 xm1 = b[n - 1], x0 = b[n], x1 = b[n + 1], x2 = b[n + 2];
+  const float t = (float)mu;
+  const float tm1 = t - 1.f, tm2 = t - 2.f, tp1 = t + 1.f;
+  const float sixth = 1.f / 6.f, half = 1.f / 2.f;
+  const float c_m1 = -(t * tm1 * tm2) * sixth;
+  const float c_0 = (tp1 * tm1 * tm2) * half;
+  const float c_1 = -(tp1 * t * tm2) * half;
+  const float c_2 = (tp1 * t * tm1) * sixth;
+  oI = c_m1 * xm1.x + c_0 * x0.x + c_1 * x1.x + c_2 * x2.x;
+  oQ = c_m1 * xm1.y + c_0 * x0.y + c_1 * x1.y + c_2 * x2.y;
+}
+
 // One pass of the `while` body (:62-120).  Returns false when the loop must stop *before* emitting
 // (output full, :101-102).  `stop_after` is set when the post-advance break (:118-119) fires.
 __device__ __forceinline__ bool mm_symbol(const MmParams& P, MmState& S, const MmView& v, int buf_count, bool room,
