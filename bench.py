@@ -91,7 +91,7 @@ class ClockSampler:
 
 def ncu_traffic():
     """DRAM bytes per launch of the FIR kernel from the committed `ncu --set full` capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
@@ -343,6 +343,10 @@ def main():
             if t:
                 r["traffic"] = t["traffic"]
                 r["algorithmic_bytes"] = 16.0 * n
+                # the FMA-pipe activity ncu measured for the same launch: an independent check of `fma_frac`, whose
+                # denominator is this run's own FFMA2 micro-benchmark (nominal peak: fma_peak_nominal)
+                r["ncu_fma_pipe_active_pct"] = t.get("fma_pipe_active_pct")
+                r["fma_frac_of_nominal"] = r["fma_tflops"] / (148 * 128 * 2 * 1.965e9 / 1e12)
     dom = max(roofs, key=lambda r: r["ms"])
     hbm_dom = max((r for r in roofs if r["bound"] == "hbm"), key=lambda r: r["ms"], default=None)
     roofline = {

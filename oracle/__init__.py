@@ -231,6 +231,14 @@ class ComplexFIRFilter(_Handle):
         lib().orc_fir_reset(self._h)
 
 
+def decimate(filtered_iq, D: int, skip: int = 0) -> np.ndarray:
+    """Row N1 (north_star item (2), SURVEY §8d "decimate-by-D variant").  The reference's matched filter is non-decimating
+    (ComplexFIRFilter.Filter, MS/Models/FIRFilter.cs:80-91, called at MS/QPSKDeModulator.cs:360), so the oracle of the
+    decimating filter is that output kept at stream indices skip, skip + D, skip + 2D, ...: pass Filter()'s output."""
+    y = _f32(filtered_iq).reshape(-1, 2)
+    return np.ascontiguousarray(y[skip::D]).reshape(-1)
+
+
 def fir_filter_f64(taps_iq, iq_in) -> np.ndarray:
     t, x = _f32(taps_iq), _f32(iq_in)
     y = np.empty(x.size, np.float64)

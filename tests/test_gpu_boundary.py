@@ -157,3 +157,25 @@ def test_handles_keep_the_device_they_were_created_on(gpu, orc):
         assert g1.DeModulate(x) == want
     finally:
         gpu.set_device(0)
+
+
+def test_counter_gather_through_the_c_abi_single_rank(gpu):
+    """qpsk_comm_* / qpsk_ber_gather (csrc/comm.cu): the library's own NCCL communicator.  One GPU here, so the
+    communicator has one rank (an all-gather over one rank); bench.py runs the same calls at N = 2, 4, 8."""
+    import torch
+    from qpsk_modulator_demodulator_b200 import shard
+    comm = shard.CounterComm(1, 0, lambda ident: ident)
+    info = comm.info()
+    assert info["n_ranks"] == 1 and info["rank"] == 0 and info["nccl_version"] >= 21000
+    C = 37
+    cnt = torch.stack([torch.arange(C, dtype=torch.int32), torch.arange(C, dtype=torch.int32) + 1000], dim=1).contiguous().cuda()
+    torch.cuda.synchronize()
+    allc = comm.gather(cnt.data_ptr(), C, C)
+    assert allc.shape == (C, 2) and np.array_equal(allc[:, 0], np.arange(C)) and np.array_equal(allc[:, 1], np.arange(C) + 1000)
+    # ragged: the block is shorter than the common width -> padded rows are dropped again by the host mirror
+    L = gpu._native.lib()
+    out = np.zeros((1, 40, 2), np.uint32)
+    assert L.qpsk_ber_gather(comm._h, cnt.data_ptr(), C, 40, out.ctypes.data) == 0
+    assert np.array_equal(out[0, :C, 1], np.arange(C) + 1000) and not out[0, C:].any()
+    assert L.qpsk_ber_gather(comm._h, cnt.data_ptr(), 41, 40, out.ctypes.data) == gpu._native.ERR_RANGE
+    comm.close()

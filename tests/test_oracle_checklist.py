@@ -232,3 +232,19 @@ def test_save_as_cs16_known_answers():
     assert m == 0.0 and out.tolist() == [0, 0, 0, 0]
     with pytest.raises(ValueError):
         np_twin.save_as_cs16(np.zeros(0, np.float32))
+
+
+def test_decimate_oracle_is_the_subsampled_streaming_filter(orc):
+    """Row N1: y_dec[m] = y[skip + m*D] of ComplexFIRFilter.Filter (FIRFilter.cs:80-91), whatever the chunking of the
+    full-rate filter underneath (its delay line is carried, :50-52)."""
+    import numpy as np
+    taps = orc.real_taps_to_iq(orc.RRCFilter.generateCoefficents(8, 0.35, 4000, 1000))
+    x = orc.fill_uniform(3, 0, 0, 2 * 1001)
+    y = orc.ComplexFIRFilter(taps).Filter(x)
+    for D, skip in ((2, 0), (4, 0), (4, 3), (16, 5), (1, 0)):
+        d = orc.decimate(y, D, skip)
+        assert d.size == 2 * len(range(skip, 1001, D))
+        assert np.array_equal(d.reshape(-1, 2), y.reshape(-1, 2)[skip::D])
+    f = orc.ComplexFIRFilter(taps)
+    y2 = np.concatenate([f.Filter(x[:2 * 333]), f.Filter(x[2 * 333:])])
+    assert np.array_equal(orc.decimate(y2, 4), orc.decimate(y, 4))
