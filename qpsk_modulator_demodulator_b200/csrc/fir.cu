@@ -910,13 +910,17 @@ struct FirCfg {
   int R, NT, per_sm;
 };
 constexpr FirCfg kFirCfgs[] = {{10, 256, 2}, {10, 320, 2}, {14, 224, 2}, {6, 256, 3}};
-inline int fir_cfg_index() {
-  static const int idx = [] {
+// QPSK_FIR_CFG=<index> forces one entry; otherwise the tap count picks: ten consumer warps (10, 320, 2) are ahead for
+// real-tap filters of ~48-96 taps (65 taps: 1.29 against 1.32 ms in the table above), eight everywhere else.
+inline int fir_cfg_index(int G = 0, bool cplx = false) {
+  static const int forced = [] {
     const char* e = getenv("QPSK_FIR_CFG");
-    const int i = e ? atoi(e) : 0;
+    if (!e) return -1;
+    const int i = atoi(e);
     return (i >= 0 && i < (int)(sizeof(kFirCfgs) / sizeof(kFirCfgs[0]))) ? i : 0;
   }();
-  return idx;
+  if (forced >= 0) return forced;
+  return (!cplx && G >= 48 && G <= 96) ? 1 : 0;
 }
 
 template <int R, int NT, bool CPLX>
@@ -927,16 +931,16 @@ int launch_tma_cfg(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, si
   QPSK_LAUNCH_CHECK();
   return QPSK_OK;
 }
-inline const char* tma_kernel_name(bool cplx) {
+inline const char* tma_kernel_name(bool cplx, int G) {
   static const char* const real_names[] = {"fir_tma_kernel<R=10,NT=256,real taps>", "fir_tma_kernel<R=10,NT=320,real taps>",
                                            "fir_tma_kernel<R=14,NT=224,real taps>", "fir_tma_kernel<R=6,NT=256,real taps>"};
   static const char* const cplx_names[] = {"fir_tma_kernel<R=10,NT=256,complex taps>", "fir_tma_kernel<R=10,NT=320,complex taps>",
                                            "fir_tma_kernel<R=14,NT=224,complex taps>", "fir_tma_kernel<R=6,NT=256,complex taps>"};
-  return (cplx ? cplx_names : real_names)[fir_cfg_index()];
+  return (cplx ? cplx_names : real_names)[fir_cfg_index(G, cplx)];
 }
 template <bool CPLX>
 int launch_tma(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, size_t smem, int grid, cudaStream_t s) {
-  switch (fir_cfg_index()) {
+  switch (fir_cfg_index(a.G, CPLX)) {
     case 1: return launch_tma_cfg<10, 320, CPLX>(a, taps, smem, grid, s);
     case 2: return launch_tma_cfg<14, 224, CPLX>(a, taps, smem, grid, s);
     case 3: return launch_tma_cfg<6, 256, CPLX>(a, taps, smem, grid, s);
@@ -959,7 +963,7 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
   const int hl = stateless ? (N - 1) : HL;
   const int G = (hl + 1 + 1) & ~1;
 
-  const FirCfg cfg = kFirCfgs[fir_cfg_index()];
+  const FirCfg cfg = kFirCfgs[fir_cfg_index(G, !real_taps)];
   const int T = cfg.R * cfg.NT;
   const int smem_budget = (cfg.per_sm == 2) ? kSmemBudget : (224 * 1024 / cfg.per_sm);
   bool use_tma = (mode == QPSK_FIR_FAST || stateless) && G <= kMaxG && hl <= T;
@@ -1009,7 +1013,7 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
         }
         QPSK_TRY(launch_tma<true>(a, t, smem, (int)grid, s));
       }
-      last_kernel = tma_kernel_name(!real_taps);
+      last_kernel = tma_kernel_name(!real_taps, G);
       if (!stateless) cur ^= 1;
       return QPSK_OK;
     }

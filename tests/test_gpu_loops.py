@@ -237,3 +237,30 @@ def test_costas_matches_oracle(gpu, orc, fs, bw):
             c.Process(np.zeros(3, np.float32))
         with pytest.raises(mod.ArgumentException):
             c.Process(np.zeros(4, np.float32), out_len=2)
+
+
+def test_fll_large_batch_kernel_choice_and_far_phase(gpu, orc):
+    """From 5120 streams the two-lanes-per-stream kernel (fll_pair_kernel) serves the FLL.  Its sin/cos is the |phase| < 64
+    form, so a caller-set phase beyond 32 goes through the lane-per-stream kernel for one call (which leaves the phase
+    wrapped); both calls, and the loop state after them, must be the oracle's bit for bit."""
+    C, L = 5200, 300
+    rng = np.random.default_rng(21)
+    x = (0.4 * rng.standard_normal((C, 2 * L))).astype(np.float32)
+    g = gpu.FLLBandEdgeFilter(2.0, 0.4, 40, 0.02, channels=C)
+    ph = np.zeros(C, np.float32)
+    fr = np.zeros(C, np.float32)
+    probe = [0, 1, 31, 32, 2600, C - 1]
+    ph[probe] = np.array([50.0, -37.5, 0.3, 6.5, 1000.25, -63.0], np.float32)
+    fr[probe] = np.array([0.1, -0.2, 0.0, 0.5, 0.01, -0.4], np.float32)
+    g.state = (ph, fr)
+    outs = [g.Process(x), g.Process(x[:, ::-1].copy())]        # first call: lane kernel (far phase); second: pair kernel
+    gp, gf = g.state
+    for c in probe + [7, 4000]:
+        o = orc.FLLBandEdgeFilter(2.0, 0.4, 40, 0.02)
+        o.state = (float(ph[c]), float(fr[c]))
+        w0 = o.Process(x[c])
+        w1 = o.Process(x[c, ::-1].copy())
+        assert np.array_equal(outs[0][c].view(np.uint32), w0.view(np.uint32)), c
+        assert np.array_equal(outs[1][c].view(np.uint32), w1.view(np.uint32)), c
+        op, of = o.state
+        assert np.float32(op) == gp[c] and np.float32(of) == gf[c], c
