@@ -730,46 +730,42 @@ __global__ void __launch_bounds__(NTO * NG, 3)
   constexpr int T_OUT = RO * NTO;
   constexpr int W = 2 * RO;
   constexpr int PP = DEC / 2 / NG;               // phase pairs per group
+  constexpr int LB = 8;                          // staged loads in flight per thread
   extern __shared__ __align__(16) unsigned char smem_dec[];
   float2* ys = reinterpret_cast<float2*>(smem_dec);          // [NG][T_OUT] partial sums
+  float2* xs = ys + NG * T_OUT;
   const int tid = threadIdx.x;
   const int to = tid % NTO, grp = tid / NTO;
   const int K = a.K;
   const int E = (T_OUT + K) * DEC;               // staged samples: the tile, the halo and the window's one-step look-ahead
-  const int EP = (E + PADS * (E / SPAN + 1) + 1) & ~1;       // padded tile, float2 slots (even)
-  float2* xs0 = ys + NG * T_OUT;                 // two tile buffers: tile t+1 lands (cp.async) while tile t is computed
-  // one tile into buffer `dst`: 8-byte cp.async per sample, zero-filled (src-size 0) outside the stream
-  auto stage = [&](long long tile, float2* dst) {
-    const int ch = (int)(tile / a.tiles_per_ch);
-    const int kt = (int)(tile - (long long)ch * a.tiles_per_ch);
-    const long long s0 = (long long)a.skip + (long long)kt * T_OUT * DEC - a.HL;   // stream index of logical xs[0]
-    const float2* xch = a.x + (long long)ch * a.ldx;
-    const float2* hch = a.hist_in + (long long)ch * a.HL;
-    for (int e = tid; e < E; e += NT) {
-      const long long sidx = s0 + e;
-      const float2* src = xch;                   // any valid address when nothing is read
-      unsigned bytes = 0;
-      if (sidx < 0) {
-        if (sidx >= -(long long)a.HL) { src = hch + (a.HL + sidx); bytes = 8; }
-      } else if (sidx < a.L) {
-        src = xch + sidx;
-        bytes = 8;
-      }
-      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + e + PADS * (e / SPAN));
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  if ((long long)blockIdx.x < a.total_tiles) stage(blockIdx.x, xs0);
-  int buf = 0;
-  for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, buf ^= 1) {
+  for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
     const int ch = (int)(tile / a.tiles_per_ch);
     const int kt = (int)(tile - (long long)ch * a.tiles_per_ch);
     const long long m0 = (long long)kt * T_OUT;
-    float2* xs = xs0 + (size_t)buf * EP;
-    if (tile + gridDim.x < a.total_tiles) stage(tile + gridDim.x, xs0 + (size_t)(buf ^ 1) * EP);
-    else asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");      // this tile has landed (the next one may still be in flight)
+    const long long s0 = (long long)a.skip + m0 * DEC - a.HL;          // stream index of logical xs[0]
+    const float2* xch = a.x + (long long)ch * a.ldx;
+    const float2* hch = a.hist_in + (long long)ch * a.HL;
+    for (int e0 = tid; e0 < E; e0 += NT * LB) {
+      float2 v[LB];
+#pragma unroll
+      for (int b = 0; b < LB; ++b) {             // LB independent loads, then LB stores: the loads overlap
+        const int e = e0 + b * NT;
+        const long long sidx = s0 + e;
+        v[b] = make_float2(0.f, 0.f);
+        if (e < E) {
+          if (sidx < 0) {
+            if (sidx >= -(long long)a.HL) v[b] = hch[a.HL + sidx];
+          } else if (sidx < a.L) {
+            v[b] = xch[sidx];
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < LB; ++b) {
+        const int e = e0 + b * NT;
+        if (e < E) xs[e + PADS * (e / SPAN)] = v[b];
+      }
+    }
     __syncthreads();
     float2 acc[RO];
 #pragma unroll
@@ -1123,8 +1119,7 @@ int FirEngine::decimate_dev(const float2* x, int64_t L, int64_t ldx, int dec, fl
       a.tiles_per_ch = (int)((nout + T_OUT - 1) / T_OUT);
       a.total_tiles = (long long)a.tiles_per_ch * channels;
       const int E = (T_OUT + K) * dec;
-      const int EP = (E + PADS * (E / SPAN + 1) + 1) & ~1;     // one padded tile buffer (the kernel keeps two)
-      const size_t smem = (size_t)(NG * T_OUT + 2 * EP) * sizeof(float2);
+      const size_t smem = (size_t)(NG * T_OUT + E + PADS * (E / SPAN + 1)) * sizeof(float2);
       if (smem > 200 * 1024) return QPSK_ERR_UNSUPPORTED;
       QPSK_TRY(allow_max_dynamic_smem((const void*)kern));
       long long per_sm = (long long)(224 * 1024) / (long long)(smem + 1024);
