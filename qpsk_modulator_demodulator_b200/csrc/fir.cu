@@ -720,7 +720,7 @@ __device__ __forceinline__ void dec_block(const float2* __restrict__ xk, const T
 // partial sums are added through shared memory, so that every decimation factor stages the same ~3600-sample tile with
 // the same 256 threads (a wider D would otherwise leave a handful of threads to load a tile).
 template <int RO, int NTO, int NG, int DEC>
-__global__ void __launch_bounds__(NTO * NG, 3)
+__global__ void __launch_bounds__(NTO * NG, 4)
     fir_decim_kernel(const __grid_constant__ DecArgs a, const __grid_constant__ TapsReal taps) {
   static_assert(DEC % 2 == 0 && (DEC / 2) % NG == 0, "phase pairs split evenly over the groups");
   constexpr int NT = NTO * NG;
@@ -1123,7 +1123,7 @@ int FirEngine::decimate_dev(const float2* x, int64_t L, int64_t ldx, int dec, fl
       if (smem > 200 * 1024) return QPSK_ERR_UNSUPPORTED;
       QPSK_TRY(allow_max_dynamic_smem((const void*)kern));
       long long per_sm = (long long)(224 * 1024) / (long long)(smem + 1024);
-      if (per_sm > 3) per_sm = 3;
+      if (per_sm > 4) per_sm = 4;
       if (per_sm < 1) per_sm = 1;
       long long grid = per_sm * device_sm_count();
       if (grid > a.total_tiles) grid = a.total_tiles;
