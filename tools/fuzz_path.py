@@ -153,7 +153,7 @@ def fuzz_demod():
         diff = bool(rng.random() < 0.7)
         tsc = None if rng.random() < 0.4 else TSC[: int(rng.choice([16, 64]))]
         use_fll = bool(rng.random() < 0.4)
-        C = int(rng.choice([1, 1, 2, 5]))
+        C = int(rng.choice([1, 1, 2, 5, 33, 40]))       # >= 32 channels: the matched filter runs fused inside the symbol-stage kernel
         mod = O.QPSKModulator(fs, rs, alpha, span, diff, tsc)
         rows = []
         nb = 2 * int(rng.integers(50, 1500))
