@@ -416,7 +416,9 @@ __global__ void __launch_bounds__(32)
       const float powLower = aLo.x * aLo.x + aLo.y * aLo.y;            // :119
       const float error = powLower - powUpper;                         // :121 (the odd lane's is the stream's)
       freq += P.beta * error;                            // :124
-      phase = phase + (freq + P.alpha * error);          // :125
+      const float p1 = phase + (freq + P.alpha * error); // :125
+      const float pw = lane_wrap_phase(p1);
+      phase = (p1 > kTwoPiF || p1 < -kTwoPiF) ? pw : p1; // :185-189
       freq = (freq > P.max_freq) ? P.max_freq : ((freq < P.min_freq) ? P.min_freq : freq);   // :191-195
       // ---- window n+1 becomes the current one: out[n] is its element N-2 ----
       if (kNewInVec) {
@@ -443,9 +445,6 @@ __global__ void __launch_bounds__(32)
       }
       pos = (pos + 1 == N) ? 0 : pos + 1;
       __syncwarp();                                    // the next iteration's window loads see both copies
-      // the rare wrap (:185-189) as a branch at the very end of the body: computed unconditionally it put an fp64 remainder
-      // (~80 cycles) on every sample's recurrence; here it costs a compare, and the body stays one basic block
-      if (phase > kTwoPiF || phase < -kTwoPiF) phase = lane_wrap_phase(phase);
     }
     if (lane < blk) {                     // flush: lane l writes sample n0 + l of every live stream
 #pragma unroll 8
