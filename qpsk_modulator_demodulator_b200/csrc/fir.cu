@@ -745,7 +745,27 @@ __global__ void __launch_bounds__(NTO * NG, 4)
     const long long s0 = (long long)a.skip + m0 * DEC - a.HL;          // stream index of logical xs[0]
     const float2* xch = a.x + (long long)ch * a.ldx;
     const float2* hch = a.hist_in + (long long)ch * a.HL;
-    for (int e0 = tid; e0 < E; e0 += NT * LB) {
+    // interior tiles whose first sample sits on a 16-byte boundary: two samples per load and store (a pair never straddles
+    // a pad: spans are an even number of samples) — half the staging instructions of the general path below
+    const bool wide = s0 >= 0 && s0 + E <= a.L && ((reinterpret_cast<uintptr_t>(xch + s0) & 15) == 0);
+    if (wide) {
+      const float4* src4 = reinterpret_cast<const float4*>(xch + s0);
+      for (int p0 = tid; p0 < E / 2; p0 += NT * LB) {
+        float4 v4[LB];
+#pragma unroll
+        for (int b = 0; b < LB; ++b) {
+          const int p = p0 + b * NT;
+          v4[b] = (p < E / 2) ? src4[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int b = 0; b < LB; ++b) {
+          const int p = p0 + b * NT;
+          const int e = 2 * p;
+          if (p < E / 2) *reinterpret_cast<float4*>(xs + e + PADS * (e / SPAN)) = v4[b];
+        }
+      }
+    }
+    for (int e0 = wide ? E : tid; e0 < E; e0 += NT * LB) {
       float2 v[LB];
 #pragma unroll
       for (int b = 0; b < LB; ++b) {             // LB independent loads, then LB stores: the loads overlap
