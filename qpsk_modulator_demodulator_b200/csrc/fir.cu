@@ -389,6 +389,13 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
+// The product rounded on its own as ONE packed instruction: fma.rn.f32x2(x, g, -0) == round(x*g) exactly (the -0 addend changes
+// neither value nor sign), and with the addend loaded at run time ptxas cannot contract it into the packed add that follows —
+// so the sum can be add.rn.f32x2 as well: FFMA2 + FADD2 per tap and output instead of FMUL2 + two scalar FADD (the kernel
+// was issue-bound on those: issue slots 76 % busy in ncu).
+__device__ float2 g_fir_neg_zero2 = {-0.0f, -0.0f};
+__device__ __forceinline__ float2 mul_then_add2(float2 acc, float2 x, float2 g, float2 nz) { return fadd2(acc, ffma2(x, g, nz)); }
+
 template <int NT>
 __global__ void __launch_bounds__(NT + 32, 3)
     fir_exact_real_kernel(const __grid_constant__ FirArgs a, const __grid_constant__ TapsReal taps, const int n_taps) {
@@ -460,6 +467,8 @@ __global__ void __launch_bounds__(NT + 32, 3)
   }
 
   // consumer warps
+  float2 nz;
+  asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(nz.x), "=f"(nz.y) : "l"(&g_fir_neg_zero2));
   const int lead = a.HL - (n_taps - 1);      // 0 or 1: xs index of window element 0 relative to the output index
   const int n_vec = n_taps & ~7;
   const int base = tid * R;
@@ -496,7 +505,7 @@ __global__ void __launch_bounds__(NT + 32, 3)
         const float g = taps.g[ib + l + lead];
         const float2 gg = make_float2(g, g);
 #pragma unroll
-        for (int r = 0; r < R; ++r) lp[r][l] = fadd2_after_mul(lp[r][l], fmul2(wv[l + r], gg));
+        for (int r = 0; r < R; ++r) lp[r][l] = mul_then_add2(lp[r][l], wv[l + r], gg, nz);
       }
       w0 = wv[8];
     }
@@ -511,7 +520,7 @@ __global__ void __launch_bounds__(NT + 32, 3)
       const float g = taps.g[i + lead];
       const float2 gg = make_float2(g, g);
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = fadd2_after_mul(acc[r], fmul2(xw[i + r], gg));
+      for (int r = 0; r < R; ++r) acc[r] = mul_then_add2(acc[r], xw[i + r], gg, nz);
     }
     // Non-finite results: an infinite SAMPLE makes the reference's hq*x terms NaN (0 * Inf), which the reduction above
     // does not model — recompute such outputs with the full complex product (an overflow to Inf gives the same value
