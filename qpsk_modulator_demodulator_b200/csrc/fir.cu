@@ -408,16 +408,9 @@ __global__ void __launch_bounds__(NT + 32, 3)
   float2* ys_base = xs_base + (size_t)a.stages * a.stage_elems;
   uint64_t* full = reinterpret_cast<uint64_t*>(ys_base + 2 * T);
   uint64_t* empty = full + a.stages;
-  // taps in shared memory, shifted so that window element i meets tap_s[i]: eight taps = two broadcast LDS.128 (straight from
-  // the constant bank they took eight indexed LDC per block of 16 products — as much time as the products themselves)
-  __shared__ __align__(16) float tap_s[kMaxG + 8];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  {
-    const int lead0 = a.HL - (n_taps - 1);
-    for (int i = tid; i < kMaxG + 8; i += NT + 32) tap_s[i] = (i + lead0 < kMaxG) ? taps.g[i + lead0] : 0.f;
-  }
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full[s], 1);
@@ -507,11 +500,10 @@ __global__ void __launch_bounds__(NT + 32, 3)
       wv[0] = w0;
 #pragma unroll
       for (int j = 1; j < 9; ++j) wv[j] = xw[ib + j];
-      const float4 ta = *reinterpret_cast<const float4*>(tap_s + ib), tb = *reinterpret_cast<const float4*>(tap_s + ib + 4);
-      const float tg[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
       for (int l = 0; l < 8; ++l) {
-        const float2 gg = make_float2(tg[l], tg[l]);
+        const float g = taps.g[ib + l + lead];
+        const float2 gg = make_float2(g, g);
 #pragma unroll
         for (int r = 0; r < R; ++r) lp[r][l] = mul_then_add2(lp[r][l], wv[l + r], gg, nz);
       }
@@ -525,7 +517,7 @@ __global__ void __launch_bounds__(NT + 32, 3)
       for (int l = 0; l < 8; ++l) acc[r] = fadd2(acc[r], lp[r][l]);   // lanes 0..7 (:176-180)
     }
     for (int i = n_vec; i < n_taps; ++i) {                             // scalar tail (:183-192)
-      const float g = tap_s[i];
+      const float g = taps.g[i + lead];
       const float2 gg = make_float2(g, g);
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = mul_then_add2(acc[r], xw[i + r], gg, nz);
