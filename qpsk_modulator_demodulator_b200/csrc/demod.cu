@@ -1474,25 +1474,35 @@ int qpsk_demod_bits(qpsk_demod* d, const float* iq_in, int64_t n_floats, char* b
   if (n_floats == 0) return QPSK_OK;                         // :350-351
   QPSK_TRY(ensure_device(d->eng.device));
   cudaStream_t s = e.stream;
-  const int64_t L = n_floats >> 1, ld = L + (L & 1);
-  QPSK_TRY(demod_stage_in(e, iq_in, L, s));
-  const long long ldb = e.bits_bound(L) + 2;
+  const int64_t L = n_floats >> 1;
+  const long long ldb = (e.bits_bound(L) + 2 + 15) & ~15LL;
   QPSK_TRY(e.d_bits.ensure((size_t)ldb * e.channels));
-  QPSK_TRY(e.bits_dev(e.h_in.p, L, ld, e.d_bits.p, ldb, e.d_nbits.p, s));
+  HostSrc hs;
+  hs.p = iq_in; hs.ld = L; hs.cs16 = false;
+  QPSK_TRY(e.bits_dev(nullptr, L, 0, e.d_bits.p, ldb, e.d_nbits.p, s, &hs));
   std::vector<long long> nb((size_t)e.channels);
   QPSK_CUDA_TRY(cudaMemcpyAsync(nb.data(), e.d_nbits.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
   QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   int st = QPSK_OK;
-  std::vector<uint8_t> tmp;
+  long long widest = 0;
   for (int c = 0; c < e.channels; ++c) {
     n_bits[c] = nb[(size_t)c];
-    if (nb[(size_t)c] > cap) { st = QPSK_ERR_CAPACITY; continue; }
-    if (nb[(size_t)c] == 0) continue;
+    if (nb[(size_t)c] > cap) st = QPSK_ERR_CAPACITY;
+    else if (nb[(size_t)c] > widest) widest = nb[(size_t)c];
+  }
+  if (widest > 0) {
     if (!bits_out) return QPSK_ERR_NULL;
-    tmp.resize((size_t)nb[(size_t)c]);
-    QPSK_CUDA_TRY(cudaMemcpy(tmp.data(), e.d_bits.p + (size_t)c * ldb, tmp.size(), cudaMemcpyDeviceToHost));
-    char* o = bits_out + (size_t)c * cap;
-    for (size_t i = 0; i < tmp.size(); ++i) o[i] = tmp[i] ? '1' : '0';
+    // bytes 0/1 -> '0'/'1' on the device, then ONE 2-D copy as wide as the longest string of the call (a channel's
+    // characters past its own n_bits are unspecified, like the rest of the caller's buffer)
+    const long long tot = ldb * e.channels;
+    long long blocks = (tot + 255) / 256;
+    const long long capb = 32LL * device_sm_count();
+    if (blocks > capb) blocks = capb;
+    bits_to_chars_kernel<<<(int)blocks, 256, 0, s>>>(e.d_bits.p, reinterpret_cast<char*>(e.d_bits.p), tot);
+    QPSK_LAUNCH_CHECK();
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(bits_out, (size_t)cap, e.d_bits.p, (size_t)ldb, (size_t)widest, (size_t)e.channels,
+                                    cudaMemcpyDeviceToHost, s));
+    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   }
   return st;
 }
@@ -1519,16 +1529,19 @@ int qpsk_demod_bits_packed(qpsk_demod* d, const float* iq_in, int64_t n_floats, 
   QPSK_CUDA_TRY(cudaMemcpyAsync(nb.data(), e.d_nbits.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
   QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   int st = QPSK_OK;
+  long long widest = 0;
   for (int c = 0; c < e.channels; ++c) {
     n_bits[c] = nb[(size_t)c];
     const long long bytes = (nb[(size_t)c] + 7) / 8;
-    if (bytes > cap_bytes) { st = QPSK_ERR_CAPACITY; continue; }
-    if (bytes == 0) continue;
-    if (!packed_out) return QPSK_ERR_NULL;
-    QPSK_CUDA_TRY(cudaMemcpyAsync(packed_out + (size_t)c * cap_bytes, e.d_pk.p + (size_t)c * ldp, (size_t)bytes,
-                                  cudaMemcpyDeviceToHost, s));
+    if (bytes > cap_bytes) st = QPSK_ERR_CAPACITY;
+    else if (bytes > widest) widest = bytes;
   }
-  QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  if (widest > 0) {
+    if (!packed_out) return QPSK_ERR_NULL;
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(packed_out, (size_t)cap_bytes, e.d_pk.p, (size_t)ldp, (size_t)widest, (size_t)e.channels,
+                                    cudaMemcpyDeviceToHost, s));
+    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+  }
   return st;
 }
 
@@ -1645,13 +1658,17 @@ int qpsk_demod_frame_bits(qpsk_demod* d, const uint8_t* bits, int64_t bits_strid
   QPSK_CUDA_TRY(cudaMemcpyAsync(np.data(), e.d_npayload.p, sizeof(long long) * e.channels, cudaMemcpyDeviceToHost, s));
   QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   int st = QPSK_OK;
+  long long widest = 0;
   for (int c = 0; c < e.channels; ++c) {
     n_bytes[c] = np[(size_t)c];
-    if (np[(size_t)c] > cap) { st = QPSK_ERR_CAPACITY; continue; }
-    if (np[(size_t)c] == 0) continue;
+    if (np[(size_t)c] > cap) st = QPSK_ERR_CAPACITY;
+    else if (np[(size_t)c] > widest) widest = np[(size_t)c];
+  }
+  if (widest > 0) {                                          // one 2-D copy as wide as the longest payload that fits
     if (!payload_out) return QPSK_ERR_NULL;
-    QPSK_CUDA_TRY(cudaMemcpy(payload_out + (size_t)c * cap, e.d_payload.p + (size_t)c * pcap, (size_t)np[(size_t)c],
-                             cudaMemcpyDeviceToHost));
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(payload_out, (size_t)cap, e.d_payload.p, (size_t)pcap, (size_t)widest, (size_t)e.channels,
+                                    cudaMemcpyDeviceToHost, s));
+    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   }
   return st;
 }
@@ -1676,13 +1693,17 @@ int qpsk_demod_constellation(qpsk_demod* d, const float* iq_in, int64_t n_floats
   QPSK_CUDA_TRY(cudaMemcpyAsync(ns.data(), dn.p, sizeof(int) * e.channels, cudaMemcpyDeviceToHost, s));
   QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   int st = QPSK_OK;
+  long long widest = 0;
   for (int c = 0; c < e.channels; ++c) {
     n_sym[c] = ns[(size_t)c];
-    if (2LL * ns[(size_t)c] > cap_floats) { st = QPSK_ERR_CAPACITY; continue; }
-    if (ns[(size_t)c] == 0) continue;
+    if (2LL * ns[(size_t)c] > cap_floats) st = QPSK_ERR_CAPACITY;
+    else if (ns[(size_t)c] > widest) widest = ns[(size_t)c];
+  }
+  if (widest > 0) {
     if (!sym_iq_out) return QPSK_ERR_NULL;
-    QPSK_CUDA_TRY(cudaMemcpy(sym_iq_out + (size_t)c * cap_floats, e.h_out.p + (size_t)c * lds, (size_t)ns[(size_t)c] * 8,
-                             cudaMemcpyDeviceToHost));
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(sym_iq_out, (size_t)cap_floats * 4, e.h_out.p, (size_t)lds * 8, (size_t)widest * 8,
+                                    (size_t)e.channels, cudaMemcpyDeviceToHost, s));
+    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   }
   return st;
 }

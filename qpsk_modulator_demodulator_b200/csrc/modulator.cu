@@ -198,8 +198,16 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
   // symbol D0 - HP + k lives at sym[k + 2*(k/8)]: two pad slots after every 8 symbols make the per-thread and
   // per-group stride 80 B (5 x 16 B, odd), so the 128-bit accesses of a quarter-warp fall in distinct banks
   __shared__ __align__(16) float2 sym[kModRegion + kModRegion / 4];
-  __shared__ int warp_tot[kModThreads / 32];
+  __shared__ __align__(16) int warp_tot[kModThreads / 32];
   __shared__ int halo_sum_s;
+  // SPS 2 / 4 / 8: the 32 lanes of a warp own 32 / SPS consecutive groups = 256 consecutive output samples (2 KiB) per round,
+  // but lane (group, phase) holds every SPS-th sample of its group: stored straight from the registers, one instruction
+  // touches 32 / SPS different 128-byte lines with 8 * SPS bytes each (ncu round 1: l1tex 89 % busy, the kernel's limiter).
+  // The round goes through a warp-private staging row instead — groups (R + 1) * SPS float2 apart, so that the 64-bit writes of
+  // a half-warp fall in distinct banks — and leaves as whole lines.
+  constexpr bool kStage = SPS == 2 || SPS == 4 || SPS == 8;
+  constexpr int kStageRow = 32 * (R + 1);
+  __shared__ __align__(16) float2 stage[kStage ? (kModThreads / 32) * kStageRow : 1];
 
   const int f = blockIdx.y, t = blockIdx.x;
   const long long D0 = (long long)t * a.TD;
@@ -234,7 +242,11 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
       if (tid == (a.HP >> 3)) halo_sum_s = inc - acc;
       __syncthreads();
       int base = inc - acc;
-      for (int w = 0; w < warp; ++w) base += warp_tot[w];
+      {
+        const int4 t0 = *reinterpret_cast<const int4*>(warp_tot), t1 = *reinterpret_cast<const int4*>(warp_tot + 4);
+        base += (warp > 0 ? t0.x : 0) + (warp > 1 ? t0.y : 0) + (warp > 2 ? t0.z : 0) + (warp > 3 ? t0.w : 0) +
+                (warp > 4 ? t1.x : 0) + (warp > 5 ? t1.y : 0) + (warp > 6 ? t1.z : 0);
+      }
       const unsigned q0 = (unsigned)((int)a.tile_pre[(long long)f * a.tiles + t] - halo_sum_s + base) & 3u;
       const unsigned q = (pre + q0 * 0x11111111u) & 0x33333333u;      // quadrant of every symbol
       // quadrant_symbol: q = 0:(+,+) 1:(-,+) 2:(-,-) 3:(+,-)  ->  I negative iff bit0 ^ bit1, Q negative iff bit1
@@ -247,21 +259,27 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
     }
     const unsigned kMag = __float_as_uint(kInvSqrt2);
     float4* dst = reinterpret_cast<float4*>(sym + 10 * tid);
-    const bool inside = d0 >= 0 && d0 + 8 <= a.n_dibits;      // all eight symbols exist (every chunk but the frame's edges)
+    if (d0 >= 0 && d0 + 8 <= a.n_dibits) {                    // all eight symbols exist (every chunk but the frame's edges)
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-      float2 v[2];
+      for (int j = 0; j < 8; j += 2) {
+        float2 v[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int sh = 31 - 4 * (7 - (j + u));      // moves the symbol's sign bit to bit 31
-        float2 sv = make_float2(__uint_as_float(kMag | ((sI << sh) & 0x80000000u)), __uint_as_float(kMag | ((sQ << sh) & 0x80000000u)));
-        if (!inside) {
-          const long long d = d0 + j + u;
-          if (d < 0 || d >= a.n_dibits) sv = make_float2(0.f, 0.f);
+        for (int u = 0; u < 2; ++u) {
+          const int sh = 31 - 4 * (7 - (j + u));    // moves the symbol's sign bit to bit 31
+          v[u] = make_float2(__uint_as_float(kMag | ((sI << sh) & 0x80000000u)), __uint_as_float(kMag | ((sQ << sh) & 0x80000000u)));
         }
-        v[u] = sv;
+        dst[j >> 1] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
       }
-      dst[j >> 1] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    } else {                                                  // kept out of the common path: 64-bit range tests per symbol
+      float2* d2 = sym + 10 * tid;
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        const int sh = 3 + 4 * j;
+        const long long d = d0 + j;
+        float2 sv = make_float2(__uint_as_float(kMag | ((sI << sh) & 0x80000000u)), __uint_as_float(kMag | ((sQ << sh) & 0x80000000u)));
+        if (d < 0 || d >= a.n_dibits) sv = make_float2(0.f, 0.f);
+        d2[j] = sv;
+      }
     }
   }
   __syncthreads();
@@ -278,6 +296,7 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
   const int n_groups = a.TD / R;
   float2* ob = a.out + (long long)f * a.out_stride + (D0 * sps - a.delay);   // output of (symbol D0, phase 0)
   const long long i_tile = D0 * sps - a.delay;    // its index in the frame
+  const bool tile_in = i_tile >= 0 && i_tile + (long long)n_groups * (R * sps) <= a.total;   // every sample of the tile exists
   for (int g = gl; g < n_groups; g += G) {
     const float2* gs = sym + 10 * ((a.HP >> 3) + g);   // the group's first symbol (padded layout)
     float2 w[R], acc[R];
@@ -313,9 +332,39 @@ __global__ void __launch_bounds__(kModThreads) mod_shape_kernel(const ModArgs a)
         w[(R - 2 - m + 16 * R) % R] = make_float2(nx.x, nx.y);      // symbol first - m - 2
       }
     }
+    if constexpr (kStage) {
+      const int glw = lane / SPS;                   // group slot within the warp
+      const int g_w = g - glw;                      // the warp's first group of this round
+      const long long iw = i_tile + (long long)g_w * (R * SPS);
+      // warp-uniform: all 32 / SPS groups exist and every sample lies inside the frame
+      if (g_w + 32 / SPS <= n_groups && (tile_in || (iw >= 0 && iw + 32 * R <= a.total))) {
+        float2* sw = stage + warp * kStageRow;
+        float2* mine = sw + glw * ((R + 1) * SPS) + p;
+#pragma unroll
+        for (int r = 0; r < R; ++r) mine[r * SPS] = acc[r];
+        __syncwarp();
+        float2* og = ob + g_w * (R * SPS);
+        if ((reinterpret_cast<unsigned long long>(og) & 15ull) == 0) {
+#pragma unroll
+          for (int k = 0; k < R / 2; ++k) {
+            const int l2 = 2 * (k * 32 + lane);     // sample index inside the round
+            const float4 v = *reinterpret_cast<const float4*>(sw + (l2 / (R * SPS)) * ((R + 1) * SPS) + l2 % (R * SPS));
+            __stcs(reinterpret_cast<float4*>(og + l2), v);
+          }
+        } else {                                    // odd filter delay or odd frame stride: 8-byte stores, still contiguous
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            const int l1 = k * 32 + lane;
+            __stcs(og + l1, sw[(l1 / (R * SPS)) * ((R + 1) * SPS) + l1 % (R * SPS)]);
+          }
+        }
+        __syncwarp();
+        continue;
+      }
+    }
     const int off = g * R * sps + p;              // relative to ob, r = 0
     const long long i0 = i_tile + off;
-    if (i0 >= 0 && i0 + (long long)(R - 1) * sps < a.total) {
+    if (tile_in || (i0 >= 0 && i0 + (long long)(R - 1) * sps < a.total)) {
 #pragma unroll
       for (int r = 0; r < R; ++r) ob[off + r * sps] = acc[r];
     } else {
