@@ -84,8 +84,14 @@ QPSK_API int qpsk_rrc_taps(double span_symbols, double beta, int sample_rate, in
                            double* out, int cap, int* n);
 
 /* ---- a2-a5  ComplexFIRFilter  (MS/Models/FIRFilter.cs:8-232) ------------------------------ */
-#define QPSK_FIR_FAST 0   /* fp32 FMA accumulation (default)                                      */
+#define QPSK_FIR_FAST 0   /* fp32 FMA accumulation (default); the library picks the kernel: for real taps from
+                           * 47 taps on the 2-parallel split below, else the tap-sequential FMA kernel          */
 #define QPSK_FIR_EXACT 1  /* the reference's summation order: 8 lane partials, no FMA (:165-192) */
+#define QPSK_FIR_FMA 2    /* always the tap-sequential FMA kernel (one rounding per tap)                         */
+#define QPSK_FIR_SPLIT 3  /* the 2-parallel fast-FIR split wherever it applies (real taps, >= 14 taps): three half-length
+                           * sub-filters per output pair, 0.8 of the multiply-adds; other summation order, still within
+                           * 1e-5 of max|y| of the reference.  Outputs are NOT bit-identical across different chunkings
+                           * of one stream (a cancelled term contains the following sample); FMA and EXACT are.    */
 /* ctor :29-53.  taps_iq interleaved complex taps; n_floats even and > 0. */
 QPSK_API int qpsk_fir_create(const float* taps_iq, int n_floats, qpsk_fir** out);
 /* the same filter over `channels` independent streams, one (N-1)-sample history each */

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libqpskcuda.so")
 
 OK = 0
 ERR_NULL, ERR_ARG, ERR_RANGE, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6, -7, -8
-FIR_FAST, FIR_EXACT = 0, 1
+FIR_FAST, FIR_EXACT, FIR_FMA, FIR_SPLIT = 0, 1, 2, 3
 
 
 class ArgumentNullException(ValueError):

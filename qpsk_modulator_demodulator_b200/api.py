@@ -16,7 +16,7 @@ from . import _native as N
 from ._native import (ArgumentException, ArgumentNullException, ArgumentOutOfRangeException, ChanParams,  # noqa: F401
                       QpskCudaError, check, lib)
 
-FIR_FAST, FIR_EXACT = N.FIR_FAST, N.FIR_EXACT
+FIR_FAST, FIR_EXACT, FIR_FMA, FIR_SPLIT = N.FIR_FAST, N.FIR_EXACT, N.FIR_FMA, N.FIR_SPLIT
 
 
 def _f32(a) -> np.ndarray:

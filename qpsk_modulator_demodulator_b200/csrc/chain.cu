@@ -47,6 +47,7 @@ struct ChainEngine {
     const std::vector<double> h = design_rrc(p.rrc_span, p.rrc_alpha, p.sample_rate, p.symbol_rate);
     const std::vector<float> iq = real_taps_as_iq(h);
     QPSK_TRY(mf.init(iq.data(), (int)iq.size(), channels));
+    mf.mode = QPSK_FIR_FMA;
     QPSK_TRY(fll.init(p.fll_sps, p.fll_rolloff, p.fll_size, p.fll_bw, channels));
     QPSK_TRY(mm.init(p.mm_sps, p.mm_kp, p.mm_ki, channels));
     QPSK_TRY(costas.init(p.costas_sample_rate, p.costas_bw_hz, p.costas_damping, channels));
@@ -136,7 +137,7 @@ int qpsk_chain_destroy(qpsk_chain* c) {
 int qpsk_chain_set_fir_mode(qpsk_chain* c, int mode) {
   if (!c) return QPSK_ERR_NULL;
   if (mode != QPSK_FIR_FAST && mode != QPSK_FIR_EXACT) return QPSK_ERR_RANGE;
-  c->eng.mf.mode = mode;
+  c->eng.mf.mode = mode == QPSK_FIR_FAST ? QPSK_FIR_FMA : mode;   // chunk-invariant bit for bit (the split kernel is not)
   return QPSK_OK;
 }
 

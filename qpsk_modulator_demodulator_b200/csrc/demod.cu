@@ -1444,7 +1444,8 @@ int qpsk_demod_destroy(qpsk_demod* d) {
 int qpsk_demod_set_fir_mode(qpsk_demod* d, int mode) {
   if (!d) return QPSK_ERR_NULL;
   if (mode != QPSK_FIR_FAST && mode != QPSK_FIR_EXACT) return QPSK_ERR_RANGE;
-  d->eng.mf.mode = mode;
+  // FAST inside the modem = the tap-sequential FMA kernel: chunk-invariant bit for bit (the time-chunk pipeline relies on it)
+  d->eng.mf.mode = mode == QPSK_FIR_FAST ? QPSK_FIR_FMA : mode;
   return QPSK_OK;
 }
 

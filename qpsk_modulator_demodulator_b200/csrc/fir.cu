@@ -355,6 +355,257 @@ __global__ void __launch_bounds__(NT + 32, R <= 6 ? 3 : 2)
 }
 
 // ---------------------------------------------------------------------------------------------
+// fir_split2_kernel: QPSK_FIR_FAST for long real-tap filters — the 2-parallel fast-FIR split
+// ---------------------------------------------------------------------------------------------
+// The FMA kernel above is bound by the FP32 pipe from ~100 taps on (84 % of its cycles at 257 taps): the only way left to
+// go faster is to issue fewer FFMA2.  Split samples and taps into even / odd phases, X0[k] = xs[b+2k], X1[k] = xs[b+2k+1],
+// H0[j] = g[2j], H1[j] = g[2j+1] (correlation form, (H*X)[m] = sum_j H[j] X[m+j]):
+//     y[b+2m]   = (H0*X0)[m] + (H1*X1)[m]
+//     y[b+2m+1] = (H0*X1)[m] + (H1*X0)[m+1]
+// and with S[k] = X1[k] + X0[k+1], H2 = H0 + H1:
+//     (H2*S)[m] = y[b+2m+1] + (H0*X0)[m+1] + (H1*X1)[m]
+// so A = H0*X0 (P+1 values), B = H1*X1 (P values), C = H2*S (P values) give 2P outputs with (3P+1) * G/2 multiply-adds
+// instead of 2P * G: 0.8 of the FFMA2 for P = 5.  The summation order differs from both the FMA kernel's and the
+// reference's (still inside north_star's 1e-5 of max|y|: tests/test_gpu_fir.py), so QPSK_FIR_EXACT never comes here.
+// S is formed once per warp and tile in a warp-private plane of shared memory (one FADD2 per sample pair), not per thread.
+// Register windows: three circular windows of P + 2 = 7 slots, 7 sub-taps (14 taps) per unrolled block, so every slot index
+// is a compile-time constant; one LDS.128 (X0, X1) and one LDS.64 (S) per sub-tap feed 16 FFMA2.
+__device__ __forceinline__ float2 fir_add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fir_sub2(float2 a, float2 b) {
+  float2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+
+constexpr int kMaxGh = kMaxG / 2;
+struct TapsSplit {
+  float h0[kMaxGh];   // g[2j]
+  float h1[kMaxGh];   // g[2j+1]
+  float h2[kMaxGh];   // h0 + h1, rounded to fp32 on the host
+};
+
+// NJ (<= 7) sub-taps starting at sub-tap j0 (a multiple of 7).  On entry wa / wb hold X0 / X1[j0 .. j0+P] in slots 0..P and wc
+// holds S[j0 .. j0+P-1] in slots 0..P-1; xn = float4 view at sample pair j0 + P + 1, sn = S plane at j0 + P.
+template <int P, int NJ>
+__device__ __forceinline__ void split2_block(const float4* __restrict__ xn, const float2* __restrict__ sn, const TapsSplit& taps, int j0,
+                                             float2 (&wa)[P + 2], float2 (&wb)[P + 2], float2 (&wc)[P + 2], float2 (&A)[P + 1],
+                                             float2 (&B)[P], float2 (&C)[P]) {
+  constexpr int W = P + 2;
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const float4 v = xn[jj];                       // (X0, X1)[j + P + 1]: first used by the next sub-tap
+    const float2 sv = sn[jj];                      // S[j + P]
+    const float t0 = taps.h0[j0 + jj], t1 = taps.h1[j0 + jj], t2 = taps.h2[j0 + jj];
+    const float2 g0 = make_float2(t0, t0), g1 = make_float2(t1, t1), g2 = make_float2(t2, t2);
+#pragma unroll
+    for (int m = 0; m <= P; ++m) A[m] = ffma2(wa[(jj + m) % W], g0, A[m]);
+#pragma unroll
+    for (int m = 0; m < P; ++m) B[m] = ffma2(wb[(jj + m) % W], g1, B[m]);
+#pragma unroll
+    for (int m = 0; m < P; ++m) C[m] = ffma2(wc[(jj + m) % W], g2, C[m]);
+    wa[(jj + P + 1) % W] = make_float2(v.x, v.y);  // slot of X0[j - 1]: dead
+    wb[(jj + P + 1) % W] = make_float2(v.z, v.w);  // slot of X1[j - 1]: dead
+    wc[(jj + P) % W] = sv;                         // slot of S[j - 2]: dead
+  }
+}
+
+template <int R, int NT>
+__global__ void __launch_bounds__(NT + 32, 2)
+    fir_split2_kernel(const __grid_constant__ FirArgs a, const __grid_constant__ TapsSplit taps) {
+  static_assert(R % 4 == 2, "R/2 odd: the per-thread strides of 8R and 4R bytes stay odd multiples of 16 / 8 bytes");
+  constexpr int P = R / 2;
+  constexpr int T = R * NT;
+  constexpr int W = P + 2;
+  constexpr int WS = 32 * R;   // outputs per consumer warp and tile
+  constexpr int NW = NT / 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* xs_base = reinterpret_cast<float2*>(smem_raw);
+  float2* ys_base = xs_base + (size_t)a.stages * a.stage_elems;     // one buffer of WS outputs per warp
+  const int spw = (WS + a.G) / 2 + 1;                                 // S values per warp (odd or even: 8-byte accesses only)
+  float2* sp_base = ys_base + T;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sp_base + (size_t)NW * spw + ((NW * spw) & 1));
+  uint64_t* empty = full + a.stages;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // ---------------- producer warp: the FMA kernel's staging ----------------
+    int stage = 0;
+    uint32_t parity = 0;
+    TileWalk w(a.tiles_per_ch);
+    for (int it = 0; w.tile < a.total_tiles; ++it, w.next()) {
+      if (it >= a.stages) mbar_wait(&empty[stage], parity ^ 1u);
+      const int ch = w.ch;
+      const long long n0 = (long long)w.k * T;
+      const long long s0 = n0 + a.advance - a.HL;
+      float2* dst = xs_base + (size_t)stage * a.stage_elems;
+      const float2* xch = a.x + (long long)ch * a.ldx;
+      uint64_t* bar = &full[stage];
+      const int E = a.E_load;
+      uint32_t tx = 0;
+      int nA = 0;
+      if (s0 < 0) {
+        nA = (int)((-s0) < (long long)E ? (-s0) : (long long)E);
+        if (a.hist_in) {
+          if (lane == 0) bulk_g2s(dst, a.hist_in + (long long)ch * a.HL + (a.HL + s0), (uint32_t)nA * 8u, bar);
+          tx += (uint32_t)nA * 8u;
+        } else {
+          for (int i = lane; i < nA; i += 32) dst[i] = make_float2(0.f, 0.f);
+        }
+      }
+      const long long m0 = s0 + nA;
+      long long avail = a.L - m0;
+      if (avail < 0) avail = 0;
+      const int nB = (int)(avail < (long long)(E - nA) ? avail : (long long)(E - nA));
+      const int nB2 = nB & ~1;
+      if (nB2 > 0) {
+        if (lane == 0) bulk_g2s(dst + nA, xch + m0, (uint32_t)nB2 * 8u, bar);
+        tx += (uint32_t)nB2 * 8u;
+      }
+      if ((nB & 1) && lane == 0) dst[nA + nB2] = xch[m0 + nB2];
+      for (int i = nA + nB + lane; i < E; i += 32) dst[i] = make_float2(0.f, 0.f);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(bar, tx);
+      if (++stage == a.stages) {
+        stage = 0;
+        parity ^= 1u;
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps ----------------
+  const int base = tid * R;
+  const int wbase = warp * WS;
+  float2* ys = ys_base + (size_t)warp * WS;
+  float2* sp = sp_base + (size_t)warp * spw;
+  const int Gh = a.G >> 1;
+  int stage = 0;
+  uint32_t parity = 0;
+  TileWalk tw(a.tiles_per_ch);
+  for (int it = 0; tw.tile < a.total_tiles; ++it, tw.next()) {
+    mbar_wait(&full[stage], parity);
+    const float2* xs = xs_base + (size_t)stage * a.stage_elems;
+
+    const int ch = tw.ch;
+    const int k = tw.k;
+    const long long n0 = (long long)k * T;
+    const long long left = a.L - n0;
+    const int valid = (int)(left < (long long)T ? left : (long long)T);
+
+    if (a.hist_out && k == a.tiles_per_ch - 1) {
+      const int off = (int)(a.L - n0);
+      float2* ho = a.hist_out + (long long)ch * a.HL;
+      for (int i = tid; i < a.HL; i += NT) ho[i] = xs[off + i];
+    }
+
+    // ---- this warp's S plane: S[q] = xs[wbase + 2q + 1] + xs[wbase + 2q + 2] ----
+    {
+      const float2* xo = xs + wbase + 1;
+      const int nq = (WS + a.G) / 2 - 1;            // the last pair a thread of this warp reads is q = WS/2 + Gh - 2
+      for (int q0 = lane; q0 < nq; q0 += 96) {      // three pairs in flight per lane: loads first (xs and sp may alias for
+        float2 u0[3], u1[3];                        // all the compiler knows, it would not hoist them over the stores)
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int q = q0 + 32 * u;
+          if (q < nq) {
+            u0[u] = xo[2 * q];
+            u1[u] = xo[2 * q + 1];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int q = q0 + 32 * u;
+          if (q < nq) sp[q] = fir_add2(u0[u], u1[u]);
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- register-tiled correlations A, B, C ----
+    float2 wa[W], wb[W], wc[W];
+    float2 A[P + 1], B[P], C[P];
+#pragma unroll
+    for (int m = 0; m <= P; ++m) A[m] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < P; ++m) {
+      B[m] = make_float2(0.f, 0.f);
+      C[m] = make_float2(0.f, 0.f);
+    }
+    const float4* xv = reinterpret_cast<const float4*>(xs + base);
+    const float2* sv = sp + lane * P;
+#pragma unroll
+    for (int m = 0; m <= P; ++m) {
+      const float4 v = xv[m];
+      wa[m] = make_float2(v.x, v.y);
+      wb[m] = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int m = 0; m < P; ++m) wc[m] = sv[m];
+    int j0 = 0;
+    for (; j0 + W <= Gh; j0 += W) split2_block<P, W>(xv + j0 + P + 1, sv + j0 + P, taps, j0, wa, wb, wc, A, B, C);
+    switch (Gh - j0) {                              // compile-time tail, same circular windows
+#define QPSK_TAIL2(K) case K: split2_block<P, (K < W ? K : 0)>(xv + j0 + P + 1, sv + j0 + P, taps, j0, wa, wb, wc, A, B, C); break;
+      QPSK_TAIL2(1) QPSK_TAIL2(2) QPSK_TAIL2(3) QPSK_TAIL2(4) QPSK_TAIL2(5) QPSK_TAIL2(6) QPSK_TAIL2(7) QPSK_TAIL2(8)
+#undef QPSK_TAIL2
+      default: break;
+    }
+    // this warp is done reading the input slot and its S plane
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+
+    // ---- epilogue: recombine, registers -> this warp's smem slice -> TMA bulk store ----
+    if (lane == 0) bulk_wait_read<0>();   // the previous tile's store has drained the slice
+    __syncwarp();
+    float4* yv = reinterpret_cast<float4*>(ys + lane * R);
+#pragma unroll
+    for (int m = 0; m < P; ++m) {
+      const float2 ye = fir_add2(A[m], B[m]);
+      const float2 yo = fir_sub2(fir_sub2(C[m], A[m + 1]), B[m]);
+      yv[m] = make_float4(ye.x, ye.y, yo.x, yo.y);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    int wvalid = valid - wbase;
+    wvalid = wvalid < 0 ? 0 : (wvalid > WS ? WS : wvalid);
+    float2* yg = a.y + (long long)ch * a.ldy + n0 + (long long)wbase;
+    if ((wvalid & 1) == 0) {
+      if (lane == 0) {
+        if (wvalid > 0) bulk_s2g(yg, ys, (uint32_t)wvalid * 8u);
+        bulk_commit();
+      }
+    } else {
+      for (int i = lane; i < wvalid; i += 32) yg[i] = ys[i];
+      if (lane == 0) bulk_commit();
+    }
+    if (++stage == a.stages) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  if (lane == 0) bulk_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
 // fir_exact_real_kernel: QPSK_FIR_EXACT for real taps on the TMA pipeline
 // ---------------------------------------------------------------------------------------------
 // ComplexDotWindow's arithmetic (FIRFilter.cs:144-211, Vector<float>.Count == 8) bit for bit: window element i (oldest
@@ -979,6 +1230,48 @@ int launch_tma(const FirArgs& a, const typename TapsOf<CPLX>::type& taps, size_t
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// fir_split2_kernel geometry and the tap count from which QPSK_FIR_FAST uses it for real taps (QPSK_FIR_SPLIT2_MIN=<G>
+// overrides, 0 = never)
+// Measured on a B200, 2^28 samples, ms for 33 / 65 / 129 / 257 taps: FMA kernel 0.797 1.296 2.367 4.456 | split (10, 256)
+// 0.825 1.187 2.020 3.656 | split (10, 320), two ring stages only: - 1.301 2.243 4.199.  Ahead from ~48 taps on, where the
+// FMA pipe rather than HBM sets the time.
+constexpr int kS2R = 10, kS2NT = 256;
+constexpr int kS2MinForced = 14;        // QPSK_FIR_SPLIT: at least one full block of seven sub-taps
+inline int fir_split2_min_g() {
+  static const int v = [] {
+    const char* e = getenv("QPSK_FIR_SPLIT2_MIN");
+    return e && *e ? atoi(e) : 48;
+  }();
+  return v;
+}
+inline bool fir_mode_is_fast(int mode) { return mode != QPSK_FIR_EXACT; }
+// a: stream, delay-line and tap geometry filled in; tile geometry and the launch happen here
+template <int R2, int NT2>
+int launch_split2(FirArgs a, const TapsSplit& t, int channels, cudaStream_t s, const char** name) {
+  constexpr int T2 = R2 * NT2, NW2 = NT2 / 32, WS2 = 32 * R2;
+  if (a.HL > T2) return QPSK_ERR_UNSUPPORTED;
+  a.tiles_per_ch = (int)((a.L + T2 - 1) / T2);
+  a.total_tiles = (long long)a.tiles_per_ch * channels;
+  a.E_load = T2 + a.G;
+  a.stage_elems = a.E_load + 2;
+  const size_t stage_bytes = (size_t)a.stage_elems * 8;
+  const int spw = (WS2 + a.G) / 2 + 1;
+  const size_t fixed = (size_t)T2 * 8 + (size_t)(NW2 * spw + ((NW2 * spw) & 1)) * 8;
+  if (fixed + 128 + 2 * stage_bytes > (size_t)kSmemBudget) return QPSK_ERR_UNSUPPORTED;
+  int stages = (int)(((size_t)kSmemBudget - fixed - 128) / stage_bytes);
+  if (stages > 4) stages = 4;
+  a.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + fixed + (size_t)stages * 16;
+  long long grid = 2LL * device_sm_count();
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  auto kern = fir_split2_kernel<R2, NT2>;
+  QPSK_TRY(allow_max_dynamic_smem((const void*)kern));
+  kern<<<(int)grid, NT2 + 32, smem, s>>>(a, t);
+  QPSK_LAUNCH_CHECK();
+  *name = "fir_split2_kernel<R=10,NT=256,real taps>";
+  return QPSK_OK;
+}
+
 }  // namespace
 
 int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t ldy, bool stateless, cudaStream_t s) {
@@ -995,7 +1288,7 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
   const FirCfg cfg = kFirCfgs[fir_cfg_index(G, !real_taps)];
   const int T = cfg.R * cfg.NT;
   const int smem_budget = (cfg.per_sm == 2) ? kSmemBudget : (224 * 1024 / cfg.per_sm);
-  bool use_tma = (mode == QPSK_FIR_FAST || stateless) && G <= kMaxG && hl <= T;
+  bool use_tma = (fir_mode_is_fast(mode) || stateless) && G <= kMaxG && hl <= T;
   if (use_tma) {
     if (!aligned16(x) || !aligned16(y)) use_tma = false;
     if (channels > 1 && ((ldx & 1) || (ldy & 1))) use_tma = false;
@@ -1005,6 +1298,31 @@ int FirEngine::run(const float2* x, float2* y, int64_t L, int64_t ldx, int64_t l
   }
   const float2* hin = stateless ? nullptr : hist[cur].p;
   float2* hout = stateless ? nullptr : hist[cur ^ 1].p;
+
+  const bool want_split = (mode == QPSK_FIR_SPLIT && G >= kS2MinForced) ||
+                          (mode == QPSK_FIR_FAST && fir_split2_min_g() > 0 && G >= fir_split2_min_g());
+  if (use_tma && real_taps && want_split) {
+    FirArgs a;
+    a.x = x; a.y = y; a.ldx = ldx; a.ldy = ldy; a.L = L;
+    a.hist_in = hin; a.hist_out = hout;
+    a.HL = hl; a.G = G; a.advance = advance;
+    TapsSplit t;
+    memset(&t, 0, sizeof t);
+    for (int i = 0; i <= hl; ++i) {
+      const int j = hl - i;
+      const float g = (j < N) ? taps_iq[2 * j] : 0.0f;
+      ((i & 1) ? t.h1 : t.h0)[i >> 1] = g;
+    }
+    for (int j = 0; j < G / 2; ++j) t.h2[j] = t.h0[j] + t.h1[j];
+    const char* name = nullptr;
+    const int st = launch_split2<kS2R, kS2NT>(a, t, channels, s, &name);
+    if (st != QPSK_ERR_UNSUPPORTED) {              // UNSUPPORTED: the ring does not fit, the FMA kernel takes the call
+      QPSK_TRY(st);
+      last_kernel = name;
+      if (!stateless) cur ^= 1;
+      return QPSK_OK;
+    }
+  }
 
   if (use_tma) {
     FirArgs a;
@@ -1130,7 +1448,7 @@ int FirEngine::decimate_dev(const float2* x, int64_t L, int64_t ldx, int dec, fl
   const int64_t skip = dec_skip;
   const int N = n_taps;
   int K = (HL + 1 + dec - 1) / dec;
-  const bool fast = mode == QPSK_FIR_FAST && real_taps && (dec == 2 || dec == 4 || dec == 8 || dec == 16) &&
+  const bool fast = fir_mode_is_fast(mode) && real_taps && (dec == 2 || dec == 4 || dec == 8 || dec == 16) &&
                     (long long)K * dec <= kMaxG && nout > 0;
   bool launched = false;
   if (fast) {
@@ -1348,7 +1666,7 @@ int qpsk_fir_last_kernel(const qpsk_fir* f, char* name, int cap) {
 }
 int qpsk_fir_set_mode(qpsk_fir* f, int mode) {
   if (!f) return QPSK_ERR_NULL;
-  if (mode != QPSK_FIR_FAST && mode != QPSK_FIR_EXACT) return QPSK_ERR_RANGE;
+  if (mode != QPSK_FIR_FAST && mode != QPSK_FIR_EXACT && mode != QPSK_FIR_FMA && mode != QPSK_FIR_SPLIT) return QPSK_ERR_RANGE;
   f->eng.mode = mode;
   return QPSK_OK;
 }

@@ -296,7 +296,20 @@ def test_full_size_sweep_properties(gpu, orc):
         for pos, comp in imp:
             m = min(nt, n - pos)
             got = y[2 * pos: 2 * (pos + m)].cpu().numpy().reshape(-1, 2)
-            assert np.array_equal(got[:, comp], taps[0:2 * m:2]), (nt, pos)
+            if "split2" in f.last_kernel():
+                # the split kernel returns odd-phase taps as (h0 + h1) - h0: right to a rounding of the pair sum, not exact
+                assert np.abs(got[:, comp] - taps[0:2 * m:2]).max() <= 2e-7 * np.abs(taps).max(), (nt, pos)
+                fm = gpu.ComplexFIRFilter(taps)
+                fm.set_mode(gpu.FIR_FMA)              # the tap-sequential kernel: the taps themselves, bit for bit
+                lo_w = pos - nt
+                yw = torch.empty(2 * (m + nt), dtype=torch.float32, device="cuda")
+                fm.filter_dev(x[2 * lo_w:].data_ptr(), yw.data_ptr(), 2 * (m + nt), stream=s)
+                torch.cuda.synchronize()
+                gw = yw[2 * nt:].cpu().numpy().reshape(-1, 2)
+                assert np.array_equal(gw[:, comp], taps[0:2 * m:2]), (nt, pos)
+                assert not gw[:, 1 - comp].any()
+            else:
+                assert np.array_equal(got[:, comp], taps[0:2 * m:2]), (nt, pos)
             assert not got[:, 1 - comp].any()
         # windows against the oracle (with enough lead-in to fill the delay line)
         for lo in (0, 2560 * 7 - 100, n // 3, n - 5000):

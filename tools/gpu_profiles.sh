@@ -11,7 +11,7 @@ $B > $OUT/${TAG}_plain_bench.json 2> $OUT/${TAG}_plain_bench.err || { echo "plai
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/${TAG}_launches_bench.csv $B > $OUT/${TAG}_ncu_launch.log 2>&1
 echo "launch list rc=$?"
 # 2. FIR kernel, one launch per tap count (the timed region: skip warm-up launches 3 x 4)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:fir_tma -s 12 -c 4 -f -o $OUT/${TAG}_prof_fir $B --no-chain --no-decimate > $OUT/${TAG}_ncu_fir.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fir_tma|fir_split2" -s 12 -c 4 -f -o $OUT/${TAG}_prof_fir $B --no-chain --no-decimate > $OUT/${TAG}_ncu_fir.log 2>&1
 echo "fir rc=$?"
 # 3. decimating FIR: one launch per (taps, D) of the bench's `decimate` leg
 python tools/decim_probe.py > $OUT/${TAG}_plain_decim.log 2>&1
