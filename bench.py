@@ -320,6 +320,30 @@ def main():
     launches = Q.launch_count()
     ms = e0.elapsed_time(e1)
     kernels = {nt: f.last_kernel() for nt, f in filters}     # what the library actually launched for each tap count
+    # in-run parity of the timed output: y still holds what the LAST timed launch wrote (the longest filter, delay line carried
+    # from the step before = the tail of x).  Two windows — the head of the stream and one across tile seams deep inside — are
+    # recomputed by the CPU oracle (checker only) from the same samples; north_star's tolerance 1e-5 * max|y|.
+    fir_parity = None
+    if rank == 0 and not args.no_cpu:
+        import oracle as O
+        nt_last, f_last = filters[-1]
+        wlen = 4096
+        taps_last = taps_for(Q, *TAPS[-1])
+        worst, scale = 0.0, 0.0
+        for lo in (0, n // 3):
+            if lo == 0:
+                seg = torch.cat([x[2 * (n - (nt_last - 1)):], x[:2 * wlen]]).cpu().numpy()
+            else:
+                seg = x[2 * (lo - (nt_last - 1)): 2 * (lo + wlen)].cpu().numpy()
+            want = O.ComplexFIRFilter(taps_last).Filter(seg)[2 * (nt_last - 1):]
+            got = y[2 * lo: 2 * (lo + wlen)].cpu().numpy()
+            worst = max(worst, float(np.abs(got - want).max()))
+            scale = max(scale, float(np.abs(want).max()))
+        fir_parity = {"launch": f"last timed launch, {nt_last} taps, {kernels[nt_last]}",
+                      "windows": f"outputs [0, {wlen}) (delay line carried from the previous step) and [n/3, n/3 + {wlen})",
+                      "oracle": "oracle.ComplexFIRFilter.Filter (reference summation order) on the same samples",
+                      "max_abs_err_over_max_abs": worst / max(scale, 1e-30), "tolerance": 1e-5,
+                      "ok": bool(worst <= 1e-5 * scale)}
     clk = clocks.stop() if rank == 0 else None
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -501,7 +525,7 @@ def main():
                                    f"per GPU per tap count (BASELINE.json configs[1])",
                        "l2": "inputs 2 GiB + outputs 2 GiB per launch >> 126 MB L2; no flush needed",
                        "parallelism": f"{world} independent streams, one per GPU, no collective"},
-            "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_by_taps": roofs, "decimate": decimate, "fma_peak_tflops_measured": fma_peak,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_by_taps": roofs, "fir_parity": fir_parity, "decimate": decimate, "fma_peak_tflops_measured": fma_peak,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "build_id": build_id, "cpu_affinity": affinity,
             "scaling_note": "`scaling: weak` refers to `value` (one independent 2^28-sample FIR stream per GPU, no communication). "
