@@ -997,14 +997,41 @@ struct DemodEngine {
   bool fuse = true;            // use symsync_decode_kernel when it applies
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;               // front-end stream of the time-chunk pipeline
+  cudaStream_t copy = nullptr;               // host-source calls: the PCIe copies (and the CS16 widening) of the chunks
   cudaEvent_t ev_in = nullptr;
-  std::vector<cudaEvent_t> ev_chunk;
+  std::vector<cudaEvent_t> ev_chunk, ev_copy;
+  // page-locked landing zone of the host entry points' results: a 2-D device-to-host copy into PAGEABLE caller memory goes
+  // row by row through the driver's bounce buffer (2048 rows of ~540 bytes: 0.3-0.8 ms, a third of a DeModulateBytes call);
+  // one contiguous copy into this buffer and a memcpy per row cost ~0.1 ms
+  uint8_t* h_land = nullptr;
+  size_t h_land_bytes = 0;
+  int landing(size_t bytes) {
+    if (bytes <= h_land_bytes) return QPSK_OK;
+    if (h_land) cudaFreeHost(h_land);
+    h_land = nullptr;
+    h_land_bytes = 0;
+    QPSK_CUDA_TRY(cudaHostAlloc((void**)&h_land, bytes, cudaHostAllocPortable));
+    h_land_bytes = bytes;
+    return QPSK_OK;
+  }
+  // rows of `width` bytes, `ld_dev` apart on the device, to rows `ld_host` apart in caller memory; synchronises `s`
+  int fetch_rows(void* host, size_t ld_host, const void* dev, size_t ld_dev, size_t width, cudaStream_t s) {
+    if (width == 0) return QPSK_OK;
+    QPSK_TRY(landing(width * (size_t)channels));
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(h_land, width, dev, ld_dev, width, (size_t)channels, cudaMemcpyDeviceToHost, s));
+    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+    for (int c = 0; c < channels; ++c) memcpy((uint8_t*)host + (size_t)c * ld_host, h_land + (size_t)c * width, width);
+    return QPSK_OK;
+  }
 
   ~DemodEngine() {
     if (stream) cudaStreamDestroy(stream);
     if (side) cudaStreamDestroy(side);
+    if (copy) cudaStreamDestroy(copy);
+    if (h_land) cudaFreeHost(h_land);
     if (ev_in) cudaEventDestroy(ev_in);
     for (cudaEvent_t e : ev_chunk) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_copy) cudaEventDestroy(e);
   }
 
   int init(int fs, int rs, float alpha, int span, double sym_bw, double costas_bw, double cfo_bw, int diff_in,
@@ -1099,11 +1126,17 @@ struct DemodEngine {
     while (n > 1 && L < (int64_t)n * 8 * kSsBlock) --n;
     return n;
   }
-  // host-source calls: chunks of >= 2 MiB of samples (below that a copy does not reach the PCIe rate), at most 16
+  // host-source calls: chunks of >= 8 MiB of samples, at most 6 — every chunk is a 2-D copy of `channels` row pieces, and short
+  // pieces cost PCIe efficiency (2048 channels x 4380 samples, Gsample/s end to end at 1 / 2 / 4 / 6 / 8 / 16 chunks: cf32 4.25 /
+  // 4.91 / 5.11 / 5.13 / 5.07 / 4.96, CS16 6.03 / 7.00 / 7.47 / 7.39 / 7.17 / 6.69; tools/e2e_chunks_sweep.py)
   int host_chunks(int64_t L, bool cs16) const {
+    static const int env = [] {
+      const char* e = getenv("QPSK_DEMOD_HOST_CHUNKS");
+      return e ? atoi(e) : 0;
+    }();
     const double bytes = (double)L * channels * (cs16 ? 4.0 : 8.0);
-    int n = (int)(bytes / (2.0 * 1024 * 1024));
-    if (n > 16) n = 16;
+    int n = env > 0 ? env : (int)(bytes / (8.0 * 1024 * 1024));
+    if (n > (env > 0 ? 16 : 6)) n = env > 0 ? 16 : 6;
     if (n < 1) n = 1;
     while (n > 1 && L < (int64_t)n * 8 * kSsBlock) --n;
     return n;
@@ -1119,13 +1152,19 @@ struct DemodEngine {
                                     (size_t)len * 4, (size_t)channels, cudaMemcpyHostToDevice, st));
     return cs16_to_cf32_launch(h_cs16.p + 2 * n0, ld, hs.scale, h_in.p + n0, ld, len, channels, st);
   }
-  int ensure_pipeline(int chunks) {
+  int ensure_pipeline(int chunks, bool from_host) {
     if (!side) QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    if (from_host && !copy) QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
     if (!ev_in) QPSK_CUDA_TRY(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
     while ((int)ev_chunk.size() < chunks) {
       cudaEvent_t e = nullptr;
       QPSK_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       ev_chunk.push_back(e);
+    }
+    while (from_host && (int)ev_copy.size() < chunks) {
+      cudaEvent_t e = nullptr;
+      QPSK_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev_copy.push_back(e);
     }
     return QPSK_OK;
   }
@@ -1290,16 +1329,28 @@ struct DemodEngine {
       // every stage carries its state from chunk to chunk exactly (FLL ring/phase, MF delay line, MM queue, Costas,
       // differential reference), so the split changes nothing but the schedule.
       QPSK_TRY(mm.ensure_queue(8, s));
-      QPSK_TRY(ensure_pipeline(chunks));
+      QPSK_TRY(ensure_pipeline(chunks, from_host));
       // equal chunks except a half-size last one: the FLL on the side stream is the critical resource throughout, so
       // what is left exposed at the end is the last chunk's MM -> Costas -> decode
       const int64_t step = ((2 * L + 2 * chunks - 2) / (2 * chunks - 1) + kSsBlock - 1) / kSsBlock * kSsBlock;
       QPSK_CUDA_TRY(cudaEventRecord(ev_in, s));
       QPSK_CUDA_TRY(cudaStreamWaitEvent(side, ev_in, 0));     // inputs (and the previous call) are complete
+      if (from_host) {
+        // the PCIe copies run on a stream of their own, all queued up front: chunk t+1 crosses the bus while the FLL (side
+        // stream) works on chunk t and the symbol stage (caller's stream) on chunk t-1.  On the side stream they would
+        // queue behind the FLL launches: copy and FLL would take turns (3.3 ms per step where 1.3 + tail is possible).
+        QPSK_CUDA_TRY(cudaStreamWaitEvent(copy, ev_in, 0));
+        int tc = 0;
+        for (int64_t n0 = 0; n0 < L; n0 += step, ++tc) {
+          const int64_t len = (L - n0 < step) ? (L - n0) : step;
+          QPSK_TRY(stage_host_chunk(*hs, n0, len, mf_ld, copy));
+          QPSK_CUDA_TRY(cudaEventRecord(ev_copy[(size_t)tc], copy));
+        }
+      }
       int t = 0;
       for (int64_t n0 = 0; n0 < L; n0 += step, ++t) {
         const int64_t len = (L - n0 < step) ? (L - n0) : step;
-        if (from_host) QPSK_TRY(stage_host_chunk(*hs, n0, len, mf_ld, side));            // PCIe copy of this chunk
+        if (from_host) QPSK_CUDA_TRY(cudaStreamWaitEvent(side, ev_copy[(size_t)t], 0));
         const float2* src = x + n0;
         int64_t lds = ldx;
         if (use_fll) {
@@ -1501,9 +1552,7 @@ int qpsk_demod_bits(qpsk_demod* d, const float* iq_in, int64_t n_floats, char* b
     if (blocks > capb) blocks = capb;
     bits_to_chars_kernel<<<(int)blocks, 256, 0, s>>>(e.d_bits.p, reinterpret_cast<char*>(e.d_bits.p), tot);
     QPSK_LAUNCH_CHECK();
-    QPSK_CUDA_TRY(cudaMemcpy2DAsync(bits_out, (size_t)cap, e.d_bits.p, (size_t)ldb, (size_t)widest, (size_t)e.channels,
-                                    cudaMemcpyDeviceToHost, s));
-    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+    QPSK_TRY(e.fetch_rows(bits_out, (size_t)cap, e.d_bits.p, (size_t)ldb, (size_t)widest, s));
   }
   return st;
 }
@@ -1539,9 +1588,7 @@ int qpsk_demod_bits_packed(qpsk_demod* d, const float* iq_in, int64_t n_floats, 
   }
   if (widest > 0) {
     if (!packed_out) return QPSK_ERR_NULL;
-    QPSK_CUDA_TRY(cudaMemcpy2DAsync(packed_out, (size_t)cap_bytes, e.d_pk.p, (size_t)ldp, (size_t)widest, (size_t)e.channels,
-                                    cudaMemcpyDeviceToHost, s));
-    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+    QPSK_TRY(e.fetch_rows(packed_out, (size_t)cap_bytes, e.d_pk.p, (size_t)ldp, (size_t)widest, s));
   }
   return st;
 }
@@ -1569,9 +1616,7 @@ static int demod_bytes_host(qpsk_demod* d, const HostSrc& hs, int64_t L, const u
   }
   if (widest > 0) {
     if (!payload_out) return QPSK_ERR_NULL;
-    QPSK_CUDA_TRY(cudaMemcpy2DAsync(payload_out, (size_t)cap, e.d_payload.p, (size_t)pcap, (size_t)widest, (size_t)e.channels,
-                                    cudaMemcpyDeviceToHost, s));
-    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+    QPSK_TRY(e.fetch_rows(payload_out, (size_t)cap, e.d_payload.p, (size_t)pcap, (size_t)widest, s));
   }
   return st;
 }
@@ -1667,9 +1712,7 @@ int qpsk_demod_frame_bits(qpsk_demod* d, const uint8_t* bits, int64_t bits_strid
   }
   if (widest > 0) {                                          // one 2-D copy as wide as the longest payload that fits
     if (!payload_out) return QPSK_ERR_NULL;
-    QPSK_CUDA_TRY(cudaMemcpy2DAsync(payload_out, (size_t)cap, e.d_payload.p, (size_t)pcap, (size_t)widest, (size_t)e.channels,
-                                    cudaMemcpyDeviceToHost, s));
-    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+    QPSK_TRY(e.fetch_rows(payload_out, (size_t)cap, e.d_payload.p, (size_t)pcap, (size_t)widest, s));
   }
   return st;
 }
@@ -1702,9 +1745,7 @@ int qpsk_demod_constellation(qpsk_demod* d, const float* iq_in, int64_t n_floats
   }
   if (widest > 0) {
     if (!sym_iq_out) return QPSK_ERR_NULL;
-    QPSK_CUDA_TRY(cudaMemcpy2DAsync(sym_iq_out, (size_t)cap_floats * 4, e.h_out.p, (size_t)lds * 8, (size_t)widest * 8,
-                                    (size_t)e.channels, cudaMemcpyDeviceToHost, s));
-    QPSK_CUDA_TRY(cudaStreamSynchronize(s));
+    QPSK_TRY(e.fetch_rows(sym_iq_out, (size_t)cap_floats * 4, e.h_out.p, (size_t)lds * 8, (size_t)widest * 8, s));
   }
   return st;
 }
