@@ -26,13 +26,16 @@ echo "chain rc=$?"
 QPSK_DEMOD_CHUNKS=1 SWEEP=16384 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fll_pair|symsync" -s 4 -c 2 -f \
   -o $OUT/${TAG}_prof_chain16k python tools/fll_impl_sweep.py > $OUT/${TAG}_ncu_chain16k.log 2>&1
 echo "chain16k rc=$?"
+# 6. modulator leg: mod_shape_kernel, one launch of 512 frames
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mod_shape -s 3 -c 1 -f -o $OUT/${TAG}_prof_mod python tools/mod_probe.py 512 2 > $OUT/${TAG}_ncu_mod.log 2>&1
+echo "mod rc=$?"
 # condense on the box: the reports themselves are too big to travel back (64 MiB limit)
-for k in fir decim chain chain16k; do
+for k in fir decim chain chain16k mod; do
   python tools/ncu_summary.py $OUT/${TAG}_prof_$k.ncu-rep $OUT/${TAG}_ncu_full_${k}_summary.csv
 done
-for k in chain chain16k; do
+for k in chain chain16k mod fir; do
   python tools/ncu_src.py $OUT/${TAG}_prof_$k.ncu-rep 40 > $OUT/${TAG}_ncu_src_$k.txt 2>&1
 done
 ls -la $OUT/${TAG}_prof_*.ncu-rep
-rm -f $OUT/${TAG}_prof_decim.ncu-rep $OUT/${TAG}_prof_chain16k.ncu-rep $OUT/${TAG}_prof_fir.ncu-rep
+rm -f $OUT/${TAG}_prof_*.ncu-rep
 du -sh $OUT
