@@ -37,6 +37,7 @@ internal static unsafe partial class QpskCuda
     [DllImport(Lib)] internal static extern int qpsk_fir_destroy(IntPtr h);
     [DllImport(Lib)] internal static extern int qpsk_fir_filter(IntPtr h, float* iqIn, float* iqOut, long nFloats, long outCap);
     [DllImport(Lib)] internal static extern int qpsk_fir_fft_filter(IntPtr h, float* iqIn, float* iqOut, long nFloats);
+    [DllImport(Lib)] internal static extern int qpsk_fir_set_mode(IntPtr h, int mode);   // QPSK_FIR_FAST 0 / EXACT 1 / FMA 2 / SPLIT 3
     // a7-a8  FLLBandEdgeFilter                      (MS/Models/Band-Edge Filter.cs:40,64)
     [DllImport(Lib)] internal static extern int qpsk_fll_create(float sps, float rolloff, int filterSize, float bw, out IntPtr h);
     [DllImport(Lib)] internal static extern int qpsk_fll_destroy(IntPtr h);

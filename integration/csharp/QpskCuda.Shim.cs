@@ -84,6 +84,15 @@ namespace QPSK.Models
             GC.KeepAlive(this);
             return y;
         }
+        /// <summary>Not in the reference: result mode of this handle (include/qpskcuda.h QPSK_FIR_*).  Fast = fp32 FMA, kernel picked
+        /// by the library (within 1e-5 of the reference); Exact = the reference's summation order, bit for bit; Fma / Split pin
+        /// one of the two FMA kernels.</summary>
+        public enum Mode { Fast = 0, Exact = 1, Fma = 2, Split = 3 }
+        public void SetMode(Mode mode)
+        {
+            QpskCuda.Check(QpskCuda.qpsk_fir_set_mode(_h, (int)mode), nameof(mode));
+            GC.KeepAlive(this);
+        }
         public void Dispose() => _o.Dispose();
     }
 
