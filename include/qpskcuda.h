@@ -120,7 +120,7 @@ QPSK_API int qpsk_fir_fft_filter_dev(qpsk_fir* f, const float* d_in, float* d_ou
  * change of D — counted ACROSS calls, so any chunking gives the same decimated stream: y_dec[m] = y[m*D].  Only the kept outputs are computed: 4N/D flop (real taps) and
  * 8 + 8/D bytes per input sample.  Shares the delay line with qpsk_fir_filter (the calls may be mixed).  Each channel
  * gets ceil((n - skip)/D) outputs; *n_out_floats = floats written per channel.  out_cap too small -> QPSK_ERR_CAPACITY
- * with no state consumed.  D = 2, 4, 8, 16 with real taps in QPSK_FIR_FAST mode run fir_decim_kernel; every other case
+ * with no state consumed.  D = 2, 4, 8, 16 with real taps in a FAST mode run fir_dec2_kernel (D = 2, 16-byte aligned rows) / fir_decim_kernel; every other case
  * (QPSK_FIR_EXACT: bit-identical to the subsampled exact filter) filters at full rate and keeps every D-th sample. */
 QPSK_API int qpsk_fir_decimate(qpsk_fir* f, const float* iq_in, int64_t n_floats, int decim, float* iq_out,
                                int64_t out_cap_floats, int64_t* n_out_floats);

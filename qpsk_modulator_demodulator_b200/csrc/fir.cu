@@ -97,6 +97,7 @@ struct FirArgs {
   int E_load;       // samples staged per tile (even)
   int stage_elems;  // float2 slots per stage (even)
   int stages;
+  long long n_out;  // fir_dec2_kernel: decimated outputs per channel
 };
 struct TapsReal {
   float g[kMaxG];
@@ -588,6 +589,172 @@ __global__ void __launch_bounds__(NT + 32, 2)
     int wvalid = valid - wbase;
     wvalid = wvalid < 0 ? 0 : (wvalid > WS ? WS : wvalid);
     float2* yg = a.y + (long long)ch * a.ldy + n0 + (long long)wbase;
+    if ((wvalid & 1) == 0) {
+      if (lane == 0) {
+        if (wvalid > 0) bulk_s2g(yg, ys, (uint32_t)wvalid * 8u);
+        bulk_commit();
+      }
+    } else {
+      for (int i = lane; i < wvalid; i += 32) yg[i] = ys[i];
+      if (lane == 0) bulk_commit();
+    }
+    if (++stage == a.stages) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  if (lane == 0) bulk_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fir_dec2_kernel: decimate-by-2 matched filter on the TMA pipeline (row N1, D = 2)
+// ---------------------------------------------------------------------------------------------
+// The even outputs of the split above need neither C nor S: y[b+2m] = (H0*X0)[m] + (H1*X1)[m] is the polyphase decimator
+// itself, G/2 multiply-adds per input sample = the algorithmic count.  With D = 2 the thread stride on a DENSE tile is
+// 8R bytes, an odd multiple of 16 for R = 10 / 14 — so, unlike D >= 4 (fir_decim_kernel's padded layout, filled through
+// registers), the tile can arrive by TMA: producer warp, full/empty mbarrier ring and per-warp bulk store exactly as in
+// fir_tma_kernel.  A kept-output phase of 1 (dec_skip) is a leading zero tap (host side), so the tile grid stays on even
+// sample indices.  Windows: two circular windows of P + 1 slots (P = R/2 outputs per thread), P + 1 sub-taps per unrolled
+// block; one LDS.128 (X0 and X1 of one position) per sub-tap feeds 2P FFMA2.
+template <int P, int NJ>
+__device__ __forceinline__ void dec2_block(const float4* __restrict__ xn, const TapsReal& taps, int j0, float2 (&wa)[P + 1],
+                                           float2 (&wb)[P + 1], float2 (&A)[P], float2 (&B)[P]) {
+  constexpr int W = P + 1;
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const float4 v = xn[jj];                       // (X0, X1)[j + P]: first used by the next sub-tap
+    const float t0 = taps.g[2 * (j0 + jj)], t1 = taps.g[2 * (j0 + jj) + 1];
+    const float2 g0 = make_float2(t0, t0), g1 = make_float2(t1, t1);
+#pragma unroll
+    for (int m = 0; m < P; ++m) A[m] = ffma2(wa[(jj + m) % W], g0, A[m]);
+#pragma unroll
+    for (int m = 0; m < P; ++m) B[m] = ffma2(wb[(jj + m) % W], g1, B[m]);
+    wa[(jj + P) % W] = make_float2(v.x, v.y);      // slot of X0[j - 1]: dead
+    wb[(jj + P) % W] = make_float2(v.z, v.w);
+  }
+}
+
+template <int R, int NT>
+__global__ void __launch_bounds__(NT + 32, 2)
+    fir_dec2_kernel(const __grid_constant__ FirArgs a, const __grid_constant__ TapsReal taps) {
+  static_assert(R % 4 == 2, "R/2 odd: thread stride 8R bytes = an odd multiple of 16");
+  constexpr int P = R / 2;
+  constexpr int T = R * NT;       // input samples per tile
+  constexpr int TO = T / 2;       // outputs per tile
+  constexpr int W = P + 1;
+  constexpr int WSO = 32 * P;     // outputs per consumer warp and tile
+  constexpr int NW = NT / 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* xs_base = reinterpret_cast<float2*>(smem_raw);
+  float2* ys_base = xs_base + (size_t)a.stages * a.stage_elems;     // two buffers of WSO outputs per warp
+  uint64_t* full = reinterpret_cast<uint64_t*>(ys_base + 2 * TO);
+  uint64_t* empty = full + a.stages;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // ---------------- producer warp: the FMA kernel's staging ----------------
+    int stage = 0;
+    uint32_t parity = 0;
+    TileWalk w(a.tiles_per_ch);
+    for (int it = 0; w.tile < a.total_tiles; ++it, w.next()) {
+      if (it >= a.stages) mbar_wait(&empty[stage], parity ^ 1u);
+      const int ch = w.ch;
+      const long long n0 = (long long)w.k * T;
+      const long long s0 = n0 - a.HL;
+      float2* dst = xs_base + (size_t)stage * a.stage_elems;
+      const float2* xch = a.x + (long long)ch * a.ldx;
+      uint64_t* bar = &full[stage];
+      const int E = a.E_load;
+      uint32_t tx = 0;
+      int nA = 0;
+      if (s0 < 0) {
+        nA = (int)((-s0) < (long long)E ? (-s0) : (long long)E);
+        if (lane == 0) bulk_g2s(dst, a.hist_in + (long long)ch * a.HL + (a.HL + s0), (uint32_t)nA * 8u, bar);
+        tx += (uint32_t)nA * 8u;
+      }
+      const long long m0 = s0 + nA;
+      long long avail = a.L - m0;
+      if (avail < 0) avail = 0;
+      const int nB = (int)(avail < (long long)(E - nA) ? avail : (long long)(E - nA));
+      const int nB2 = nB & ~1;
+      if (nB2 > 0) {
+        if (lane == 0) bulk_g2s(dst + nA, xch + m0, (uint32_t)nB2 * 8u, bar);
+        tx += (uint32_t)nB2 * 8u;
+      }
+      if ((nB & 1) && lane == 0) dst[nA + nB2] = xch[m0 + nB2];
+      for (int i = nA + nB + lane; i < E; i += 32) dst[i] = make_float2(0.f, 0.f);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(bar, tx);
+      if (++stage == a.stages) {
+        stage = 0;
+        parity ^= 1u;
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps ----------------
+  const int base = tid * R;
+  float2* ys_warp = ys_base + (size_t)warp * (2 * WSO);
+  const int Gh = a.G >> 1;
+  int stage = 0;
+  uint32_t parity = 0;
+  TileWalk tw(a.tiles_per_ch);
+  for (int it = 0; tw.tile < a.total_tiles; ++it, tw.next()) {
+    mbar_wait(&full[stage], parity);
+    const float2* xs = xs_base + (size_t)stage * a.stage_elems;
+    const int ch = tw.ch;
+    const long long o0 = (long long)tw.k * TO;               // first output of the tile
+    const long long left = a.n_out - o0;
+    const int valid = (int)(left < (long long)TO ? left : (long long)TO);
+
+    float2 wa[W], wb[W], A[P], B[P];
+#pragma unroll
+    for (int m = 0; m < P; ++m) {
+      A[m] = make_float2(0.f, 0.f);
+      B[m] = make_float2(0.f, 0.f);
+    }
+    const float4* xv = reinterpret_cast<const float4*>(xs + base);
+#pragma unroll
+    for (int m = 0; m < P; ++m) {
+      const float4 v = xv[m];
+      wa[m] = make_float2(v.x, v.y);
+      wb[m] = make_float2(v.z, v.w);
+    }
+    int j0 = 0;
+    for (; j0 + W <= Gh; j0 += W) dec2_block<P, W>(xv + j0 + P, taps, j0, wa, wb, A, B);
+    switch (Gh - j0) {
+#define QPSK_TAILD(K) case K: dec2_block<P, (K < W ? K : 0)>(xv + j0 + P, taps, j0, wa, wb, A, B); break;
+      QPSK_TAILD(1) QPSK_TAILD(2) QPSK_TAILD(3) QPSK_TAILD(4) QPSK_TAILD(5) QPSK_TAILD(6) QPSK_TAILD(7)
+#undef QPSK_TAILD
+      default: break;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+
+    // ---- epilogue: y = A + B -> this warp's smem slice -> TMA bulk store ----
+    float2* ys = ys_warp + (size_t)(it & 1) * WSO;
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < P; ++m) ys[lane * P + m] = fir_add2(A[m], B[m]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    int wvalid = valid - warp * WSO;
+    wvalid = wvalid < 0 ? 0 : (wvalid > WSO ? WSO : wvalid);
+    float2* yg = a.y + (long long)ch * a.ldy + o0 + (long long)warp * WSO;
     if ((wvalid & 1) == 0) {
       if (lane == 0) {
         if (wvalid > 0) bulk_s2g(yg, ys, (uint32_t)wvalid * 8u);
@@ -1479,7 +1646,47 @@ int FirEngine::decimate_dev(const float2* x, int64_t L, int64_t ldx, int dec, fl
       return QPSK_OK;
     };
     int st = QPSK_ERR_UNSUPPORTED;
-    switch (dec) {
+    // D = 2 on the TMA pipeline (fir_dec2_kernel) when the pointers allow bulk copies; QPSK_FIR_DEC2_TMA=0 keeps the
+    // register-staged kernel (A/B runs)
+    static const bool dec2_tma = [] {
+      const char* e = getenv("QPSK_FIR_DEC2_TMA");
+      return !(e && e[0] == '0');
+    }();
+    if (dec == 2 && dec2_tma && aligned16(x) && aligned16(y) && !(channels > 1 && ((ldx & 1) || (ldy & 1)))) {
+      constexpr int R2 = 14, NT2 = 256, T2 = R2 * NT2, TO2 = T2 / 2;
+      const int Gs = (HL + 1 + (int)skip + 1) & ~1;
+      if (Gs <= kMaxG && HL <= T2) {
+        FirArgs fa;
+        fa.x = x; fa.y = y; fa.ldx = ldx; fa.ldy = ldy; fa.L = L;
+        fa.hist_in = hist[cur].p; fa.hist_out = nullptr;
+        fa.n_out = nout;
+        fa.tiles_per_ch = (int)((nout + TO2 - 1) / TO2);
+        fa.total_tiles = (long long)fa.tiles_per_ch * channels;
+        fa.HL = HL; fa.G = Gs; fa.advance = 0;
+        fa.E_load = T2 + Gs;
+        fa.stage_elems = fa.E_load + 2;
+        const size_t stage_bytes = (size_t)fa.stage_elems * 8;
+        const size_t out_bytes = (size_t)2 * TO2 * 8;
+        int stages = (int)((kSmemBudget - out_bytes - 128) / stage_bytes);
+        if (stages > 4) stages = 4;
+        if (stages >= 2) {
+          fa.stages = stages;
+          const size_t smem = (size_t)stages * stage_bytes + out_bytes + (size_t)stages * 16;
+          TapsReal ts;                                        // a kept-output phase of 1 = one leading zero tap
+          memset(&ts, 0, sizeof ts);
+          for (int i = 0; i <= HL; ++i) ts.g[i + (int)skip] = t.g[i];
+          long long grid = 2LL * device_sm_count();
+          if (grid > fa.total_tiles) grid = fa.total_tiles;
+          auto kern = fir_dec2_kernel<R2, NT2>;
+          QPSK_TRY(allow_max_dynamic_smem((const void*)kern));
+          kern<<<(int)grid, NT2 + 32, smem, s>>>(fa, ts);
+          QPSK_LAUNCH_CHECK();
+          last_kernel = "fir_dec2_kernel<R=14,NT=256,D=2>";
+          st = QPSK_OK;
+        }
+      }
+    }
+    if (st != QPSK_OK) switch (dec) {
       case 2: st = go(fir_decim_kernel<7, 256, 1, 2>, 256, 1, 0); last_kernel = "fir_decim_kernel<RO=7,NTO=256,NG=1,D=2>"; break;
       case 4: st = go(fir_decim_kernel<7, 128, 2, 4>, 128, 2, 2); last_kernel = "fir_decim_kernel<RO=7,NTO=128,NG=2,D=4>"; break;
       case 8: st = go(fir_decim_kernel<7, 64, 4, 8>, 64, 4, 2); last_kernel = "fir_decim_kernel<RO=7,NTO=64,NG=4,D=8>"; break;

@@ -33,7 +33,8 @@ def test_decimate_matches_subsampled_oracle(gpu, orc, span, sps, dec):
     f = gpu.ComplexFIRFilter(taps)
     got = f.Decimate(x, dec)
     assert _close(got, want)
-    assert f.last_kernel().startswith("fir_decim_kernel")
+    # D = 2 rides the TMA pipeline (fir_dec2_kernel); D = 4, 8, 16 the padded register-staged kernel
+    assert f.last_kernel().startswith("fir_dec2_kernel" if dec == 2 else "fir_decim_kernel"), f.last_kernel()
 
 
 def test_decimate_streaming_any_chunking(gpu, orc):
@@ -131,3 +132,34 @@ def test_decimate_dev_full_size_properties(gpu, orc):
         torch.cuda.synchronize()
         assert torch.equal(y2, y * 2.0)                         # scaling by 2 is exact in fp32
         del y, y2, x2
+
+
+@pytest.mark.parametrize("aligned", [False, True])
+def test_decimate_by_2_kernels_agree_across_an_odd_cut(gpu, orc, aligned):
+    """Bulk copies need 16-byte aligned rows: a device pointer that starts on an odd sample falls back to the register-staged
+    fir_decim_kernel<D=2>, an aligned one takes fir_dec2_kernel.  Either way two calls with an odd first length give the
+    decimated stream of one call (on the TMA kernel the kept-output phase of 1 is a leading zero tap)."""
+    import torch
+    taps = _taps(gpu, 16, 4)                                    # 65 taps
+    L, cut = 30001, 10001
+    x = orc.fill_uniform(9, 2, 0, 2 * (L + 2))
+    off = 2 if aligned else 1                                   # first sample of the stream inside the device buffer
+    want = _sub(orc.ComplexFIRFilter(taps).Filter(x[2 * off: 2 * (off + L)]), 2)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(2 * (L + 4), dtype=torch.float32, device="cuda")
+    f = gpu.ComplexFIRFilter(taps)
+    p = dx.data_ptr() + 8 * off
+    n1 = f.decimate_dev(p, 2 * cut, 2, dy.data_ptr(), 2 * (L + 4))
+    k1 = f.last_kernel()
+    # the second call's output row starts right after the first one's: aligned only if n1 is even, so give it its own buffer
+    dz = torch.zeros(2 * (L + 4), dtype=torch.float32, device="cuda")
+    n2 = f.decimate_dev(p + 8 * cut, 2 * (L - cut), 2, dz.data_ptr(), 2 * (L + 4))
+    k2 = f.last_kernel()
+    torch.cuda.synchronize()
+    assert k1.startswith("fir_dec2_kernel" if aligned else "fir_decim_kernel"), k1
+    # the second call starts on an odd sample of an aligned buffer (cut is odd): the pointer is misaligned exactly when the
+    # first one was aligned
+    assert k2.startswith("fir_decim_kernel" if aligned else "fir_dec2_kernel"), k2
+    got = np.concatenate([dy.cpu().numpy()[:n1], dz.cpu().numpy()[:n2]])          # the counts are in floats
+    assert n1 + n2 == want.size
+    assert _close(got, want)
