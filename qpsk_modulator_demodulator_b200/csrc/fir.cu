@@ -1120,13 +1120,14 @@ struct DecArgs {
   int HL, K, skip;             // K polyphase taps per phase; first kept output at input index `skip`
 };
 
-template <int RO, int NSTEP, int DEC>
+template <int RO, int NSTEP, int DEC, bool DENSE = false>
 __device__ __forceinline__ void dec_block(const float2* __restrict__ xk, const TapsReal& taps, int t0, float2 (&wA)[2 * RO],
                                           float2 (&wB)[2 * RO], float2 (&acc)[RO]) {
   // NSTEP (<= 2*RO) polyphase taps starting at k0 (t0 = k0*DEC + 2*pair); on entry slots 0..RO-1 of the circular windows
   // hold elements k0 .. k0+RO-1 of the two phases; xk = address of element k0 (first phase), pads not yet applied.
+  // DENSE: the tile as a bulk copy left it (no pads).
   constexpr int W = 2 * RO;
-  constexpr int PADS = (DEC == 2) ? 0 : 2;
+  constexpr int PADS = (DEC == 2 || DENSE) ? 0 : 2;
 #pragma unroll
   for (int kk = 0; kk < NSTEP; ++kk) {
     // element k0 + kk + RO: (kk + RO) / RO thread spans further on
@@ -1259,6 +1260,177 @@ __global__ void __launch_bounds__(NTO * NG, 4)
       yc[o] = sum;
     }
     __syncthreads();                             // tile and partial sums are dead: the next tile may overwrite them
+  }
+}
+
+// fir_decim_kernel's arithmetic on the TMA pipeline, D = 4, 8, 16: one producer warp stages the DENSE tile (+ halo) by bulk
+// copies into a full/empty mbarrier ring, so the loads of tile t+1 are in flight under the arithmetic of tile t (the
+// register-staged kernel alternates the two inside a CTA and leans on four resident CTAs).  Read in place, a dense tile costs
+// 2- / 4- / 8-way bank conflicts on every LDS.128 for D = 4 / 8 / 16 (thread span 56*D bytes = 14 / 28 / 56 sixteen-byte chunks;
+// measured: 0.56 / 0.87 / 1.64 ms against 0.68 / 0.65 / 0.62 for the padded register-staged kernel) — so the compute threads
+// first move the tile into the PADDED layout of fir_decim_kernel (one LDS.128 + STS.128 per sample pair, both conflict-free),
+// hand the ring slot back at once, and run the same phase-pair loops on the padded copy.  An odd kept-output phase is a
+// leading zero tap (host side): the ring stays on even sample indices.
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int RO, int NTO, int NG, int DEC, bool REPACK>
+__global__ void __launch_bounds__(NTO * NG + 32, 2)
+    fir_decim_tma_kernel(const __grid_constant__ FirArgs a, const __grid_constant__ TapsReal taps) {
+  static_assert(DEC % 2 == 0 && (DEC / 2) % NG == 0, "phase pairs split evenly over the groups");
+  constexpr int NT = NTO * NG;
+  constexpr int NW = NT / 32;
+  constexpr int SPAN = RO * DEC;
+  constexpr int T_OUT = RO * NTO;
+  constexpr int T_IN = T_OUT * DEC;
+  constexpr int W = 2 * RO;
+  constexpr int PP = DEC / 2 / NG;
+  constexpr int PADS = 2;
+  constexpr int PITCH = SPAN + PADS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* xs_base = reinterpret_cast<float2*>(smem_raw);
+  float2* ys = xs_base + (size_t)a.stages * a.stage_elems;            // [NG][T_OUT] partial sums
+  float2* xpad = ys + NG * T_OUT;                                     // REPACK: the tile in the padded layout
+  const int pad_elems = REPACK ? ((a.E_load + PADS * (a.E_load / SPAN + 1) + 1) & ~1) : 0;
+  uint64_t* full = reinterpret_cast<uint64_t*>(xpad + pad_elems);
+  uint64_t* empty = full + a.stages;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int K = a.G;                                                  // polyphase taps per phase
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    int stage = 0;
+    uint32_t parity = 0;
+    TileWalk w(a.tiles_per_ch);
+    for (int it = 0; w.tile < a.total_tiles; ++it, w.next()) {
+      if (it >= a.stages) mbar_wait(&empty[stage], parity ^ 1u);
+      const int ch = w.ch;
+      const long long s0 = (long long)a.advance + (long long)w.k * T_IN - a.HL;   // advance = the even part of the kept-output phase
+      float2* dst = xs_base + (size_t)stage * a.stage_elems;
+      const float2* xch = a.x + (long long)ch * a.ldx;
+      uint64_t* bar = &full[stage];
+      const int E = a.E_load;
+      uint32_t tx = 0;
+      int nA = 0;
+      if (s0 < 0) {
+        nA = (int)((-s0) < (long long)E ? (-s0) : (long long)E);
+        if (lane == 0) bulk_g2s(dst, a.hist_in + (long long)ch * a.HL + (a.HL + s0), (uint32_t)nA * 8u, bar);
+        tx += (uint32_t)nA * 8u;
+      }
+      const long long m0 = s0 + nA;
+      long long avail = a.L - m0;
+      if (avail < 0) avail = 0;
+      const int nB = (int)(avail < (long long)(E - nA) ? avail : (long long)(E - nA));
+      const int nB2 = nB & ~1;
+      if (nB2 > 0) {
+        if (lane == 0) bulk_g2s(dst + nA, xch + m0, (uint32_t)nB2 * 8u, bar);
+        tx += (uint32_t)nB2 * 8u;
+      }
+      if ((nB & 1) && lane == 0) dst[nA + nB2] = xch[m0 + nB2];
+      for (int i = nA + nB + lane; i < E; i += 32) dst[i] = make_float2(0.f, 0.f);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(bar, tx);
+      if (++stage == a.stages) {
+        stage = 0;
+        parity ^= 1u;
+      }
+    }
+    return;
+  }
+
+  const int to = tid % NTO, grp = tid / NTO;
+  int stage = 0;
+  uint32_t parity = 0;
+  TileWalk tw(a.tiles_per_ch);
+  for (int it = 0; tw.tile < a.total_tiles; ++it, tw.next()) {
+    mbar_wait(&full[stage], parity);
+    const float2* xs = xs_base + (size_t)stage * a.stage_elems;
+    const int ch = tw.ch;
+    const long long m0 = (long long)tw.k * T_OUT;
+    // dense ring slot -> padded layout (a pair never straddles a pad: spans are an even number of samples)
+    if constexpr (REPACK) {
+      const float4* src4 = reinterpret_cast<const float4*>(xs);
+      const int np = a.E_load >> 1;
+      for (int p0 = tid; p0 < np; p0 += 4 * NT) {
+        float4 v4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int p = p0 + u * NT;
+          if (p < np) v4[u] = src4[p];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int p = p0 + u * NT;
+          if (p < np) *reinterpret_cast<float4*>(xpad + 2 * p + PADS * ((2 * p) / SPAN)) = v4[u];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);                      // the ring slot goes back before the arithmetic starts
+      named_bar_sync(1, NT);
+    }
+    constexpr int PD = REPACK ? PADS : 0;                             // pad slots per span in the layout the loops read
+    float2 acc[RO];
+#pragma unroll
+    for (int r = 0; r < RO; ++r) acc[r] = make_float2(0.f, 0.f);
+    const float2* xb = REPACK ? xpad + to * PITCH : xs + to * SPAN;
+    for (int pp = 0; pp < PP; ++pp) {
+      const int pair = grp * PP + pp;
+      float2 wA[W], wB[W];
+      const float2* xp = xb + 2 * pair;
+#pragma unroll
+      for (int j = 0; j < RO; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(xp + j * DEC);
+        wA[j] = make_float2(v.x, v.y);
+        wB[j] = make_float2(v.z, v.w);
+      }
+      int k0 = 0;
+      for (; k0 + W <= K; k0 += W)
+        dec_block<RO, W, DEC, !REPACK>(xp + k0 * DEC + PD * (k0 / RO), taps, k0 * DEC + 2 * pair, wA, wB, acc);
+      const float2* xk = xp + k0 * DEC + PD * (k0 / RO);
+      const int t0 = k0 * DEC + 2 * pair;
+      switch (K - k0) {
+#define QPSK_DTAIL(S) case S: dec_block<RO, (S < W ? S : 0), DEC, !REPACK>(xk, taps, t0, wA, wB, acc); break;
+        QPSK_DTAIL(1) QPSK_DTAIL(2) QPSK_DTAIL(3) QPSK_DTAIL(4) QPSK_DTAIL(5) QPSK_DTAIL(6) QPSK_DTAIL(7) QPSK_DTAIL(8)
+        QPSK_DTAIL(9) QPSK_DTAIL(10) QPSK_DTAIL(11) QPSK_DTAIL(12) QPSK_DTAIL(13)
+#undef QPSK_DTAIL
+        default: break;
+      }
+    }
+    if constexpr (!REPACK) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);                      // this warp is done with the ring slot
+    }
+    float2* yp = ys + grp * T_OUT + to * RO;
+#pragma unroll
+    for (int r = 0; r < RO; ++r) yp[r] = acc[r];
+    named_bar_sync(1, NT);
+    float2* yc = a.y + (long long)ch * a.ldy + m0;
+    const long long left = a.n_out - m0;
+    for (int o = tid; o < T_OUT && o < left; o += NT) {
+      float2 sum = ys[o];
+#pragma unroll
+      for (int g2 = 1; g2 < NG; ++g2) {
+        const float2 p = ys[g2 * T_OUT + o];
+        sum.x += p.x;
+        sum.y += p.y;
+      }
+      yc[o] = sum;
+    }
+    named_bar_sync(1, NT);                                            // the partial sums and the padded tile are dead
+    if (++stage == a.stages) {
+      stage = 0;
+      parity ^= 1u;
+    }
   }
 }
 
@@ -1685,6 +1857,51 @@ int FirEngine::decimate_dev(const float2* x, int64_t L, int64_t ldx, int dec, fl
           st = QPSK_OK;
         }
       }
+    }
+    // D = 4, 8, 16 on the same pipeline (fir_decim_tma_kernel, dense tiles)
+    if (dec > 2 && dec2_tma && aligned16(x) && !(channels > 1 && (ldx & 1))) {
+      const int sk = (int)(skip & 1);
+      const int Ks = (HL + 1 + sk + dec - 1) / dec;
+      auto go_tma = [&](auto kern, int NTO, int NG, bool repack, const char* name) -> int {
+        const int T_OUT = 7 * NTO;
+        if ((long long)Ks * dec > kMaxG) return QPSK_ERR_UNSUPPORTED;
+        FirArgs fa;
+        fa.x = x; fa.y = y; fa.ldx = ldx; fa.ldy = ldy; fa.L = L;
+        fa.hist_in = hist[cur].p; fa.hist_out = nullptr;
+        fa.n_out = nout;
+        fa.tiles_per_ch = (int)((nout + T_OUT - 1) / T_OUT);
+        fa.total_tiles = (long long)fa.tiles_per_ch * channels;
+        fa.HL = HL; fa.G = Ks; fa.advance = (int)(skip & ~1LL);
+        fa.E_load = (T_OUT + Ks) * dec;
+        fa.stage_elems = fa.E_load + 2;
+        const size_t stage_bytes = (size_t)fa.stage_elems * 8;
+        const int span = 7 * dec;
+        const size_t pad_elems = repack ? (size_t)((fa.E_load + 2 * (fa.E_load / span + 1) + 1) & ~1) : 0;
+        const size_t fixed = (size_t)NG * T_OUT * 8 + pad_elems * 8;
+        if (fixed + 128 + 2 * stage_bytes > (size_t)kSmemBudget) return QPSK_ERR_UNSUPPORTED;
+        int stages = (int)(((size_t)kSmemBudget - fixed - 128) / stage_bytes);
+        if (stages > 4) stages = 4;
+        fa.stages = stages;
+        const size_t smem = (size_t)stages * stage_bytes + fixed + (size_t)stages * 16;
+        TapsReal ts;
+        memset(&ts, 0, sizeof ts);
+        for (int i = 0; i <= HL; ++i) ts.g[i + sk] = t.g[i];
+        long long grid = 2LL * device_sm_count();
+        if (grid > fa.total_tiles) grid = fa.total_tiles;
+        QPSK_TRY(allow_max_dynamic_smem((const void*)kern));
+        kern<<<(int)grid, NTO * NG + 32, smem, s>>>(fa, ts);
+        QPSK_LAUNCH_CHECK();
+        last_kernel = name;
+        return QPSK_OK;
+      };
+      switch (dec) {
+        // D = 4 reads the dense tile in place (2-way conflicts cost less than the repack and its barrier: 0.558 against
+        // 0.638 ms at 65 taps); D = 8 / 16 repack (0.614 / 0.590 against 0.874 / 1.636 in place)
+        case 4: st = go_tma(fir_decim_tma_kernel<7, 128, 2, 4, false>, 128, 2, false, "fir_decim_tma_kernel<RO=7,NTO=128,NG=2,D=4,dense>"); break;
+        case 8: st = go_tma(fir_decim_tma_kernel<7, 64, 4, 8, true>, 64, 4, true, "fir_decim_tma_kernel<RO=7,NTO=64,NG=4,D=8,repack>"); break;
+        case 16: st = go_tma(fir_decim_tma_kernel<7, 32, 8, 16, true>, 32, 8, true, "fir_decim_tma_kernel<RO=7,NTO=32,NG=8,D=16,repack>"); break;
+      }
+      if (st != QPSK_OK && st != QPSK_ERR_UNSUPPORTED) return st;
     }
     if (st != QPSK_OK) switch (dec) {
       case 2: st = go(fir_decim_kernel<7, 256, 1, 2>, 256, 1, 0); last_kernel = "fir_decim_kernel<RO=7,NTO=256,NG=1,D=2>"; break;

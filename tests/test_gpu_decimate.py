@@ -34,7 +34,7 @@ def test_decimate_matches_subsampled_oracle(gpu, orc, span, sps, dec):
     got = f.Decimate(x, dec)
     assert _close(got, want)
     # D = 2 rides the TMA pipeline (fir_dec2_kernel); D = 4, 8, 16 the padded register-staged kernel
-    assert f.last_kernel().startswith("fir_dec2_kernel" if dec == 2 else "fir_decim_kernel"), f.last_kernel()
+    assert f.last_kernel().startswith("fir_dec2_kernel" if dec == 2 else "fir_decim_tma_kernel"), f.last_kernel()
 
 
 def test_decimate_streaming_any_chunking(gpu, orc):
