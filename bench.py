@@ -427,7 +427,10 @@ def main():
             decimate.append({"taps": nt, "decim": dec, "kernel": f.last_kernel(), "ms": tms, "msamples_s_in": n / (tms * 1e-3) / 1e6,
                              "bound": bound, "hbm_gbs": gbs, "fma_tflops": tf,
                              "frac": gbs / hbm_peak if bound == "hbm" else tf / fma_peak,
-                             "algorithmic": "8 + 8/D B and 4*taps/D flop per input sample"})
+                             "algorithmic": "8 + 8/D B and 4*taps/D flop per input sample",
+                             "peak_note": "HBM peak = the driver-measured COPY bandwidth (1 B read per B written); these launches "
+                                          "read D B per B written, and read-heavy mixes run above the copy figure on this part "
+                                          "(a pure fill reaches 7.5 TB/s), so an HBM-bound frac can touch 1.0"})
             del f
 
     # ---- e2e: host-pointer C ABI with pinned buffers -------------------------------------------

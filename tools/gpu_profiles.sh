@@ -15,7 +15,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fir
 echo "fir rc=$?"
 # 3. decimating FIR: one launch per (taps, D) of the bench's `decimate` leg
 python tools/decim_probe.py > $OUT/${TAG}_plain_decim.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:fir_decim -c 6 -f -o $OUT/${TAG}_prof_decim python tools/decim_probe.py > $OUT/${TAG}_ncu_decim.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:fir_dec -c 6 -f -o $OUT/${TAG}_prof_decim python tools/decim_probe.py > $OUT/${TAG}_ncu_decim.log 2>&1
 echo "decim rc=$?"
 # 4. chain at 2048 channels, every stage one launch (no time-chunk pipeline): FLL (duo), fused MF + symbol stage, TSC strip, BER
 QPSK_DEMOD_CHUNKS=1 python tools/chain_only.py fll 2 > $OUT/${TAG}_plain_chain_fll.log 2>&1

@@ -11,7 +11,7 @@ def rows(name):
     return [dict(zip(r[0], x)) for x in r[2:]]
 
 
-def entry(row, split_at):
+def entry(row, split_at="("):
     rd, wr = float(row["dram__bytes_read.sum"]) * 1e9, float(row["dram__bytes_write.sum"]) * 1e9
     return {"kernel": row["Kernel Name"].split(split_at)[0].strip(), "block": row["Block Size"],
             "registers": int(row["launch__registers_per_thread"]),
@@ -26,11 +26,11 @@ out = {"source": f"profiles/{tag}_ncu_full_fir_summary.csv (ncu --set full --clo
                  "--no-decimate`: the four launches of the first timed step, 2^28 samples each)",
        "log2_samples": 28, "per_taps": {}}
 for taps, row in zip((33, 65, 129, 257), rows(f"{tag}_ncu_full_fir_summary.csv")):
-    out["per_taps"][str(taps)] = entry(row, "(FirArgs")
+    out["per_taps"][str(taps)] = entry(row)
 out["kernel"] = " / ".join(sorted({v["kernel"] for v in out["per_taps"].values()}))
 dec = {}
 for (t, D), row in zip(((33, 2), (65, 2), (129, 2), (65, 4), (129, 8), (257, 16)), rows(f"{tag}_ncu_full_decim_summary.csv")):
-    e = entry(row, "(DecArgs")
+    e = entry(row)
     e["ctas_per_sm"] = int(float(row["launch__occupancy_limit_registers"]))
     e["algorithmic"] = 2 ** 28 * (8 + 8 / D)
     dec[f"{t}/{D}"] = e
