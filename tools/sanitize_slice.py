@@ -2,7 +2,8 @@
 (memcheck / racecheck / synccheck / initcheck) — SURVEY §5's counterpart of the reference's (absent) race detection:
 
   FIR      fir_tma_kernel (mbarrier ring, TMA bulk loads / per-warp bulk stores) over several tile seams, streaming in
-           two chunks (delay-line ping-pong), real and complex taps, stateless alignment; fir_exact_real_kernel
+           two chunks (delay-line ping-pong), real and complex taps, stateless alignment; fir_exact_real_kernel;
+           fir_split2_kernel; fir_dec2_kernel / fir_decim_tma_kernel (D = 2, 4, 8, 16)
   FLL      fll_duo_kernel (chain warp / side warp hand-off through shared memory + mbarriers), 40 and 10 taps,
            fll_lane_kernel forced, generic group kernel (13 taps)
   symsync  symsync_decode_kernel (cp.async double buffer, two-warp symbol queue), with TSC strip and framer
@@ -45,6 +46,17 @@ for span, sps in ((16, 2), (16, 4)) if small else ((16, 2), (16, 4), (16, 16)):
     ge = np.concatenate([fe.Filter(x[:cut]), fe.Filter(x[cut:])])
     assert np.array_equal(ge.view(np.uint32), want.view(np.uint32)), ("fir exact", span, sps)
     assert close(Q.ComplexFIRFilter(taps).fftFilter(x), O.ComplexFIRFilter(taps).fftFilter(x)), ("fftFilter", span, sps)
+# the 2-parallel split kernel (S planes per warp, single-buffered output slice) and the decimators on the TMA ring
+t129 = Q.real_taps_to_iq(Q.RRCFilter.generateCoefficents(16, 0.35, 8000, 1000))
+fs_ = Q.ComplexFIRFilter(t129)
+fs_.set_mode(Q.FIR_SPLIT)
+cut = 2 * (L // 3 + 1)
+gs = np.concatenate([fs_.Filter(x[:cut]), fs_.Filter(x[cut:])])
+assert "split2" in fs_.last_kernel() and close(gs, O.ComplexFIRFilter(t129).Filter(x)), "fir split"
+for dec in (2, 4, 8, 16):
+    fd = Q.ComplexFIRFilter(t129)
+    gd_ = np.concatenate([fd.Decimate(x[:cut], dec), fd.Decimate(x[cut:], dec)])
+    assert close(gd_, O.decimate(O.ComplexFIRFilter(t129).Filter(x), dec)), ("decimate", dec, fd.last_kernel())
 rng = np.random.default_rng(5)
 ct = rng.standard_normal(2 * 40).astype(np.float32) * 0.1
 assert close(Q.ComplexFIRFilter(ct).Filter(x), O.ComplexFIRFilter(ct).Filter(x)), "fir complex taps"
