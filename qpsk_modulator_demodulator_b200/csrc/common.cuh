@@ -48,6 +48,13 @@ int ensure_device(int dev = -1);  // cudaSetDevice(dev, or current_device()) + a
 int allow_max_dynamic_smem(const void* kernel);
 int device_sm_count();         // of the device the calling thread has current (call after ensure_device)
 
+// Host side of the pageable-memory path.  cudaMemcpyAsync on memory the driver has not page-locked is a blocking, staged copy on
+// the calling thread: the H2D / kernel / D2H pipelines of the host entry points degenerate into a sequence (FIR end to end:
+// 0.85 Gsample/s against 5.6 on page-locked buffers).  Such calls go through page-locked staging slots instead, filled and
+// drained by a small pool of host threads (QPSK_HOST_COPY_THREADS, default 6) while the DMA engines work on the other slots.
+bool host_ptr_is_pageable(const void* p);            // true when the driver does not know the address as page-locked memory
+void host_parallel_copy(void* dst, const void* src, size_t bytes);   // blocking; split over the pool and the caller
+
 // RAII device buffer
 template <typename T>
 struct DevBuf {

@@ -2,6 +2,9 @@
 #include <math.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <thread>
+#include <vector>
 #include <mutex>
 #include <set>
 #include <utility>
@@ -180,6 +183,100 @@ bool blank_or_null(const char* s) {
   for (; *s; ++s)
     if (!(*s == ' ' || (*s >= '\t' && *s <= '\r'))) return false;
   return true;
+}
+
+
+// ---- host copy pool -------------------------------------------------------------------------------------------------
+bool host_ptr_is_pageable(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();                                  // older runtimes report unknown host memory as an error
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+namespace {
+class HostCopyPool {
+ public:
+  static HostCopyPool& get() {
+    static HostCopyPool pool;
+    return pool;
+  }
+  void copy(char* dst, const char* src, size_t bytes) {
+    const size_t kMinPart = 256 * 1024;                  // below that a second thread costs more than it copies
+    std::lock_guard<std::mutex> call(call_m_);           // one parallel copy at a time: the pool is per process
+    int parts = (int)workers_.size() + 1;
+    if ((size_t)parts * kMinPart > bytes) parts = (int)(bytes / kMinPart);
+    if (parts <= 1) {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    const size_t step = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      jobs_.clear();
+      for (int i = 1; i < parts; ++i) {
+        const size_t off = (size_t)i * step;
+        if (off >= bytes) break;
+        jobs_.push_back({dst + off, src + off, bytes - off < step ? bytes - off : step});
+      }
+      next_ = 0;
+      pending_ = (int)jobs_.size();
+    }
+    cv_work_.notify_all();
+    memcpy(dst, src, step < bytes ? step : bytes);
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+  }
+
+ private:
+  struct Job {
+    char* d;
+    const char* s;
+    size_t n;
+  };
+  HostCopyPool() {
+    int n = 6;
+    if (const char* e = getenv("QPSK_HOST_COPY_THREADS")) n = atoi(e);
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && n > hw) n = hw;
+    if (n < 1) n = 1;
+    for (int i = 1; i < n; ++i) workers_.emplace_back([this] { run(); });
+  }
+  ~HostCopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_work_.notify_all();
+    for (std::thread& t : workers_) t.join();
+  }
+  void run() {
+    std::unique_lock<std::mutex> lk(m_);
+    for (;;) {
+      cv_work_.wait(lk, [&] { return stop_ || next_ < jobs_.size(); });
+      if (stop_) return;
+      const Job j = jobs_[next_++];
+      lk.unlock();
+      memcpy(j.d, j.s, j.n);
+      lk.lock();
+      if (--pending_ == 0) cv_done_.notify_all();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_, call_m_;
+  std::condition_variable cv_work_, cv_done_;
+  std::vector<Job> jobs_;
+  size_t next_ = 0;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+}  // namespace
+
+void host_parallel_copy(void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return;
+  HostCopyPool::get().copy((char*)dst, (const char*)src, bytes);
 }
 
 }  // namespace qpsk

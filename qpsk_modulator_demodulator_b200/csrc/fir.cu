@@ -1959,11 +1959,32 @@ struct qpsk_fir {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_h2d[kSlots] = {}, ev_k[kSlots] = {}, ev_d2h[kSlots] = {};
   DevBuf<float2> d_in[kSlots], d_out[kSlots];
+  // page-locked staging slots of the pageable-memory path (allocated on first use, one chunk each)
+  float2* h_in[kSlots] = {};
+  float2* h_out[kSlots] = {};
+  size_t h_elems = 0;
+  int staging(size_t elems) {
+    if (elems <= h_elems) return QPSK_OK;
+    for (int i = 0; i < kSlots; ++i) {
+      if (h_in[i]) cudaFreeHost(h_in[i]);
+      if (h_out[i]) cudaFreeHost(h_out[i]);
+      h_in[i] = h_out[i] = nullptr;
+    }
+    h_elems = 0;
+    for (int i = 0; i < kSlots; ++i) {
+      QPSK_CUDA_TRY(cudaHostAlloc((void**)&h_in[i], elems * sizeof(float2), cudaHostAllocPortable));
+      QPSK_CUDA_TRY(cudaHostAlloc((void**)&h_out[i], elems * sizeof(float2), cudaHostAllocPortable));
+    }
+    h_elems = elems;
+    return QPSK_OK;
+  }
   ~qpsk_fir() {
     for (int i = 0; i < kSlots; ++i) {
       if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
       if (ev_k[i]) cudaEventDestroy(ev_k[i]);
       if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+      if (h_in[i]) cudaFreeHost(h_in[i]);
+      if (h_out[i]) cudaFreeHost(h_out[i]);
     }
     if (s_in) cudaStreamDestroy(s_in);
     if (s_out) cudaStreamDestroy(s_out);
@@ -2011,13 +2032,31 @@ int fir_host_stream(qpsk_fir* f, const float* in, float* out, int64_t L, bool st
     QPSK_TRY(f->d_out[b].ensure((size_t)(kChunk + look)));
   }
   const int64_t chunks = (L + kChunk - 1) / kChunk;
+  // pageable caller memory: an asynchronous copy on it blocks the calling thread and the three stages run one after the
+  // other; the chunks go through page-locked staging slots instead, filled / drained by the host copy pool (common.cuh)
+  const bool bounce_in = host_ptr_is_pageable(in), bounce_out = host_ptr_is_pageable(out);
+  if (bounce_in || bounce_out) QPSK_TRY(f->staging((size_t)(kChunk + look)));
+  auto drain = [&](int64_t c) -> int {                    // chunk c of the output: staging slot -> caller memory
+    const int b = (int)(c % kSlots);
+    const int64_t off = c * kChunk;
+    const int64_t len = (L - off < kChunk) ? (L - off) : kChunk;
+    QPSK_CUDA_TRY(cudaEventSynchronize(f->ev_d2h[b]));
+    host_parallel_copy(out + 2 * off, f->h_out[b], (size_t)len * 8);
+    return QPSK_OK;
+  };
   for (int64_t c = 0; c < chunks; ++c) {
     const int b = (int)(c % kSlots);
     const int64_t off = c * kChunk;
     const int64_t len = (L - off < kChunk) ? (L - off) : kChunk;
     const int64_t in_len = (L - off < len + look) ? (L - off) : (len + look);
+    const float* src = in + 2 * off;
+    if (bounce_in) {
+      if (c >= kSlots) QPSK_CUDA_TRY(cudaEventSynchronize(f->ev_h2d[b]));        // the slot's previous DMA has read it
+      host_parallel_copy(f->h_in[b], src, (size_t)in_len * 8);
+      src = reinterpret_cast<const float*>(f->h_in[b]);
+    }
     if (c >= kSlots) QPSK_CUDA_TRY(cudaStreamWaitEvent(f->s_in, f->ev_k[b], 0));  // slot's previous kernel done
-    QPSK_CUDA_TRY(cudaMemcpyAsync(f->d_in[b].p, in + 2 * off, (size_t)in_len * 8, cudaMemcpyHostToDevice, f->s_in));
+    QPSK_CUDA_TRY(cudaMemcpyAsync(f->d_in[b].p, src, (size_t)in_len * 8, cudaMemcpyHostToDevice, f->s_in));
     QPSK_CUDA_TRY(cudaEventRecord(f->ev_h2d[b], f->s_in));
     QPSK_CUDA_TRY(cudaStreamWaitEvent(e.stream, f->ev_h2d[b], 0));
     if (c >= kSlots) QPSK_CUDA_TRY(cudaStreamWaitEvent(e.stream, f->ev_d2h[b], 0));  // slot's previous D2H done
@@ -2025,9 +2064,13 @@ int fir_host_stream(qpsk_fir* f, const float* in, float* out, int64_t L, bool st
                        : e.filter_dev(f->d_in[b].p, f->d_out[b].p, len, len, len, e.stream));
     QPSK_CUDA_TRY(cudaEventRecord(f->ev_k[b], e.stream));
     QPSK_CUDA_TRY(cudaStreamWaitEvent(f->s_out, f->ev_k[b], 0));
-    QPSK_CUDA_TRY(cudaMemcpyAsync(out + 2 * off, f->d_out[b].p, (size_t)len * 8, cudaMemcpyDeviceToHost, f->s_out));
+    float* dst = bounce_out ? reinterpret_cast<float*>(f->h_out[b]) : out + 2 * off;
+    QPSK_CUDA_TRY(cudaMemcpyAsync(dst, f->d_out[b].p, (size_t)len * 8, cudaMemcpyDeviceToHost, f->s_out));
     QPSK_CUDA_TRY(cudaEventRecord(f->ev_d2h[b], f->s_out));
+    // the slot of chunk c is written again by chunk c + kSlots: chunk c - 1 leaves its slot now, two iterations early
+    if (bounce_out && c >= 1) QPSK_TRY(drain(c - 1));
   }
+  if (bounce_out) QPSK_TRY(drain(chunks - 1));
   QPSK_CUDA_TRY(cudaStreamSynchronize(f->s_out));
   QPSK_CUDA_TRY(cudaStreamSynchronize(e.stream));
   return QPSK_OK;
