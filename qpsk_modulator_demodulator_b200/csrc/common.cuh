@@ -54,6 +54,8 @@ int device_sm_count();         // of the device the calling thread has current (
 // drained by a small pool of host threads (QPSK_HOST_COPY_THREADS, default 6) while the DMA engines work on the other slots.
 bool host_ptr_is_pageable(const void* p);            // true when the driver does not know the address as page-locked memory
 void host_parallel_copy(void* dst, const void* src, size_t bytes);   // blocking; split over the pool and the caller
+// `rows` pieces of `width` bytes, `spitch` / `dpitch` bytes apart (a time chunk of a [channels][samples] block)
+void host_parallel_copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows);
 
 // RAII device buffer
 template <typename T>

@@ -203,8 +203,8 @@ class HostCopyPool {
     static HostCopyPool pool;
     return pool;
   }
+  static constexpr size_t kMinPart = 256 * 1024;         // below that a second thread costs more than it copies
   void copy(char* dst, const char* src, size_t bytes) {
-    const size_t kMinPart = 256 * 1024;                  // below that a second thread costs more than it copies
     std::lock_guard<std::mutex> call(call_m_);           // one parallel copy at a time: the pool is per process
     int parts = (int)workers_.size() + 1;
     if ((size_t)parts * kMinPart > bytes) parts = (int)(bytes / kMinPart);
@@ -213,29 +213,49 @@ class HostCopyPool {
       return;
     }
     const size_t step = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
-    {
-      std::lock_guard<std::mutex> lk(m_);
-      jobs_.clear();
-      for (int i = 1; i < parts; ++i) {
-        const size_t off = (size_t)i * step;
-        if (off >= bytes) break;
-        jobs_.push_back({dst + off, src + off, bytes - off < step ? bytes - off : step});
-      }
-      next_ = 0;
-      pending_ = (int)jobs_.size();
+    std::vector<Job> js;
+    for (int i = 0; i < parts; ++i) {
+      const size_t off = (size_t)i * step;
+      if (off >= bytes) break;
+      js.push_back({dst + off, src + off, bytes - off < step ? bytes - off : step, 1, 0, 0});
     }
-    cv_work_.notify_all();
-    memcpy(dst, src, step < bytes ? step : bytes);
-    std::unique_lock<std::mutex> lk(m_);
-    cv_done_.wait(lk, [&] { return pending_ == 0; });
+    dispatch(js);
+  }
+  void copy_rows(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t rows) {
+    std::lock_guard<std::mutex> call(call_m_);
+    int parts = (int)workers_.size() + 1;
+    if ((size_t)parts * kMinPart > width * rows) parts = (int)(width * rows / kMinPart);
+    if (parts < 1) parts = 1;
+    const size_t per = (rows + parts - 1) / parts;
+    std::vector<Job> js;
+    for (size_t r0 = 0; r0 < rows; r0 += per)
+      js.push_back({dst + r0 * dpitch, src + r0 * spitch, width, rows - r0 < per ? rows - r0 : per, dpitch, spitch});
+    dispatch(js);
   }
 
  private:
   struct Job {
     char* d;
     const char* s;
-    size_t n;
+    size_t n, rows, dpitch, spitch;
   };
+  static void work(const Job& j) {
+    for (size_t r = 0; r < j.rows; ++r) memcpy(j.d + r * j.dpitch, j.s + r * j.spitch, j.n);
+  }
+  // the first job runs on the caller, the rest on the pool; returns when all are done
+  void dispatch(const std::vector<Job>& js) {
+    if (js.empty()) return;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      jobs_.assign(js.begin() + 1, js.end());
+      next_ = 0;
+      pending_ = (int)jobs_.size();
+    }
+    if (!jobs_.empty()) cv_work_.notify_all();
+    work(js[0]);
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+  }
   HostCopyPool() {
     int n = 6;
     if (const char* e = getenv("QPSK_HOST_COPY_THREADS")) n = atoi(e);
@@ -259,7 +279,7 @@ class HostCopyPool {
       if (stop_) return;
       const Job j = jobs_[next_++];
       lk.unlock();
-      memcpy(j.d, j.s, j.n);
+      work(j);
       lk.lock();
       if (--pending_ == 0) cv_done_.notify_all();
     }
@@ -277,6 +297,10 @@ class HostCopyPool {
 void host_parallel_copy(void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return;
   HostCopyPool::get().copy((char*)dst, (const char*)src, bytes);
+}
+void host_parallel_copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {
+  if (width == 0 || rows == 0) return;
+  HostCopyPool::get().copy_rows((char*)dst, dpitch, (const char*)src, spitch, width, rows);
 }
 
 }  // namespace qpsk

@@ -967,6 +967,7 @@ struct HostSrc {
   int64_t ld = 0;               // complex samples between consecutive channels
   bool cs16 = false;
   float scale = 1.0f;           // cf32 = (float)int16 * scale
+  bool pageable = false;        // the driver does not know the memory as page-locked: chunks go through h_bounce
 };
 int cs16_to_cf32_launch(const int16_t* d_in, long long ld_in, float scale, float2* d_out, long long ld_out, long long L, int channels,
                         cudaStream_t s);   // stream.cu
@@ -1029,6 +1030,7 @@ struct DemodEngine {
     if (side) cudaStreamDestroy(side);
     if (copy) cudaStreamDestroy(copy);
     if (h_land) cudaFreeHost(h_land);
+    if (h_bounce) cudaFreeHost(h_bounce);
     if (ev_in) cudaEventDestroy(ev_in);
     for (cudaEvent_t e : ev_chunk) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_copy) cudaEventDestroy(e);
@@ -1141,16 +1143,44 @@ struct DemodEngine {
     while (n > 1 && L < (int64_t)n * 8 * kSsBlock) --n;
     return n;
   }
-  // copy (and widen) samples [n0, n0+len) of every channel from the host source into h_in, on stream `st`
+  // copy (and widen) samples [n0, n0+len) of every channel from the host source into h_in, on stream `st`.  Pageable
+  // sources: an asynchronous copy on them blocks the calling thread in the driver's own staging; the row pieces are gathered
+  // into a page-locked mirror of the block by the host copy pool instead (common.cuh) and leave from there.
   int stage_host_chunk(const HostSrc& hs, int64_t n0, int64_t len, int64_t ld, cudaStream_t st) {
+    const size_t esz = hs.cs16 ? 4 : 8;                      // bytes per complex sample on the host
+    const char* src = (const char*)hs.p + (size_t)n0 * esz;
+    size_t spitch = (size_t)hs.ld * esz;
+    if (hs.pageable && h_bounce) {
+      char* mirror = (char*)h_bounce + (size_t)n0 * esz;
+      host_parallel_copy_rows(mirror, spitch, src, spitch, (size_t)len * esz, (size_t)channels);
+      src = mirror;
+    }
     if (!hs.cs16) {
-      QPSK_CUDA_TRY(cudaMemcpy2DAsync(h_in.p + n0, (size_t)ld * 8, (const float2*)hs.p + n0, (size_t)hs.ld * 8, (size_t)len * 8,
-                                      (size_t)channels, cudaMemcpyHostToDevice, st));
+      QPSK_CUDA_TRY(cudaMemcpy2DAsync(h_in.p + n0, (size_t)ld * 8, src, spitch, (size_t)len * 8, (size_t)channels,
+                                      cudaMemcpyHostToDevice, st));
       return QPSK_OK;
     }
-    QPSK_CUDA_TRY(cudaMemcpy2DAsync(h_cs16.p + 2 * n0, (size_t)ld * 4, (const int16_t*)hs.p + 2 * n0, (size_t)hs.ld * 4,
-                                    (size_t)len * 4, (size_t)channels, cudaMemcpyHostToDevice, st));
+    QPSK_CUDA_TRY(cudaMemcpy2DAsync(h_cs16.p + 2 * n0, (size_t)ld * 4, src, spitch, (size_t)len * 4, (size_t)channels,
+                                    cudaMemcpyHostToDevice, st));
     return cs16_to_cf32_launch(h_cs16.p + 2 * n0, ld, hs.scale, h_in.p + n0, ld, len, channels, st);
+  }
+  // page-locked mirror of a pageable host block (up to 512 MiB; larger blocks stay on the driver's pageable path)
+  void* h_bounce = nullptr;
+  size_t h_bounce_bytes = 0;
+  int ensure_bounce(size_t bytes) {
+    if (bytes > ((size_t)512 << 20)) {
+      if (h_bounce) cudaFreeHost(h_bounce);
+      h_bounce = nullptr;
+      h_bounce_bytes = 0;
+      return QPSK_OK;
+    }
+    if (bytes <= h_bounce_bytes) return QPSK_OK;
+    if (h_bounce) cudaFreeHost(h_bounce);
+    h_bounce = nullptr;
+    h_bounce_bytes = 0;
+    QPSK_CUDA_TRY(cudaHostAlloc(&h_bounce, bytes, cudaHostAllocPortable));
+    h_bounce_bytes = bytes;
+    return QPSK_OK;
   }
   int ensure_pipeline(int chunks, bool from_host) {
     if (!side) QPSK_CUDA_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
@@ -1275,6 +1305,7 @@ struct DemodEngine {
     const bool fuse_mf = fused && can_fuse_mf();
     const bool from_host = hs != nullptr && hs->p != nullptr;
     int chunks = (fused && use_fll) ? pipeline_chunks(L) : 1;
+    HostSrc hsrc;
     if (from_host) {
       const int64_t ld = L + (L & 1);
       QPSK_TRY(h_in.ensure((size_t)ld * channels));
@@ -1283,7 +1314,10 @@ struct DemodEngine {
       ldx = ld;
       const int hc = fused ? host_chunks(L, hs->cs16) : 1;
       if (hc > chunks) chunks = hc;
-      if (chunks == 1) QPSK_TRY(stage_host_chunk(*hs, 0, L, ld, s));
+      hsrc = *hs;
+      hsrc.pageable = host_ptr_is_pageable(hs->p);
+      if (hsrc.pageable) QPSK_TRY(ensure_bounce((size_t)channels * (size_t)hs->ld * (hs->cs16 ? 4 : 8)));
+      if (chunks == 1) QPSK_TRY(stage_host_chunk(hsrc, 0, L, ld, s));
     }
     const float2* sym_in = nullptr;                  // what the symbol-stage kernel reads in the single-launch case
     int64_t sym_in_ld = 0;
@@ -1335,22 +1369,18 @@ struct DemodEngine {
       const int64_t step = ((2 * L + 2 * chunks - 2) / (2 * chunks - 1) + kSsBlock - 1) / kSsBlock * kSsBlock;
       QPSK_CUDA_TRY(cudaEventRecord(ev_in, s));
       QPSK_CUDA_TRY(cudaStreamWaitEvent(side, ev_in, 0));     // inputs (and the previous call) are complete
-      if (from_host) {
-        // the PCIe copies run on a stream of their own, all queued up front: chunk t+1 crosses the bus while the FLL (side
-        // stream) works on chunk t and the symbol stage (caller's stream) on chunk t-1.  On the side stream they would
-        // queue behind the FLL launches: copy and FLL would take turns (3.3 ms per step where 1.3 + tail is possible).
-        QPSK_CUDA_TRY(cudaStreamWaitEvent(copy, ev_in, 0));
-        int tc = 0;
-        for (int64_t n0 = 0; n0 < L; n0 += step, ++tc) {
-          const int64_t len = (L - n0 < step) ? (L - n0) : step;
-          QPSK_TRY(stage_host_chunk(*hs, n0, len, mf_ld, copy));
-          QPSK_CUDA_TRY(cudaEventRecord(ev_copy[(size_t)tc], copy));
-        }
-      }
+      // the PCIe copies run on a stream of their own: chunk t+1 crosses the bus while the FLL (side stream) works on chunk t
+      // and the symbol stage (caller's stream) on chunk t-1.  On the side stream they would queue behind the FLL launches:
+      // copy and FLL would take turns (3.3 ms per step where 1.3 + tail is possible).
+      if (from_host) QPSK_CUDA_TRY(cudaStreamWaitEvent(copy, ev_in, 0));
       int t = 0;
       for (int64_t n0 = 0; n0 < L; n0 += step, ++t) {
         const int64_t len = (L - n0 < step) ? (L - n0) : step;
-        if (from_host) QPSK_CUDA_TRY(cudaStreamWaitEvent(side, ev_copy[(size_t)t], 0));
+        if (from_host) {
+          QPSK_TRY(stage_host_chunk(hsrc, n0, len, mf_ld, copy));      // pageable source: the host gathers the chunk first
+          QPSK_CUDA_TRY(cudaEventRecord(ev_copy[(size_t)t], copy));
+          QPSK_CUDA_TRY(cudaStreamWaitEvent(side, ev_copy[(size_t)t], 0));
+        }
         const float2* src = x + n0;
         int64_t lds = ldx;
         if (use_fll) {
