@@ -424,7 +424,18 @@ def main():
             gbs = (8.0 + 8.0 / dec) * n / (tms * 1e-3) / 1e9
             tf = 4.0 * nt / dec * n / (tms * 1e-3) / 1e12
             bound = "hbm" if ((8.0 + 8.0 / dec) / (hbm_peak * 1e9)) >= (4.0 * nt / dec / (fma_peak * 1e12)) else "fma"
-            decimate.append({"taps": nt, "decim": dec, "kernel": f.last_kernel(), "ms": tms, "msamples_s_in": n / (tms * 1e-3) / 1e6,
+            par = None
+            if rank == 0 and not args.no_cpu:
+                # the timed output against the oracle: first 2048 kept outputs (delay line carried from the previous call = the
+                # tail of x; n is a multiple of D, so the kept-output phase is 0) — oracle filter at full rate, every D-th kept
+                import oracle as O
+                wo = 2048
+                seg = torch.cat([x[2 * (n - (nt - 1)):], x[:2 * wo * dec]]).cpu().numpy()
+                want = O.decimate(O.ComplexFIRFilter(t).Filter(seg)[2 * (nt - 1):], dec)
+                got = y[:2 * wo].cpu().numpy()
+                err = float(np.abs(got - want).max() / max(float(np.abs(want).max()), 1e-30))
+                par = {"outputs_checked": wo, "max_abs_err_over_max_abs": err, "tolerance": 1e-5, "ok": bool(err <= 1e-5)}
+            decimate.append({"taps": nt, "decim": dec, "kernel": f.last_kernel(), "parity": par, "ms": tms, "msamples_s_in": n / (tms * 1e-3) / 1e6,
                              "bound": bound, "hbm_gbs": gbs, "fma_tflops": tf,
                              "frac": gbs / hbm_peak if bound == "hbm" else tf / fma_peak,
                              "algorithmic": "8 + 8/D B and 4*taps/D flop per input sample",
@@ -527,7 +538,8 @@ def main():
                     scaling_legs[key + "_saturated"] = bench_chain.run_chain(
                         Q, torch, d, world, rank, stream, use_fll=fll, channels_per_gpu=tot, parity_channels=0,
                         label=f"saturated weak: {tot} channels per GPU", **common)
-        modulator = bench_chain.run_modulator(Q, torch, d, world, rank, stream, steps=k, warmup=3, hbm_peak=hbm_peak)
+        modulator = bench_chain.run_modulator(Q, torch, d, world, rank, stream, steps=k, warmup=3, hbm_peak=hbm_peak,
+                                              parity=cpu_legs)
         chain_e2e = chain_fll_e2e = modulator_e2e = None
         if not args.no_e2e:
             ks = max(1, min(args.steps, 5))

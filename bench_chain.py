@@ -213,7 +213,7 @@ def run_chain(Q, torch, dist, world, rank, stream, steps=3, warmup=3, channels_p
 
 
 def run_modulator(Q, torch, dist, world, rank, stream, steps=3, warmup=3, frames_per_gpu=2048, n_payload=65536,
-                  hbm_peak=6461.8):
+                  hbm_peak=6461.8, parity=False):
     from qpsk_modulator_demodulator_b200 import shard
     fs, rs = 4000, 1000
     F = frames_per_gpu
@@ -251,8 +251,22 @@ def run_modulator(Q, torch, dist, world, rank, stream, steps=3, warmup=3, frames
     samples = world * F * (ff // 2) * steps
     per_gpu_bytes = (8.0 * F * (ff // 2) + F * n_payload * 2.0) * steps   # 8 B written/sample + payload read twice
     gbs = per_gpu_bytes / (ms * 1e-3) / 1e9
+    par = None
+    if parity:
+        # what the last timed step wrote, against the oracle's QPSKModulator.ModulateBytes (fp64 FFT convolution) on the same
+        # payloads: the first and the last frame of the batch; north_star's tolerance 1e-5 * max|y|
+        import oracle as O
+        om = O.QPSKModulator(fs, rs, 0.35, 10, True, TSC)
+        worst = 0.0
+        for fr in (0, F - 1):
+            want = om.ModulateBytes(pay[fr].cpu().numpy().tobytes(), b"START", b"END")
+            got = out[fr, :ff].cpu().numpy()
+            worst = max(worst, float(np.abs(got - want).max() / np.abs(want).max()))
+        par = {"frames_checked": 2, "samples_per_frame": ff // 2, "max_abs_err_over_max_abs": worst, "tolerance": 1e-5,
+               "ok": bool(worst <= 1e-5)}
     del out
     return {
+        "parity": par,
         "workload": f"{world * F} frames ({F}/GPU) x {n_payload} B payload ({world * F * n_payload / 2**30:.3f} GiB), "
                     f"START|payload|END + 64-bit TSC, differential, sps 4, span 10 (41 taps), alpha .35; "
                     f"{F * (ff // 2) * 8 / 1e9:.1f} GB written per GPU per step",
