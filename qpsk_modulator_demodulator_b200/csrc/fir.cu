@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(NT + 32, 2)
   float2* ys_base = xs_base + (size_t)a.stages * a.stage_elems;     // one buffer of WS outputs per warp
   const int spw = (WS + a.G) / 2 + 1;                                 // S values per warp (odd or even: 8-byte accesses only)
   float2* sp_base = ys_base + T;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sp_base + (size_t)NW * spw + ((NW * spw) & 1));
+  uint64_t* full = reinterpret_cast<uint64_t*>(sp_base + (size_t)NW * spw);   // float2 slots: 8-byte aligned as mbarriers need
   uint64_t* empty = full + a.stages;
 
   const int tid = threadIdx.x;
@@ -1597,7 +1597,7 @@ int launch_split2(FirArgs a, const TapsSplit& t, int channels, cudaStream_t s, c
   a.stage_elems = a.E_load + 2;
   const size_t stage_bytes = (size_t)a.stage_elems * 8;
   const int spw = (WS2 + a.G) / 2 + 1;
-  const size_t fixed = (size_t)T2 * 8 + (size_t)(NW2 * spw + ((NW2 * spw) & 1)) * 8;
+  const size_t fixed = (size_t)T2 * 8 + (size_t)NW2 * spw * 8;
   if (fixed + 128 + 2 * stage_bytes > (size_t)kSmemBudget) return QPSK_ERR_UNSUPPORTED;
   int stages = (int)(((size_t)kSmemBudget - fixed - 128) / stage_bytes);
   if (stages > 4) stages = 4;
