@@ -485,5 +485,16 @@ def run_modulator_e2e(Q, torch, dist, world, rank, steps=3, frames_per_gpu=256, 
            "value": world * F * (ff // 2) / dt / 1e6, "unit": "Msamples/s (output)", "ms_per_step": 1e3 * dt,
            "step_ms": [round(1e3 * v, 2) for v in ts], "h2d_bytes_per_step": F * n_payload, "d2h_bytes_per_step": F * ff * 4,
            "d2h_gbs": F * ff * 4 / dt / 1e9, "bound": "pcie (device-to-host)"}
+    if world == 1:
+        # the same call into a pageable output block (a C# float[] that was not registered): one timed step
+        outq = np.empty(F * ff, np.float32)
+        outq.fill(0.0)                                          # every page resident before the timing (np.zeros maps lazily)
+        mod.ModulateFrames(pay[:8], b"START", b"END", out_ptr=outq.ctypes.data, out_stride_floats=ff)
+        t0 = time.perf_counter()
+        mod.ModulateFrames(pay, b"START", b"END", out_ptr=outq.ctypes.data, out_stride_floats=ff)
+        tq = time.perf_counter() - t0
+        res["pageable"] = {"value": F * (ff // 2) / tq / 1e6, "unit": "Msamples/s (output)", "steps": 1,
+                           "equal_to_pinned_run": bool(np.array_equal(outq, outp.array[: F * ff]))}
+        del outq
     outp.free()
     return res

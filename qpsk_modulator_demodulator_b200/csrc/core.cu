@@ -188,6 +188,11 @@ bool blank_or_null(const char* s) {
 
 // ---- host copy pool -------------------------------------------------------------------------------------------------
 bool host_ptr_is_pageable(const void* p) {
+  static const bool off = [] {
+    const char* e = getenv("QPSK_HOST_BOUNCE");          // 0: leave pageable memory to the driver's own staging (A/B runs)
+    return e && e[0] == '0';
+  }();
+  if (off) return false;
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
     cudaGetLastError();                                  // older runtimes report unknown host memory as an error

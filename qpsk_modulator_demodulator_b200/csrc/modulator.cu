@@ -579,10 +579,25 @@ struct qpsk_mod {
   cudaEvent_t ev_k[kSlots] = {}, ev_d2h[kSlots] = {};
   DevBuf<uint8_t> d_pay[kSlots];
   DevBuf<float2> d_grp[kSlots];
+  // page-locked landing slots for a pageable output block (common.cuh: host copy pool), allocated on first use
+  float2* h_grp[kSlots] = {};
+  size_t h_grp_elems = 0;
+  int landing(size_t elems) {
+    if (elems <= h_grp_elems) return QPSK_OK;
+    for (int i = 0; i < kSlots; ++i) {
+      if (h_grp[i]) cudaFreeHost(h_grp[i]);
+      h_grp[i] = nullptr;
+    }
+    h_grp_elems = 0;
+    for (int i = 0; i < kSlots; ++i) QPSK_CUDA_TRY(cudaHostAlloc((void**)&h_grp[i], elems * sizeof(float2), cudaHostAllocPortable));
+    h_grp_elems = elems;
+    return QPSK_OK;
+  }
   ~qpsk_mod() {
     for (int i = 0; i < kSlots; ++i) {
       if (ev_k[i]) cudaEventDestroy(ev_k[i]);
       if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+      if (h_grp[i]) cudaFreeHost(h_grp[i]);
     }
     if (s_out) cudaStreamDestroy(s_out);
   }
@@ -767,6 +782,19 @@ int qpsk_mod_modulate_frames(qpsk_mod* m, const uint8_t* payloads, int64_t n_pay
     QPSK_TRY(m->d_pay[b].ensure((size_t)(G * (n_payload > 0 ? n_payload : 1))));
   }
   cudaStream_t s = e.stream;
+  // a pageable output block: an asynchronous copy into it blocks the calling thread, so the groups land in page-locked slots
+  // and the host copy pool moves them on while the next groups are shaped and copied
+  const bool bounce = host_ptr_is_pageable(iq_out);
+  if (bounce) QPSK_TRY(m->landing((size_t)(G * stride_c)));
+  auto drain = [&](int gi) -> int {
+    const int b = gi % qpsk_mod::kSlots;
+    const int64_t f0 = (int64_t)gi * G;
+    const int nf = (int)((frames - f0 < G) ? (frames - f0) : G);
+    QPSK_CUDA_TRY(cudaEventSynchronize(m->ev_d2h[b]));
+    host_parallel_copy_rows(iq_out + (size_t)f0 * out_stride_floats, (size_t)out_stride_floats * 4, m->h_grp[b], (size_t)stride_c * 8,
+                            (size_t)fc * 8, (size_t)nf);
+    return QPSK_OK;
+  };
   int g = 0;
   for (int64_t f0 = 0; f0 < frames; f0 += G, ++g) {
     const int b = g % qpsk_mod::kSlots;
@@ -779,10 +807,16 @@ int qpsk_mod_modulate_frames(qpsk_mod* m, const uint8_t* payloads, int64_t n_pay
                                &ff2, s));
     QPSK_CUDA_TRY(cudaEventRecord(m->ev_k[b], s));
     QPSK_CUDA_TRY(cudaStreamWaitEvent(m->s_out, m->ev_k[b], 0));
-    QPSK_CUDA_TRY(cudaMemcpy2DAsync(iq_out + (size_t)f0 * out_stride_floats, (size_t)out_stride_floats * 4, m->d_grp[b].p,
-                                    (size_t)stride_c * 8, (size_t)fc * 8, (size_t)nf, cudaMemcpyDeviceToHost, m->s_out));
+    if (bounce) {
+      QPSK_CUDA_TRY(cudaMemcpyAsync(m->h_grp[b], m->d_grp[b].p, (size_t)nf * stride_c * 8, cudaMemcpyDeviceToHost, m->s_out));
+    } else {
+      QPSK_CUDA_TRY(cudaMemcpy2DAsync(iq_out + (size_t)f0 * out_stride_floats, (size_t)out_stride_floats * 4, m->d_grp[b].p,
+                                      (size_t)stride_c * 8, (size_t)fc * 8, (size_t)nf, cudaMemcpyDeviceToHost, m->s_out));
+    }
     QPSK_CUDA_TRY(cudaEventRecord(m->ev_d2h[b], m->s_out));
+    if (bounce && g >= 1) QPSK_TRY(drain(g - 1));             // group g - 1 leaves its slot two iterations before it is reused
   }
+  if (bounce && g >= 1) QPSK_TRY(drain(g - 1));
   QPSK_CUDA_TRY(cudaStreamSynchronize(m->s_out));
   QPSK_CUDA_TRY(cudaStreamSynchronize(s));
   return QPSK_OK;
