@@ -67,3 +67,45 @@ def test_concurrent_handles_match_oracle(gpu, orc):
     for x in th:
         x.join()
     assert not errors, errors[:5]
+
+
+def test_concurrent_pageable_streams_share_the_host_copy_pool(gpu, orc):
+    """Long streams in PAGEABLE numpy arrays from several threads at once: every call goes through its handle's page-locked
+    staging slots, filled and drained by the one host copy pool of the process (core.cu HostCopyPool) — the calls serialise on
+    the pool, never mix their chunks, and give the one-shot result of the same kernel."""
+    n_threads = 3
+    L = 2 * (1 << 21) + 4567                                      # three pipeline chunks
+    rng = np.random.default_rng(5)
+    taps = [orc.real_taps_to_iq(orc.RRCFilter.generateCoefficents(10, 0.35, (2 + t) * 1000, 1000)) for t in range(n_threads)]
+    xs = [rng.standard_normal(2 * L).astype(np.float32) for _ in range(n_threads)]
+    got = [None] * n_threads
+    errors = []
+    start = threading.Barrier(n_threads)
+
+    def worker(t):
+        try:
+            f = gpu.ComplexFIRFilter(taps[t])
+            f.set_mode(gpu.FIR_FMA)
+            start.wait()
+            got[t] = f.Filter(xs[t])
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errors, errors
+    import torch
+    for t in range(n_threads):
+        dx = torch.from_numpy(xs[t]).cuda()
+        dy = torch.empty_like(dx)
+        f = gpu.ComplexFIRFilter(taps[t])
+        f.set_mode(gpu.FIR_FMA)
+        f.filter_dev(dx.data_ptr(), dy.data_ptr(), 2 * L)         # one launch over the whole stream, device resident
+        torch.cuda.synchronize()
+        assert np.array_equal(dy.cpu().numpy().view(np.uint32), got[t].view(np.uint32)), t
+        # and a window against the oracle
+        w = orc.ComplexFIRFilter(taps[t]).Filter(xs[t][: 2 * 50000])
+        assert np.abs(got[t][: 2 * 50000] - w).max() <= 1e-5 * np.abs(w).max()
