@@ -272,13 +272,16 @@ __global__ void pack_bits_kernel(const uint8_t* __restrict__ bits, long long bit
   }
 }
 
-// one warp per channel
-__global__ void __launch_bounds__(128)
+// one CTA of four warps per channel (one warp per channel left every lane a chain of ~70 dependent load batches on an
+// 8400-bit burst: 15 us for 2048 channels, against ~5 for the bytes it reads)
+constexpr int kBerThreads = 128;
+__global__ void __launch_bounds__(kBerThreads)
     ber_kernel(const uint8_t* __restrict__ rx, long long rx_stride, const long long* __restrict__ n_rx,
                const uint8_t* __restrict__ ref, long long ref_stride, long long n_ref, int C, uint32_t* counters) {
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ unsigned warp_err[kBerThreads / 32];
+  const int c = blockIdx.x;
   if (c >= C) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x;                       // position inside the channel's CTA
   const uint8_t* r = rx + (long long)c * rx_stride;
   const uint8_t* f = ref + (long long)c * ref_stride;
   const long long have = n_rx[c];
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(128)
     const uint32_t* fw = reinterpret_cast<const uint32_t*>(fb - foff);
     const int sh = 8 * foff;
 #pragma unroll 4
-    for (long long i = lane; i < nw; i += 32) {
+    for (long long i = lane; i < nw; i += kBerThreads) {
       const uint32_t a = rw[i];
       const uint32_t lo = fw[i];
       const uint32_t hi = sh ? fw[i + 1] : 0u;               // holds bytes of this word whenever sh != 0
@@ -305,11 +308,16 @@ __global__ void __launch_bounds__(128)
       err += (unsigned)__popc(__vcmpne4(a, b)) >> 3;
     }
   }
-  for (long long i = head + 4 * nw + lane; i < n; i += 32) err += (r[i] != f[i]) ? 1u : 0u;
+  for (long long i = head + 4 * nw + lane; i < n; i += kBerThreads) err += (r[i] != f[i]) ? 1u : 0u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+  if ((lane & 31) == 0) warp_err[lane >> 5] = err;
+  __syncthreads();
   if (lane == 0) {
-    counters[2 * c] = err + (uint32_t)(n_ref - n);   // bits that never arrived count as errors
+    unsigned tot = 0;
+#pragma unroll
+    for (int w = 0; w < kBerThreads / 32; ++w) tot += warp_err[w];
+    counters[2 * c] = tot + (uint32_t)(n_ref - n);   // bits that never arrived count as errors
     counters[2 * c + 1] = (uint32_t)n_ref;
   }
 }
@@ -499,7 +507,7 @@ int qpsk_ber_count_dev(const uint8_t* d_rx_bits, int64_t rx_stride, const int64_
   if (!d_rx_bits || !d_n_rx || !d_counters) return QPSK_ERR_NULL;
   if (n_ref > 0 && !d_ref_bits) return QPSK_ERR_NULL;
   QPSK_TRY(ensure_device());
-  ber_kernel<<<(channels + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_rx_bits, rx_stride, (const long long*)d_n_rx, d_ref_bits,
+  ber_kernel<<<channels, kBerThreads, 0, (cudaStream_t)stream>>>(d_rx_bits, rx_stride, (const long long*)d_n_rx, d_ref_bits,
                                                                   ref_stride, n_ref, channels, d_counters);
   QPSK_LAUNCH_CHECK();
   return QPSK_OK;
